@@ -1,0 +1,113 @@
+/*
+ * pgr_b200.h — C ABI of libpgr_b200.so: the B200 (sm_100a) implementation of pgr-tk's SHIMMER indexing hot path.
+ *
+ * Each entry point names the reference interface (GeneDx/pgr-tk, paths relative to the reference root) it replaces.
+ * Conventions (modelled on the reference's only FFI precedent, libagc: pgr-db/build.rs:17-55, pgr-db/src/agc_io.rs):
+ *   - opaque handles, int return codes (0 = ok, <0 = error; pgr_b200_last_error() gives the thread-local message),
+ *   - every output buffer is allocated by the library and released with pgr_b200_free(),
+ *   - inputs are borrowed for the duration of the call only,
+ *   - PODs are #[repr(C)]-compatible.
+ * There is NO CPU fallback: every compute entry point fails with PGR_E_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef PGR_B200_H
+#define PGR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGR_OK 0
+#define PGR_E_ARG (-1)        /* NULL / inconsistent argument                                              */
+#define PGR_E_SPEC (-2)       /* violates assert!(k <= 56), assert!(w <= 128), assert!(r > 0 && r < 13)    */
+                              /* (shmmrutils.rs:443-445, :575-576)                                         */
+#define PGR_E_NO_DEVICE (-3)  /* no CUDA device / driver: the library never computes on the CPU            */
+#define PGR_E_CUDA (-4)       /* a CUDA runtime call failed                                                */
+#define PGR_E_IO (-5)         /* file could not be read / written / parsed                                 */
+#define PGR_E_LIMIT (-6)      /* sequence longer than 2^31-1 (MM128 pos is 31 bits, shmmrutils.rs:261-263) */
+#define PGR_E_ASSERT (-7)     /* a reference assert would have fired (e.g. aln.rs:24)                      */
+
+/* shmmrutils.rs:225-229 — x = hash<<8 | span(k), y = rid<<32 | pos<<1 | strand */
+typedef struct { uint64_t x, y; } pgr_mm128;
+/* shmmrutils.rs:20-27 */
+typedef struct { uint32_t w, k, r, min_span, sketch; } pgr_shmmr_spec;
+/* seq_db.rs:75 FragmentSignature (frg_id, seq_id, bgn, end, orientation); the 17-byte packed form exists only on disk */
+typedef struct { uint32_t frg_id, sid, bgn, end; uint8_t ori; uint8_t pad_[3]; } pgr_frag_sig;
+/* seq_db.rs:1198 FragmentHit minus its Vec: ((h0,h1),(pos0,pos1,orientation)) */
+typedef struct { uint64_t h0, h1; uint32_t bgn, end; uint8_t ori; uint8_t pad_[7]; } pgr_query_pair;
+/* aln.rs:10 HitPair ((q_bgn,q_end,q_ori),(t_bgn,t_end,t_ori)) */
+typedef struct { uint32_t qb, qe, tb, te; uint8_t qo, to; uint8_t pad_[2]; } pgr_hit_pair;
+/* graph_utils.rs:47-52 AdjPair (sid, ShmmrGraphNode a, ShmmrGraphNode b) */
+typedef struct { uint32_t sid; uint8_t ori0, ori1, pad_[2]; uint64_t a0, a1, b0, b1; } pgr_adj_pair;
+
+/* query_fragment_to_hps arguments (aln.rs:147-158); Option<u32> is encoded as a negative value = None */
+typedef struct {
+    float penalty;
+    int64_t max_count, max_count_query, max_count_target, max_aln_span, max_gap;
+    int32_t oriented;
+} pgr_query_params;
+
+/* flat result of a batch of query_fragment_to_hps calls (aln.rs:145 TargetHitPairLists per query).
+ * query q owns targets [q_target_off[q], q_target_off[q+1]); target t (ascending sid within a query) owns chains
+ * [target_chain_off[t], target_chain_off[t+1]); chain c owns hits [chain_hit_off[c], chain_hit_off[c+1]). */
+typedef struct {
+    size_t n_queries, n_targets, n_chains, n_hits;
+    uint64_t *q_target_off;
+    uint32_t *target_sid;
+    uint64_t *target_chain_off;
+    float *chain_score;
+    uint64_t *chain_hit_off;
+    pgr_hit_pair *hits;
+} pgr_query_result;
+
+typedef struct pgr_b200_ctx pgr_b200_ctx;      /* one per (thread, device): streams, device arenas            */
+typedef struct pgr_b200_index pgr_b200_index;  /* CompactSeqDB.frag_map as a device-resident CSR (seq_db.rs:95-100) */
+
+/* ---- library / device ------------------------------------------------------------------------------------ */
+int pgr_b200_device_count(void);
+const char *pgr_b200_last_error(void);
+void pgr_b200_free(void *p);
+/* pinned host staging for callers that want the H2D copy at PCIe rate (bench.py e2e leg) */
+void *pgr_b200_host_alloc(size_t bytes);
+void pgr_b200_host_free(void *p);
+
+/* ---- sequence_to_shmmrs ---------------------------------------------------------------------------------- */
+/* replaces shmmrutils::sequence_to_shmmrs(rid, &seq, &spec, padding) -> Vec<MM128>   (shmmrutils.rs:657-669);
+ * re-entrant (the reference calls it from rayon workers, seq_db.rs:461, pgr-query.rs:135). */
+int pgr_b200_sequence_to_shmmrs(uint32_t rid, const uint8_t *seq, size_t len, const pgr_shmmr_spec *spec, int padding,
+                                pgr_mm128 **out, size_t *n_out);
+/* replaces CompactSeqDB::get_shmmrs_from_seqs (seq_db.rs:456-469): one call per batch, HOST buffers in and out.
+ * offsets has n+1 entries (caller-allocated); *out is library-allocated. */
+int pgr_b200_shmmrs_batch(size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens,
+                          const pgr_shmmr_spec *spec, int padding, pgr_mm128 **out, size_t *offsets);
+
+/* ---- explicit device context (device-resident pipeline; what bench.py times as `value`) ------------------ */
+pgr_b200_ctx *pgr_b200_ctx_new(int device);
+void pgr_b200_ctx_free(pgr_b200_ctx *ctx);
+/* use an existing CUDA stream (cudaStream_t as void*) for all work of this ctx; NULL = the ctx's own stream */
+int pgr_b200_ctx_set_stream(pgr_b200_ctx *ctx, void *cuda_stream);
+/* copy a batch of host sequences into the ctx's device sequence store (replaces what is there) */
+int pgr_b200_ctx_upload(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens);
+/* adopt sequences that already live in device memory: base + offs[i] (each offs[i] 32-byte aligned, with at least
+ * 16 KiB of readable slack before offs[0] and after the last sequence) */
+int pgr_b200_ctx_set_device_seqs(pgr_b200_ctx *ctx, const uint8_t *dev_base, size_t n, const uint32_t *rids,
+                                 const uint64_t *offs, const uint64_t *lens);
+/* run sequence_to_shmmrs over the store; results stay on the device. n_shmmrs = total count. Asynchronous w.r.t. the
+ * host except for small control read-backs. */
+int pgr_b200_ctx_shmmrs(pgr_b200_ctx *ctx, const pgr_shmmr_spec *spec, int padding, size_t *n_shmmrs);
+/* device pointers of the last pgr_b200_ctx_shmmrs result: MM128[n_shmmrs] and uint64 offsets[n+1] */
+int pgr_b200_ctx_shmmrs_device(pgr_b200_ctx *ctx, const pgr_mm128 **d_mm, const uint64_t **d_offsets);
+/* copy the last result to the host (library-allocated *out; offsets caller-allocated, n+1) */
+int pgr_b200_ctx_shmmrs_download(pgr_b200_ctx *ctx, pgr_mm128 **out, size_t *offsets);
+/* per-stage device times (ms, CUDA events) of the last ctx call; names is a static NULL-terminated array */
+int pgr_b200_ctx_timings(pgr_b200_ctx *ctx, const char *const **names, const float **ms, size_t *n);
+/* counters of the last shmmrs call: [0] kernel launches, [1] level-0 minimizers, [2] sequences replayed sequentially,
+ * [3] arena retries */
+int pgr_b200_ctx_counters(pgr_b200_ctx *ctx, uint64_t out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

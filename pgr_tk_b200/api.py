@@ -1,0 +1,217 @@
+"""ctypes binding of libpgr_b200.so (C ABI: include/pgr_b200.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libpgr_b200.so")
+
+MM128 = np.dtype([("x", "<u8"), ("y", "<u8")])
+SIG = np.dtype([("frg_id", "<u4"), ("sid", "<u4"), ("bgn", "<u4"), ("end", "<u4"), ("ori", "u1"), ("pad", "u1", 3)])
+QPAIR = np.dtype([("h0", "<u8"), ("h1", "<u8"), ("bgn", "<u4"), ("end", "<u4"), ("ori", "u1"), ("pad", "u1", 7)])
+HITPAIR = np.dtype([("qb", "<u4"), ("qe", "<u4"), ("tb", "<u4"), ("te", "<u4"), ("qo", "u1"), ("to", "u1"), ("pad", "u1", 2)])
+ADJ = np.dtype([("sid", "<u4"), ("ori0", "u1"), ("ori1", "u1"), ("pad", "u1", 2),
+                ("a0", "<u8"), ("a1", "<u8"), ("b0", "<u8"), ("b1", "<u8")])
+
+
+class PgrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pgr_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ShmmrSpec(C.Structure):
+    """shmmrutils.rs:20-27"""
+    _fields_ = [("w", C.c_uint32), ("k", C.c_uint32), ("r", C.c_uint32), ("min_span", C.c_uint32), ("sketch", C.c_uint32)]
+
+    def __init__(self, w=80, k=56, r=4, min_span=64, sketch=False):
+        super().__init__(w, k, r, min_span, 1 if sketch else 0)
+
+
+def library_path():
+    return _LIB
+
+
+def build_library(force=False):
+    """compile libpgr_b200.so in-tree (nvcc, sm_100a)"""
+    csrc = os.path.join(_HERE, "csrc")
+    if force and os.path.exists(_LIB):
+        os.remove(_LIB)
+    subprocess.check_call(["make", "-C", csrc, "-s"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            raise PgrError(-3, "libpgr_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(_LIB)
+        vp, sz, u32, u64 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64
+        P = C.POINTER
+        L.pgr_b200_device_count.restype = C.c_int
+        L.pgr_b200_last_error.restype = C.c_char_p
+        L.pgr_b200_free.argtypes = [vp]
+        L.pgr_b200_host_alloc.restype = vp
+        L.pgr_b200_host_alloc.argtypes = [sz]
+        L.pgr_b200_host_free.argtypes = [vp]
+        L.pgr_b200_sequence_to_shmmrs.argtypes = [u32, vp, sz, P(ShmmrSpec), C.c_int, P(vp), P(sz)]
+        L.pgr_b200_shmmrs_batch.argtypes = [sz, vp, vp, vp, P(ShmmrSpec), C.c_int, P(vp), vp]
+        L.pgr_b200_ctx_new.restype = vp
+        L.pgr_b200_ctx_new.argtypes = [C.c_int]
+        L.pgr_b200_ctx_free.argtypes = [vp]
+        L.pgr_b200_ctx_set_stream.argtypes = [vp, vp]
+        L.pgr_b200_ctx_upload.argtypes = [vp, sz, vp, vp, vp]
+        L.pgr_b200_ctx_set_device_seqs.argtypes = [vp, vp, sz, vp, vp, vp]
+        L.pgr_b200_ctx_shmmrs.argtypes = [vp, P(ShmmrSpec), C.c_int, P(sz)]
+        L.pgr_b200_ctx_shmmrs_device.argtypes = [vp, P(vp), P(vp)]
+        L.pgr_b200_ctx_shmmrs_download.argtypes = [vp, P(vp), vp]
+        L.pgr_b200_ctx_timings.argtypes = [vp, P(P(C.c_char_p)), P(P(C.c_float)), P(sz)]
+        L.pgr_b200_ctx_counters.argtypes = [vp, P(u64 * 8)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PgrError(rc, lib().pgr_b200_last_error().decode(errors="replace"))
+
+
+def device_count():
+    return lib().pgr_b200_device_count()
+
+
+def _bytes(seq):
+    if isinstance(seq, np.ndarray):
+        return np.ascontiguousarray(seq, dtype=np.uint8)
+    return np.frombuffer(bytes(seq), dtype=np.uint8)
+
+
+def _take(ptr, n, dtype):
+    dtype = np.dtype(dtype)
+    if n:
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=n).copy()
+    else:
+        arr = np.zeros(0, dtype=dtype)
+    if ptr.value:
+        lib().pgr_b200_free(ptr)
+    return arr
+
+
+def _seq_arrays(seqs):
+    arrs = [_bytes(s) for s in seqs]
+    n = len(arrs)
+    ptrs = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in arrs])
+    lens = (C.c_size_t * max(1, n))(*[a.size for a in arrs])
+    return arrs, ptrs, lens
+
+
+def sequence_to_shmmrs(rid, seq, spec, padding=False):
+    """shmmrutils::sequence_to_shmmrs(rid, &seq, &spec, padding) -> Vec<MM128>  (shmmrutils.rs:657-669)"""
+    a = _bytes(seq)
+    out, n = C.c_void_p(), C.c_size_t()
+    _check(lib().pgr_b200_sequence_to_shmmrs(rid, a.ctypes.data, a.size, C.byref(spec), int(padding), C.byref(out), C.byref(n)))
+    return _take(out, n.value, MM128)
+
+
+def get_shmmrs_from_seqs(rids, seqs, spec, padding=False):
+    """CompactSeqDB::get_shmmrs_from_seqs (seq_db.rs:456-469) -> (MM128[total], offsets[n+1])"""
+    arrs, ptrs, lens = _seq_arrays(seqs)
+    n = len(arrs)
+    r = np.ascontiguousarray(rids, dtype=np.uint32)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    out = C.c_void_p()
+    _check(lib().pgr_b200_shmmrs_batch(n, r.ctypes.data, ptrs, lens, C.byref(spec), int(padding), C.byref(out), offs.ctypes.data))
+    return _take(out, int(offs[n]), MM128), offs
+
+
+class HostBuffer:
+    """pinned host memory (pgr_b200_host_alloc) exposed as a numpy uint8 array"""
+
+    def __init__(self, nbytes):
+        self.ptr = lib().pgr_b200_host_alloc(nbytes)
+        if not self.ptr:
+            _check(-4)
+        self.nbytes = nbytes
+        self.array = np.frombuffer((C.c_uint8 * nbytes).from_address(self.ptr), dtype=np.uint8)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().pgr_b200_host_free(self.ptr)
+            self.ptr = None
+
+
+def host_alloc(nbytes):
+    return HostBuffer(nbytes)
+
+
+class Ctx:
+    """explicit device context (one per device / thread)"""
+
+    def __init__(self, device=0):
+        self.h = lib().pgr_b200_ctx_new(device)
+        if not self.h:
+            _check(-3)
+        self.n_seq = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pgr_b200_ctx_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream):
+        _check(lib().pgr_b200_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def upload(self, seqs, rids=None):
+        arrs, ptrs, lens = _seq_arrays(seqs)
+        n = len(arrs)
+        r = np.ascontiguousarray(rids if rids is not None else np.arange(n), dtype=np.uint32)
+        _check(lib().pgr_b200_ctx_upload(self.h, n, r.ctypes.data, ptrs, lens))
+        self.n_seq = n
+
+    def upload_ptrs(self, ptrs, lens, rids=None):
+        """upload from raw host pointers (e.g. slices of a pinned HostBuffer)"""
+        n = len(ptrs)
+        p = (C.c_void_p * max(1, n))(*ptrs)
+        l = (C.c_size_t * max(1, n))(*lens)
+        r = np.ascontiguousarray(rids if rids is not None else np.arange(n), dtype=np.uint32)
+        _check(lib().pgr_b200_ctx_upload(self.h, n, r.ctypes.data, p, l))
+        self.n_seq = n
+
+    def set_device_seqs(self, dev_base, offs, lens, rids=None):
+        n = len(offs)
+        o = np.ascontiguousarray(offs, dtype=np.uint64)
+        l = np.ascontiguousarray(lens, dtype=np.uint64)
+        r = np.ascontiguousarray(rids if rids is not None else np.arange(n), dtype=np.uint32)
+        _check(lib().pgr_b200_ctx_set_device_seqs(self.h, C.c_void_p(dev_base), n, r.ctypes.data, o.ctypes.data, l.ctypes.data))
+        self.n_seq = n
+
+    def shmmrs(self, spec, padding=False):
+        n = C.c_size_t()
+        _check(lib().pgr_b200_ctx_shmmrs(self.h, C.byref(spec), int(padding), C.byref(n)))
+        return n.value
+
+    def shmmrs_download(self):
+        offs = np.zeros(self.n_seq + 1, dtype=np.uint64)
+        out = C.c_void_p()
+        _check(lib().pgr_b200_ctx_shmmrs_download(self.h, C.byref(out), offs.ctypes.data))
+        return _take(out, int(offs[self.n_seq]), MM128), offs
+
+    def timings(self):
+        names, ms, n = C.POINTER(C.c_char_p)(), C.POINTER(C.c_float)(), C.c_size_t()
+        _check(lib().pgr_b200_ctx_timings(self.h, C.byref(names), C.byref(ms), C.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+    def counters(self):
+        out = (C.c_uint64 * 8)()
+        _check(lib().pgr_b200_ctx_counters(self.h, C.byref(out)))
+        return list(out)

@@ -1,0 +1,48 @@
+// common.cuh — shared device/host helpers of libpgr_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/pgr_b200.h"
+
+namespace pgr {
+
+// thread-local last error (pgr_b200_last_error)
+void set_error(const char *fmt, ...);
+const char *get_error();
+
+#define PGR_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            ::pgr::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return PGR_E_CUDA;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+// shmmrutils.rs:271-280 (Thomas Wang 64-bit mix).  Written with multiplies by constants so that ptxas maps the
+// shift-adds to IMAD.WIDE on the FMA pipe and leaves the xor-shifts on the ALU pipe.
+__host__ __device__ __forceinline__ uint64_t u64hash(uint64_t key) {
+    key = key * 0x1FFFFFull - 1ull;   // (!key) + (key << 21)
+    key ^= key >> 24;
+    key *= 265ull;                    // (key + (key << 3)) + (key << 8)
+    key ^= key >> 14;
+    key *= 21ull;                     // (key + (key << 2)) + (key << 4)
+    key ^= key >> 28;
+    key *= 0x80000001ull;             // key + (key << 31)
+    return key;
+}
+
+constexpr uint64_t HASH_XOR = 0xAD12CF59ull;  // shmmrutils.rs:491
+
+// device-side mirror of pgr_shmmr_spec plus derived constants
+struct SpecDev {
+    uint32_t w, k, r, min_span, sketch;
+};
+
+template <class T>
+__host__ __device__ __forceinline__ T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+}  // namespace pgr

@@ -1,0 +1,680 @@
+// ctx.cu — device context, sequence store and the sequence_to_shmmrs pipeline (host orchestration).
+#include "ctx.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "shmmr_kernels.cuh"
+
+namespace pgr {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+int StageTimer::begin(const char *name, cudaStream_t st) {
+    if (used == ev0.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ev0.push_back(a); ev1.push_back(b); names.push_back(name); ms.push_back(0.f);
+    }
+    names[used] = name;
+    cudaEventRecord(ev0[used], st);
+    return (int)used++;
+}
+void StageTimer::end(int slot, cudaStream_t st) { cudaEventRecord(ev1[slot], st); }
+void StageTimer::collect() {
+    for (size_t i = 0; i < used; i++) {
+        cudaEventSynchronize(ev1[i]);
+        cudaEventElapsedTime(&ms[i], ev0[i], ev1[i]);
+    }
+    names_z.assign(names.begin(), names.begin() + used);
+    names_z.push_back(nullptr);
+}
+void StageTimer::destroy() {
+    for (auto e : ev0) cudaEventDestroy(e);
+    for (auto e : ev1) cudaEventDestroy(e);
+    ev0.clear(); ev1.clear();
+}
+
+int check_spec(const pgr_shmmr_spec *s) {
+    if (!s) { set_error("spec is NULL"); return PGR_E_ARG; }
+    if (s->k == 0 || s->k > 56) { set_error("assert!(k <= 56) violated (k=%u)", s->k); return PGR_E_SPEC; }
+    if (!(s->r > 0 && s->r < 13)) { set_error("assert!(r > 0 && r < 13) violated (r=%u)", s->r); return PGR_E_SPEC; }
+    if (!s->sketch && (s->w == 0 || s->w > 128)) { set_error("assert!(w <= 128) violated (w=%u)", s->w); return PGR_E_SPEC; }
+    return PGR_OK;
+}
+
+}  // namespace pgr
+
+using namespace pgr;
+
+int pgr_b200_ctx::ensure_stage(size_t bytes) {
+    if (bytes <= h_stage_cap) return PGR_OK;
+    if (h_stage) cudaFreeHost(h_stage);
+    h_stage = nullptr; h_stage_cap = 0;
+    PGR_CUDA(cudaMallocHost(&h_stage, bytes));
+    h_stage_cap = bytes;
+    return PGR_OK;
+}
+int pgr_b200_ctx::ensure_ctl(size_t bytes) {
+    if (bytes <= h_ctl_cap) return PGR_OK;
+    if (h_ctl) cudaFreeHost(h_ctl);
+    h_ctl = nullptr; h_ctl_cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    PGR_CUDA(cudaMallocHost(&h_ctl, want));
+    h_ctl_cap = want;
+    return PGR_OK;
+}
+
+#define PGR_TRY(x) do { int rc__ = (x); if (rc__ != PGR_OK) return rc__; } while (0)
+
+extern "C" {
+
+int pgr_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+const char *pgr_b200_last_error(void) { return get_error(); }
+void pgr_b200_free(void *p) { free(p); }
+void *pgr_b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_error("cudaMallocHost(%zu) failed", bytes); cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pgr_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+pgr_b200_ctx *pgr_b200_ctx_new(int device) {
+    int n = pgr_b200_device_count();
+    if (n <= 0) { set_error("no CUDA device available: libpgr_b200 has no CPU fallback"); return nullptr; }
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return nullptr; }
+    if (prop.major < 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return nullptr; }
+    pgr_b200_ctx *ctx = new pgr_b200_ctx();
+    ctx->device = device;
+    ctx->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete ctx; return nullptr; }
+    ctx->stream = ctx->own_stream;
+    return ctx;
+}
+
+void pgr_b200_ctx_free(pgr_b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    pgr::DevBuf *bufs[] = {&ctx->seq_store, &ctx->d_off, &ctx->d_len, &ctx->d_rid, &ctx->tile_prefix, &ctx->cta_tile, &ctx->arena,
+                           &ctx->chunk_count, &ctx->seq_count, &ctx->seq_flag, &ctx->replay_list, &ctx->replay_count,
+                           &ctx->chunk_prefix, &ctx->seq_fast, &ctx->seq_dst, &ctx->bufA, &ctx->bufB, &ctx->flags,
+                           &ctx->block_sum, &ctx->block_prefix, &ctx->off_a, &ctx->off_b, &ctx->fix_mm, &ctx->fix_off};
+    for (auto b : bufs) b->release();
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    ctx->timer.destroy();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int pgr_b200_ctx_set_stream(pgr_b200_ctx *ctx, void *cuda_stream) {
+    if (!ctx) { set_error("ctx is NULL"); return PGR_E_ARG; }
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return PGR_OK;
+}
+
+static int set_seq_tables(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids) {
+    ctx->n_seq = n;
+    ctx->h_rid.resize(n);
+    for (size_t i = 0; i < n; i++) ctx->h_rid[i] = rids ? rids[i] : (uint32_t)i;
+    PGR_TRY(ctx->d_off.ensure((n + 1) * sizeof(uint64_t)));
+    PGR_TRY(ctx->d_len.ensure((n + 1) * sizeof(uint32_t)));
+    PGR_TRY(ctx->d_rid.ensure((n + 1) * sizeof(uint32_t)));
+    if (n) {
+        PGR_CUDA(cudaMemcpyAsync(ctx->d_off.p, ctx->h_off.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        PGR_CUDA(cudaMemcpyAsync(ctx->d_len.p, ctx->h_len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        PGR_CUDA(cudaMemcpyAsync(ctx->d_rid.p, ctx->h_rid.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PGR_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors may be reused by the next call
+    ctx->result_valid = false;
+    return PGR_OK;
+}
+
+int pgr_b200_ctx_upload(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens) {
+    if (!ctx || (n && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(ctx->device));
+    ctx->h_off.resize(n);
+    ctx->h_len.resize(n);
+    uint64_t off = SEQ_SLACK, total = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (lens[i] > 0x7FFFFF00ull) { set_error("sequence %zu longer than 2^31 (MM128 pos is 31 bits)", i); return PGR_E_LIMIT; }
+        if (lens[i] && !seqs[i]) { set_error("sequence %zu is NULL", i); return PGR_E_ARG; }
+        ctx->h_off[i] = off;
+        ctx->h_len[i] = (uint32_t)lens[i];
+        off += (lens[i] + 31) & ~(uint64_t)31;
+        total += lens[i];
+    }
+    const uint64_t store_bytes = off + SEQ_SLACK;
+    const bool grew = store_bytes > ctx->seq_store.cap;
+    PGR_TRY(ctx->seq_store.ensure(store_bytes));
+    if (grew) PGR_CUDA(cudaMemsetAsync(ctx->seq_store.p, 0, ctx->seq_store.cap, ctx->stream));
+    uint8_t *base = ctx->seq_store.as<uint8_t>();
+    // large sequences go straight from the caller's buffer (full PCIe rate when it is pinned);
+    // small ones are packed through a pinned staging buffer so that they share one copy
+    const size_t BIG = 1u << 20, STAGE = 64u << 20;
+    PGR_TRY(ctx->ensure_stage(2 * STAGE));
+    uint8_t *stage[2] = {(uint8_t *)ctx->h_stage, (uint8_t *)ctx->h_stage + STAGE};
+    cudaEvent_t ev[2];
+    PGR_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    PGR_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int cur = 0;
+    bool used[2] = {false, false};
+    size_t i = 0;
+    int rc = PGR_OK;
+    while (i < n && rc == PGR_OK) {
+        if (lens[i] >= BIG) {
+            if (cudaMemcpyAsync(base + ctx->h_off[i], seqs[i], lens[i], cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = PGR_E_CUDA;
+            i++;
+            continue;
+        }
+        // run of small sequences [i, j) whose device span fits the staging buffer
+        const uint64_t span0 = ctx->h_off[i];
+        size_t j = i;
+        while (j < n && lens[j] < BIG && (ctx->h_off[j] - span0) + ((lens[j] + 31) & ~(size_t)31) <= STAGE) j++;
+        if (used[cur]) cudaEventSynchronize(ev[cur]);
+        uint64_t span = 0;
+        for (size_t q = i; q < j; q++) {
+            const uint64_t rel = ctx->h_off[q] - span0;
+            if (lens[q]) memcpy(stage[cur] + rel, seqs[q], lens[q]);
+            const uint64_t padded = (lens[q] + 31) & ~(uint64_t)31;
+            if (padded > lens[q]) memset(stage[cur] + rel + lens[q], 0, padded - lens[q]);
+            span = rel + padded;
+        }
+        if (span && cudaMemcpyAsync(base + span0, stage[cur], span, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = PGR_E_CUDA;
+        cudaEventRecord(ev[cur], ctx->stream);
+        used[cur] = true;
+        cur ^= 1;
+        i = j;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (rc != PGR_OK) { set_error("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
+    ctx->d_seq = base;
+    ctx->total_bases = total;
+    return set_seq_tables(ctx, n, rids);
+}
+
+int pgr_b200_ctx_set_device_seqs(pgr_b200_ctx *ctx, const uint8_t *dev_base, size_t n, const uint32_t *rids, const uint64_t *offs,
+                                 const uint64_t *lens) {
+    if (!ctx || (n && (!dev_base || !offs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(ctx->device));
+    if (((uintptr_t)dev_base) & 31) { set_error("device base pointer must be 32-byte aligned"); return PGR_E_ARG; }
+    ctx->h_off.resize(n);
+    ctx->h_len.resize(n);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (offs[i] & 31) { set_error("sequence offset %zu is not 32-byte aligned", i); return PGR_E_ARG; }
+        if (offs[i] < SEQ_SLACK) { set_error("need %zu bytes of slack before the first sequence", SEQ_SLACK); return PGR_E_ARG; }
+        if (lens[i] > 0x7FFFFF00ull) { set_error("sequence %zu longer than 2^31", i); return PGR_E_LIMIT; }
+        ctx->h_off[i] = offs[i];
+        ctx->h_len[i] = (uint32_t)lens[i];
+        total += lens[i];
+    }
+    ctx->d_seq = dev_base;
+    ctx->total_bases = total;
+    return set_seq_tables(ctx, n, rids);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Level {
+    const pgr_mm128 *in; uint64_t n_in; const uint64_t *off_in;
+    pgr_mm128 *out; uint64_t *off_out;
+};
+
+// one reduce_shmmr level (kind 0) or the min_span filter (kind 1): flags -> block scan -> ordered scatter
+int run_level(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, const uint64_t *off_in, pgr_mm128 *out,
+              uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out) {
+    cudaStream_t st = ctx->stream;
+    const size_t n = ctx->n_seq;
+    if (n_in == 0) {
+        PGR_CUDA(cudaMemsetAsync(off_out, 0, (n + 1) * sizeof(uint64_t), st));
+        *n_out = 0;
+        return PGR_OK;
+    }
+    if (n_in >= (1ull << 32) * LV_BLK / 2) { set_error("list too long"); return PGR_E_LIMIT; }
+    const uint32_t n_blocks = (uint32_t)ceil_div<uint64_t>(n_in, LV_BLK);
+    PGR_TRY(ctx->flags.ensure(n_in));
+    PGR_TRY(ctx->block_sum.ensure((size_t)n_blocks * sizeof(uint32_t)));
+    PGR_TRY(ctx->block_prefix.ensure(((size_t)n_blocks + 1) * sizeof(uint64_t)));
+    LevelParams p;
+    p.in = in; p.n_in = n_in; p.seq_off_in = off_in; p.n_seq = (uint32_t)n;
+    p.r = spec.r; p.padding = padding ? 1u : 0u; p.min_span = spec.min_span;
+    p.flags = ctx->flags.as<uint8_t>(); p.block_sum = ctx->block_sum.as<uint32_t>();
+    p.block_prefix = ctx->block_prefix.as<uint64_t>();
+    p.out = out; p.seq_off_out = off_out; p.rid = ctx->d_rid.as<uint32_t>(); p.patch_rid = patch_rid ? 1u : 0u;
+    if (kind == 0) level_flags_kernel<0><<<n_blocks, LV_NT, 0, st>>>(p);
+    else level_flags_kernel<1><<<n_blocks, LV_NT, 0, st>>>(p);
+    block_scan_kernel<<<1, 1024, 0, st>>>(p.block_sum, p.block_prefix, n_blocks);
+    level_scatter_kernel<<<n_blocks, LV_NT, 0, st>>>(p);
+    ctx->counters[0] += 3;
+    PGR_CUDA(cudaGetLastError());
+    PGR_TRY(ctx->ensure_ctl(64));
+    PGR_CUDA(cudaMemcpyAsync(ctx->h_ctl, p.block_prefix + n_blocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    *n_out = *(uint64_t *)ctx->h_ctl;
+    return PGR_OK;
+}
+
+template <int W, int K>
+int launch_l0(const L0Params &p, int grid, cudaStream_t st) {
+    PGR_CUDA(cudaFuncSetAttribute(l0_kernel<W, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(L0Smem)));
+    l0_kernel<W, K><<<grid, L0_NT, sizeof(L0Smem), st>>>(p);
+    PGR_CUDA(cudaGetLastError());
+    return PGR_OK;
+}
+
+template <int W, int K>
+int occupancy_l0(int *occ) {
+    PGR_CUDA(cudaFuncSetAttribute(l0_kernel<W, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(L0Smem)));
+    PGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, l0_kernel<W, K>, L0_NT, sizeof(L0Smem)));
+    return PGR_OK;
+}
+
+// level-0 minimizers for the whole store -> flat list in ctx->bufA, per-sequence offsets in ctx->seq_dst
+int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
+    cudaStream_t st = ctx->stream;
+    const size_t n = ctx->n_seq;
+    const uint32_t w = spec.w, k = spec.k;
+    const uint32_t halo = ((w - 1 + 31) / 32) * 32;
+    const uint32_t TI = L0_KPOS - 2 * halo;
+    // tiles per sequence
+    std::vector<uint32_t> tile_prefix(n + 1);
+    uint64_t nt64 = 0;
+    for (size_t i = 0; i < n; i++) {
+        tile_prefix[i] = (uint32_t)nt64;
+        const uint32_t L = ctx->h_len[i];
+        if (L > k) nt64 += ceil_div<uint32_t>(L, TI);
+        if (nt64 >= 0xFFFFFFF0ull) { set_error("too many tiles in one batch"); return PGR_E_LIMIT; }
+    }
+    tile_prefix[n] = (uint32_t)nt64;
+    const uint32_t n_tiles = (uint32_t)nt64;
+    PGR_TRY(ctx->seq_dst.ensure((n + 1) * sizeof(uint64_t)));
+    if (n_tiles == 0) {
+        PGR_CUDA(cudaMemsetAsync(ctx->seq_dst.p, 0, (n + 1) * sizeof(uint64_t), st));
+        *n_l0 = 0;
+        return PGR_OK;
+    }
+    int occ = 1;
+    const int variant = (w == 80 && k == 56) ? 1 : (w == 48 && k == 56) ? 2 : 0;
+    if (variant == 1) PGR_TRY((occupancy_l0<80, 56>(&occ)));
+    else if (variant == 2) PGR_TRY((occupancy_l0<48, 56>(&occ)));
+    else PGR_TRY((occupancy_l0<0, 0>(&occ)));
+    if (occ < 1) { set_error("l0_kernel does not fit on an SM"); return PGR_E_CUDA; }
+    const uint32_t G = std::min<uint32_t>(n_tiles, (uint32_t)(ctx->n_sm * occ));
+    // static, cost-balanced partition of the tile sequence over the CTAs (contiguous ranges keep the output ordered)
+    std::vector<uint32_t> cta_tile(G + 1);
+    std::vector<uint64_t> cta_cost(G, 0);
+    {
+        auto tile_cost = [&](uint32_t L, uint32_t j) -> uint64_t {
+            const uint64_t lo = (uint64_t)j * TI;
+            return std::min<uint64_t>(TI, L - lo) + 2 * halo + 256;
+        };
+        uint64_t total_cost = 0;
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t cnt = tile_prefix[i + 1] - tile_prefix[i];
+            for (uint32_t j = 0; j < cnt; j++) total_cost += tile_cost(ctx->h_len[i], j);
+        }
+        uint64_t acc = 0;
+        uint32_t c = 0, t = 0;
+        cta_tile[0] = 0;
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t cnt = tile_prefix[i + 1] - tile_prefix[i];
+            for (uint32_t j = 0; j < cnt; j++, t++) {
+                const uint64_t tc = tile_cost(ctx->h_len[i], j);
+                // close CTA c before tile t when it already holds its share and enough tiles remain for the rest
+                while (c + 1 < G && acc >= (total_cost * (c + 1)) / G && t > cta_tile[c]) { c++; cta_tile[c] = t; }
+                acc += tc;
+                cta_cost[c] += tc;
+            }
+        }
+        while (c + 1 <= G) { c++; cta_tile[c] = n_tiles; }
+    }
+    uint64_t max_cost = 0;
+    for (uint32_t c = 0; c < G; c++) max_cost = std::max(max_cost, cta_cost[c]);
+    PGR_TRY(ctx->tile_prefix.ensure((n + 1) * sizeof(uint32_t)));
+    PGR_TRY(ctx->cta_tile.ensure((G + 1) * sizeof(uint32_t)));
+    PGR_TRY(ctx->chunk_count.ensure(G * sizeof(uint64_t)));
+    PGR_TRY(ctx->seq_count.ensure(n * sizeof(uint32_t)));
+    PGR_TRY(ctx->seq_flag.ensure(n * sizeof(uint32_t)));
+    PGR_CUDA(cudaMemcpyAsync(ctx->tile_prefix.p, tile_prefix.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    PGR_CUDA(cudaMemcpyAsync(ctx->cta_tile.p, cta_tile.data(), (G + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // arena: expected density 2/(w+1) with 2x headroom; exact retry on overflow
+    uint64_t chunk_cap = (uint64_t)((double)max_cost * std::min(1.0, 4.0 / (w + 1.0))) + 1024;
+    chunk_cap = std::max(chunk_cap, ctx->chunk_cap * 0 + chunk_cap);
+    PGR_TRY(ctx->ensure_ctl(G * sizeof(uint64_t) + 2 * n * sizeof(uint32_t) + 64));
+    uint64_t *h_chunk = (uint64_t *)ctx->h_ctl;
+    uint32_t *h_count = (uint32_t *)(h_chunk + G);
+    uint32_t *h_flag = h_count + n;
+    for (int attempt = 0;; attempt++) {
+        PGR_TRY(ctx->arena.ensure((size_t)G * chunk_cap * sizeof(pgr_mm128)));
+        ctx->chunk_cap = chunk_cap;
+        PGR_CUDA(cudaMemsetAsync(ctx->seq_count.p, 0, n * sizeof(uint32_t), st));
+        PGR_CUDA(cudaMemsetAsync(ctx->seq_flag.p, 0, n * sizeof(uint32_t), st));
+        L0Params p;
+        p.seq = ctx->d_seq; p.off = ctx->d_off.as<uint64_t>(); p.len = ctx->d_len.as<uint32_t>();
+        p.tile_prefix = ctx->tile_prefix.as<uint32_t>(); p.cta_tile = ctx->cta_tile.as<uint32_t>();
+        p.n_seq = (uint32_t)n; p.w = w; p.k = k; p.tile_stride = TI; p.halo = halo;
+        p.arena = ctx->arena.as<pgr_mm128>(); p.chunk_cap = chunk_cap;
+        p.chunk_count = ctx->chunk_count.as<uint64_t>(); p.seq_count = ctx->seq_count.as<uint32_t>();
+        p.seq_flag = ctx->seq_flag.as<uint32_t>();
+        const int slot = ctx->timer.begin("l0_minimizers", st);
+        if (variant == 1) PGR_TRY((launch_l0<80, 56>(p, (int)G, st)));
+        else if (variant == 2) PGR_TRY((launch_l0<48, 56>(p, (int)G, st)));
+        else PGR_TRY((launch_l0<0, 0>(p, (int)G, st)));
+        ctx->timer.end(slot, st);
+        ctx->counters[0] += 1;
+        PGR_CUDA(cudaMemcpyAsync(h_chunk, ctx->chunk_count.p, G * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(h_count, ctx->seq_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(h_flag, ctx->seq_flag.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaStreamSynchronize(st));
+        uint64_t mx = 0;
+        for (uint32_t c = 0; c < G; c++) mx = std::max(mx, h_chunk[c]);
+        if (mx <= chunk_cap) break;
+        if (attempt >= 2) { set_error("level-0 arena overflow persists"); return PGR_E_CUDA; }
+        chunk_cap = mx + mx / 16 + 64;
+        ctx->counters[3] += 1;
+    }
+    // sequences flagged for sequential replay
+    std::vector<uint32_t> replay;
+    for (size_t i = 0; i < n; i++) if (h_flag[i]) replay.push_back((uint32_t)i);
+    std::vector<uint32_t> final_count(h_count, h_count + n);
+    if (!replay.empty()) {
+        PGR_TRY(ctx->replay_list.ensure(replay.size() * sizeof(uint32_t)));
+        PGR_TRY(ctx->replay_count.ensure(n * sizeof(uint32_t)));
+        PGR_CUDA(cudaMemcpyAsync(ctx->replay_list.p, replay.data(), replay.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        ReplayParams rp;
+        rp.seq = ctx->d_seq; rp.off = ctx->d_off.as<uint64_t>(); rp.len = ctx->d_len.as<uint32_t>();
+        rp.list = ctx->replay_list.as<uint32_t>(); rp.n_list = (uint32_t)replay.size(); rp.w = w; rp.k = k;
+        rp.count = ctx->replay_count.as<uint32_t>(); rp.dst_off = nullptr; rp.dst = nullptr;
+        const int slot = ctx->timer.begin("l0_replay_count", st);
+        replay_l0_kernel<0><<<ceil_div<uint32_t>(rp.n_list, 32), 32, 0, st>>>(rp);
+        ctx->timer.end(slot, st);
+        ctx->counters[0] += 1;
+        PGR_CUDA(cudaGetLastError());
+        std::vector<uint32_t> rc(n);
+        PGR_CUDA(cudaMemcpyAsync(h_count, ctx->replay_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t sid : replay) final_count[sid] = h_count[sid];
+        // h_count now holds replay counts at flagged slots only; restore semantics below via final_count
+    }
+    ctx->counters[2] = replay.size();
+    // host scans (small arrays)
+    std::vector<uint64_t> seq_fast(n), seq_dst(n + 1), chunk_prefix(G + 1);
+    {
+        // fast-path counts are what the kernel accumulated (before replay substitution)
+        uint64_t a = 0, b = 0;
+        // re-read the fast counts: they were overwritten in h_count only when a replay happened
+        std::vector<uint32_t> fast(n);
+        if (replay.empty()) {
+            for (size_t i = 0; i < n; i++) fast[i] = final_count[i];
+        } else {
+            PGR_CUDA(cudaMemcpyAsync(h_count, ctx->seq_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < n; i++) fast[i] = h_count[i];
+        }
+        for (size_t i = 0; i < n; i++) { seq_fast[i] = a; a += fast[i]; seq_dst[i] = b; b += final_count[i]; }
+        seq_dst[n] = b;
+        uint64_t c0 = 0;
+        for (uint32_t c = 0; c < G; c++) { chunk_prefix[c] = c0; c0 += h_chunk[c]; }
+        chunk_prefix[G] = c0;
+    }
+    const uint64_t total = seq_dst[n];
+    *n_l0 = total;
+    PGR_TRY(ctx->seq_fast.ensure(n * sizeof(uint64_t)));
+    PGR_TRY(ctx->chunk_prefix.ensure((G + 1) * sizeof(uint64_t)));
+    PGR_CUDA(cudaMemcpyAsync(ctx->seq_fast.p, seq_fast.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGR_CUDA(cudaMemcpyAsync(ctx->seq_dst.p, seq_dst.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGR_CUDA(cudaMemcpyAsync(ctx->chunk_prefix.p, chunk_prefix.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGR_TRY(ctx->bufA.ensure(std::max<uint64_t>(total, 1) * sizeof(pgr_mm128)));
+    PGR_TRY(ctx->bufB.ensure(std::max<uint64_t>(total, 1) * sizeof(pgr_mm128)));
+    if (total) {
+        GatherParams gp;
+        gp.arena = ctx->arena.as<pgr_mm128>(); gp.chunk_cap = chunk_cap; gp.chunk_prefix = ctx->chunk_prefix.as<uint64_t>();
+        gp.n_chunks = G; gp.seq_fast = ctx->seq_fast.as<uint64_t>(); gp.seq_dst = ctx->seq_dst.as<uint64_t>();
+        gp.seq_flag = ctx->seq_flag.as<uint32_t>(); gp.flat = ctx->bufA.as<pgr_mm128>();
+        const int slot = ctx->timer.begin("l0_gather", st);
+        gather_l0_kernel<<<dim3(16, G), 256, 0, st>>>(gp);
+        ctx->timer.end(slot, st);
+        ctx->counters[0] += 1;
+        PGR_CUDA(cudaGetLastError());
+    }
+    if (!replay.empty()) {
+        ReplayParams rp;
+        rp.seq = ctx->d_seq; rp.off = ctx->d_off.as<uint64_t>(); rp.len = ctx->d_len.as<uint32_t>();
+        rp.list = ctx->replay_list.as<uint32_t>(); rp.n_list = (uint32_t)replay.size(); rp.w = w; rp.k = k;
+        rp.count = nullptr; rp.dst_off = ctx->seq_dst.as<uint64_t>(); rp.dst = ctx->bufA.as<pgr_mm128>();
+        const int slot = ctx->timer.begin("l0_replay_write", st);
+        replay_l0_kernel<1><<<ceil_div<uint32_t>(rp.n_list, 32), 32, 0, st>>>(rp);
+        ctx->timer.end(slot, st);
+        ctx->counters[0] += 1;
+        PGR_CUDA(cudaGetLastError());
+    }
+    // the host vectors above are pageable: make sure the async copies are done before they go out of scope
+    PGR_CUDA(cudaStreamSynchronize(st));
+    return PGR_OK;
+}
+
+// sketch mode (shmmrutils.rs:558-630): flat list of kept k-mers in ctx->bufA, offsets in ctx->seq_dst
+int run_sketch(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
+    cudaStream_t st = ctx->stream;
+    const size_t n = ctx->n_seq;
+    std::vector<uint64_t> seg_prefix(n + 1);
+    uint64_t n_segs = 0;
+    for (size_t i = 0; i < n; i++) { seg_prefix[i] = n_segs; n_segs += ceil_div<uint64_t>(ctx->h_len[i], SK_SEG); }
+    seg_prefix[n] = n_segs;
+    PGR_TRY(ctx->seq_dst.ensure((n + 1) * sizeof(uint64_t)));
+    if (n_segs == 0) {
+        PGR_CUDA(cudaMemsetAsync(ctx->seq_dst.p, 0, (n + 1) * sizeof(uint64_t), st));
+        *n_l0 = 0;
+        return PGR_OK;
+    }
+    // reuse: tile_prefix <- seg_prefix (u64), seq_count <- seg_count, chunk_prefix <- seg_off
+    PGR_TRY(ctx->tile_prefix.ensure((n + 1) * sizeof(uint64_t)));
+    PGR_TRY(ctx->seq_count.ensure(n_segs * sizeof(uint32_t)));
+    PGR_TRY(ctx->chunk_prefix.ensure((n_segs + 1) * sizeof(uint64_t)));
+    PGR_CUDA(cudaMemcpyAsync(ctx->tile_prefix.p, seg_prefix.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    SketchParams sp;
+    sp.seq = ctx->d_seq; sp.off = ctx->d_off.as<uint64_t>(); sp.len = ctx->d_len.as<uint32_t>();
+    sp.blk_prefix = ctx->tile_prefix.as<uint64_t>(); sp.n_seq = (uint32_t)n; sp.k = spec.k; sp.r = spec.r;
+    sp.seg_count = ctx->seq_count.as<uint32_t>(); sp.seg_off = nullptr; sp.out = nullptr;
+    const uint32_t grid = (uint32_t)ceil_div<uint64_t>(n_segs, 128);
+    int slot = ctx->timer.begin("sketch_count", st);
+    sketch_kernel<0><<<grid, 128, 0, st>>>(sp, n_segs);
+    ctx->timer.end(slot, st);
+    PGR_CUDA(cudaGetLastError());
+    PGR_TRY(ctx->ensure_ctl(n_segs * sizeof(uint32_t) + 64));
+    uint32_t *h_seg = (uint32_t *)ctx->h_ctl;
+    PGR_CUDA(cudaMemcpyAsync(h_seg, ctx->seq_count.p, n_segs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint64_t> seg_off(n_segs + 1), seq_dst(n + 1);
+    uint64_t a = 0;
+    for (uint64_t s = 0; s < n_segs; s++) { seg_off[s] = a; a += h_seg[s]; }
+    seg_off[n_segs] = a;
+    for (size_t i = 0; i <= n; i++) seq_dst[i] = seg_off[seg_prefix[i]];
+    *n_l0 = a;
+    PGR_CUDA(cudaMemcpyAsync(ctx->chunk_prefix.p, seg_off.data(), (n_segs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGR_CUDA(cudaMemcpyAsync(ctx->seq_dst.p, seq_dst.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGR_TRY(ctx->bufA.ensure(std::max<uint64_t>(a, 1) * sizeof(pgr_mm128)));
+    PGR_TRY(ctx->bufB.ensure(std::max<uint64_t>(a, 1) * sizeof(pgr_mm128)));
+    sp.seg_off = ctx->chunk_prefix.as<uint64_t>(); sp.out = ctx->bufA.as<pgr_mm128>();
+    slot = ctx->timer.begin("sketch_write", st);
+    sketch_kernel<1><<<grid, 128, 0, st>>>(sp, n_segs);
+    ctx->timer.end(slot, st);
+    ctx->counters[0] += 2;
+    PGR_CUDA(cudaGetLastError());
+    PGR_CUDA(cudaStreamSynchronize(st));
+    return PGR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgr_b200_ctx_shmmrs(pgr_b200_ctx *ctx, const pgr_shmmr_spec *spec_in, int padding, size_t *n_shmmrs) {
+    if (!ctx) { set_error("ctx is NULL"); return PGR_E_ARG; }
+    PGR_TRY(check_spec(spec_in));
+    const pgr_shmmr_spec spec = *spec_in;
+    PGR_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->timer.reset();
+    memset(ctx->counters, 0, sizeof ctx->counters);
+    ctx->result_valid = false;
+    const size_t n = ctx->n_seq;
+    PGR_TRY(ctx->off_a.ensure((n + 1) * sizeof(uint64_t)));
+    PGR_TRY(ctx->off_b.ensure((n + 1) * sizeof(uint64_t)));
+    uint64_t n_cur = 0;
+    if (spec.sketch) PGR_TRY(run_sketch(ctx, spec, &n_cur));
+    else PGR_TRY(run_l0(ctx, spec, &n_cur));
+    ctx->counters[1] = n_cur;
+    PGR_TRY(ctx->bufA.ensure(std::max<uint64_t>(n_cur, 1) * sizeof(pgr_mm128)));
+    PGR_TRY(ctx->bufB.ensure(std::max<uint64_t>(n_cur, 1) * sizeof(pgr_mm128)));
+    const pgr_mm128 *cur = ctx->bufA.as<pgr_mm128>();
+    const uint64_t *cur_off = ctx->seq_dst.as<uint64_t>();
+    const int slot = ctx->timer.begin("reduce_and_span", st);
+    if (!spec.sketch && spec.r > 1) {
+        uint64_t n1 = 0, n2 = 0;
+        PGR_TRY(run_level(ctx, 0, cur, n_cur, cur_off, ctx->bufB.as<pgr_mm128>(), ctx->off_a.as<uint64_t>(), spec, padding, false, &n1));
+        PGR_TRY(run_level(ctx, 0, ctx->bufB.as<pgr_mm128>(), n1, ctx->off_a.as<uint64_t>(), ctx->bufA.as<pgr_mm128>(),
+                          ctx->off_b.as<uint64_t>(), spec, padding, false, &n2));
+        cur = ctx->bufA.as<pgr_mm128>(); cur_off = ctx->off_b.as<uint64_t>(); n_cur = n2;
+    }
+    uint64_t n_fin = 0;
+    PGR_TRY(run_level(ctx, 1, cur, n_cur, cur_off, ctx->bufB.as<pgr_mm128>(), ctx->off_a.as<uint64_t>(), spec, 0, true, &n_fin));
+    ctx->timer.end(slot, st);
+    ctx->d_result = ctx->bufB.as<pgr_mm128>();
+    ctx->d_result_off = ctx->off_a.as<uint64_t>();
+    ctx->n_result = n_fin;
+
+    // padding=true with an empty level-0 list: reduce_shmmr keeps its MAX sentinels and the span filter leaves two
+    // of them (shmmrutils.rs:367-380 twice, then :541-553).  Rare API corner; rebuilt on the host.
+    if (padding && !spec.sketch && spec.r > 1 && n) {
+        std::vector<uint64_t> l0_off(n + 1), fin_off(n + 1);
+        PGR_CUDA(cudaMemcpyAsync(l0_off.data(), ctx->seq_dst.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(fin_off.data(), ctx->d_result_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaStreamSynchronize(st));
+        bool any = false;
+        for (size_t i = 0; i < n; i++) any = any || (l0_off[i + 1] == l0_off[i]);
+        if (any) {
+            std::vector<pgr_mm128> mm(n_fin), out;
+            if (n_fin) PGR_CUDA(cudaMemcpy(mm.data(), ctx->d_result, n_fin * sizeof(pgr_mm128), cudaMemcpyDeviceToHost));
+            std::vector<uint64_t> noff(n + 1);
+            for (size_t i = 0; i < n; i++) {
+                noff[i] = out.size();
+                if (l0_off[i + 1] == l0_off[i]) {
+                    const pgr_mm128 s = {~0ull, ~0ull};
+                    out.push_back(s); out.push_back(s);
+                } else {
+                    out.insert(out.end(), mm.begin() + fin_off[i], mm.begin() + fin_off[i + 1]);
+                }
+            }
+            noff[n] = out.size();
+            PGR_TRY(ctx->fix_mm.ensure(std::max<size_t>(1, out.size()) * sizeof(pgr_mm128)));
+            PGR_TRY(ctx->fix_off.ensure((n + 1) * sizeof(uint64_t)));
+            PGR_CUDA(cudaMemcpy(ctx->fix_mm.p, out.data(), out.size() * sizeof(pgr_mm128), cudaMemcpyHostToDevice));
+            PGR_CUDA(cudaMemcpy(ctx->fix_off.p, noff.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+            ctx->d_result = ctx->fix_mm.as<pgr_mm128>();
+            ctx->d_result_off = ctx->fix_off.as<uint64_t>();
+            ctx->n_result = out.size();
+        }
+    }
+    ctx->result_valid = true;
+    if (n_shmmrs) *n_shmmrs = ctx->n_result;
+    return PGR_OK;
+}
+
+int pgr_b200_ctx_shmmrs_device(pgr_b200_ctx *ctx, const pgr_mm128 **d_mm, const uint64_t **d_offsets) {
+    if (!ctx || !ctx->result_valid) { set_error("no shimmer result available"); return PGR_E_ARG; }
+    if (d_mm) *d_mm = ctx->d_result;
+    if (d_offsets) *d_offsets = ctx->d_result_off;
+    return PGR_OK;
+}
+
+int pgr_b200_ctx_shmmrs_download(pgr_b200_ctx *ctx, pgr_mm128 **out, size_t *offsets) {
+    if (!ctx || !ctx->result_valid || !out || !offsets) { set_error("no shimmer result available / NULL argument"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = ctx->n_seq;
+    pgr_mm128 *o = (pgr_mm128 *)malloc(std::max<size_t>(1, ctx->n_result) * sizeof(pgr_mm128));
+    if (!o) { set_error("out of host memory"); return PGR_E_ARG; }
+    std::vector<uint64_t> off(n + 1);
+    cudaError_t e = cudaSuccess;
+    if (ctx->n_result) e = cudaMemcpyAsync(o, ctx->d_result, ctx->n_result * sizeof(pgr_mm128), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(off.data(), ctx->d_result_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { free(o); set_error("D2H failed: %s", cudaGetErrorString(e)); return PGR_E_CUDA; }
+    for (size_t i = 0; i <= n; i++) offsets[i] = (size_t)off[i];
+    *out = o;
+    return PGR_OK;
+}
+
+int pgr_b200_ctx_timings(pgr_b200_ctx *ctx, const char *const **names, const float **ms, size_t *n) {
+    if (!ctx) { set_error("ctx is NULL"); return PGR_E_ARG; }
+    ctx->timer.collect();
+    if (names) *names = ctx->timer.names_z.data();
+    if (ms) *ms = ctx->timer.ms.data();
+    if (n) *n = ctx->timer.used;
+    return PGR_OK;
+}
+
+int pgr_b200_ctx_counters(pgr_b200_ctx *ctx, uint64_t out[8]) {
+    if (!ctx || !out) { set_error("NULL argument"); return PGR_E_ARG; }
+    memcpy(out, ctx->counters, sizeof ctx->counters);
+    return PGR_OK;
+}
+
+// ---- one-shot host API (thread-local default context on device 0) ---------------------------------------------
+static pgr_b200_ctx *tls_ctx() {
+    struct Holder { pgr_b200_ctx *c = nullptr; ~Holder() { /* leaked on purpose: CUDA may already be torn down */ } };
+    static thread_local Holder h;
+    if (!h.c) h.c = pgr_b200_ctx_new(0);
+    return h.c;
+}
+
+int pgr_b200_shmmrs_batch(size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens,
+                          const pgr_shmmr_spec *spec, int padding, pgr_mm128 **out, size_t *offsets) {
+    if (!out || !offsets) { set_error("NULL output argument"); return PGR_E_ARG; }
+    PGR_TRY(check_spec(spec));
+    pgr_b200_ctx *ctx = tls_ctx();
+    if (!ctx) return PGR_E_NO_DEVICE;
+    PGR_TRY(pgr_b200_ctx_upload(ctx, n, rids, seqs, lens));
+    size_t ns = 0;
+    PGR_TRY(pgr_b200_ctx_shmmrs(ctx, spec, padding, &ns));
+    return pgr_b200_ctx_shmmrs_download(ctx, out, offsets);
+}
+
+int pgr_b200_sequence_to_shmmrs(uint32_t rid, const uint8_t *seq, size_t len, const pgr_shmmr_spec *spec, int padding,
+                                pgr_mm128 **out, size_t *n_out) {
+    if (!n_out) { set_error("NULL output argument"); return PGR_E_ARG; }
+    size_t offs[2] = {0, 0};
+    const uint8_t *ptrs[1] = {seq};
+    const size_t lens[1] = {len};
+    const uint32_t rids[1] = {rid};
+    PGR_TRY(pgr_b200_shmmrs_batch(1, rids, ptrs, lens, spec, padding, out, offs));
+    *n_out = offs[1];
+    return PGR_OK;
+}
+
+}  // extern "C"

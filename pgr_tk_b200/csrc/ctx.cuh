@@ -1,0 +1,74 @@
+// ctx.cuh — device context: streams, grow-only device buffers, the device sequence store.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace pgr {
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return PGR_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        PGR_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return PGR_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct StageTimer {
+    std::vector<const char *> names;
+    std::vector<cudaEvent_t> ev0, ev1;
+    std::vector<float> ms;
+    std::vector<const char *> names_z;  // NULL-terminated copy handed to the C ABI
+    size_t used = 0;
+    void reset() { used = 0; }
+    int begin(const char *name, cudaStream_t st);
+    void end(int slot, cudaStream_t st);
+    void collect();
+    void destroy();
+};
+
+constexpr size_t SEQ_SLACK = 16384;  // readable bytes kept before the first and after the last sequence
+
+}  // namespace pgr
+
+struct pgr_b200_ctx {
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // sequence store
+    pgr::DevBuf seq_store;              // owned copy (upload) — unused when sequences were adopted
+    const uint8_t *d_seq = nullptr;     // base pointer used by kernels
+    pgr::DevBuf d_off, d_len, d_rid;
+    std::vector<uint64_t> h_off;
+    std::vector<uint32_t> h_len, h_rid;
+    size_t n_seq = 0;
+    uint64_t total_bases = 0;
+    // pinned staging for small sequences and control read-backs
+    void *h_stage = nullptr; size_t h_stage_cap = 0;
+    void *h_ctl = nullptr; size_t h_ctl_cap = 0;
+    // shimmer pipeline buffers
+    pgr::DevBuf tile_prefix, cta_tile, arena, chunk_count, seq_count, seq_flag, replay_list, replay_count;
+    pgr::DevBuf chunk_prefix, seq_fast, seq_dst, bufA, bufB, flags, block_sum, block_prefix, off_a, off_b;
+    uint64_t chunk_cap = 0;
+    // result of the last shmmrs call
+    const pgr_mm128 *d_result = nullptr;
+    const uint64_t *d_result_off = nullptr;
+    size_t n_result = 0;
+    bool result_valid = false;
+    // padding fix-up (rare): host-side rebuilt result
+    pgr::DevBuf fix_mm, fix_off;
+    pgr::StageTimer timer;
+    uint64_t counters[8] = {0};
+
+    int ensure_stage(size_t bytes);
+    int ensure_ctl(size_t bytes);
+};

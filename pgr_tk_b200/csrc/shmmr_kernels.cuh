@@ -1,0 +1,766 @@
+// shmmr_kernels.cuh — sm_100a kernels for sequence_to_shmmrs (shmmrutils.rs:417-669).
+//
+// The reference walks every sequence with a sequential state machine (ring buffer, min_mer, mdist).  These kernels
+// use the equivalent LOCAL rule (DESIGN.md "Local rule", property-tested in tests/test_local_rule.py):
+//   level 0 : position p in [k, L) is a minimizer  <=>  x[p] is a (tie-inclusive) minimum of some window of w
+//             consecutive k-mer keys that lies inside [k, min(L, L-w+k)); the last w-k positions are replayed
+//             (rescans only) by one thread of the sequence's last tile;
+//   level 1,2: the same window-minimum rule over list indices with window r (reduce_shmmr, applied twice);
+//   min_span filter on the level-2 list.
+// Sequences containing a byte outside ACGTacgt or a pushed reverse-complement palindrome (fmmer == rmmer,
+// shmmrutils.rs:477) are flagged and recomputed by replay_l0_kernel, an exact sequential restatement.
+#pragma once
+#include "common.cuh"
+
+namespace pgr {
+
+constexpr int L0_NT = 256;                 // threads per CTA; thread t owns the 32-base block t of the tile's load region
+constexpr int L0_CTX = 2;                  // leading context-only blocks (a 56-mer reaches 55 bases back)
+constexpr int L0_KB = L0_NT - L0_CTX;      // blocks that get keys: 254
+constexpr int L0_KPOS = L0_KB * 32;        // key positions per tile: 8128
+constexpr int L0_PADB = 6;                 // spare blocks on both sides of the smem arrays (van Herk neighbours)
+constexpr int L0_ARR = (L0_KB + 2 * L0_PADB) * 33;  // padded u32 array length
+constexpr int L0_TAILCAP = 288;            // max level-0 entries the tail replay can emit (<= 2w + slack)
+
+struct L0Params {
+    const uint8_t *seq;          // device sequence store
+    const uint64_t *off;         // [n_seq] byte offset of each sequence (32-byte aligned)
+    const uint32_t *len;         // [n_seq]
+    const uint32_t *tile_prefix; // [n_seq+1] cumulative tile count
+    const uint32_t *cta_tile;    // [grid+1] static tile range per CTA
+    uint32_t n_seq;
+    uint32_t w, k;
+    uint32_t tile_stride;        // TI: output positions per tile
+    uint32_t halo;               // HB*32 >= w-1
+    pgr_mm128 *arena;            // level-0 output, one private chunk per CTA
+    uint64_t chunk_cap;          // entries per chunk
+    uint64_t *chunk_count;       // [grid] entries demanded by each CTA (may exceed chunk_cap => host retries)
+    uint32_t *seq_count;         // [n_seq] level-0 entries per sequence (atomicAdd per tile)
+    uint32_t *seq_flag;          // [n_seq] != 0 => sequence must be replayed sequentially
+};
+
+__device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+
+// 4 ASCII bases (one little-endian word) -> 4 plane bits each, first base in the MOST significant of the 4 bits.
+// code bit0 = bit1 of (c ^ (c >> 1)), code bit1 = bit2 of c  (A=0,C=1,G=2,T=3; case-insensitive)
+__device__ __forceinline__ void planes4(uint32_t wd, uint32_t &p0, uint32_t &p1) {
+    const uint32_t t = wd ^ (wd >> 1);
+    // bits at 1,9,17,25 (resp. 2,10,18,26) gathered to the top nibble by one multiply (no carries collide)
+    p0 = ((t & 0x02020202u) * 0x40201008u) >> 28;    // bit 1+8i -> 31-i
+    p1 = ((wd & 0x04040404u) * 0x20100804u) >> 28;   // bit 2+8i -> 31-i
+}
+
+// true iff all 4 bytes of wd are one of ACGTacgt
+__device__ __forceinline__ bool word_is_acgt(uint32_t wd) {
+    const uint32_t u = wd & 0xDFDFDFDFu;             // upper-case
+    const uint32_t v = u ^ 0x41414141u;              // A->00 C->02 G->06 T->15
+    // valid values: 0x00, 0x02, 0x06, 0x15.  bits 3,5,6,7 must be clear; then (b4,b2,b1,b0) in {0000,0010,0110,1101}
+    const uint32_t b0 = v, b1 = v >> 1, b2 = v >> 2, b4 = v >> 4;
+    // invalid combos: b0 != b4 ; b2 & ~b1 & ~b4 ... written as: ok = (b0 == b4) && (b4 ? (b2 && !b1) : (!b2 || b1))
+    const uint32_t x04 = b0 ^ b4;                    // must be 0
+    const uint32_t t_ok = b2 & ~b1;                  // T: b2=1,b1=0
+    const uint32_t n_ok = ~b2 | b1;                  // A,C,G: not (b2=1,b1=0)
+    const uint32_t ok = (b4 & t_ok) | (~b4 & n_ok);
+    const uint32_t bad = (v & 0xE8E8E8E8u) | ((x04 | ~ok) & 0x01010101u);
+    return bad == 0;
+}
+
+__device__ __forceinline__ bool byte_is_acgt(uint32_t c) {
+    c &= 0xDFu;
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
+
+__device__ __forceinline__ uint32_t min3u(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
+__device__ __forceinline__ uint32_t max3u(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
+
+struct L0Smem {
+    uint32_t H[L0_ARR];      // hi 32 bits of x  (= hash bits 24..55); padded index q + q/32 + PADB*33
+    uint32_t X[L0_ARR];      // lo 32 bits of x  (= hash bits 0..23 << 8 | k)
+    uint32_t P[L0_ARR];      // van Herk exchange: prefix minima (pass 1) then suffix maxima (pass 2)
+    uint32_t F0[L0_NT + 8], F1[L0_NT + 8], R0[L0_NT + 8], R1[L0_NT + 8];  // bit planes per 32-base block
+    uint32_t bext[L0_KB + 2 * L0_PADB];   // block min (pass 1) / block max (pass 2)
+    uint32_t cmask[L0_KB + 2 * L0_PADB];  // candidate / selected bit masks per block
+    uint32_t strand[L0_KB];
+    uint32_t wsum[L0_NT / 32];
+    pgr_mm128 tail[L0_TAILCAP];
+    uint32_t tail_n;
+    // tile descriptor
+    uint32_t seq_id, seq_len;
+    int32_t keys_start;      // sequence position of key index 0 (multiple of 32, may be negative)
+    int32_t out_lo, out_hi;  // output position range [out_lo, out_hi)
+    uint32_t is_last;
+    uint32_t bad;            // tile saw an invalid byte or a palindrome
+    uint64_t seq_off;
+};
+
+__device__ __forceinline__ int pidx(int q) { return q + (q >> 5) + L0_PADB * 33; }  // q may be negative (>= -PADB*32)
+
+// exact 64-bit key compare helpers on the split arrays
+__device__ __forceinline__ bool key_lt(const L0Smem &s, int qa, int qb) {  // x[qa] < x[qb]
+    const uint32_t ha = s.H[pidx(qa)], hb = s.H[pidx(qb)];
+    return ha < hb || (ha == hb && s.X[pidx(qa)] < s.X[pidx(qb)]);
+}
+
+// Level-0 minimizers of one tile.  W, K > 0 are compile-time specialisations; 0 = read from params.
+template <int W, int K>
+__global__ void __launch_bounds__(L0_NT, 2) l0_kernel(const L0Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    L0Smem &s = *reinterpret_cast<L0Smem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t w = W ? (uint32_t)W : p.w;
+    const uint32_t k = K ? (uint32_t)K : p.k;
+    const uint64_t kmask = ~0ull >> (64 - k);
+    const uint32_t mlo = (uint32_t)kmask, mhi = (uint32_t)(kmask >> 32);
+
+    const uint32_t t_begin = p.cta_tile[blockIdx.x], t_end = p.cta_tile[blockIdx.x + 1];
+    uint64_t running = 0;  // entries this CTA has produced so far (thread 0 keeps the authoritative copy)
+    pgr_mm128 *chunk = p.arena + (uint64_t)blockIdx.x * p.chunk_cap;
+
+    // spare blocks of the exchange arrays are never written with real data; give them harmless values once
+    for (int i = tid; i < L0_KB + 2 * L0_PADB; i += L0_NT) { s.bext[i] = 0; s.cmask[i] = 0; }
+
+    for (uint32_t tile = t_begin; tile < t_end; ++tile) {
+        __syncthreads();  // previous tile fully consumed
+        if (tid == 0) {
+            // tile -> (sequence, tile index): largest sid with tile_prefix[sid] <= tile
+            uint32_t lo = 0, hi = p.n_seq;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (p.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+            }
+            const uint32_t sid = lo, j = tile - p.tile_prefix[sid];
+            const uint32_t L = p.len[sid];
+            const uint32_t nt = p.tile_prefix[sid + 1] - p.tile_prefix[sid];
+            int32_t ks = (int32_t)(j * p.tile_stride) - (int32_t)p.halo;
+            const bool last = (j + 1 == nt);
+            if (last) {  // the tail replay needs keys and selections back to E - 2w: pull the tile back if it is short
+                const int32_t need = ((int32_t)L - 3 * (int32_t)w - 32) & ~31;
+                if (need < ks) ks = need;
+                if (ks < -(int32_t)p.halo) ks = -(int32_t)p.halo;
+            }
+            s.seq_id = sid; s.seq_len = L; s.keys_start = ks; s.is_last = last ? 1u : 0u;
+            s.out_lo = (int32_t)(j * p.tile_stride);
+            s.out_hi = (int32_t)min((uint64_t)L, (uint64_t)(j + 1) * p.tile_stride);
+            s.seq_off = p.off[sid];
+            s.bad = 0; s.tail_n = 0;
+        }
+        __syncthreads();
+        const int32_t L = (int32_t)s.seq_len;
+        const int32_t keys_start = s.keys_start;
+        const int32_t blk_pos = keys_start + 32 * (tid - L0_CTX);  // sequence position of this thread's first base
+        const uint8_t *gseq = p.seq + s.seq_off;
+
+        // ---- phase 1: 32 bases -> plane words -------------------------------------------------------------
+        uint32_t f0 = 0, f1 = 0;
+        const bool blk_live = (blk_pos + 32 > 0) && (blk_pos < L);  // block intersects the sequence
+        if (blk_live) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(gseq + blk_pos);
+            const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+            const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t a, b;
+                planes4(wd[j], a, b);
+                f0 = (f0 << 4) | a;
+                f1 = (f1 << 4) | b;
+                ok = ok && word_is_acgt(wd[j]);
+            }
+            if (!ok || blk_pos < 0 || blk_pos + 32 > L) {
+                // slow exact check restricted to the bytes that belong to the sequence
+                bool bad = false;
+#pragma unroll 1
+                for (int j = 0; j < 32; j++) {
+                    const int pos = blk_pos + j;
+                    if (pos >= 0 && pos < L) bad = bad || !byte_is_acgt((wd[j >> 2] >> (8 * (j & 3))) & 0xFF);
+                }
+                if (bad) s.bad = 1;
+            }
+        }
+        s.F0[tid] = f0; s.F1[tid] = f1;
+        s.R0[tid] = ~__brev(f0); s.R1[tid] = ~__brev(f1);   // complement planes, first base in the LEAST significant bit
+        if (tid < 8) { s.F0[L0_NT + tid] = 0; s.F1[L0_NT + tid] = 0; s.R0[L0_NT + tid] = 0; s.R1[L0_NT + tid] = 0; }
+        __syncthreads();
+
+        // ---- phase 2: keys for blocks 2..255 ---------------------------------------------------------------
+        const int kb = tid - L0_CTX;  // key block index
+        if (tid >= L0_CTX) {
+            uint32_t strand = 0;
+            if (blk_live) {
+                const uint32_t a2 = s.F0[tid - 2], a1 = s.F0[tid - 1], a0 = f0;
+                const uint32_t b2 = s.F1[tid - 2], b1 = s.F1[tid - 1], b0 = f1;
+                // r-planes: Q = G >> (32*(tid-2) + 65 - k), so that rmmer(i) = (Q >> i) & kmask
+                const uint32_t cp = 65u - k, cs = cp >> 5, cb = cp & 31;
+                const int g = tid - 2 + (int)cs;
+                const uint32_t q00 = fsr(s.R0[g], s.R0[g + 1], cb), q01 = fsr(s.R0[g + 1], s.R0[g + 2], cb),
+                               q02 = fsr(s.R0[g + 2], s.R0[g + 3], cb);
+                const uint32_t q10 = fsr(s.R1[g], s.R1[g + 1], cb), q11 = fsr(s.R1[g + 1], s.R1[g + 2], cb),
+                               q12 = fsr(s.R1[g + 2], s.R1[g + 3], cb);
+                const int base = pidx(32 * kb);
+#pragma unroll 8
+                for (int i = 0; i < 32; i++) {
+                    const uint32_t sh = 31 - i;
+                    const uint32_t f0lo = fsr(a0, a1, sh) & mlo, f0hi = fsr(a1, a2, sh) & mhi;
+                    const uint32_t f1lo = fsr(b0, b1, sh) & mlo, f1hi = fsr(b1, b2, sh) & mhi;
+                    const uint32_t r0lo = fsr(q00, q01, i) & mlo, r0hi = fsr(q01, q02, i) & mhi;
+                    const uint32_t r1lo = fsr(q10, q11, i) & mlo, r1hi = fsr(q11, q12, i) & mhi;
+                    const uint64_t F0 = ((uint64_t)f0hi << 32) | f0lo, R0 = ((uint64_t)r0hi << 32) | r0lo;
+                    const bool rev = R0 < F0;                       // shmmrutils.rs:486 (plane 0 only)
+                    if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
+                        const int pos = blk_pos + i;
+                        if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) s.bad = 1;
+                    }
+                    const uint64_t u = rev ? R0 : F0;
+                    const uint64_t v = rev ? (((uint64_t)r1hi << 32) | r1lo) : (((uint64_t)f1hi << 32) | f1lo);
+                    const uint64_t h = u64hash(u) ^ u64hash(v ^ HASH_XOR);
+                    s.H[base + i] = (uint32_t)(h >> 24);
+                    s.X[base + i] = ((uint32_t)h << 8) | k;
+                    strand |= (rev ? 1u : 0u) << i;
+                }
+            }
+            s.strand[kb] = strand;
+        }
+        __syncthreads();
+
+        // ---- phase 3: window-minimum candidates on the 32-bit key prefix ----------------------------------
+        // valid window starts a (sequence positions): [k, Eb - w], Eb = min(L, L - w + k)
+        const int32_t Eb = min(L, L - (int32_t)w + (int32_t)k);
+        const int32_t a_lo = (int32_t)k, a_hi = Eb - (int32_t)w;            // inclusive bounds
+        uint32_t cand = 0;
+        {   // every thread runs this phase (threads 0,1 work on spare blocks) so that barriers stay uniform
+            const int base = pidx(32 * kb);
+            const int c = (int)w - 1, d = c >> 5, cr = c & 31;
+            // mask of window starts / positions of this block that are valid
+            uint32_t amask = 0, pmask = 0;
+            {
+                const int lo = max(a_lo - blk_pos, 0), hi = min(a_hi - blk_pos, 31);
+                if (lo <= hi) amask = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+                // positions that lie in some valid window and in this tile's output range
+                const int plo = max(max(a_lo, s.out_lo) - blk_pos, 0);
+                const int phi = min(min(a_hi + (int)w - 1, s.out_hi - 1) - blk_pos, 31);
+                if (plo <= phi) pmask = (0xFFFFFFFFu >> (31 - phi)) & (0xFFFFFFFFu << plo);
+            }
+            if (w > 32) {
+                // van Herk / Gil-Werman with one 32-position block per thread
+                uint32_t m[32];
+                {   // prefix minima -> smem, suffix minima -> registers
+                    uint32_t run = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int o = 0; o < 32; o++) { m[o] = s.H[base + o]; run = min(run, m[o]); s.P[base + o] = run; }
+                    run = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int o = 31; o >= 0; o--) { run = min(run, m[o]); m[o] = run; }
+                    s.bext[kb + L0_PADB] = run;
+                }
+                __syncthreads();
+                {
+                    uint32_t mid1 = 0xFFFFFFFFu;
+                    for (int b = 1; b < d; b++) mid1 = min(mid1, s.bext[kb + L0_PADB + b]);
+                    const uint32_t mid2 = min(mid1, s.bext[kb + L0_PADB + d]);
+                    const int pb = pidx(32 * (kb + d)) + cr;   // padded index of P_{kb+d}[cr]
+#pragma unroll
+                    for (int o = 0; o < 32; o++) {
+                        const bool carry = (o + cr) >= 32;
+                        const uint32_t far = s.P[pb + o + (carry ? 1 : 0)];
+                        const uint32_t mv = min3u(m[o], carry ? mid2 : mid1, far);
+                        m[o] = ((amask >> o) & 1u) ? mv : 0u;      // invalid windows contribute nothing to the max
+                    }
+                }
+                __syncthreads();
+                {   // suffix maxima of m -> smem; block max
+                    uint32_t run = 0;
+#pragma unroll
+                    for (int o = 31; o >= 0; o--) { run = max(run, m[o]); s.P[base + o] = run; }
+                    s.bext[kb + L0_PADB] = run;
+                }
+                __syncthreads();
+                {
+                    uint32_t mid1 = 0;
+                    for (int b = 1; b < d; b++) mid1 = max(mid1, s.bext[kb + L0_PADB - b]);
+                    const uint32_t mid2 = max(mid1, s.bext[kb + L0_PADB - d]);
+                    const int sb = pidx(32 * (kb - d)) - cr;
+                    uint32_t run = 0;
+#pragma unroll
+                    for (int o = 0; o < 32; o++) {
+                        const bool borrow = o < cr;
+                        run = max(run, m[o]);
+                        const uint32_t far = s.P[sb + o - (borrow ? 1 : 0)];
+                        const uint32_t M = max3u(run, borrow ? mid2 : mid1, far);
+                        cand |= (M == s.H[base + o] ? 1u : 0u) << o;
+                    }
+                }
+                cand &= pmask;
+            } else {
+                // small windows: direct evaluation (w <= 32); w is uniform, so no barrier mismatch with the branch above
+                if (tid < L0_CTX) pmask = 0;
+                for (int o = 0; o < 32; o++) {
+                    if (!((pmask >> o) & 1u)) continue;
+                    const int q = 32 * kb + o;
+                    const uint32_t hq = s.H[pidx(q)];
+                    // l / r = run of neighbours with H >= hq inside the valid position range
+                    const int pos = blk_pos + o;
+                    const int maxl = min((int)w - 1, pos - a_lo), maxr = min((int)w - 1, (a_hi + (int)w - 1) - pos);
+                    int l = 0, r = 0;
+                    while (l < maxl && s.H[pidx(q - l - 1)] >= hq) l++;
+                    while (r < maxr && s.H[pidx(q + r + 1)] >= hq) r++;
+                    if (l + r + 1 >= (int)w) cand |= 1u << o;
+                }
+            }
+            if (tid < L0_CTX) cand = 0;
+            s.cmask[kb + L0_PADB] = cand;
+        }
+        __syncthreads();
+
+        // ---- phase 4: resolve candidates that tie on the 32-bit prefix with another candidate (exact 64-bit) -
+        uint32_t sel = cand;
+        if (tid >= L0_CTX && cand) {
+            const int nbk = ((int)w + 30) >> 5;  // neighbour blocks that can hold a position closer than w
+            uint32_t rem = cand;
+            while (rem) {
+                const int o = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int q = 32 * kb + o;
+                const uint32_t hq = s.H[pidx(q)];
+                bool tie = false;
+                for (int b = -nbk; b <= nbk && !tie; b++) {
+                    uint32_t cm = s.cmask[kb + L0_PADB + b];
+                    if (b == 0) cm &= ~(1u << o);
+                    while (cm) {
+                        const int o2 = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        const int q2 = 32 * (kb + b) + o2;
+                        if (abs(q2 - q) < (int)w && s.H[pidx(q2)] == hq) { tie = true; break; }
+                    }
+                }
+                if (tie) {
+                    const int pos = blk_pos + o;
+                    const int maxl = min((int)w - 1, pos - a_lo), maxr = min((int)w - 1, (a_hi + (int)w - 1) - pos);
+                    int l = 0, r = 0;
+                    while (l < maxl && !key_lt(s, q - l - 1, q)) l++;
+                    while (r < maxr && !key_lt(s, q + r + 1, q)) r++;
+                    if (l + r + 1 < (int)w) sel &= ~(1u << o);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid >= L0_CTX) s.cmask[kb + L0_PADB] = sel;
+        __syncthreads();
+
+        // ---- phase 5: tail replay (last tile of the sequence; shmmrutils.rs:503-515 with rule (2) disabled) --
+        if (s.is_last && tid == 0 && (int32_t)w > (int32_t)k && L > (int32_t)k) {
+            // q = last selected position below Eb (selections of the whole sequence, not only this tile's range)
+            const int32_t t_lo = max(Eb, (int32_t)k);
+            int32_t q = -1;
+            {
+                int32_t hi_pos = min(Eb, L) - 1;
+                for (int32_t pos = hi_pos; pos >= a_lo && pos >= Eb - (int32_t)w; pos--) {
+                    const int qq = pos - keys_start;
+                    if (qq < 0) break;
+                    // selection status of pos: recompute exactly (positions before out_lo belong to the previous tile)
+                    const int maxl = min((int)w - 1, pos - a_lo), maxr = min((int)w - 1, (a_hi + (int)w - 1) - pos);
+                    if (maxr < 0) continue;
+                    int l = 0, r = 0;
+                    while (l < maxl && !key_lt(s, qq - l - 1, qq)) l++;
+                    while (r < maxr && !key_lt(s, qq + r + 1, qq)) r++;
+                    if (l + r + 1 >= (int)w) { q = pos; break; }
+                }
+            }
+            uint32_t n = 0;
+            for (int32_t pos = t_lo; pos < L; pos++) {
+                const bool fire = (q < 0) ? (pos == (int32_t)(k + w - 1)) : (pos == q + (int32_t)w);
+                if (!fire) continue;
+                const int qe = pos - keys_start, qa = qe - (int)w + 1;
+                int best = qa;
+                for (int j = qa + 1; j <= qe; j++) if (key_lt(s, j, best)) best = j;
+                for (int j = qa; j <= qe; j++) {
+                    if (!key_lt(s, best, j)) {  // x[j] == min
+                        const int pj = j + keys_start;
+                        if (n < L0_TAILCAP) {
+                            pgr_mm128 mm;
+                            mm.x = ((uint64_t)s.H[pidx(j)] << 32) | s.X[pidx(j)];
+                            mm.y = ((uint64_t)s.seq_id << 32) | ((uint64_t)(uint32_t)pj << 1) |
+                                   ((s.strand[j >> 5] >> (j & 31)) & 1u);
+                            s.tail[n] = mm;
+                        }
+                        n++;
+                        q = pj;
+                    }
+                }
+            }
+            s.tail_n = n;
+        }
+
+        // ---- phase 6: ordered compaction into the CTA's chunk ----------------------------------------------
+        const uint32_t cnt = (tid >= L0_CTX) ? __popc(sel) : 0;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, dlt);
+            if (lane >= dlt) incl += v;
+        }
+        if (lane == 31) s.wsum[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < L0_NT / 32; i++) { const uint32_t v = s.wsum[i]; if (i < warp) wbase += v; total += v; }
+        const uint32_t tail_n = s.tail_n;
+        if (cnt) {
+            uint64_t dst = running + wbase + incl - cnt;
+            uint32_t rem = sel;
+            const uint32_t strand = s.strand[kb];
+            while (rem) {
+                const int o = __ffs(rem) - 1;
+                rem &= rem - 1;
+                if (dst < p.chunk_cap) {
+                    const int q = 32 * kb + o;
+                    pgr_mm128 mm;
+                    mm.x = ((uint64_t)s.H[pidx(q)] << 32) | s.X[pidx(q)];
+                    mm.y = ((uint64_t)s.seq_id << 32) | ((uint64_t)(uint32_t)(blk_pos + o) << 1) | ((strand >> o) & 1u);
+                    chunk[dst] = mm;
+                }
+                dst++;
+            }
+        }
+        for (uint32_t i = tid; i < min(tail_n, (uint32_t)L0_TAILCAP); i += L0_NT) {
+            const uint64_t dst = running + total + i;
+            if (dst < p.chunk_cap) chunk[dst] = s.tail[i];
+        }
+        if (tid == 0) {
+            atomicAdd(&p.seq_count[s.seq_id], total + tail_n);
+            if (s.bad || tail_n > L0_TAILCAP) atomicOr(&p.seq_flag[s.seq_id], 1u);
+        }
+        running += total + tail_n;
+    }
+    if (tid == 0) p.chunk_count[blockIdx.x] = running;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exact sequential restatement of the level-0 loop (shmmrutils.rs:440-530) for flagged sequences: one thread per
+// sequence, ring buffer in local memory.  mode 0 = count only, mode 1 = write at dst[seq_l0_off[s] + i].
+struct ReplayParams {
+    const uint8_t *seq; const uint64_t *off; const uint32_t *len;
+    const uint32_t *list;       // [n_list] sequence ordinals to replay
+    uint32_t n_list;
+    uint32_t w, k;
+    uint32_t *count;            // [n_seq] out (mode 0)
+    const uint64_t *dst_off;    // [n_seq] (mode 1)
+    pgr_mm128 *dst;
+};
+
+__device__ __forceinline__ uint32_t base_code(uint32_t c) {  // LUT of shmmrutils.rs:426-436
+    if (c < 4) return c;
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
+
+template <int MODE>
+__global__ void replay_l0_kernel(const ReplayParams p) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= p.n_list) return;
+    const uint32_t sid = p.list[li];
+    const uint8_t *sq = p.seq + p.off[sid];
+    const uint64_t L = p.len[sid];
+    const uint32_t w = p.w, k = p.k;
+    const uint64_t mask = ~0ull >> (64 - k);
+    const uint32_t shift = k - 1;
+    uint64_t rx[128]; uint32_t ry[128];   // ring buffer (w <= 128): x and (pos<<1|strand)
+    for (uint32_t i = 0; i < w; i++) { rx[i] = ~0ull; ry[i] = ~0u; }
+    uint32_t r_start = 0, r_end = 0, r_len = 0;
+    uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;
+    uint64_t min_x = ~0ull, mdist = 0, n_out = 0;
+    pgr_mm128 *dst = MODE ? p.dst + p.dst_off[sid] : nullptr;
+    const uint64_t rule2_end = L - (uint64_t)w + (uint64_t)k;  // wrapping, shmmrutils.rs:518
+    for (uint64_t pos = 0; pos < L; pos++) {
+        const uint32_t c = base_code(sq[pos]);
+        if (c < 4) {
+            f0 = ((f0 << 1) | (c & 1)) & mask;
+            f1 = ((f1 << 1) | (c >> 1)) & mask;
+            const uint64_t rc = 3 ^ c;
+            r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask;
+            r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
+        }
+        if (f0 == r0 && f1 == r1) continue;
+        if (pos < k) continue;
+        const bool rev = r0 < f0;
+        const uint64_t h = rev ? (u64hash(r0) ^ u64hash(r1 ^ HASH_XOR)) : (u64hash(f0) ^ u64hash(f1 ^ HASH_XOR));
+        const uint64_t mx = (h << 8) | k;
+        const uint32_t my = ((uint32_t)pos << 1) | (rev ? 1u : 0u);
+        rx[r_end] = mx; ry[r_end] = my;
+        r_end = (r_end + 1) % w;
+        if (r_len < w) r_len++; else r_start = (r_start + 1) % w;
+        if (mdist == (uint64_t)(w - 1)) {
+            uint64_t mn = ~0ull;
+            for (uint32_t i = 0; i < r_len; i++) if (rx[i] < mn) mn = rx[i];
+            uint32_t last_y = 0;
+            for (uint32_t i = 0; i < w; i++) {
+                const uint32_t sl = (r_start + i) % w;
+                if (rx[sl] == mn) {
+                    if (MODE) { pgr_mm128 mm; mm.x = rx[sl]; mm.y = ((uint64_t)sid << 32) | ry[sl]; dst[n_out] = mm; }
+                    n_out++;
+                    last_y = ry[sl];
+                }
+            }
+            min_x = mn;
+            mdist = pos - (uint64_t)(last_y >> 1);
+            continue;
+        } else if (mx <= min_x && pos >= (uint64_t)(w + k) && pos < rule2_end && pos < L) {
+            if (MODE) { pgr_mm128 mm; mm.x = mx; mm.y = ((uint64_t)sid << 32) | my; dst[n_out] = mm; }
+            n_out++;
+            min_x = mx;
+            mdist = 0;
+            continue;
+        }
+        mdist++;
+    }
+    if (!MODE) p.count[sid] = (uint32_t)n_out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// chunked arena -> flat level-0 list.  Entry i of chunk c has logical (fast-path) index chunk_prefix[c] + i; it goes
+// to flat[seq_dst[s] + (logical - seq_fast[s])] unless its sequence was flagged for replay.
+struct GatherParams {
+    const pgr_mm128 *arena; uint64_t chunk_cap;
+    const uint64_t *chunk_prefix;   // [grid+1]
+    uint32_t n_chunks;
+    const uint64_t *seq_fast;       // [n_seq] exclusive scan of fast-path counts
+    const uint64_t *seq_dst;        // [n_seq+1] exclusive scan of final counts
+    const uint32_t *seq_flag;
+    pgr_mm128 *flat;
+};
+
+__global__ void gather_l0_kernel(const GatherParams p) {
+    const uint32_t c = blockIdx.y;
+    const uint64_t n = p.chunk_prefix[c + 1] - p.chunk_prefix[c];
+    const uint64_t base = p.chunk_prefix[c];
+    const pgr_mm128 *src = p.arena + (uint64_t)c * p.chunk_cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const pgr_mm128 mm = src[i];
+        const uint32_t sid = (uint32_t)(mm.y >> 32);
+        if (p.seq_flag[sid]) continue;
+        p.flat[p.seq_dst[sid] + (base + i - p.seq_fast[sid])] = mm;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Levels 1 and 2 (reduce_shmmr, shmmrutils.rs:359-415) and the min_span filter (:536-555) on the flat list.
+// y>>32 holds the sequence ordinal; seq_off[] are the list offsets of each sequence.
+// flag kinds: 0 = window-minimum rule with window r (padding = virtual MAX sentinels), 1 = min_span filter.
+struct LevelParams {
+    const pgr_mm128 *in; uint64_t n_in;
+    const uint64_t *seq_off_in;  // [n_seq+1]
+    uint32_t n_seq;
+    uint32_t r, padding, min_span;
+    uint8_t *flags;              // [n_in]
+    uint32_t *block_sum;         // [n_blocks]
+    uint64_t *block_prefix;      // [n_blocks+1]
+    pgr_mm128 *out;
+    uint64_t *seq_off_out;       // [n_seq+1]
+    const uint32_t *rid;         // final pass only: ordinal -> caller's rid
+    uint32_t patch_rid;
+};
+
+constexpr int LV_NT = 256, LV_PER = 8, LV_BLK = LV_NT * LV_PER;
+
+template <int KIND>
+__global__ void __launch_bounds__(LV_NT) level_flags_kernel(const LevelParams p) {
+    __shared__ uint32_t wsum[LV_NT / 32];
+    const uint64_t i0 = (uint64_t)blockIdx.x * LV_BLK;
+    uint32_t cnt = 0;
+    for (int j = 0; j < LV_PER; j++) {
+        const uint64_t i = i0 + (uint64_t)j * LV_NT + threadIdx.x;
+        if (i >= p.n_in) break;
+        const pgr_mm128 me = p.in[i];
+        const uint32_t sid = (uint32_t)(me.y >> 32);
+        const uint64_t b = p.seq_off_in[sid], e = p.seq_off_in[sid + 1];
+        bool keep;
+        if (KIND == 0) {
+            const uint32_t r = p.r;
+            uint32_t l = 0, rr = 0;
+            for (uint32_t d = 1; d < r; d++) {
+                if (i < b + d) { if (p.padding) l = r - 1; break; }
+                if (p.in[i - d].x < me.x) break;
+                l = d;
+            }
+            for (uint32_t d = 1; d < r; d++) {
+                if (i + d >= e) { if (p.padding) rr = r - 1; break; }
+                if (p.in[i + d].x < me.x) break;
+                rr = d;
+            }
+            keep = (l + rr + 1 >= r);
+        } else {
+            if (i == b || i + 1 == e) {
+                keep = true;
+            } else {
+                const pgr_mm128 pv = p.in[i - 1], nx = p.in[i + 1];
+                const uint32_t pp = (uint32_t)(pv.y & 0xFFFFFFFFu) >> 1, cp = (uint32_t)(me.y & 0xFFFFFFFFu) >> 1,
+                               np = (uint32_t)(nx.y & 0xFFFFFFFFu) >> 1;
+                keep = (uint32_t)(cp - pp) > p.min_span && (uint32_t)(np - cp) > p.min_span && pv.x != me.x && me.x != nx.x;
+            }
+        }
+        p.flags[i] = keep ? 1 : 0;
+        cnt += keep ? 1u : 0u;
+    }
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xFFFFFFFFu, cnt, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < LV_NT / 32; i++) t += wsum[i];
+        p.block_sum[blockIdx.x] = t;
+    }
+}
+
+// single-CTA exclusive scan of block sums (n_blocks is small: n_in / 2048)
+__global__ void __launch_bounds__(1024) block_scan_kernel(const uint32_t *block_sum, uint64_t *block_prefix, uint32_t n_blocks) {
+    __shared__ uint64_t wtot[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = (i < n_blocks) ? block_sum[i] : 0;
+        uint64_t incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((threadIdx.x & 31) >= d) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint64_t wb = 0;
+        for (uint32_t j = 0; j < (threadIdx.x >> 5); j++) wb += wtot[j];
+        const uint64_t c0 = carry;
+        if (i < n_blocks) block_prefix[i] = c0 + wb + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c0 + wb + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_prefix[n_blocks] = carry;
+}
+
+__global__ void __launch_bounds__(LV_NT) level_scatter_kernel(const LevelParams p) {
+    __shared__ uint32_t excl[LV_BLK + 1];
+    __shared__ uint32_t wsum[LV_NT / 32];
+    const uint64_t i0 = (uint64_t)blockIdx.x * LV_BLK;
+    const uint64_t bp = p.block_prefix[blockIdx.x];
+    // thread t owns elements i0 + t*LV_PER .. +LV_PER (contiguous, so ranks are in order)
+    uint8_t f[LV_PER];
+    uint32_t cnt = 0;
+    const uint64_t my0 = i0 + (uint64_t)threadIdx.x * LV_PER;
+#pragma unroll
+    for (int j = 0; j < LV_PER; j++) {
+        f[j] = (my0 + j < p.n_in) ? p.flags[my0 + j] : 0;
+        cnt += f[j];
+    }
+    uint32_t incl = cnt;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((threadIdx.x & 31) >= d) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t wb = 0;
+    for (uint32_t j = 0; j < (threadIdx.x >> 5); j++) wb += wsum[j];
+    uint32_t rank = wb + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < LV_PER; j++) {
+        excl[threadIdx.x * LV_PER + j] = rank;
+        if (f[j]) {
+            pgr_mm128 mm = p.in[my0 + j];
+            if (p.patch_rid) mm.y = ((uint64_t)p.rid[(uint32_t)(mm.y >> 32)] << 32) | (mm.y & 0xFFFFFFFFull);
+            p.out[bp + rank] = mm;
+            rank++;
+        }
+    }
+    if (threadIdx.x == LV_NT - 1) excl[LV_BLK] = rank;
+    __syncthreads();
+    // sequences whose first input element lies in this block get their output offset from the local scan
+    const uint64_t i1 = min(i0 + (uint64_t)LV_BLK, p.n_in);
+    const bool last_block = (i1 == p.n_in);
+    // first sid with seq_off_in[sid] >= i0
+    uint32_t lo = 0, hi = p.n_seq + 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.seq_off_in[mid] < i0) lo = mid + 1; else hi = mid;
+    }
+    for (uint32_t sid = lo + threadIdx.x; sid <= p.n_seq; sid += LV_NT) {
+        const uint64_t b = p.seq_off_in[sid];
+        if (b < i1 || (last_block && b == i1)) p.seq_off_out[sid] = bp + excl[b - i0]; else break;
+    }
+}
+
+// sketch mode (shmmrutils.rs:558-630): every position whose full 64-bit hash is below the threshold is kept.
+// One thread per 32-base block, rolling over its positions (k-mer windows from the plane words as in l0_kernel is
+// the fast design; sketch mode is not on the benchmarked path, so this kernel favours simplicity: two passes,
+// count then write, exact for every input including invalid bytes and palindromes).
+struct SketchParams {
+    const uint8_t *seq; const uint64_t *off; const uint32_t *len;
+    const uint64_t *blk_prefix;   // [n_seq+1] cumulative number of 1024-base segments
+    uint32_t n_seq; uint32_t k, r;
+    uint32_t *seg_count;          // [n_segs]
+    const uint64_t *seg_off;      // [n_segs+1] (pass 2)
+    pgr_mm128 *out;
+};
+
+constexpr int SK_SEG = 1024;
+
+template <int MODE>
+__global__ void sketch_kernel(const SketchParams p, uint64_t n_segs) {
+    const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n_segs) return;
+    uint32_t lo = 0, hi = p.n_seq;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (p.blk_prefix[mid] <= seg) lo = mid; else hi = mid; }
+    const uint32_t sid = lo;
+    const uint64_t L = p.len[sid];
+    const uint8_t *sq = p.seq + p.off[sid];
+    const uint64_t s0 = (seg - p.blk_prefix[sid]) * SK_SEG, s1 = min(L, s0 + SK_SEG);
+    const uint32_t k = p.k;
+    const uint64_t mask = ~0ull >> (64 - k);
+    const uint32_t shift = k - 1;
+    const uint64_t thr = (~0ull >> 4) >> p.r;
+    // registers at s0: replay the last k valid bases before s0
+    uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;
+    {
+        uint64_t b = s0; uint32_t got = 0;
+        while (b > 0 && got < k) { b--; if (base_code(sq[b]) < 4) got++; }
+        for (uint64_t q = b; q < s0; q++) {
+            const uint32_t c = base_code(sq[q]);
+            if (c < 4) {
+                f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
+                const uint64_t rc = 3 ^ c;
+                r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
+            }
+        }
+    }
+    uint64_t n = 0;
+    pgr_mm128 *dst = MODE ? p.out + p.seg_off[seg] : nullptr;
+    for (uint64_t pos = s0; pos < s1; pos++) {
+        const uint32_t c = base_code(sq[pos]);
+        if (c < 4) {
+            f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
+            const uint64_t rc = 3 ^ c;
+            r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
+        }
+        if (f0 == r0 && f1 == r1) continue;
+        if (pos < k) continue;
+        const bool rev = r0 < f0;
+        const uint64_t h = rev ? (u64hash(r0) ^ u64hash(r1 ^ HASH_XOR)) : (u64hash(f0) ^ u64hash(f1 ^ HASH_XOR));
+        if (h < thr) {
+            if (MODE) {
+                pgr_mm128 mm;
+                mm.x = (h << 8) | k;
+                mm.y = ((uint64_t)sid << 32) | ((uint64_t)(uint32_t)pos << 1) | (rev ? 1u : 0u);
+                dst[n] = mm;
+            }
+            n++;
+        }
+    }
+    if (!MODE) p.seg_count[seg] = (uint32_t)n;
+}
+
+}  // namespace pgr

@@ -1,0 +1,52 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports every symbol include/pgr_b200.h
+declares, and compute entry points fail loudly (no CPU fallback) when no device is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pgr_tk_b200 as pg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "pgr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pgr_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(pg.library_path()):
+        pg.build_library()
+    L = ctypes.CDLL(pg.library_path())
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_pod_layouts():
+    assert pg.MM128.itemsize == 16 and pg.SIG.itemsize == 20 and pg.QPAIR.itemsize == 32
+    assert pg.HITPAIR.itemsize == 20 and pg.ADJ.itemsize == 40
+    assert ctypes.sizeof(pg.ShmmrSpec) == 20
+
+
+def test_no_cpu_fallback_without_device():
+    if pg.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pg.PgrError) as e:
+        pg.sequence_to_shmmrs(0, b"ACGT" * 100, pg.ShmmrSpec())
+    assert e.value.code == -3
+    with pytest.raises(pg.PgrError):
+        pg.Ctx(0)
+
+
+def test_spec_asserts_become_error_codes():
+    # shmmrutils.rs:443-445 asserts -> PGR_E_SPEC before any device work
+    for bad in (pg.ShmmrSpec(80, 57, 4, 64), pg.ShmmrSpec(129, 56, 4, 64), pg.ShmmrSpec(80, 56, 0, 64), pg.ShmmrSpec(80, 56, 13, 64)):
+        with pytest.raises(pg.PgrError) as e:
+            pg.sequence_to_shmmrs(0, b"ACGT" * 100, bad)
+        assert e.value.code == -2

@@ -1,0 +1,137 @@
+"""GPU parity: sequence_to_shmmrs through the C ABI vs the CPU oracle (bit-exact MM128 lists)."""
+import os
+
+import numpy as np
+import pytest
+
+import orc
+import pgr_tk_b200 as pg
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def ospec(s):
+    return orc.mkspec(s.w, s.k, s.r, s.min_span, bool(s.sketch))
+
+
+def rand_seq(rng, L, alphabet=b"ACGT"):
+    a = np.frombuffer(alphabet, dtype=np.uint8)
+    return a[rng.integers(0, len(a), size=L)].tobytes()
+
+
+def assert_batch_equal(seqs, spec, padding=False, rids=None):
+    rids = list(range(len(seqs))) if rids is None else rids
+    got, goff = pg.get_shmmrs_from_seqs(rids, seqs, spec, padding)
+    exp, eoff = orc.shmmrs_batch(rids, seqs, ospec(spec), padding, nthreads=8)
+    assert list(goff) == list(eoff), (spec.w, spec.k, spec.r, spec.min_span, padding)
+    assert np.array_equal(got["x"], exp["x"])
+    assert np.array_equal(got["y"], exp["y"])
+    return len(got)
+
+
+def test_fixture_sequences_default_spec():
+    recs = orc.parse_fasta(os.path.join(GOLDEN, "test_seqs.fa"))
+    n = assert_batch_equal([s for _, s in recs], pg.ShmmrSpec(80, 56, 4, 64))
+    assert n == 886
+
+
+def test_fixture_sequences_other_specs():
+    recs = orc.parse_fasta(os.path.join(GOLDEN, "test_seqs.fa"))
+    seqs = [s for _, s in recs]
+    for w, k, r, ms in [(48, 56, 4, 12), (24, 24, 12, 24), (31, 31, 1, 0), (80, 56, 1, 0), (128, 56, 2, 10), (33, 16, 3, 5), (97, 41, 5, 0)]:
+        assert_batch_equal(seqs, pg.ShmmrSpec(w, k, r, ms))
+
+
+def test_single_sequence_api_and_rid():
+    recs = orc.parse_fasta(os.path.join(GOLDEN, "test_seqs.fa"))
+    spec = pg.ShmmrSpec()
+    got = pg.sequence_to_shmmrs(1234, recs[3][1], spec)
+    exp = orc.sequence_to_shmmrs(1234, recs[3][1], ospec(spec))
+    assert np.array_equal(got, exp)
+    assert np.all((got["y"] >> 32) == 1234)
+
+
+def test_boundary_known_answer_padding():
+    recs = orc.parse_fasta(os.path.join(GOLDEN, "boundary_seqs.fa"))
+    spec = pg.ShmmrSpec(24, 24, 12, 24)
+    for _, s in recs:
+        got = pg.sequence_to_shmmrs(0, s, spec, padding=True)
+        assert len(got) == 2
+        assert np.array_equal(got, orc.sequence_to_shmmrs(0, s, ospec(spec), True))
+
+
+def test_rc_match_sketch():
+    recs = orc.parse_fasta(os.path.join(GOLDEN, "test_rev.fa"))
+    for sketch in (True, False):
+        spec = pg.ShmmrSpec(80, 56, 4, 64, sketch)
+        s0 = pg.sequence_to_shmmrs(0, recs[0][1], spec)
+        s1 = pg.sequence_to_shmmrs(0, recs[1][1], spec)
+        assert len(s0) > 0
+        assert list(s0["x"] >> 8) == list((s1["x"] >> 8)[::-1])
+        assert np.array_equal(s0, orc.sequence_to_shmmrs(0, recs[0][1], ospec(spec)))
+
+
+def test_long_random_contigs_multi_tile():
+    rng = np.random.default_rng(1)
+    seqs = [rand_seq(rng, L) for L in (1_000_000, 7936, 7937, 8128, 15872, 15873, 200_003, 31, 56, 57, 135, 136, 137, 0, 1)]
+    for spec in (pg.ShmmrSpec(80, 56, 4, 64), pg.ShmmrSpec(48, 56, 4, 12)):
+        assert_batch_equal(seqs, spec)
+
+
+def test_random_specs_edge_lengths():
+    rng = np.random.default_rng(7)
+    ks = [5, 7, 8, 11, 16, 24, 31, 56]
+    ws = [1, 2, 3, 8, 24, 32, 33, 48, 64, 65, 80, 96, 97, 128]
+    for it in range(40):
+        k = ks[rng.integers(len(ks))]
+        w = ws[rng.integers(len(ws))]
+        r = int(rng.integers(1, 13))
+        ms = int([0, 4, 12, 64][rng.integers(4)])
+        edge = [0, 1, k - 1, k, k + 1, w + k - 1, w + k, w + k + 1, 2 * w + k, 3 * w + k, 3 * w + 31, 3 * w + 33]
+        seqs = [rand_seq(rng, L) for L in edge] + [rand_seq(rng, int(rng.integers(100, 30000))) for _ in range(6)]
+        assert_batch_equal(seqs, pg.ShmmrSpec(w, k, r, ms), padding=bool(rng.integers(2)))
+
+
+def test_low_complexity_and_ties():
+    rng = np.random.default_rng(11)
+    seqs = [b"A" * 5000, b"AC" * 4000, b"ACG" * 3000, rand_seq(rng, 20000, b"AC"),
+            (rand_seq(rng, 37) * 400), rand_seq(rng, 3000) + b"T" * 3000 + rand_seq(rng, 3000)]
+    for w, k, r, ms in [(80, 56, 4, 64), (48, 56, 4, 12), (80, 31, 4, 0), (33, 7, 2, 0), (16, 5, 3, 0)]:
+        assert_batch_equal(seqs, pg.ShmmrSpec(w, k, r, ms))
+
+
+def test_invalid_bytes_and_palindromes_take_replay_path():
+    rng = np.random.default_rng(13)
+    s1 = bytearray(rand_seq(rng, 50000))
+    s1[20000:20100] = b"N" * 100
+    s2 = rand_seq(rng, 10000) + b"AT" * 60 + rand_seq(rng, 10000)   # (AT)n >= 56: reverse-complement palindromes
+    s3 = rand_seq(rng, 30000, b"ACGTacgtNn")
+    s4 = bytes([0, 1, 2, 3]) * 2000
+    seqs = [bytes(s1), s2, s3, s4, rand_seq(rng, 40000)]
+    for spec in (pg.ShmmrSpec(80, 56, 4, 64), pg.ShmmrSpec(24, 24, 12, 24), pg.ShmmrSpec(80, 56, 4, 64, True)):
+        assert_batch_equal(seqs, spec)
+    ctx = pg.Ctx(0)
+    ctx.upload(seqs)
+    ctx.shmmrs(pg.ShmmrSpec())
+    assert ctx.counters()[2] == 4  # four sequences were replayed, the clean one was not
+    ctx.close()
+
+
+def test_sketch_mode_random():
+    rng = np.random.default_rng(17)
+    seqs = [rand_seq(rng, int(L)) for L in (0, 10, 1023, 1024, 1025, 50000, 3000)] + [rand_seq(rng, 5000, b"ACGTN")]
+    for k, r, ms in [(56, 4, 64), (16, 1, 0), (24, 2, 12)]:
+        assert_batch_equal(seqs, pg.ShmmrSpec(80, k, r, ms, True))
+
+
+def test_lowercase_is_fast_path():
+    rng = np.random.default_rng(19)
+    s = rand_seq(rng, 60000, b"ACGTacgt")
+    ctx = pg.Ctx(0)
+    ctx.upload([s])
+    ctx.shmmrs(pg.ShmmrSpec())
+    got, off = ctx.shmmrs_download()
+    assert ctx.counters()[2] == 0
+    assert np.array_equal(got, orc.sequence_to_shmmrs(0, s, orc.mkspec()))
+    ctx.close()
