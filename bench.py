@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — Gbases/s SHIMMER-indexed (BASELINE.json metric) on N B200s of one node.
+
+Workload (BASELINE.json configs[1]): sequence_to_shmmrs on 1000 synthetic 5 Mb contigs (uniform ACGT), spec
+w=80 k=56 r=4 min_span=64, per GPU (weak scaling: every rank indexes its own 1000 contigs; no data-path collective).
+A step = one pass of the hot path over that batch.
+
+  value : device-resident throughput (inputs already in HBM), CUDA events on the launch stream, max over ranks
+  e2e   : the same work through the reference-facing C ABI call pgr_b200_shmmrs_batch with HOST (pinned) buffers:
+          H2D of the 5 GB of bases and D2H of the MM128 result inside the timed region
+  roofline : dominant kernel (l0_minimizers), algorithmic bytes (1 B/base + 16 B/shimmer) / its CUDA-event time
+  cpu_baseline : the C++ oracle (restatement of the reference's rayon path) on the box's host cores, bounded sample
+
+`--impl reference` times the oracle alone (all host threads), same metric/config, on a bounded sample per step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+N_CONTIGS = 1000
+CONTIG_LEN = 5_000_000
+SPEC = (80, 56, 4, 64)
+SLACK = 16384
+ALGO_BYTES_PER_BASE_IN = 1.0
+ALGO_BYTES_PER_SHMMR = 16.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--contigs", type=int, default=N_CONTIGS, help="contigs per GPU (default = the BASELINE config)")
+    ap.add_argument("--contig-len", type=int, default=CONTIG_LEN)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def synth_contig(seed, length):
+    rng = np.random.default_rng(seed)
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=length, dtype=np.uint8)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """the reference arm: the C++ oracle (port of the reference's rayon path) on all host cores, bounded sample"""
+    if rank != 0:
+        return
+    import orc
+    cores = host_cores()
+    # bounded sample of the workload: enough contigs for ~1-2 s of wall time per step on this box
+    n_sample = min(args.contigs, max(2 * cores, 16))
+    seqs = [synth_contig(1000 + i, args.contig_len) for i in range(n_sample)]
+    spec = orc.mkspec(*SPEC)
+    rids = list(range(n_sample))
+    bases = n_sample * args.contig_len
+    for _ in range(args.warmup):
+        orc.shmmrs_batch(rids[:cores], seqs[:cores], spec, False, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.shmmrs_batch(rids, seqs, spec, False, nthreads=cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = bases / dt / 1e9
+    sample = "%d of %d contigs x %d bases per step, one sequence per thread (seq_db.rs:461)" % (n_sample, args.contigs, args.contig_len)
+    line = {
+        "impl": "reference", "metric": "Gbases/sec SHIMMER-indexed", "value": val, "unit": "Gbases/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "sequence_to_shmmrs on %d synthetic %d-base contigs per GPU, w=80 k=56 r=4 min_span=64" % (args.contigs, args.contig_len),
+                   "note": "C++ restatement of the reference's rayon CPU path (the Rust reference cannot be built in this image)"},
+        "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import pgr_tk_b200 as pg
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if pg.device_count() <= local_rank:
+        raise SystemExit("no CUDA device for rank %d: this benchmark has no CPU fallback" % rank)
+    pg.set_default_device(local_rank)
+
+    n_contigs, clen = args.contigs, args.contig_len
+    assert clen % 32 == 0
+    bases = n_contigs * clen
+    spec = pg.ShmmrSpec(*SPEC)
+
+    # ---- synthetic workload, generated on the device (seeded per rank), laid out as the library's sequence store ----
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    store = torch.zeros(SLACK + bases + SLACK, dtype=torch.uint8, device=dev)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    chunk = 250_000_000
+    for o in range(0, bases, chunk):
+        m = min(chunk, bases - o)
+        idx = torch.randint(0, 4, (m,), generator=g, device=dev, dtype=torch.uint8)
+        store[SLACK + o: SLACK + o + m] = lut[idx.to(torch.int64)]
+        del idx
+    torch.cuda.synchronize()
+    offs = (SLACK + np.arange(n_contigs, dtype=np.uint64) * np.uint64(clen)).astype(np.uint64)
+    lens = np.full(n_contigs, clen, dtype=np.uint64)
+
+    ctx = pg.Ctx(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_device_seqs(store.data_ptr(), offs, lens)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------------------
+    n_shmmrs = 0
+    for _ in range(args.warmup):
+        n_shmmrs = ctx.shmmrs(spec)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0_ms, stage_ms, launches = [], {}, 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        n_shmmrs = ctx.shmmrs(spec)
+        launches += ctx.counters()[0]
+        for nm, ms in ctx.timings():
+            stage_ms.setdefault(nm, []).append(ms)
+            if nm == "l0_minimizers":
+                l0_ms.append(ms)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = world * bases / (dev_ms_max * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    l0 = statistics.mean(l0_ms) if l0_ms else float("nan")
+    algo_bytes = ALGO_BYTES_PER_BASE_IN * bases + ALGO_BYTES_PER_SHMMR * n_shmmrs
+    achieved = algo_bytes / (l0 * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "l0_kernel<80,56> (l0_minimizers)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": l0,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "note": "integer-issue bound, not HBM bound (SURVEY §8d): ~100 int32 ops per base; see DESIGN.md and profiles/"}
+    traffic_file = os.path.join(ROOT, "profiles", "l0_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            tj = json.load(open(traffic_file))
+            roofline["traffic"] = tj.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = tj.get("source")
+        except Exception:
+            pass
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        L = pg.lib()
+        hb = pg.host_alloc(bases)
+        hb_t = torch.from_numpy(hb.array)
+        hb_t.copy_(store[SLACK: SLACK + bases])   # same bytes as the device-resident run
+        torch.cuda.synchronize()
+        ptrs = (C.c_void_p * n_contigs)(*[hb.ptr + i * clen for i in range(n_contigs)])
+        clens = (C.c_size_t * n_contigs)(*([clen] * n_contigs))
+        rids = np.arange(n_contigs, dtype=np.uint32)
+        offs_out = np.zeros(n_contigs + 1, dtype=np.uint64)
+        out = C.c_void_p()
+        times = []
+        d2h = 0
+        for it in range(2 + args.steps):
+            barrier()
+            t0 = time.perf_counter()
+            rc = L.pgr_b200_shmmrs_batch(n_contigs, rids.ctypes.data, ptrs, clens, C.byref(spec), 0, C.byref(out), offs_out.ctypes.data)
+            t1 = time.perf_counter()
+            if rc != 0:
+                raise SystemExit("pgr_b200_shmmrs_batch failed: %s" % L.pgr_b200_last_error().decode())
+            assert int(offs_out[-1]) == n_shmmrs, (int(offs_out[-1]), n_shmmrs)
+            d2h = int(offs_out[-1]) * 16 + (n_contigs + 1) * 8
+            L.pgr_b200_free(out)
+            if it >= 2:
+                times.append(t1 - t0)
+        e_ms = statistics.mean(times) * 1e3
+        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te.item())
+        e2e = {"value": world * bases / (e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": bases, "d2h_bytes_per_step": d2h,
+               "api": "pgr_b200_shmmrs_batch (host pointers in pinned memory -> host MM128 array)"}
+        hb.free()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import orc
+        cores = host_cores()
+        n_sample = min(n_contigs, max(2 * cores, 16))
+        sample = store[SLACK: SLACK + n_sample * clen].cpu().numpy()
+        seqs = [sample[i * clen:(i + 1) * clen] for i in range(n_sample)]
+        ospec = orc.mkspec(*SPEC)
+        orc.shmmrs_batch(list(range(min(cores, n_sample))), seqs[:cores], ospec, False, nthreads=cores)  # warm
+        t0 = time.perf_counter()
+        cpu_out, cpu_off = orc.shmmrs_batch(list(range(n_sample)), seqs, ospec, False, nthreads=cores)
+        dt = time.perf_counter() - t0
+        # and it doubles as a full-size parity spot check of the resident result
+        got, goff = ctx.shmmrs_download()
+        k = int(goff[n_sample])
+        assert k == int(cpu_off[-1]) and np.array_equal(got[:k], cpu_out), "GPU result differs from the oracle on the CPU sample"
+        cpu = {"value": n_sample * clen / dt / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
+               "sample": "first %d of %d contigs x %d bases, one sequence per thread (seq_db.rs:461); parity of these contigs checked" % (n_sample, n_contigs, clen)}
+
+    if rank == 0:
+        line = {
+            "metric": "Gbases/sec SHIMMER-indexed", "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "sequence_to_shmmrs on %d synthetic %d-base contigs per GPU, w=80 k=56 r=4 min_span=64" % (n_contigs, clen),
+                       "bases_per_gpu": bases, "shmmrs_per_gpu": n_shmmrs, "l2": "inputs (%.1f GB) larger than L2" % (bases / 1e9),
+                       "parallelism": "sequences sharded over %d GPU(s), no data-path collective" % world},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
+            "stages_ms": {k: statistics.mean(v) for k, v in stage_ms.items()},
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -67,6 +67,9 @@ typedef struct pgr_b200_index pgr_b200_index;  /* CompactSeqDB.frag_map as a dev
 
 /* ---- library / device ------------------------------------------------------------------------------------ */
 int pgr_b200_device_count(void);
+/* device used by the one-shot host calls (pgr_b200_sequence_to_shmmrs, pgr_b200_shmmrs_batch) of the calling thread;
+ * default 0.  One process per GPU sets it to its local rank. */
+int pgr_b200_set_default_device(int device);
 const char *pgr_b200_last_error(void);
 void pgr_b200_free(void *p);
 /* pinned host staging for callers that want the H2D copy at PCIe rate (bench.py e2e leg) */

@@ -56,6 +56,7 @@ def lib():
         P = C.POINTER
         L.pgr_b200_device_count.restype = C.c_int
         L.pgr_b200_last_error.restype = C.c_char_p
+        L.pgr_b200_set_default_device.argtypes = [C.c_int]
         L.pgr_b200_free.argtypes = [vp]
         L.pgr_b200_host_alloc.restype = vp
         L.pgr_b200_host_alloc.argtypes = [sz]
@@ -84,6 +85,10 @@ def _check(rc):
 
 def device_count():
     return lib().pgr_b200_device_count()
+
+
+def set_default_device(device):
+    _check(lib().pgr_b200_set_default_device(device))
 
 
 def _bytes(seq):

@@ -646,11 +646,19 @@ int pgr_b200_ctx_counters(pgr_b200_ctx *ctx, uint64_t out[8]) {
 }
 
 // ---- one-shot host API (thread-local default context on device 0) ---------------------------------------------
+static thread_local int g_default_device = 0;
+static thread_local pgr_b200_ctx *g_tls_ctx = nullptr;  // leaked at thread exit on purpose: CUDA may already be torn down
+
+int pgr_b200_set_default_device(int device) {
+    if (device < 0 || device >= pgr_b200_device_count()) { set_error("device %d out of range", device); return PGR_E_ARG; }
+    if (g_tls_ctx && g_tls_ctx->device != device) { pgr_b200_ctx_free(g_tls_ctx); g_tls_ctx = nullptr; }
+    g_default_device = device;
+    return PGR_OK;
+}
+
 static pgr_b200_ctx *tls_ctx() {
-    struct Holder { pgr_b200_ctx *c = nullptr; ~Holder() { /* leaked on purpose: CUDA may already be torn down */ } };
-    static thread_local Holder h;
-    if (!h.c) h.c = pgr_b200_ctx_new(0);
-    return h.c;
+    if (!g_tls_ctx) g_tls_ctx = pgr_b200_ctx_new(g_default_device);
+    return g_tls_ctx;
 }
 
 int pgr_b200_shmmrs_batch(size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens,
