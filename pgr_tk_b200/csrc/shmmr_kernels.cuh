@@ -14,13 +14,14 @@
 
 namespace pgr {
 
-constexpr int L0_NT = 256;                 // threads per CTA; thread t owns the 32-base block t of the tile's load region
+constexpr int L0_NT = 128;                 // threads per CTA; thread t owns the 32-base block t of the tile's load region
 constexpr int L0_CTX = 2;                  // leading context-only blocks (a 56-mer reaches 55 bases back)
-constexpr int L0_KB = L0_NT - L0_CTX;      // blocks that get keys: 254
-constexpr int L0_KPOS = L0_KB * 32;        // key positions per tile: 8128
+constexpr int L0_KB = L0_NT - L0_CTX;      // blocks that get keys
+constexpr int L0_KPOS = L0_KB * 32;        // key positions per tile
 constexpr int L0_PADB = 6;                 // spare blocks on both sides of the smem arrays (van Herk neighbours)
 constexpr int L0_ARR = (L0_KB + 2 * L0_PADB) * 33;  // padded u32 array length
-constexpr int L0_TAILCAP = 288;            // max level-0 entries the tail replay can emit (<= 2w + slack)
+constexpr int L0_MIN_CTAS = 5;             // resident CTAs per SM the kernel is compiled for
+constexpr int L0_LISTCAP = L0_ARR * 2;     // u16 entries that fit in the P array
 
 struct L0Params {
     const uint8_t *seq;          // device sequence store
@@ -56,7 +57,6 @@ __device__ __forceinline__ bool word_is_acgt(uint32_t wd) {
     const uint32_t v = u ^ 0x41414141u;              // A->00 C->02 G->06 T->15
     // valid values: 0x00, 0x02, 0x06, 0x15.  bits 3,5,6,7 must be clear; then (b4,b2,b1,b0) in {0000,0010,0110,1101}
     const uint32_t b0 = v, b1 = v >> 1, b2 = v >> 2, b4 = v >> 4;
-    // invalid combos: b0 != b4 ; b2 & ~b1 & ~b4 ... written as: ok = (b0 == b4) && (b4 ? (b2 && !b1) : (!b2 || b1))
     const uint32_t x04 = b0 ^ b4;                    // must be 0
     const uint32_t t_ok = b2 & ~b1;                  // T: b2=1,b1=0
     const uint32_t n_ok = ~b2 | b1;                  // A,C,G: not (b2=1,b1=0)
@@ -74,16 +74,13 @@ __device__ __forceinline__ uint32_t min3u(uint32_t a, uint32_t b, uint32_t c) { 
 __device__ __forceinline__ uint32_t max3u(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
 
 struct L0Smem {
-    uint32_t H[L0_ARR];      // hi 32 bits of x  (= hash bits 24..55); padded index q + q/32 + PADB*33
-    uint32_t X[L0_ARR];      // lo 32 bits of x  (= hash bits 0..23 << 8 | k)
-    uint32_t P[L0_ARR];      // van Herk exchange: prefix minima (pass 1) then suffix maxima (pass 2)
+    uint32_t H[L0_ARR];      // bits 24..55 of the k-mer hash = the high word of MM128.x; padded index q + q/32 + PADB*33
+    uint32_t P[L0_ARR];      // van Herk exchange: prefix minima (pass 1) then suffix maxima (pass 2); afterwards it
+                             // holds `list`: ordered key indices (u16) of the selected positions + tail replay entries
     uint32_t F0[L0_NT + 8], F1[L0_NT + 8], R0[L0_NT + 8], R1[L0_NT + 8];  // bit planes per 32-base block
     uint32_t bext[L0_KB + 2 * L0_PADB];   // block min (pass 1) / block max (pass 2)
-    uint32_t cmask[L0_KB + 2 * L0_PADB];  // candidate / selected bit masks per block
-    uint32_t strand[L0_KB];
     uint32_t wsum[L0_NT / 32];
-    pgr_mm128 tail[L0_TAILCAP];
-    uint32_t tail_n;
+    uint32_t n_list, n_tail, any_reject;
     // tile descriptor
     uint32_t seq_id, seq_len;
     int32_t keys_start;      // sequence position of key index 0 (multiple of 32, may be negative)
@@ -95,15 +92,54 @@ struct L0Smem {
 
 __device__ __forceinline__ int pidx(int q) { return q + (q >> 5) + L0_PADB * 33; }  // q may be negative (>= -PADB*32)
 
-// exact 64-bit key compare helpers on the split arrays
-__device__ __forceinline__ bool key_lt(const L0Smem &s, int qa, int qb) {  // x[qa] < x[qb]
+// k-mer registers of key index q rebuilt from the plane words (same arithmetic as the key loop)
+struct KmerRegs { uint64_t f0, f1, r0, r1; };
+__device__ __forceinline__ KmerRegs kmer_at(const L0Smem &s, int q, uint32_t k) {
+    const int t = (q >> 5) + L0_CTX, i = q & 31;
+    const uint64_t kmask = ~0ull >> (64 - k);
+    const uint32_t sh = 31 - i;
+    const uint32_t cp = 65u - k, cs = cp >> 5, cb = cp & 31;
+    const int g = t - 2 + (int)cs;
+    KmerRegs r;
+    r.f0 = (((uint64_t)fsr(s.F0[t - 1], s.F0[t - 2], sh) << 32) | fsr(s.F0[t], s.F0[t - 1], sh)) & kmask;
+    r.f1 = (((uint64_t)fsr(s.F1[t - 1], s.F1[t - 2], sh) << 32) | fsr(s.F1[t], s.F1[t - 1], sh)) & kmask;
+    const uint32_t q00 = fsr(s.R0[g], s.R0[g + 1], cb), q01 = fsr(s.R0[g + 1], s.R0[g + 2], cb), q02 = fsr(s.R0[g + 2], s.R0[g + 3], cb);
+    const uint32_t q10 = fsr(s.R1[g], s.R1[g + 1], cb), q11 = fsr(s.R1[g + 1], s.R1[g + 2], cb), q12 = fsr(s.R1[g + 2], s.R1[g + 3], cb);
+    r.r0 = (((uint64_t)fsr(q01, q02, i) << 32) | fsr(q00, q01, i)) & kmask;
+    r.r1 = (((uint64_t)fsr(q11, q12, i) << 32) | fsr(q10, q11, i)) & kmask;
+    return r;
+}
+// full 64-bit hash and strand of key index q (shmmrutils.rs:485-496)
+__device__ __forceinline__ uint64_t hash_at(const L0Smem &s, int q, uint32_t k, uint32_t &strand) {
+    const KmerRegs r = kmer_at(s, q, k);
+    const bool rev = r.r0 < r.f0;
+    strand = rev ? 1u : 0u;
+    return rev ? (u64hash(r.r0) ^ u64hash(r.r1 ^ HASH_XOR)) : (u64hash(r.f0) ^ u64hash(r.f1 ^ HASH_XOR));
+}
+// exact compare x[qa] < x[qb] (x = hash << 8 | k): 32-bit prefix first, the remaining 24 bits only on a prefix tie
+__device__ __noinline__ bool key_lt_slow(const L0Smem &s, int qa, int qb, uint32_t k) {
+    uint32_t st;
+    const uint64_t a = hash_at(s, qa, k, st) << 8, b = hash_at(s, qb, k, st) << 8;
+    return a < b;
+}
+__device__ __forceinline__ bool key_lt(const L0Smem &s, int qa, int qb, uint32_t k) {
     const uint32_t ha = s.H[pidx(qa)], hb = s.H[pidx(qb)];
-    return ha < hb || (ha == hb && s.X[pidx(qa)] < s.X[pidx(qb)]);
+    if (ha != hb) return ha < hb;
+    return key_lt_slow(s, qa, qb, k);
+}
+// exact tie-inclusive selection test of key index q at sequence position pos (valid window starts [a_lo, a_hi])
+__device__ __noinline__ bool selected_exact(const L0Smem &s, int q, int pos, int w, int a_lo, int a_hi, uint32_t k) {
+    const int maxl = min(w - 1, pos - a_lo), maxr = min(w - 1, (a_hi + w - 1) - pos);
+    if (maxl < 0 || maxr < 0) return false;
+    int l = 0, r = 0;
+    while (l < maxl && !key_lt(s, q - l - 1, q, k)) l++;
+    while (r < maxr && !key_lt(s, q + r + 1, q, k)) r++;
+    return l + r + 1 >= w;
 }
 
 // Level-0 minimizers of one tile.  W, K > 0 are compile-time specialisations; 0 = read from params.
 template <int W, int K>
-__global__ void __launch_bounds__(L0_NT, 2) l0_kernel(const L0Params p) {
+__global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     L0Smem &s = *reinterpret_cast<L0Smem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -113,12 +149,14 @@ __global__ void __launch_bounds__(L0_NT, 2) l0_kernel(const L0Params p) {
     const uint64_t kmask = ~0ull >> (64 - k);
     const uint32_t mlo = (uint32_t)kmask, mhi = (uint32_t)(kmask >> 32);
 
+    uint16_t *const list = reinterpret_cast<uint16_t *>(s.P);
     const uint32_t t_begin = p.cta_tile[blockIdx.x], t_end = p.cta_tile[blockIdx.x + 1];
-    uint64_t running = 0;  // entries this CTA has produced so far (thread 0 keeps the authoritative copy)
+    uint64_t running = 0;  // entries this CTA has produced so far (identical in every thread)
     pgr_mm128 *chunk = p.arena + (uint64_t)blockIdx.x * p.chunk_cap;
 
     // spare blocks of the exchange arrays are never written with real data; give them harmless values once
-    for (int i = tid; i < L0_KB + 2 * L0_PADB; i += L0_NT) { s.bext[i] = 0; s.cmask[i] = 0; }
+    for (int i = tid; i < L0_KB + 2 * L0_PADB; i += L0_NT) s.bext[i] = 0;
+    for (int i = tid; i < L0_ARR; i += L0_NT) { s.H[i] = 0; s.P[i] = 0; }
 
     for (uint32_t tile = t_begin; tile < t_end; ++tile) {
         __syncthreads();  // previous tile fully consumed
@@ -143,7 +181,7 @@ __global__ void __launch_bounds__(L0_NT, 2) l0_kernel(const L0Params p) {
             s.out_lo = (int32_t)(j * p.tile_stride);
             s.out_hi = (int32_t)min((uint64_t)L, (uint64_t)(j + 1) * p.tile_stride);
             s.seq_off = p.off[sid];
-            s.bad = 0; s.tail_n = 0;
+            s.bad = 0; s.n_tail = 0; s.any_reject = 0;
         }
         __syncthreads();
         const int32_t L = (int32_t)s.seq_len;
@@ -183,43 +221,37 @@ __global__ void __launch_bounds__(L0_NT, 2) l0_kernel(const L0Params p) {
         if (tid < 8) { s.F0[L0_NT + tid] = 0; s.F1[L0_NT + tid] = 0; s.R0[L0_NT + tid] = 0; s.R1[L0_NT + tid] = 0; }
         __syncthreads();
 
-        // ---- phase 2: keys for blocks 2..255 ---------------------------------------------------------------
-        const int kb = tid - L0_CTX;  // key block index
-        if (tid >= L0_CTX) {
-            uint32_t strand = 0;
-            if (blk_live) {
-                const uint32_t a2 = s.F0[tid - 2], a1 = s.F0[tid - 1], a0 = f0;
-                const uint32_t b2 = s.F1[tid - 2], b1 = s.F1[tid - 1], b0 = f1;
-                // r-planes: Q = G >> (32*(tid-2) + 65 - k), so that rmmer(i) = (Q >> i) & kmask
-                const uint32_t cp = 65u - k, cs = cp >> 5, cb = cp & 31;
-                const int g = tid - 2 + (int)cs;
-                const uint32_t q00 = fsr(s.R0[g], s.R0[g + 1], cb), q01 = fsr(s.R0[g + 1], s.R0[g + 2], cb),
-                               q02 = fsr(s.R0[g + 2], s.R0[g + 3], cb);
-                const uint32_t q10 = fsr(s.R1[g], s.R1[g + 1], cb), q11 = fsr(s.R1[g + 1], s.R1[g + 2], cb),
-                               q12 = fsr(s.R1[g + 2], s.R1[g + 3], cb);
-                const int base = pidx(32 * kb);
+        // ---- phase 2: keys for blocks CTX.. ------------------------------------------------------------------
+        const int kb = tid - L0_CTX;  // key block index (negative for the two context threads)
+        if (tid >= L0_CTX && blk_live) {
+            const uint32_t a2 = s.F0[tid - 2], a1 = s.F0[tid - 1], a0 = f0;
+            const uint32_t b2 = s.F1[tid - 2], b1 = s.F1[tid - 1], b0 = f1;
+            // r-planes: Q = G >> (32*(tid-2) + 65 - k), so that rmmer(i) = (Q >> i) & kmask
+            const uint32_t cp = 65u - k, cs = cp >> 5, cb = cp & 31;
+            const int g = tid - 2 + (int)cs;
+            const uint32_t q00 = fsr(s.R0[g], s.R0[g + 1], cb), q01 = fsr(s.R0[g + 1], s.R0[g + 2], cb),
+                           q02 = fsr(s.R0[g + 2], s.R0[g + 3], cb);
+            const uint32_t q10 = fsr(s.R1[g], s.R1[g + 1], cb), q11 = fsr(s.R1[g + 1], s.R1[g + 2], cb),
+                           q12 = fsr(s.R1[g + 2], s.R1[g + 3], cb);
+            const int base = pidx(32 * kb);
 #pragma unroll 8
-                for (int i = 0; i < 32; i++) {
-                    const uint32_t sh = 31 - i;
-                    const uint32_t f0lo = fsr(a0, a1, sh) & mlo, f0hi = fsr(a1, a2, sh) & mhi;
-                    const uint32_t f1lo = fsr(b0, b1, sh) & mlo, f1hi = fsr(b1, b2, sh) & mhi;
-                    const uint32_t r0lo = fsr(q00, q01, i) & mlo, r0hi = fsr(q01, q02, i) & mhi;
-                    const uint32_t r1lo = fsr(q10, q11, i) & mlo, r1hi = fsr(q11, q12, i) & mhi;
-                    const uint64_t F0 = ((uint64_t)f0hi << 32) | f0lo, R0 = ((uint64_t)r0hi << 32) | r0lo;
-                    const bool rev = R0 < F0;                       // shmmrutils.rs:486 (plane 0 only)
-                    if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
-                        const int pos = blk_pos + i;
-                        if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) s.bad = 1;
-                    }
-                    const uint64_t u = rev ? R0 : F0;
-                    const uint64_t v = rev ? (((uint64_t)r1hi << 32) | r1lo) : (((uint64_t)f1hi << 32) | f1lo);
-                    const uint64_t h = u64hash(u) ^ u64hash(v ^ HASH_XOR);
-                    s.H[base + i] = (uint32_t)(h >> 24);
-                    s.X[base + i] = ((uint32_t)h << 8) | k;
-                    strand |= (rev ? 1u : 0u) << i;
+            for (int i = 0; i < 32; i++) {
+                const uint32_t sh = 31 - i;
+                const uint32_t f0lo = fsr(a0, a1, sh) & mlo, f0hi = fsr(a1, a2, sh) & mhi;
+                const uint32_t f1lo = fsr(b0, b1, sh) & mlo, f1hi = fsr(b1, b2, sh) & mhi;
+                const uint32_t r0lo = fsr(q00, q01, i) & mlo, r0hi = fsr(q01, q02, i) & mhi;
+                const uint32_t r1lo = fsr(q10, q11, i) & mlo, r1hi = fsr(q11, q12, i) & mhi;
+                const uint64_t F0 = ((uint64_t)f0hi << 32) | f0lo, R0 = ((uint64_t)r0hi << 32) | r0lo;
+                const bool rev = R0 < F0;                       // shmmrutils.rs:486 (plane 0 only)
+                if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
+                    const int pos = blk_pos + i;
+                    if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) s.bad = 1;
                 }
+                const uint64_t u = rev ? R0 : F0;
+                const uint64_t v = rev ? (((uint64_t)r1hi << 32) | r1lo) : (((uint64_t)f1hi << 32) | f1lo);
+                const uint64_t h = u64hash(u) ^ u64hash(v ^ HASH_XOR);
+                s.H[base + i] = (uint32_t)(h >> 24);
             }
-            s.strand[kb] = strand;
         }
         __syncthreads();
 
@@ -241,6 +273,7 @@ __global__ void __launch_bounds__(L0_NT, 2) l0_kernel(const L0Params p) {
                 const int phi = min(min(a_hi + (int)w - 1, s.out_hi - 1) - blk_pos, 31);
                 if (plo <= phi) pmask = (0xFFFFFFFFu >> (31 - phi)) & (0xFFFFFFFFu << plo);
             }
+            if (tid < L0_CTX) pmask = 0;
             if (w > 32) {
                 // van Herk / Gil-Werman with one 32-position block per thread
                 uint32_t m[32];
@@ -293,7 +326,6 @@ __global__ void __launch_bounds__(L0_NT, 2) l0_kernel(const L0Params p) {
                 cand &= pmask;
             } else {
                 // small windows: direct evaluation (w <= 32); w is uniform, so no barrier mismatch with the branch above
-                if (tid < L0_CTX) pmask = 0;
                 for (int o = 0; o < 32; o++) {
                     if (!((pmask >> o) & 1u)) continue;
                     const int q = 32 * kb + o;
@@ -307,92 +339,10 @@ __global__ void __launch_bounds__(L0_NT, 2) l0_kernel(const L0Params p) {
                     if (l + r + 1 >= (int)w) cand |= 1u << o;
                 }
             }
-            if (tid < L0_CTX) cand = 0;
-            s.cmask[kb + L0_PADB] = cand;
-        }
-        __syncthreads();
-
-        // ---- phase 4: resolve candidates that tie on the 32-bit prefix with another candidate (exact 64-bit) -
-        uint32_t sel = cand;
-        if (tid >= L0_CTX && cand) {
-            const int nbk = ((int)w + 30) >> 5;  // neighbour blocks that can hold a position closer than w
-            uint32_t rem = cand;
-            while (rem) {
-                const int o = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const int q = 32 * kb + o;
-                const uint32_t hq = s.H[pidx(q)];
-                bool tie = false;
-                for (int b = -nbk; b <= nbk && !tie; b++) {
-                    uint32_t cm = s.cmask[kb + L0_PADB + b];
-                    if (b == 0) cm &= ~(1u << o);
-                    while (cm) {
-                        const int o2 = __ffs(cm) - 1;
-                        cm &= cm - 1;
-                        const int q2 = 32 * (kb + b) + o2;
-                        if (abs(q2 - q) < (int)w && s.H[pidx(q2)] == hq) { tie = true; break; }
-                    }
-                }
-                if (tie) {
-                    const int pos = blk_pos + o;
-                    const int maxl = min((int)w - 1, pos - a_lo), maxr = min((int)w - 1, (a_hi + (int)w - 1) - pos);
-                    int l = 0, r = 0;
-                    while (l < maxl && !key_lt(s, q - l - 1, q)) l++;
-                    while (r < maxr && !key_lt(s, q + r + 1, q)) r++;
-                    if (l + r + 1 < (int)w) sel &= ~(1u << o);
-                }
-            }
-        }
-        __syncthreads();
-        if (tid >= L0_CTX) s.cmask[kb + L0_PADB] = sel;
-        __syncthreads();
-
-        // ---- phase 5: tail replay (last tile of the sequence; shmmrutils.rs:503-515 with rule (2) disabled) --
-        if (s.is_last && tid == 0 && (int32_t)w > (int32_t)k && L > (int32_t)k) {
-            // q = last selected position below Eb (selections of the whole sequence, not only this tile's range)
-            const int32_t t_lo = max(Eb, (int32_t)k);
-            int32_t q = -1;
-            {
-                int32_t hi_pos = min(Eb, L) - 1;
-                for (int32_t pos = hi_pos; pos >= a_lo && pos >= Eb - (int32_t)w; pos--) {
-                    const int qq = pos - keys_start;
-                    if (qq < 0) break;
-                    // selection status of pos: recompute exactly (positions before out_lo belong to the previous tile)
-                    const int maxl = min((int)w - 1, pos - a_lo), maxr = min((int)w - 1, (a_hi + (int)w - 1) - pos);
-                    if (maxr < 0) continue;
-                    int l = 0, r = 0;
-                    while (l < maxl && !key_lt(s, qq - l - 1, qq)) l++;
-                    while (r < maxr && !key_lt(s, qq + r + 1, qq)) r++;
-                    if (l + r + 1 >= (int)w) { q = pos; break; }
-                }
-            }
-            uint32_t n = 0;
-            for (int32_t pos = t_lo; pos < L; pos++) {
-                const bool fire = (q < 0) ? (pos == (int32_t)(k + w - 1)) : (pos == q + (int32_t)w);
-                if (!fire) continue;
-                const int qe = pos - keys_start, qa = qe - (int)w + 1;
-                int best = qa;
-                for (int j = qa + 1; j <= qe; j++) if (key_lt(s, j, best)) best = j;
-                for (int j = qa; j <= qe; j++) {
-                    if (!key_lt(s, best, j)) {  // x[j] == min
-                        const int pj = j + keys_start;
-                        if (n < L0_TAILCAP) {
-                            pgr_mm128 mm;
-                            mm.x = ((uint64_t)s.H[pidx(j)] << 32) | s.X[pidx(j)];
-                            mm.y = ((uint64_t)s.seq_id << 32) | ((uint64_t)(uint32_t)pj << 1) |
-                                   ((s.strand[j >> 5] >> (j & 31)) & 1u);
-                            s.tail[n] = mm;
-                        }
-                        n++;
-                        q = pj;
-                    }
-                }
-            }
-            s.tail_n = n;
         }
 
-        // ---- phase 6: ordered compaction into the CTA's chunk ----------------------------------------------
-        const uint32_t cnt = (tid >= L0_CTX) ? __popc(sel) : 0;
+        // ---- phase 4: ordered list of the candidates ----------------------------------------------------------
+        const uint32_t cnt = __popc(cand);
         uint32_t incl = cnt;
 #pragma unroll
         for (int dlt = 1; dlt < 32; dlt <<= 1) {
@@ -404,33 +354,90 @@ __global__ void __launch_bounds__(L0_NT, 2) l0_kernel(const L0Params p) {
         uint32_t wbase = 0, total = 0;
 #pragma unroll
         for (int i = 0; i < L0_NT / 32; i++) { const uint32_t v = s.wsum[i]; if (i < warp) wbase += v; total += v; }
-        const uint32_t tail_n = s.tail_n;
-        if (cnt) {
-            uint64_t dst = running + wbase + incl - cnt;
-            uint32_t rem = sel;
-            const uint32_t strand = s.strand[kb];
+        {
+            uint32_t dst = wbase + incl - cnt, rem = cand;
             while (rem) {
                 const int o = __ffs(rem) - 1;
                 rem &= rem - 1;
-                if (dst < p.chunk_cap) {
-                    const int q = 32 * kb + o;
-                    pgr_mm128 mm;
-                    mm.x = ((uint64_t)s.H[pidx(q)] << 32) | s.X[pidx(q)];
-                    mm.y = ((uint64_t)s.seq_id << 32) | ((uint64_t)(uint32_t)(blk_pos + o) << 1) | ((strand >> o) & 1u);
-                    chunk[dst] = mm;
-                }
-                dst++;
+                list[dst++] = (uint16_t)(32 * kb + o);
             }
         }
-        for (uint32_t i = tid; i < min(tail_n, (uint32_t)L0_TAILCAP); i += L0_NT) {
-            const uint64_t dst = running + total + i;
-            if (dst < p.chunk_cap) chunk[dst] = s.tail[i];
+        __syncthreads();
+
+        // ---- phase 5: candidates that tie on the 32-bit prefix with a neighbouring candidate: exact 64-bit test --
+        for (uint32_t j = tid; j < total; j += L0_NT) {
+            const int q = list[j];
+            const uint32_t hq = s.H[pidx(q)];
+            bool tie = false;
+            for (int jj = (int)j - 1; jj >= 0 && q - (int)list[jj] < (int)w && !tie; jj--) tie = (s.H[pidx(list[jj])] == hq);
+            for (uint32_t jj = j + 1; jj < total && (int)list[jj] - q < (int)w && !tie; jj++) tie = (s.H[pidx(list[jj])] == hq);
+            if (tie && !selected_exact(s, q, q + keys_start, (int)w, a_lo, a_hi, k)) s.any_reject = 1u + j;  // any value != 0
+        }
+        __syncthreads();
+        uint32_t n_list = total;
+        if (s.any_reject) {   // rare: re-evaluate every candidate exactly and rebuild the list (single thread)
+            if (tid == 0) {
+                uint32_t o = 0;
+                for (uint32_t j = 0; j < total; j++) {
+                    const int q = list[j];
+                    if (selected_exact(s, q, q + keys_start, (int)w, a_lo, a_hi, k)) list[o++] = (uint16_t)q;
+                }
+                s.n_list = o;
+            }
+            __syncthreads();
+            n_list = s.n_list;
+        }
+
+        // ---- phase 6: tail replay (last tile of the sequence; shmmrutils.rs:503-515 with rule (2) disabled) ---
+        if (s.is_last && (int32_t)w > (int32_t)k && L > (int32_t)k) {
+            if (tid == 0) {
+                // q = last selected position below Eb (selections of the whole sequence, not only this tile's range)
+                const int32_t t_lo = max(Eb, (int32_t)k);
+                int32_t q = -1;
+                for (int32_t pos = Eb - 1; pos >= a_lo && pos >= Eb - (int32_t)w; pos--) {
+                    const int qq = pos - keys_start;
+                    if (qq < 0) break;
+                    if (selected_exact(s, qq, pos, (int)w, a_lo, a_hi, k)) { q = pos; break; }
+                }
+                uint32_t n = 0;
+                for (int32_t pos = t_lo; pos < L; pos++) {
+                    const bool fire = (q < 0) ? (pos == (int32_t)(k + w - 1)) : (pos == q + (int32_t)w);
+                    if (!fire) continue;
+                    const int qe = pos - keys_start, qa = qe - (int)w + 1;
+                    int best = qa;
+                    for (int j = qa + 1; j <= qe; j++) if (key_lt(s, j, best, k)) best = j;
+                    for (int j = qa; j <= qe; j++) {
+                        if (!key_lt(s, best, j, k)) {  // x[j] == min
+                            if (n_list + n < (uint32_t)L0_LISTCAP) list[n_list + n] = (uint16_t)j;
+                            n++;
+                            q = j + keys_start;
+                        }
+                    }
+                }
+                s.n_tail = n;
+            }
+            __syncthreads();
+        }
+        const uint32_t n_tail = s.n_tail;
+        const uint32_t n_all = n_list + n_tail;
+
+        // ---- phase 7: rebuild the full MM128 of every selected position and write it (coalesced) -------------
+        for (uint32_t j = tid; j < min(n_all, (uint32_t)L0_LISTCAP); j += L0_NT) {
+            const uint64_t dst = running + j;
+            if (dst >= p.chunk_cap) break;
+            const int q = list[j];
+            uint32_t strand;
+            const uint64_t h = hash_at(s, q, k, strand);
+            pgr_mm128 mm;
+            mm.x = (h << 8) | k;
+            mm.y = ((uint64_t)s.seq_id << 32) | ((uint64_t)(uint32_t)(q + keys_start) << 1) | strand;
+            chunk[dst] = mm;
         }
         if (tid == 0) {
-            atomicAdd(&p.seq_count[s.seq_id], total + tail_n);
-            if (s.bad || tail_n > L0_TAILCAP) atomicOr(&p.seq_flag[s.seq_id], 1u);
+            atomicAdd(&p.seq_count[s.seq_id], n_all);
+            if (s.bad || n_all > (uint32_t)L0_LISTCAP) atomicOr(&p.seq_flag[s.seq_id], 1u);
         }
-        running += total + tail_n;
+        running += n_all;
     }
     if (tid == 0) p.chunk_count[blockIdx.x] = running;
 }
