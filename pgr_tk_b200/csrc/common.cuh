@@ -12,6 +12,9 @@ namespace pgr {
 // thread-local last error (pgr_b200_last_error)
 void set_error(const char *fmt, ...);
 const char *get_error();
+// caller-owned result buffers (pinned pool for large ones); released by pgr_b200_free
+void *result_alloc(size_t bytes);
+void result_free(void *p);
 
 #define PGR_CUDA(call)                                                                          \
     do {                                                                                        \

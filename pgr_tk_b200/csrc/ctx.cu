@@ -46,6 +46,46 @@ void StageTimer::destroy() {
     ev0.clear(); ev1.clear();
 }
 
+// Result buffers handed to the caller.  Large ones come from a small pool of pinned host buffers so that the D2H copy
+// runs at PCIe rate and no page faults are taken on every call; pgr_b200_free() returns them to the pool.
+namespace {
+struct PoolEntry { void *p; size_t cap; bool in_use; };
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool;
+constexpr size_t POOL_MIN = 1u << 20;     // smaller results use malloc
+constexpr size_t POOL_MAX_FREE = 4;       // idle pinned buffers kept around
+}  // namespace
+
+void *result_alloc(size_t bytes) {
+    if (bytes < POOL_MIN) return malloc(bytes ? bytes : 1);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (size_t i = 0; i < g_pool.size(); i++)
+        if (!g_pool[i].in_use && g_pool[i].cap >= bytes && (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = (int)i;
+    if (best >= 0) { g_pool[best].in_use = true; return g_pool[best].p; }
+    void *p = nullptr;
+    const size_t cap = bytes + bytes / 8;
+    if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); return malloc(bytes); }
+    g_pool.push_back({p, cap, true});
+    return p;
+}
+
+void result_free(void *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); i++) {
+            if (g_pool[i].p != p) continue;
+            g_pool[i].in_use = false;
+            size_t idle = 0;
+            for (auto &e : g_pool) idle += e.in_use ? 0 : 1;
+            if (idle > POOL_MAX_FREE) { cudaFreeHost(p); g_pool.erase(g_pool.begin() + i); }
+            return;
+        }
+    }
+    free(p);
+}
+
 int check_spec(const pgr_shmmr_spec *s) {
     if (!s) { set_error("spec is NULL"); return PGR_E_ARG; }
     if (s->k == 0 || s->k > 56) { set_error("assert!(k <= 56) violated (k=%u)", s->k); return PGR_E_SPEC; }
@@ -86,7 +126,7 @@ int pgr_b200_device_count(void) {
     return n;
 }
 const char *pgr_b200_last_error(void) { return get_error(); }
-void pgr_b200_free(void *p) { free(p); }
+void pgr_b200_free(void *p) { pgr::result_free(p); }
 void *pgr_b200_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_error("cudaMallocHost(%zu) failed", bytes); cudaGetLastError(); return nullptr; }
@@ -123,6 +163,7 @@ void pgr_b200_ctx_free(pgr_b200_ctx *ctx) {
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     ctx->timer.destroy();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
@@ -149,9 +190,9 @@ static int set_seq_tables(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids) {
     return PGR_OK;
 }
 
-int pgr_b200_ctx_upload(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens) {
-    if (!ctx || (n && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
-    PGR_CUDA(cudaSetDevice(ctx->device));
+// lay the batch out in the device sequence store (32-byte aligned starts, SEQ_SLACK bytes before and after) and
+// publish the per-sequence tables; no sequence bytes are copied yet
+static int upload_layout(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens) {
     ctx->h_off.resize(n);
     ctx->h_len.resize(n);
     uint64_t off = SEQ_SLACK, total = 0;
@@ -166,30 +207,43 @@ int pgr_b200_ctx_upload(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const
     const uint64_t store_bytes = off + SEQ_SLACK;
     const bool grew = store_bytes > ctx->seq_store.cap;
     PGR_TRY(ctx->seq_store.ensure(store_bytes));
-    if (grew) PGR_CUDA(cudaMemsetAsync(ctx->seq_store.p, 0, ctx->seq_store.cap, ctx->stream));
+    if (grew) {
+        PGR_CUDA(cudaMemsetAsync(ctx->seq_store.p, 0, ctx->seq_store.cap, ctx->stream));
+        PGR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->d_seq = ctx->seq_store.as<uint8_t>();
+    ctx->total_bases = total;
+    return set_seq_tables(ctx, n, rids);
+}
+
+// copy sequences [i0, i1) into the store on stream `st` (asynchronous when the caller's buffers are pinned).
+// Large sequences go straight from the caller's buffer; small ones are packed through a pinned staging buffer so
+// that they share one copy.
+static int upload_copy(pgr_b200_ctx *ctx, const uint8_t *const *seqs, const size_t *lens, size_t i0, size_t i1, cudaStream_t st) {
     uint8_t *base = ctx->seq_store.as<uint8_t>();
-    // large sequences go straight from the caller's buffer (full PCIe rate when it is pinned);
-    // small ones are packed through a pinned staging buffer so that they share one copy
     const size_t BIG = 1u << 20, STAGE = 64u << 20;
-    PGR_TRY(ctx->ensure_stage(2 * STAGE));
-    uint8_t *stage[2] = {(uint8_t *)ctx->h_stage, (uint8_t *)ctx->h_stage + STAGE};
-    cudaEvent_t ev[2];
-    PGR_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    PGR_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     int cur = 0;
     bool used[2] = {false, false};
-    size_t i = 0;
+    size_t i = i0;
     int rc = PGR_OK;
-    while (i < n && rc == PGR_OK) {
+    while (i < i1 && rc == PGR_OK) {
         if (lens[i] >= BIG) {
-            if (cudaMemcpyAsync(base + ctx->h_off[i], seqs[i], lens[i], cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = PGR_E_CUDA;
+            if (cudaMemcpyAsync(base + ctx->h_off[i], seqs[i], lens[i], cudaMemcpyHostToDevice, st) != cudaSuccess) rc = PGR_E_CUDA;
             i++;
             continue;
+        }
+        if (!stage[0]) {
+            if ((rc = ctx->ensure_stage(2 * STAGE)) != PGR_OK) break;
+            stage[0] = (uint8_t *)ctx->h_stage; stage[1] = stage[0] + STAGE;
+            cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
         }
         // run of small sequences [i, j) whose device span fits the staging buffer
         const uint64_t span0 = ctx->h_off[i];
         size_t j = i;
-        while (j < n && lens[j] < BIG && (ctx->h_off[j] - span0) + ((lens[j] + 31) & ~(size_t)31) <= STAGE) j++;
+        while (j < i1 && lens[j] < BIG && (ctx->h_off[j] - span0) + ((lens[j] + 31) & ~(size_t)31) <= STAGE) j++;
         if (used[cur]) cudaEventSynchronize(ev[cur]);
         uint64_t span = 0;
         for (size_t q = i; q < j; q++) {
@@ -199,19 +253,30 @@ int pgr_b200_ctx_upload(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const
             if (padded > lens[q]) memset(stage[cur] + rel + lens[q], 0, padded - lens[q]);
             span = rel + padded;
         }
-        if (span && cudaMemcpyAsync(base + span0, stage[cur], span, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = PGR_E_CUDA;
-        cudaEventRecord(ev[cur], ctx->stream);
+        if (span && cudaMemcpyAsync(base + span0, stage[cur], span, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = PGR_E_CUDA;
+        cudaEventRecord(ev[cur], st);
         used[cur] = true;
         cur ^= 1;
         i = j;
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
-    if (rc != PGR_OK) { set_error("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
-    ctx->d_seq = base;
-    ctx->total_bases = total;
-    return set_seq_tables(ctx, n, rids);
+    if (stage[0]) {
+        // the staging buffers are reused by the next call: wait until the copies that read them are done
+        if (used[0]) cudaEventSynchronize(ev[0]);
+        if (used[1]) cudaEventSynchronize(ev[1]);
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+    }
+    if (rc == PGR_E_CUDA) set_error("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+int pgr_b200_ctx_upload(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens) {
+    if (!ctx || (n && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(ctx->device));
+    PGR_TRY(upload_layout(ctx, n, rids, seqs, lens));
+    PGR_TRY(upload_copy(ctx, seqs, lens, 0, n, ctx->stream));
+    PGR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PGR_OK;
 }
 
 int pgr_b200_ctx_set_device_seqs(pgr_b200_ctx *ctx, const uint8_t *dev_base, size_t n, const uint32_t *rids, const uint64_t *offs,
@@ -249,7 +314,7 @@ struct Level {
 int run_level(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, const uint64_t *off_in, pgr_mm128 *out,
               uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out) {
     cudaStream_t st = ctx->stream;
-    const size_t n = ctx->n_seq;
+    const size_t n = ctx->rn;
     if (n_in == 0) {
         PGR_CUDA(cudaMemsetAsync(off_out, 0, (n + 1) * sizeof(uint64_t), st));
         *n_out = 0;
@@ -265,7 +330,7 @@ int run_level(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, c
     p.r = spec.r; p.padding = padding ? 1u : 0u; p.min_span = spec.min_span;
     p.flags = ctx->flags.as<uint8_t>(); p.block_sum = ctx->block_sum.as<uint32_t>();
     p.block_prefix = ctx->block_prefix.as<uint64_t>();
-    p.out = out; p.seq_off_out = off_out; p.rid = ctx->d_rid.as<uint32_t>(); p.patch_rid = patch_rid ? 1u : 0u;
+    p.out = out; p.seq_off_out = off_out; p.rid = (ctx->d_rid.as<uint32_t>() + ctx->r0); p.patch_rid = patch_rid ? 1u : 0u;
     if (kind == 0) level_flags_kernel<0><<<n_blocks, LV_NT, 0, st>>>(p);
     else level_flags_kernel<1><<<n_blocks, LV_NT, 0, st>>>(p);
     block_scan_kernel<<<1, 1024, 0, st>>>(p.block_sum, p.block_prefix, n_blocks);
@@ -297,7 +362,7 @@ int occupancy_l0(int *occ) {
 // level-0 minimizers for the whole store -> flat list in ctx->bufA, per-sequence offsets in ctx->seq_dst
 int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     cudaStream_t st = ctx->stream;
-    const size_t n = ctx->n_seq;
+    const size_t n = ctx->rn;
     const uint32_t w = spec.w, k = spec.k;
     const uint32_t halo = ((w - 1 + 31) / 32) * 32;
     const uint32_t TI = L0_KPOS - 2 * halo;
@@ -306,7 +371,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     uint64_t nt64 = 0;
     for (size_t i = 0; i < n; i++) {
         tile_prefix[i] = (uint32_t)nt64;
-        const uint32_t L = ctx->h_len[i];
+        const uint32_t L = ctx->h_len[ctx->r0 + i];
         if (L > k) nt64 += ceil_div<uint32_t>(L, TI);
         if (nt64 >= 0xFFFFFFF0ull) { set_error("too many tiles in one batch"); return PGR_E_LIMIT; }
     }
@@ -325,36 +390,12 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     else PGR_TRY((occupancy_l0<0, 0>(&occ)));
     if (occ < 1) { set_error("l0_kernel does not fit on an SM"); return PGR_E_CUDA; }
     const uint32_t G = std::min<uint32_t>(n_tiles, (uint32_t)(ctx->n_sm * occ));
-    // static, cost-balanced partition of the tile sequence over the CTAs (contiguous ranges keep the output ordered)
+    // static partition of the tile sequence over the CTAs: contiguous, equal tile counts (every tile costs about the
+    // same; contiguous ranges keep each CTA's output chunk in sequence/position order)
     std::vector<uint32_t> cta_tile(G + 1);
-    std::vector<uint64_t> cta_cost(G, 0);
-    {
-        auto tile_cost = [&](uint32_t L, uint32_t j) -> uint64_t {
-            const uint64_t lo = (uint64_t)j * TI;
-            return std::min<uint64_t>(TI, L - lo) + 2 * halo + 256;
-        };
-        uint64_t total_cost = 0;
-        for (size_t i = 0; i < n; i++) {
-            const uint32_t cnt = tile_prefix[i + 1] - tile_prefix[i];
-            for (uint32_t j = 0; j < cnt; j++) total_cost += tile_cost(ctx->h_len[i], j);
-        }
-        uint64_t acc = 0;
-        uint32_t c = 0, t = 0;
-        cta_tile[0] = 0;
-        for (size_t i = 0; i < n; i++) {
-            const uint32_t cnt = tile_prefix[i + 1] - tile_prefix[i];
-            for (uint32_t j = 0; j < cnt; j++, t++) {
-                const uint64_t tc = tile_cost(ctx->h_len[i], j);
-                // close CTA c before tile t when it already holds its share and enough tiles remain for the rest
-                while (c + 1 < G && acc >= (total_cost * (c + 1)) / G && t > cta_tile[c]) { c++; cta_tile[c] = t; }
-                acc += tc;
-                cta_cost[c] += tc;
-            }
-        }
-        while (c + 1 <= G) { c++; cta_tile[c] = n_tiles; }
-    }
     uint64_t max_cost = 0;
-    for (uint32_t c = 0; c < G; c++) max_cost = std::max(max_cost, cta_cost[c]);
+    for (uint32_t c = 0; c <= G; c++) cta_tile[c] = (uint32_t)(((uint64_t)n_tiles * c) / G);
+    for (uint32_t c = 0; c < G; c++) max_cost = std::max<uint64_t>(max_cost, (uint64_t)(cta_tile[c + 1] - cta_tile[c]) * TI);
     PGR_TRY(ctx->tile_prefix.ensure((n + 1) * sizeof(uint32_t)));
     PGR_TRY(ctx->cta_tile.ensure((G + 1) * sizeof(uint32_t)));
     PGR_TRY(ctx->chunk_count.ensure(G * sizeof(uint64_t)));
@@ -375,7 +416,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         PGR_CUDA(cudaMemsetAsync(ctx->seq_count.p, 0, n * sizeof(uint32_t), st));
         PGR_CUDA(cudaMemsetAsync(ctx->seq_flag.p, 0, n * sizeof(uint32_t), st));
         L0Params p;
-        p.seq = ctx->d_seq; p.off = ctx->d_off.as<uint64_t>(); p.len = ctx->d_len.as<uint32_t>();
+        p.seq = ctx->d_seq; p.off = (ctx->d_off.as<uint64_t>() + ctx->r0); p.len = (ctx->d_len.as<uint32_t>() + ctx->r0);
         p.tile_prefix = ctx->tile_prefix.as<uint32_t>(); p.cta_tile = ctx->cta_tile.as<uint32_t>();
         p.n_seq = (uint32_t)n; p.w = w; p.k = k; p.tile_stride = TI; p.halo = halo;
         p.arena = ctx->arena.as<pgr_mm128>(); p.chunk_cap = chunk_cap;
@@ -407,7 +448,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         PGR_TRY(ctx->replay_count.ensure(n * sizeof(uint32_t)));
         PGR_CUDA(cudaMemcpyAsync(ctx->replay_list.p, replay.data(), replay.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         ReplayParams rp;
-        rp.seq = ctx->d_seq; rp.off = ctx->d_off.as<uint64_t>(); rp.len = ctx->d_len.as<uint32_t>();
+        rp.seq = ctx->d_seq; rp.off = (ctx->d_off.as<uint64_t>() + ctx->r0); rp.len = (ctx->d_len.as<uint32_t>() + ctx->r0);
         rp.list = ctx->replay_list.as<uint32_t>(); rp.n_list = (uint32_t)replay.size(); rp.w = w; rp.k = k;
         rp.count = ctx->replay_count.as<uint32_t>(); rp.dst_off = nullptr; rp.dst = nullptr;
         const int slot = ctx->timer.begin("l0_replay_count", st);
@@ -464,7 +505,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     }
     if (!replay.empty()) {
         ReplayParams rp;
-        rp.seq = ctx->d_seq; rp.off = ctx->d_off.as<uint64_t>(); rp.len = ctx->d_len.as<uint32_t>();
+        rp.seq = ctx->d_seq; rp.off = (ctx->d_off.as<uint64_t>() + ctx->r0); rp.len = (ctx->d_len.as<uint32_t>() + ctx->r0);
         rp.list = ctx->replay_list.as<uint32_t>(); rp.n_list = (uint32_t)replay.size(); rp.w = w; rp.k = k;
         rp.count = nullptr; rp.dst_off = ctx->seq_dst.as<uint64_t>(); rp.dst = ctx->bufA.as<pgr_mm128>();
         const int slot = ctx->timer.begin("l0_replay_write", st);
@@ -481,10 +522,10 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
 // sketch mode (shmmrutils.rs:558-630): flat list of kept k-mers in ctx->bufA, offsets in ctx->seq_dst
 int run_sketch(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     cudaStream_t st = ctx->stream;
-    const size_t n = ctx->n_seq;
+    const size_t n = ctx->rn;
     std::vector<uint64_t> seg_prefix(n + 1);
     uint64_t n_segs = 0;
-    for (size_t i = 0; i < n; i++) { seg_prefix[i] = n_segs; n_segs += ceil_div<uint64_t>(ctx->h_len[i], SK_SEG); }
+    for (size_t i = 0; i < n; i++) { seg_prefix[i] = n_segs; n_segs += ceil_div<uint64_t>(ctx->h_len[ctx->r0 + i], SK_SEG); }
     seg_prefix[n] = n_segs;
     PGR_TRY(ctx->seq_dst.ensure((n + 1) * sizeof(uint64_t)));
     if (n_segs == 0) {
@@ -498,7 +539,7 @@ int run_sketch(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     PGR_TRY(ctx->chunk_prefix.ensure((n_segs + 1) * sizeof(uint64_t)));
     PGR_CUDA(cudaMemcpyAsync(ctx->tile_prefix.p, seg_prefix.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     SketchParams sp;
-    sp.seq = ctx->d_seq; sp.off = ctx->d_off.as<uint64_t>(); sp.len = ctx->d_len.as<uint32_t>();
+    sp.seq = ctx->d_seq; sp.off = (ctx->d_off.as<uint64_t>() + ctx->r0); sp.len = (ctx->d_len.as<uint32_t>() + ctx->r0);
     sp.blk_prefix = ctx->tile_prefix.as<uint64_t>(); sp.n_seq = (uint32_t)n; sp.k = spec.k; sp.r = spec.r;
     sp.seg_count = ctx->seq_count.as<uint32_t>(); sp.seg_off = nullptr; sp.out = nullptr;
     const uint32_t grid = (uint32_t)ceil_div<uint64_t>(n_segs, 128);
@@ -534,16 +575,11 @@ int run_sketch(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
 
 extern "C" {
 
-int pgr_b200_ctx_shmmrs(pgr_b200_ctx *ctx, const pgr_shmmr_spec *spec_in, int padding, size_t *n_shmmrs) {
-    if (!ctx) { set_error("ctx is NULL"); return PGR_E_ARG; }
-    PGR_TRY(check_spec(spec_in));
-    const pgr_shmmr_spec spec = *spec_in;
-    PGR_CUDA(cudaSetDevice(ctx->device));
+// sequence_to_shmmrs over the sequence range [ctx->r0, ctx->r0 + ctx->rn) of the store
+static int shmmrs_range(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, int padding, size_t *n_shmmrs) {
     cudaStream_t st = ctx->stream;
-    ctx->timer.reset();
-    memset(ctx->counters, 0, sizeof ctx->counters);
     ctx->result_valid = false;
-    const size_t n = ctx->n_seq;
+    const size_t n = ctx->rn;
     PGR_TRY(ctx->off_a.ensure((n + 1) * sizeof(uint64_t)));
     PGR_TRY(ctx->off_b.ensure((n + 1) * sizeof(uint64_t)));
     uint64_t n_cur = 0;
@@ -606,6 +642,17 @@ int pgr_b200_ctx_shmmrs(pgr_b200_ctx *ctx, const pgr_shmmr_spec *spec_in, int pa
     return PGR_OK;
 }
 
+int pgr_b200_ctx_shmmrs(pgr_b200_ctx *ctx, const pgr_shmmr_spec *spec_in, int padding, size_t *n_shmmrs) {
+    if (!ctx) { set_error("ctx is NULL"); return PGR_E_ARG; }
+    PGR_TRY(check_spec(spec_in));
+    PGR_CUDA(cudaSetDevice(ctx->device));
+    ctx->timer.reset();
+    memset(ctx->counters, 0, sizeof ctx->counters);
+    ctx->r0 = 0;
+    ctx->rn = ctx->n_seq;
+    return shmmrs_range(ctx, *spec_in, padding, n_shmmrs);
+}
+
 int pgr_b200_ctx_shmmrs_device(pgr_b200_ctx *ctx, const pgr_mm128 **d_mm, const uint64_t **d_offsets) {
     if (!ctx || !ctx->result_valid) { set_error("no shimmer result available"); return PGR_E_ARG; }
     if (d_mm) *d_mm = ctx->d_result;
@@ -616,15 +663,15 @@ int pgr_b200_ctx_shmmrs_device(pgr_b200_ctx *ctx, const pgr_mm128 **d_mm, const 
 int pgr_b200_ctx_shmmrs_download(pgr_b200_ctx *ctx, pgr_mm128 **out, size_t *offsets) {
     if (!ctx || !ctx->result_valid || !out || !offsets) { set_error("no shimmer result available / NULL argument"); return PGR_E_ARG; }
     PGR_CUDA(cudaSetDevice(ctx->device));
-    const size_t n = ctx->n_seq;
-    pgr_mm128 *o = (pgr_mm128 *)malloc(std::max<size_t>(1, ctx->n_result) * sizeof(pgr_mm128));
+    const size_t n = ctx->rn;
+    pgr_mm128 *o = (pgr_mm128 *)result_alloc(std::max<size_t>(1, ctx->n_result) * sizeof(pgr_mm128));
     if (!o) { set_error("out of host memory"); return PGR_E_ARG; }
     std::vector<uint64_t> off(n + 1);
     cudaError_t e = cudaSuccess;
     if (ctx->n_result) e = cudaMemcpyAsync(o, ctx->d_result, ctx->n_result * sizeof(pgr_mm128), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(off.data(), ctx->d_result_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { free(o); set_error("D2H failed: %s", cudaGetErrorString(e)); return PGR_E_CUDA; }
+    if (e != cudaSuccess) { result_free(o); set_error("D2H failed: %s", cudaGetErrorString(e)); return PGR_E_CUDA; }
     for (size_t i = 0; i <= n; i++) offsets[i] = (size_t)off[i];
     *out = o;
     return PGR_OK;
@@ -661,16 +708,83 @@ static pgr_b200_ctx *tls_ctx() {
     return g_tls_ctx;
 }
 
+// One call per batch with HOST buffers in and out.  The batch is cut into chunks of whole sequences; the H2D copies of
+// all chunks are queued on a copy stream up front and the pipeline of chunk c runs on the compute stream as soon as its
+// bytes have landed, so that PCIe transfer and kernels overlap.  Results are appended to one pinned result buffer.
 int pgr_b200_shmmrs_batch(size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens,
                           const pgr_shmmr_spec *spec, int padding, pgr_mm128 **out, size_t *offsets) {
-    if (!out || !offsets) { set_error("NULL output argument"); return PGR_E_ARG; }
+    if (!out || !offsets || (n && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
     PGR_TRY(check_spec(spec));
     pgr_b200_ctx *ctx = tls_ctx();
     if (!ctx) return PGR_E_NO_DEVICE;
-    PGR_TRY(pgr_b200_ctx_upload(ctx, n, rids, seqs, lens));
-    size_t ns = 0;
-    PGR_TRY(pgr_b200_ctx_shmmrs(ctx, spec, padding, &ns));
-    return pgr_b200_ctx_shmmrs_download(ctx, out, offsets);
+    PGR_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) PGR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    PGR_TRY(upload_layout(ctx, n, rids, seqs, lens));
+    ctx->timer.reset();
+    memset(ctx->counters, 0, sizeof ctx->counters);
+    // chunk boundaries: about 1/16 of the batch each, at least 64 MB, whole sequences
+    const uint64_t chunk_bytes = std::max<uint64_t>(64ull << 20, ctx->total_bases / 16);
+    std::vector<size_t> cut(1, 0);
+    {
+        uint64_t acc = 0;
+        for (size_t i = 0; i < n; i++) {
+            acc += lens[i];
+            if (acc >= chunk_bytes && i + 1 < n) { cut.push_back(i + 1); acc = 0; }
+        }
+        cut.push_back(n);
+    }
+    const size_t n_chunks = cut.size() - 1;
+    std::vector<cudaEvent_t> ev(n_chunks);
+    int rc = PGR_OK;
+    for (size_t c = 0; c < n_chunks; c++) cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming);
+    for (size_t c = 0; c < n_chunks && rc == PGR_OK; c++) {
+        rc = upload_copy(ctx, seqs, lens, cut[c], cut[c + 1], ctx->copy_stream);
+        cudaEventRecord(ev[c], ctx->copy_stream);
+    }
+    // result buffer: expected density + headroom, grown on demand
+    size_t cap = std::max<size_t>(4096, (size_t)(ctx->total_bases / 128));
+    pgr_mm128 *res = (pgr_mm128 *)result_alloc(cap * sizeof(pgr_mm128));
+    size_t n_res = 0;
+    uint64_t launches = 0, l0_total = 0, replayed = 0, retries = 0;
+    std::vector<uint64_t> off;
+    offsets[0] = 0;
+    for (size_t c = 0; c < n_chunks && rc == PGR_OK; c++) {
+        cudaStreamWaitEvent(ctx->stream, ev[c], 0);
+        ctx->r0 = cut[c];
+        ctx->rn = cut[c + 1] - cut[c];
+        memset(ctx->counters, 0, sizeof ctx->counters);
+        size_t ns = 0;
+        if ((rc = shmmrs_range(ctx, *spec, padding, &ns)) != PGR_OK) break;
+        launches += ctx->counters[0]; l0_total += ctx->counters[1]; replayed += ctx->counters[2]; retries += ctx->counters[3];
+        if (n_res + ns > cap) {
+            size_t ncap = std::max(n_res + ns, cap * 2);
+            pgr_mm128 *nres = (pgr_mm128 *)result_alloc(ncap * sizeof(pgr_mm128));
+            if (!nres) { rc = PGR_E_ARG; set_error("out of host memory"); break; }
+            // earlier chunks may still be in flight into `res`
+            cudaStreamSynchronize(ctx->stream);
+            memcpy(nres, res, n_res * sizeof(pgr_mm128));
+            result_free(res);
+            res = nres; cap = ncap;
+        }
+        off.resize(ctx->rn + 1);
+        cudaError_t e = cudaSuccess;
+        if (ns) e = cudaMemcpyAsync(res + n_res, ctx->d_result, ns * sizeof(pgr_mm128), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(off.data(), ctx->d_result_off, (ctx->rn + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+        // the next chunk reuses the device result buffers and `off`: wait for this chunk's copies
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error("D2H failed: %s", cudaGetErrorString(e)); rc = PGR_E_CUDA; break; }
+        for (size_t i = 0; i < ctx->rn; i++) offsets[cut[c] + i + 1] = n_res + (size_t)off[i + 1];
+        n_res += ns;
+    }
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (size_t c = 0; c < n_chunks; c++) cudaEventDestroy(ev[c]);
+    ctx->r0 = 0; ctx->rn = ctx->n_seq;
+    ctx->result_valid = false;  // the device holds only the last chunk
+    ctx->counters[0] = launches; ctx->counters[1] = l0_total; ctx->counters[2] = replayed; ctx->counters[3] = retries;
+    if (rc != PGR_OK) { result_free(res); return rc; }
+    if (n == 0) offsets[0] = 0;
+    *out = res;
+    return PGR_OK;
 }
 
 int pgr_b200_sequence_to_shmmrs(uint32_t rid, const uint8_t *seq, size_t len, const pgr_shmmr_spec *spec, int padding,

@@ -43,7 +43,7 @@ constexpr size_t SEQ_SLACK = 16384;  // readable bytes kept before the first and
 struct pgr_b200_ctx {
     int device = 0;
     int n_sm = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     // sequence store
     pgr::DevBuf seq_store;              // owned copy (upload) — unused when sequences were adopted
     const uint8_t *d_seq = nullptr;     // base pointer used by kernels
@@ -51,6 +51,7 @@ struct pgr_b200_ctx {
     std::vector<uint64_t> h_off;
     std::vector<uint32_t> h_len, h_rid;
     size_t n_seq = 0;
+    size_t r0 = 0, rn = 0;              // sequence range the pipeline currently works on (chunked batches)
     uint64_t total_bases = 0;
     // pinned staging for small sequences and control read-backs
     void *h_stage = nullptr; size_t h_stage_cap = 0;
