@@ -110,6 +110,39 @@ int pgr_b200_ctx_timings(pgr_b200_ctx *ctx, const char *const **names, const flo
  * [3] arena retries */
 int pgr_b200_ctx_counters(pgr_b200_ctx *ctx, uint64_t out[8]);
 
+/* ---- ShmmrFragMap index (CompactSeqDB.frag_map, seq_db.rs:72-100) ------------------------------------------- */
+/* frg_id_mode 0: FASTX numbering, a global running fragment counter (prefix, one per pair, suffix; an empty sequence
+ *                consumes two) — CompactSeqDB::seq_to_compressed, seq_db.rs:203-231,326-347 (pgr-make-frgdb, load_from_fastx)
+ * frg_id_mode 1: AGC numbering, the per-sequence pair ordinal — seq_to_index + load_index_from_seq_vec,
+ *                seq_db.rs:360-418,573-615 (pgr-mdb).   device < 0 = the calling thread's default device. */
+pgr_b200_index *pgr_b200_index_new(const pgr_shmmr_spec *spec, int frg_id_mode, int device);
+void pgr_b200_index_free(pgr_b200_index *idx);
+int pgr_b200_index_get_spec(const pgr_b200_index *idx, pgr_shmmr_spec *spec);
+/* replaces CompactSeqDB::load_seqs_from_seq_vec / load_index_from_seq_vec (seq_db.rs:507-525, :573-615) for the index
+ * part: shimmers of the batch, pairs, tuples appended in (sequence, position) order.  HOST buffers. */
+int pgr_b200_index_add_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens);
+/* two-step variant for the multi-GPU build: stage computes the batch's shimmers and reports how many fragment ids the
+ * batch consumes; commit emits the tuples with `frag_base` = fragments that precede this batch globally. */
+int pgr_b200_index_stage_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
+                               uint64_t *n_frags_in_batch);
+int pgr_b200_index_commit_batch(pgr_b200_index *idx, uint32_t frag_base);
+/* stable sort by (h0,h1) and CSR build; implied by every read access */
+int pgr_b200_index_finalize(pgr_b200_index *idx);
+int pgr_b200_index_counts(pgr_b200_index *idx, size_t *n_keys, size_t *n_sigs, uint32_t *n_frags);
+/* canonical form of the map: keys ascending ((h0,h1) as 2 x u64 each), offsets[n_keys+1], per-key signatures in
+ * insertion order.  Caller-allocated (sizes from pgr_b200_index_counts). */
+int pgr_b200_index_export_csr(pgr_b200_index *idx, uint64_t *keys, uint64_t *offsets, pgr_frag_sig *sigs);
+/* the raw tuples in device memory (40-byte records {u64 h0,h1; u32 frg_id,sid,bgn,end,ori,pad}) for the inter-GPU
+ * exchange, and the way back in */
+int pgr_b200_index_tuples_device(pgr_b200_index *idx, void **dev_tuples, size_t *n_tuples);
+int pgr_b200_index_set_tuples_device(pgr_b200_index *idx, const void *dev_tuples, size_t n_tuples);
+/* stable partition of the tuples into n_parts key ranges (part p holds h0 in [splitters[p-1], splitters[p])), the
+ * layout an all-to-all needs; counts[n_parts] out */
+int pgr_b200_index_partition(pgr_b200_index *idx, size_t n_parts, const uint64_t *splitters, uint64_t *counts);
+/* write_shmmr_map_file (seq_db.rs:1291-1326; keys written ascending) / read_mdb_file (seq_db.rs:1328-1407) */
+int pgr_b200_index_write_mdb(pgr_b200_index *idx, const char *path);
+pgr_b200_index *pgr_b200_index_read_mdb(const char *path, int device);
+
 #ifdef __cplusplus
 }
 #endif

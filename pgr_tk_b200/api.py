@@ -74,6 +74,22 @@ def lib():
         L.pgr_b200_ctx_shmmrs_download.argtypes = [vp, P(vp), vp]
         L.pgr_b200_ctx_timings.argtypes = [vp, P(P(C.c_char_p)), P(P(C.c_float)), P(sz)]
         L.pgr_b200_ctx_counters.argtypes = [vp, P(u64 * 8)]
+        L.pgr_b200_index_new.restype = vp
+        L.pgr_b200_index_new.argtypes = [P(ShmmrSpec), C.c_int, C.c_int]
+        L.pgr_b200_index_free.argtypes = [vp]
+        L.pgr_b200_index_get_spec.argtypes = [vp, P(ShmmrSpec)]
+        L.pgr_b200_index_add_batch.argtypes = [vp, sz, vp, vp, vp]
+        L.pgr_b200_index_stage_batch.argtypes = [vp, sz, vp, vp, vp, P(u64)]
+        L.pgr_b200_index_commit_batch.argtypes = [vp, u32]
+        L.pgr_b200_index_finalize.argtypes = [vp]
+        L.pgr_b200_index_counts.argtypes = [vp, P(sz), P(sz), P(u32)]
+        L.pgr_b200_index_export_csr.argtypes = [vp, vp, vp, vp]
+        L.pgr_b200_index_tuples_device.argtypes = [vp, P(vp), P(sz)]
+        L.pgr_b200_index_set_tuples_device.argtypes = [vp, vp, sz]
+        L.pgr_b200_index_partition.argtypes = [vp, sz, vp, vp]
+        L.pgr_b200_index_write_mdb.argtypes = [vp, C.c_char_p]
+        L.pgr_b200_index_read_mdb.restype = vp
+        L.pgr_b200_index_read_mdb.argtypes = [C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -220,3 +236,97 @@ class Ctx:
         out = (C.c_uint64 * 8)()
         _check(lib().pgr_b200_ctx_counters(self.h, C.byref(out)))
         return list(out)
+
+
+TUPLE = np.dtype([("h0", "<u8"), ("h1", "<u8"), ("frg_id", "<u4"), ("sid", "<u4"), ("bgn", "<u4"), ("end", "<u4"),
+                  ("ori", "<u4"), ("pad", "<u4")])
+
+FRG_ID_FASTX, FRG_ID_AGC = 0, 1
+
+
+class ShmmrIndex:
+    """device-resident ShmmrFragMap: the index part of CompactSeqDB (seq_db.rs:95-100)"""
+
+    def __init__(self, spec=None, frg_id_mode=FRG_ID_FASTX, device=-1, handle=None):
+        self.h = handle if handle is not None else lib().pgr_b200_index_new(C.byref(spec), frg_id_mode, device)
+        if not self.h:
+            _check(-3 if device_count() == 0 else -1)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pgr_b200_index_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @classmethod
+    def read_mdb(cls, path, device=-1):
+        """read_mdb_file (seq_db.rs:1328-1407)"""
+        h = lib().pgr_b200_index_read_mdb(path.encode(), device)
+        if not h:
+            _check(-5)
+        return cls(handle=h)
+
+    def spec(self):
+        s = ShmmrSpec()
+        _check(lib().pgr_b200_index_get_spec(self.h, C.byref(s)))
+        return s
+
+    def add_batch(self, sids, seqs):
+        """load_seqs_from_seq_vec / load_index_from_seq_vec, index part (seq_db.rs:507-525, :573-615)"""
+        arrs, ptrs, lens = _seq_arrays(seqs)
+        s = np.ascontiguousarray(sids, dtype=np.uint32)
+        _check(lib().pgr_b200_index_add_batch(self.h, len(arrs), s.ctypes.data, ptrs, lens))
+
+    def stage_batch(self, sids, seqs):
+        arrs, ptrs, lens = _seq_arrays(seqs)
+        s = np.ascontiguousarray(sids, dtype=np.uint32)
+        nf = C.c_uint64()
+        _check(lib().pgr_b200_index_stage_batch(self.h, len(arrs), s.ctypes.data, ptrs, lens, C.byref(nf)))
+        return nf.value
+
+    def commit_batch(self, frag_base):
+        _check(lib().pgr_b200_index_commit_batch(self.h, frag_base))
+
+    def finalize(self):
+        _check(lib().pgr_b200_index_finalize(self.h))
+
+    def counts(self):
+        nk, ns, nf = C.c_size_t(), C.c_size_t(), C.c_uint32()
+        _check(lib().pgr_b200_index_counts(self.h, C.byref(nk), C.byref(ns), C.byref(nf)))
+        return nk.value, ns.value, nf.value
+
+    def export(self):
+        """canonical CSR: keys[n_keys,2] ascending, offsets[n_keys+1], sigs[n_sigs]"""
+        nk, ns, _ = self.counts()
+        keys = np.zeros((max(nk, 1), 2), dtype=np.uint64)
+        offs = np.zeros(nk + 1, dtype=np.uint64)
+        sigs = np.zeros(max(ns, 1), dtype=SIG)
+        _check(lib().pgr_b200_index_export_csr(self.h, keys.ctypes.data, offs.ctypes.data, sigs.ctypes.data))
+        return keys[:nk], offs, sigs[:ns]
+
+    def as_map(self):
+        keys, offs, sigs = self.export()
+        m = {}
+        for i in range(len(keys)):
+            v = sigs[int(offs[i]):int(offs[i + 1])]
+            m[(int(keys[i, 0]), int(keys[i, 1]))] = [(int(a["frg_id"]), int(a["sid"]), int(a["bgn"]), int(a["end"]), int(a["ori"])) for a in v]
+        return m
+
+    def tuples_device(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib().pgr_b200_index_tuples_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def set_tuples_device(self, dev_ptr, n):
+        _check(lib().pgr_b200_index_set_tuples_device(self.h, C.c_void_p(dev_ptr), n))
+
+    def partition(self, splitters):
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        counts = np.zeros(len(sp) + 1, dtype=np.uint64)
+        _check(lib().pgr_b200_index_partition(self.h, len(sp) + 1, sp.ctypes.data, counts.ctypes.data))
+        return counts
+
+    def write_mdb(self, path):
+        """write_shmmr_map_file (seq_db.rs:1291-1326), keys ascending"""
+        _check(lib().pgr_b200_index_write_mdb(self.h, path.encode()))

@@ -116,7 +116,6 @@ int pgr_b200_ctx::ensure_ctl(size_t bytes) {
     return PGR_OK;
 }
 
-#define PGR_TRY(x) do { int rc__ = (x); if (rc__ != PGR_OK) return rc__; } while (0)
 
 extern "C" {
 
@@ -575,8 +574,10 @@ int run_sketch(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
 
 extern "C" {
 
+}  // extern "C"
+
 // sequence_to_shmmrs over the sequence range [ctx->r0, ctx->r0 + ctx->rn) of the store
-static int shmmrs_range(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, int padding, size_t *n_shmmrs) {
+int pgr::shmmrs_range(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, int padding, size_t *n_shmmrs) {
     cudaStream_t st = ctx->stream;
     ctx->result_valid = false;
     const size_t n = ctx->rn;
@@ -642,6 +643,8 @@ static int shmmrs_range(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, int paddi
     return PGR_OK;
 }
 
+extern "C" {
+
 int pgr_b200_ctx_shmmrs(pgr_b200_ctx *ctx, const pgr_shmmr_spec *spec_in, int padding, size_t *n_shmmrs) {
     if (!ctx) { set_error("ctx is NULL"); return PGR_E_ARG; }
     PGR_TRY(check_spec(spec_in));
@@ -650,7 +653,7 @@ int pgr_b200_ctx_shmmrs(pgr_b200_ctx *ctx, const pgr_shmmr_spec *spec_in, int pa
     memset(ctx->counters, 0, sizeof ctx->counters);
     ctx->r0 = 0;
     ctx->rn = ctx->n_seq;
-    return shmmrs_range(ctx, *spec_in, padding, n_shmmrs);
+    return pgr::shmmrs_range(ctx, *spec_in, padding, n_shmmrs);
 }
 
 int pgr_b200_ctx_shmmrs_device(pgr_b200_ctx *ctx, const pgr_mm128 **d_mm, const uint64_t **d_offsets) {
@@ -693,35 +696,38 @@ int pgr_b200_ctx_counters(pgr_b200_ctx *ctx, uint64_t out[8]) {
 }
 
 // ---- one-shot host API (thread-local default context on device 0) ---------------------------------------------
+}  // extern "C"
+
 static thread_local int g_default_device = 0;
 static thread_local pgr_b200_ctx *g_tls_ctx = nullptr;  // leaked at thread exit on purpose: CUDA may already be torn down
+int pgr::default_device() { return g_default_device; }
 
-int pgr_b200_set_default_device(int device) {
+extern "C" int pgr_b200_set_default_device(int device) {
     if (device < 0 || device >= pgr_b200_device_count()) { set_error("device %d out of range", device); return PGR_E_ARG; }
     if (g_tls_ctx && g_tls_ctx->device != device) { pgr_b200_ctx_free(g_tls_ctx); g_tls_ctx = nullptr; }
     g_default_device = device;
     return PGR_OK;
 }
 
-static pgr_b200_ctx *tls_ctx() {
+pgr_b200_ctx *pgr::tls_ctx() {
     if (!g_tls_ctx) g_tls_ctx = pgr_b200_ctx_new(g_default_device);
     return g_tls_ctx;
 }
 
-// One call per batch with HOST buffers in and out.  The batch is cut into chunks of whole sequences; the H2D copies of
-// all chunks are queued on a copy stream up front and the pipeline of chunk c runs on the compute stream as soon as its
-// bytes have landed, so that PCIe transfer and kernels overlap.  Results are appended to one pinned result buffer.
-int pgr_b200_shmmrs_batch(size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens,
-                          const pgr_shmmr_spec *spec, int padding, pgr_mm128 **out, size_t *offsets) {
-    if (!out || !offsets || (n && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
-    PGR_TRY(check_spec(spec));
-    pgr_b200_ctx *ctx = tls_ctx();
-    if (!ctx) return PGR_E_NO_DEVICE;
+extern "C" {
+
+}  // extern "C"
+
+// Host batch -> device, chunk by chunk.  The batch is cut into chunks of whole sequences; the H2D copies of all chunks
+// are queued on a copy stream up front and the shimmer pipeline of chunk c runs on the compute stream as soon as its
+// bytes have landed, so that PCIe transfer and kernels overlap.  on_chunk(first_seq, n_seqs, n_shmmrs) consumes the
+// chunk's device-resident result (ctx->d_result / ctx->d_result_off) before the next chunk overwrites it.
+int pgr::run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens,
+                     const pgr_shmmr_spec &spec, int padding, const std::function<int(size_t, size_t, size_t)> &on_chunk) {
     PGR_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->copy_stream) PGR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     PGR_TRY(upload_layout(ctx, n, rids, seqs, lens));
     ctx->timer.reset();
-    memset(ctx->counters, 0, sizeof ctx->counters);
     // chunk boundaries: about 1/16 of the batch each, at least 64 MB, whole sequences
     const uint64_t chunk_bytes = std::max<uint64_t>(64ull << 20, ctx->total_bases / 16);
     std::vector<size_t> cut(1, 0);
@@ -741,48 +747,65 @@ int pgr_b200_shmmrs_batch(size_t n, const uint32_t *rids, const uint8_t *const *
         rc = upload_copy(ctx, seqs, lens, cut[c], cut[c + 1], ctx->copy_stream);
         cudaEventRecord(ev[c], ctx->copy_stream);
     }
-    // result buffer: expected density + headroom, grown on demand
-    size_t cap = std::max<size_t>(4096, (size_t)(ctx->total_bases / 128));
-    pgr_mm128 *res = (pgr_mm128 *)result_alloc(cap * sizeof(pgr_mm128));
-    size_t n_res = 0;
-    uint64_t launches = 0, l0_total = 0, replayed = 0, retries = 0;
-    std::vector<uint64_t> off;
-    offsets[0] = 0;
+    uint64_t tot[8] = {0};
     for (size_t c = 0; c < n_chunks && rc == PGR_OK; c++) {
         cudaStreamWaitEvent(ctx->stream, ev[c], 0);
         ctx->r0 = cut[c];
         ctx->rn = cut[c + 1] - cut[c];
         memset(ctx->counters, 0, sizeof ctx->counters);
         size_t ns = 0;
-        if ((rc = shmmrs_range(ctx, *spec, padding, &ns)) != PGR_OK) break;
-        launches += ctx->counters[0]; l0_total += ctx->counters[1]; replayed += ctx->counters[2]; retries += ctx->counters[3];
-        if (n_res + ns > cap) {
-            size_t ncap = std::max(n_res + ns, cap * 2);
-            pgr_mm128 *nres = (pgr_mm128 *)result_alloc(ncap * sizeof(pgr_mm128));
-            if (!nres) { rc = PGR_E_ARG; set_error("out of host memory"); break; }
-            // earlier chunks may still be in flight into `res`
-            cudaStreamSynchronize(ctx->stream);
-            memcpy(nres, res, n_res * sizeof(pgr_mm128));
-            result_free(res);
-            res = nres; cap = ncap;
-        }
-        off.resize(ctx->rn + 1);
-        cudaError_t e = cudaSuccess;
-        if (ns) e = cudaMemcpyAsync(res + n_res, ctx->d_result, ns * sizeof(pgr_mm128), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(off.data(), ctx->d_result_off, (ctx->rn + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
-        // the next chunk reuses the device result buffers and `off`: wait for this chunk's copies
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { set_error("D2H failed: %s", cudaGetErrorString(e)); rc = PGR_E_CUDA; break; }
-        for (size_t i = 0; i < ctx->rn; i++) offsets[cut[c] + i + 1] = n_res + (size_t)off[i + 1];
-        n_res += ns;
+        if ((rc = shmmrs_range(ctx, spec, padding, &ns)) != PGR_OK) break;
+        for (int i = 0; i < 8; i++) tot[i] += ctx->counters[i];
+        rc = on_chunk(cut[c], ctx->rn, ns);
     }
     cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
     for (size_t c = 0; c < n_chunks; c++) cudaEventDestroy(ev[c]);
     ctx->r0 = 0; ctx->rn = ctx->n_seq;
     ctx->result_valid = false;  // the device holds only the last chunk
-    ctx->counters[0] = launches; ctx->counters[1] = l0_total; ctx->counters[2] = replayed; ctx->counters[3] = retries;
+    memcpy(ctx->counters, tot, sizeof tot);
+    return rc;
+}
+
+extern "C" {
+
+// replaces CompactSeqDB::get_shmmrs_from_seqs: one call per batch with HOST buffers in and out
+int pgr_b200_shmmrs_batch(size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens,
+                          const pgr_shmmr_spec *spec, int padding, pgr_mm128 **out, size_t *offsets) {
+    if (!out || !offsets || (n && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
+    PGR_TRY(check_spec(spec));
+    pgr_b200_ctx *ctx = pgr::tls_ctx();
+    if (!ctx) return PGR_E_NO_DEVICE;
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) total += lens[i];
+    // result buffer: expected density + headroom, grown on demand
+    size_t cap = std::max<size_t>(4096, (size_t)(total / 128));
+    pgr_mm128 *res = (pgr_mm128 *)result_alloc(cap * sizeof(pgr_mm128));
+    if (!res) { set_error("out of host memory"); return PGR_E_ARG; }
+    size_t n_res = 0;
+    std::vector<uint64_t> off;
+    offsets[0] = 0;
+    const int rc = pgr::run_chunked(ctx, n, rids, seqs, lens, *spec, padding, [&](size_t c0, size_t cn, size_t ns) -> int {
+        if (n_res + ns > cap) {
+            const size_t ncap = std::max(n_res + ns, cap * 2);
+            pgr_mm128 *nres = (pgr_mm128 *)result_alloc(ncap * sizeof(pgr_mm128));
+            if (!nres) { set_error("out of host memory"); return PGR_E_ARG; }
+            memcpy(nres, res, n_res * sizeof(pgr_mm128));  // earlier chunks were synchronised below
+            result_free(res);
+            res = nres; cap = ncap;
+        }
+        off.resize(cn + 1);
+        cudaError_t e = cudaSuccess;
+        if (ns) e = cudaMemcpyAsync(res + n_res, ctx->d_result, ns * sizeof(pgr_mm128), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(off.data(), ctx->d_result_off, (cn + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+        // the next chunk reuses the device result buffers and `off`: wait for this chunk's copies
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error("D2H failed: %s", cudaGetErrorString(e)); return PGR_E_CUDA; }
+        for (size_t i = 0; i < cn; i++) offsets[c0 + i + 1] = n_res + (size_t)off[i + 1];
+        n_res += ns;
+        return PGR_OK;
+    });
     if (rc != PGR_OK) { result_free(res); return rc; }
-    if (n == 0) offsets[0] = 0;
     *out = res;
     return PGR_OK;
 }

@@ -1,5 +1,6 @@
 // ctx.cuh — device context: streams, grow-only device buffers, the device sequence store.
 #pragma once
+#include <functional>
 #include <vector>
 
 #include "common.cuh"
@@ -73,3 +74,14 @@ struct pgr_b200_ctx {
     int ensure_stage(size_t bytes);
     int ensure_ctl(size_t bytes);
 };
+
+namespace pgr {
+int check_spec(const pgr_shmmr_spec *s);
+int default_device();
+pgr_b200_ctx *tls_ctx();
+int shmmrs_range(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, int padding, size_t *n_shmmrs);
+int run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const uint8_t *const *seqs, const size_t *lens,
+                const pgr_shmmr_spec &spec, int padding, const std::function<int(size_t, size_t, size_t)> &on_chunk);
+}  // namespace pgr
+
+#define PGR_TRY(x) do { int rc__ = (x); if (rc__ != PGR_OK) return rc__; } while (0)

@@ -1,0 +1,35 @@
+// index.cuh — pgr_b200_index: device-resident ShmmrFragMap.
+#pragma once
+#include <vector>
+
+#include "ctx.cuh"
+#include "index_kernels.cuh"
+#include "shmmr_kernels.cuh"
+
+struct pgr_b200_index {
+    pgr_shmmr_spec spec;
+    int mode = 0;                     // 0 = FASTX global fragment counter, 1 = AGC per-sequence pair ordinal
+    pgr_b200_ctx *ctx = nullptr;      // owned: shimmer pipeline + streams
+    pgr::DevBuf tuples;               // FragTuple[n_tuples], insertion order
+    uint64_t n_tuples = 0;
+    uint32_t n_frags = 0;             // == frags.len() of the reference's FASTX path (seq_db.rs:203)
+    // CSR, valid when finalized
+    pgr::DevBuf ukeys, offsets, sigs;
+    uint64_t n_keys = 0;
+    bool finalized = false;
+    // staged batch (multi-GPU build: shimmers first, fragment-id base later)
+    bool staged = false;
+    std::vector<uint32_t> staged_sids;
+    size_t staged_n_mm = 0;
+    // scratch
+    pgr::DevBuf keysA, keysB, idxA, idxB, hist, head, block_sum, block_prefix, d_sid, d_pair_off, d_frg_base;
+    pgr::DevBuf qtuples, q_hit_begin, q_hit_count, scratch0, scratch1, scratch2, scratch3;
+    uint64_t launches = 0;
+};
+
+namespace pgr {
+int index_reserve_tuples(pgr_b200_index *idx, uint64_t need);
+int index_batch_tuples(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
+                       bool query_mode, DevBuf *qbuf, uint64_t *n_pairs_total, std::vector<uint64_t> *pairs_per_seq);
+int index_sort(pgr_b200_index *idx, uint64_t n, int first_pass, int last_pass);
+}  // namespace pgr

@@ -1,0 +1,3 @@
+// lib.cu — single translation unit of libpgr_b200.so (kernels are defined in headers shared by the parts below).
+#include "ctx.cu"
+#include "index.cu"
