@@ -143,6 +143,27 @@ int pgr_b200_index_partition(pgr_b200_index *idx, size_t n_parts, const uint64_t
 int pgr_b200_index_write_mdb(pgr_b200_index *idx, const char *path);
 pgr_b200_index *pgr_b200_index_read_mdb(const char *path, int device);
 
+/* ---- query, chaining, adjacency ------------------------------------------------------------------------------ */
+/* replaces seq_db::raw_query_fragment(&frag_map, &query, &spec) -> Vec<FragmentHit> (seq_db.rs:1200-1228): per query
+ * shimmer pair (strict '<' canonicalisation, :1213-1217) its key/position/orientation and the signatures of the key:
+ * hits[hit_off[i] .. hit_off[i+1]).  Library-allocated outputs (pgr_b200_free). */
+int pgr_b200_raw_query(pgr_b200_index *idx, const uint8_t *seq, size_t len, pgr_query_pair **pairs, size_t *n_pairs, uint64_t **hit_off,
+                       pgr_frag_sig **hits);
+/* replaces SeqIndexDB::query_fragment_to_hps (ext.rs:252-282 -> aln.rs:147-242) for a batch of queries (the reference
+ * runs one rayon task per query, pgr-query.rs:135).  Canonical forms where the reference leaks hash-map order: targets
+ * ascending by sid; equal-score chain heads by position in the q_bgn-sorted hit list. */
+int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_queries, const uint8_t *const *seqs, const size_t *lens,
+                         const pgr_query_params *params, pgr_query_result **out);
+void pgr_b200_query_result_free(pgr_query_result *r);
+/* replaces aln::sparse_aln(&mut sp_hits, max_span, penalty, max_gap, oriented) (aln.rs:12-142) on one hit list; hits is
+ * sorted in place (stable by q_bgn, aln.rs:21); max_gap < 0 = None.  PGR_E_ASSERT when n < 2 (aln.rs:24). */
+int pgr_b200_sparse_aln(pgr_hit_pair *hits, size_t n, uint32_t max_span, float penalty, int64_t max_gap, int oriented, size_t *n_chains,
+                        uint64_t **chain_off, float **scores, pgr_hit_pair **chain_hits);
+/* replaces seq_db::frag_map_to_adj_list(&frag_map, min_count, keeps) -> AdjList (seq_db.rs:876-944); has_keeps = 0
+ * encodes None */
+int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *keeps, size_t n_keeps, int has_keeps, pgr_adj_pair **out,
+                      size_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,19 @@ class ShmmrSpec(C.Structure):
         super().__init__(w, k, r, min_span, 1 if sketch else 0)
 
 
+class QueryParams(C.Structure):
+    """arguments of query_fragment_to_hps (aln.rs:147-158); Option<u32> = negative for None"""
+    _fields_ = [("penalty", C.c_float), ("max_count", C.c_int64), ("max_count_query", C.c_int64), ("max_count_target", C.c_int64),
+                ("max_aln_span", C.c_int64), ("max_gap", C.c_int64), ("oriented", C.c_int32)]
+
+
+class QueryResult(C.Structure):
+    _fields_ = [("n_queries", C.c_size_t), ("n_targets", C.c_size_t), ("n_chains", C.c_size_t), ("n_hits", C.c_size_t),
+                ("q_target_off", C.POINTER(C.c_uint64)), ("target_sid", C.POINTER(C.c_uint32)),
+                ("target_chain_off", C.POINTER(C.c_uint64)), ("chain_score", C.POINTER(C.c_float)),
+                ("chain_hit_off", C.POINTER(C.c_uint64)), ("hits", C.c_void_p)]
+
+
 def library_path():
     return _LIB
 
@@ -90,6 +103,11 @@ def lib():
         L.pgr_b200_index_write_mdb.argtypes = [vp, C.c_char_p]
         L.pgr_b200_index_read_mdb.restype = vp
         L.pgr_b200_index_read_mdb.argtypes = [C.c_char_p, C.c_int]
+        L.pgr_b200_raw_query.argtypes = [vp, vp, sz, P(vp), P(sz), P(vp), P(vp)]
+        L.pgr_b200_query_batch.argtypes = [vp, sz, vp, vp, P(QueryParams), P(P(QueryResult))]
+        L.pgr_b200_query_result_free.argtypes = [P(QueryResult)]
+        L.pgr_b200_sparse_aln.argtypes = [vp, sz, u32, C.c_float, C.c_int64, C.c_int, P(sz), P(vp), P(vp), P(vp)]
+        L.pgr_b200_adj_list.argtypes = [vp, sz, vp, sz, C.c_int, P(vp), P(sz)]
         _lib = L
     return _lib
 
@@ -330,3 +348,58 @@ class ShmmrIndex:
     def write_mdb(self, path):
         """write_shmmr_map_file (seq_db.rs:1291-1326), keys ascending"""
         _check(lib().pgr_b200_index_write_mdb(self.h, path.encode()))
+
+    def raw_query(self, seq):
+        """raw_query_fragment (seq_db.rs:1200-1228) -> (pairs QPAIR[n], hit_off[n+1], hits SIG[...])"""
+        a = _bytes(seq)
+        pairs, n, off, hits = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_void_p()
+        _check(lib().pgr_b200_raw_query(self.h, a.ctypes.data, a.size, C.byref(pairs), C.byref(n), C.byref(off), C.byref(hits)))
+        offs = _take(off, n.value + 1, np.uint64)
+        return _take(pairs, n.value, QPAIR), offs, _take(hits, int(offs[-1]), SIG)
+
+    def query_batch(self, seqs, penalty, max_count=None, max_count_query=None, max_count_target=None, max_aln_span=None,
+                    max_gap=None, oriented=False):
+        """query_fragment_to_hps (ext.rs:252-282) for every sequence of `seqs`.
+        Returns (q_target_off, target_sid, target_chain_off, chain_score, chain_hit_off, hits HITPAIR[...])"""
+        arrs, ptrs, lens = _seq_arrays(seqs)
+        opt = lambda v: -1 if v is None else int(v)
+        prm = QueryParams(penalty, opt(max_count), opt(max_count_query), opt(max_count_target), opt(max_aln_span), opt(max_gap), int(oriented))
+        res = C.POINTER(QueryResult)()
+        _check(lib().pgr_b200_query_batch(self.h, len(arrs), ptrs, lens, C.byref(prm), C.byref(res)))
+        r = res.contents
+
+        def arr(ptr, n, dt):
+            dt = np.dtype(dt)
+            if n == 0:
+                return np.zeros(0, dtype=dt)
+            addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
+            return np.frombuffer((C.c_char * (n * dt.itemsize)).from_address(addr), dtype=dt, count=n).copy()
+
+        out = (arr(r.q_target_off, r.n_queries + 1, np.uint64), arr(r.target_sid, r.n_targets, np.uint32),
+               arr(r.target_chain_off, r.n_targets + 1, np.uint64), arr(r.chain_score, r.n_chains, np.float32),
+               arr(r.chain_hit_off, r.n_chains + 1, np.uint64), arr(r.hits, r.n_hits, HITPAIR))
+        lib().pgr_b200_query_result_free(res)
+        return out
+
+    def query_fragment_to_hps(self, seq, penalty, **kw):
+        """single-query form: (target_sid, target_chain_off, chain_score, chain_hit_off, hits)"""
+        r = self.query_batch([seq], penalty, **kw)
+        return r[1:]
+
+    def adj_list(self, min_count, keeps=None):
+        """frag_map_to_adj_list (seq_db.rs:876-944) -> ADJ[...]"""
+        k = np.ascontiguousarray(keeps if keeps is not None else [], dtype=np.uint32)
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(lib().pgr_b200_adj_list(self.h, min_count, k.ctypes.data, k.size, int(keeps is not None), C.byref(out), C.byref(n)))
+        return _take(out, n.value, ADJ)
+
+
+def sparse_aln(hits, max_span, penalty, max_gap=None, oriented=False):
+    """aln::sparse_aln (aln.rs:12-142) -> (scores, chain_off, chain_hits, sorted_hits)"""
+    h = np.ascontiguousarray(hits, dtype=HITPAIR).copy()
+    nc = C.c_size_t()
+    off, sc, ch = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _check(lib().pgr_b200_sparse_aln(h.ctypes.data, h.size, max_span, penalty, -1 if max_gap is None else int(max_gap), int(oriented),
+                                     C.byref(nc), C.byref(off), C.byref(sc), C.byref(ch)))
+    off_a = _take(off, nc.value + 1, np.uint64)
+    return _take(sc, nc.value, np.float32), off_a, _take(ch, int(off_a[-1]), HITPAIR), h

@@ -189,7 +189,9 @@ void pgr_b200_index_free(pgr_b200_index *idx) {
     cudaStreamSynchronize(idx->ctx->stream);
     DevBuf *bufs[] = {&idx->tuples, &idx->ukeys, &idx->offsets, &idx->sigs, &idx->keysA, &idx->keysB, &idx->idxA, &idx->idxB, &idx->hist,
                       &idx->head, &idx->block_sum, &idx->block_prefix, &idx->d_sid, &idx->d_pair_off, &idx->d_frg_base, &idx->qtuples,
-                      &idx->q_hit_begin, &idx->q_hit_count, &idx->scratch0, &idx->scratch1, &idx->scratch2, &idx->scratch3};
+                      &idx->q_hit_begin, &idx->q_hit_count, &idx->scratch0, &idx->scratch1, &idx->scratch2, &idx->scratch3,
+                      &idx->sid_count, &idx->hitsA, &idx->hitsB, &idx->seg_keys, &idx->seg_off, &idx->chain_f, &idx->chain_u, &idx->chain_b,
+                      &idx->chain_seg};
     for (auto b : bufs) b->release();
     pgr_b200_ctx_free(idx->ctx);
     delete idx;
@@ -240,6 +242,7 @@ int pgr_b200_index_commit_batch(pgr_b200_index *idx, uint32_t frag_base) {
 int pgr_b200_index_finalize(pgr_b200_index *idx) {
     if (!idx) { set_error("idx is NULL"); return PGR_E_ARG; }
     if (idx->finalized) return PGR_OK;
+    idx->sid_count_valid = false;
     pgr_b200_ctx *ctx = idx->ctx;
     PGR_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

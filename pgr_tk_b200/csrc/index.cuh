@@ -24,6 +24,8 @@ struct pgr_b200_index {
     // scratch
     pgr::DevBuf keysA, keysB, idxA, idxB, hist, head, block_sum, block_prefix, d_sid, d_pair_off, d_frg_base;
     pgr::DevBuf qtuples, q_hit_begin, q_hit_count, scratch0, scratch1, scratch2, scratch3;
+    pgr::DevBuf sid_count, hitsA, hitsB, seg_keys, seg_off, chain_f, chain_u, chain_b, chain_seg;
+    bool sid_count_valid = false;
     uint64_t launches = 0;
 };
 
@@ -32,4 +34,6 @@ int index_reserve_tuples(pgr_b200_index *idx, uint64_t need);
 int index_batch_tuples(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
                        bool query_mode, DevBuf *qbuf, uint64_t *n_pairs_total, std::vector<uint64_t> *pairs_per_seq);
 int index_sort(pgr_b200_index *idx, uint64_t n, int first_pass, int last_pass);
+__global__ void iota_kernel(uint32_t *p, uint64_t n);
+__global__ void set_u64_kernel(uint64_t *p, uint64_t v);
 }  // namespace pgr

@@ -1,3 +1,4 @@
 // lib.cu — single translation unit of libpgr_b200.so (kernels are defined in headers shared by the parts below).
 #include "ctx.cu"
 #include "index.cu"
+#include "query.cu"

@@ -1,0 +1,382 @@
+// query.cu — raw_query_fragment (seq_db.rs:1200-1228), query_fragment_to_hps (aln.rs:147-242 via ext.rs:252-282),
+// sparse_aln (aln.rs:12-142) and frag_map_to_adj_list (seq_db.rs:876-944) against the device-resident index.
+#include <algorithm>
+#include <cstring>
+
+#include "index.cuh"
+#include "query_kernels.cuh"
+
+using namespace pgr;
+
+namespace {
+
+int scan_u32(pgr_b200_index *idx, const uint32_t *v, uint64_t n, uint64_t *out /* n+1 */, uint64_t *total) {
+    cudaStream_t st = idx->ctx->stream;
+    if (n == 0) {
+        PGR_CUDA(cudaMemsetAsync(out, 0, sizeof(uint64_t), st));
+        if (total) *total = 0;
+        return PGR_OK;
+    }
+    const uint32_t nb = (uint32_t)ceil_div<uint64_t>(n + 1, SC_BLK);  // +1: slot n (the total) must be owned by a block
+    PGR_TRY(idx->block_sum.ensure(nb * sizeof(uint32_t)));
+    PGR_TRY(idx->block_prefix.ensure((nb + 1) * sizeof(uint64_t)));
+    scan_reduce_kernel<<<nb, SC_NT, 0, st>>>(v, n, idx->block_sum.as<uint32_t>());
+    block_scan_kernel<<<1, 1024, 0, st>>>(idx->block_sum.as<uint32_t>(), idx->block_prefix.as<uint64_t>(), nb);
+    scan_apply_kernel<<<nb, SC_NT, 0, st>>>(v, n, idx->block_prefix.as<uint64_t>(), out);
+    idx->launches += 3;
+    PGR_CUDA(cudaGetLastError());
+    if (total) {
+        PGR_TRY(idx->ctx->ensure_ctl(64));
+        PGR_CUDA(cudaMemcpyAsync(idx->ctx->h_ctl, out + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaStreamSynchronize(st));
+        *total = *(uint64_t *)idx->ctx->h_ctl;
+    }
+    return PGR_OK;
+}
+
+// per-signature same-sid counts of the index (computed once per finalize)
+int ensure_sid_count(pgr_b200_index *idx) {
+    PGR_TRY(pgr_b200_index_finalize(idx));
+    if (idx->sid_count_valid) return PGR_OK;
+    PGR_TRY(idx->sid_count.ensure(std::max<uint64_t>(1, idx->n_tuples) * sizeof(uint32_t)));
+    if (idx->n_keys) {
+        sid_count_kernel<<<(uint32_t)ceil_div<uint64_t>(idx->n_keys, 128), 128, 0, idx->ctx->stream>>>(
+            idx->sigs.as<pgr_frag_sig>(), idx->offsets.as<uint64_t>(), idx->n_keys, idx->sid_count.as<uint32_t>());
+        idx->launches += 1;
+        PGR_CUDA(cudaGetLastError());
+    }
+    idx->sid_count_valid = true;
+    return PGR_OK;
+}
+
+// query shimmers -> query tuples (device, idx->qtuples) + pair offsets per query (host) + lookup
+int query_pairs_and_lookup(pgr_b200_index *idx, size_t n_q, const uint8_t *const *seqs, const size_t *lens, uint64_t *n_qp_out,
+                           std::vector<uint64_t> *qp_off_out) {
+    PGR_TRY(pgr_b200_index_finalize(idx));
+    cudaStream_t st = idx->ctx->stream;
+    std::vector<uint32_t> qids(n_q);
+    for (size_t i = 0; i < n_q; i++) qids[i] = (uint32_t)i;
+    std::vector<uint64_t> per_seq;
+    uint64_t n_qp = 0;
+    PGR_TRY(index_batch_tuples(idx, n_q, qids.data(), seqs, lens, true, &idx->qtuples, &n_qp, &per_seq));
+    qp_off_out->assign(n_q + 1, 0);
+    for (size_t i = 0; i < n_q; i++) (*qp_off_out)[i + 1] = (*qp_off_out)[i] + per_seq[i];
+    *n_qp_out = n_qp;
+    PGR_TRY(idx->q_hit_begin.ensure(std::max<uint64_t>(1, n_qp) * sizeof(uint64_t)));
+    PGR_TRY(idx->q_hit_count.ensure(std::max<uint64_t>(1, n_qp) * sizeof(uint32_t)));
+    if (n_qp) {
+        lookup_kernel<<<(uint32_t)ceil_div<uint64_t>(n_qp, 256), 256, 0, st>>>(idx->qtuples.as<FragTuple>(), n_qp, idx->ukeys.as<SortKey>(),
+                                                                              idx->offsets.as<uint64_t>(), idx->n_keys,
+                                                                              idx->q_hit_begin.as<uint64_t>(), idx->q_hit_count.as<uint32_t>());
+        idx->launches += 1;
+        PGR_CUDA(cudaGetLastError());
+    }
+    return PGR_OK;
+}
+
+template <class T>
+T *host_dup(const std::vector<T> &v) {
+    T *p = (T *)malloc(std::max<size_t>(1, v.size()) * sizeof(T));
+    if (p && !v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+// replaces seq_db::raw_query_fragment(frag_map, query, spec) -> Vec<FragmentHit>
+int pgr_b200_raw_query(pgr_b200_index *idx, const uint8_t *seq, size_t len, pgr_query_pair **pairs, size_t *n_pairs, uint64_t **hit_off,
+                       pgr_frag_sig **hits) {
+    if (!idx || !pairs || !n_pairs || !hit_off || !hits) { set_error("NULL argument"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(idx->ctx->device));
+    cudaStream_t st = idx->ctx->stream;
+    const uint8_t *sp[1] = {seq};
+    const size_t ln[1] = {len};
+    uint64_t n_qp = 0;
+    std::vector<uint64_t> qp_off;
+    PGR_TRY(query_pairs_and_lookup(idx, 1, sp, ln, &n_qp, &qp_off));
+    std::vector<FragTuple> qt(n_qp);
+    std::vector<uint64_t> hb(n_qp);
+    std::vector<uint32_t> hc(n_qp);
+    if (n_qp) {
+        PGR_CUDA(cudaMemcpyAsync(qt.data(), idx->qtuples.p, n_qp * sizeof(FragTuple), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(hb.data(), idx->q_hit_begin.p, n_qp * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(hc.data(), idx->q_hit_count.p, n_qp * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<pgr_query_pair> qp(n_qp);
+    std::vector<uint64_t> off(n_qp + 1, 0);
+    for (uint64_t i = 0; i < n_qp; i++) {
+        memset(&qp[i], 0, sizeof qp[i]);
+        qp[i].h0 = qt[i].h0; qp[i].h1 = qt[i].h1; qp[i].bgn = qt[i].bgn; qp[i].end = qt[i].end; qp[i].ori = (uint8_t)qt[i].ori;
+        off[i + 1] = off[i] + hc[i];
+    }
+    std::vector<pgr_frag_sig> hs(off[n_qp]);
+    for (uint64_t i = 0; i < n_qp; i++)
+        if (hc[i]) PGR_CUDA(cudaMemcpyAsync(hs.data() + off[i], idx->sigs.as<pgr_frag_sig>() + hb[i], hc[i] * sizeof(pgr_frag_sig), cudaMemcpyDeviceToHost, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    *pairs = host_dup(qp);
+    *n_pairs = n_qp;
+    *hit_off = host_dup(off);
+    *hits = host_dup(hs);
+    return PGR_OK;
+}
+
+void pgr_b200_query_result_free(pgr_query_result *r) {
+    if (!r) return;
+    free(r->q_target_off); free(r->target_sid); free(r->target_chain_off); free(r->chain_score); free(r->chain_hit_off); free(r->hits);
+    free(r);
+}
+
+// replaces SeqIndexDB::query_fragment_to_hps (ext.rs:252-282) for a batch of queries
+int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *seqs, const size_t *lens, const pgr_query_params *prm,
+                         pgr_query_result **out) {
+    if (!idx || !prm || !out || (n_q && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(idx->ctx->device));
+    pgr_b200_ctx *ctx = idx->ctx;
+    cudaStream_t st = ctx->stream;
+    PGR_TRY(ensure_sid_count(idx));
+    uint64_t n_qp = 0;
+    std::vector<uint64_t> qp_off;
+    PGR_TRY(query_pairs_and_lookup(idx, n_q, seqs, lens, &n_qp, &qp_off));
+
+    QueryFilter f;
+    f.max_count = prm->max_count < 0 ? 128u : (uint32_t)prm->max_count;
+    f.max_count_query = prm->max_count_query < 0 ? 128u : (uint32_t)prm->max_count_query;
+    f.max_count_target = prm->max_count_target < 0 ? 128u : (uint32_t)prm->max_count_target;
+    const uint32_t max_span = prm->max_aln_span < 0 ? 8u : (uint32_t)prm->max_aln_span;
+
+    std::vector<uint64_t> q_target_off(n_q + 1, 0), target_chain_off(1, 0), chain_hit_off(1, 0);
+    std::vector<uint32_t> target_sid;
+    std::vector<float> chain_score;
+    std::vector<pgr_hit_pair> hits_out;
+
+    uint64_t n_hits = 0;
+    if (n_qp) {
+        // per-pair statistics, filters, expansion
+        PGR_TRY(idx->scratch0.ensure((n_q + 1) * sizeof(uint64_t)));
+        PGR_CUDA(cudaMemcpyAsync(idx->scratch0.p, qp_off.data(), (n_q + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        PGR_TRY(idx->scratch1.ensure(n_qp * sizeof(uint32_t) * 2));
+        uint32_t *qcount = idx->scratch1.as<uint32_t>(), *nh = qcount + n_qp;
+        const uint32_t g = (uint32_t)ceil_div<uint64_t>(n_qp, 256);
+        qpair_count_kernel<<<g, 256, 0, st>>>(idx->qtuples.as<FragTuple>(), n_qp, idx->scratch0.as<uint64_t>(), qcount);
+        hit_count_kernel<<<g, 256, 0, st>>>(n_qp, qcount, idx->q_hit_begin.as<uint64_t>(), idx->q_hit_count.as<uint32_t>(),
+                                            idx->sid_count.as<uint32_t>(), f, nh);
+        idx->launches += 2;
+        PGR_TRY(idx->scratch2.ensure((n_qp + 1) * sizeof(uint64_t)));
+        PGR_TRY(scan_u32(idx, nh, n_qp, idx->scratch2.as<uint64_t>(), &n_hits));
+        if (n_hits >= 0xFFFFFFF0ull) { set_error("more than 2^32 hit pairs in one batch"); return PGR_E_LIMIT; }
+        if (n_hits) {
+            PGR_TRY(idx->hitsA.ensure(n_hits * sizeof(HitRec)));
+            PGR_TRY(idx->hitsB.ensure(n_hits * sizeof(HitRec)));
+            PGR_TRY(idx->keysA.ensure(n_hits * sizeof(SortKey)));
+            PGR_TRY(idx->idxA.ensure(n_hits * sizeof(uint32_t)));
+            hit_expand_kernel<<<g, 256, 0, st>>>(idx->qtuples.as<FragTuple>(), n_qp, qcount, idx->q_hit_begin.as<uint64_t>(),
+                                                 idx->q_hit_count.as<uint32_t>(), idx->sid_count.as<uint32_t>(), idx->sigs.as<pgr_frag_sig>(), f,
+                                                 idx->scratch2.as<uint64_t>(), idx->hitsA.as<HitRec>(), idx->keysA.as<SortKey>());
+            const uint32_t gh = (uint32_t)ceil_div<uint64_t>(n_hits, 256);
+            iota_kernel<<<gh, 256, 0, st>>>(idx->idxA.as<uint32_t>(), n_hits);
+            idx->launches += 2;
+            // stable sort by (qid, sid): bytes 0..3 of k1 (sid) then bytes 0..3 of k0 (qid)
+            PGR_TRY(index_sort(idx, n_hits, 0, 3));
+            PGR_TRY(index_sort(idx, n_hits, 7, 10));
+            PGR_TRY(idx->head.ensure(n_hits));
+            hit_gather_kernel<<<gh, 256, 0, st>>>(idx->hitsA.as<HitRec>(), idx->keysA.as<SortKey>(), idx->idxA.as<uint32_t>(), n_hits,
+                                                  idx->hitsB.as<HitRec>(), idx->head.as<uint8_t>());
+            // segments = runs of equal (qid, sid)
+            const uint32_t nb = (uint32_t)ceil_div<uint64_t>(n_hits, CS_BLK);
+            PGR_TRY(idx->block_sum.ensure(nb * sizeof(uint32_t)));
+            PGR_TRY(idx->block_prefix.ensure((nb + 1) * sizeof(uint64_t)));
+            csr_count_kernel<<<nb, CS_NT, 0, st>>>(idx->head.as<uint8_t>(), n_hits, idx->block_sum.as<uint32_t>());
+            block_scan_kernel<<<1, 1024, 0, st>>>(idx->block_sum.as<uint32_t>(), idx->block_prefix.as<uint64_t>(), nb);
+            PGR_TRY(ctx->ensure_ctl(64));
+            PGR_CUDA(cudaMemcpyAsync(ctx->h_ctl, idx->block_prefix.as<uint64_t>() + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaStreamSynchronize(st));
+            const uint64_t n_seg = *(uint64_t *)ctx->h_ctl;
+            PGR_TRY(idx->seg_keys.ensure(n_seg * sizeof(SortKey)));
+            PGR_TRY(idx->seg_off.ensure((n_seg + 1) * sizeof(uint64_t)));
+            csr_write_kernel<<<nb, CS_NT, 0, st>>>(idx->head.as<uint8_t>(), idx->keysA.as<SortKey>(), n_hits, idx->block_prefix.as<uint64_t>(),
+                                                   idx->seg_keys.as<SortKey>(), idx->seg_off.as<uint64_t>());
+            set_u64_kernel<<<1, 1, 0, st>>>(idx->seg_off.as<uint64_t>() + n_seg, n_hits);
+            idx->launches += 5;
+            // chaining
+            PGR_TRY(idx->chain_f.ensure(n_hits * sizeof(float) * 2));
+            PGR_TRY(idx->chain_u.ensure(n_hits * sizeof(uint32_t) * 5));
+            PGR_TRY(idx->chain_b.ensure(n_hits * 2));
+            PGR_TRY(idx->chain_seg.ensure(n_seg * sizeof(uint32_t) * 3));
+            ChainParams cp;
+            cp.hits = idx->hitsB.as<HitRec>(); cp.seg_off = idx->seg_off.as<uint64_t>(); cp.n_seg = n_seg;
+            cp.max_span = max_span; cp.penalty = prm->penalty; cp.has_gap = prm->max_gap >= 0 ? 1u : 0u;
+            cp.max_gap = prm->max_gap >= 0 ? (float)(uint32_t)prm->max_gap : 0.0f; cp.oriented = prm->oriented ? 1u : 0u;
+            cp.v_s = idx->chain_f.as<float>(); cp.out_score = cp.v_s + n_hits;
+            uint32_t *u = idx->chain_u.as<uint32_t>();
+            cp.best_pre = (int32_t *)u; cp.cls_first = u + n_hits; cp.cls_last = u + 2 * n_hits; cp.order = u + 3 * n_hits; cp.out_idx = u + 4 * n_hits;
+            cp.visited = idx->chain_b.as<uint8_t>(); cp.out_start = cp.visited + n_hits;
+            cp.seg_n_out = idx->chain_seg.as<uint32_t>(); cp.seg_n_chains = cp.seg_n_out + n_seg; cp.seg_err = cp.seg_n_out + 2 * n_seg;
+            chain_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 64), 64, 0, st>>>(cp);
+            idx->launches += 1;
+            PGR_CUDA(cudaGetLastError());
+            // read back and assemble the nested result (host pass over the output)
+            std::vector<SortKey> seg_keys(n_seg);
+            std::vector<uint64_t> seg_off(n_seg + 1);
+            std::vector<uint32_t> seg_meta(3 * n_seg), out_idx(n_hits);
+            std::vector<uint8_t> out_start(n_hits);
+            std::vector<float> out_score(n_hits);
+            std::vector<HitRec> hrec(n_hits);
+            PGR_CUDA(cudaMemcpyAsync(seg_keys.data(), idx->seg_keys.p, n_seg * sizeof(SortKey), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaMemcpyAsync(seg_off.data(), idx->seg_off.p, (n_seg + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaMemcpyAsync(seg_meta.data(), idx->chain_seg.p, 3 * n_seg * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaMemcpyAsync(out_idx.data(), cp.out_idx, n_hits * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaMemcpyAsync(out_start.data(), cp.out_start, n_hits, cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaMemcpyAsync(out_score.data(), cp.out_score, n_hits * sizeof(float), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaMemcpyAsync(hrec.data(), idx->hitsB.p, n_hits * sizeof(HitRec), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaStreamSynchronize(st));
+            size_t qi = 0;
+            for (uint64_t s = 0; s < n_seg; s++) {
+                if (seg_meta[2 * n_seg + s]) { set_error("sparse_aln: all scores <= 0 (the reference would not terminate)"); return PGR_E_ASSERT; }
+                const uint32_t n_out = seg_meta[s];
+                if (n_out == 0) continue;  // segments with a single hit are dropped (aln.rs:237)
+                const uint32_t qid = (uint32_t)seg_keys[s].k0;
+                while (qi < qid) { qi++; q_target_off[qi] = target_sid.size(); }
+                target_sid.push_back((uint32_t)seg_keys[s].k1);
+                const uint64_t b = seg_off[s];
+                for (uint32_t a = 0; a < n_out; a++) {
+                    if (out_start[b + a]) {
+                        if (a) chain_hit_off.push_back(hits_out.size());
+                        chain_score.push_back(out_score[b + a]);
+                    }
+                    const HitRec &h = hrec[b + out_idx[b + a]];
+                    pgr_hit_pair hp;
+                    memset(&hp, 0, sizeof hp);
+                    hp.qb = h.qb; hp.qe = h.qe; hp.qo = h.qo; hp.tb = h.tb; hp.te = h.te; hp.to = h.to;
+                    hits_out.push_back(hp);
+                }
+                chain_hit_off.push_back(hits_out.size());
+                target_chain_off.push_back(chain_score.size());
+            }
+            while (qi < n_q) { qi++; q_target_off[qi] = target_sid.size(); }
+        }
+    }
+    // chain_hit_off was built with one leading 0 and one entry per chain end
+    pgr_query_result *r = (pgr_query_result *)calloc(1, sizeof(pgr_query_result));
+    r->n_queries = n_q; r->n_targets = target_sid.size(); r->n_chains = chain_score.size(); r->n_hits = hits_out.size();
+    r->q_target_off = host_dup(q_target_off); r->target_sid = host_dup(target_sid); r->target_chain_off = host_dup(target_chain_off);
+    r->chain_score = host_dup(chain_score); r->chain_hit_off = host_dup(chain_hit_off); r->hits = host_dup(hits_out);
+    *out = r;
+    return PGR_OK;
+}
+
+// replaces aln::sparse_aln(&mut sp_hits, max_span, penalty, max_gap, oriented) on one hit list.  hits is sorted in place
+// (stable, by q_bgn, aln.rs:21).
+int pgr_b200_sparse_aln(pgr_hit_pair *hits, size_t n, uint32_t max_span, float penalty, int64_t max_gap, int oriented, size_t *n_chains,
+                        uint64_t **chain_off, float **scores, pgr_hit_pair **chain_hits) {
+    if (!hits || !n_chains || !chain_off || !scores || !chain_hits) { set_error("NULL argument"); return PGR_E_ARG; }
+    if (n < 2) { set_error("assert!(sp_hits.len() > 1) violated (aln.rs:24)"); return PGR_E_ASSERT; }
+    pgr_b200_ctx *ctx = tls_ctx();
+    if (!ctx) return PGR_E_NO_DEVICE;
+    PGR_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::stable_sort(hits, hits + n, [](const pgr_hit_pair &a, const pgr_hit_pair &b) { return a.qb < b.qb; });
+    std::vector<HitRec> hr(n);
+    for (size_t i = 0; i < n; i++) {
+        memset(&hr[i], 0, sizeof(HitRec));
+        hr[i].qb = hits[i].qb; hr[i].qe = hits[i].qe; hr[i].qo = hits[i].qo; hr[i].tb = hits[i].tb; hr[i].te = hits[i].te; hr[i].to = hits[i].to;
+    }
+    DevBuf d_hits, d_f, d_u, d_b, d_seg;
+    int rc = PGR_OK;
+    auto cleanup = [&]() { d_hits.release(); d_f.release(); d_u.release(); d_b.release(); d_seg.release(); };
+    if ((rc = d_hits.ensure(n * sizeof(HitRec))) || (rc = d_f.ensure(n * sizeof(float) * 2)) || (rc = d_u.ensure(n * sizeof(uint32_t) * 5)) ||
+        (rc = d_b.ensure(n * 2)) || (rc = d_seg.ensure(64))) { cleanup(); return rc; }
+    const uint64_t seg_off_h[2] = {0, n};
+    uint64_t *d_off = d_seg.as<uint64_t>();
+    uint32_t *d_meta = (uint32_t *)(d_off + 2);
+    cudaMemcpyAsync(d_hits.p, hr.data(), n * sizeof(HitRec), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_off, seg_off_h, sizeof seg_off_h, cudaMemcpyHostToDevice, st);
+    ChainParams cp;
+    cp.hits = d_hits.as<HitRec>(); cp.seg_off = d_off; cp.n_seg = 1; cp.max_span = max_span; cp.penalty = penalty;
+    cp.has_gap = max_gap >= 0 ? 1u : 0u; cp.max_gap = max_gap >= 0 ? (float)(uint32_t)max_gap : 0.0f; cp.oriented = oriented ? 1u : 0u;
+    cp.v_s = d_f.as<float>(); cp.out_score = cp.v_s + n;
+    uint32_t *u = d_u.as<uint32_t>();
+    cp.best_pre = (int32_t *)u; cp.cls_first = u + n; cp.cls_last = u + 2 * n; cp.order = u + 3 * n; cp.out_idx = u + 4 * n;
+    cp.visited = d_b.as<uint8_t>(); cp.out_start = cp.visited + n;
+    cp.seg_n_out = d_meta; cp.seg_n_chains = d_meta + 1; cp.seg_err = d_meta + 2;
+    chain_kernel<<<1, 64, 0, st>>>(cp);
+    std::vector<uint32_t> out_idx(n);
+    std::vector<uint8_t> out_start(n);
+    std::vector<float> out_score(n);
+    uint32_t meta[3] = {0, 0, 0};
+    cudaMemcpyAsync(out_idx.data(), cp.out_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(out_start.data(), cp.out_start, n, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(out_score.data(), cp.out_score, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(meta, d_meta, sizeof meta, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) { set_error("sparse_aln kernel failed: %s", cudaGetErrorString(e)); return PGR_E_CUDA; }
+    if (meta[2]) { set_error("sparse_aln: all scores <= 0 (the reference would not terminate)"); return PGR_E_ASSERT; }
+    std::vector<uint64_t> off;
+    std::vector<float> sc;
+    std::vector<pgr_hit_pair> ch;
+    for (uint32_t a = 0; a < meta[0]; a++) {
+        if (out_start[a]) { off.push_back(ch.size()); sc.push_back(out_score[a]); }
+        ch.push_back(hits[out_idx[a]]);
+    }
+    off.push_back(ch.size());
+    *n_chains = sc.size();
+    *chain_off = host_dup(off);
+    *scores = host_dup(sc);
+    *chain_hits = host_dup(ch);
+    return PGR_OK;
+}
+
+// replaces seq_db::frag_map_to_adj_list(&frag_map, min_count, keeps) -> AdjList
+int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *keeps, size_t n_keeps, int has_keeps, pgr_adj_pair **out,
+                      size_t *n_out) {
+    if (!idx || !out || !n_out) { set_error("NULL argument"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(idx->ctx->device));
+    PGR_TRY(pgr_b200_index_finalize(idx));
+    cudaStream_t st = idx->ctx->stream;
+    const uint64_t n = idx->n_tuples;
+    *out = (pgr_adj_pair *)malloc(sizeof(pgr_adj_pair));
+    *n_out = 0;
+    if (n < 2) return PGR_OK;  // seq_db.rs:889-891
+    std::vector<uint32_t> ks(keeps, keeps + (has_keeps ? n_keeps : 0));
+    std::sort(ks.begin(), ks.end());
+    PGR_TRY(idx->scratch0.ensure(std::max<size_t>(1, ks.size()) * sizeof(uint32_t)));
+    if (!ks.empty()) PGR_CUDA(cudaMemcpyAsync(idx->scratch0.p, ks.data(), ks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    PGR_TRY(idx->hitsA.ensure(n * sizeof(AdjRow)));
+    PGR_TRY(idx->keysA.ensure(n * sizeof(SortKey)));
+    PGR_TRY(idx->idxA.ensure(n * sizeof(uint32_t)));
+    const uint32_t g = (uint32_t)ceil_div<uint64_t>(n, 256);
+    AdjRow *rows = idx->hitsA.as<AdjRow>();
+    adj_rows_kernel<<<g, 256, 0, st>>>(idx->ukeys.as<SortKey>(), idx->offsets.as<uint64_t>(), idx->sigs.as<pgr_frag_sig>(), n, idx->n_keys,
+                                       (uint64_t)min_count, idx->scratch0.as<uint32_t>(), (uint32_t)ks.size(), has_keeps ? 1u : 0u, rows);
+    iota_kernel<<<g, 256, 0, st>>>(idx->idxA.as<uint32_t>(), n);
+    idx->launches += 2;
+    for (int round = 0; round < 3; round++) {   // out.par_sort() on the full tuple (seq_db.rs:892)
+        adj_keys_kernel<<<g, 256, 0, st>>>(rows, idx->idxA.as<uint32_t>(), n, round, idx->keysA.as<SortKey>());
+        idx->launches += 1;
+        PGR_TRY(index_sort(idx, n, 0, 13));
+    }
+    PGR_TRY(idx->scratch1.ensure(n * sizeof(uint32_t)));
+    PGR_TRY(idx->scratch2.ensure((n + 1) * sizeof(uint64_t)));
+    adj_flag_kernel<<<g, 256, 0, st>>>(rows, idx->idxA.as<uint32_t>(), n, idx->scratch1.as<uint32_t>());
+    uint64_t total = 0;
+    PGR_TRY(scan_u32(idx, idx->scratch1.as<uint32_t>(), n, idx->scratch2.as<uint64_t>(), &total));
+    idx->launches += 1;
+    if (total == 0) return PGR_OK;
+    PGR_TRY(idx->scratch3.ensure(total * sizeof(pgr_adj_pair)));
+    adj_emit_kernel<<<g, 256, 0, st>>>(rows, idx->idxA.as<uint32_t>(), n, idx->scratch1.as<uint32_t>(), idx->scratch2.as<uint64_t>(),
+                                       idx->scratch3.as<pgr_adj_pair>());
+    idx->launches += 1;
+    PGR_CUDA(cudaGetLastError());
+    free(*out);
+    *out = (pgr_adj_pair *)malloc(total * sizeof(pgr_adj_pair));
+    if (!*out) { set_error("out of host memory"); return PGR_E_ARG; }
+    PGR_CUDA(cudaMemcpyAsync(*out, idx->scratch3.p, total * sizeof(pgr_adj_pair), cudaMemcpyDeviceToHost, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    *n_out = total;
+    return PGR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+// query_kernels.cuh — batched query_fragment_to_hps (aln.rs:147-242) and sparse_aln (aln.rs:12-142), and
+// frag_map_to_adj_list (seq_db.rs:876-944).
+#pragma once
+#include "index_kernels.cuh"
+
+namespace pgr {
+
+// ---- generic exclusive scan of u32 counts into u64 offsets (n+1 entries) --------------------------------------------
+constexpr int SC_NT = 256, SC_PER = 8, SC_BLK = SC_NT * SC_PER;
+__global__ void __launch_bounds__(SC_NT) scan_reduce_kernel(const uint32_t *v, uint64_t n, uint32_t *block_sum) {
+    __shared__ uint32_t wsum[SC_NT / 32];
+    const uint64_t i0 = (uint64_t)blockIdx.x * SC_BLK;
+    uint32_t c = 0;
+    for (int j = 0; j < SC_PER; j++) { const uint64_t i = i0 + (uint64_t)j * SC_NT + threadIdx.x; if (i < n) c += v[i]; }
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < SC_NT / 32; i++) t += wsum[i]; block_sum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(SC_NT) scan_apply_kernel(const uint32_t *v, uint64_t n, const uint64_t *block_prefix, uint64_t *out) {
+    __shared__ uint32_t wsum[SC_NT / 32];
+    const uint64_t i0 = (uint64_t)blockIdx.x * SC_BLK + (uint64_t)threadIdx.x * SC_PER;
+    uint32_t x[SC_PER], c = 0;
+#pragma unroll
+    for (int j = 0; j < SC_PER; j++) { x[j] = (i0 + j < n) ? v[i0 + j] : 0; c += x[j]; }
+    uint32_t incl = c;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((threadIdx.x & 31) >= d) incl += t; }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t wb = 0;
+    for (uint32_t j = 0; j < (threadIdx.x >> 5); j++) wb += wsum[j];
+    uint64_t r = block_prefix[blockIdx.x] + wb + incl - c;
+#pragma unroll
+    for (int j = 0; j < SC_PER; j++) { if (i0 + j < n) out[i0 + j] = r; r += x[j]; }
+    if (i0 <= n && n < i0 + SC_PER) out[n] = block_prefix[blockIdx.x] + wb + incl;  // total, written by the thread that owns slot n
+}
+
+// ---- per-signature count of signatures with the same sid inside its key's vector (aln.rs:183-191) ----------------------
+// run-length when the vector is sid-monotone (the normal case: sequences are added in sid order), full scan otherwise
+__global__ void sid_count_kernel(const pgr_frag_sig *sigs, const uint64_t *offsets, uint64_t n_keys, uint32_t *sid_count) {
+    const uint64_t kx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (kx >= n_keys) return;
+    const uint64_t b = offsets[kx], e = offsets[kx + 1];
+    bool mono = true;
+    for (uint64_t i = b + 1; i < e; i++) mono = mono && (sigs[i - 1].sid <= sigs[i].sid);
+    if (mono) {
+        uint64_t i = b;
+        while (i < e) {
+            uint64_t j = i + 1;
+            while (j < e && sigs[j].sid == sigs[i].sid) j++;
+            for (uint64_t q = i; q < j; q++) sid_count[q] = (uint32_t)(j - i);
+            i = j;
+        }
+    } else {
+        for (uint64_t i = b; i < e; i++) {
+            uint32_t c = 0;
+            for (uint64_t j = b; j < e; j++) c += (sigs[j].sid == sigs[i].sid) ? 1u : 0u;
+            sid_count[i] = c;
+        }
+    }
+}
+
+// ---- query pair statistics -------------------------------------------------------------------------------------------
+// qcount[i] = number of pairs of the same query with the same key (shmmr_pair_hash_count, aln.rs:172-182)
+__global__ void qpair_count_kernel(const FragTuple *qt, uint64_t n_qp, const uint64_t *qp_off, uint32_t *qcount) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_qp) return;
+    const uint32_t q = qt[i].sid;
+    const uint64_t b = qp_off[q], e = qp_off[q + 1];
+    const uint64_t h0 = qt[i].h0, h1 = qt[i].h1;
+    uint32_t c = 0;
+    for (uint64_t j = b; j < e; j++) c += (qt[j].h0 == h0 && qt[j].h1 == h1) ? 1u : 0u;
+    qcount[i] = c;
+}
+
+struct QueryFilter { uint32_t max_count, max_count_query, max_count_target; };
+
+// number of hit pairs a query pair contributes after the count filters (aln.rs:197-228)
+__global__ void hit_count_kernel(uint64_t n_qp, const uint32_t *qcount, const uint64_t *hit_begin, const uint32_t *hit_cnt,
+                                 const uint32_t *sid_count, QueryFilter f, uint32_t *n_hits) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_qp) return;
+    const uint32_t c = qcount[i];
+    uint32_t n = 0;
+    if (c <= f.max_count && c <= f.max_count_query) {
+        const uint64_t b = hit_begin[i];
+        for (uint32_t j = 0; j < hit_cnt[i]; j++) {
+            const uint64_t tc = (uint64_t)c * sid_count[b + j];
+            n += (tc <= f.max_count_target) ? 1u : 0u;
+        }
+    }
+    n_hits[i] = n;
+}
+
+struct HitRec {          // 32 bytes
+    uint32_t qid, sid;   // query ordinal, target sequence id
+    uint32_t qb, qe, tb, te;
+    uint8_t qo, to, pad_[2];
+    uint32_t pad2_;
+};
+static_assert(sizeof(HitRec) == 32, "HitRec layout");
+
+__global__ void hit_expand_kernel(const FragTuple *qt, uint64_t n_qp, const uint32_t *qcount, const uint64_t *hit_begin,
+                                  const uint32_t *hit_cnt, const uint32_t *sid_count, const pgr_frag_sig *sigs, QueryFilter f,
+                                  const uint64_t *hit_off, HitRec *hits, SortKey *keys) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_qp) return;
+    const uint32_t c = qcount[i];
+    if (!(c <= f.max_count && c <= f.max_count_query)) return;
+    const FragTuple t = qt[i];
+    uint64_t o = hit_off[i];
+    const uint64_t b = hit_begin[i];
+    for (uint32_t j = 0; j < hit_cnt[i]; j++) {
+        const uint64_t tc = (uint64_t)c * sid_count[b + j];
+        if (tc > f.max_count_target) continue;
+        const pgr_frag_sig sg = sigs[b + j];
+        HitRec h;
+        h.qid = t.sid; h.sid = sg.sid; h.qb = t.bgn; h.qe = t.end; h.qo = (uint8_t)t.ori;
+        h.tb = sg.bgn; h.te = sg.end; h.to = sg.ori; h.pad_[0] = h.pad_[1] = 0; h.pad2_ = 0;
+        hits[o] = h;
+        SortKey k; k.k0 = t.sid; k.k1 = sg.sid;
+        keys[o] = k;
+        o++;
+    }
+}
+
+__global__ void hit_gather_kernel(const HitRec *in, const SortKey *keys, const uint32_t *idx, uint64_t n, HitRec *out, uint8_t *head) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = in[idx[i]];
+    head[i] = (i == 0 || keys[i].k0 != keys[i - 1].k0 || keys[i].k1 != keys[i - 1].k1) ? 1 : 0;
+}
+
+// ---- sparse_aln (aln.rs:12-142), one thread per (query, target) segment ---------------------------------------------
+struct ChainParams {
+    const HitRec *hits;          // sorted by (qid, sid), each segment already non-decreasing in qb (stable)
+    const uint64_t *seg_off;     // [n_seg+1]
+    uint64_t n_seg;
+    uint32_t max_span;
+    float penalty;
+    uint32_t has_gap; float max_gap;
+    uint32_t oriented;
+    // per-hit scratch / outputs (same indexing as hits)
+    float *v_s;                  // score of each vertex
+    int32_t *best_pre;           // index (within segment) of the best predecessor, -1 = none
+    uint32_t *cls_first, *cls_last;  // duplicate classes (HashMap keyed by HitPair value)
+    uint32_t *order;             // heap-sorted vertex order for head selection
+    uint8_t *visited;
+    // outputs
+    uint32_t *out_idx;           // chain members as segment-relative hit indices, chains back to back
+    uint8_t *out_start;          // 1 where a chain starts
+    float *out_score;            // chain score at its start slot
+    uint32_t *seg_n_out, *seg_n_chains;
+    uint32_t *seg_err;           // aln.rs would spin forever (all scores <= 0)
+};
+
+__device__ __forceinline__ bool same_hp(const HitRec &a, const HitRec &b) {
+    return a.qb == b.qb && a.qe == b.qe && a.qo == b.qo && a.tb == b.tb && a.te == b.te && a.to == b.to;
+}
+__device__ __forceinline__ bool same_q(const HitRec &a, const HitRec &b) { return a.qb == b.qb && a.qe == b.qe && a.qo == b.qo; }
+
+// order[] comparison: higher score first, then lower index (canonical replacement for FxHashSet iteration order)
+__device__ __forceinline__ bool head_before(const float *vs, uint32_t a, uint32_t b) {
+    return vs[a] > vs[b] || (vs[a] == vs[b] && a < b);
+}
+
+__global__ void chain_kernel(const ChainParams p) {
+    const uint64_t sgi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sgi >= p.n_seg) return;
+    const uint64_t b = p.seg_off[sgi], e = p.seg_off[sgi + 1];
+    const uint32_t n = (uint32_t)(e - b);
+    p.seg_n_out[sgi] = 0; p.seg_n_chains[sgi] = 0; p.seg_err[sgi] = 0;
+    if (n < 2) return;  // aln.rs:237 filter(|(_sid, hps)| hps.len() > 1)
+    const HitRec *h = p.hits + b;
+    float *vs = p.v_s + b;
+    int32_t *bp = p.best_pre + b;
+    uint32_t *cf = p.cls_first + b, *cl = p.cls_last + b, *ord = p.order + b;
+    uint8_t *vis = p.visited + b;
+    // duplicate classes: identical HitPairs share one map entry; equal values have equal qb, so they sit in one qb run
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t f = i, l = i;
+        for (uint32_t j = i; j > 0 && h[j - 1].qb == h[i].qb; j--) if (same_hp(h[j - 1], h[i])) f = j - 1;
+        for (uint32_t j = i + 1; j < n && h[j].qb == h[i].qb; j++) if (same_hp(h[j], h[i])) l = j;
+        cf[i] = f; cl[i] = l;
+    }
+    // DP (aln.rs:25-103).  v_s.get(pre) sees the LATEST inserted duplicate with index < i
+    vs[0] = __fsub_rn((float)h[0].qe, (float)h[0].qb);
+    bp[0] = -1;
+    for (uint32_t i = 1; i < n; i++) {
+        const HitRec hp = h[i];
+        const float len = __fsub_rn((float)hp.qe, (float)hp.qb);
+        float best_s = 0.0f;
+        int32_t best_v = -1;
+        // span_set: distinct (qb,qe,qo) seen so far; hits are sorted by qb, so a small list suffices only when max_span
+        // is small; in general count distinct values by scanning the already visited range
+        uint32_t span = 0;
+        for (uint32_t j = i; j-- > 0;) {
+            const HitRec pre = h[j];
+            if (p.oriented && ((pre.qo ^ pre.to) != (hp.qo ^ hp.to))) continue;
+            if (p.has_gap) {
+                const float dq = fabsf(__fsub_rn((float)hp.qb, (float)pre.qe));
+                const float dt = (hp.qo == hp.to) ? fabsf(__fsub_rn((float)hp.tb, (float)pre.te)) : fabsf(__fsub_rn((float)hp.te, (float)pre.tb));
+                if (dq > p.max_gap || dt > p.max_gap) continue;
+            }
+            if (same_q(pre, hp)) continue;
+            // span_set.insert(pre.0): new iff no admitted predecessor with the same (qb,qe,qo) was seen at a larger index
+            bool seen = false;
+            for (uint32_t jj = j + 1; jj < i && !seen; jj++) {
+                const HitRec o = h[jj];
+                if (!same_q(o, pre)) { if (o.qb != pre.qb) break; continue; }
+                // o has the same left fragment: it was inserted unless it was skipped by the gates above
+                bool skipped = false;
+                if (p.oriented && ((o.qo ^ o.to) != (hp.qo ^ hp.to))) skipped = true;
+                if (!skipped && p.has_gap) {
+                    const float dq = fabsf(__fsub_rn((float)hp.qb, (float)o.qe));
+                    const float dt = (hp.qo == hp.to) ? fabsf(__fsub_rn((float)hp.tb, (float)o.te)) : fabsf(__fsub_rn((float)hp.te, (float)o.tb));
+                    if (dq > p.max_gap || dt > p.max_gap) skipped = true;
+                }
+                if (!skipped) seen = true;
+            }
+            if (!seen) span++;
+            // latest duplicate of pre with index < i
+            uint32_t jl = j;
+            for (uint32_t jj = j + 1; jj < i && h[jj].qb == pre.qb; jj++) if (same_hp(h[jj], pre)) jl = jj;
+            const float p_s = vs[jl];
+            float s = __fadd_rn(p_s, len);
+            const float dq = fabsf(__fsub_rn((float)hp.qb, (float)pre.qe));
+            const float dt = (hp.qo == hp.to) ? fabsf(__fsub_rn((float)hp.tb, (float)pre.te)) : fabsf(__fsub_rn((float)hp.te, (float)pre.tb));
+            s = __fsub_rn(s, __fmul_rn(p.penalty, __fadd_rn(dq, dt)));
+            if (s > best_s) { best_s = s; best_v = (int32_t)j; }
+            if (span >= p.max_span) break;
+        }
+        if (best_s > 0.0f) { vs[i] = best_s; bp[i] = best_v; }
+        else { vs[i] = len; bp[i] = -1; }
+    }
+    // final map values: a class reads the entry of its last duplicate
+    // head order: heap sort of class representatives (first occurrences) by (score desc, index asc)
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < n; i++) { vis[i] = 0; if (cf[i] == i) ord[m++] = i; }
+    auto key_before = [&](uint32_t a, uint32_t bidx) {  // a, bidx are class representatives
+        const float sa = vs[cl[a]], sb = vs[cl[bidx]];
+        return sa > sb || (sa == sb && a < bidx);
+    };
+    // heap sort ascending in "before" order: build a max-heap on the inverse relation
+    auto sift = [&](uint32_t start, uint32_t end) {
+        uint32_t root = start;
+        for (;;) {
+            uint32_t child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && key_before(ord[child], ord[child + 1])) child++;   // pick the one that comes LATER
+            if (key_before(ord[root], ord[child])) { const uint32_t t = ord[root]; ord[root] = ord[child]; ord[child] = t; root = child; }
+            else break;
+        }
+    };
+    if (m > 1) {
+        for (uint32_t s = m / 2; s-- > 0;) sift(s, m);
+        for (uint32_t end = m; end-- > 1;) { const uint32_t t = ord[0]; ord[0] = ord[end]; ord[end] = t; sift(0, end); }
+    }
+    // traceback (aln.rs:105-141)
+    uint32_t n_out = 0, n_ch = 0;
+    uint32_t *oi = p.out_idx + b;
+    uint8_t *ost = p.out_start + b;
+    float *osc = p.out_score + b;
+    for (uint32_t t = 0; t < m; t++) {
+        const uint32_t head = ord[t];
+        if (vis[head]) continue;
+        const float best_s = vs[cl[head]];
+        if (!(best_s > 0.0f)) { p.seg_err[sgi] = 1; break; }   // the reference loops forever here
+        const uint32_t start = n_out;
+        int32_t v = (int32_t)head;
+        while (v >= 0) {
+            const uint32_t rep = cf[v];
+            if (vis[rep]) break;
+            vis[rep] = 1;
+            oi[n_out++] = rep;
+            v = bp[cl[rep]];
+        }
+        // reverse the track in place
+        for (uint32_t a = start, z = n_out; a + 1 < z; a++, z--) { const uint32_t tt = oi[a]; oi[a] = oi[z - 1]; oi[z - 1] = tt; }
+        for (uint32_t a = start; a < n_out; a++) ost[a] = 0;
+        ost[start] = 1;
+        osc[start] = __fsub_rn(best_s, vs[cl[oi[start]]]);
+        n_ch++;
+    }
+    p.seg_n_out[sgi] = n_out;
+    p.seg_n_chains[sgi] = n_ch;
+}
+
+// ---- frag_map_to_adj_list (seq_db.rs:876-944) --------------------------------------------------------------------------
+struct AdjRow { uint32_t sid, bgn, end, ori; uint64_t h0, h1; uint32_t ok, pad_; };   // 40 bytes
+static_assert(sizeof(AdjRow) == 40, "AdjRow layout");
+
+// flatten the CSR into rows + a first sort key (sid, bgn); the remaining tuple fields are tie-breakers handled below
+__global__ void adj_rows_kernel(const SortKey *ukeys, const uint64_t *offsets, const pgr_frag_sig *sigs, uint64_t n_sigs, uint64_t n_keys,
+                                uint64_t min_count, const uint32_t *keeps, uint32_t n_keeps, uint32_t has_keeps, AdjRow *rows) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sigs) return;
+    // key of signature i: largest kx with offsets[kx] <= i
+    uint64_t lo = 0, hi = n_keys;
+    while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (offsets[mid] <= i) lo = mid; else hi = mid; }
+    const pgr_frag_sig sg = sigs[i];
+    AdjRow r;
+    r.sid = sg.sid; r.bgn = sg.bgn; r.end = sg.end; r.ori = sg.ori; r.h0 = ukeys[lo].k0; r.h1 = ukeys[lo].k1; r.pad_ = 0;
+    bool ok = (offsets[lo + 1] - offsets[lo]) >= min_count;
+    if (!ok && has_keeps) {
+        uint32_t a = 0, z = n_keeps;  // keeps is sorted ascending by the host
+        while (a < z) { const uint32_t mid = (a + z) >> 1; if (keeps[mid] < sg.sid) a = mid + 1; else z = mid; }
+        ok = (a < n_keeps && keeps[a] == sg.sid);
+    }
+    r.ok = ok ? 1u : 0u;
+    rows[i] = r;
+}
+
+// sort keys for the full-tuple order (sid, bgn, end, h0, h1, ori): three LSD rounds of the 128-bit sorter
+//   round 1: (h1, ori)   round 2: (end, h0)   round 3: (sid, bgn)
+__global__ void adj_keys_kernel(const AdjRow *rows, const uint32_t *idx, uint64_t n, int round, SortKey *keys) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const AdjRow &r = rows[idx ? idx[i] : i];
+    SortKey k;
+    if (round == 0) { k.k0 = r.h1; k.k1 = r.ori; }
+    else if (round == 1) { k.k0 = r.end; k.k1 = r.h0; }
+    else { k.k0 = r.sid; k.k1 = r.bgn; }
+    keys[i] = k;
+}
+
+__global__ void adj_flag_kernel(const AdjRow *rows, const uint32_t *idx, uint64_t n, uint32_t *cnt) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = 0;
+    if (i + 1 < n) {
+        const AdjRow &v = rows[idx[i]], &w = rows[idx[i + 1]];
+        if (v.ok && w.ok && v.sid == w.sid && v.end == w.bgn) c = 2;
+    }
+    cnt[i] = c;
+}
+__global__ void adj_emit_kernel(const AdjRow *rows, const uint32_t *idx, uint64_t n, const uint32_t *cnt, const uint64_t *off, pgr_adj_pair *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || cnt[i] == 0) return;
+    const AdjRow &v = rows[idx[i]], &w = rows[idx[i + 1]];
+    pgr_adj_pair a;
+    a.sid = v.sid; a.pad_[0] = a.pad_[1] = 0;
+    a.a0 = v.h0; a.a1 = v.h1; a.ori0 = (uint8_t)v.ori; a.b0 = w.h0; a.b1 = w.h1; a.ori1 = (uint8_t)w.ori;
+    out[off[i]] = a;
+    pgr_adj_pair r;
+    r.sid = v.sid; r.pad_[0] = r.pad_[1] = 0;
+    r.a0 = w.h0; r.a1 = w.h1; r.ori0 = (uint8_t)(1 - w.ori); r.b0 = v.h0; r.b1 = v.h1; r.ori1 = (uint8_t)(1 - v.ori);
+    out[off[i] + 1] = r;
+}
+
+}  // namespace pgr
