@@ -45,6 +45,9 @@ struct SpecDev {
     uint32_t w, k, r, min_span, sketch;
 };
 
+// PGR_B200_TRACE=1: wall-clock stage trace on stderr (synchronises the device at every mark; debugging aid only)
+void trace_mark(const char *what);
+
 template <class T>
 __host__ __device__ __forceinline__ T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 
 #include "shmmr_kernels.cuh"
@@ -19,6 +20,18 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 const char *get_error() { return g_err; }
+
+void trace_mark(const char *what) {
+    static const bool on = getenv("PGR_B200_TRACE") != nullptr;
+    if (!on) return;
+    static thread_local double last = 0;
+    cudaDeviceSynchronize();
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    fprintf(stderr, "[pgr_b200 trace] %-40s +%.3f ms\n", what, last == 0 ? 0.0 : now - last);
+    last = now;
+}
 
 int StageTimer::begin(const char *name, cudaStream_t st) {
     if (used == ev0.size()) {
@@ -156,7 +169,7 @@ void pgr_b200_ctx_free(pgr_b200_ctx *ctx) {
     pgr::DevBuf *bufs[] = {&ctx->seq_store, &ctx->d_off, &ctx->d_len, &ctx->d_rid, &ctx->tile_prefix, &ctx->cta_tile, &ctx->arena,
                            &ctx->chunk_count, &ctx->seq_count, &ctx->seq_flag, &ctx->replay_list, &ctx->replay_count,
                            &ctx->chunk_prefix, &ctx->seq_fast, &ctx->seq_dst, &ctx->bufA, &ctx->bufB, &ctx->flags,
-                           &ctx->block_sum, &ctx->block_prefix, &ctx->off_a, &ctx->off_b, &ctx->fix_mm, &ctx->fix_off};
+                           &ctx->block_sum, &ctx->block_prefix, &ctx->off_a, &ctx->off_b, &ctx->fix_mm, &ctx->fix_off, &ctx->skips, &ctx->n_skips};
     for (auto b : bufs) b->release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -358,6 +371,140 @@ int occupancy_l0(int *occ) {
     return PGR_OK;
 }
 
+// Replace the level-0 entries around pushed palindromic positions (fmmer == rmmer) by an exact replay of the reference
+// machine (patch_replay_kernel), then splice: flat list moves bufA -> bufB -> (swap) bufA, offsets updated in seq_dst.
+int apply_palindrome_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_skips, const std::vector<uint32_t> &flagged,
+                             const std::vector<uint64_t> &off0, uint64_t *n_l0) {
+    cudaStream_t st = ctx->stream;
+    const size_t n = ctx->rn;
+    std::vector<uint2> sk(n_skips);
+    PGR_CUDA(cudaMemcpyAsync(sk.data(), ctx->skips.p, n_skips * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint64_t> key;
+    key.reserve(n_skips);
+    for (auto &e : sk) if (!flagged[e.x]) key.push_back(((uint64_t)e.x << 32) | e.y);   // flagged sequences are replayed whole
+    std::sort(key.begin(), key.end());
+    key.erase(std::unique(key.begin(), key.end()), key.end());       // halo positions are seen by two tiles
+    if (key.empty()) return PGR_OK;
+    std::vector<uint32_t> aff_seq, skip_off(1, 0), skip_pos;
+    for (size_t i = 0; i < key.size(); i++) {
+        const uint32_t s = (uint32_t)(key[i] >> 32);
+        if (aff_seq.empty() || aff_seq.back() != s) { if (!aff_seq.empty()) skip_off.push_back((uint32_t)skip_pos.size()); aff_seq.push_back(s); }
+        skip_pos.push_back((uint32_t)key[i]);
+    }
+    skip_off.push_back((uint32_t)skip_pos.size());
+    const uint32_t n_aff = (uint32_t)aff_seq.size(), n_slots = (uint32_t)skip_pos.size();
+    DevBuf d_aff, d_soff, d_spos, d_np, d_q, d_eoff, d_entries, d_meta, d_epatch;
+    auto cleanup = [&]() { d_aff.release(); d_soff.release(); d_spos.release(); d_np.release(); d_q.release(); d_eoff.release();
+                           d_entries.release(); d_meta.release(); d_epatch.release(); };
+    int rc = PGR_OK;
+#define PATCH_TRY(x) do { rc = (x); if (rc != PGR_OK) { cleanup(); return rc; } } while (0)
+#define PATCH_CUDA(x) do { if ((x) != cudaSuccess) { set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); cleanup(); return PGR_E_CUDA; } } while (0)
+    PATCH_TRY(d_aff.ensure(n_aff * 4)); PATCH_TRY(d_soff.ensure((n_aff + 1) * 4)); PATCH_TRY(d_spos.ensure(n_slots * 4));
+    PATCH_TRY(d_np.ensure(n_aff * 4)); PATCH_TRY(d_q.ensure((size_t)n_slots * 4 * 3)); PATCH_TRY(d_eoff.ensure((size_t)n_slots * 8));
+    PATCH_CUDA(cudaMemcpyAsync(d_aff.p, aff_seq.data(), n_aff * 4, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(d_soff.p, skip_off.data(), (n_aff + 1) * 4, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(d_spos.p, skip_pos.data(), n_slots * 4, cudaMemcpyHostToDevice, st));
+    PatchParams pp;
+    pp.seq = ctx->d_seq; pp.off = ctx->d_off.as<uint64_t>() + ctx->r0; pp.len = ctx->d_len.as<uint32_t>() + ctx->r0;
+    pp.aff_seq = d_aff.as<uint32_t>(); pp.skip_off = d_soff.as<uint32_t>(); pp.skip_pos = d_spos.as<uint32_t>(); pp.n_aff = n_aff;
+    pp.w = spec.w; pp.k = spec.k; pp.n_patches = d_np.as<uint32_t>();
+    pp.q0 = d_q.as<uint32_t>(); pp.q1 = pp.q0 + n_slots; pp.n_add = pp.q0 + 2 * n_slots;
+    pp.entry_off = d_eoff.as<uint64_t>(); pp.entries = nullptr;
+    const int slot_t = ctx->timer.begin("l0_palindrome_patches", st);
+    patch_replay_kernel<0><<<ceil_div<uint32_t>(n_aff, 32), 32, 0, st>>>(pp);
+    PATCH_CUDA(cudaGetLastError());
+    std::vector<uint32_t> h_np(n_aff), h_q(3 * (size_t)n_slots);
+    PATCH_CUDA(cudaMemcpyAsync(h_np.data(), d_np.p, n_aff * 4, cudaMemcpyDeviceToHost, st));
+    PATCH_CUDA(cudaMemcpyAsync(h_q.data(), d_q.p, (size_t)n_slots * 12, cudaMemcpyDeviceToHost, st));
+    PATCH_CUDA(cudaStreamSynchronize(st));
+    // compact patch table (sorted by sequence, then position) + per-slot entry offsets for the write pass
+    std::vector<uint32_t> pseq, pq0, pq1, padd;
+    std::vector<uint64_t> pentry_off, slot_eoff(n_slots, 0);
+    std::vector<int32_t> seq_first(n, -1);
+    std::vector<uint32_t> seq_np(n, 0);
+    uint64_t n_entries = 0;
+    for (uint32_t a = 0; a < n_aff; a++) {
+        seq_first[aff_seq[a]] = (int32_t)pseq.size();
+        seq_np[aff_seq[a]] = h_np[a];
+        for (uint32_t j = 0; j < h_np[a]; j++) {
+            const uint32_t slot = skip_off[a] + j;
+            pseq.push_back(aff_seq[a]); pq0.push_back(h_q[slot]); pq1.push_back(h_q[n_slots + slot]); padd.push_back(h_q[2 * (size_t)n_slots + slot]);
+            pentry_off.push_back(n_entries);
+            slot_eoff[slot] = n_entries;
+            n_entries += h_q[2 * (size_t)n_slots + slot];
+        }
+    }
+    const uint32_t n_patches = (uint32_t)pseq.size();
+    PATCH_TRY(d_entries.ensure(std::max<uint64_t>(1, n_entries) * sizeof(pgr_mm128)));
+    PATCH_CUDA(cudaMemcpyAsync(d_eoff.p, slot_eoff.data(), (size_t)n_slots * 8, cudaMemcpyHostToDevice, st));
+    pp.entries = d_entries.as<pgr_mm128>();
+    patch_replay_kernel<1><<<ceil_div<uint32_t>(n_aff, 32), 32, 0, st>>>(pp);
+    PATCH_CUDA(cudaGetLastError());
+    // patch metadata on the device: [pseq | pq0 | pq1 | padd | plb | pub] u32, then pentry_off, pdelta, pdst u64/i64
+    const size_t P = n_patches;
+    PATCH_TRY(d_meta.ensure(P * 4 * 6 + P * 8 * 3 + n * 4 * 2 + (n + 1) * 8 + 64));
+    uint32_t *m_u32 = d_meta.as<uint32_t>();
+    uint64_t *m_u64 = (uint64_t *)(m_u32 + 6 * P + (P & 1) * 0 + ((6 * P) & 1));
+    // keep 8-byte alignment of the u64 block
+    m_u64 = (uint64_t *)(((uintptr_t)(m_u32 + 6 * P) + 7) & ~(uintptr_t)7);
+    int32_t *m_first = (int32_t *)(m_u64 + 3 * P + (n + 1));
+    uint32_t *m_np = (uint32_t *)(m_first + n);
+    PATCH_CUDA(cudaMemcpyAsync(m_u32, pseq.data(), P * 4, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(m_u32 + P, pq0.data(), P * 4, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(m_u32 + 2 * P, pq1.data(), P * 4, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(m_u32 + 3 * P, padd.data(), P * 4, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(m_u64, pentry_off.data(), P * 8, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(m_first, seq_first.data(), n * 4, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(m_np, seq_np.data(), n * 4, cudaMemcpyHostToDevice, st));
+    SpliceParams sp;
+    sp.flat0 = ctx->bufA.as<pgr_mm128>(); sp.off0 = ctx->seq_dst.as<uint64_t>(); sp.n_seq = (uint32_t)n;
+    sp.seq_first_patch = m_first; sp.seq_n_patch = m_np;
+    sp.pseq = m_u32; sp.pq0 = m_u32 + P; sp.pq1 = m_u32 + 2 * P; sp.pn_add = m_u32 + 3 * P; sp.plb = m_u32 + 4 * P; sp.pub = m_u32 + 5 * P;
+    sp.pentry_off = m_u64; sp.pdelta = (const int64_t *)(m_u64 + P); sp.pdst = m_u64 + 2 * P; sp.off1 = m_u64 + 3 * P;
+    sp.entries = d_entries.as<pgr_mm128>(); sp.n_patches = n_patches; sp.n0 = off0[n];
+    splice_bounds_kernel<<<ceil_div<uint32_t>(n_patches, 64), 64, 0, st>>>(sp);
+    PATCH_CUDA(cudaGetLastError());
+    std::vector<uint32_t> plb(P), pub(P);
+    PATCH_CUDA(cudaMemcpyAsync(plb.data(), sp.plb, P * 4, cudaMemcpyDeviceToHost, st));
+    PATCH_CUDA(cudaMemcpyAsync(pub.data(), sp.pub, P * 4, cudaMemcpyDeviceToHost, st));
+    PATCH_CUDA(cudaStreamSynchronize(st));
+    std::vector<int64_t> pdelta(P), seq_delta(n, 0);
+    for (size_t j = 0; j < P; j++) {
+        pdelta[j] = seq_delta[pseq[j]];
+        seq_delta[pseq[j]] += (int64_t)padd[j] - (int64_t)(pub[j] - plb[j]);
+    }
+    std::vector<uint64_t> off1(n + 1), pdst(P);
+    uint64_t acc = 0;
+    for (size_t i = 0; i < n; i++) { off1[i] = acc; acc += (uint64_t)((int64_t)(off0[i + 1] - off0[i]) + seq_delta[i]); }
+    off1[n] = acc;
+    for (size_t j = 0; j < P; j++) pdst[j] = off1[pseq[j]] + plb[j] + (uint64_t)pdelta[j];
+    std::vector<uint32_t> entry_patch(n_entries);
+    for (size_t j = 0; j < P; j++) for (uint32_t e = 0; e < padd[j]; e++) entry_patch[pentry_off[j] + e] = (uint32_t)j;
+    PATCH_TRY(d_epatch.ensure(std::max<uint64_t>(1, n_entries) * 4));
+    PATCH_CUDA(cudaMemcpyAsync((void *)sp.pdelta, pdelta.data(), P * 8, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync((void *)sp.pdst, pdst.data(), P * 8, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync((void *)sp.off1, off1.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_entries) PATCH_CUDA(cudaMemcpyAsync(d_epatch.p, entry_patch.data(), n_entries * 4, cudaMemcpyHostToDevice, st));
+    PATCH_TRY(ctx->bufB.ensure(std::max<uint64_t>(1, acc) * sizeof(pgr_mm128)));
+    sp.flat1 = ctx->bufB.as<pgr_mm128>();
+    if (sp.n0) splice_copy_kernel<<<(uint32_t)ceil_div<uint64_t>(sp.n0, 256), 256, 0, st>>>(sp);
+    if (n_entries) splice_patch_kernel<<<(uint32_t)ceil_div<uint64_t>(n_entries, 256), 256, 0, st>>>(sp, n_entries, d_epatch.as<uint32_t>());
+    PATCH_CUDA(cudaGetLastError());
+    PATCH_CUDA(cudaMemcpyAsync(ctx->seq_dst.p, off1.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    ctx->timer.end(slot_t, st);
+    PATCH_CUDA(cudaStreamSynchronize(st));
+    ctx->counters[0] += 5;
+    ctx->counters[4] = n_patches;
+    std::swap(ctx->bufA, ctx->bufB);
+    PATCH_TRY(ctx->bufB.ensure(std::max<uint64_t>(1, acc) * sizeof(pgr_mm128)));
+    *n_l0 = acc;
+    cleanup();
+#undef PATCH_TRY
+#undef PATCH_CUDA
+    return PGR_OK;
+}
+
 // level-0 minimizers for the whole store -> flat list in ctx->bufA, per-sequence offsets in ctx->seq_dst
 int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     cudaStream_t st = ctx->stream;
@@ -400,20 +547,24 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     PGR_TRY(ctx->chunk_count.ensure(G * sizeof(uint64_t)));
     PGR_TRY(ctx->seq_count.ensure(n * sizeof(uint32_t)));
     PGR_TRY(ctx->seq_flag.ensure(n * sizeof(uint32_t)));
+    PGR_TRY(ctx->skips.ensure((size_t)SKIP_CAP * sizeof(uint2)));
+    PGR_TRY(ctx->n_skips.ensure(64));
     PGR_CUDA(cudaMemcpyAsync(ctx->tile_prefix.p, tile_prefix.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     PGR_CUDA(cudaMemcpyAsync(ctx->cta_tile.p, cta_tile.data(), (G + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     // arena: expected density 2/(w+1) with 2x headroom; exact retry on overflow
     uint64_t chunk_cap = (uint64_t)((double)max_cost * std::min(1.0, 4.0 / (w + 1.0))) + 1024;
     chunk_cap = std::max(chunk_cap, ctx->chunk_cap * 0 + chunk_cap);
-    PGR_TRY(ctx->ensure_ctl(G * sizeof(uint64_t) + 2 * n * sizeof(uint32_t) + 64));
+    PGR_TRY(ctx->ensure_ctl(G * sizeof(uint64_t) + 2 * n * sizeof(uint32_t) + 128));
     uint64_t *h_chunk = (uint64_t *)ctx->h_ctl;
     uint32_t *h_count = (uint32_t *)(h_chunk + G);
     uint32_t *h_flag = h_count + n;
+    uint32_t *h_nskips = h_flag + n;
     for (int attempt = 0;; attempt++) {
         PGR_TRY(ctx->arena.ensure((size_t)G * chunk_cap * sizeof(pgr_mm128)));
         ctx->chunk_cap = chunk_cap;
         PGR_CUDA(cudaMemsetAsync(ctx->seq_count.p, 0, n * sizeof(uint32_t), st));
         PGR_CUDA(cudaMemsetAsync(ctx->seq_flag.p, 0, n * sizeof(uint32_t), st));
+        PGR_CUDA(cudaMemsetAsync(ctx->n_skips.p, 0, sizeof(uint32_t), st));
         L0Params p;
         p.seq = ctx->d_seq; p.off = (ctx->d_off.as<uint64_t>() + ctx->r0); p.len = (ctx->d_len.as<uint32_t>() + ctx->r0);
         p.tile_prefix = ctx->tile_prefix.as<uint32_t>(); p.cta_tile = ctx->cta_tile.as<uint32_t>();
@@ -421,6 +572,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         p.arena = ctx->arena.as<pgr_mm128>(); p.chunk_cap = chunk_cap;
         p.chunk_count = ctx->chunk_count.as<uint64_t>(); p.seq_count = ctx->seq_count.as<uint32_t>();
         p.seq_flag = ctx->seq_flag.as<uint32_t>();
+        p.skips = ctx->skips.as<uint2>(); p.n_skips = ctx->n_skips.as<uint32_t>(); p.skip_cap = SKIP_CAP;
         const int slot = ctx->timer.begin("l0_minimizers", st);
         if (variant == 1) PGR_TRY((launch_l0<80, 56>(p, (int)G, st)));
         else if (variant == 2) PGR_TRY((launch_l0<48, 56>(p, (int)G, st)));
@@ -430,6 +582,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         PGR_CUDA(cudaMemcpyAsync(h_chunk, ctx->chunk_count.p, G * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         PGR_CUDA(cudaMemcpyAsync(h_count, ctx->seq_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         PGR_CUDA(cudaMemcpyAsync(h_flag, ctx->seq_flag.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(h_nskips, ctx->n_skips.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         PGR_CUDA(cudaStreamSynchronize(st));
         uint64_t mx = 0;
         for (uint32_t c = 0; c < G; c++) mx = std::max(mx, h_chunk[c]);
@@ -515,6 +668,11 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     }
     // the host vectors above are pageable: make sure the async copies are done before they go out of scope
     PGR_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_skips = std::min<uint32_t>(*h_nskips, SKIP_CAP);
+    if (n_skips && total) {
+        std::vector<uint32_t> flags(h_flag, h_flag + n);
+        PGR_TRY(apply_palindrome_patches(ctx, spec, n_skips, flags, seq_dst, n_l0));
+    }
     return PGR_OK;
 }
 

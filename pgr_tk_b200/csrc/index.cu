@@ -206,7 +206,10 @@ int pgr_b200_index_get_spec(const pgr_b200_index *idx, pgr_shmmr_spec *spec) {
 int pgr_b200_index_add_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens) {
     if (!idx || (n && (!sids || !seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
     idx->finalized = false;
-    return index_batch_tuples(idx, n, sids, seqs, lens, false, nullptr, nullptr, nullptr);
+    trace_mark("index_add_batch: begin");
+    const int rc = index_batch_tuples(idx, n, sids, seqs, lens, false, nullptr, nullptr, nullptr);
+    trace_mark("index_add_batch: shimmers + tuples");
+    return rc;
 }
 
 int pgr_b200_index_stage_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
@@ -247,6 +250,7 @@ int pgr_b200_index_finalize(pgr_b200_index *idx) {
     PGR_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint64_t n = idx->n_tuples;
+    trace_mark("index_finalize: begin");
     if (n >= 0xFFFFFFF0ull) { set_error("more than 2^32 tuples on one device"); return PGR_E_LIMIT; }
     PGR_TRY(idx->offsets.ensure(sizeof(uint64_t) * (n + 2)));
     if (n == 0) {
@@ -283,6 +287,7 @@ int pgr_b200_index_finalize(pgr_b200_index *idx) {
     PGR_CUDA(cudaGetLastError());
     PGR_CUDA(cudaStreamSynchronize(st));
     idx->finalized = true;
+    trace_mark("index_finalize: sort + CSR");
     return PGR_OK;
 }
 

@@ -136,10 +136,13 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
     PGR_CUDA(cudaSetDevice(idx->ctx->device));
     pgr_b200_ctx *ctx = idx->ctx;
     cudaStream_t st = ctx->stream;
+    trace_mark("query_batch: begin");
     PGR_TRY(ensure_sid_count(idx));
+    trace_mark("query_batch: sid_count");
     uint64_t n_qp = 0;
     std::vector<uint64_t> qp_off;
     PGR_TRY(query_pairs_and_lookup(idx, n_q, seqs, lens, &n_qp, &qp_off));
+    trace_mark("query_batch: shimmers+pairs+lookup");
 
     QueryFilter f;
     f.max_count = prm->max_count < 0 ? 128u : (uint32_t)prm->max_count;
@@ -178,6 +181,7 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
             const uint32_t gh = (uint32_t)ceil_div<uint64_t>(n_hits, 256);
             iota_kernel<<<gh, 256, 0, st>>>(idx->idxA.as<uint32_t>(), n_hits);
             idx->launches += 2;
+            trace_mark("query_batch: filters+expand");
             // stable sort by (qid, sid): bytes 0..3 of k1 (sid) then bytes 0..3 of k0 (qid)
             PGR_TRY(index_sort(idx, n_hits, 0, 3));
             PGR_TRY(index_sort(idx, n_hits, 7, 10));
@@ -200,6 +204,7 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
                                                    idx->seg_keys.as<SortKey>(), idx->seg_off.as<uint64_t>());
             set_u64_kernel<<<1, 1, 0, st>>>(idx->seg_off.as<uint64_t>() + n_seg, n_hits);
             idx->launches += 5;
+            trace_mark("query_batch: sort+segments");
             // chaining
             PGR_TRY(idx->chain_f.ensure(n_hits * sizeof(float) * 2));
             PGR_TRY(idx->chain_u.ensure(n_hits * sizeof(uint32_t) * 5));
@@ -217,6 +222,7 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
             chain_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 64), 64, 0, st>>>(cp);
             idx->launches += 1;
             PGR_CUDA(cudaGetLastError());
+            trace_mark("query_batch: chain kernel");
             // read back and assemble the nested result (host pass over the output)
             std::vector<SortKey> seg_keys(n_seg);
             std::vector<uint64_t> seg_off(n_seg + 1);
@@ -232,6 +238,7 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
             PGR_CUDA(cudaMemcpyAsync(out_score.data(), cp.out_score, n_hits * sizeof(float), cudaMemcpyDeviceToHost, st));
             PGR_CUDA(cudaMemcpyAsync(hrec.data(), idx->hitsB.p, n_hits * sizeof(HitRec), cudaMemcpyDeviceToHost, st));
             PGR_CUDA(cudaStreamSynchronize(st));
+            trace_mark("query_batch: D2H");
             size_t qi = 0;
             for (uint64_t s = 0; s < n_seg; s++) {
                 if (seg_meta[2 * n_seg + s]) { set_error("sparse_aln: all scores <= 0 (the reference would not terminate)"); return PGR_E_ASSERT; }
@@ -258,6 +265,7 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
             while (qi < n_q) { qi++; q_target_off[qi] = target_sid.size(); }
         }
     }
+    trace_mark("query_batch: host assembly");
     // chain_hit_off was built with one leading 0 and one entry per chain end
     pgr_query_result *r = (pgr_query_result *)calloc(1, sizeof(pgr_query_result));
     r->n_queries = n_q; r->n_targets = target_sid.size(); r->n_chains = chain_score.size(); r->n_hits = hits_out.size();
@@ -340,6 +348,7 @@ int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *kee
     *out = (pgr_adj_pair *)malloc(sizeof(pgr_adj_pair));
     *n_out = 0;
     if (n < 2) return PGR_OK;  // seq_db.rs:889-891
+    trace_mark("adj_list: begin (after finalize)");
     std::vector<uint32_t> ks(keeps, keeps + (has_keeps ? n_keeps : 0));
     std::sort(ks.begin(), ks.end());
     PGR_TRY(idx->scratch0.ensure(std::max<size_t>(1, ks.size()) * sizeof(uint32_t)));
@@ -358,6 +367,7 @@ int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *kee
         idx->launches += 1;
         PGR_TRY(index_sort(idx, n, 0, 13));
     }
+    trace_mark("adj_list: rows + 3 sort rounds");
     PGR_TRY(idx->scratch1.ensure(n * sizeof(uint32_t)));
     PGR_TRY(idx->scratch2.ensure((n + 1) * sizeof(uint64_t)));
     adj_flag_kernel<<<g, 256, 0, st>>>(rows, idx->idxA.as<uint32_t>(), n, idx->scratch1.as<uint32_t>());
@@ -376,6 +386,7 @@ int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *kee
     PGR_CUDA(cudaMemcpyAsync(*out, idx->scratch3.p, total * sizeof(pgr_adj_pair), cudaMemcpyDeviceToHost, st));
     PGR_CUDA(cudaStreamSynchronize(st));
     *n_out = total;
+    trace_mark("adj_list: join + D2H");
     return PGR_OK;
 }
 

@@ -38,6 +38,9 @@ struct L0Params {
     uint64_t *chunk_count;       // [grid] entries demanded by each CTA (may exceed chunk_cap => host retries)
     uint32_t *seq_count;         // [n_seq] level-0 entries per sequence (atomicAdd per tile)
     uint32_t *seq_flag;          // [n_seq] != 0 => sequence must be replayed sequentially
+    uint2 *skips;                // (sequence, position) of pushed positions with fmmer == rmmer (shmmrutils.rs:477)
+    uint32_t *n_skips;           // running count; beyond skip_cap the sequence is flagged instead
+    uint32_t skip_cap;
 };
 
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
@@ -245,7 +248,11 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                 const bool rev = R0 < F0;                       // shmmrutils.rs:486 (plane 0 only)
                 if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
                     const int pos = blk_pos + i;
-                    if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) s.bad = 1;
+                    if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) {
+                        // a palindrome is not pushed: the neighbourhood is re-derived by patch_replay_kernel
+                        const uint32_t slot = atomicAdd(p.n_skips, 1u);
+                        if (slot < p.skip_cap) p.skips[slot] = make_uint2(s.seq_id, (uint32_t)pos); else s.bad = 1;
+                    }
                 }
                 const uint64_t u = rev ? R0 : F0;
                 const uint64_t v = rev ? (((uint64_t)r1hi << 32) | r1lo) : (((uint64_t)f1hi << 32) | f1lo);
@@ -526,6 +533,201 @@ __global__ void replay_l0_kernel(const ReplayParams p) {
         mdist++;
     }
     if (!MODE) p.count[sid] = (uint32_t)n_out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Palindrome patches.  A pushed position with fmmer == rmmer is skipped by the reference (not pushed, mdist not
+// advanced), which breaks the local rule in its neighbourhood and can leave the machine in an anomalous state
+// (duplicate emissions, stuck mdist) until its next emission.  One thread per affected sequence replays the exact
+// machine around every cluster of such positions:
+//   start S = p* - 2w (a fresh machine is in sync with the true one after w pushes without a skip; S is pulled back so
+//   that those w pushes lie before L-w+k, or set to k = the true start when the cluster is near the sequence start);
+//   emissions at times < T0 = S + w are discarded, q0 = position of the last of them;
+//   the replay ends at the first emission at a time t with  p_last + 2w <= t < L-w+k - w  and no further skip within w
+//   (from there the machine is in its normal regime and the windows of later positions contain no skip): q1 = the
+//   position emitted last; otherwise it runs to the end of the sequence (q1 = UINT32_MAX).
+// The patch replaces the tile kernel's level-0 entries with q0 < pos <= q1.
+struct PatchParams {
+    const uint8_t *seq; const uint64_t *off; const uint32_t *len;
+    const uint32_t *aff_seq;      // [n_aff] sequence ordinals with skips
+    const uint32_t *skip_off;     // [n_aff+1] offsets into skip_pos
+    const uint32_t *skip_pos;     // sorted positions per affected sequence
+    uint32_t n_aff;
+    uint32_t w, k;
+    // per-patch outputs, slot = skip_off[a] + j (at most one patch per skip)
+    uint32_t *n_patches;          // [n_aff]
+    uint32_t *q0, *q1, *n_add;    // q0 = UINT32_MAX encodes "from the start" (-1)
+    const uint64_t *entry_off;    // [n_slots] (mode 1) where the patch's entries go
+    pgr_mm128 *entries;
+};
+
+template <int MODE>
+__global__ void patch_replay_kernel(const PatchParams p) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= p.n_aff) return;
+    const uint32_t sid = p.aff_seq[a];
+    const uint8_t *sq = p.seq + p.off[sid];
+    const int64_t L = p.len[sid];
+    const int64_t w = p.w, k = p.k;
+    const uint64_t mask = ~0ull >> (64 - k);
+    const uint32_t shift = (uint32_t)k - 1;
+    const int64_t E = L - w + k;                      // rule (2) active for pos < E
+    const uint32_t *sk = p.skip_pos + p.skip_off[a];
+    const uint32_t ns = p.skip_off[a + 1] - p.skip_off[a];
+    const uint32_t slot0 = p.skip_off[a];
+    uint32_t n_patch = 0, si = 0;
+    uint64_t rx[128]; uint32_t ry[128];
+    while (si < ns) {
+        const int64_t pstar = sk[si];
+        int64_t S = pstar - 2 * w;
+        if (S + w > E - 1) S = E - 1 - w;
+        bool from_start = false;
+        if (S < k + w + 1) { S = k; from_start = true; }
+        const int64_t T0 = from_start ? k : S + w;
+        // registers: roll over the k bases before S (positions S-k .. S-1); from the true start they begin at zero
+        uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;
+        const int64_t r_begin = from_start ? 0 : S - k;
+        for (int64_t q = r_begin; q < S; q++) {
+            const uint32_t c = base_code(sq[q]);
+            if (c < 4) {
+                f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
+                const uint64_t rc = 3 ^ c;
+                r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
+            }
+        }
+        for (int64_t i = 0; i < w; i++) { rx[i] = ~0ull; ry[i] = ~0u; }
+        uint32_t r_start = 0, r_end = 0, r_len = 0;
+        uint64_t min_x = ~0ull, mdist = 0;
+        int64_t p_last = pstar;
+        uint32_t q0 = 0xFFFFFFFFu, q1 = 0xFFFFFFFFu, n_add = 0;
+        uint32_t last_emit = 0xFFFFFFFFu;
+        bool done = false;
+        pgr_mm128 *dst = MODE ? p.entries + p.entry_off[slot0 + n_patch] : nullptr;
+        for (int64_t pos = S; pos < L && !done; pos++) {
+            const uint32_t c = base_code(sq[pos]);
+            if (c < 4) {
+                f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
+                const uint64_t rc = 3 ^ c;
+                r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
+            }
+            if (f0 == r0 && f1 == r1) { if (pos >= k) p_last = pos; continue; }
+            if (pos < k) continue;
+            const bool rev = r0 < f0;
+            const uint64_t h = rev ? (u64hash(r0) ^ u64hash(r1 ^ HASH_XOR)) : (u64hash(f0) ^ u64hash(f1 ^ HASH_XOR));
+            const uint64_t mx = (h << 8) | (uint64_t)k;
+            const uint32_t my = ((uint32_t)pos << 1) | (rev ? 1u : 0u);
+            rx[r_end] = mx; ry[r_end] = my;
+            r_end = (r_end + 1) % (uint32_t)w;
+            if (r_len < (uint32_t)w) r_len++; else r_start = (r_start + 1) % (uint32_t)w;
+            bool emitted = false;
+            if (mdist == (uint64_t)(w - 1)) {
+                uint64_t mn = ~0ull;
+                for (uint32_t i = 0; i < r_len; i++) if (rx[i] < mn) mn = rx[i];
+                uint32_t last_y = 0;
+                for (uint32_t i = 0; i < (uint32_t)w; i++) {
+                    const uint32_t sl = (r_start + i) % (uint32_t)w;
+                    if (rx[sl] == mn) {
+                        if (pos >= T0) {
+                            if (MODE) { pgr_mm128 mm; mm.x = rx[sl]; mm.y = ((uint64_t)sid << 32) | ry[sl]; dst[n_add] = mm; }
+                            n_add++;
+                        } else {
+                            q0 = ry[sl] >> 1;
+                        }
+                        last_y = ry[sl];
+                        last_emit = ry[sl] >> 1;
+                        emitted = true;
+                    }
+                }
+                min_x = mn;
+                mdist = (uint64_t)pos - (uint64_t)(last_y >> 1);
+            } else if (mx <= min_x && pos >= w + k && pos < E && pos < L) {
+                if (pos >= T0) {
+                    if (MODE) { pgr_mm128 mm; mm.x = mx; mm.y = ((uint64_t)sid << 32) | my; dst[n_add] = mm; }
+                    n_add++;
+                } else {
+                    q0 = (uint32_t)pos;
+                }
+                last_emit = (uint32_t)pos;
+                emitted = true;
+                min_x = mx;
+                mdist = 0;
+            } else {
+                mdist++;
+            }
+            if (emitted && pos >= T0) {
+                // every skip up to pos has been seen by the machine; find the next one in the list
+                while (si < ns && (int64_t)sk[si] <= pos) si++;
+                const bool next_far = (si >= ns) || ((int64_t)sk[si] > pos + w);
+                if (pos >= p_last + 2 * w && pos < E - w && next_far) { q1 = last_emit; done = true; }
+            }
+        }
+        if (!done) si = ns;  // ran to the end of the sequence: everything after q0 is replaced
+        if (from_start) q0 = 0xFFFFFFFFu;
+        p.q0[slot0 + n_patch] = q0; p.q1[slot0 + n_patch] = q1; p.n_add[slot0 + n_patch] = n_add;
+        n_patch++;
+    }
+    p.n_patches[a] = n_patch;
+}
+
+// splice the patches into the flat level-0 list.  Patches are sorted by (sequence, q0); per patch: lb = number of the
+// sequence's entries with pos <= q0 (0 for "from the start"), ub = number with pos <= q1.
+struct SpliceParams {
+    const pgr_mm128 *flat0; const uint64_t *off0;      // before
+    pgr_mm128 *flat1; const uint64_t *off1;            // after
+    uint32_t n_seq;
+    const int32_t *seq_first_patch;                    // [n_seq] first patch index of the sequence or -1
+    const uint32_t *seq_n_patch;                       // [n_seq]
+    const uint32_t *pq0, *pq1;                         // per patch
+    uint32_t *plb, *pub;                               // per patch (bounds kernel output)
+    const int64_t *pdelta;                             // per patch: cumulative (added - removed) of the sequence's EARLIER patches
+    const uint64_t *pdst;                              // per patch: where its entries start in flat1
+    const uint32_t *pseq; const uint32_t *pn_add; const uint64_t *pentry_off;
+    const pgr_mm128 *entries;
+    uint32_t n_patches;
+    uint64_t n0;
+};
+
+__device__ __forceinline__ uint32_t mm_pos32(const pgr_mm128 &m) { return (uint32_t)(m.y & 0xFFFFFFFFu) >> 1; }
+
+__global__ void splice_bounds_kernel(const SpliceParams p) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.n_patches) return;
+    const uint32_t s = p.pseq[j];
+    const uint64_t b = p.off0[s], e = p.off0[s + 1];
+    auto count_le = [&](uint32_t q) -> uint32_t {   // entries of s with pos <= q
+        uint64_t lo = b, hi = e;
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (mm_pos32(p.flat0[mid]) <= q) lo = mid + 1; else hi = mid; }
+        return (uint32_t)(lo - b);
+    };
+    p.plb[j] = (p.pq0[j] == 0xFFFFFFFFu) ? 0u : count_le(p.pq0[j]);
+    p.pub[j] = (p.pq1[j] == 0xFFFFFFFFu) ? (uint32_t)(e - b) : count_le(p.pq1[j]);
+}
+
+__global__ void splice_copy_kernel(const SpliceParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n0) return;
+    const pgr_mm128 mm = p.flat0[i];
+    const uint32_t s = (uint32_t)(mm.y >> 32);
+    const uint64_t rel = i - p.off0[s];
+    const int32_t fp = p.seq_first_patch[s];
+    if (fp < 0) { p.flat1[p.off1[s] + rel] = mm; return; }
+    // patches of s are sorted; find the last one whose lb <= rel
+    const uint32_t np = p.seq_n_patch[s];
+    int64_t delta = 0;
+    for (uint32_t j = 0; j < np; j++) {
+        const uint32_t lb = p.plb[fp + j], ub = p.pub[fp + j];
+        if (rel < lb) break;
+        if (rel < ub) return;                          // inside (q0, q1]: replaced by the patch
+        delta = p.pdelta[fp + j] + (int64_t)p.pn_add[fp + j] - (int64_t)(ub - lb);
+    }
+    p.flat1[p.off1[s] + (uint64_t)((int64_t)rel + delta)] = mm;
+}
+
+__global__ void splice_patch_kernel(const SpliceParams p, uint64_t n_entries_total, const uint32_t *entry_patch) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_entries_total) return;
+    const uint32_t j = entry_patch[i];
+    p.flat1[p.pdst[j] + (i - p.pentry_off[j])] = p.entries[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -114,8 +114,51 @@ def test_invalid_bytes_and_palindromes_take_replay_path():
     ctx = pg.Ctx(0)
     ctx.upload(seqs)
     ctx.shmmrs(pg.ShmmrSpec())
-    assert ctx.counters()[2] == 4  # four sequences were replayed, the clean one was not
+    c = ctx.counters()
+    assert c[2] == 3   # invalid bytes: whole-sequence replay (s1, s3, s4); the clean sequence is not replayed
+    assert c[4] >= 1   # the (AT)n palindromes of s2 are handled by a local patch
     ctx.close()
+
+
+COMP = bytes.maketrans(b"ACGT", b"TGCA")
+
+
+def revcomp(s):
+    return s.translate(COMP)[::-1]
+
+
+def test_palindrome_patches_inverted_repeats_and_runs():
+    """pushed positions with fmmer == rmmer (shmmrutils.rs:477) are re-derived by an exact local replay"""
+    rng = np.random.default_rng(101)
+    u = rand_seq(rng, 4000)
+    seqs = [
+        rand_seq(rng, 20000) + u + revcomp(u) + rand_seq(rng, 20000),                 # perfect inverted repeat: one palindromic centre
+        rand_seq(rng, 300) + u + revcomp(u) + rand_seq(rng, 100),                     # near both ends
+        u[:200] + revcomp(u[:200]),                                                   # whole sequence is one palindrome
+        rand_seq(rng, 9000) + b"AT" * 400 + rand_seq(rng, 9000),                      # long run of consecutive skips
+        b"AT" * 300 + rand_seq(rng, 5000) + b"TA" * 100,                              # runs at the very start / end
+        b"".join(rand_seq(rng, int(rng.integers(150, 900))) + x + revcomp(x) for x in [rand_seq(rng, 70) for _ in range(40)]),  # many clusters
+        rand_seq(rng, 30000),                                                         # clean
+    ]
+    for w, k, r, ms in [(80, 56, 4, 64), (48, 56, 4, 12), (24, 24, 12, 24), (128, 56, 2, 0), (33, 40, 3, 5), (80, 56, 1, 0)]:
+        assert_batch_equal(seqs, pg.ShmmrSpec(w, k, r, ms))
+    ctx = pg.Ctx(0)
+    ctx.upload(seqs)
+    ctx.shmmrs(pg.ShmmrSpec())
+    c = ctx.counters()
+    assert c[2] == 0 and c[4] >= 6
+    ctx.close()
+
+
+def test_palindrome_patches_small_even_k_random():
+    """even small k makes palindromic k-mers frequent on random sequence: clusters merge, replays run long"""
+    rng = np.random.default_rng(103)
+    for it in range(12):
+        k = [6, 8, 10, 12, 16][rng.integers(5)]
+        w = [4, 8, 24, 33, 48, 80, 128][rng.integers(7)]
+        r = int(rng.integers(1, 6))
+        seqs = [rand_seq(rng, int(rng.integers(50, 40000))) for _ in range(6)] + [rand_seq(rng, 9000, b"AT"), rand_seq(rng, 9000, b"ACGTTTTAAA")]
+        assert_batch_equal(seqs, pg.ShmmrSpec(w, k, r, int([0, 5, 30][rng.integers(3)])), padding=bool(rng.integers(2)))
 
 
 def test_sketch_mode_random():
