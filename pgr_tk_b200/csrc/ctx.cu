@@ -233,7 +233,7 @@ static int upload_layout(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, cons
 // that they share one copy.
 static int upload_copy(pgr_b200_ctx *ctx, const uint8_t *const *seqs, const size_t *lens, size_t i0, size_t i1, cudaStream_t st) {
     uint8_t *base = ctx->seq_store.as<uint8_t>();
-    const size_t BIG = 1u << 20, STAGE = 64u << 20;
+    const size_t BIG = 128u << 10, STAGE = 16u << 20;   // pinning is ~0.3 ms/MB: keep the staging buffers small
     uint8_t *stage[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int cur = 0;
@@ -591,6 +591,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         chunk_cap = mx + mx / 16 + 64;
         ctx->counters[3] += 1;
     }
+    trace_mark("run_l0: l0 kernel + control read-back");
     // sequences flagged for sequential replay
     std::vector<uint32_t> replay;
     for (size_t i = 0; i < n; i++) if (h_flag[i]) replay.push_back((uint32_t)i);
@@ -668,10 +669,12 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     }
     // the host vectors above are pageable: make sure the async copies are done before they go out of scope
     PGR_CUDA(cudaStreamSynchronize(st));
+    trace_mark("run_l0: replay + gather");
     const uint32_t n_skips = std::min<uint32_t>(*h_nskips, SKIP_CAP);
     if (n_skips && total) {
         std::vector<uint32_t> flags(h_flag, h_flag + n);
         PGR_TRY(apply_palindrome_patches(ctx, spec, n_skips, flags, seq_dst, n_l0));
+        trace_mark("run_l0: palindrome patches");
     }
     return PGR_OK;
 }
@@ -884,7 +887,9 @@ int pgr::run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const ui
                      const pgr_shmmr_spec &spec, int padding, const std::function<int(size_t, size_t, size_t)> &on_chunk) {
     PGR_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->copy_stream) PGR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    trace_mark("run_chunked: begin");
     PGR_TRY(upload_layout(ctx, n, rids, seqs, lens));
+    trace_mark("run_chunked: layout");
     ctx->timer.reset();
     // chunk boundaries: about 1/16 of the batch each, at least 64 MB, whole sequences
     const uint64_t chunk_bytes = std::max<uint64_t>(64ull << 20, ctx->total_bases / 16);
@@ -906,6 +911,7 @@ int pgr::run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const ui
         cudaEventRecord(ev[c], ctx->copy_stream);
     }
     uint64_t tot[8] = {0};
+    trace_mark("run_chunked: H2D queued/staged");
     for (size_t c = 0; c < n_chunks && rc == PGR_OK; c++) {
         cudaStreamWaitEvent(ctx->stream, ev[c], 0);
         ctx->r0 = cut[c];
@@ -914,7 +920,9 @@ int pgr::run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const ui
         size_t ns = 0;
         if ((rc = shmmrs_range(ctx, spec, padding, &ns)) != PGR_OK) break;
         for (int i = 0; i < 8; i++) tot[i] += ctx->counters[i];
+        trace_mark("run_chunked: chunk reduce+span");
         rc = on_chunk(cut[c], ctx->rn, ns);
+        trace_mark("run_chunked: on_chunk");
     }
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);

@@ -191,7 +191,7 @@ void pgr_b200_index_free(pgr_b200_index *idx) {
                       &idx->head, &idx->block_sum, &idx->block_prefix, &idx->d_sid, &idx->d_pair_off, &idx->d_frg_base, &idx->qtuples,
                       &idx->q_hit_begin, &idx->q_hit_count, &idx->scratch0, &idx->scratch1, &idx->scratch2, &idx->scratch3,
                       &idx->sid_count, &idx->hitsA, &idx->hitsB, &idx->seg_keys, &idx->seg_off, &idx->chain_f, &idx->chain_u, &idx->chain_b,
-                      &idx->chain_seg};
+                      &idx->chain_seg, &idx->asm_prefix, &idx->asm_has, &idx->asm_out};
     for (auto b : bufs) b->release();
     pgr_b200_ctx_free(idx->ctx);
     delete idx;

@@ -125,7 +125,8 @@ int pgr_b200_raw_query(pgr_b200_index *idx, const uint8_t *seq, size_t len, pgr_
 
 void pgr_b200_query_result_free(pgr_query_result *r) {
     if (!r) return;
-    free(r->q_target_off); free(r->target_sid); free(r->target_chain_off); free(r->chain_score); free(r->chain_hit_off); free(r->hits);
+    result_free(r->q_target_off); result_free(r->target_sid); result_free(r->target_chain_off); result_free(r->chain_score);
+    result_free(r->chain_hit_off); result_free(r->hits);
     free(r);
 }
 
@@ -150,10 +151,11 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
     f.max_count_target = prm->max_count_target < 0 ? 128u : (uint32_t)prm->max_count_target;
     const uint32_t max_span = prm->max_aln_span < 0 ? 8u : (uint32_t)prm->max_aln_span;
 
-    std::vector<uint64_t> q_target_off(n_q + 1, 0), target_chain_off(1, 0), chain_hit_off(1, 0);
-    std::vector<uint32_t> target_sid;
-    std::vector<float> chain_score;
-    std::vector<pgr_hit_pair> hits_out;
+    std::vector<uint64_t> q_target_off(n_q + 1, 0);
+    uint32_t *r_target_sid = nullptr; uint64_t *r_target_chain_off = nullptr; float *r_chain_score = nullptr;
+    uint64_t *r_chain_hit_off = nullptr; pgr_hit_pair *r_hits = nullptr;
+    size_t n_targets = 0, n_chains = 0, n_hits_out = 0;
+    bool have_result = false;
 
     uint64_t n_hits = 0;
     if (n_qp) {
@@ -223,54 +225,79 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
             idx->launches += 1;
             PGR_CUDA(cudaGetLastError());
             trace_mark("query_batch: chain kernel");
-            // read back and assemble the nested result (host pass over the output)
-            std::vector<SortKey> seg_keys(n_seg);
-            std::vector<uint64_t> seg_off(n_seg + 1);
-            std::vector<uint32_t> seg_meta(3 * n_seg), out_idx(n_hits);
-            std::vector<uint8_t> out_start(n_hits);
-            std::vector<float> out_score(n_hits);
-            std::vector<HitRec> hrec(n_hits);
-            PGR_CUDA(cudaMemcpyAsync(seg_keys.data(), idx->seg_keys.p, n_seg * sizeof(SortKey), cudaMemcpyDeviceToHost, st));
-            PGR_CUDA(cudaMemcpyAsync(seg_off.data(), idx->seg_off.p, (n_seg + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-            PGR_CUDA(cudaMemcpyAsync(seg_meta.data(), idx->chain_seg.p, 3 * n_seg * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            PGR_CUDA(cudaMemcpyAsync(out_idx.data(), cp.out_idx, n_hits * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            PGR_CUDA(cudaMemcpyAsync(out_start.data(), cp.out_start, n_hits, cudaMemcpyDeviceToHost, st));
-            PGR_CUDA(cudaMemcpyAsync(out_score.data(), cp.out_score, n_hits * sizeof(float), cudaMemcpyDeviceToHost, st));
-            PGR_CUDA(cudaMemcpyAsync(hrec.data(), idx->hitsB.p, n_hits * sizeof(HitRec), cudaMemcpyDeviceToHost, st));
-            PGR_CUDA(cudaStreamSynchronize(st));
-            trace_mark("query_batch: D2H");
-            size_t qi = 0;
-            for (uint64_t s = 0; s < n_seg; s++) {
-                if (seg_meta[2 * n_seg + s]) { set_error("sparse_aln: all scores <= 0 (the reference would not terminate)"); return PGR_E_ASSERT; }
-                const uint32_t n_out = seg_meta[s];
-                if (n_out == 0) continue;  // segments with a single hit are dropped (aln.rs:237)
-                const uint32_t qid = (uint32_t)seg_keys[s].k0;
-                while (qi < qid) { qi++; q_target_off[qi] = target_sid.size(); }
-                target_sid.push_back((uint32_t)seg_keys[s].k1);
-                const uint64_t b = seg_off[s];
-                for (uint32_t a = 0; a < n_out; a++) {
-                    if (out_start[b + a]) {
-                        if (a) chain_hit_off.push_back(hits_out.size());
-                        chain_score.push_back(out_score[b + a]);
-                    }
-                    const HitRec &h = hrec[b + out_idx[b + a]];
-                    pgr_hit_pair hp;
-                    memset(&hp, 0, sizeof hp);
-                    hp.qb = h.qb; hp.qe = h.qe; hp.qo = h.qo; hp.tb = h.tb; hp.te = h.te; hp.to = h.to;
-                    hits_out.push_back(hp);
-                }
-                chain_hit_off.push_back(hits_out.size());
-                target_chain_off.push_back(chain_score.size());
+            // nested result arrays on the device, then one D2H per array into (pinned) result buffers
+            uint64_t tot_hits = 0, tot_chains = 0, tot_targets = 0;
+            PGR_TRY(idx->asm_prefix.ensure(3 * (n_seg + 1) * sizeof(uint64_t)));
+            PGR_TRY(idx->asm_has.ensure(n_seg * sizeof(uint32_t)));
+            uint64_t *hit_prefix = idx->asm_prefix.as<uint64_t>(), *chain_prefix = hit_prefix + (n_seg + 1), *target_prefix = chain_prefix + (n_seg + 1);
+            seg_has_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 256), 256, 0, st>>>(cp.seg_n_out, n_seg, idx->asm_has.as<uint32_t>());
+            PGR_TRY(scan_u32(idx, cp.seg_n_out, n_seg, hit_prefix, &tot_hits));
+            PGR_TRY(scan_u32(idx, cp.seg_n_chains, n_seg, chain_prefix, &tot_chains));
+            PGR_TRY(scan_u32(idx, idx->asm_has.as<uint32_t>(), n_seg, target_prefix, &tot_targets));
+            // reference behaviour check: a segment whose scores are all <= 0 would never terminate in aln.rs:108-131
+            {
+                std::vector<uint32_t> err(n_seg);
+                PGR_CUDA(cudaMemcpyAsync(err.data(), cp.seg_err, n_seg * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                PGR_CUDA(cudaStreamSynchronize(st));
+                for (uint64_t s = 0; s < n_seg; s++)
+                    if (err[s]) { set_error("sparse_aln: all scores <= 0 (the reference would not terminate)"); return PGR_E_ASSERT; }
             }
-            while (qi < n_q) { qi++; q_target_off[qi] = target_sid.size(); }
+            PGR_TRY(idx->asm_out.ensure(tot_targets * 16 + (tot_targets + 1) * 8 + tot_chains * 4 + (tot_chains + 1) * 8 + tot_hits * sizeof(pgr_hit_pair) + 256));
+            uint8_t *ob = idx->asm_out.as<uint8_t>();
+            AssembleParams ap;
+            ap.hits = idx->hitsB.as<HitRec>(); ap.seg_off = idx->seg_off.as<uint64_t>(); ap.seg_keys = idx->seg_keys.as<SortKey>(); ap.n_seg = n_seg;
+            ap.out_idx = cp.out_idx; ap.out_start = cp.out_start; ap.out_score = cp.out_score; ap.seg_n_out = cp.seg_n_out;
+            ap.hit_prefix = hit_prefix; ap.chain_prefix = chain_prefix; ap.target_prefix = target_prefix;
+            ap.target_chain_off = (uint64_t *)ob; ob += (tot_targets + 1) * 8;
+            ap.chain_hit_off = (uint64_t *)ob; ob += (tot_chains + 1) * 8;
+            ap.hits_out = (pgr_hit_pair *)ob; ob += ((tot_hits * sizeof(pgr_hit_pair) + 7) & ~(size_t)7);
+            ap.target_sid = (uint32_t *)ob; ob += tot_targets * 4;
+            ap.target_qid = (uint32_t *)ob; ob += tot_targets * 4;
+            ap.chain_score = (float *)ob;
+            assemble_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 128), 128, 0, st>>>(ap);
+            set_u64_kernel<<<1, 1, 0, st>>>(ap.target_chain_off + tot_targets, tot_chains);
+            set_u64_kernel<<<1, 1, 0, st>>>(ap.chain_hit_off + tot_chains, tot_hits);
+            idx->launches += 4;
+            PGR_CUDA(cudaGetLastError());
+            trace_mark("query_batch: device assembly");
+            r_target_sid = (uint32_t *)result_alloc(std::max<uint64_t>(1, tot_targets) * 4);
+            r_target_chain_off = (uint64_t *)result_alloc((tot_targets + 1) * 8);
+            r_chain_score = (float *)result_alloc(std::max<uint64_t>(1, tot_chains) * 4);
+            r_chain_hit_off = (uint64_t *)result_alloc((tot_chains + 1) * 8);
+            r_hits = (pgr_hit_pair *)result_alloc(std::max<uint64_t>(1, tot_hits) * sizeof(pgr_hit_pair));
+            std::vector<uint32_t> tq(tot_targets);
+            if (tot_targets) {
+                PGR_CUDA(cudaMemcpyAsync(r_target_sid, ap.target_sid, tot_targets * 4, cudaMemcpyDeviceToHost, st));
+                PGR_CUDA(cudaMemcpyAsync(tq.data(), ap.target_qid, tot_targets * 4, cudaMemcpyDeviceToHost, st));
+            }
+            PGR_CUDA(cudaMemcpyAsync(r_target_chain_off, ap.target_chain_off, (tot_targets + 1) * 8, cudaMemcpyDeviceToHost, st));
+            if (tot_chains) PGR_CUDA(cudaMemcpyAsync(r_chain_score, ap.chain_score, tot_chains * 4, cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaMemcpyAsync(r_chain_hit_off, ap.chain_hit_off, (tot_chains + 1) * 8, cudaMemcpyDeviceToHost, st));
+            if (tot_hits) PGR_CUDA(cudaMemcpyAsync(r_hits, ap.hits_out, tot_hits * sizeof(pgr_hit_pair), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaStreamSynchronize(st));
+            n_targets = tot_targets; n_chains = tot_chains; n_hits_out = tot_hits;
+            // targets are sorted by query: q_target_off[q] = number of targets of queries < q
+            size_t ti = 0;
+            for (size_t q = 0; q < n_q; q++) {
+                q_target_off[q] = ti;
+                while (ti < tot_targets && tq[ti] == q) ti++;
+            }
+            q_target_off[n_q] = ti;
+            have_result = true;
         }
     }
     trace_mark("query_batch: host assembly");
-    // chain_hit_off was built with one leading 0 and one entry per chain end
+    if (!have_result) {
+        r_target_sid = (uint32_t *)result_alloc(4); r_target_chain_off = (uint64_t *)result_alloc(8); r_chain_score = (float *)result_alloc(4);
+        r_chain_hit_off = (uint64_t *)result_alloc(8); r_hits = (pgr_hit_pair *)result_alloc(sizeof(pgr_hit_pair));
+        r_target_chain_off[0] = 0; r_chain_hit_off[0] = 0;
+    }
     pgr_query_result *r = (pgr_query_result *)calloc(1, sizeof(pgr_query_result));
-    r->n_queries = n_q; r->n_targets = target_sid.size(); r->n_chains = chain_score.size(); r->n_hits = hits_out.size();
-    r->q_target_off = host_dup(q_target_off); r->target_sid = host_dup(target_sid); r->target_chain_off = host_dup(target_chain_off);
-    r->chain_score = host_dup(chain_score); r->chain_hit_off = host_dup(chain_hit_off); r->hits = host_dup(hits_out);
+    r->n_queries = n_q; r->n_targets = n_targets; r->n_chains = n_chains; r->n_hits = n_hits_out;
+    r->q_target_off = (uint64_t *)result_alloc((n_q + 1) * 8);
+    memcpy(r->q_target_off, q_target_off.data(), (n_q + 1) * 8);
+    r->target_sid = r_target_sid; r->target_chain_off = r_target_chain_off; r->chain_score = r_chain_score;
+    r->chain_hit_off = r_chain_hit_off; r->hits = r_hits;
     *out = r;
     return PGR_OK;
 }
@@ -345,7 +372,7 @@ int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *kee
     PGR_TRY(pgr_b200_index_finalize(idx));
     cudaStream_t st = idx->ctx->stream;
     const uint64_t n = idx->n_tuples;
-    *out = (pgr_adj_pair *)malloc(sizeof(pgr_adj_pair));
+    *out = (pgr_adj_pair *)result_alloc(sizeof(pgr_adj_pair));
     *n_out = 0;
     if (n < 2) return PGR_OK;  // seq_db.rs:889-891
     trace_mark("adj_list: begin (after finalize)");
@@ -380,8 +407,8 @@ int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *kee
                                        idx->scratch3.as<pgr_adj_pair>());
     idx->launches += 1;
     PGR_CUDA(cudaGetLastError());
-    free(*out);
-    *out = (pgr_adj_pair *)malloc(total * sizeof(pgr_adj_pair));
+    result_free(*out);
+    *out = (pgr_adj_pair *)result_alloc(total * sizeof(pgr_adj_pair));
     if (!*out) { set_error("out of host memory"); return PGR_E_ARG; }
     PGR_CUDA(cudaMemcpyAsync(*out, idx->scratch3.p, total * sizeof(pgr_adj_pair), cudaMemcpyDeviceToHost, st));
     PGR_CUDA(cudaStreamSynchronize(st));

@@ -286,6 +286,38 @@ __global__ void chain_kernel(const ChainParams p) {
     p.seg_n_chains[sgi] = n_ch;
 }
 
+// nested result arrays built on the device: one thread per segment copies its chains to their final places
+struct AssembleParams {
+    const HitRec *hits; const uint64_t *seg_off; const SortKey *seg_keys; uint64_t n_seg;
+    const uint32_t *out_idx; const uint8_t *out_start; const float *out_score;
+    const uint32_t *seg_n_out;
+    const uint64_t *hit_prefix, *chain_prefix, *target_prefix;     // exclusive scans over segments
+    uint32_t *target_sid, *target_qid; uint64_t *target_chain_off;
+    float *chain_score; uint64_t *chain_hit_off; pgr_hit_pair *hits_out;
+};
+__global__ void seg_has_kernel(const uint32_t *seg_n_out, uint64_t n_seg, uint32_t *has) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_seg) has[s] = seg_n_out[s] ? 1u : 0u;
+}
+__global__ void assemble_kernel(const AssembleParams p) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n_seg) return;
+    const uint32_t n_out = p.seg_n_out[s];
+    if (n_out == 0) return;
+    const uint64_t t = p.target_prefix[s], b = p.seg_off[s], hb = p.hit_prefix[s];
+    p.target_sid[t] = (uint32_t)p.seg_keys[s].k1;
+    p.target_qid[t] = (uint32_t)p.seg_keys[s].k0;
+    p.target_chain_off[t] = p.chain_prefix[s];
+    uint64_t c = p.chain_prefix[s];
+    for (uint32_t a = 0; a < n_out; a++) {
+        if (p.out_start[b + a]) { p.chain_score[c] = p.out_score[b + a]; p.chain_hit_off[c] = hb + a; c++; }
+        const HitRec h = p.hits[b + p.out_idx[b + a]];
+        pgr_hit_pair hp;
+        hp.qb = h.qb; hp.qe = h.qe; hp.tb = h.tb; hp.te = h.te; hp.qo = h.qo; hp.to = h.to; hp.pad_[0] = hp.pad_[1] = 0;
+        p.hits_out[hb + a] = hp;
+    }
+}
+
 // ---- frag_map_to_adj_list (seq_db.rs:876-944) --------------------------------------------------------------------------
 struct AdjRow { uint32_t sid, bgn, end, ori; uint64_t h0, h1; uint32_t ok, pad_; };   // 40 bytes
 static_assert(sizeof(AdjRow) == 40, "AdjRow layout");
