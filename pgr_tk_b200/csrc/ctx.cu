@@ -66,7 +66,7 @@ struct PoolEntry { void *p; size_t cap; bool in_use; };
 std::mutex g_pool_mu;
 std::vector<PoolEntry> g_pool;
 constexpr size_t POOL_MIN = 1u << 20;     // smaller results use malloc
-constexpr size_t POOL_MAX_FREE = 4;       // idle pinned buffers kept around
+constexpr size_t POOL_MAX_FREE = 16;      // idle pinned buffers kept around
 }  // namespace
 
 void *result_alloc(size_t bytes) {

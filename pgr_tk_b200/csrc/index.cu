@@ -135,6 +135,7 @@ int index_sort(pgr_b200_index *idx, uint64_t n, int first_pass, int last_pass) {
         PGR_CUDA(cudaStreamSynchronize(st));
         idx->launches += 3;
         if (*(uint32_t *)idx->ctx->h_ctl == 0) { std::swap(ka, kb); std::swap(ia, ib); }
+        trace_mark("index_sort: pass");
     }
     if (ka != idx->keysA.as<SortKey>()) { std::swap(idx->keysA, idx->keysB); std::swap(idx->idxA, idx->idxB); }
     return PGR_OK;
@@ -261,6 +262,7 @@ int pgr_b200_index_finalize(pgr_b200_index *idx) {
     }
     PGR_TRY(idx->keysA.ensure(n * sizeof(SortKey)));
     PGR_TRY(idx->idxA.ensure(n * sizeof(uint32_t)));
+    trace_mark("index_finalize: alloc");
     const uint32_t g = (uint32_t)ceil_div<uint64_t>(n, 256);
     tuple_keys_kernel<<<g, 256, 0, st>>>(idx->tuples.as<FragTuple>(), n, idx->keysA.as<SortKey>());
     iota_kernel<<<g, 256, 0, st>>>(idx->idxA.as<uint32_t>(), n);

@@ -10,7 +10,7 @@
 namespace pgr {
 
 constexpr int RS_NT = 256;            // threads per CTA (8 warps)
-constexpr int RS_SEG = 2048;          // elements per warp segment; a warp walks its segment in order, 32 at a time
+constexpr int RS_SEG = 8192;          // elements per warp segment; a warp walks its segment in order, 32 at a time
 constexpr int RS_WARPS = RS_NT / 32;
 
 // sort record: 128-bit key (k0 major, k1 minor) + index of the tuple in insertion order
