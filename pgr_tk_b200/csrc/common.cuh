@@ -40,6 +40,38 @@ __host__ __device__ __forceinline__ uint64_t u64hash(uint64_t key) {
 
 constexpr uint64_t HASH_XOR = 0xAD12CF59ull;  // shmmrutils.rs:491
 
+// Device variant on split 32-bit words (same arithmetic; 64-bit constant multiplies spelled as IMAD.WIDE + IMAD).
+#ifdef __CUDACC__
+template <int S>
+__device__ __forceinline__ void xorshift_r(uint32_t &lo, uint32_t &hi) {   // key ^= key >> S, 0 < S < 32
+    const uint32_t t_lo = __funnelshift_r(lo, hi, S);
+    const uint32_t t_hi = hi >> S;
+    lo ^= t_lo; hi ^= t_hi;
+}
+// (hi:lo) * C + A (mod 2^64) with a 32-bit constant C: one IMAD.WIDE for the low word product and one IMAD for the
+// high word (the compiler's generic 64-bit multiply spends three)
+template <uint32_t C>
+__device__ __forceinline__ void mul64c(uint32_t &lo, uint32_t &hi, uint64_t addend = 0) {
+    const uint64_t t = (uint64_t)lo * (uint64_t)C + addend;
+    hi = hi * C + (uint32_t)(t >> 32);
+    lo = (uint32_t)t;
+}
+__device__ __forceinline__ void u64hash_dev32(uint32_t &lo, uint32_t &hi) {
+    mul64c<0x1FFFFFu>(lo, hi, ~0ull);      // key * (2^21 - 1) - 1
+    xorshift_r<24>(lo, hi);
+    mul64c<265u>(lo, hi);
+    xorshift_r<14>(lo, hi);
+    mul64c<21u>(lo, hi);
+    xorshift_r<28>(lo, hi);
+    mul64c<0x80000001u>(lo, hi);
+}
+__device__ __forceinline__ uint64_t u64hash_dev(uint64_t key) {
+    uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+    u64hash_dev32(lo, hi);
+    return ((uint64_t)hi << 32) | lo;
+}
+#endif
+
 // device-side mirror of pgr_shmmr_spec plus derived constants
 struct SpecDev {
     uint32_t w, k, r, min_span, sketch;

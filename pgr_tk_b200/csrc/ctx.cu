@@ -356,12 +356,21 @@ int run_level(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, c
     return PGR_OK;
 }
 
-template <int W, int K>
-int launch_l0(const L0Params &p, int grid, cudaStream_t st) {
-    PGR_CUDA(cudaFuncSetAttribute(l0_kernel<W, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(L0Smem)));
-    l0_kernel<W, K><<<grid, L0_NT, sizeof(L0Smem), st>>>(p);
+template <int W, int K, int U>
+int launch_l0u(const L0Params &p, int grid, cudaStream_t st) {
+    PGR_CUDA(cudaFuncSetAttribute(l0_kernel<W, K, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(L0Smem)));
+    l0_kernel<W, K, U><<<grid, L0_NT, sizeof(L0Smem), st>>>(p);
     PGR_CUDA(cudaGetLastError());
     return PGR_OK;
+}
+template <int W, int K>
+int launch_l0(const L0Params &p, int grid, cudaStream_t st) {
+    // PGR_B200_L0_UNROLL selects the key-loop unroll factor of the specialised kernels (tuning aid)
+    static const int u = getenv("PGR_B200_L0_UNROLL") ? atoi(getenv("PGR_B200_L0_UNROLL")) : 8;
+    if (W == 80 && u == 4) return launch_l0u<W, K, 4>(p, grid, st);
+    if (W == 80 && u == 16) return launch_l0u<W, K, 16>(p, grid, st);
+    if (W == 80 && u == 32) return launch_l0u<W, K, 32>(p, grid, st);
+    return launch_l0u<W, K, 8>(p, grid, st);
 }
 
 template <int W, int K>

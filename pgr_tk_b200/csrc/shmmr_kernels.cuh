@@ -140,8 +140,15 @@ __device__ __noinline__ bool selected_exact(const L0Smem &s, int q, int pos, int
     return l + r + 1 >= w;
 }
 
+// cold path of the key loop: a pushed palindrome (not pushed by the reference); the neighbourhood is re-derived by
+// patch_replay_kernel
+__device__ __noinline__ void record_skip(uint32_t *n_skips, uint2 *skips, uint32_t cap, uint32_t seq_id, int pos, uint32_t *bad) {
+    const uint32_t slot = atomicAdd(n_skips, 1u);
+    if (slot < cap) skips[slot] = make_uint2(seq_id, (uint32_t)pos); else *bad = 1;
+}
+
 // Level-0 minimizers of one tile.  W, K > 0 are compile-time specialisations; 0 = read from params.
-template <int W, int K>
+template <int W, int K, int U = 8>
 __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     L0Smem &s = *reinterpret_cast<L0Smem *>(smem_raw);
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             const uint32_t q10 = fsr(s.R1[g], s.R1[g + 1], cb), q11 = fsr(s.R1[g + 1], s.R1[g + 2], cb),
                            q12 = fsr(s.R1[g + 2], s.R1[g + 3], cb);
             const int base = pidx(32 * kb);
-#pragma unroll 8
+#pragma unroll U
             for (int i = 0; i < 32; i++) {
                 const uint32_t sh = 31 - i;
                 const uint32_t f0lo = fsr(a0, a1, sh) & mlo, f0hi = fsr(a1, a2, sh) & mhi;
@@ -248,15 +255,11 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                 const bool rev = R0 < F0;                       // shmmrutils.rs:486 (plane 0 only)
                 if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
                     const int pos = blk_pos + i;
-                    if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) {
-                        // a palindrome is not pushed: the neighbourhood is re-derived by patch_replay_kernel
-                        const uint32_t slot = atomicAdd(p.n_skips, 1u);
-                        if (slot < p.skip_cap) p.skips[slot] = make_uint2(s.seq_id, (uint32_t)pos); else s.bad = 1;
-                    }
+                    if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) record_skip(p.n_skips, p.skips, p.skip_cap, s.seq_id, pos, &s.bad);
                 }
                 const uint64_t u = rev ? R0 : F0;
                 const uint64_t v = rev ? (((uint64_t)r1hi << 32) | r1lo) : (((uint64_t)f1hi << 32) | f1lo);
-                const uint64_t h = u64hash(u) ^ u64hash(v ^ HASH_XOR);
+                const uint64_t h = u64hash_dev(u) ^ u64hash_dev(v ^ HASH_XOR);
                 s.H[base + i] = (uint32_t)(h >> 24);
             }
         }
