@@ -146,6 +146,10 @@ __global__ void iota_kernel(uint32_t *p, uint64_t n) {
     if (i < n) p[i] = (uint32_t)i;
 }
 __global__ void set_u64_kernel(uint64_t *p, uint64_t v) { *p = v; }
+__global__ void add_frg_base_kernel(FragTuple *t, uint64_t n, uint32_t base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[i].frg_id += base;
+}
 
 // destination part of every tuple: number of splitters <= h0
 __global__ void dest_keys_kernel(const FragTuple *t, uint64_t n, const uint64_t *splitters, uint32_t n_split, SortKey *keys,
@@ -213,32 +217,36 @@ int pgr_b200_index_add_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids
     return rc;
 }
 
+// stage: the chunked, copy/compute-overlapped path of add_batch with fragment ids counted from 0; commit shifts the ids
+// of the staged tuples by the number of fragments that precede this batch globally (known only after the ranks have
+// exchanged their totals)
 int pgr_b200_index_stage_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
                                uint64_t *n_frags_in_batch) {
     if (!idx || (n && (!sids || !seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
-    pgr_b200_ctx *ctx = idx->ctx;
-    PGR_TRY(pgr_b200_ctx_upload(ctx, n, nullptr, seqs, lens));
-    size_t ns = 0;
-    PGR_TRY(pgr_b200_ctx_shmmrs(ctx, &idx->spec, 0, &ns));
-    idx->staged_sids.assign(sids, sids + n);
-    idx->staged_n_mm = ns;
-    std::vector<uint64_t> off(n + 1);
-    PGR_CUDA(cudaMemcpyAsync(off.data(), ctx->d_result_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    PGR_CUDA(cudaStreamSynchronize(ctx->stream));
-    uint64_t frags = 0;
-    for (size_t i = 0; i < n; i++) { const uint64_t k = off[i + 1] - off[i]; frags += k ? k + 1 : 2; }
-    if (n_frags_in_batch) *n_frags_in_batch = (idx->mode == 0) ? frags : 0;
+    if (idx->staged) { set_error("a staged batch is pending: call pgr_b200_index_commit_batch first"); return PGR_E_ARG; }
+    idx->finalized = false;
+    idx->staged_prev_frags = idx->n_frags;
+    idx->staged_t0 = idx->n_tuples;
+    idx->n_frags = 0;
+    const int rc = index_batch_tuples(idx, n, sids, seqs, lens, false, nullptr, nullptr, nullptr);
+    if (rc != PGR_OK) { idx->n_frags = idx->staged_prev_frags; return rc; }
+    idx->staged_frags = idx->n_frags;
+    if (n_frags_in_batch) *n_frags_in_batch = (idx->mode == 0) ? idx->staged_frags : 0;
     idx->staged = true;
     return PGR_OK;
 }
 
 int pgr_b200_index_commit_batch(pgr_b200_index *idx, uint32_t frag_base) {
     if (!idx || !idx->staged) { set_error("no staged batch"); return PGR_E_ARG; }
-    idx->n_frags = frag_base;
-    idx->finalized = false;
-    uint64_t np = 0;
-    idx->ctx->r0 = 0; idx->ctx->rn = idx->ctx->n_seq;
-    PGR_TRY(emit_tuples(idx, idx->staged_sids.data(), idx->staged_sids.size(), idx->staged_n_mm, false, nullptr, &np));
+    PGR_CUDA(cudaSetDevice(idx->ctx->device));
+    const uint64_t nt = idx->n_tuples - idx->staged_t0;
+    if (idx->mode == 0 && frag_base && nt) {
+        add_frg_base_kernel<<<(uint32_t)ceil_div<uint64_t>(nt, 256), 256, 0, idx->ctx->stream>>>(idx->tuples.as<FragTuple>() + idx->staged_t0, nt, frag_base);
+        idx->launches += 1;
+        PGR_CUDA(cudaGetLastError());
+        PGR_CUDA(cudaStreamSynchronize(idx->ctx->stream));
+    }
+    idx->n_frags = (idx->mode == 0) ? frag_base + idx->staged_frags : 0;
     idx->staged = false;
     return PGR_OK;
 }

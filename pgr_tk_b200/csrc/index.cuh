@@ -19,8 +19,8 @@ struct pgr_b200_index {
     bool finalized = false;
     // staged batch (multi-GPU build: shimmers first, fragment-id base later)
     bool staged = false;
-    std::vector<uint32_t> staged_sids;
-    size_t staged_n_mm = 0;
+    uint64_t staged_t0 = 0;           // first tuple of the staged batch
+    uint32_t staged_frags = 0, staged_prev_frags = 0;
     // scratch
     pgr::DevBuf keysA, keysB, idxA, idxB, hist, head, block_sum, block_prefix, d_sid, d_pair_off, d_frg_base;
     pgr::DevBuf qtuples, q_hit_begin, q_hit_count, scratch0, scratch1, scratch2, scratch3;
