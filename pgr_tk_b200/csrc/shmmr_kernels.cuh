@@ -18,7 +18,7 @@ constexpr int L0_NT = 128;                 // threads per CTA; thread t owns the
 constexpr int L0_CTX = 2;                  // leading context-only blocks (a 56-mer reaches 55 bases back)
 constexpr int L0_KB = L0_NT - L0_CTX;      // blocks that get keys
 constexpr int L0_KPOS = L0_KB * 32;        // key positions per tile
-constexpr int L0_PADB = 6;                 // spare blocks on both sides of the smem arrays (van Herk neighbours)
+constexpr int L0_PADB = 4;                 // spare blocks on both sides of the smem arrays (van Herk neighbours, w <= 128)
 constexpr int L0_ARR = (L0_KB + 2 * L0_PADB) * 33;  // padded u32 array length
 constexpr int L0_MIN_CTAS = 5;             // resident CTAs per SM the kernel is compiled for
 constexpr int L0_LISTCAP = L0_ARR * 2;     // u16 entries that fit in the P array
@@ -80,20 +80,28 @@ struct L0Smem {
     uint32_t H[L0_ARR];      // bits 24..55 of the k-mer hash = the high word of MM128.x; padded index q + q/32 + PADB*33
     uint32_t P[L0_ARR];      // van Herk exchange: prefix minima (pass 1) then suffix maxima (pass 2); afterwards it
                              // holds `list`: ordered key indices (u16) of the selected positions + tail replay entries
-    uint32_t F0[L0_NT + 8], F1[L0_NT + 8], R0[L0_NT + 8], R1[L0_NT + 8];  // bit planes per 32-base block
+    uint32_t F0[L0_NT + 8], F1[L0_NT + 8];   // bit planes per 32-base block, first base in the MOST significant bit;
+                                             // the complement planes (first base in the LEAST significant bit) are ~brev()
     uint32_t bext[L0_KB + 2 * L0_PADB];   // block min (pass 1) / block max (pass 2)
     uint32_t wsum[L0_NT / 32];
-    uint32_t n_list, n_tail, any_reject;
-    // tile descriptor
-    uint32_t seq_id, seq_len;
-    int32_t keys_start;      // sequence position of key index 0 (multiple of 32, may be negative)
-    int32_t out_lo, out_hi;  // output position range [out_lo, out_hi)
-    uint32_t is_last;
-    uint32_t bad;            // tile saw an invalid byte or a palindrome
-    uint64_t seq_off;
+    uint32_t n_list;
+    // tile descriptors, double-buffered: thread 0 prepares tile t+1 while the CTA works on tile t, and every thread
+    // issues its 32-byte load for tile t+1 before the key loop of tile t (software prefetch across tiles)
+    struct TileDesc {
+        uint32_t seq_id, seq_len;
+        int32_t keys_start;      // sequence position of key index 0 (multiple of 32, may be negative)
+        int32_t out_lo, out_hi;  // output position range [out_lo, out_hi)
+        uint32_t is_last;
+        uint32_t bad;            // tile saw an invalid byte (or lost a palindrome record)
+        uint32_t n_tail, any_reject, pad_;
+        uint64_t seq_off;
+    } td[2];
 };
 
 __device__ __forceinline__ int pidx(int q) { return q + (q >> 5) + L0_PADB * 33; }  // q may be negative (>= -PADB*32)
+
+// complement plane word of block j (blocks past the tile read as 0, like the reference's empty registers)
+__device__ __forceinline__ uint32_t rplane(const uint32_t *F, int j) { return j < L0_NT ? ~__brev(F[j]) : 0u; }
 
 // k-mer registers of key index q rebuilt from the plane words (same arithmetic as the key loop)
 struct KmerRegs { uint64_t f0, f1, r0, r1; };
@@ -106,8 +114,10 @@ __device__ __forceinline__ KmerRegs kmer_at(const L0Smem &s, int q, uint32_t k) 
     KmerRegs r;
     r.f0 = (((uint64_t)fsr(s.F0[t - 1], s.F0[t - 2], sh) << 32) | fsr(s.F0[t], s.F0[t - 1], sh)) & kmask;
     r.f1 = (((uint64_t)fsr(s.F1[t - 1], s.F1[t - 2], sh) << 32) | fsr(s.F1[t], s.F1[t - 1], sh)) & kmask;
-    const uint32_t q00 = fsr(s.R0[g], s.R0[g + 1], cb), q01 = fsr(s.R0[g + 1], s.R0[g + 2], cb), q02 = fsr(s.R0[g + 2], s.R0[g + 3], cb);
-    const uint32_t q10 = fsr(s.R1[g], s.R1[g + 1], cb), q11 = fsr(s.R1[g + 1], s.R1[g + 2], cb), q12 = fsr(s.R1[g + 2], s.R1[g + 3], cb);
+    const uint32_t ra0 = rplane(s.F0, g), ra1 = rplane(s.F0, g + 1), ra2 = rplane(s.F0, g + 2), ra3 = rplane(s.F0, g + 3);
+    const uint32_t rb0 = rplane(s.F1, g), rb1 = rplane(s.F1, g + 1), rb2 = rplane(s.F1, g + 2), rb3 = rplane(s.F1, g + 3);
+    const uint32_t q00 = fsr(ra0, ra1, cb), q01 = fsr(ra1, ra2, cb), q02 = fsr(ra2, ra3, cb);
+    const uint32_t q10 = fsr(rb0, rb1, cb), q11 = fsr(rb1, rb2, cb), q12 = fsr(rb2, rb3, cb);
     r.r0 = (((uint64_t)fsr(q01, q02, i) << 32) | fsr(q00, q01, i)) & kmask;
     r.r1 = (((uint64_t)fsr(q11, q12, i) << 32) | fsr(q10, q11, i)) & kmask;
     return r;
@@ -140,6 +150,31 @@ __device__ __noinline__ bool selected_exact(const L0Smem &s, int q, int pos, int
     return l + r + 1 >= w;
 }
 
+// tile -> descriptor (executed by one thread)
+__device__ __forceinline__ void make_tile_desc(const L0Params &p, uint32_t tile, uint32_t w, L0Smem::TileDesc &d) {
+    // (sequence, tile index): largest sid with tile_prefix[sid] <= tile
+    uint32_t lo = 0, hi = p.n_seq;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+    }
+    const uint32_t sid = lo, j = tile - p.tile_prefix[sid];
+    const uint32_t L = p.len[sid];
+    const uint32_t nt = p.tile_prefix[sid + 1] - p.tile_prefix[sid];
+    int32_t ks = (int32_t)(j * p.tile_stride) - (int32_t)p.halo;
+    const bool last = (j + 1 == nt);
+    if (last) {  // the tail replay needs keys and selections back to E - 2w: pull the tile back if it is short
+        const int32_t need = ((int32_t)L - 3 * (int32_t)w - 32) & ~31;
+        if (need < ks) ks = need;
+        if (ks < -(int32_t)p.halo) ks = -(int32_t)p.halo;
+    }
+    d.seq_id = sid; d.seq_len = L; d.keys_start = ks; d.is_last = last ? 1u : 0u;
+    d.out_lo = (int32_t)(j * p.tile_stride);
+    d.out_hi = (int32_t)min((uint64_t)L, (uint64_t)(j + 1) * p.tile_stride);
+    d.seq_off = p.off[sid];
+    d.bad = 0; d.n_tail = 0; d.any_reject = 0;
+}
+
 // cold path of the key loop: a pushed palindrome (not pushed by the reference); the neighbourhood is re-derived by
 // patch_replay_kernel
 __device__ __noinline__ void record_skip(uint32_t *n_skips, uint2 *skips, uint32_t cap, uint32_t seq_id, int pos, uint32_t *bad) {
@@ -168,43 +203,30 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
     for (int i = tid; i < L0_KB + 2 * L0_PADB; i += L0_NT) s.bext[i] = 0;
     for (int i = tid; i < L0_ARR; i += L0_NT) { s.H[i] = 0; s.P[i] = 0; }
 
-    for (uint32_t tile = t_begin; tile < t_end; ++tile) {
-        __syncthreads();  // previous tile fully consumed
-        if (tid == 0) {
-            // tile -> (sequence, tile index): largest sid with tile_prefix[sid] <= tile
-            uint32_t lo = 0, hi = p.n_seq;
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (p.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
-            }
-            const uint32_t sid = lo, j = tile - p.tile_prefix[sid];
-            const uint32_t L = p.len[sid];
-            const uint32_t nt = p.tile_prefix[sid + 1] - p.tile_prefix[sid];
-            int32_t ks = (int32_t)(j * p.tile_stride) - (int32_t)p.halo;
-            const bool last = (j + 1 == nt);
-            if (last) {  // the tail replay needs keys and selections back to E - 2w: pull the tile back if it is short
-                const int32_t need = ((int32_t)L - 3 * (int32_t)w - 32) & ~31;
-                if (need < ks) ks = need;
-                if (ks < -(int32_t)p.halo) ks = -(int32_t)p.halo;
-            }
-            s.seq_id = sid; s.seq_len = L; s.keys_start = ks; s.is_last = last ? 1u : 0u;
-            s.out_lo = (int32_t)(j * p.tile_stride);
-            s.out_hi = (int32_t)min((uint64_t)L, (uint64_t)(j + 1) * p.tile_stride);
-            s.seq_off = p.off[sid];
-            s.bad = 0; s.n_tail = 0; s.any_reject = 0;
+    // first tile: descriptor + this thread's 32 bases
+    if (tid == 0 && t_begin < t_end) make_tile_desc(p, t_begin, w, s.td[0]);
+    __syncthreads();
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+    if (t_begin < t_end) {
+        const int32_t bp = s.td[0].keys_start + 32 * (tid - L0_CTX);
+        if (bp + 32 > 0 && bp < (int32_t)s.td[0].seq_len) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.seq + s.td[0].seq_off + bp);
+            v0 = __ldg(src); v1 = __ldg(src + 1);
         }
-        __syncthreads();
-        const int32_t L = (int32_t)s.seq_len;
-        const int32_t keys_start = s.keys_start;
+    }
+    int cur = 0;
+    for (uint32_t tile = t_begin; tile < t_end; ++tile, cur ^= 1) {
+        L0Smem::TileDesc &D = s.td[cur];
+        const bool has_next = tile + 1 < t_end;
+        if (tid == 0 && has_next) make_tile_desc(p, tile + 1, w, s.td[cur ^ 1]);   // overlaps with phases 1-2 of this tile
+        const int32_t L = (int32_t)D.seq_len;
+        const int32_t keys_start = D.keys_start;
         const int32_t blk_pos = keys_start + 32 * (tid - L0_CTX);  // sequence position of this thread's first base
-        const uint8_t *gseq = p.seq + s.seq_off;
 
         // ---- phase 1: 32 bases -> plane words -------------------------------------------------------------
         uint32_t f0 = 0, f1 = 0;
         const bool blk_live = (blk_pos + 32 > 0) && (blk_pos < L);  // block intersects the sequence
         if (blk_live) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(gseq + blk_pos);
-            const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
             const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             bool ok = true;
 #pragma unroll
@@ -216,20 +238,28 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                 ok = ok && word_is_acgt(wd[j]);
             }
             if (!ok || blk_pos < 0 || blk_pos + 32 > L) {
-                // slow exact check restricted to the bytes that belong to the sequence
-                bool bad = false;
+                // slow exact check restricted to the bytes that belong to the sequence; the first byte outside ACGTacgt
+                // seeds an exact local replay (patch_replay_kernel), like a palindrome does
+                int first_bad = -1;
 #pragma unroll 1
                 for (int j = 0; j < 32; j++) {
                     const int pos = blk_pos + j;
-                    if (pos >= 0 && pos < L) bad = bad || !byte_is_acgt((wd[j >> 2] >> (8 * (j & 3))) & 0xFF);
+                    if (first_bad < 0 && pos >= 0 && pos < L && !byte_is_acgt((wd[j >> 2] >> (8 * (j & 3))) & 0xFF)) first_bad = pos;
                 }
-                if (bad) s.bad = 1;
+                if (first_bad >= 0) record_skip(p.n_skips, p.skips, p.skip_cap, D.seq_id, first_bad, &D.bad);
             }
         }
         s.F0[tid] = f0; s.F1[tid] = f1;
-        s.R0[tid] = ~__brev(f0); s.R1[tid] = ~__brev(f1);   // complement planes, first base in the LEAST significant bit
-        if (tid < 8) { s.F0[L0_NT + tid] = 0; s.F1[L0_NT + tid] = 0; s.R0[L0_NT + tid] = 0; s.R1[L0_NT + tid] = 0; }
-        __syncthreads();
+        if (tid < 8) { s.F0[L0_NT + tid] = 0; s.F1[L0_NT + tid] = 0; }
+        __syncthreads();   // planes visible; also publishes thread 0's descriptor of the next tile
+        if (has_next) {    // the loads fly while the key loop runs
+            const L0Smem::TileDesc &N = s.td[cur ^ 1];
+            const int32_t bp = N.keys_start + 32 * (tid - L0_CTX);
+            if (bp + 32 > 0 && bp < (int32_t)N.seq_len) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.seq + N.seq_off + bp);
+                v0 = __ldg(src); v1 = __ldg(src + 1);
+            }
+        }
 
         // ---- phase 2: keys for blocks CTX.. ------------------------------------------------------------------
         const int kb = tid - L0_CTX;  // key block index (negative for the two context threads)
@@ -239,10 +269,10 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             // r-planes: Q = G >> (32*(tid-2) + 65 - k), so that rmmer(i) = (Q >> i) & kmask
             const uint32_t cp = 65u - k, cs = cp >> 5, cb = cp & 31;
             const int g = tid - 2 + (int)cs;
-            const uint32_t q00 = fsr(s.R0[g], s.R0[g + 1], cb), q01 = fsr(s.R0[g + 1], s.R0[g + 2], cb),
-                           q02 = fsr(s.R0[g + 2], s.R0[g + 3], cb);
-            const uint32_t q10 = fsr(s.R1[g], s.R1[g + 1], cb), q11 = fsr(s.R1[g + 1], s.R1[g + 2], cb),
-                           q12 = fsr(s.R1[g + 2], s.R1[g + 3], cb);
+            const uint32_t ra0 = rplane(s.F0, g), ra1 = rplane(s.F0, g + 1), ra2 = rplane(s.F0, g + 2), ra3 = rplane(s.F0, g + 3);
+            const uint32_t rb0 = rplane(s.F1, g), rb1 = rplane(s.F1, g + 1), rb2 = rplane(s.F1, g + 2), rb3 = rplane(s.F1, g + 3);
+            const uint32_t q00 = fsr(ra0, ra1, cb), q01 = fsr(ra1, ra2, cb), q02 = fsr(ra2, ra3, cb);
+            const uint32_t q10 = fsr(rb0, rb1, cb), q11 = fsr(rb1, rb2, cb), q12 = fsr(rb2, rb3, cb);
             const int base = pidx(32 * kb);
 #pragma unroll U
             for (int i = 0; i < 32; i++) {
@@ -255,7 +285,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                 const bool rev = R0 < F0;                       // shmmrutils.rs:486 (plane 0 only)
                 if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
                     const int pos = blk_pos + i;
-                    if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) record_skip(p.n_skips, p.skips, p.skip_cap, s.seq_id, pos, &s.bad);
+                    if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) record_skip(p.n_skips, p.skips, p.skip_cap, D.seq_id, pos, &D.bad);
                 }
                 const uint64_t u = rev ? R0 : F0;
                 const uint64_t v = rev ? (((uint64_t)r1hi << 32) | r1lo) : (((uint64_t)f1hi << 32) | f1lo);
@@ -279,8 +309,8 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                 const int lo = max(a_lo - blk_pos, 0), hi = min(a_hi - blk_pos, 31);
                 if (lo <= hi) amask = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
                 // positions that lie in some valid window and in this tile's output range
-                const int plo = max(max(a_lo, s.out_lo) - blk_pos, 0);
-                const int phi = min(min(a_hi + (int)w - 1, s.out_hi - 1) - blk_pos, 31);
+                const int plo = max(max(a_lo, D.out_lo) - blk_pos, 0);
+                const int phi = min(min(a_hi + (int)w - 1, D.out_hi - 1) - blk_pos, 31);
                 if (plo <= phi) pmask = (0xFFFFFFFFu >> (31 - phi)) & (0xFFFFFFFFu << plo);
             }
             if (tid < L0_CTX) pmask = 0;
@@ -318,7 +348,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                     s.bext[kb + L0_PADB] = run;
                 }
                 __syncthreads();
-                {
+                if (tid >= L0_CTX) {   // the two context threads have no blocks to their left inside the arrays
                     uint32_t mid1 = 0;
                     for (int b = 1; b < d; b++) mid1 = max(mid1, s.bext[kb + L0_PADB - b]);
                     const uint32_t mid2 = max(mid1, s.bext[kb + L0_PADB - d]);
@@ -381,11 +411,11 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             bool tie = false;
             for (int jj = (int)j - 1; jj >= 0 && q - (int)list[jj] < (int)w && !tie; jj--) tie = (s.H[pidx(list[jj])] == hq);
             for (uint32_t jj = j + 1; jj < total && (int)list[jj] - q < (int)w && !tie; jj++) tie = (s.H[pidx(list[jj])] == hq);
-            if (tie && !selected_exact(s, q, q + keys_start, (int)w, a_lo, a_hi, k)) s.any_reject = 1u + j;  // any value != 0
+            if (tie && !selected_exact(s, q, q + keys_start, (int)w, a_lo, a_hi, k)) D.any_reject = 1u + j;  // any value != 0
         }
         __syncthreads();
         uint32_t n_list = total;
-        if (s.any_reject) {   // rare: re-evaluate every candidate exactly and rebuild the list (single thread)
+        if (D.any_reject) {   // rare: re-evaluate every candidate exactly and rebuild the list (single thread)
             if (tid == 0) {
                 uint32_t o = 0;
                 for (uint32_t j = 0; j < total; j++) {
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         }
 
         // ---- phase 6: tail replay (last tile of the sequence; shmmrutils.rs:503-515 with rule (2) disabled) ---
-        if (s.is_last && (int32_t)w > (int32_t)k && L > (int32_t)k) {
+        if (D.is_last && (int32_t)w > (int32_t)k && L > (int32_t)k) {
             if (tid == 0) {
                 // q = last selected position below Eb (selections of the whole sequence, not only this tile's range)
                 const int32_t t_lo = max(Eb, (int32_t)k);
@@ -424,11 +454,11 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                         }
                     }
                 }
-                s.n_tail = n;
+                D.n_tail = n;
             }
             __syncthreads();
         }
-        const uint32_t n_tail = s.n_tail;
+        const uint32_t n_tail = D.n_tail;
         const uint32_t n_all = n_list + n_tail;
 
         // ---- phase 7: rebuild the full MM128 of every selected position and write it (coalesced) -------------
@@ -440,14 +470,15 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             const uint64_t h = hash_at(s, q, k, strand);
             pgr_mm128 mm;
             mm.x = (h << 8) | k;
-            mm.y = ((uint64_t)s.seq_id << 32) | ((uint64_t)(uint32_t)(q + keys_start) << 1) | strand;
+            mm.y = ((uint64_t)D.seq_id << 32) | ((uint64_t)(uint32_t)(q + keys_start) << 1) | strand;
             chunk[dst] = mm;
         }
         if (tid == 0) {
-            atomicAdd(&p.seq_count[s.seq_id], n_all);
-            if (s.bad || n_all > (uint32_t)L0_LISTCAP) atomicOr(&p.seq_flag[s.seq_id], 1u);
+            atomicAdd(&p.seq_count[D.seq_id], n_all);
+            if (D.bad || n_all > (uint32_t)L0_LISTCAP) atomicOr(&p.seq_flag[D.seq_id], 1u);
         }
         running += n_all;
+        __syncthreads();  // tile fully consumed before its smem is reused
     }
     if (tid == 0) p.chunk_count[blockIdx.x] = running;
 }
@@ -587,16 +618,26 @@ __global__ void patch_replay_kernel(const PatchParams p) {
         bool from_start = false;
         if (S < k + w + 1) { S = k; from_start = true; }
         const int64_t T0 = from_start ? k : S + w;
-        // registers: roll over the k bases before S (positions S-k .. S-1); from the true start they begin at zero
+        // registers at S: the last k VALID bases before S (shmmrutils.rs:461-476 updates them on valid bases only);
+        // from the true start they begin at zero.  `since_bad` counts the bytes since the last one outside ACGTacgt:
+        // the tile kernel's key at p is the true key iff the k bytes ending at p are all ACGTacgt.
         uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;
-        const int64_t r_begin = from_start ? 0 : S - k;
+        int64_t r_begin = 0;
+        if (!from_start) {
+            int64_t b = S; int64_t got = 0;
+            while (b > 0 && got < k) { b--; if (base_code(sq[b]) < 4) got++; }
+            r_begin = b;
+        }
+        int64_t since_bad = 1 << 30;
         for (int64_t q = r_begin; q < S; q++) {
-            const uint32_t c = base_code(sq[q]);
+            const uint32_t ch = sq[q];
+            const uint32_t c = base_code(ch);
             if (c < 4) {
                 f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
                 const uint64_t rc = 3 ^ c;
                 r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
             }
+            since_bad = byte_is_acgt(ch) ? since_bad + 1 : 0;
         }
         for (int64_t i = 0; i < w; i++) { rx[i] = ~0ull; ry[i] = ~0u; }
         uint32_t r_start = 0, r_end = 0, r_len = 0;
@@ -607,12 +648,15 @@ __global__ void patch_replay_kernel(const PatchParams p) {
         bool done = false;
         pgr_mm128 *dst = MODE ? p.entries + p.entry_off[slot0 + n_patch] : nullptr;
         for (int64_t pos = S; pos < L && !done; pos++) {
-            const uint32_t c = base_code(sq[pos]);
+            const uint32_t ch = sq[pos];
+            const uint32_t c = base_code(ch);
             if (c < 4) {
                 f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
                 const uint64_t rc = 3 ^ c;
                 r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
             }
+            since_bad = byte_is_acgt(ch) ? since_bad + 1 : 0;
+            if (since_bad < k) p_last = pos;              // the tile kernel's key here is not the reference's
             if (f0 == r0 && f1 == r1) { if (pos >= k) p_last = pos; continue; }
             if (pos < k) continue;
             const bool rev = r0 < f0;
@@ -660,8 +704,13 @@ __global__ void patch_replay_kernel(const PatchParams p) {
             if (emitted && pos >= T0) {
                 // every skip up to pos has been seen by the machine; find the next one in the list
                 while (si < ns && (int64_t)sk[si] <= pos) si++;
-                const bool next_far = (si >= ns) || ((int64_t)sk[si] > pos + w);
-                if (pos >= p_last + 2 * w && pos < E - w && next_far) { q1 = last_emit; done = true; }
+                bool next_far = (si >= ns) || ((int64_t)sk[si] > pos + w);
+                if (next_far && pos >= p_last + 2 * w && pos < E - w) {
+                    // invalid bytes are recorded once per 32-base block: make sure none hides just ahead
+                    const int64_t ahead = min(L, pos + w + 33);
+                    for (int64_t q = pos + 1; q < ahead && next_far; q++) next_far = byte_is_acgt(sq[q]);
+                    if (next_far) { q1 = last_emit; done = true; }
+                }
             }
         }
         if (!done) si = ns;  // ran to the end of the sequence: everything after q0 is replaced

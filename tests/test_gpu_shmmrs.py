@@ -115,8 +115,35 @@ def test_invalid_bytes_and_palindromes_take_replay_path():
     ctx.upload(seqs)
     ctx.shmmrs(pg.ShmmrSpec())
     c = ctx.counters()
-    assert c[2] == 3   # invalid bytes: whole-sequence replay (s1, s3, s4); the clean sequence is not replayed
-    assert c[4] >= 1   # the (AT)n palindromes of s2 are handled by a local patch
+    assert c[2] == 0   # nothing needs the whole-sequence replay any more
+    assert c[4] >= 4   # invalid bytes and the (AT)n palindromes are handled by local patches
+    ctx.close()
+
+
+def test_invalid_byte_patches():
+    """bytes outside ACGTacgt do not update the k-mer registers but the stale k-mer is still pushed (shmmrutils.rs:461-476)"""
+    rng = np.random.default_rng(107)
+    r = lambda L, a=b"ACGT": rand_seq(rng, L, a)
+    seqs = [
+        r(30000) + b"N" * 5000 + r(30000),                 # one long N run
+        b"N" * 300 + r(9000) + b"N" * 200,                 # at both ends
+        b"N" * 4000,                                       # nothing valid at all
+        b"NNNN" + r(40) + b"N" + r(30) + b"NN" + r(5000),  # fewer than k valid bases before position k
+        r(8000) + b"n" + r(8000) + b"-" + r(31) + b"R" + r(8000),          # isolated single bytes
+        bytes([0, 1, 2, 3]) * 1500 + r(3000),              # raw codes 0..3 are valid for the reference's LUT
+        r(20000, b"ACGTacgtN"),                            # dense N (every ~9th byte)
+        r(20000, b"ACGT" * 30 + b"N"),                     # sparse N (every ~120th byte)
+        b"AT" * 200 + b"N" * 10 + b"AT" * 200 + r(4000),   # palindromes next to N
+        r(50000),                                          # clean
+    ]
+    for w, k, r_, ms in [(80, 56, 4, 64), (48, 56, 4, 12), (24, 24, 12, 24), (8, 12, 2, 0), (128, 31, 3, 7), (5, 7, 1, 0)]:
+        for padding in (False, True):
+            assert_batch_equal(seqs, pg.ShmmrSpec(w, k, r_, ms), padding=padding)
+    ctx = pg.Ctx(0)
+    ctx.upload(seqs)
+    ctx.shmmrs(pg.ShmmrSpec())
+    c = ctx.counters()
+    assert c[2] == 0 and c[4] >= 8
     ctx.close()
 
 
