@@ -1,0 +1,26 @@
+"""small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel family once, tiny inputs"""
+import os, sys
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, 'tests'))
+import numpy as np
+import pgr_tk_b200 as pg
+rng = np.random.default_rng(3)
+acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+def r(L): return acgt[rng.integers(0, 4, size=L)].tobytes()
+u = r(3000)
+seqs = [r(30000), r(9000) + b"N" * 50 + r(9000), r(5000) + b"AT" * 100 + r(5000), r(100), b"", r(12000)]
+for spec in (pg.ShmmrSpec(80, 56, 4, 64), pg.ShmmrSpec(24, 24, 12, 24), pg.ShmmrSpec(128, 31, 2, 0), pg.ShmmrSpec(80, 56, 4, 64, True)):
+    mm, off = pg.get_shmmrs_from_seqs(list(range(len(seqs))), seqs, spec)
+    print("shimmers", len(mm))
+idx = pg.ShmmrIndex(pg.ShmmrSpec(48, 56, 4, 12), 0)
+base = r(40000)
+haps = []
+for h in range(5):
+    s = bytearray(base)
+    for p in np.nonzero(rng.random(len(s)) < 0.003)[0]: s[p] = b"ACGT"[rng.integers(0, 4)]
+    haps.append(bytes(s))
+idx.add_batch(list(range(5)), haps)
+print("index", idx.counts())
+res = idx.query_batch([haps[1][2000:22000], haps[3][10000:30000], b"ACGT"], 0.025, max_count=128, max_count_query=128, max_count_target=128, max_aln_span=8)
+print("query", [len(x) for x in res])
+print("adj", len(idx.adj_list(0)), len(idx.adj_list(2, [1])))
+print("partition", idx.partition([1 << 40, 1 << 44]))
