@@ -71,7 +71,7 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
@@ -83,9 +83,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
 
     def stop(self):
+        t_end = time.time()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,7 +99,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t_begin = getattr(self, "t_begin", 0.0)
+        # the sampler is started before the warm-up so that it is already streaming; keep the samples that arrived during
+        # the timed region (plus one polling interval of slack)
+        for ts, ln in self.lines:
+            if ts < t_begin or ts > t_end + 0.05:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -197,11 +206,12 @@ def main():
 
     # ---- device-resident timing ---------------------------------------------------------------------------------
     n_shmmrs = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         n_shmmrs = ctx.shmmrs(spec)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0_ms, stage_ms, launches = [], {}, 0
     ev0.record(stream)

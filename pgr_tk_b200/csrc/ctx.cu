@@ -903,8 +903,9 @@ int pgr::run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const ui
     PGR_TRY(upload_layout(ctx, n, rids, seqs, lens));
     trace_mark("run_chunked: layout");
     ctx->timer.reset();
-    // chunk boundaries: about 1/16 of the batch each, at least 64 MB, whole sequences
-    const uint64_t chunk_bytes = std::max<uint64_t>(64ull << 20, ctx->total_bases / 16);
+    // chunk boundaries: about 1/8 of the batch each, at least 192 MB (every chunk costs ~1.5 ms of launches and control
+    // read-backs), whole sequences
+    const uint64_t chunk_bytes = std::max<uint64_t>(192ull << 20, ctx->total_bases / 8);
     std::vector<size_t> cut(1, 0);
     {
         uint64_t acc = 0;
