@@ -151,12 +151,20 @@ pgr_b200_ctx *pgr_b200_ctx_new(int device) {
     if (n <= 0) { set_error("no CUDA device available: libpgr_b200 has no CPU fallback"); return nullptr; }
     if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return nullptr; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return nullptr; }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return nullptr; }
-    if (prop.major < 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return nullptr; }
+    int cc_major = 0, n_sm = 0;
+    if (cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { set_error("cudaDeviceGetAttribute failed"); return nullptr; }
+    if (cc_major < 10) { set_error("device %d is sm_%dx; this library is built for sm_100a only", device, cc_major); return nullptr; }
+    {   // keep freed device memory in the pool (see DevBuf)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     pgr_b200_ctx *ctx = new pgr_b200_ctx();
     ctx->device = device;
-    ctx->n_sm = prop.multiProcessorCount;
+    ctx->n_sm = n_sm;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete ctx; return nullptr; }
     ctx->stream = ctx->own_stream;
     return ctx;
@@ -558,6 +566,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     PGR_TRY(ctx->seq_flag.ensure(n * sizeof(uint32_t)));
     PGR_TRY(ctx->skips.ensure((size_t)SKIP_CAP * sizeof(uint2)));
     PGR_TRY(ctx->n_skips.ensure(64));
+    trace_mark("run_l0: partition + buffers");
     PGR_CUDA(cudaMemcpyAsync(ctx->tile_prefix.p, tile_prefix.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     PGR_CUDA(cudaMemcpyAsync(ctx->cta_tile.p, cta_tile.data(), (G + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     // arena: expected density 2/(w+1) with 2x headroom; exact retry on overflow
@@ -582,12 +591,14 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         p.chunk_count = ctx->chunk_count.as<uint64_t>(); p.seq_count = ctx->seq_count.as<uint32_t>();
         p.seq_flag = ctx->seq_flag.as<uint32_t>();
         p.skips = ctx->skips.as<uint2>(); p.n_skips = ctx->n_skips.as<uint32_t>(); p.skip_cap = SKIP_CAP;
+        trace_mark("run_l0: arena + memsets");
         const int slot = ctx->timer.begin("l0_minimizers", st);
         if (variant == 1) PGR_TRY((launch_l0<80, 56>(p, (int)G, st)));
         else if (variant == 2) PGR_TRY((launch_l0<48, 56>(p, (int)G, st)));
         else PGR_TRY((launch_l0<0, 0>(p, (int)G, st)));
         ctx->timer.end(slot, st);
         ctx->counters[0] += 1;
+        trace_mark("run_l0: kernel");
         PGR_CUDA(cudaMemcpyAsync(h_chunk, ctx->chunk_count.p, G * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         PGR_CUDA(cudaMemcpyAsync(h_count, ctx->seq_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         PGR_CUDA(cudaMemcpyAsync(h_flag, ctx->seq_flag.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

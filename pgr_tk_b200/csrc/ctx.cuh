@@ -7,20 +7,27 @@
 
 namespace pgr {
 
-// grow-only device buffer
+// grow-only device buffer, backed by the device's stream-ordered memory pool (cudaMallocAsync): the pool keeps freed
+// blocks (release threshold = unlimited, set in pgr_b200_ctx_new), so contexts and indexes that come and go in one
+// process do not pay cudaMalloc/cudaFree again
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return PGR_OK;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        release();
         size_t want = bytes + bytes / 8 + 256;
-        PGR_CUDA(cudaMalloc(&p, want));
+        PGR_CUDA(cudaMallocAsync(&p, want, (cudaStream_t)0));
+        PGR_CUDA(cudaStreamSynchronize((cudaStream_t)0));
         cap = want;
         return PGR_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() {
+        if (!p) return;
+        cudaDeviceSynchronize();   // growing/releasing is rare; nothing in flight may still use the old block
+        cudaFreeAsync(p, (cudaStream_t)0);
+        p = nullptr; cap = 0;
+    }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
