@@ -45,27 +45,25 @@ struct L0Params {
 
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
 
-// 4 ASCII bases (one little-endian word) -> 4 plane bits each, first base in the MOST significant of the 4 bits.
-// code bit0 = bit1 of (c ^ (c >> 1)), code bit1 = bit2 of c  (A=0,C=1,G=2,T=3; case-insensitive)
+// 4 ASCII bases (one little-endian word) -> 4 plane bits each in the TOP nibble of a product word, first base most
+// significant.  code bit0 = bit1 of (c ^ (c >> 1)), code bit1 = bit2 of c  (A=0,C=1,G=2,T=3; case-insensitive).
+// Bits 1,9,17,25 (resp. 2,10,18,26) are gathered by one multiply (no partial products collide, so no carries).
 __device__ __forceinline__ void planes4(uint32_t wd, uint32_t &p0, uint32_t &p1) {
     const uint32_t t = wd ^ (wd >> 1);
-    // bits at 1,9,17,25 (resp. 2,10,18,26) gathered to the top nibble by one multiply (no carries collide)
-    p0 = ((t & 0x02020202u) * 0x40201008u) >> 28;    // bit 1+8i -> 31-i
-    p1 = ((wd & 0x04040404u) * 0x20100804u) >> 28;   // bit 2+8i -> 31-i
+    p0 = (t & 0x02020202u) * 0x40201008u;    // bit 1+8i -> 31-i
+    p1 = (wd & 0x04040404u) * 0x20100804u;   // bit 2+8i -> 31-i
 }
 
-// true iff all 4 bytes of wd are one of ACGTacgt
-__device__ __forceinline__ bool word_is_acgt(uint32_t wd) {
-    const uint32_t u = wd & 0xDFDFDFDFu;             // upper-case
-    const uint32_t v = u ^ 0x41414141u;              // A->00 C->02 G->06 T->15
+// non-zero iff some byte of wd is not one of ACGTacgt
+__device__ __forceinline__ uint32_t word_not_acgt(uint32_t wd) {
+    const uint32_t v = (wd & 0xDFDFDFDFu) ^ 0x41414141u;   // upper-case; A->00 C->02 G->06 T->15
     // valid values: 0x00, 0x02, 0x06, 0x15.  bits 3,5,6,7 must be clear; then (b4,b2,b1,b0) in {0000,0010,0110,1101}
-    const uint32_t b0 = v, b1 = v >> 1, b2 = v >> 2, b4 = v >> 4;
-    const uint32_t x04 = b0 ^ b4;                    // must be 0
+    const uint32_t b1 = v >> 1, b2 = v >> 2, b4 = v >> 4;
+    const uint32_t x04 = v ^ b4;                     // b0 == b4
     const uint32_t t_ok = b2 & ~b1;                  // T: b2=1,b1=0
     const uint32_t n_ok = ~b2 | b1;                  // A,C,G: not (b2=1,b1=0)
     const uint32_t ok = (b4 & t_ok) | (~b4 & n_ok);
-    const uint32_t bad = (v & 0xE8E8E8E8u) | ((x04 | ~ok) & 0x01010101u);
-    return bad == 0;
+    return (v & 0xE8E8E8E8u) | ((x04 | ~ok) & 0x01010101u);
 }
 
 __device__ __forceinline__ bool byte_is_acgt(uint32_t c) {
@@ -228,16 +226,16 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         const bool blk_live = (blk_pos + 32 > 0) && (blk_pos < L);  // block intersects the sequence
         if (blk_live) {
             const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            bool ok = true;
+            uint32_t bad_bits = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 uint32_t a, b;
                 planes4(wd[j], a, b);
-                f0 = (f0 << 4) | a;
-                f1 = (f1 << 4) | b;
-                ok = ok && word_is_acgt(wd[j]);
+                f0 = __funnelshift_l(a, f0, 4);      // (f0 << 4) | (a >> 28)
+                f1 = __funnelshift_l(b, f1, 4);
+                bad_bits |= word_not_acgt(wd[j]);
             }
-            if (!ok || blk_pos < 0 || blk_pos + 32 > L) {
+            if (bad_bits || blk_pos < 0 || blk_pos + 32 > L) {
                 // slow exact check restricted to the bytes that belong to the sequence; the first byte outside ACGTacgt
                 // seeds an exact local replay (patch_replay_kernel), like a palindrome does
                 int first_bad = -1;
@@ -281,16 +279,22 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                 const uint32_t f1lo = fsr(b0, b1, sh) & mlo, f1hi = fsr(b1, b2, sh) & mhi;
                 const uint32_t r0lo = fsr(q00, q01, i) & mlo, r0hi = fsr(q01, q02, i) & mhi;
                 const uint32_t r1lo = fsr(q10, q11, i) & mlo, r1hi = fsr(q11, q12, i) & mhi;
-                const uint64_t F0 = ((uint64_t)f0hi << 32) | f0lo, R0 = ((uint64_t)r0hi << 32) | r0lo;
-                const bool rev = R0 < F0;                       // shmmrutils.rs:486 (plane 0 only)
                 if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
                     const int pos = blk_pos + i;
-                    if (F0 == R0 && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) record_skip(p.n_skips, p.skips, p.skip_cap, D.seq_id, pos, &D.bad);
+                    if (f0hi == r0hi && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) record_skip(p.n_skips, p.skips, p.skip_cap, D.seq_id, pos, &D.bad);
                 }
-                const uint64_t u = rev ? R0 : F0;
-                const uint64_t v = rev ? (((uint64_t)r1hi << 32) | r1lo) : (((uint64_t)f1hi << 32) | f1lo);
-                const uint64_t h = u64hash_dev(u) ^ u64hash_dev(v ^ HASH_XOR);
-                s.H[base + i] = (uint32_t)(h >> 24);
+                // strand: reverse iff rmmer.0 < fmmer.0 (shmmrutils.rs:486, plane 0 only); one 64-bit compare, four selects
+                uint32_t ulo, uhi, vlo, vhi;
+                asm("{\n\t.reg .pred p;\n\t.reg .b64 a, b;\n\t"
+                    "mov.b64 a, {%4, %5};\n\tmov.b64 b, {%6, %7};\n\tsetp.lt.u64 p, a, b;\n\t"
+                    "selp.b32 %0, %4, %6, p;\n\tselp.b32 %1, %5, %7, p;\n\tselp.b32 %2, %8, %10, p;\n\tselp.b32 %3, %9, %11, p;\n\t}"
+                    : "=r"(ulo), "=r"(uhi), "=r"(vlo), "=r"(vhi)
+                    : "r"(r0lo), "r"(r0hi), "r"(f0lo), "r"(f0hi), "r"(r1lo), "r"(r1hi), "r"(f1lo), "r"(f1hi));
+                vlo ^= (uint32_t)HASH_XOR;
+                u64hash_dev32(ulo, uhi);
+                u64hash_dev32(vlo, vhi);
+                // MM128.x high word = hash bits 24..55
+                s.H[base + i] = __funnelshift_r(ulo ^ vlo, uhi ^ vhi, 24);
             }
         }
         __syncthreads();
@@ -336,8 +340,11 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                     for (int o = 0; o < 32; o++) {
                         const bool carry = (o + cr) >= 32;
                         const uint32_t far = s.P[pb + o + (carry ? 1 : 0)];
-                        const uint32_t mv = min3u(m[o], carry ? mid2 : mid1, far);
-                        m[o] = ((amask >> o) & 1u) ? mv : 0u;      // invalid windows contribute nothing to the max
+                        m[o] = min3u(m[o], carry ? mid2 : mid1, far);
+                    }
+                    if (amask != 0xFFFFFFFFu) {   // blocks at the sequence ends: invalid windows contribute nothing to the max
+#pragma unroll
+                        for (int o = 0; o < 32; o++) m[o] = ((amask >> o) & 1u) ? m[o] : 0u;
                     }
                 }
                 __syncthreads();
@@ -360,7 +367,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                         run = max(run, m[o]);
                         const uint32_t far = s.P[sb + o - (borrow ? 1 : 0)];
                         const uint32_t M = max3u(run, borrow ? mid2 : mid1, far);
-                        cand |= (M == s.H[base + o] ? 1u : 0u) << o;
+                        if (M == s.H[base + o]) cand |= 1u << o;
                     }
                 }
                 cand &= pmask;
