@@ -330,8 +330,54 @@ struct Level {
     pgr_mm128 *out; uint64_t *off_out;
 };
 
-// one reduce_shmmr level (kind 0) or the min_span filter (kind 1): flags -> block scan -> ordered scatter
+// one reduce_shmmr level (kind 0) or the min_span filter (kind 1) in a single pass over the list (decoupled look-back)
+int run_level_3pass(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, const uint64_t *off_in, pgr_mm128 *out,
+                    uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out);
+
 int run_level(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, const uint64_t *off_in, pgr_mm128 *out,
+              uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out) {
+    // measured on config 2 (1.2e8 level-0 entries): three-pass 2.84 ms, single-pass look-back 3.48 ms (2048-entry tiles are
+    // too small to amortise the look-back latency with ~600 CTAs in flight) -> the three-pass path is the default
+    static const bool one_pass = getenv("PGR_B200_LEVELS_1PASS") != nullptr;   // A/B switch (tuning aid)
+    if (!one_pass) return run_level_3pass(ctx, kind, in, n_in, off_in, out, off_out, spec, padding, patch_rid, n_out);
+    cudaStream_t st = ctx->stream;
+    const size_t n = ctx->rn;
+    if (n_in == 0) {
+        PGR_CUDA(cudaMemsetAsync(off_out, 0, (n + 1) * sizeof(uint64_t), st));
+        *n_out = 0;
+        return PGR_OK;
+    }
+    const uint64_t n_tiles64 = ceil_div<uint64_t>(n_in, LF_TILE);
+    if (n_tiles64 >= 0x7FFFFFFFull) { set_error("list too long"); return PGR_E_LIMIT; }
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
+    PGR_TRY(ctx->block_prefix.ensure(((size_t)n_tiles + 4) * sizeof(uint64_t)));
+    PGR_CUDA(cudaMemsetAsync(ctx->block_prefix.p, 0, ((size_t)n_tiles + 4) * sizeof(uint64_t), st));
+    LevelFusedParams p;
+    p.in = in; p.n_in = n_in; p.seq_off_in = off_in; p.n_seq = (uint32_t)n;
+    p.r = spec.r; p.padding = padding ? 1u : 0u; p.min_span = spec.min_span;
+    p.out = out; p.seq_off_out = off_out; p.rid = ctx->d_rid.as<uint32_t>() + ctx->r0; p.patch_rid = patch_rid ? 1u : 0u;
+    p.tile_status = (unsigned long long *)ctx->block_prefix.p;
+    p.total_out = ctx->block_prefix.as<uint64_t>() + n_tiles;
+    p.ticket = (uint32_t *)(ctx->block_prefix.as<uint64_t>() + n_tiles + 1);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGR_CUDA(cudaFuncSetAttribute(level_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LevelFusedSmem)));
+        PGR_CUDA(cudaFuncSetAttribute(level_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LevelFusedSmem)));
+        attr_set = true;
+    }
+    if (kind == 0) level_fused_kernel<0><<<n_tiles, LF_NT, sizeof(LevelFusedSmem), st>>>(p);
+    else level_fused_kernel<1><<<n_tiles, LF_NT, sizeof(LevelFusedSmem), st>>>(p);
+    ctx->counters[0] += 1;
+    PGR_CUDA(cudaGetLastError());
+    PGR_TRY(ctx->ensure_ctl(64));
+    PGR_CUDA(cudaMemcpyAsync(ctx->h_ctl, p.total_out, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    *n_out = *(uint64_t *)ctx->h_ctl;
+    return PGR_OK;
+}
+
+// the same level as three kernels: flags -> block scan -> ordered scatter
+int run_level_3pass(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, const uint64_t *off_in, pgr_mm128 *out,
               uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out) {
     cudaStream_t st = ctx->stream;
     const size_t n = ctx->rn;

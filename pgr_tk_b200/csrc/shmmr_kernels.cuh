@@ -962,6 +962,153 @@ __global__ void __launch_bounds__(LV_NT) level_scatter_kernel(const LevelParams 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-pass version of one level (flags + ordered compaction in ONE kernel): the list is read from HBM once, the tile
+// and a halo of r-1 entries live in shared memory, and the global output offset of a tile comes from a decoupled
+// look-back over per-tile status words (aggregate / inclusive prefix), tiles being handed out in order by a ticket.
+constexpr int LF_NT = 256, LF_PER = 8, LF_TILE = LF_NT * LF_PER, LF_HALO = 12;
+constexpr int LF_N = LF_TILE + 2 * LF_HALO;
+
+struct LevelFusedParams {
+    const pgr_mm128 *in; uint64_t n_in;
+    const uint64_t *seq_off_in;  // [n_seq+1]
+    uint32_t n_seq;
+    uint32_t r, padding, min_span;
+    pgr_mm128 *out;
+    uint64_t *seq_off_out;       // [n_seq+1]
+    const uint32_t *rid; uint32_t patch_rid;
+    unsigned long long *tile_status;   // [n_tiles] zeroed: bits 62..63 = 0 invalid / 1 aggregate / 2 inclusive prefix
+    uint32_t *ticket;                  // zeroed
+    uint64_t *total_out;
+};
+
+struct LevelFusedSmem {
+    uint64_t x[LF_N + LF_N / 8 + 8];   // index q + q/8: one pad per 8 entries keeps the 8-per-thread accesses conflict-light
+    uint64_t y[LF_N + LF_N / 8 + 8];
+    uint32_t excl[LF_TILE + 1];
+    uint32_t wsum[LF_NT / 32];
+    uint32_t tile;
+    uint64_t base;
+};
+__device__ __forceinline__ int lf_idx(int q) { return q + (q >> 3); }
+
+template <int KIND>
+__global__ void __launch_bounds__(LF_NT) level_fused_kernel(const LevelFusedParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LevelFusedSmem &s = *reinterpret_cast<LevelFusedSmem *>(smem_raw);
+    if (threadIdx.x == 0) s.tile = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s.tile;
+    const int64_t i0 = (int64_t)tile * LF_TILE;
+    const int64_t n = (int64_t)p.n_in;
+    // tile + halo -> shared memory; q = 0 is global index i0 - LF_HALO
+    for (int q = threadIdx.x; q < LF_N; q += LF_NT) {
+        const int64_t g = i0 - LF_HALO + q;
+        pgr_mm128 m; m.x = 0; m.y = ~0ull;       // sequence ordinal 0xFFFFFFFF never matches: acts as a boundary
+        if (g >= 0 && g < n) m = p.in[g];
+        s.x[lf_idx(q)] = m.x; s.y[lf_idx(q)] = m.y;
+    }
+    __syncthreads();
+    const uint32_t r = p.r;
+    uint32_t fl = 0, cnt = 0;
+    const int q0 = LF_HALO + threadIdx.x * LF_PER;
+#pragma unroll
+    for (int j = 0; j < LF_PER; j++) {
+        const int q = q0 + j;
+        const int64_t g = i0 - LF_HALO + q;
+        if (g >= n) break;
+        const uint64_t xe = s.x[lf_idx(q)], ye = s.y[lf_idx(q)];
+        const uint32_t sq = (uint32_t)(ye >> 32);
+        bool keep;
+        if (KIND == 0) {
+            uint32_t l = 0, rr = 0;
+            for (uint32_t d = 1; d < r; d++) {
+                if ((uint32_t)(s.y[lf_idx(q - d)] >> 32) != sq) { if (p.padding) l = r - 1; break; }
+                if (s.x[lf_idx(q - d)] < xe) break;
+                l = d;
+            }
+            for (uint32_t d = 1; d < r; d++) {
+                if ((uint32_t)(s.y[lf_idx(q + d)] >> 32) != sq) { if (p.padding) rr = r - 1; break; }
+                if (s.x[lf_idx(q + d)] < xe) break;
+                rr = d;
+            }
+            keep = (l + rr + 1 >= r);
+        } else {
+            const uint64_t yp = s.y[lf_idx(q - 1)], yn = s.y[lf_idx(q + 1)];
+            if ((uint32_t)(yp >> 32) != sq || (uint32_t)(yn >> 32) != sq) {
+                keep = true;   // first or last shimmer of its sequence
+            } else {
+                const uint32_t pp = (uint32_t)(yp & 0xFFFFFFFFu) >> 1, cp = (uint32_t)(ye & 0xFFFFFFFFu) >> 1, np = (uint32_t)(yn & 0xFFFFFFFFu) >> 1;
+                keep = (uint32_t)(cp - pp) > p.min_span && (uint32_t)(np - cp) > p.min_span && s.x[lf_idx(q - 1)] != xe && xe != s.x[lf_idx(q + 1)];
+            }
+        }
+        if (keep) { fl |= 1u << j; cnt++; }
+    }
+    // CTA scan of the per-thread counts
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = cnt;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s.wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wb = 0, total = 0;
+    for (int i = 0; i < LF_NT / 32; i++) { const uint32_t v = s.wsum[i]; if (i < warp) wb += v; total += v; }
+    // decoupled look-back (warp 0): publish the aggregate, then sum predecessors until an inclusive prefix is met
+    if (warp == 0) {
+        const unsigned long long FLAG_A = 1ull << 62, FLAG_P = 2ull << 62, VMASK = (1ull << 62) - 1;
+        volatile unsigned long long *st = p.tile_status;
+        if (lane == 0) { st[tile] = (tile == 0 ? FLAG_P : FLAG_A) | (unsigned long long)total; __threadfence(); }
+        uint64_t excl = 0;
+        if (tile > 0) {
+            int64_t look = (int64_t)tile - 1;
+            for (;;) {
+                const int64_t j = look - lane;
+                unsigned long long v = FLAG_P;   // lanes past the beginning read as "prefix 0"
+                if (j >= 0) { do { v = st[j]; } while ((v >> 62) == 0); }
+                const uint32_t is_p = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+                // sum the values of lanes up to and including the first prefix lane
+                const int first_p = is_p ? __ffs(is_p) - 1 : 32;
+                uint64_t val = (lane <= first_p) ? (uint64_t)(v & VMASK) : 0;
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xFFFFFFFFu, val, d);
+                val = __shfl_sync(0xFFFFFFFFu, val, 0);
+                excl += val;
+                if (is_p) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            st[tile] = FLAG_P | (unsigned long long)(excl + total);
+            __threadfence();
+            s.base = excl;
+            if (i0 + LF_TILE >= n) *p.total_out = excl + total;
+        }
+    }
+    __syncthreads();
+    const uint64_t base = s.base;
+    uint32_t rank = wb + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < LF_PER; j++) {
+        s.excl[threadIdx.x * LF_PER + j] = rank;
+        if ((fl >> j) & 1u) {
+            const int q = q0 + j;
+            pgr_mm128 mm; mm.x = s.x[lf_idx(q)]; mm.y = s.y[lf_idx(q)];
+            if (p.patch_rid) mm.y = ((uint64_t)p.rid[(uint32_t)(mm.y >> 32)] << 32) | (mm.y & 0xFFFFFFFFull);
+            p.out[base + rank] = mm;
+            rank++;
+        }
+    }
+    if (threadIdx.x == LF_NT - 1) s.excl[LF_TILE] = rank;
+    __syncthreads();
+    // sequences whose first input element lies in this tile get their output offset from the local scan
+    const int64_t i1 = min(i0 + (int64_t)LF_TILE, n);
+    const bool last_tile = (i1 == n);
+    uint32_t lo = 0, hi = p.n_seq + 1;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((int64_t)p.seq_off_in[mid] < i0) lo = mid + 1; else hi = mid; }
+    for (uint32_t sid = lo + threadIdx.x; sid <= p.n_seq; sid += LF_NT) {
+        const int64_t b = (int64_t)p.seq_off_in[sid];
+        if (b < i1 || (last_tile && b == i1)) p.seq_off_out[sid] = base + s.excl[b - i0]; else break;
+    }
+}
+
 // sketch mode (shmmrutils.rs:558-630): every position whose full 64-bit hash is below the threshold is kept.
 // One thread per 32-base block, rolling over its positions (k-mer windows from the plane words as in l0_kernel is
 // the fast design; sketch mode is not on the benchmarked path, so this kernel favours simplicity: two passes,
