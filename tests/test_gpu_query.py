@@ -167,3 +167,36 @@ def test_adj_list_matches_oracle():
     recs = orc.parse_fasta(os.path.join(GOLDEN, "test_seqs.fa"))
     g2, o2 = build_pair([s for _, s in recs])
     assert fields_equal(g2.adj_list(0), o2.adj_list(0), names)
+
+
+def test_colliding_sids_and_duplicate_signatures():
+    """pgr-mdb restarts sid at 0 for every .agc file (seq_db.rs:543): per-key vectors are then not sid-monotone and can
+    hold identical signatures; counts, hit expansion and the HitPair-keyed maps of sparse_aln must still agree."""
+    rng = np.random.default_rng(41)
+    haps = pangenome(rng, 6, 60000, snp=0.002, with_dup=False)
+    g = pg.ShmmrIndex(pg.ShmmrSpec(48, 56, 4, 12), pg.FRG_ID_AGC)
+    o = orc.Index(orc.mkspec(48, 56, 4, 12), 1)
+    for lo in (0, 2, 4):                      # three "files", sids 0,1 each time; the last one repeats a sequence
+        batch = [haps[lo], haps[lo + 1]] if lo < 4 else [haps[0], haps[5]]
+        g.add_batch([0, 1], batch)
+        o.add_batch([0, 1], batch)
+    gk, go, gs = g.export()
+    ok_, oo, os_ = o.export()
+    assert np.array_equal(gk, ok_) and np.array_equal(go, oo) and fields_equal(gs, os_, ["frg_id", "sid", "bgn", "end", "ori"])
+    queries = [mutate(rng, haps[0][3000:33000], 0.001), revcomp(haps[3][10000:40000]), haps[5][:20000]]
+    for kw in (dict(max_count=128, max_count_query=128, max_count_target=128, max_aln_span=8),
+               dict(max_count=2, max_count_query=2, max_count_target=2, max_aln_span=8),
+               dict(max_count=128, max_count_query=128, max_count_target=3, max_aln_span=2, oriented=True)):
+        assert_query_equal(g, o, queries, 0.025, **kw)
+    names = ["sid", "ori0", "ori1", "a0", "a1", "b0", "b1"]
+    for mc in (0, 2, 4):
+        assert fields_equal(g.adj_list(mc), o.adj_list(mc), names)
+
+
+def test_query_long_and_tiny_queries_mixed():
+    rng = np.random.default_rng(43)
+    haps = pangenome(rng, 5, 200000)
+    g, o = build_pair(haps)
+    queries = [haps[2][:150000], b"A", haps[1][1000:1400], revcomp(haps[4][50000:190000]), b"N" * 3000, haps[0][100:3000]]
+    n = assert_query_equal(g, o, queries, 0.025, max_count=128, max_count_query=128, max_count_target=128, max_aln_span=8)
+    assert n >= 3
