@@ -6,7 +6,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libpgr_b200.so")
+# PGR_B200_LIB points at an alternative build of the same library (tuning aid)
+_LIB = os.environ.get("PGR_B200_LIB") or os.path.join(_HERE, "libpgr_b200.so")
 
 MM128 = np.dtype([("x", "<u8"), ("y", "<u8")])
 SIG = np.dtype([("frg_id", "<u4"), ("sid", "<u4"), ("bgn", "<u4"), ("end", "<u4"), ("ori", "u1"), ("pad", "u1", 3)])

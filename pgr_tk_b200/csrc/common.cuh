@@ -65,6 +65,16 @@ __device__ __forceinline__ void u64hash_dev32(uint32_t &lo, uint32_t &hi) {
     xorshift_r<28>(lo, hi);
     mul64c<0x80000001u>(lo, hi);
 }
+// as u64hash_dev32 with the -1 of the first step supplied by the caller (a kernel parameter, see L0Params::m1)
+__device__ __forceinline__ void u64hash_dev32m(uint32_t &lo, uint32_t &hi, uint64_t m1) {
+    mul64c<0x1FFFFFu>(lo, hi, m1);
+    xorshift_r<24>(lo, hi);
+    mul64c<265u>(lo, hi);
+    xorshift_r<14>(lo, hi);
+    mul64c<21u>(lo, hi);
+    xorshift_r<28>(lo, hi);
+    mul64c<0x80000001u>(lo, hi);
+}
 __device__ __forceinline__ uint64_t u64hash_dev(uint64_t key) {
     uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
     u64hash_dev32(lo, hi);

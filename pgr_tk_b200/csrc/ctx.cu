@@ -419,18 +419,17 @@ int launch_l0u(const L0Params &p, int grid, cudaStream_t st) {
 }
 template <int W, int K>
 int launch_l0(const L0Params &p, int grid, cudaStream_t st) {
-    // PGR_B200_L0_UNROLL selects the key-loop unroll factor of the specialised kernels (tuning aid)
-    static const int u = getenv("PGR_B200_L0_UNROLL") ? atoi(getenv("PGR_B200_L0_UNROLL")) : 8;
-    if (W == 80 && u == 4) return launch_l0u<W, K, 4>(p, grid, st);
+    // PGR_B200_L0_UNROLL selects the key-loop unroll factor of the w=80 kernel (tuning aid; 4 measured best, 8 within 1 %)
+    static const int u = getenv("PGR_B200_L0_UNROLL") ? atoi(getenv("PGR_B200_L0_UNROLL")) : 4;
+    if (W == 80 && u == 8) return launch_l0u<W, K, 8>(p, grid, st);
     if (W == 80 && u == 16) return launch_l0u<W, K, 16>(p, grid, st);
-    if (W == 80 && u == 32) return launch_l0u<W, K, 32>(p, grid, st);
-    return launch_l0u<W, K, 8>(p, grid, st);
+    return launch_l0u<W, K, 4>(p, grid, st);
 }
 
 template <int W, int K>
 int occupancy_l0(int *occ) {
-    PGR_CUDA(cudaFuncSetAttribute(l0_kernel<W, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(L0Smem)));
-    PGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, l0_kernel<W, K>, L0_NT, sizeof(L0Smem)));
+    PGR_CUDA(cudaFuncSetAttribute(l0_kernel<W, K, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(L0Smem)));
+    PGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, l0_kernel<W, K, 4>, L0_NT, sizeof(L0Smem)));
     return PGR_OK;
 }
 
@@ -637,6 +636,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         p.chunk_count = ctx->chunk_count.as<uint64_t>(); p.seq_count = ctx->seq_count.as<uint32_t>();
         p.seq_flag = ctx->seq_flag.as<uint32_t>();
         p.skips = ctx->skips.as<uint2>(); p.n_skips = ctx->n_skips.as<uint32_t>(); p.skip_cap = SKIP_CAP;
+        p.m1 = ~0ull;
         trace_mark("run_l0: arena + memsets");
         const int slot = ctx->timer.begin("l0_minimizers", st);
         if (variant == 1) PGR_TRY((launch_l0<80, 56>(p, (int)G, st)));

@@ -14,13 +14,20 @@
 
 namespace pgr {
 
-constexpr int L0_NT = 128;                 // threads per CTA; thread t owns the 32-base block t of the tile's load region
+// tile geometry; overridable at build time for tuning (make NVCCFLAGS+=-DPGR_L0_NT=256 ...)
+#ifndef PGR_L0_NT
+#define PGR_L0_NT 256
+#endif
+#ifndef PGR_L0_MIN_CTAS
+#define PGR_L0_MIN_CTAS 3
+#endif
+constexpr int L0_NT = PGR_L0_NT;           // threads per CTA; thread t owns the 32-base block t of the tile's load region
 constexpr int L0_CTX = 2;                  // leading context-only blocks (a 56-mer reaches 55 bases back)
 constexpr int L0_KB = L0_NT - L0_CTX;      // blocks that get keys
 constexpr int L0_KPOS = L0_KB * 32;        // key positions per tile
 constexpr int L0_PADB = 4;                 // spare blocks on both sides of the smem arrays (van Herk neighbours, w <= 128)
 constexpr int L0_ARR = (L0_KB + 2 * L0_PADB) * 33;  // padded u32 array length
-constexpr int L0_MIN_CTAS = 5;             // resident CTAs per SM the kernel is compiled for
+constexpr int L0_MIN_CTAS = PGR_L0_MIN_CTAS;  // resident CTAs per SM the kernel is compiled for
 constexpr int L0_LISTCAP = L0_ARR * 2;     // u16 entries that fit in the P array
 
 struct L0Params {
@@ -41,6 +48,8 @@ struct L0Params {
     uint2 *skips;                // (sequence, position) of pushed positions with fmmer == rmmer (shmmrutils.rs:477)
     uint32_t *n_skips;           // running count; beyond skip_cap the sequence is flagged instead
     uint32_t skip_cap;
+    uint64_t m1;                 // ~0 (the -1 of the hash's first step) as a parameter: an IMAD.WIDE addend straight from the constant bank
+                                 // instead of two MOVs per position
 };
 
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
@@ -180,6 +189,20 @@ __device__ __noinline__ void record_skip(uint32_t *n_skips, uint2 *skips, uint32
     if (slot < cap) skips[slot] = make_uint2(seq_id, (uint32_t)pos); else *bad = 1;
 }
 
+// cold path of the fast key loop: some position of this thread's block has equal top words of plane 0 on both strands, so the
+// strand picked from them may be wrong: redo the prefix of those positions exactly and record the palindromes
+__device__ __noinline__ void strand_tie_scan(uint32_t *n_skips, uint2 *skips, uint32_t cap, L0Smem &s, L0Smem::TileDesc &D, int kb, int32_t blk_pos, int32_t L, uint32_t k) {
+    for (int i = 0; i < 32; i++) {
+        const int q = 32 * kb + i, pos = blk_pos + i;
+        const KmerRegs r = kmer_at(s, q, k);
+        if ((uint32_t)(r.f0 >> (k - 32)) != (uint32_t)(r.r0 >> (k - 32))) continue;
+        const bool rev = r.r0 < r.f0;
+        const uint64_t h = rev ? (u64hash(r.r0) ^ u64hash(r.r1 ^ HASH_XOR)) : (u64hash(r.f0) ^ u64hash(r.f1 ^ HASH_XOR));
+        s.H[pidx(q)] = (uint32_t)(h >> 24);
+        if (r.f0 == r.r0 && r.f1 == r.r1 && pos >= (int)k && pos < L) record_skip(n_skips, skips, cap, D.seq_id, pos, &D.bad);
+    }
+}
+
 // Level-0 minimizers of one tile.  W, K > 0 are compile-time specialisations; 0 = read from params.
 template <int W, int K, int U = 8>
 __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p) {
@@ -272,29 +295,68 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             const uint32_t q00 = fsr(ra0, ra1, cb), q01 = fsr(ra1, ra2, cb), q02 = fsr(ra2, ra3, cb);
             const uint32_t q10 = fsr(rb0, rb1, cb), q11 = fsr(rb1, rb2, cb), q12 = fsr(rb2, rb3, cb);
             const int base = pidx(32 * kb);
+            if constexpr (K > 32) {
+                // Fast key loop (K > 32; 61 instructions per position against 72 for the generic loop below).  Each
+                // strand carries X = the TOP 32 bits of its K-bit plane-0 register (bits [K-32, K)), a plain funnel
+                // extraction from the plane string pre-shifted by K-32 once per thread.  The strand (shmmrutils.rs:486) is
+                // decided on X alone: one 32-bit compare + one min; the low word of plane 0 and both words of plane 1
+                // are extracted for the chosen strand only (unconditional forward extraction, predicated overwrite), and
+                // the high words are X >> (64-K), so no masks are needed.  Blocks in which some position has equal X on
+                // both strands (every palindrome is one) are redone exactly after the loop (strand_tie_scan, cold).
+                constexpr uint32_t PS = K - 32, HS = 64 - K;
+                const uint32_t a0p = fsr(a0, a1, PS), a1p = fsr(a1, a2, PS);
+                const uint32_t b0p = fsr(b0, b1, PS), b1p = fsr(b1, b2, PS);
+                const uint32_t q0p0 = fsr(q00, q01, PS), q0p1 = fsr(q01, q02, PS);
+                const uint32_t q1p0 = fsr(q10, q11, PS), q1p1 = fsr(q11, q12, PS);
+                const uint64_t m1 = p.m1;
+                uint32_t tacc = 0xFFFFFFFFu;   // min over the block of X_f ^ X_r: 0 <=> some position ties
 #pragma unroll U
-            for (int i = 0; i < 32; i++) {
-                const uint32_t sh = 31 - i;
-                const uint32_t f0lo = fsr(a0, a1, sh) & mlo, f0hi = fsr(a1, a2, sh) & mhi;
-                const uint32_t f1lo = fsr(b0, b1, sh) & mlo, f1hi = fsr(b1, b2, sh) & mhi;
-                const uint32_t r0lo = fsr(q00, q01, i) & mlo, r0hi = fsr(q01, q02, i) & mhi;
-                const uint32_t r1lo = fsr(q10, q11, i) & mlo, r1hi = fsr(q11, q12, i) & mhi;
-                if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
-                    const int pos = blk_pos + i;
-                    if (f0hi == r0hi && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) record_skip(p.n_skips, p.skips, p.skip_cap, D.seq_id, pos, &D.bad);
+                for (int i = 0; i < 32; i++) {
+                    const uint32_t sh = 31 - i;
+                    const uint32_t f0x = fsr(a0p, a1p, sh), r0x = fsr(q0p0, q0p1, i);
+                    tacc = min(tacc, f0x ^ r0x);
+                    const uint32_t ux = min(f0x, r0x);
+                    uint32_t ulo, vlo, vx;
+                    asm("{\n\t.reg .pred p;\n\t"
+                        "setp.lt.u32 p, %3, %4;\n\t"
+                        "shf.r.wrap.b32 %0, %11, %12, %18;\n\t@p shf.r.wrap.b32 %0, %5, %6, %17;\n\t"
+                        "shf.r.wrap.b32 %1, %13, %14, %18;\n\t@p shf.r.wrap.b32 %1, %7, %8, %17;\n\t"
+                        "shf.r.wrap.b32 %2, %15, %16, %18;\n\t@p shf.r.wrap.b32 %2, %9, %10, %17;\n\t}"
+                        : "=&r"(ulo), "=&r"(vlo), "=&r"(vx)
+                        : "r"(r0x), "r"(f0x), "r"(q00), "r"(q01), "r"(q10), "r"(q11), "r"(q1p0), "r"(q1p1),
+                          "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(b0p), "r"(b1p), "r"((uint32_t)i), "r"(sh));
+                    uint32_t uhi = ux >> HS, vhi = vx >> HS;
+                    vlo ^= (uint32_t)HASH_XOR;
+                    u64hash_dev32m(ulo, uhi, m1);
+                    u64hash_dev32m(vlo, vhi, m1);
+                    s.H[base + i] = __funnelshift_r(ulo ^ vlo, uhi ^ vhi, 24);
                 }
-                // strand: reverse iff rmmer.0 < fmmer.0 (shmmrutils.rs:486, plane 0 only); one 64-bit compare, four selects
-                uint32_t ulo, uhi, vlo, vhi;
-                asm("{\n\t.reg .pred p;\n\t.reg .b64 a, b;\n\t"
-                    "mov.b64 a, {%4, %5};\n\tmov.b64 b, {%6, %7};\n\tsetp.lt.u64 p, a, b;\n\t"
-                    "selp.b32 %0, %4, %6, p;\n\tselp.b32 %1, %5, %7, p;\n\tselp.b32 %2, %8, %10, p;\n\tselp.b32 %3, %9, %11, p;\n\t}"
-                    : "=r"(ulo), "=r"(uhi), "=r"(vlo), "=r"(vhi)
-                    : "r"(r0lo), "r"(r0hi), "r"(f0lo), "r"(f0hi), "r"(r1lo), "r"(r1hi), "r"(f1lo), "r"(f1hi));
-                vlo ^= (uint32_t)HASH_XOR;
-                u64hash_dev32(ulo, uhi);
-                u64hash_dev32(vlo, vhi);
-                // MM128.x high word = hash bits 24..55
-                s.H[base + i] = __funnelshift_r(ulo ^ vlo, uhi ^ vhi, 24);
+                if (tacc == 0) strand_tie_scan(p.n_skips, p.skips, p.skip_cap, s, D, kb, blk_pos, L, k);
+            } else {
+    #pragma unroll U
+                for (int i = 0; i < 32; i++) {
+                    const uint32_t sh = 31 - i;
+                    const uint32_t f0lo = fsr(a0, a1, sh) & mlo, f0hi = fsr(a1, a2, sh) & mhi;
+                    const uint32_t f1lo = fsr(b0, b1, sh) & mlo, f1hi = fsr(b1, b2, sh) & mhi;
+                    const uint32_t r0lo = fsr(q00, q01, i) & mlo, r0hi = fsr(q01, q02, i) & mhi;
+                    const uint32_t r1lo = fsr(q10, q11, i) & mlo, r1hi = fsr(q11, q12, i) & mhi;
+                    if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
+                        const int pos = blk_pos + i;
+                        if (f0hi == r0hi && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) record_skip(p.n_skips, p.skips, p.skip_cap, D.seq_id, pos, &D.bad);
+                    }
+                    // strand: reverse iff rmmer.0 < fmmer.0 (shmmrutils.rs:486, plane 0 only); one 64-bit compare, four selects
+                    uint32_t ulo, uhi, vlo, vhi;
+                    asm("{\n\t.reg .pred p;\n\t.reg .b64 a, b;\n\t"
+                        "mov.b64 a, {%4, %5};\n\tmov.b64 b, {%6, %7};\n\tsetp.lt.u64 p, a, b;\n\t"
+                        "selp.b32 %0, %4, %6, p;\n\tselp.b32 %1, %5, %7, p;\n\tselp.b32 %2, %8, %10, p;\n\tselp.b32 %3, %9, %11, p;\n\t}"
+                        : "=r"(ulo), "=r"(uhi), "=r"(vlo), "=r"(vhi)
+                        : "r"(r0lo), "r"(r0hi), "r"(f0lo), "r"(f0hi), "r"(r1lo), "r"(r1hi), "r"(f1lo), "r"(f1hi));
+                    vlo ^= (uint32_t)HASH_XOR;
+                    u64hash_dev32(ulo, uhi);
+                    u64hash_dev32(vlo, vhi);
+                    // MM128.x high word = hash bits 24..55
+                    s.H[base + i] = __funnelshift_r(ulo ^ vlo, uhi ^ vhi, 24);
+                }
             }
         }
         __syncthreads();
