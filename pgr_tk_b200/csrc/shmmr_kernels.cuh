@@ -62,17 +62,19 @@ __device__ __forceinline__ void planes4(uint32_t wd, uint32_t &p0, uint32_t &p1)
     p0 = (t & 0x02020202u) * 0x40201008u;    // bit 1+8i -> 31-i
     p1 = (wd & 0x04040404u) * 0x20100804u;   // bit 2+8i -> 31-i
 }
-
-// non-zero iff some byte of wd is not one of ACGTacgt
-__device__ __forceinline__ uint32_t word_not_acgt(uint32_t wd) {
-    const uint32_t v = (wd & 0xDFDFDFDFu) ^ 0x41414141u;   // upper-case; A->00 C->02 G->06 T->15
-    // valid values: 0x00, 0x02, 0x06, 0x15.  bits 3,5,6,7 must be clear; then (b4,b2,b1,b0) in {0000,0010,0110,1101}
-    const uint32_t b1 = v >> 1, b2 = v >> 2, b4 = v >> 4;
-    const uint32_t x04 = v ^ b4;                     // b0 == b4
-    const uint32_t t_ok = b2 & ~b1;                  // T: b2=1,b1=0
-    const uint32_t n_ok = ~b2 | b1;                  // A,C,G: not (b2=1,b1=0)
-    const uint32_t ok = (b4 & t_ok) | (~b4 & n_ok);
-    return (v & 0xE8E8E8E8u) | ((x04 | ~ok) & 0x01010101u);
+// planes4 plus a validity word: bits outside 0x20 of some byte of `diff` are set iff that byte is not one of ACGTacgt.
+// The 2-bit codes, doubled, become the four nibbles of a PRMT selector that looks the expected upper-case letter up in
+// the byte pool {A,-,C,-,G,-,T,-}; the caller ORs (expected ^ byte) over the block and masks the case bit once.
+__device__ __forceinline__ void planes4v(uint32_t wd, uint32_t &p0, uint32_t &p1, uint32_t &diff) {
+    const uint32_t t = wd ^ (wd >> 1);
+    const uint32_t c0 = t & 0x02020202u, c1 = wd & 0x04040404u;
+    p0 = c0 * 0x40201008u;
+    p1 = c1 * 0x20100804u;
+    const uint32_t m = c0 | c1;                       // per byte: code << 1 (0, 2, 4, 6) in the low nibble
+    const uint32_t n = m | (m >> 4);                  // byte 0 = nibbles (code0, code1), byte 2 = nibbles (code2, code3)
+    const uint32_t sel = __byte_perm(n, 0u, 0x4420);  // low half = byte 0, byte 2
+    const uint32_t expect = __byte_perm(0x00430041u, 0x00540047u, sel);   // 'A', 'C' | 'G', 'T' at even pool slots
+    diff |= expect ^ wd;
 }
 
 __device__ __forceinline__ bool byte_is_acgt(uint32_t c) {
@@ -84,13 +86,14 @@ __device__ __forceinline__ uint32_t min3u(uint32_t a, uint32_t b, uint32_t c) { 
 __device__ __forceinline__ uint32_t max3u(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
 
 struct L0Smem {
-    uint32_t H[L0_ARR];      // bits 24..55 of the k-mer hash = the high word of MM128.x; padded index q + q/32 + PADB*33
+    uint32_t H[L0_ARR];      // key prefix: the top bits of MM128.x (hash bits 32..55 in the K > 32 kernels, 24..55 in the
+                             // generic one); padded index q + q/32 + PADB*33
     uint32_t P[L0_ARR];      // van Herk exchange: prefix minima (pass 1) then suffix maxima (pass 2); afterwards it
                              // holds `list`: ordered key indices (u16) of the selected positions + tail replay entries
     uint32_t F0[L0_NT + 8], F1[L0_NT + 8];   // bit planes per 32-base block, first base in the MOST significant bit;
                                              // the complement planes (first base in the LEAST significant bit) are ~brev()
     uint32_t bext[L0_KB + 2 * L0_PADB];   // block min (pass 1) / block max (pass 2)
-    uint32_t wsum[L0_NT / 32];
+    uint64_t wsum[L0_NT / 32];
     uint32_t n_list;
     // tile descriptors, double-buffered: thread 0 prepares tile t+1 while the CTA works on tile t, and every thread
     // issues its 32-byte load for tile t+1 before the key loop of tile t (software prefetch across tiles)
@@ -198,7 +201,7 @@ __device__ __noinline__ void strand_tie_scan(uint32_t *n_skips, uint2 *skips, ui
         if ((uint32_t)(r.f0 >> (k - 32)) != (uint32_t)(r.r0 >> (k - 32))) continue;
         const bool rev = r.r0 < r.f0;
         const uint64_t h = rev ? (u64hash(r.r0) ^ u64hash(r.r1 ^ HASH_XOR)) : (u64hash(r.f0) ^ u64hash(r.f1 ^ HASH_XOR));
-        s.H[pidx(q)] = (uint32_t)(h >> 24);
+        s.H[pidx(q)] = (uint32_t)(h >> 32) & 0x00FFFFFFu;   // the fast loop's 24-bit prefix
         if (r.f0 == r.r0 && r.f1 == r.r1 && pos >= (int)k && pos < L) record_skip(n_skips, skips, cap, D.seq_id, pos, &D.bad);
     }
 }
@@ -253,11 +256,11 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 uint32_t a, b;
-                planes4(wd[j], a, b);
+                planes4v(wd[j], a, b, bad_bits);
                 f0 = __funnelshift_l(a, f0, 4);      // (f0 << 4) | (a >> 28)
                 f1 = __funnelshift_l(b, f1, 4);
-                bad_bits |= word_not_acgt(wd[j]);
             }
+            bad_bits &= 0xDFDFDFDFu;                 // lower case is valid
             if (bad_bits || blk_pos < 0 || blk_pos + 32 > L) {
                 // slow exact check restricted to the bytes that belong to the sequence; the first byte outside ACGTacgt
                 // seeds an exact local replay (patch_replay_kernel), like a palindrome does
@@ -309,29 +312,33 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                 const uint32_t q0p0 = fsr(q00, q01, PS), q0p1 = fsr(q01, q02, PS);
                 const uint32_t q1p0 = fsr(q10, q11, PS), q1p1 = fsr(q11, q12, PS);
                 const uint64_t m1 = p.m1;
-                uint32_t tacc = 0xFFFFFFFFu;   // min over the block of X_f ^ X_r: 0 <=> some position ties
+                bool no_tie = true;   // stays true unless some position of the block has X_f == X_r
 #pragma unroll U
                 for (int i = 0; i < 32; i++) {
-                    const uint32_t sh = 31 - i;
-                    const uint32_t f0x = fsr(a0p, a1p, sh), r0x = fsr(q0p0, q0p1, i);
-                    tacc = min(tacc, f0x ^ r0x);
+                    // forward window: bits [31-i, 63-i) of (a1:a0) = left funnel by i+1 (clamped: 32 at i = 31), so that
+                    // positions i and i+1 share the shift-amount register i+1 (reverse window: right funnel by i)
+                    const uint32_t sl = (uint32_t)i + 1u;
+                    const uint32_t f0x = __funnelshift_lc(a0p, a1p, sl), r0x = fsr(q0p0, q0p1, i);
+                    no_tie &= (f0x != r0x);
                     const uint32_t ux = min(f0x, r0x);
                     uint32_t ulo, vlo, vx;
                     asm("{\n\t.reg .pred p;\n\t"
                         "setp.lt.u32 p, %3, %4;\n\t"
-                        "shf.r.wrap.b32 %0, %11, %12, %18;\n\t@p shf.r.wrap.b32 %0, %5, %6, %17;\n\t"
-                        "shf.r.wrap.b32 %1, %13, %14, %18;\n\t@p shf.r.wrap.b32 %1, %7, %8, %17;\n\t"
-                        "shf.r.wrap.b32 %2, %15, %16, %18;\n\t@p shf.r.wrap.b32 %2, %9, %10, %17;\n\t}"
+                        "shf.l.clamp.b32 %0, %11, %12, %18;\n\t@p shf.r.wrap.b32 %0, %5, %6, %17;\n\t"
+                        "shf.l.clamp.b32 %1, %13, %14, %18;\n\t@p shf.r.wrap.b32 %1, %7, %8, %17;\n\t"
+                        "shf.l.clamp.b32 %2, %15, %16, %18;\n\t@p shf.r.wrap.b32 %2, %9, %10, %17;\n\t}"
                         : "=&r"(ulo), "=&r"(vlo), "=&r"(vx)
                         : "r"(r0x), "r"(f0x), "r"(q00), "r"(q01), "r"(q10), "r"(q11), "r"(q1p0), "r"(q1p1),
-                          "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(b0p), "r"(b1p), "r"((uint32_t)i), "r"(sh));
+                          "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(b0p), "r"(b1p), "r"((uint32_t)i), "r"(sl));
                     uint32_t uhi = ux >> HS, vhi = vx >> HS;
                     vlo ^= (uint32_t)HASH_XOR;
                     u64hash_dev32m(ulo, uhi, m1);
                     u64hash_dev32m(vlo, vhi, m1);
-                    s.H[base + i] = __funnelshift_r(ulo ^ vlo, uhi ^ vhi, 24);
+                    // key prefix of this kernel: the top 24 bits of MM128.x = hash bits 32..55 (one LOP3); any prefix of x
+                    // orders consistently with x, and prefix ties between candidates are resolved exactly in phase 5
+                    s.H[base + i] = (uhi ^ vhi) & 0x00FFFFFFu;
                 }
-                if (tacc == 0) strand_tie_scan(p.n_skips, p.skips, p.skip_cap, s, D, kb, blk_pos, L, k);
+                if (!no_tie) strand_tie_scan(p.n_skips, p.skips, p.skip_cap, s, D, kb, blk_pos, L, k);
             } else {
     #pragma unroll U
                 for (int i = 0; i < 32; i++) {
@@ -365,21 +372,25 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         // valid window starts a (sequence positions): [k, Eb - w], Eb = min(L, L - w + k)
         const int32_t Eb = min(L, L - (int32_t)w + (int32_t)k);
         const int32_t a_lo = (int32_t)k, a_hi = Eb - (int32_t)w;            // inclusive bounds
-        uint32_t cand = 0;
+        uint32_t cand = 0, omask = 0, bmask = 0;
         {   // every thread runs this phase (threads 0,1 work on spare blocks) so that barriers stay uniform
             const int base = pidx(32 * kb);
             const int c = (int)w - 1, d = c >> 5, cr = c & 31;
-            // mask of window starts / positions of this block that are valid
-            uint32_t amask = 0, pmask = 0;
+            // masks of this block: valid window starts (amask), positions that lie in some valid window (vmask), and
+            // the part of those inside / below this tile's output range (omask / bmask).  Candidates are collected over
+            // vmask, halo included: a halo candidate can tie on the key prefix with a candidate of the output range
+            uint32_t amask = 0, vmask = 0;
             {
                 const int lo = max(a_lo - blk_pos, 0), hi = min(a_hi - blk_pos, 31);
                 if (lo <= hi) amask = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
-                // positions that lie in some valid window and in this tile's output range
-                const int plo = max(max(a_lo, D.out_lo) - blk_pos, 0);
-                const int phi = min(min(a_hi + (int)w - 1, D.out_hi - 1) - blk_pos, 31);
-                if (plo <= phi) pmask = (0xFFFFFFFFu >> (31 - phi)) & (0xFFFFFFFFu << plo);
+                const int vlo = max(a_lo - blk_pos, 0), vhi = min(a_hi + (int)w - 1 - blk_pos, 31);
+                if (vlo <= vhi) vmask = (0xFFFFFFFFu >> (31 - vhi)) & (0xFFFFFFFFu << vlo);
+                const int plo = max(D.out_lo - blk_pos, 0), phi = min(D.out_hi - 1 - blk_pos, 31);
+                if (plo <= phi) omask = (0xFFFFFFFFu >> (31 - phi)) & (0xFFFFFFFFu << plo);
+                const int bhi = min(D.out_lo - 1 - blk_pos, 31);
+                if (bhi >= 0) bmask = 0xFFFFFFFFu >> (31 - bhi);
             }
-            if (tid < L0_CTX) pmask = 0;
+            if (tid < L0_CTX) vmask = 0;
             if (w > 32) {
                 // van Herk / Gil-Werman with one 32-position block per thread
                 uint32_t m[32];
@@ -432,16 +443,17 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                         if (M == s.H[base + o]) cand |= 1u << o;
                     }
                 }
-                cand &= pmask;
+                cand &= vmask;
             } else {
                 // small windows: direct evaluation (w <= 32); w is uniform, so no barrier mismatch with the branch above
                 for (int o = 0; o < 32; o++) {
-                    if (!((pmask >> o) & 1u)) continue;
+                    if (!((vmask >> o) & 1u)) continue;
                     const int q = 32 * kb + o;
                     const uint32_t hq = s.H[pidx(q)];
-                    // l / r = run of neighbours with H >= hq inside the valid position range
+                    // l / r = run of neighbours with H >= hq inside the valid position range (and inside the tile's keys:
+                    // a halo position may be under-counted, which only matters for windows that leave the tile)
                     const int pos = blk_pos + o;
-                    const int maxl = min((int)w - 1, pos - a_lo), maxr = min((int)w - 1, (a_hi + (int)w - 1) - pos);
+                    const int maxl = min(min((int)w - 1, pos - a_lo), q), maxr = min(min((int)w - 1, (a_hi + (int)w - 1) - pos), L0_KPOS - 1 - q);
                     int l = 0, r = 0;
                     while (l < maxl && s.H[pidx(q - l - 1)] >= hq) l++;
                     while (r < maxr && s.H[pidx(q + r + 1)] >= hq) r++;
@@ -450,21 +462,25 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             }
         }
 
-        // ---- phase 4: ordered list of the candidates ----------------------------------------------------------
+        // ---- phase 4: ordered list of the candidates (halo included) -----------------------------------------------
+        // one scan carries three counts: all candidates, those below the output range, those inside it
         const uint32_t cnt = __popc(cand);
-        uint32_t incl = cnt;
+        uint64_t incl = (uint64_t)cnt | ((uint64_t)__popc(cand & bmask) << 21) | ((uint64_t)__popc(cand & omask) << 42);
 #pragma unroll
         for (int dlt = 1; dlt < 32; dlt <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, dlt);
+            const uint64_t v = __shfl_up_sync(0xFFFFFFFFu, incl, dlt);
             if (lane >= dlt) incl += v;
         }
         if (lane == 31) s.wsum[warp] = incl;
         __syncthreads();
-        uint32_t wbase = 0, total = 0;
+        uint64_t wbase = 0, tot3 = 0;
 #pragma unroll
-        for (int i = 0; i < L0_NT / 32; i++) { const uint32_t v = s.wsum[i]; if (i < warp) wbase += v; total += v; }
+        for (int i = 0; i < L0_NT / 32; i++) { const uint64_t v = s.wsum[i]; if (i < warp) wbase += v; tot3 += v; }
+        const uint32_t total = (uint32_t)tot3 & 0x1FFFFFu;            // all candidates
+        const uint32_t lo_idx = (uint32_t)(tot3 >> 21) & 0x1FFFFFu;   // list index of the first one in the output range
+        const uint32_t n_in = (uint32_t)(tot3 >> 42);                 // candidates in the output range
         {
-            uint32_t dst = wbase + incl - cnt, rem = cand;
+            uint32_t dst = ((uint32_t)(wbase + incl) & 0x1FFFFFu) - cnt, rem = cand;
             while (rem) {
                 const int o = __ffs(rem) - 1;
                 rem &= rem - 1;
@@ -473,24 +489,24 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         }
         __syncthreads();
 
-        // ---- phase 5: candidates that tie on the 32-bit prefix with a neighbouring candidate: exact 64-bit test --
-        for (uint32_t j = tid; j < total; j += L0_NT) {
-            const int q = list[j];
+        // ---- phase 5: candidates that tie on the key prefix with a neighbouring candidate: exact 64-bit test -----------
+        // A candidate without such a tie is the strict minimum of one of its windows, hence selected.  One with a tie
+        // (the other may sit in the halo) is tested exactly; a rejected one is marked (bit 15) and dropped below.
+        for (uint32_t j = lo_idx + tid; j < lo_idx + n_in; j += L0_NT) {
+            const int q = list[j] & 0x7FFF;
             const uint32_t hq = s.H[pidx(q)];
             bool tie = false;
-            for (int jj = (int)j - 1; jj >= 0 && q - (int)list[jj] < (int)w && !tie; jj--) tie = (s.H[pidx(list[jj])] == hq);
-            for (uint32_t jj = j + 1; jj < total && (int)list[jj] - q < (int)w && !tie; jj++) tie = (s.H[pidx(list[jj])] == hq);
-            if (tie && !selected_exact(s, q, q + keys_start, (int)w, a_lo, a_hi, k)) D.any_reject = 1u + j;  // any value != 0
+            for (int jj = (int)j - 1; jj >= 0 && q - (int)(list[jj] & 0x7FFF) < (int)w && !tie; jj--) tie = (s.H[pidx(list[jj] & 0x7FFF)] == hq);
+            for (uint32_t jj = j + 1; jj < total && (int)(list[jj] & 0x7FFF) - q < (int)w && !tie; jj++) tie = (s.H[pidx(list[jj] & 0x7FFF)] == hq);
+            if (tie && !selected_exact(s, q, q + keys_start, (int)w, a_lo, a_hi, k)) { list[j] = (uint16_t)(q | 0x8000); D.any_reject = 1u; }
         }
         __syncthreads();
-        uint32_t n_list = total;
-        if (D.any_reject) {   // rare: re-evaluate every candidate exactly and rebuild the list (single thread)
+        uint16_t *const olist = list + lo_idx;   // the output range is a contiguous part of the position-ordered list
+        uint32_t n_list = n_in;
+        if (D.any_reject) {   // rare: drop the marked entries
             if (tid == 0) {
                 uint32_t o = 0;
-                for (uint32_t j = 0; j < total; j++) {
-                    const int q = list[j];
-                    if (selected_exact(s, q, q + keys_start, (int)w, a_lo, a_hi, k)) list[o++] = (uint16_t)q;
-                }
+                for (uint32_t j = 0; j < n_in; j++) if (!(olist[j] & 0x8000)) olist[o++] = olist[j];
                 s.n_list = o;
             }
             __syncthreads();
@@ -517,7 +533,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                     for (int j = qa + 1; j <= qe; j++) if (key_lt(s, j, best, k)) best = j;
                     for (int j = qa; j <= qe; j++) {
                         if (!key_lt(s, best, j, k)) {  // x[j] == min
-                            if (n_list + n < (uint32_t)L0_LISTCAP) list[n_list + n] = (uint16_t)j;
+                            if (lo_idx + n_list + n < (uint32_t)L0_LISTCAP) olist[n_list + n] = (uint16_t)j;
                             n++;
                             q = j + keys_start;
                         }
@@ -531,10 +547,10 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         const uint32_t n_all = n_list + n_tail;
 
         // ---- phase 7: rebuild the full MM128 of every selected position and write it (coalesced) -------------
-        for (uint32_t j = tid; j < min(n_all, (uint32_t)L0_LISTCAP); j += L0_NT) {
+        for (uint32_t j = tid; j < min(n_all, (uint32_t)L0_LISTCAP - lo_idx); j += L0_NT) {
             const uint64_t dst = running + j;
             if (dst >= p.chunk_cap) break;
-            const int q = list[j];
+            const int q = olist[j];
             uint32_t strand;
             const uint64_t h = hash_at(s, q, k, strand);
             pgr_mm128 mm;
@@ -544,7 +560,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         }
         if (tid == 0) {
             atomicAdd(&p.seq_count[D.seq_id], n_all);
-            if (D.bad || n_all > (uint32_t)L0_LISTCAP) atomicOr(&p.seq_flag[D.seq_id], 1u);
+            if (D.bad || lo_idx + n_all > (uint32_t)L0_LISTCAP) atomicOr(&p.seq_flag[D.seq_id], 1u);
         }
         running += n_all;
         __syncthreads();  // tile fully consumed before its smem is reused
