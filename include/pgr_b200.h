@@ -42,6 +42,15 @@ typedef struct { uint32_t qb, qe, tb, te; uint8_t qo, to; uint8_t pad_[2]; } pgr
 /* graph_utils.rs:47-52 AdjPair (sid, ShmmrGraphNode a, ShmmrGraphNode b) */
 typedef struct { uint32_t sid; uint8_t ori0, ori1, pad_[2]; uint64_t a0, a1, b0, b1; } pgr_adj_pair;
 
+/* graph_utils.rs:47 ShmmrGraphNode (hash0, hash1, orientation) */
+typedef struct { uint64_t h0, h1; uint8_t ori; uint8_t pad_[7]; } pgr_graph_node;
+/* seq_db.rs:1001-1010 PBundleNode (node, Option<previous_node>, node_weight, is_leaf, global_rank, branch, branch_rank) */
+typedef struct {
+    pgr_graph_node node, prev;
+    uint8_t has_prev, is_leaf, pad_[2];
+    uint32_t weight, rank, branch, branch_rank, pad2_;
+} pgr_dfs_node;
+
 /* query_fragment_to_hps arguments (aln.rs:147-158); Option<u32> is encoded as a negative value = None */
 typedef struct {
     float penalty;
@@ -163,6 +172,18 @@ int pgr_b200_sparse_aln(pgr_hit_pair *hits, size_t n, uint32_t max_span, float p
  * encodes None */
 int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *keeps, size_t n_keeps, int has_keeps, pgr_adj_pair **out,
                       size_t *n_out);
+
+/* ---- MAP-graph traversal (host-side walks in the reference too; vertex weights come from the device index) ------ */
+/* replaces seq_db::sort_adj_list_by_weighted_dfs(&frag_map, &adj_list, start) -> Vec<PBundleNode> (seq_db.rs:1013-1061,
+ * walking graph_utils.rs:63-290 BiDiGraphWeightedDfs).  PGR_E_ASSERT when start is not a vertex ("Node not found",
+ * graph_utils.rs:107) or a vertex is not a key of the index (seq_db.rs:1031). */
+int pgr_b200_sort_adj_list_by_weighted_dfs(pgr_b200_index *idx, const pgr_adj_pair *adj, size_t n_adj, const pgr_graph_node *start,
+                                           pgr_dfs_node **out, size_t *n_out);
+/* replaces seq_db::get_principal_bundles_from_adj_list(&frag_map, &adj_list, path_len_cutoff) -> (Vec<Vec<ShmmrGraphNode>>,
+ * AdjList) (seq_db.rs:1063-1186): bundle b owns vertices[bundle_off[b] .. bundle_off[b+1]) (longest first, stable), plus the
+ * adjacency pairs between vertices of the long paths.  PGR_E_ASSERT on an empty adjacency list (seq_db.rs:1068). */
+int pgr_b200_principal_bundles(pgr_b200_index *idx, const pgr_adj_pair *adj, size_t n_adj, size_t path_len_cutoff, pgr_graph_node **vertices,
+                               uint64_t **bundle_off, size_t *n_bundles, pgr_adj_pair **filtered, size_t *n_filtered);
 
 #ifdef __cplusplus
 }

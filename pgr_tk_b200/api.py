@@ -13,6 +13,10 @@ MM128 = np.dtype([("x", "<u8"), ("y", "<u8")])
 SIG = np.dtype([("frg_id", "<u4"), ("sid", "<u4"), ("bgn", "<u4"), ("end", "<u4"), ("ori", "u1"), ("pad", "u1", 3)])
 QPAIR = np.dtype([("h0", "<u8"), ("h1", "<u8"), ("bgn", "<u4"), ("end", "<u4"), ("ori", "u1"), ("pad", "u1", 7)])
 HITPAIR = np.dtype([("qb", "<u4"), ("qe", "<u4"), ("tb", "<u4"), ("te", "<u4"), ("qo", "u1"), ("to", "u1"), ("pad", "u1", 2)])
+GNODE = np.dtype([("h0", "<u8"), ("h1", "<u8"), ("ori", "u1"), ("pad", "u1", 7)])
+DFSNODE = np.dtype([("node", GNODE), ("prev", GNODE), ("has_prev", "u1"), ("is_leaf", "u1"), ("pad", "u1", 2),
+                    ("weight", "<u4"), ("rank", "<u4"), ("branch", "<u4"), ("branch_rank", "<u4"), ("pad2", "<u4")])
+assert GNODE.itemsize == 24 and DFSNODE.itemsize == 72
 ADJ = np.dtype([("sid", "<u4"), ("ori0", "u1"), ("ori1", "u1"), ("pad", "u1", 2),
                 ("a0", "<u8"), ("a1", "<u8"), ("b0", "<u8"), ("b1", "<u8")])
 
@@ -109,6 +113,8 @@ def lib():
         L.pgr_b200_query_result_free.argtypes = [P(QueryResult)]
         L.pgr_b200_sparse_aln.argtypes = [vp, sz, u32, C.c_float, C.c_int64, C.c_int, P(sz), P(vp), P(vp), P(vp)]
         L.pgr_b200_adj_list.argtypes = [vp, sz, vp, sz, C.c_int, P(vp), P(sz)]
+        L.pgr_b200_sort_adj_list_by_weighted_dfs.argtypes = [vp, vp, sz, vp, P(vp), P(sz)]
+        L.pgr_b200_principal_bundles.argtypes = [vp, vp, sz, sz, P(vp), P(vp), P(sz), P(vp), P(sz)]
         _lib = L
     return _lib
 
@@ -393,6 +399,33 @@ class ShmmrIndex:
         out, n = C.c_void_p(), C.c_size_t()
         _check(lib().pgr_b200_adj_list(self.h, min_count, k.ctypes.data, k.size, int(keeps is not None), C.byref(out), C.byref(n)))
         return _take(out, n.value, ADJ)
+
+    def sort_adj_list_by_weighted_dfs(self, adj, start):
+        """seq_db::sort_adj_list_by_weighted_dfs (seq_db.rs:1013-1061); start = (h0, h1, ori) -> DFSNODE[...]"""
+        a = np.ascontiguousarray(adj, dtype=ADJ)
+        st = np.zeros(1, dtype=GNODE)
+        st["h0"], st["h1"], st["ori"] = start
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(lib().pgr_b200_sort_adj_list_by_weighted_dfs(self.h, a.ctypes.data, a.size, st.ctypes.data, C.byref(out), C.byref(n)))
+        return _take(out, n.value, DFSNODE)
+
+    def get_principal_bundles_from_adj_list(self, adj, path_len_cutoff):
+        """seq_db::get_principal_bundles_from_adj_list (seq_db.rs:1063-1186) -> (list of GNODE arrays, filtered ADJ[...])"""
+        a = np.ascontiguousarray(adj, dtype=ADJ)
+        v, off, flt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nb, nf = C.c_size_t(), C.c_size_t()
+        _check(lib().pgr_b200_principal_bundles(self.h, a.ctypes.data, a.size, path_len_cutoff, C.byref(v), C.byref(off), C.byref(nb),
+                                                C.byref(flt), C.byref(nf)))
+        off_a = _take(off, nb.value + 1, np.uint64)
+        verts = _take(v, int(off_a[-1]), GNODE)
+        return [verts[int(off_a[i]):int(off_a[i + 1])] for i in range(nb.value)], _take(flt, nf.value, ADJ)
+
+    def get_principal_bundles(self, min_count, path_len_cutoff, keeps=None):
+        """SeqIndexDB::get_principal_bundles (ext.rs:491-510): [] when the adjacency list is empty"""
+        adj = self.adj_list(min_count, keeps)
+        if adj.size == 0:
+            return []
+        return self.get_principal_bundles_from_adj_list(adj, path_len_cutoff)[0]
 
 
 def sparse_aln(hits, max_span, penalty, max_gap=None, oriented=False):

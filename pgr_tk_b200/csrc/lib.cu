@@ -2,3 +2,4 @@
 #include "ctx.cu"
 #include "index.cu"
 #include "query.cu"
+#include "bundles.cu"
