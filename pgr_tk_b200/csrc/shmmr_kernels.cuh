@@ -160,15 +160,24 @@ __device__ __noinline__ bool selected_exact(const L0Smem &s, int q, int pos, int
     return l + r + 1 >= w;
 }
 
-// tile -> descriptor (executed by one thread)
-__device__ __forceinline__ void make_tile_desc(const L0Params &p, uint32_t tile, uint32_t w, L0Smem::TileDesc &d) {
-    // (sequence, tile index): largest sid with tile_prefix[sid] <= tile
-    uint32_t lo = 0, hi = p.n_seq;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (p.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+// tile -> descriptor (executed by one thread).  sid_hint = sequence of the previous tile of this CTA (tiles are handed
+// out in order, so the next tile belongs to the same sequence or to one shortly after it: no binary search, whose ten
+// dependent loads would keep the whole CTA waiting at the next barrier); UINT32_MAX = none (first tile of the CTA).
+__device__ __forceinline__ uint32_t make_tile_desc(const L0Params &p, uint32_t tile, uint32_t w, L0Smem::TileDesc &d, uint32_t sid_hint) {
+    uint32_t sid;
+    if (sid_hint != 0xFFFFFFFFu) {
+        sid = sid_hint;
+        while (p.tile_prefix[sid + 1] <= tile) sid++;   // sequences without tiles (L <= k) are skipped
+    } else {
+        // (sequence, tile index): largest sid with tile_prefix[sid] <= tile
+        uint32_t lo = 0, hi = p.n_seq;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+        }
+        sid = lo;
     }
-    const uint32_t sid = lo, j = tile - p.tile_prefix[sid];
+    const uint32_t j = tile - p.tile_prefix[sid];
     const uint32_t L = p.len[sid];
     const uint32_t nt = p.tile_prefix[sid + 1] - p.tile_prefix[sid];
     int32_t ks = (int32_t)(j * p.tile_stride) - (int32_t)p.halo;
@@ -183,6 +192,7 @@ __device__ __forceinline__ void make_tile_desc(const L0Params &p, uint32_t tile,
     d.out_hi = (int32_t)min((uint64_t)L, (uint64_t)(j + 1) * p.tile_stride);
     d.seq_off = p.off[sid];
     d.bad = 0; d.n_tail = 0; d.any_reject = 0;
+    return sid;
 }
 
 // cold path of the key loop: a pushed palindrome (not pushed by the reference); the neighbourhood is re-derived by
@@ -228,7 +238,8 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
     for (int i = tid; i < L0_ARR; i += L0_NT) { s.H[i] = 0; s.P[i] = 0; }
 
     // first tile: descriptor + this thread's 32 bases
-    if (tid == 0 && t_begin < t_end) make_tile_desc(p, t_begin, w, s.td[0]);
+    uint32_t desc_sid = 0xFFFFFFFFu;   // thread 0: sequence of the newest descriptor
+    if (tid == 0 && t_begin < t_end) desc_sid = make_tile_desc(p, t_begin, w, s.td[0], desc_sid);
     __syncthreads();
     uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
     if (t_begin < t_end) {
@@ -242,7 +253,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
     for (uint32_t tile = t_begin; tile < t_end; ++tile, cur ^= 1) {
         L0Smem::TileDesc &D = s.td[cur];
         const bool has_next = tile + 1 < t_end;
-        if (tid == 0 && has_next) make_tile_desc(p, tile + 1, w, s.td[cur ^ 1]);   // overlaps with phases 1-2 of this tile
+        if (tid == 0 && has_next) desc_sid = make_tile_desc(p, tile + 1, w, s.td[cur ^ 1], desc_sid);   // overlaps with phases 1-2 of this tile
         const int32_t L = (int32_t)D.seq_len;
         const int32_t keys_start = D.keys_start;
         const int32_t blk_pos = keys_start + 32 * (tid - L0_CTX);  // sequence position of this thread's first base
