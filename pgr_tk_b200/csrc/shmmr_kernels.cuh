@@ -93,7 +93,7 @@ struct L0Smem {
     uint32_t F0[L0_NT + 8], F1[L0_NT + 8];   // bit planes per 32-base block, first base in the MOST significant bit;
                                              // the complement planes (first base in the LEAST significant bit) are ~brev()
     uint32_t bext[L0_KB + 2 * L0_PADB];   // block min (pass 1) / block max (pass 2)
-    uint64_t wsum[L0_NT / 32];
+    alignas(16) uint32_t wsum[(L0_NT / 32 + 3) / 4 * 4];
     uint32_t n_list;
     // tile descriptors, double-buffered: thread 0 prepares tile t+1 while the CTA works on tile t, and every thread
     // issues its 32-byte load for tile t+1 before the key loop of tile t (software prefetch across tiles)
@@ -103,7 +103,9 @@ struct L0Smem {
         int32_t out_lo, out_hi;  // output position range [out_lo, out_hi)
         uint32_t is_last;
         uint32_t bad;            // tile saw an invalid byte (or lost a palindrome record)
-        uint32_t n_tail, any_reject, pad_;
+        uint32_t n_tail, any_reject;
+        uint32_t n_pre, n_post;  // candidates below / above the output range (phase 4)
+        uint32_t pad_;
         uint64_t seq_off;
     } td[2];
 };
@@ -138,6 +140,37 @@ __device__ __forceinline__ uint64_t hash_at(const L0Smem &s, int q, uint32_t k, 
     const bool rev = r.r0 < r.f0;
     strand = rev ? 1u : 0u;
     return rev ? (u64hash(r.r0) ^ u64hash(r.r1 ^ HASH_XOR)) : (u64hash(r.f0) ^ u64hash(r.f1 ^ HASH_XOR));
+}
+// the same for the K > 32 kernels with the arithmetic of the fast key loop (top word X of each strand, 32-bit halves,
+// IMAD.WIDE hash): phase 7 runs it once per selected position, ~100 instructions instead of ~200
+template <int K>
+__device__ __forceinline__ uint64_t hash_at_fast(const L0Smem &s, int q, uint32_t &strand) {
+    constexpr uint32_t PS = K - 32, HS = 64 - K;
+    constexpr uint32_t cp = 65u - K, cs = cp >> 5, cb = cp & 31;
+    const int t = (q >> 5) + L0_CTX, i = q & 31;
+    const uint32_t sh = 31 - i;
+    const int g = t - 2 + (int)cs;
+    // plane 0, both strands: (X, lo) orders like the K-bit register
+    const uint32_t a0 = s.F0[t], a1 = s.F0[t - 1], a2 = s.F0[t - 2];
+    const uint32_t ra0 = rplane(s.F0, g), ra1 = rplane(s.F0, g + 1), ra2 = rplane(s.F0, g + 2), ra3 = rplane(s.F0, g + 3);
+    const uint32_t q00 = fsr(ra0, ra1, cb), q01 = fsr(ra1, ra2, cb), q02 = fsr(ra2, ra3, cb);
+    const uint32_t f0lo = fsr(a0, a1, sh), f0x = fsr(fsr(a0, a1, PS), fsr(a1, a2, PS), sh);
+    const uint32_t r0lo = fsr(q00, q01, i), r0x = fsr(fsr(q00, q01, PS), fsr(q01, q02, PS), i);
+    const bool rev = (r0x < f0x) || (r0x == f0x && r0lo < f0lo);   // rmmer.0 < fmmer.0 (shmmrutils.rs:486)
+    strand = rev ? 1u : 0u;
+    uint32_t ulo = rev ? r0lo : f0lo, uhi = (rev ? r0x : f0x) >> HS;
+    // plane 1 of the chosen strand only
+    uint32_t x0, x1, x2, amt;
+    if (rev) {
+        const uint32_t rb0 = rplane(s.F1, g), rb1 = rplane(s.F1, g + 1), rb2 = rplane(s.F1, g + 2), rb3 = rplane(s.F1, g + 3);
+        x0 = fsr(rb0, rb1, cb); x1 = fsr(rb1, rb2, cb); x2 = fsr(rb2, rb3, cb); amt = (uint32_t)i;
+    } else {
+        x0 = s.F1[t]; x1 = s.F1[t - 1]; x2 = s.F1[t - 2]; amt = sh;
+    }
+    uint32_t vlo = fsr(x0, x1, amt) ^ (uint32_t)HASH_XOR, vhi = fsr(fsr(x0, x1, PS), fsr(x1, x2, PS), amt) >> HS;
+    u64hash_dev32(ulo, uhi);
+    u64hash_dev32(vlo, vhi);
+    return ((uint64_t)(uhi ^ vhi) << 32) | (ulo ^ vlo);
 }
 // exact compare x[qa] < x[qb] (x = hash << 8 | k): 32-bit prefix first, the remaining 24 bits only on a prefix tie
 __device__ __noinline__ bool key_lt_slow(const L0Smem &s, int qa, int qb, uint32_t k) {
@@ -191,7 +224,7 @@ __device__ __forceinline__ uint32_t make_tile_desc(const L0Params &p, uint32_t t
     d.out_lo = (int32_t)(j * p.tile_stride);
     d.out_hi = (int32_t)min((uint64_t)L, (uint64_t)(j + 1) * p.tile_stride);
     d.seq_off = p.off[sid];
-    d.bad = 0; d.n_tail = 0; d.any_reject = 0;
+    d.bad = 0; d.n_tail = 0; d.any_reject = 0; d.n_pre = 0; d.n_post = 0;
     return sid;
 }
 
@@ -235,6 +268,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
 
     // spare blocks of the exchange arrays are never written with real data; give them harmless values once
     for (int i = tid; i < L0_KB + 2 * L0_PADB; i += L0_NT) s.bext[i] = 0;
+    if (tid < (int)(sizeof(s.wsum) / sizeof(uint32_t))) s.wsum[tid] = 0;   // padding entries stay 0
     for (int i = tid; i < L0_ARR; i += L0_NT) { s.H[i] = 0; s.P[i] = 0; }
 
     // first tile: descriptor + this thread's 32 bases
@@ -474,24 +508,37 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         }
 
         // ---- phase 4: ordered list of the candidates (halo included) -----------------------------------------------
-        // one scan carries three counts: all candidates, those below the output range, those inside it
+        // block-wide scan of the candidate counts; the few candidates below / above the output range (halo blocks only)
+        // are counted with shared-memory atomics: the list is position-ordered, so the output range is list[n_pre, n_pre + n_in)
         const uint32_t cnt = __popc(cand);
-        uint64_t incl = (uint64_t)cnt | ((uint64_t)__popc(cand & bmask) << 21) | ((uint64_t)__popc(cand & omask) << 42);
+        {
+            const uint32_t c_pre = __popc(cand & bmask), c_post = __popc(cand & ~(omask | bmask));
+            if (c_pre) atomicAdd(&D.n_pre, c_pre);
+            if (c_post) atomicAdd(&D.n_post, c_post);
+        }
+        uint32_t incl = cnt;
 #pragma unroll
         for (int dlt = 1; dlt < 32; dlt <<= 1) {
-            const uint64_t v = __shfl_up_sync(0xFFFFFFFFu, incl, dlt);
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, dlt);
             if (lane >= dlt) incl += v;
         }
         if (lane == 31) s.wsum[warp] = incl;
         __syncthreads();
-        uint64_t wbase = 0, tot3 = 0;
-#pragma unroll
-        for (int i = 0; i < L0_NT / 32; i++) { const uint64_t v = s.wsum[i]; if (i < warp) wbase += v; tot3 += v; }
-        const uint32_t total = (uint32_t)tot3 & 0x1FFFFFu;            // all candidates
-        const uint32_t lo_idx = (uint32_t)(tot3 >> 21) & 0x1FFFFFu;   // list index of the first one in the output range
-        const uint32_t n_in = (uint32_t)(tot3 >> 42);                 // candidates in the output range
+        uint32_t wbase = 0, total = 0;
         {
-            uint32_t dst = ((uint32_t)(wbase + incl) & 0x1FFFFFu) - cnt, rem = cand;
+            const uint4 *wv = reinterpret_cast<const uint4 *>(s.wsum);
+#pragma unroll
+            for (int i = 0; i < (L0_NT / 32 + 3) / 4; i++) {
+                const uint4 v = wv[i];
+                const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) { if (4 * i + j < warp) wbase += e[j]; total += e[j]; }
+            }
+        }
+        const uint32_t lo_idx = D.n_pre;                       // list index of the first candidate in the output range
+        const uint32_t n_in = total - D.n_pre - D.n_post;      // candidates in the output range
+        {
+            uint32_t dst = wbase + incl - cnt, rem = cand;
             while (rem) {
                 const int o = __ffs(rem) - 1;
                 rem &= rem - 1;
@@ -563,7 +610,8 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             if (dst >= p.chunk_cap) break;
             const int q = olist[j];
             uint32_t strand;
-            const uint64_t h = hash_at(s, q, k, strand);
+            uint64_t h;
+            if constexpr (K > 32) h = hash_at_fast<K>(s, q, strand); else h = hash_at(s, q, k, strand);
             pgr_mm128 mm;
             mm.x = (h << 8) | k;
             mm.y = ((uint64_t)D.seq_id << 32) | ((uint64_t)(uint32_t)(q + keys_start) << 1) | strand;
