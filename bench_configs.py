@@ -292,9 +292,15 @@ def config5(pg, orc, scale):
     parity = len(adj) == len(oadj) and all(np.array_equal(adj[f], oadj[f]) for f in names)
     adj2, oadj2 = g.adj_list(3, [0, 5]), o.adj_list(3, [0, 5])
     parity = parity and len(adj2) == len(oadj2) and all(np.array_equal(adj2[f], oadj2[f]) for f in names)
+    # principal bundles (pgr-pbundle-decomp defaults: min_cov 0, min_branch_size 8): host-side walk over the GPU adjacency list
+    t0 = time.perf_counter()
+    bundles, flt = g.get_principal_bundles_from_adj_list(adj, 8)
+    pb_s = time.perf_counter() - t0
     emit({"config": 5, "workload": "shimmers + ShmmrFragMap + frag_map_to_adj_list, 94 haplotypes of a repetitive locus (%.1f Mbases), 48/56/4/12" % (sum(map(len, haps)) / 1e6),
           "n_gpus": 1, "ms": min(times) * 1e3, "value": sum(map(len, haps)) / min(times) / 1e9, "unit": "Gbases/s", "adj_pairs": int(len(adj)),
           "n_sigs": g.counts()[1], "adjlist_bit_exact_vs_oracle": bool(parity),
+          "principal_bundles": {"ms": pb_s * 1e3, "n_bundles": len(bundles), "vertices": int(sum(len(b) for b in bundles)), "filtered_adj_pairs": int(len(flt)),
+                                "note": "sequential graph walk on the host as in the reference (seq_db.rs:1063-1186); parity unpinned (petgraph orders), tests compare with oracle/bundles_oracle.py"},
           "cpu_baseline": {"ms": cpu_s * 1e3, "cores": host_cores(), "kind": "port", "sample": "the whole config (oracle, all cores for shimmers)"}})
     assert parity
 
