@@ -3,6 +3,7 @@
 #include <zlib.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace pgrb200 {
@@ -79,6 +80,7 @@ int SeqIndexDB::load_from_fastx(const std::string &path, uint32_t w, uint32_t k,
     spec_.w = w; spec_.k = k; spec_.r = r; spec_.min_span = min_span; spec_.sketch = 0;
     if (idx_) { pgr_b200_index_free(idx_); idx_ = nullptr; }
     seqs_.clear();
+    seq_data_.clear();
     idx_ = pgr_b200_index_new(&spec_, 0 /* FASTX fragment numbering */, -1);
     if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
     return load_seqs_from_fastx(path);
@@ -109,6 +111,51 @@ int SeqIndexDB::load_seqs_from_fastx(const std::string &path) {
     // one GPU call per file: the batch boundary (129 records) only sets the reference's parallel granularity, it has
     // no effect on results (fragment ids are a running counter across batches)
     const int rc = pgr_b200_index_add_batch(idx_, recs.size(), sids.data(), ptrs.data(), lens.data());
+    if (rc != PGR_OK) err_ = pgr_b200_last_error();
+    if (keep_seqs_) for (auto &r : recs) seq_data_.push_back(std::move(r.seq));
+    return rc;
+}
+
+int SeqIndexDB::load_from_index_files(const std::string &prefix) {
+    if (idx_) { pgr_b200_index_free(idx_); idx_ = nullptr; }
+    seqs_.clear();
+    seq_data_.clear();
+    idx_ = pgr_b200_index_read_mdb((prefix + ".mdb").c_str(), -1);
+    if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_IO; }
+    pgr_b200_index_get_spec(idx_, &spec_);
+    FILE *f = fopen((prefix + ".midx").c_str(), "rb");
+    if (!f) { err_ = "cannot open " + prefix + ".midx"; return PGR_E_IO; }
+    char *line = nullptr;
+    size_t cap = 0;
+    ssize_t n;
+    while ((n = getline(&line, &cap, f)) > 0) {     // sid \t len \t ctg_name \t source (seq_db.rs:795-807)
+        std::string l(line, (size_t)n);
+        while (!l.empty() && (l.back() == '\n' || l.back() == '\r')) l.pop_back();
+        std::vector<std::string> fld;
+        size_t a = 0;
+        for (;;) { const size_t b = l.find('\t', a); fld.push_back(l.substr(a, b == std::string::npos ? b : b - a)); if (b == std::string::npos) break; a = b + 1; }
+        if (fld.size() < 4) { err_ = "malformed .midx line"; free(line); fclose(f); return PGR_E_IO; }
+        CompactSeq cs;
+        cs.id = (uint32_t)strtoul(fld[0].c_str(), nullptr, 10); cs.len = strtoull(fld[1].c_str(), nullptr, 10); cs.name = fld[2]; cs.source = fld[3];
+        seqs_.push_back(std::move(cs));
+    }
+    free(line);
+    fclose(f);
+    return PGR_OK;
+}
+
+bool SeqIndexDB::get_sub_seq_by_id(uint32_t sid, size_t bgn, size_t end, std::vector<uint8_t> &out) const {
+    if (sid >= seq_data_.size() || bgn > end || end > seq_data_[sid].size()) return false;
+    out.assign(seq_data_[sid].begin() + (ptrdiff_t)bgn, seq_data_[sid].begin() + (ptrdiff_t)end);
+    return true;
+}
+
+int SeqIndexDB::query_fragment_to_hps(const std::vector<SeqRec> &queries, const pgr_query_params &params, pgr_query_result **out) {
+    if (!idx_) { err_ = "no index"; return PGR_E_ARG; }
+    std::vector<const uint8_t *> ptrs;
+    std::vector<size_t> lens;
+    for (auto &q : queries) { ptrs.push_back(q.seq.data()); lens.push_back(q.seq.size()); }
+    const int rc = pgr_b200_query_batch(idx_, queries.size(), ptrs.data(), lens.data(), &params, out);
     if (rc != PGR_OK) err_ = pgr_b200_last_error();
     return rc;
 }

@@ -4,6 +4,8 @@
 //   SeqIndexDB         ext.rs:48-64,152-199 load_from_fastx / append_from_fastx (FASTX back end, index part)
 //                      seq_db.rs:471-525 record batching (<=129 records per call), sid = running record index
 //                      seq_db.rs:790-810 write_shmmr_map_index (.mdb + .midx)
+//                      ext.rs:87-150 load_from_*_index, index part (.mdb + .midx read back; no sequence store)
+//                      ext.rs:252-282 query_fragment_to_hps (batched), ext.rs:455-489 get_sub_seq_by_id (FASTX back end)
 #pragma once
 #include <cstdint>
 #include <string>
@@ -30,6 +32,16 @@ public:
     int load_from_fastx(const std::string &path, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span);
     // ext.rs:180-199
     int append_from_fastx(const std::string &path);
+    // index part of ext.rs:87-150 (load_from_agc_index / load_from_frg_index): <prefix>.mdb + <prefix>.midx; sequences are
+    // not available afterwards (the .agc / .frg stores are out of scope)
+    int load_from_index_files(const std::string &prefix);
+    // keep the sequences of load_from_fastx in host memory (needed by get_sub_seq_by_id); set before loading
+    void keep_sequences(bool on) { keep_seqs_ = on; }
+    // ext.rs:455-489 for the FASTX back end: seq[bgn..end); false when the sequence is not held
+    bool get_sub_seq_by_id(uint32_t sid, size_t bgn, size_t end, std::vector<uint8_t> &out) const;
+    // ext.rs:252-282 for a batch of queries (pgr-query.rs:135 runs one rayon task per query); result freed by the caller
+    // with pgr_b200_query_result_free
+    int query_fragment_to_hps(const std::vector<SeqRec> &queries, const pgr_query_params &params, pgr_query_result **out);
     // seq_db.rs:790-810 (index part of ext.rs:201-207 write_frag_and_index_files)
     int write_shmmr_map_index(const std::string &prefix);
     const std::vector<CompactSeq> &seqs() const { return seqs_; }
@@ -41,6 +53,8 @@ private:
     pgr_b200_index *idx_ = nullptr;
     pgr_shmmr_spec spec_{};
     std::vector<CompactSeq> seqs_;
+    std::vector<std::vector<uint8_t>> seq_data_;
+    bool keep_seqs_ = false;
     std::string err_;
 };
 

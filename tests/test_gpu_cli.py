@@ -54,3 +54,87 @@ def test_make_frgdb_cli_append_and_flags(tmp_path):
     assert len(open(prefix + ".midx").readlines()) == 68
     # the .mdb can be loaded back by the library
     assert pg.ShmmrIndex.read_mdb(prefix + ".mdb").as_map() == o.as_map()
+
+
+# ---- pgr-b200-query (pgr-query.rs) ---------------------------------------------------------------------------------------
+import sys  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import query_post_oracle as qpo  # noqa: E402
+
+QCLI = os.path.join(ROOT, "pgr_tk_b200", "pgr-b200-query")
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _write_fasta(path, recs):
+    with open(path, "w") as f:
+        for name, seq in recs:
+            f.write(">%s some description\n" % name)
+            s = seq.decode()
+            for i in range(0, len(s), 80):
+                f.write(s[i:i + 80] + "\n")
+
+
+def _oracle_targets(o, q, penalty, **kw):
+    osid, otco, osc, ocho, ohits = o.query_fragment_to_hps(q, penalty, **kw)
+    targets = []
+    for t, sid in enumerate(osid):
+        alns = []
+        for c in range(int(otco[t]), int(otco[t + 1])):
+            hp = [((int(h["qb"]), int(h["qe"]), int(h["qo"])), (int(h["tb"]), int(h["te"]), int(h["to"]))) for h in ohits[int(ocho[c]):int(ocho[c + 1])]]
+            alns.append((float(osc[c]), hp))
+        targets.append((int(sid), alns))
+    return targets
+
+
+def test_query_cli_matches_oracle_postprocessing(tmp_path):
+    if not os.path.exists(QCLI):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "pgr_tk_b200", "host")])
+    rng = np.random.default_rng(101)
+    anc = ACGT[rng.integers(0, 4, size=160000)]
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[[65, 67, 71, 84]] = [84, 71, 67, 65]
+    haps = []
+    for h in range(6):
+        s = anc.copy()
+        m = np.nonzero(rng.random(len(s)) < 2e-3)[0]
+        s[m] = ACGT[rng.integers(0, 4, size=len(m))]
+        if h % 2:     # an inversion and a large deletion: several chains / orientations per target
+            a = int(rng.integers(40000, 60000))
+            s = np.concatenate([s[:a], comp[s[a:a + 15000]][::-1], s[a + 15000:a + 40000], s[a + 70000:]])
+        haps.append(s.tobytes())
+    db_fa = str(tmp_path / "db.fa")
+    _write_fasta(db_fa, [("hap%d" % i, s) for i, s in enumerate(haps)])
+    queries = [("q_fwd", haps[0][30000:130000]), ("q_rev", bytes(comp[np.frombuffer(haps[2][20000:90000], dtype=np.uint8)][::-1])),
+               ("q_none", ACGT[rng.integers(0, 4, size=5000)].tobytes())]
+    q_fa = str(tmp_path / "q.fa")
+    _write_fasta(q_fa, queries)
+    o = orc.Index(orc.mkspec(), 0)
+    o.add_batch(list(range(len(haps))), haps)
+    seq_info = {i: ("hap%d" % i, db_fa) for i in range(len(haps))}
+    kw = dict(max_count=128, max_count_query=128, max_count_target=128, max_aln_span=8)
+    for tol, bed in ((100000, False), (1000, True)):
+        prefix = str(tmp_path / ("out_%d" % tol))
+        cmd = [QCLI, db_fa, q_fa, prefix, "--fastx-file", "--merge-range-tol", str(tol)] + (["--bed-summary"] if bed else [])
+        subprocess.check_call(cmd, cwd=ROOT)
+        n_regions = 0
+        for idx, (qn, qs) in enumerate(queries):
+            merged = qpo.merge_query_hits(_oracle_targets(o, qs, 0.025, **kw), tol)
+            text, subs = qpo.hit_lines(idx, qn, len(qs), merged, seq_info, bed=bed)
+            got = open("%s.%03d.%s" % (prefix, idx, "hit.bed" if bed else "hit")).read()
+            assert got == text, (tol, idx)
+            fa_exp = "".join(">%s\n%s\n" % (nm, (qpo.reverse_complement(haps[sid][b:e]) if ori else haps[sid][b:e]).decode()) for nm, sid, b, e, ori in subs)
+            assert open("%s.%03d.fa" % (prefix, idx)).read() == fa_exp
+            n_regions += len(subs)
+        assert n_regions >= 8
+    # index files + --only-summary (the .mdb/.midx of pgr-b200-make-frgdb read back)
+    fl = tmp_path / "files.txt"
+    fl.write_text(db_fa + "\n")
+    subprocess.check_call([CLI, str(fl), str(tmp_path / "idx")], cwd=ROOT)
+    prefix = str(tmp_path / "out_idx")
+    subprocess.check_call([QCLI, str(tmp_path / "idx"), q_fa, prefix, "--only-summary"], cwd=ROOT)
+    for idx in range(len(queries)):
+        assert open("%s.%03d.hit" % (prefix, idx)).read() == open("%s.%03d.hit" % (str(tmp_path / "out_100000"), idx)).read()
+        assert not os.path.exists("%s.%03d.fa" % (prefix, idx))
