@@ -1,0 +1,139 @@
+"""pbundle_oracle.py — TEST INFRASTRUCTURE ONLY.  Pure-Python restatement of the principal-bundle bookkeeping of
+pgr-pbundle-decomp: ext.rs:552-650 (get_principal_bundles_with_id), ext.rs:976-1015 (get_principal_bundle_decomposition),
+pgr-bin/src/bin/pgr-pbundle-decomp.rs:62-137 (group_smps_by_principle_bundle_id) and :337-529 (the .bed and
+.ctg.summary.tsv writers).  f32 arithmetic goes through numpy.float32; Rust's `{}` of an f32 is the shortest
+round-trip decimal without exponent.  PARITY UNPINNED (no reference fixture); the bundles themselves come from
+bundles_oracle.py.  A smp is (h0, h1, bgn, end, ori); a bundle vertex (h0, h1, ori).
+"""
+import numpy as np
+
+f32 = np.float32
+
+
+def f32_display(v):
+    v = f32(v)
+    if np.isnan(v):
+        return "NaN"
+    if np.isinf(v):
+        return "inf" if v > 0 else "-inf"
+    return np.format_float_positional(v, unique=True, trim="-")
+
+
+def principal_bundles_with_id(pb, smps_by_sid):
+    """ext.rs:552-650 -> ([(bundle_id, mean_order, vertices)], vertex_map {(h0,h1): (bid, ori, pos)})"""
+    vmap = {}
+    for bid, path in enumerate(pb):
+        for p, v in enumerate(path):
+            vmap[(v[0], v[1])] = (bid, v[2], p)
+    directions, orders = {}, {}
+    for sid in sorted(smps_by_sid):
+        visited = set()
+        for order, v in enumerate(smps_by_sid[sid]):
+            b = vmap.get((v[0], v[1]))
+            if b is None:
+                continue
+            if b[0] not in visited:
+                orders.setdefault(b[0], []).append(f32(order))
+                visited.add(b[0])
+            directions.setdefault(b[0], []).append(0 if b[1] == v[4] else 1)
+    mod = []
+    for bid in range(len(pb)):
+        if bid in orders:
+            s = f32(0.0)
+            for o in orders[bid]:
+                s = f32(s + o)
+            mean = int(f32(s / f32(len(orders[bid]))))
+            d = directions[bid]
+            mod.append((mean, bid, 0 if sum(d) < (len(d) >> 1) else 1))
+        else:
+            mod.append((2 ** 64 - 1, bid, 0))
+    mod.sort()
+    out = []
+    for ord_, bid, direction in mod:
+        if direction == 1:
+            rpb = [(v[0], v[1], 1 - v[2]) for v in reversed(pb[bid])]
+            for p, v in enumerate(rpb):
+                vmap[(v[0], v[1])] = (bid, v[2], p)
+            out.append((bid, ord_, rpb))
+        else:
+            out.append((bid, ord_, list(pb[bid])))
+    return out, vmap
+
+
+def group_smps(smps, vmap, cutoff, merge_distance):
+    """pgr-pbundle-decomp.rs:62-137 -> [[(smp, bid, d, bpos), ...], ...]"""
+    pre = None
+    allp, cur = [], []
+    for smp in smps:
+        info = vmap.get((smp[0], smp[1]))
+        if info is None:
+            continue
+        d = 0 if smp[4] == info[1] else 1
+        bid, bpos = info[0], info[2]
+        if pre is None:
+            cur = [(smp, bid, d, bpos)]
+            pre = (bid, d)
+            continue
+        if (bid, d) != pre:
+            if cur[-1][0][3] - cur[0][0][2] > cutoff:
+                allp.append(cur)
+            cur = []
+            pre = (bid, d)
+        cur.append((smp, bid, d, bpos))
+    if cur and cur[-1][0][3] - cur[0][0][2] > cutoff:
+        allp.append(cur)
+    if not allp:
+        return []
+    rtn = []
+    part = list(allp[0])
+    for p in allp[1:]:
+        last = part[-1]
+        if last[1] == p[0][1] and last[2] == p[0][2] and abs(p[0][0][2] - last[0][3]) < merge_distance:
+            part.extend(p)
+        else:
+            rtn.append(part)
+            part = list(p)
+    if part:
+        rtn.append(part)
+    return rtn
+
+
+def decomposition_files(cmd_string, seq_info, smps_by_sid, pbid, vmap, k, cutoff, merge_distance):
+    """seq_info = [(sid, len, ctg)]; -> (bed text, summary text)"""
+    bid_to_size = {b[0]: len(b[2]) for b in pbid}
+    order = sorted(seq_info, key=lambda t: t[2])
+    bed = ["# cmd: %s" % cmd_string]
+    rep, non = {}, {}
+    for sid, _ln, ctg in order:
+        parts = group_smps(smps_by_sid[sid], vmap, cutoff, merge_distance)
+        cnt = {}
+        for p in parts:
+            cnt[p[0][1]] = cnt.get(p[0][1], 0) + 1
+        for p in parts:
+            b, e = p[0][0][2], p[-1][0][3] + k
+            bid = p[0][1]
+            r = cnt[bid] > 1
+            (rep if r else non).setdefault(sid, []).append(e - b - k)
+            bed.append("%s\t%d\t%d\t%d:%d:%d:%d:%d:%s" % (ctg, b, e, bid, bid_to_size[bid], p[0][2], p[0][3], p[-1][3], "R" if r else "U"))
+    hdr = ["ctg", "length", "repeat_bundle_count", "repeat_bundle_sum", "repeat_bundle_percentage", "repeat_bundle_mean", "repeat_bundle_min",
+           "repeat_bundle_max", "non_repeat_bundle_count", "non_repeat_bundle_sum", "non_repeat_bundle_percentage", "non_repeat_bundle_mean",
+           "non_repeat_bundle_min", "non_repeat_bundle_max", "total_bundle_count", "total_bundle_coverage_percentage"]
+    summ = ["#" + "\t".join(hdr)]
+
+    def stats(v):
+        if not v:
+            return 0, "NA", "NA", "NA"
+        s = sum(v)
+        return s, f32_display(f32(s) / f32(len(v))), str(min(v)), str(max(v))
+
+    def pct(x, ln):
+        return f32_display(f32(f32(100.0) * f32(x)) / f32(ln))
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for sid, ln, ctg in order:
+            rv, nv = rep.get(sid, []), non.get(sid, [])
+            rs, rmean, rmin, rmax = stats(rv)
+            ns, nmean, nmin, nmax = stats(nv)
+            summ.append("\t".join(map(str, [ctg, ln, len(rv), rs, pct(rs, ln), rmean, rmin, rmax, len(nv), ns, pct(ns, ln), nmean, nmin, nmax,
+                                            len(rv) + len(nv), pct(rs + ns, ln)])))
+    return "\n".join(bed) + "\n", "\n".join(summ) + "\n"

@@ -138,3 +138,42 @@ def test_query_cli_matches_oracle_postprocessing(tmp_path):
     for idx in range(len(queries)):
         assert open("%s.%03d.hit" % (prefix, idx)).read() == open("%s.%03d.hit" % (str(tmp_path / "out_100000"), idx)).read()
         assert not os.path.exists("%s.%03d.fa" % (prefix, idx))
+
+
+# ---- pgr-b200-pbundle-decomp (pgr-pbundle-decomp.rs) ----------------------------------------------------------------------
+import bundles_oracle as bo  # noqa: E402
+import pbundle_oracle as pbo  # noqa: E402
+
+PCLI = os.path.join(ROOT, "pgr_tk_b200", "pgr-b200-pbundle-decomp")
+
+
+def test_pbundle_decomp_cli_matches_oracle(tmp_path):
+    if not os.path.exists(PCLI):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "pgr_tk_b200", "host")])
+    from test_gpu_bundles import repetitive_locus
+    haps = repetitive_locus(29, 10, n_units=5, unit_len=7000, flank=25000)
+    fa = str(tmp_path / "locus.fa")
+    _write_fasta(fa, [("hap_%02d" % (len(haps) - i), s) for i, s in enumerate(haps)])     # names sort differently from sids
+    spec_t = (48, 56, 4, 12)
+    o = orc.Index(orc.mkspec(*spec_t), 0)
+    o.add_batch(list(range(len(haps))), haps)
+    keys, offs, _ = o.export()
+    kk = keys.reshape(-1, 2)
+    cnt = {(int(kk[i, 0]), int(kk[i, 1])): int(offs[i + 1] - offs[i]) for i in range(len(kk))}
+    adj = o.adj_list(0)
+    adj_t = [(int(r["sid"]), (int(r["a0"]), int(r["a1"]), int(r["ori0"])), (int(r["b0"]), int(r["b1"]), int(r["ori1"]))) for r in adj]
+    smps = {}
+    for sid, s in enumerate(haps):
+        pairs, _, _ = o.raw_query(s)
+        smps[sid] = [(int(p["h0"]), int(p["h1"]), int(p["bgn"]), int(p["end"]), int(p["ori"])) for p in pairs]
+    seq_info = [(sid, len(s), "hap_%02d" % (len(haps) - sid)) for sid, s in enumerate(haps)]
+    for extra, (cut, merge, branch) in (([], (2500, 10000, 8)), (["--bundle-length-cutoff", "500", "--bundle-merge-distance", "2000", "--min-branch-size", "3"], (500, 2000, 3))):
+        pb, _ = bo.get_principal_bundles_from_adj_list(cnt, adj_t, branch)
+        pbid, vmap = pbo.principal_bundles_with_id(pb, smps)
+        prefix = str(tmp_path / ("pb%d" % cut))
+        cmd = [PCLI, fa, prefix] + extra
+        subprocess.check_call(cmd, cwd=ROOT)
+        bed, summ = pbo.decomposition_files(" ".join(cmd), seq_info, smps, pbid, vmap, spec_t[1], cut, merge)
+        assert open(prefix + ".bed").read() == bed
+        assert open(prefix + ".ctg.summary.tsv").read() == summ
+        assert bed.count("\n") > 20 and ":R" in bed and ":U" in bed
