@@ -177,7 +177,7 @@ void pgr_b200_ctx_free(pgr_b200_ctx *ctx) {
     pgr::DevBuf *bufs[] = {&ctx->seq_store, &ctx->d_off, &ctx->d_len, &ctx->d_rid, &ctx->tile_prefix, &ctx->cta_tile, &ctx->arena,
                            &ctx->chunk_count, &ctx->seq_count, &ctx->seq_flag, &ctx->replay_list, &ctx->replay_count,
                            &ctx->chunk_prefix, &ctx->seq_fast, &ctx->seq_dst, &ctx->bufA, &ctx->bufB, &ctx->flags,
-                           &ctx->block_sum, &ctx->block_prefix, &ctx->off_a, &ctx->off_b, &ctx->fix_mm, &ctx->fix_off, &ctx->skips, &ctx->n_skips};
+                           &ctx->block_sum, &ctx->block_prefix, &ctx->block_chunk, &ctx->off_a, &ctx->off_b, &ctx->fix_mm, &ctx->fix_off, &ctx->skips, &ctx->n_skips};
     for (auto b : bufs) b->release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -332,14 +332,14 @@ struct Level {
 
 // one reduce_shmmr level (kind 0) or the min_span filter (kind 1) in a single pass over the list (decoupled look-back)
 int run_level_3pass(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, const uint64_t *off_in, pgr_mm128 *out,
-                    uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out);
+                    uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out, const ChunkView &cv);
 
 int run_level(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, const uint64_t *off_in, pgr_mm128 *out,
-              uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out) {
+              uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out, const ChunkView &cv) {
     // measured on config 2 (1.2e8 level-0 entries): three-pass 2.84 ms, single-pass look-back 3.48 ms (2048-entry tiles are
     // too small to amortise the look-back latency with ~600 CTAs in flight) -> the three-pass path is the default
     static const bool one_pass = getenv("PGR_B200_LEVELS_1PASS") != nullptr;   // A/B switch (tuning aid)
-    if (!one_pass) return run_level_3pass(ctx, kind, in, n_in, off_in, out, off_out, spec, padding, patch_rid, n_out);
+    if (!one_pass || cv.prefix) return run_level_3pass(ctx, kind, in, n_in, off_in, out, off_out, spec, padding, patch_rid, n_out, cv);
     cudaStream_t st = ctx->stream;
     const size_t n = ctx->rn;
     if (n_in == 0) {
@@ -378,7 +378,7 @@ int run_level(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, c
 
 // the same level as three kernels: flags -> block scan -> ordered scatter
 int run_level_3pass(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n_in, const uint64_t *off_in, pgr_mm128 *out,
-              uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out) {
+              uint64_t *off_out, const pgr_shmmr_spec &spec, int padding, bool patch_rid, uint64_t *n_out, const ChunkView &cv) {
     cudaStream_t st = ctx->stream;
     const size_t n = ctx->rn;
     if (n_in == 0) {
@@ -397,10 +397,27 @@ int run_level_3pass(pgr_b200_ctx *ctx, int kind, const pgr_mm128 *in, uint64_t n
     p.flags = ctx->flags.as<uint8_t>(); p.block_sum = ctx->block_sum.as<uint32_t>();
     p.block_prefix = ctx->block_prefix.as<uint64_t>();
     p.out = out; p.seq_off_out = off_out; p.rid = (ctx->d_rid.as<uint32_t>() + ctx->r0); p.patch_rid = patch_rid ? 1u : 0u;
-    if (kind == 0) level_flags_kernel<0><<<n_blocks, LV_NT, 0, st>>>(p);
-    else level_flags_kernel<1><<<n_blocks, LV_NT, 0, st>>>(p);
-    block_scan_kernel<<<1, 1024, 0, st>>>(p.block_sum, p.block_prefix, n_blocks);
-    level_scatter_kernel<<<n_blocks, LV_NT, 0, st>>>(p);
+    // PGR_B200_LEVELS_UNTILED=1 selects the first-generation kernels (per-entry offset look-ups, strided scatter): A/B aid
+    static const bool untiled = getenv("PGR_B200_LEVELS_UNTILED") != nullptr;
+    if (untiled && !cv.prefix) {
+        if (kind == 0) level_flags_kernel<0><<<n_blocks, LV_NT, 0, st>>>(p);
+        else level_flags_kernel<1><<<n_blocks, LV_NT, 0, st>>>(p);
+        block_scan_kernel<<<1, 1024, 0, st>>>(p.block_sum, p.block_prefix, n_blocks);
+        level_scatter_kernel<<<n_blocks, LV_NT, 0, st>>>(p);
+    } else {
+        ChunkView v = cv;
+        if (v.prefix) {   // chunked input: one small kernel finds every block's first chunk
+            PGR_TRY(ctx->block_chunk.ensure((size_t)n_blocks * sizeof(uint32_t)));
+            v.block_chunk = ctx->block_chunk.as<uint32_t>();
+            block_chunk_kernel<<<ceil_div<uint32_t>(n_blocks, 256), 256, 0, st>>>(v, n_blocks, n_in, ctx->block_chunk.as<uint32_t>());
+            ctx->counters[0] += 1;
+        }
+        const ChunkView &cv = v;
+        if (kind == 0) level_flags_tiled_kernel<0><<<n_blocks, LV_NT, 0, st>>>(p, cv);
+        else level_flags_tiled_kernel<1><<<n_blocks, LV_NT, 0, st>>>(p, cv);
+        block_scan_kernel<<<1, 1024, 0, st>>>(p.block_sum, p.block_prefix, n_blocks);
+        level_scatter_tiled_kernel<<<n_blocks, LV_NT, 0, st>>>(p, cv);
+    }
     ctx->counters[0] += 3;
     PGR_CUDA(cudaGetLastError());
     PGR_TRY(ctx->ensure_ctl(64));
@@ -569,6 +586,7 @@ int apply_palindrome_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint
 
 // level-0 minimizers for the whole store -> flat list in ctx->bufA, per-sequence offsets in ctx->seq_dst
 int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
+    ctx->l0_chunked = false;
     cudaStream_t st = ctx->stream;
     const size_t n = ctx->rn;
     const uint32_t w = spec.w, k = spec.k;
@@ -711,7 +729,13 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     PGR_CUDA(cudaMemcpyAsync(ctx->chunk_prefix.p, chunk_prefix.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     PGR_TRY(ctx->bufA.ensure(std::max<uint64_t>(total, 1) * sizeof(pgr_mm128)));
     PGR_TRY(ctx->bufB.ensure(std::max<uint64_t>(total, 1) * sizeof(pgr_mm128)));
-    if (total) {
+    // No sequence to replay and no palindrome / invalid-byte record: the level-0 list is never patched, so the next
+    // level reads it straight from the arena chunks (ChunkView) and the gather pass is skipped.
+    const uint32_t n_skips_seen = std::min<uint32_t>(*h_nskips, SKIP_CAP);
+    static const bool always_gather = getenv("PGR_B200_ALWAYS_GATHER") != nullptr;   // A/B aid
+    ctx->l0_chunked = total && replay.empty() && n_skips_seen == 0 && !always_gather;
+    ctx->l0_chunk_cap = chunk_cap; ctx->l0_chunks = G;
+    if (total && !ctx->l0_chunked) {
         GatherParams gp;
         gp.arena = ctx->arena.as<pgr_mm128>(); gp.chunk_cap = chunk_cap; gp.chunk_prefix = ctx->chunk_prefix.as<uint64_t>();
         gp.n_chunks = G; gp.seq_fast = ctx->seq_fast.as<uint64_t>(); gp.seq_dst = ctx->seq_dst.as<uint64_t>();
@@ -818,19 +842,25 @@ int pgr::shmmrs_range(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, int padding
     PGR_TRY(ctx->bufB.ensure(std::max<uint64_t>(n_cur, 1) * sizeof(pgr_mm128)));
     const pgr_mm128 *cur = ctx->bufA.as<pgr_mm128>();
     const uint64_t *cur_off = ctx->seq_dst.as<uint64_t>();
-    // reduce_shmmr twice, then the min_span filter: each is flags -> block scan -> ordered scatter over the flat list.
+    ChunkView cv = {nullptr, 0, 0, nullptr};   // flat list
+    const ChunkView flat = cv;
+    if (!spec.sketch && ctx->l0_chunked) {   // the level-0 list still lives in the arena chunks (run_l0)
+        cur = ctx->arena.as<pgr_mm128>();
+        cv.prefix = ctx->chunk_prefix.as<uint64_t>(); cv.cap = ctx->l0_chunk_cap; cv.n_chunks = ctx->l0_chunks;
+    }
+    // reduce_shmmr twice, then the min_span filter: each is flags -> block scan -> ordered scatter over the list.
     // (A fused single-kernel version with the levels as index lists in shared memory was measured slower: 6.6 ms vs
     // 2.8 ms on config 2 -- its per-CTA compactions serialise on barriers.)
     const int slot = ctx->timer.begin("reduce_and_span", st);
     if (!spec.sketch && spec.r > 1) {
         uint64_t n1 = 0, n2 = 0;
-        PGR_TRY(run_level(ctx, 0, cur, n_cur, cur_off, ctx->bufB.as<pgr_mm128>(), ctx->off_a.as<uint64_t>(), spec, padding, false, &n1));
+        PGR_TRY(run_level(ctx, 0, cur, n_cur, cur_off, ctx->bufB.as<pgr_mm128>(), ctx->off_a.as<uint64_t>(), spec, padding, false, &n1, cv));
         PGR_TRY(run_level(ctx, 0, ctx->bufB.as<pgr_mm128>(), n1, ctx->off_a.as<uint64_t>(), ctx->bufA.as<pgr_mm128>(),
-                          ctx->off_b.as<uint64_t>(), spec, padding, false, &n2));
-        cur = ctx->bufA.as<pgr_mm128>(); cur_off = ctx->off_b.as<uint64_t>(); n_cur = n2;
+                          ctx->off_b.as<uint64_t>(), spec, padding, false, &n2, flat));
+        cur = ctx->bufA.as<pgr_mm128>(); cur_off = ctx->off_b.as<uint64_t>(); n_cur = n2; cv = flat;
     }
     uint64_t n_fin = 0;
-    PGR_TRY(run_level(ctx, 1, cur, n_cur, cur_off, ctx->bufB.as<pgr_mm128>(), ctx->off_a.as<uint64_t>(), spec, 0, true, &n_fin));
+    PGR_TRY(run_level(ctx, 1, cur, n_cur, cur_off, ctx->bufB.as<pgr_mm128>(), ctx->off_a.as<uint64_t>(), spec, 0, true, &n_fin, cv));
     ctx->timer.end(slot, st);
     ctx->d_result = ctx->bufB.as<pgr_mm128>();
     ctx->d_result_off = ctx->off_a.as<uint64_t>();

@@ -67,13 +67,17 @@ struct pgr_b200_ctx {
     void *h_ctl = nullptr; size_t h_ctl_cap = 0;
     // shimmer pipeline buffers
     pgr::DevBuf tile_prefix, cta_tile, arena, chunk_count, seq_count, seq_flag, replay_list, replay_count;
-    pgr::DevBuf chunk_prefix, seq_fast, seq_dst, bufA, bufB, flags, block_sum, block_prefix, off_a, off_b, skips, n_skips;
+    pgr::DevBuf chunk_prefix, seq_fast, seq_dst, bufA, bufB, flags, block_sum, block_prefix, block_chunk, off_a, off_b, skips, n_skips;
     uint64_t chunk_cap = 0;
     // result of the last shmmrs call
     const pgr_mm128 *d_result = nullptr;
     const uint64_t *d_result_off = nullptr;
     size_t n_result = 0;
     bool result_valid = false;
+    // level-0 list left in the arena chunks by run_l0 (no gather): read through a ChunkView by the next level
+    bool l0_chunked = false;
+    uint64_t l0_chunk_cap = 0;
+    uint32_t l0_chunks = 0;
     // padding fix-up (rare): host-side rebuilt result
     pgr::DevBuf fix_mm, fix_off;
     pgr::StageTimer timer;

@@ -1100,6 +1100,186 @@ __global__ void __launch_bounds__(LV_NT) level_scatter_kernel(const LevelParams 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Tiled versions of the two kernels above (the default path).  The list is read with coalesced 16-byte loads into a
+// shared-memory tile with a halo of r-1 entries; sequence boundaries come from the ordinal in y>>32 of the neighbours
+// (the list is grouped by sequence), so there are no per-entry offset look-ups; the scatter assigns consecutive
+// entries to consecutive lanes (ballot ranks) so that its loads and stores coalesce.  The input may also be the
+// level-0 ARENA itself (n_chunks > 0): logical index i lives in chunk c with chunk_prefix[c] <= i < chunk_prefix[c+1] at
+// arena[c * chunk_cap + (i - chunk_prefix[c])], which saves the gather pass when no sequence needs patching.
+struct ChunkView {
+    const uint64_t *prefix;        // [n_chunks+1] logical index of each chunk's first entry; nullptr = flat list
+    uint64_t cap;                  // entries per chunk
+    uint32_t n_chunks;
+    const uint32_t *block_chunk;   // [n_blocks] chunk of the first index a block touches (block_chunk_kernel): without it
+                                   // every thread would start with a binary search of dependent loads
+};
+struct ChunkCursor {          // per-thread cache of the chunk that held the last index
+    uint32_t c; uint64_t lo, hi;
+};
+__device__ __forceinline__ void cursor_seek(const ChunkView &v, ChunkCursor &k, uint64_t i) {
+    uint32_t lo = 0, hi = v.n_chunks;   // largest c with prefix[c] <= i, skipping empty chunks (prefix[c+1] > i)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (v.prefix[mid] <= i) lo = mid; else hi = mid;
+    }
+    k.c = lo; k.lo = v.prefix[lo]; k.hi = v.prefix[lo + 1];
+}
+__device__ __forceinline__ uint64_t physical_index(const ChunkView &v, ChunkCursor &k, uint64_t i) {
+    if (v.prefix == nullptr) return i;
+    if (i < k.lo || i >= k.hi) cursor_seek(v, k, i);
+    return (uint64_t)k.c * v.cap + (i - k.lo);
+}
+__device__ __forceinline__ pgr_mm128 load_mm(const pgr_mm128 *p) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);   // entries are 16-byte aligned
+    pgr_mm128 m; m.x = v.x; m.y = v.y;
+    return m;
+}
+__device__ __forceinline__ void store_mm(pgr_mm128 *p, const pgr_mm128 &m) {
+    *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(m.x, m.y);
+}
+
+__device__ __forceinline__ ChunkCursor cursor_for_block(const ChunkView &v, uint32_t block) {
+    ChunkCursor k = {0, 1, 0};   // empty range: the first access seeks (flat lists never look at it)
+    if (v.prefix != nullptr) { k.c = v.block_chunk[block]; k.lo = v.prefix[k.c]; k.hi = v.prefix[k.c + 1]; }
+    return k;
+}
+
+constexpr int LT_HALO = 12;   // r - 1 <= 11
+constexpr uint32_t LT_NOSEQ = 0xFFFFFFFFu;
+
+// chunk of the first logical index block b of the tiled kernels touches (its left halo)
+__global__ void block_chunk_kernel(const ChunkView v, uint32_t n_blocks, uint64_t n_in, uint32_t *block_chunk) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint64_t i0 = (uint64_t)b * LV_BLK;
+    uint64_t i = i0 >= (uint64_t)LT_HALO ? i0 - LT_HALO : 0;
+    if (i >= n_in) i = n_in - 1;
+    ChunkCursor k;
+    cursor_seek(v, k, i);
+    block_chunk[b] = k.c;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(LV_NT) level_flags_tiled_kernel(const LevelParams p, const ChunkView cv) {
+    __shared__ uint64_t sx[LV_BLK + 2 * LT_HALO];
+    __shared__ uint32_t ssid[LV_BLK + 2 * LT_HALO];
+    __shared__ uint32_t spos[KIND == 1 ? LV_BLK + 2 * LT_HALO : 1];
+    __shared__ uint32_t wsum[LV_NT / 32];
+    const uint64_t i0 = (uint64_t)blockIdx.x * LV_BLK;
+    ChunkCursor cur = cursor_for_block(cv, blockIdx.x);
+    for (int t = threadIdx.x; t < LV_BLK + 2 * LT_HALO; t += LV_NT) {
+        const int64_t i = (int64_t)i0 - LT_HALO + t;
+        uint64_t x = 0; uint32_t sid = LT_NOSEQ, pos = 0;
+        if (i >= 0 && (uint64_t)i < p.n_in) {
+            const pgr_mm128 m = load_mm(p.in + physical_index(cv, cur, (uint64_t)i));
+            x = m.x; sid = (uint32_t)(m.y >> 32); pos = (uint32_t)(m.y & 0xFFFFFFFFu) >> 1;
+        }
+        sx[t] = x; ssid[t] = sid;
+        if (KIND == 1) spos[t] = pos;
+    }
+    __syncthreads();
+    uint32_t cnt = 0;
+    const int r = (int)p.r;
+#pragma unroll
+    for (int j = 0; j < LV_PER; j++) {
+        const int e = j * LV_NT + threadIdx.x;       // element of the block
+        const uint64_t i = i0 + e;
+        if (i >= p.n_in) break;
+        const int t = e + LT_HALO;
+        const uint64_t x = sx[t];
+        const uint32_t sid = ssid[t];
+        bool keep;
+        if (KIND == 0) {
+            int l = 0, rr = 0;
+            for (int d = 1; d < r; d++) {
+                if (ssid[t - d] != sid) { if (p.padding) l = r - 1; break; }   // left end of the sequence
+                if (sx[t - d] < x) break;
+                l = d;
+            }
+            for (int d = 1; d < r; d++) {
+                if (ssid[t + d] != sid) { if (p.padding) rr = r - 1; break; }
+                if (sx[t + d] < x) break;
+                rr = d;
+            }
+            keep = (l + rr + 1 >= r);
+        } else {
+            if (ssid[t - 1] != sid || ssid[t + 1] != sid) keep = true;           // first / last of its sequence
+            else {
+                const uint32_t pp = spos[t - 1], cp = spos[t], np = spos[t + 1];
+                keep = (uint32_t)(cp - pp) > p.min_span && (uint32_t)(np - cp) > p.min_span && sx[t - 1] != x && x != sx[t + 1];
+            }
+        }
+        p.flags[i] = keep ? 1 : 0;
+        cnt += keep ? 1u : 0u;
+    }
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xFFFFFFFFu, cnt, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < LV_NT / 32; i++) t += wsum[i];
+        p.block_sum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(LV_NT) level_scatter_tiled_kernel(const LevelParams p, const ChunkView cv) {
+    __shared__ uint32_t excl[LV_BLK + 1];                  // exclusive rank of every element of the block
+    __shared__ uint32_t wcnt[LV_PER][LV_NT / 32];          // kept entries per (row, warp)
+    const uint64_t i0 = (uint64_t)blockIdx.x * LV_BLK;
+    const uint64_t bp = p.block_prefix[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t masks[LV_PER];
+    uint8_t f[LV_PER];
+#pragma unroll
+    for (int j = 0; j < LV_PER; j++) {
+        const uint64_t i = i0 + (uint64_t)j * LV_NT + threadIdx.x;
+        f[j] = (i < p.n_in) ? p.flags[i] : 0;
+        masks[j] = __ballot_sync(0xFFFFFFFFu, f[j] != 0);
+        if (lane == 0) wcnt[j][warp] = __popc(masks[j]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {   // exclusive scan of the LV_PER * (LV_NT/32) counts in element order (row-major), in place
+        constexpr int NC = LV_PER * (LV_NT / 32);
+        uint32_t *flat = &wcnt[0][0];
+        uint32_t carry = 0;
+        for (int base = 0; base < NC; base += 32) {
+            const uint32_t v = (base + lane < NC) ? flat[base + lane] : 0;
+            uint32_t incl = v;
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+            if (base + lane < NC) flat[base + lane] = carry + incl - v;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (lane == 0) excl[LV_BLK] = carry;
+    }
+    __syncthreads();
+    ChunkCursor cur = cursor_for_block(cv, blockIdx.x);
+#pragma unroll
+    for (int j = 0; j < LV_PER; j++) {
+        const int e = j * LV_NT + threadIdx.x;
+        const uint32_t rank = wcnt[j][warp] + __popc(masks[j] & ((1u << lane) - 1u));
+        excl[e] = rank;
+        if (f[j]) {
+            pgr_mm128 mm = load_mm(p.in + physical_index(cv, cur, i0 + e));
+            if (p.patch_rid) mm.y = ((uint64_t)p.rid[(uint32_t)(mm.y >> 32)] << 32) | (mm.y & 0xFFFFFFFFull);
+            store_mm(p.out + bp + rank, mm);
+        }
+    }
+    __syncthreads();
+    // sequences whose first input element lies in this block get their output offset from the local scan
+    const uint64_t i1 = min(i0 + (uint64_t)LV_BLK, p.n_in);
+    const bool last_block = (i1 == p.n_in);
+    uint32_t lo = 0, hi = p.n_seq + 1;   // first sid with seq_off_in[sid] >= i0
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.seq_off_in[mid] < i0) lo = mid + 1; else hi = mid;
+    }
+    for (uint32_t sid = lo + threadIdx.x; sid <= p.n_seq; sid += LV_NT) {
+        const uint64_t b = p.seq_off_in[sid];
+        if (b < i1 || (last_block && b == i1)) p.seq_off_out[sid] = bp + excl[b - i0]; else break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Single-pass version of one level (flags + ordered compaction in ONE kernel): the list is read from HBM once, the tile
 // and a halo of r-1 entries live in shared memory, and the global output offset of a tile comes from a decoupled
 // look-back over per-tile status words (aggregate / inclusive prefix), tiles being handed out in order by a ticket.
