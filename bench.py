@@ -57,6 +57,33 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_cpus(local_rank):
+    """Pin this rank (and the pinned host buffers it allocates afterwards) to the CPUs NVML reports as local to its GPU,
+    so that on a two-socket box the H2D copies of the e2e leg do not cross the socket interconnect.  Returns the CPU list
+    or None when NVML, the mask or the cgroup leave nothing to bind to.  PGR_B200_NO_BIND=1 disables it."""
+    if os.environ.get("PGR_B200_NO_BIND"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        index = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            ids = [int(t) for t in vis.split(",")]
+            if local_rank < len(ids):
+                index = ids[local_rank]
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        use = cpus & os.sched_getaffinity(0)
+        if not use or use == os.sched_getaffinity(0):
+            return None if not use else sorted(use)
+        os.sched_setaffinity(0, use)
+        return sorted(use)
+    except Exception:
+        return None
+
+
 def synth_contig(seed, length):
     rng = np.random.default_rng(seed)
     return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=length, dtype=np.uint8)]
@@ -161,6 +188,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    bound = bind_to_gpu_cpus(local_rank)   # before torch / CUDA create their threads and pinned buffers
+
     import torch
     import torch.distributed as dist
 
@@ -246,13 +275,22 @@ def main():
     roofline = {"bound": "hbm", "kernel": "l0_kernel<80,56> (l0_minimizers)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": l0,
                 "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "integer-issue bound, not HBM bound (SURVEY §8d): ~100 int32 ops per base; see DESIGN.md and profiles/"}
+                "note": "integer-issue bound, not HBM bound (SURVEY §8d): ~93 int32 instructions per base, ALU pipe 71 % busy; see int_issue, DESIGN.md and profiles/"}
     traffic_file = os.path.join(ROOT, "profiles", "l0_traffic.json")
     if os.path.exists(traffic_file):
         try:
             tj = json.load(open(traffic_file))
             roofline["traffic"] = tj.get("dram_bytes_per_launch")
             roofline["traffic_source"] = tj.get("source")
+            if tj.get("thread_instr_per_base") and clocks.get("sm_mhz"):
+                # the ceiling that actually binds this kernel: INT32 instruction issue, 128 lanes per SM per clock
+                tipb = float(tj["thread_instr_per_base"])
+                n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                peak_i = n_sm * 128 * float(clocks["sm_mhz"]) * 1e6
+                ach_i = tipb * bases / (l0 * 1e-3)
+                roofline["int_issue"] = {"thread_instr_per_base": tipb, "achieved_instr_per_s": ach_i, "peak_instr_per_s": peak_i,
+                                         "frac": ach_i / peak_i, "alu_pipe_busy": tj.get("alu_pipe_busy"),
+                                         "source": tj.get("instr_source"), "peak_source": "%d SMs x 128 lanes x %.0f MHz (sampled)" % (n_sm, clocks["sm_mhz"])}
         except Exception:
             pass
 
@@ -320,7 +358,8 @@ def main():
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": "sequence_to_shmmrs on %d synthetic %d-base contigs per GPU, w=80 k=56 r=4 min_span=64" % (n_contigs, clen),
                        "bases_per_gpu": bases, "shmmrs_per_gpu": n_shmmrs, "l2": "inputs (%.1f GB) larger than L2" % (bases / 1e9),
-                       "parallelism": "sequences sharded over %d GPU(s), no data-path collective" % world},
+                       "parallelism": "sequences sharded over %d GPU(s), no data-path collective" % world,
+                       "cpu_binding": ("rank 0 bound to %d GPU-local CPUs (NVML affinity)" % len(bound)) if bound else "none"},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
             "stages_ms": {k: statistics.mean(v) for k, v in stage_ms.items()},
         }
