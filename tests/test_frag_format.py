@@ -1,0 +1,77 @@
+"""CPU: the fragment store (.sdx/.frg) codec and the fragment-compression oracle against the REFERENCE'S OWN FIXTURE
+(pgr-db/test/test_data/test_seqs_frag.{sdx,frg}, written by the reference from test_seqs.fa with 80/56/4/64):
+  * the fixture decodes (bincode 2 standard config, raw deflate per 256-fragment chunk) to 952 fragments that reconstruct
+    exactly the 66 sequences of test_seqs.fa (seq_db.rs:685-735);
+  * re-encoding the decoded chunks gives the inflated payloads back byte for byte;
+  * oracle/frag_oracle.py (match_reads, deltas_to_aln_segs, seq_to_compressed restated) reproduces every one of the 952
+    fragments - alignment segments, base fragment ids, orientation flags - and the .sdx sequence table and chunk lengths."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import frag_format as ff  # noqa: E402
+import frag_oracle as fo  # noqa: E402
+
+import orc  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def load_fixture():
+    cs, addr, seqs = ff.read_sdx(os.path.join(GOLDEN, "test_seqs_frag.sdx"))
+    payloads = ff.read_frg_chunks(os.path.join(GOLDEN, "test_seqs_frag.frg"), addr)
+    return cs, addr, seqs, payloads, ff.decode_chunks(payloads)
+
+
+def oracle_db(recs, spec_t=(80, 56, 4, 64), source="test_seqs.fa"):
+    spec = orc.mkspec(*spec_t)
+    db = fo.CompactSeqDB(spec_t[1])
+    for sid, (name, seq) in enumerate(recs):
+        mm, _ = orc.shmmrs_batch([sid], [seq], spec, False)
+        sh = [(int(x) >> 8, (int(y) & 0xFFFFFFFF) >> 1) for x, y in zip(mm["x"], mm["y"])]
+        db.seq_to_compressed(source, name, sid, seq, sh)
+    return db
+
+
+def test_fixture_decodes_to_the_fasta():
+    cs, addr, seqs, payloads, frags = load_fixture()
+    recs = orc.parse_fasta(os.path.join(GOLDEN, "test_seqs.fa"))
+    assert cs == 256 and len(addr) == 4 and len(seqs) == 66 and len(frags) == 952
+    kinds = [f[0] for f in frags]
+    assert kinds.count(ff.FRAG_ALN) == 633 and kinds.count(ff.FRAG_INTERNAL) == 187 and kinds.count(ff.FRAG_PREFIX) == 66
+    for i, s in enumerate(seqs):
+        assert s["id"] == i and s["name"] == recs[i][0] and s["len"] == len(recs[i][1]) and s["source"] == "test_seqs.fa"
+        assert ff.get_seq(frags, 56, s) == recs[i][1]
+    for i, p in enumerate(payloads):
+        assert ff.enc_chunk(frags[i * cs:(i + 1) * cs]) == p
+    # chunk table: (offset, compressed length, bases held) - seq_db.rs:832-860
+    off = 0
+    for i, (o, ln, bases) in enumerate(addr):
+        assert o == off
+        off += ln
+        tot = 0
+        for f in frags[i * cs:(i + 1) * cs]:
+            tot += (f[3] - 56) if f[0] == ff.FRAG_ALN else (len(f[1]) - 56 if f[0] == ff.FRAG_INTERNAL else len(f[1]))
+        assert tot == bases
+
+
+def test_oracle_reproduces_the_fixture_fragments():
+    _, _, seqs, _, frags = load_fixture()
+    recs = orc.parse_fasta(os.path.join(GOLDEN, "test_seqs.fa"))
+    db = oracle_db(recs)
+    assert len(db.frags) == len(frags)
+    assert db.frags == frags
+    assert [(s["seq_frag_range"], s["len"], s["name"]) for s in db.seqs] == [(s["seq_frag_range"], s["len"], s["name"]) for s in seqs]
+
+
+def test_match_reads_known_cases():
+    a = b"ACGTACGTTTGACCAGTAGGATCCATTAGACCAGGATTTACCAGGGATTTAGGACCATAGGACCCATTTAG" * 3
+    m = fo.match_reads(a, a, True, 0.1, 0, 0, 32)
+    assert m["deltas"] == [] and m["end0"] == len(a) and m["end1"] == len(a)
+    assert fo.deltas_to_aln_segs(m["deltas"], m["end0"], m["end1"], a, a) == [(ff.SEG_FULL,)]
+    b = a[:50] + b"T" + a[50:120] + a[123:]                 # one insertion, one 3-base deletion
+    m = fo.match_reads(a, b, True, 0.1, 0, 0, 32)
+    segs = fo.deltas_to_aln_segs(m["deltas"], m["end0"], m["end1"], a, b)
+    assert ff.reconstruct_from_segs(a, segs) == b
+    assert fo.match_reads(a, bytes(reversed(a)), True, 0.1, 0, 0, 32) is None   # too divergent for d_max / the band
