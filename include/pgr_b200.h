@@ -51,6 +51,17 @@ typedef struct {
     uint32_t weight, rank, branch, branch_rank, pad2_;
 } pgr_dfs_node;
 
+/* seq_db.rs:34-41 AlnSegment: type 0 = FullMatch, 1 = Match(a, b), 2 = Insertion(a as u8) */
+typedef struct { uint32_t type, a, b; } pgr_aln_seg;
+/* seq_db.rs:48-55 Fragment, by reference to the caller's sequences: kind 0 = AlnSegments((ref_frag, reversed, len, segs)),
+ * 1 = Prefix, 2 = Internal, 3 = Suffix; the bases of kinds 1-3 (and the aligned bases of kind 0) are [bgn, end) of
+ * sequence sid (for kinds 0 and 2 including the leading k-mer); len = end - bgn */
+typedef struct {
+    uint8_t kind, reversed, pad_[2];
+    uint32_t sid, bgn, end, len, ref_frag, n_segs, pad2_;
+    uint64_t seg_off;
+} pgr_fragment;
+
 /* query_fragment_to_hps arguments (aln.rs:147-158); Option<u32> is encoded as a negative value = None */
 typedef struct {
     float penalty;
@@ -172,6 +183,14 @@ int pgr_b200_sparse_aln(pgr_hit_pair *hits, size_t n, uint32_t max_span, float p
  * encodes None */
 int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *keeps, size_t n_keeps, int has_keeps, pgr_adj_pair **out,
                       size_t *n_out);
+
+/* ---- fragment compression (the .frg/.sdx content of pgr-make-frgdb) --------------------------------------------- */
+/* replaces the alignment branch of CompactSeqDB::seq_to_compressed (seq_db.rs:189-358; shmmrutils::match_reads
+ * shmmrutils.rs:57-223, deltas_to_aln_segs seq_db.rs:113-156) for every sequence of a FASTX-mode index: the caller passes the
+ * sequences again (exactly the indexed ones); the result is `frags` of the reference in frg_id order (one record per
+ * fragment) plus the alignment segments they point into.  Library-allocated (pgr_b200_free). */
+int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
+                                      pgr_fragment **frags, size_t *n_frags, pgr_aln_seg **segs, size_t *n_segs);
 
 /* ---- MAP-graph traversal (host-side walks in the reference too; vertex weights come from the device index) ------ */
 /* replaces seq_db::sort_adj_list_by_weighted_dfs(&frag_map, &adj_list, start) -> Vec<PBundleNode> (seq_db.rs:1013-1061,

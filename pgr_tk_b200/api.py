@@ -17,6 +17,10 @@ GNODE = np.dtype([("h0", "<u8"), ("h1", "<u8"), ("ori", "u1"), ("pad", "u1", 7)]
 DFSNODE = np.dtype([("node", GNODE), ("prev", GNODE), ("has_prev", "u1"), ("is_leaf", "u1"), ("pad", "u1", 2),
                     ("weight", "<u4"), ("rank", "<u4"), ("branch", "<u4"), ("branch_rank", "<u4"), ("pad2", "<u4")])
 assert GNODE.itemsize == 24 and DFSNODE.itemsize == 72
+ALNSEG = np.dtype([("type", "<u4"), ("a", "<u4"), ("b", "<u4")])
+FRAGMENT = np.dtype([("kind", "u1"), ("reversed", "u1"), ("pad", "u1", 2), ("sid", "<u4"), ("bgn", "<u4"), ("end", "<u4"), ("len", "<u4"),
+                     ("ref_frag", "<u4"), ("n_segs", "<u4"), ("pad2", "<u4"), ("seg_off", "<u8")])
+assert ALNSEG.itemsize == 12 and FRAGMENT.itemsize == 40
 ADJ = np.dtype([("sid", "<u4"), ("ori0", "u1"), ("ori1", "u1"), ("pad", "u1", 2),
                 ("a0", "<u8"), ("a1", "<u8"), ("b0", "<u8"), ("b1", "<u8")])
 
@@ -113,6 +117,7 @@ def lib():
         L.pgr_b200_query_result_free.argtypes = [P(QueryResult)]
         L.pgr_b200_sparse_aln.argtypes = [vp, sz, u32, C.c_float, C.c_int64, C.c_int, P(sz), P(vp), P(vp), P(vp)]
         L.pgr_b200_adj_list.argtypes = [vp, sz, vp, sz, C.c_int, P(vp), P(sz)]
+        L.pgr_b200_index_compress_fragments.argtypes = [vp, sz, vp, vp, vp, P(vp), P(sz), P(vp), P(sz)]
         L.pgr_b200_sort_adj_list_by_weighted_dfs.argtypes = [vp, vp, sz, vp, P(vp), P(sz)]
         L.pgr_b200_principal_bundles.argtypes = [vp, vp, sz, sz, P(vp), P(vp), P(sz), P(vp), P(sz)]
         _lib = L
@@ -399,6 +404,16 @@ class ShmmrIndex:
         out, n = C.c_void_p(), C.c_size_t()
         _check(lib().pgr_b200_adj_list(self.h, min_count, k.ctypes.data, k.size, int(keeps is not None), C.byref(out), C.byref(n)))
         return _take(out, n.value, ADJ)
+
+    def compress_fragments(self, sids, seqs):
+        """CompactSeqDB.frags after load_seqs (seq_db.rs:189-358) -> (FRAGMENT[n_frags], ALNSEG[n_segs])"""
+        keep, ptrs, lens = _seq_arrays(seqs)
+        sid_a = np.ascontiguousarray(sids, dtype=np.uint32)
+        fr, sg = C.c_void_p(), C.c_void_p()
+        nf, ns = C.c_size_t(), C.c_size_t()
+        _check(lib().pgr_b200_index_compress_fragments(self.h, len(seqs), sid_a.ctypes.data, ptrs, lens, C.byref(fr), C.byref(nf), C.byref(sg), C.byref(ns)))
+        del keep
+        return _take(fr, nf.value, FRAGMENT), _take(sg, ns.value, ALNSEG)
 
     def sort_adj_list_by_weighted_dfs(self, adj, start):
         """seq_db::sort_adj_list_by_weighted_dfs (seq_db.rs:1013-1061); start = (h0, h1, ori) -> DFSNODE[...]"""

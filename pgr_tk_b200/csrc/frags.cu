@@ -1,0 +1,323 @@
+// frags.cu — fragment compression of the FASTX path on the GPU: CompactSeqDB::seq_to_compressed's alignment branch
+// (seq_db.rs:249-320) with shmmrutils::match_reads (shmmrutils.rs:57-223, the banded O(nD) variant), track_delta_point
+// (:35-54) and deltas_to_aln_segs (seq_db.rs:113-156).
+//
+// The reference walks the sequences in order; an internal fragment (the bases between two adjacent shimmers, with the
+// leading k-mer) longer than 128 bases is aligned against the earlier fragments of the same shimmer pair that are stored
+// raw (`Fragment::Internal`), in insertion order, and becomes `AlnSegments` against the first that matches.  All fragments
+// of one pair are one row of the finalized index (CSR, insertion order = (sequence, ordinal)), and rows are independent:
+// ONE THREAD PER ROW replays the reference's decisions for its row — which entries stay Internal, which base each
+// other entry aligns to — with the reference's alignment, band and traceback reproduced step by step, so the segments
+// are identical (tests compare with oracle/frag_oracle.py, which is pinned to the reference's own .frg fixture).
+// Two passes: (0) decide kind / base / orientation and count the segments, (1) write the segments at their offsets.
+#include <algorithm>
+#include <vector>
+
+#include "index.cuh"
+
+namespace pgr {
+
+struct FragWork {
+    const SortKey *ukeys; const uint64_t *offsets; const pgr_frag_sig *sigs; uint64_t n_keys;
+    const uint8_t *seq; const uint64_t *seq_off;   // sequence store and per-sid byte offsets (sid -> offset; ~0 = absent)
+    uint32_t n_sid, k;
+    uint32_t d_cap;                                // scratch is sized for d_max <= d_cap
+    uint32_t *scratch; uint64_t scratch_stride;    // per thread, in u32 words
+    uint8_t *kind;                                 // [n_sigs] 0 = AlnSegments, 2 = Internal
+    uint8_t *rc;                                   // [n_sigs]
+    uint32_t *ref_sig;                             // [n_sigs] CSR position of the base fragment
+    uint32_t *n_segs;                              // [n_sigs]
+    const uint64_t *seg_off;                       // [n_sigs+1] (pass 1)
+    pgr_aln_seg *segs;                             // (pass 1)
+    uint32_t *overflow;                            // set when a fragment needs d_max > d_cap
+};
+
+constexpr int FR_BAND = 32;                        // match_reads(.., bandwidth = 32) (seq_db.rs:285)
+constexpr int FR_KPER = FR_BAND / 2 + 2;           // k values per d (band width <= 32, step 2) + slack
+
+__device__ __forceinline__ uint8_t rc_base(uint8_t b) {   // fasta_io.rs:26-44
+    switch (b) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+        default: return b;
+    }
+}
+
+struct FragView {   // a fragment as match_reads sees it: seq[bgn-k .. end) of its sequence, reverse-complemented or not
+    const uint8_t *p; uint32_t len; bool rc;
+    __device__ __forceinline__ uint8_t at(uint32_t i) const { return rc ? rc_base(p[len - 1 - i]) : p[i]; }
+};
+
+// One alignment + traceback.  emit(type, a, b) receives the segments in the order deltas_to_aln_segs pushes them (i.e.
+// REVERSED; the caller stores them back to front).  Returns false when match_reads returns None.
+template <class Emit>
+__device__ bool align_fragment(const FragWork &w, uint32_t *scr, const FragView &s0, const FragView &s1, Emit emit) {
+    const uint32_t len0 = s0.len, len1 = s1.len;
+    const uint32_t d_max = 32 + (uint32_t)(0.1 * (double)(len0 < len1 ? len0 : len1));
+    if (d_max > w.d_cap) { *w.overflow = 1; return false; }
+    // scratch: U[2*d_cap+3], V[2*d_cap+3] indexed by k + d_cap + 1; then per d: kmin, FR_KPER packed delta points
+    uint32_t *U = scr, *V = scr + (2 * w.d_cap + 3);
+    uint32_t *DP = V + (2 * w.d_cap + 3);
+    const int kb = (int)w.d_cap + 1;
+    for (int kk = -(int)d_max - 1; kk <= (int)d_max + 1; kk++) { U[kk + kb] = 0; V[kk + kb] = 0; }
+    int k_min = 0, k_max = 0, best_m = -1;
+    bool matched = false;
+    uint32_t d_final = 0, end0 = 0, end1 = 0;
+    int k_final = 0;
+    for (uint32_t d = 0; d < d_max; d++) {
+        if (k_max - k_min > FR_BAND) break;
+        uint32_t *row = DP + (size_t)d * (FR_KPER + 1);
+        row[0] = (uint32_t)k_min;
+        for (int kk = k_min; kk <= k_max; kk += 2) {
+            const uint32_t vn = V[kk - 1 + kb], vp = V[kk + 1 + kb];
+            uint32_t x;
+            int pre_k;
+            if (kk == k_min || (kk != k_max && vn < vp)) { x = vp; pre_k = kk + 1; } else { x = vn + 1; pre_k = kk - 1; }
+            uint32_t y = (uint32_t)((int)x - kk);
+            row[1 + ((kk - k_min) >> 1)] = x | ((kk - pre_k) > 0 ? 0x80000000u : 0u);   // dk = +1 / -1
+            while (x < len0 && y < len1 && s0.at(x) == s1.at(y)) { x++; y++; }
+            U[kk + kb] = x + y; V[kk + kb] = x;
+            if ((int)(x + y) > best_m) best_m = (int)(x + y);
+            if (x >= len0 || y >= len1) { matched = true; d_final = d; k_final = kk; end0 = x; end1 = y; break; }
+        }
+        int k_max_new = k_min, k_min_new = k_max;
+        for (int k2 = k_min; k2 <= k_max; k2 += 2)
+            if ((int)U[k2 + kb] >= best_m - FR_BAND) { if (k2 < k_min_new) k_min_new = k2; if (k2 > k_max_new) k_max_new = k2; }
+        k_max = k_max_new + 1; k_min = k_min_new - 1;
+        if (matched) break;
+    }
+    if (!matched) return false;   // min_match_len = 0: a match is never discarded afterwards
+    // deltas (track_delta_point: d_final .. 1, kept when bgn0 = 0 <= x <= end0) -> segments (deltas_to_aln_segs)
+    // is the delta list empty?  (FullMatch needs that and equal lengths)
+    bool any_delta = false;
+    {
+        uint32_t d = d_final; int kk = k_final;
+        while (d > 0) {
+            const uint32_t *row = DP + (size_t)d * (FR_KPER + 1);
+            const uint32_t e = row[1 + ((kk - (int)row[0]) >> 1)];
+            if ((e & 0x7FFFFFFFu) <= end0) { any_delta = true; break; }
+            kk -= (e >> 31) ? 1 : -1;
+            d--;
+        }
+    }
+    if (!any_delta && len0 == len1) { emit(0u, 0u, 0u); return true; }
+    uint32_t x = end0, y = end1;
+    for (uint32_t yy = len1; yy > y; yy--) emit(2u, (uint32_t)s1.at(yy - 1), 0u);
+    {
+        uint32_t d = d_final; int kk = k_final;
+        while (d > 0) {
+            const uint32_t *row = DP + (size_t)d * (FR_KPER + 1);
+            const uint32_t e = row[1 + ((kk - (int)row[0]) >> 1)];
+            const uint32_t x1 = e & 0x7FFFFFFFu;
+            const int dk = (e >> 31) ? 1 : -1;
+            if (x1 <= end0) {
+                const uint32_t y1 = (uint32_t)((int)x1 - kk);
+                if (x1 < x) emit(1u, x1, x);
+                x = x1; y = y1;
+                if (dk > 0) x -= 1; else emit(2u, (uint32_t)s1.at(y - 1), 0u);
+            }
+            kk -= dk;
+            d--;
+        }
+    }
+    if (x != 0) emit(1u, 0u, x);
+    return true;
+}
+
+template <int PASS>
+__global__ void frag_compress_kernel(const FragWork w, uint32_t n_threads) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;
+    uint32_t *scr = w.scratch + (size_t)t * w.scratch_stride;
+    for (uint64_t row = t; row < w.n_keys; row += n_threads) {
+        const uint64_t r0 = w.offsets[row], r1 = w.offsets[row + 1];
+        for (uint64_t j = r0; j < r1; j++) {
+            const pgr_frag_sig sj = w.sigs[j];
+            if (PASS == 0) {
+                w.kind[j] = 2; w.rc[j] = 0; w.ref_sig[j] = 0; w.n_segs[j] = 0;
+                if (sj.end - sj.bgn <= 128) continue;
+                FragView fj;
+                fj.len = sj.end - sj.bgn + w.k;
+                fj.p = w.seq + w.seq_off[sj.sid] + (sj.bgn - w.k);
+                for (uint64_t i = r0; i < j; i++) {
+                    const pgr_frag_sig si = w.sigs[i];
+                    if (si.sid >= sj.sid) break;          // the map a sequence sees holds earlier sequences only
+                    if (w.kind[i] != 2) continue;         // only raw fragments serve as a base
+                    FragView fi;
+                    fi.len = si.end - si.bgn + w.k; fi.rc = false;
+                    fi.p = w.seq + w.seq_off[si.sid] + (si.bgn - w.k);
+                    fj.rc = sj.ori != si.ori;
+                    uint32_t cnt = 0;
+                    if (align_fragment(w, scr, fi, fj, [&](uint32_t, uint32_t, uint32_t) { cnt++; })) {
+                        w.kind[j] = 0; w.rc[j] = fj.rc ? 1 : 0; w.ref_sig[j] = (uint32_t)(i - r0); w.n_segs[j] = cnt;
+                        break;
+                    }
+                }
+            } else {
+                if (w.kind[j] != 0) continue;
+                const pgr_frag_sig si = w.sigs[r0 + w.ref_sig[j]];
+                FragView fi, fj;
+                fi.len = si.end - si.bgn + w.k; fi.rc = false;
+                fi.p = w.seq + w.seq_off[si.sid] + (si.bgn - w.k);
+                fj.len = sj.end - sj.bgn + w.k; fj.rc = w.rc[j] != 0;
+                fj.p = w.seq + w.seq_off[sj.sid] + (sj.bgn - w.k);
+                pgr_aln_seg *out = w.segs + w.seg_off[j];
+                uint32_t pos = w.n_segs[j];
+                align_fragment(w, scr, fi, fj, [&](uint32_t type, uint32_t a, uint32_t b) {
+                    pos--;
+                    pgr_aln_seg s; s.type = type; s.a = a; s.b = b;
+                    out[pos] = s;
+                });
+            }
+        }
+    }
+}
+
+__global__ void max_span_kernel(const pgr_frag_sig *sigs, uint64_t n, uint32_t *mx) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicMax(mx, sigs[i].end - sigs[i].bgn);
+}
+
+}  // namespace pgr
+
+using namespace pgr;
+
+extern "C" {
+
+int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
+                                      pgr_fragment **frags, size_t *n_frags, pgr_aln_seg **segs, size_t *n_segs) {
+    if (!idx || (n && (!sids || !seqs || !lens)) || !frags || !n_frags || !segs || !n_segs) { set_error("NULL argument"); return PGR_E_ARG; }
+    if (idx->mode != 0) { set_error("fragment compression follows the FASTX fragment numbering (frg_id_mode 0)"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(idx->ctx->device));
+    PGR_TRY(pgr_b200_index_finalize(idx));
+    cudaStream_t st = idx->ctx->stream;
+    const uint64_t ns = idx->n_tuples, nk = idx->n_keys;
+    const uint32_t k = idx->spec.k;
+    // ---- host copy of the signatures (fragment records are assembled on the host) ----
+    std::vector<pgr_frag_sig> hs(ns);
+    if (ns) PGR_CUDA(cudaMemcpyAsync(hs.data(), idx->sigs.p, ns * sizeof(pgr_frag_sig), cudaMemcpyDeviceToHost, st));
+    // ---- sequence store on the device: sid -> offset ----
+    uint32_t n_sid = 0;
+    for (size_t i = 0; i < n; i++) n_sid = std::max<uint32_t>(n_sid, sids[i] + 1);
+    std::vector<uint64_t> off(std::max<uint32_t>(n_sid, 1), ~0ull);
+    std::vector<const uint8_t *> sp(n_sid, nullptr);
+    std::vector<size_t> sl(n_sid, 0);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) { off[sids[i]] = total; total += lens[i]; sp[sids[i]] = seqs[i]; sl[sids[i]] = lens[i]; }
+    DevBuf d_seq, d_off, d_kind, d_rc, d_ref, d_ns, d_segoff, d_segs, d_scr, d_flag;
+    auto release_all = [&]() { for (DevBuf *b : {&d_seq, &d_off, &d_kind, &d_rc, &d_ref, &d_ns, &d_segoff, &d_segs, &d_scr, &d_flag}) b->release(); };
+    PGR_TRY(d_seq.ensure(std::max<uint64_t>(total, 1)));
+    PGR_TRY(d_off.ensure(off.size() * sizeof(uint64_t)));
+    for (size_t i = 0; i < n; i++) if (lens[i]) PGR_CUDA(cudaMemcpyAsync((uint8_t *)d_seq.p + off[sids[i]], seqs[i], lens[i], cudaMemcpyHostToDevice, st));
+    PGR_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    for (uint64_t i = 0; i < ns; i++)
+        if (hs[i].sid >= n_sid || off[hs[i].sid] == ~0ull || hs[i].end > sl[hs[i].sid] || hs[i].bgn < k) { release_all(); set_error("a fragment refers to a sequence that was not passed (sid %u)", hs[i].sid); return PGR_E_ARG; }
+    // ---- device work ----
+    std::vector<uint8_t> h_kind(ns), h_rc(ns);
+    std::vector<uint32_t> h_ref(ns), h_ns(ns);
+    std::vector<uint64_t> h_segoff(ns + 1, 0);
+    std::vector<pgr_aln_seg> h_segs;
+    if (ns) {
+        PGR_TRY(d_kind.ensure(ns)); PGR_TRY(d_rc.ensure(ns)); PGR_TRY(d_ref.ensure(ns * sizeof(uint32_t))); PGR_TRY(d_ns.ensure(ns * sizeof(uint32_t)));
+        PGR_TRY(d_segoff.ensure((ns + 1) * sizeof(uint64_t))); PGR_TRY(d_flag.ensure(64));
+        PGR_CUDA(cudaMemsetAsync(d_flag.p, 0, 64, st));
+        max_span_kernel<<<(unsigned)ceil_div<uint64_t>(ns, 256), 256, 0, st>>>(idx->sigs.as<pgr_frag_sig>(), ns, d_flag.as<uint32_t>() + 1);
+        uint32_t h_flag[2];
+        PGR_CUDA(cudaMemcpyAsync(h_flag, d_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaStreamSynchronize(st));
+        FragWork w;
+        w.ukeys = idx->ukeys.as<SortKey>(); w.offsets = idx->offsets.as<uint64_t>(); w.sigs = idx->sigs.as<pgr_frag_sig>(); w.n_keys = nk;
+        w.seq = d_seq.as<uint8_t>(); w.seq_off = d_off.as<uint64_t>(); w.n_sid = n_sid; w.k = k;
+        w.d_cap = 32 + (uint32_t)(0.1 * (double)(h_flag[1] + k)) + 1;
+        w.scratch_stride = 2ull * (2 * w.d_cap + 3) + (uint64_t)w.d_cap * (FR_KPER + 1);
+        uint32_t n_threads = (uint32_t)std::min<uint64_t>(nk, 32768);
+        while (n_threads > 256 && (uint64_t)n_threads * w.scratch_stride * 4 > (2ull << 30)) n_threads /= 2;   // <= 2 GiB of scratch
+        PGR_TRY(d_scr.ensure((uint64_t)n_threads * w.scratch_stride * sizeof(uint32_t)));
+        w.scratch = d_scr.as<uint32_t>();
+        w.kind = d_kind.as<uint8_t>(); w.rc = d_rc.as<uint8_t>(); w.ref_sig = d_ref.as<uint32_t>(); w.n_segs = d_ns.as<uint32_t>();
+        w.seg_off = nullptr; w.segs = nullptr; w.overflow = d_flag.as<uint32_t>();
+        const unsigned grid = ceil_div<uint32_t>(n_threads, 128);
+        frag_compress_kernel<0><<<grid, 128, 0, st>>>(w, n_threads);
+        idx->launches += 2;
+        PGR_CUDA(cudaGetLastError());
+        uint64_t tot_segs = 0;
+        PGR_TRY(scan_u32(idx, d_ns.as<uint32_t>(), ns, d_segoff.as<uint64_t>(), &tot_segs));
+        PGR_TRY(d_segs.ensure(std::max<uint64_t>(tot_segs, 1) * sizeof(pgr_aln_seg)));
+        w.seg_off = d_segoff.as<uint64_t>(); w.segs = d_segs.as<pgr_aln_seg>();
+        frag_compress_kernel<1><<<grid, 128, 0, st>>>(w, n_threads);
+        idx->launches += 1;
+        PGR_CUDA(cudaGetLastError());
+        h_segs.resize(tot_segs);
+        PGR_CUDA(cudaMemcpyAsync(h_kind.data(), d_kind.p, ns, cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(h_rc.data(), d_rc.p, ns, cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(h_ref.data(), d_ref.p, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(h_ns.data(), d_ns.p, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(h_segoff.data(), d_segoff.p, (ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (tot_segs) PGR_CUDA(cudaMemcpyAsync(h_segs.data(), d_segs.p, tot_segs * sizeof(pgr_aln_seg), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaMemcpyAsync(h_flag, d_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaStreamSynchronize(st));
+        if (h_flag[0]) { release_all(); set_error("fragment longer than the alignment scratch was sized for"); return PGR_E_LIMIT; }
+    }
+    release_all();
+    // ---- fragment records in frg_id order (seq_db.rs:203-231, :326-347) ----
+    // internal fragments by frg_id; the CSR rows give each one's base as a row-relative position
+    std::vector<uint64_t> row_start(ns);
+    {
+        std::vector<uint64_t> h_off(nk + 1);
+        if (nk) PGR_CUDA(cudaMemcpy(h_off.data(), idx->offsets.p, (nk + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        for (uint64_t r = 0; r < nk; r++) for (uint64_t j = h_off[r]; j < h_off[r + 1]; j++) row_start[j] = h_off[r];
+    }
+    const size_t nf = idx->n_frags;
+    std::vector<int64_t> sig_of(nf, -1);
+    for (uint64_t i = 0; i < ns; i++) { if (hs[i].frg_id >= nf) { set_error("fragment id out of range"); return PGR_E_ARG; } sig_of[hs[i].frg_id] = (int64_t)i; }
+    // sequences in sid order; a sequence's internal fragments are consecutive ids between its prefix and its suffix
+    std::vector<uint32_t> order;
+    for (uint32_t s = 0; s < n_sid; s++) if (off[s] != ~0ull) order.push_back(s);
+    *frags = (pgr_fragment *)result_alloc(std::max<size_t>(nf, 1) * sizeof(pgr_fragment));
+    *segs = (pgr_aln_seg *)result_alloc(std::max<size_t>(h_segs.size(), 1) * sizeof(pgr_aln_seg));
+    if (!*frags || !*segs) { set_error("out of host memory"); return PGR_E_ARG; }
+    if (!h_segs.empty()) memcpy(*segs, h_segs.data(), h_segs.size() * sizeof(pgr_aln_seg));
+    size_t f = 0;
+    auto put = [&](uint8_t kind, uint32_t sid, uint32_t bgn, uint32_t end) -> pgr_fragment & {
+        pgr_fragment &r = (*frags)[f++];
+        memset(&r, 0, sizeof r);
+        r.kind = kind; r.sid = sid; r.bgn = bgn; r.end = end; r.len = end - bgn;
+        return r;
+    };
+    for (uint32_t s : order) {
+        if (f >= nf) { set_error("more fragments than the index counted"); return PGR_E_ARG; }
+        const uint32_t L = (uint32_t)sl[s];
+        // internal fragments of s start at id f + 1 when the sequence has pairs
+        if (f + 1 < nf && sig_of[f + 1] >= 0 && hs[(size_t)sig_of[f + 1]].sid == s) {
+            put(1, s, 0, hs[(size_t)sig_of[f + 1]].bgn);                                  // Prefix(seq[..pos0 + 1])
+            uint32_t last_end = 0;
+            while (f < nf && sig_of[f] >= 0 && hs[(size_t)sig_of[f]].sid == s) {
+                const uint64_t j = (uint64_t)sig_of[f];
+                pgr_fragment &r = put(h_kind[j], s, hs[j].bgn - k, hs[j].end);
+                if (h_kind[j] == 0) {
+                    r.reversed = h_rc[j];
+                    r.ref_frag = hs[row_start[j] + h_ref[j]].frg_id;
+                    r.seg_off = h_segoff[j]; r.n_segs = h_ns[j];
+                }
+                last_end = hs[j].end;
+            }
+            put(3, s, last_end, L);                                                       // Suffix(seq[pos_last + 1..])
+        } else {
+            // no pair: 0 shimmers -> Prefix(whole), Suffix(empty); 1 shimmer -> split after it.  Rare: recompute the shimmers.
+            pgr_mm128 *mm = nullptr;
+            size_t nm = 0;
+            PGR_TRY(pgr_b200_sequence_to_shmmrs(s, sp[s], sl[s], &idx->spec, 0, &mm, &nm));
+            const uint32_t cut = nm ? (((uint32_t)(mm[0].y & 0xFFFFFFFFu) >> 1) + 1) : L;
+            pgr_b200_free(mm);
+            put(1, s, 0, cut);
+            put(3, s, cut, L);
+        }
+    }
+    if (f != nf) { set_error("fragment count mismatch: assembled %zu, index counted %zu", f, nf); return PGR_E_ARG; }
+    *n_frags = nf;
+    *n_segs = h_segs.size();
+    return PGR_OK;
+}
+
+}  // extern "C"

@@ -3,3 +3,4 @@
 #include "index.cu"
 #include "query.cu"
 #include "bundles.cu"
+#include "frags.cu"
