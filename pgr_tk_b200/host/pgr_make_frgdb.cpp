@@ -1,7 +1,8 @@
 // pgr-b200-make-frgdb — same command line as pgr-make-frgdb (pgr-bin/src/bin/pgr-make-frgdb.rs:18-46):
 //   pgr-b200-make-frgdb <filelist> <prefix> [-w 80] [-k 56] [-r 4] [--min-span 64]
 // Builds the SHIMMER index of the FASTA/FASTQ(.gz) files listed in <filelist> on the B200 and writes
-// <prefix>.mdb + <prefix>.midx.  The fragment store (<prefix>.sdx/.frg) is out of scope for this build.
+// <prefix>.mdb + <prefix>.midx + <prefix>.sdx + <prefix>.frg (ext.rs:201-207 write_frag_and_index_files); the fragments are
+// compressed on the GPU (pgr_b200_index_compress_fragments).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,6 +42,7 @@ int main(int argc, char **argv) {
     std::ifstream in(filelist);
     if (!in) { fprintf(stderr, "can't open the input file that contains the paths to the fastx files\n"); return 1; }
     pgrb200::SeqIndexDB sdb;
+    sdb.keep_sequences(true);   // the fragment store holds the bases
     std::string line;
     size_t fid = 0;
     while (std::getline(in, line)) {
@@ -50,7 +52,9 @@ int main(int argc, char **argv) {
         fid++;
     }
     if (fid == 0) { fprintf(stderr, "empty file list\n"); return 1; }
-    const int rc = sdb.write_shmmr_map_index(prefix);
+    int rc = sdb.write_to_frag_files(prefix);                // seq_db.rs:814-873
+    if (rc != PGR_OK) { fprintf(stderr, "%s\n", sdb.error().c_str()); return 1; }
+    rc = sdb.write_shmmr_map_index(prefix);                  // seq_db.rs:790-810
     if (rc != PGR_OK) { fprintf(stderr, "%s\n", sdb.error().c_str()); return 1; }
     return 0;
 }

@@ -2,6 +2,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -158,6 +159,99 @@ int SeqIndexDB::query_fragment_to_hps(const std::vector<SeqRec> &queries, const 
     const int rc = pgr_b200_query_batch(idx_, queries.size(), ptrs.data(), lens.data(), &params, out);
     if (rc != PGR_OK) err_ = pgr_b200_last_error();
     return rc;
+}
+
+// ---- bincode 2 `config::standard()`: little endian, variable-length integers ----------------------------------------
+static void put_varint(std::vector<uint8_t> &o, uint64_t v) {
+    if (v < 251) { o.push_back((uint8_t)v); return; }
+    int n; uint8_t tag;
+    if (v < (1ull << 16)) { n = 2; tag = 251; } else if (v < (1ull << 32)) { n = 4; tag = 252; } else { n = 8; tag = 253; }
+    o.push_back(tag);
+    for (int i = 0; i < n; i++) o.push_back((uint8_t)(v >> (8 * i)));
+}
+static void put_bytes(std::vector<uint8_t> &o, const uint8_t *p, size_t n) { put_varint(o, n); o.insert(o.end(), p, p + n); }
+static void put_string(std::vector<uint8_t> &o, const std::string &s) { put_bytes(o, (const uint8_t *)s.data(), s.size()); }
+
+// raw deflate (the reference uses flate2's DeflateEncoder, Compression::default(); the streams differ byte-wise between
+// deflate implementations, their inflated content is what is compared)
+static bool deflate_raw(const std::vector<uint8_t> &in, std::vector<uint8_t> &out) {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    out.resize(deflateBound(&zs, in.size()));
+    zs.next_in = const_cast<Bytef *>(in.data()); zs.avail_in = (uInt)in.size();
+    zs.next_out = out.data(); zs.avail_out = (uInt)out.size();
+    const int rc = deflate(&zs, Z_FINISH);
+    out.resize(zs.total_out);
+    deflateEnd(&zs);
+    return rc == Z_STREAM_END;
+}
+
+int SeqIndexDB::write_to_frag_files(const std::string &prefix, size_t chunk_size) {
+    if (!idx_) { err_ = "no index"; return PGR_E_ARG; }
+    if (seq_data_.size() != seqs_.size()) { err_ = "write_to_frag_files needs the sequences (keep_sequences(true) before loading)"; return PGR_E_ARG; }
+    std::vector<uint32_t> sids;
+    std::vector<const uint8_t *> ptrs;
+    std::vector<size_t> lens;
+    for (size_t i = 0; i < seqs_.size(); i++) { sids.push_back(seqs_[i].id); ptrs.push_back(seq_data_[i].data()); lens.push_back(seq_data_[i].size()); }
+    pgr_fragment *frags = nullptr;
+    pgr_aln_seg *segs = nullptr;
+    size_t nf = 0, nsg = 0;
+    int rc = pgr_b200_index_compress_fragments(idx_, seqs_.size(), sids.data(), ptrs.data(), lens.data(), &frags, &nf, &segs, &nsg);
+    if (rc != PGR_OK) { err_ = pgr_b200_last_error(); return rc; }
+    FILE *frg = fopen((prefix + ".frg").c_str(), "wb"), *sdx = fopen((prefix + ".sdx").c_str(), "wb");
+    if (!frg || !sdx) { err_ = "frag file creating fail"; if (frg) fclose(frg); if (sdx) fclose(sdx); pgr_b200_free(frags); pgr_b200_free(segs); return PGR_E_IO; }
+    fwrite("FRG:0.5", 1, 7, frg);
+    fwrite("SDX:0.5", 1, 7, sdx);
+    const uint32_t k = spec_.k;
+    std::vector<uint8_t> sd;
+    put_varint(sd, chunk_size);
+    put_varint(sd, (nf + chunk_size - 1) / chunk_size);
+    std::vector<std::pair<uint32_t, uint32_t>> range(seqs_.size(), {0, 0});   // per sequence (first fragment, count)
+    uint64_t offset = 0;
+    for (size_t c0 = 0; c0 < nf; c0 += chunk_size) {
+        const size_t c1 = std::min(nf, c0 + chunk_size);
+        std::vector<uint8_t> w, z;
+        put_varint(w, c1 - c0);
+        uint32_t total_len = 0;
+        for (size_t i = c0; i < c1; i++) {
+            const pgr_fragment &f = frags[i];
+            auto &rg = range[f.sid];
+            if (rg.second == 0) rg.first = (uint32_t)i;
+            rg.second++;
+            put_varint(w, f.kind);
+            if (f.kind == 0) {                               // AlnSegments((ref, reversed, len, Vec<AlnSegment>))
+                put_varint(w, f.ref_frag); w.push_back(f.reversed ? 1 : 0); put_varint(w, f.len); put_varint(w, f.n_segs);
+                for (uint32_t s = 0; s < f.n_segs; s++) {
+                    const pgr_aln_seg &g = segs[f.seg_off + s];
+                    put_varint(w, g.type);
+                    if (g.type == 1) { put_varint(w, g.a); put_varint(w, g.b); } else if (g.type == 2) w.push_back((uint8_t)g.a);
+                }
+                total_len += f.len - k;
+            } else {
+                put_bytes(w, seq_data_[f.sid].data() + f.bgn, f.end - f.bgn);
+                total_len += f.kind == 2 ? f.len - k : f.len;
+            }
+        }
+        if (!deflate_raw(w, z)) { err_ = "deflate failed"; fclose(frg); fclose(sdx); pgr_b200_free(frags); pgr_b200_free(segs); return PGR_E_IO; }
+        fwrite(z.data(), 1, z.size(), frg);
+        put_varint(sd, offset); put_varint(sd, z.size()); put_varint(sd, total_len);
+        offset += z.size();
+    }
+    put_varint(sd, seqs_.size());
+    for (size_t i = 0; i < seqs_.size(); i++) {              // CompactSeq {source: Option<String>, name, id, seq_frag_range, len}
+        sd.push_back(1); put_string(sd, seqs_[i].source);
+        put_string(sd, seqs_[i].name);
+        put_varint(sd, seqs_[i].id);
+        put_varint(sd, range[i].first); put_varint(sd, range[i].second);
+        put_varint(sd, seqs_[i].len);
+    }
+    fwrite(sd.data(), 1, sd.size(), sdx);
+    fclose(frg);
+    fclose(sdx);
+    pgr_b200_free(frags);
+    pgr_b200_free(segs);
+    return PGR_OK;
 }
 
 int SeqIndexDB::write_shmmr_map_index(const std::string &prefix) {

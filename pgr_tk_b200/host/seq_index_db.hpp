@@ -4,6 +4,7 @@
 //   SeqIndexDB         ext.rs:48-64,152-199 load_from_fastx / append_from_fastx (FASTX back end, index part)
 //                      seq_db.rs:471-525 record batching (<=129 records per call), sid = running record index
 //                      seq_db.rs:790-810 write_shmmr_map_index (.mdb + .midx)
+//                      seq_db.rs:814-873 write_to_frag_files (.sdx + .frg)
 //                      ext.rs:87-150 load_from_*_index, index part (.mdb + .midx read back; no sequence store)
 //                      ext.rs:252-282 query_fragment_to_hps (batched), ext.rs:455-489 get_sub_seq_by_id (FASTX back end)
 #pragma once
@@ -44,6 +45,9 @@ public:
     int query_fragment_to_hps(const std::vector<SeqRec> &queries, const pgr_query_params &params, pgr_query_result **out);
     // seq_db.rs:790-810 (index part of ext.rs:201-207 write_frag_and_index_files)
     int write_shmmr_map_index(const std::string &prefix);
+    // seq_db.rs:814-873 write_to_frag_files: <prefix>.sdx + <prefix>.frg (fragments compressed on the GPU, bincode 2
+    // standard-config encoding and one raw-deflate stream per 256-fragment chunk on the host); needs keep_sequences(true)
+    int write_to_frag_files(const std::string &prefix, size_t chunk_size = 256);
     const std::vector<CompactSeq> &seqs() const { return seqs_; }
     pgr_b200_index *index() { return idx_; }
     const std::string &error() const { return err_; }

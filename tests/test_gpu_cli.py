@@ -35,6 +35,21 @@ def test_make_frgdb_cli_matches_fixture_and_oracle(tmp_path):
     assert len(got_midx) == len(ref_midx) == 66
     for g, r in zip(got_midx, ref_midx):
         assert g[:3] == r[:3] and os.path.basename(g[3]) == os.path.basename(r[3])
+    # the fragment store: decoded content equals the reference's own .sdx/.frg (the deflate streams themselves differ
+    # between zlib and the reference's miniz; the inflated bincode payloads are byte-identical)
+    import frag_format as ff
+    rcs, raddr, rseqs = ff.read_sdx(os.path.join(GOLDEN, "test_seqs_frag.sdx"))
+    rpay = ff.read_frg_chunks(os.path.join(GOLDEN, "test_seqs_frag.frg"), raddr)
+    gcs, gaddr, gseqs = ff.read_sdx(prefix + ".sdx")
+    gpay = ff.read_frg_chunks(prefix + ".frg", gaddr)
+    assert gcs == rcs == 256 and gpay == rpay
+    assert [a[2] for a in gaddr] == [a[2] for a in raddr]
+    assert [a[0] for a in gaddr] == [sum(x[1] for x in gaddr[:i]) for i in range(len(gaddr))]
+    strip = lambda q: [(x["name"], x["id"], x["seq_frag_range"], x["len"], os.path.basename(x["source"])) for x in q]
+    assert strip(gseqs) == strip(rseqs)
+    frags = ff.decode_chunks(gpay)
+    recs = orc.parse_fasta(fa)
+    assert all(ff.get_seq(frags, 56, x) == recs[i][1] for i, x in enumerate(gseqs))
 
 
 def test_make_frgdb_cli_append_and_flags(tmp_path):
