@@ -156,7 +156,20 @@ def config3(pg, orc, scale, dist_info):
             "bgn_lt_end": bool(np.all(sigs["bgn"] < sigs["end"])),
             "frg_ids_unique": int(len(np.unique(sigs["frg_id"]))) == ns,
         }
+        # fragment compression (the .frg content of pgr-make-frgdb, SURVEY f-1): every internal fragment aligned on the GPU
+        frag_info = None
+        if os.environ.get("PGR_B200_BENCH_FRAGS", "1") != "0":
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fr, sg = g.compress_fragments(list(range(n_hap)), views)
+            fr_s = time.perf_counter() - t0
+            kinds = np.bincount(fr["kind"], minlength=4)
+            raw = int(fr["len"][fr["kind"] != 0].sum())
+            frag_info = {"ms": fr_s * 1e3, "n_fragments": int(len(fr)), "aln_segments_fragments": int(kinds[0]), "internal_raw": int(kinds[2]),
+                         "alignment_segments": int(len(sg)), "bases_kept_raw": raw, "compression": bases_local / max(raw, 1),
+                         "note": "host sequences in, per-fragment records + segments out (H2D of the bases and D2H inside)"}
         emit({"config": 3, "workload": "ShmmrFragMap build, %d haplotypes x %d bases (%.2f Gbases), 80/56/4/64" % (n_hap, L, bases_local / 1e9),
+              "fragment_compression": frag_info,
               "n_gpus": 1, "value": bases_local / min(times) / 1e9, "unit": "Gbases/s", "ms": min(times) * 1e3, "times_ms": [t * 1e3 for t in times],
               "n_keys": nk, "n_sigs": ns, "n_frags": nf, "timed": "host (pinned) sequences -> sorted CSR in HBM (H2D inside)",
               "parity_two_haplotypes_vs_oracle": parity, "properties": props,
