@@ -2,9 +2,9 @@
 //   pgr-b200-query <pgr_db_prefix | fastx> <query.fa> <output_prefix> [--fastx-file] [-w 80 -k 56 -r 4 --min-span 64]
 //       [--gap-penalty-factor 0.025] [--merge-range-tol 100000] [--max-count 128] [--max-query-count 128]
 //       [--max-target-count 128] [--max-aln-chain-span 8] [--only-summary] [--bed-summary]
-// --fastx-file: the database is built from the FASTA/FASTQ(.gz) file (SeqIndexDB::load_from_fastx, ext.rs:152) and target
-// sub-sequences can be written.  Otherwise <pgr_db_prefix>.mdb/.midx are loaded; the .agc/.frg sequence stores are out
-// of scope here, so that mode needs --only-summary.  All queries go to the GPU in ONE batched call (the reference runs one
+// --fastx-file: the database is built from the FASTA/FASTQ(.gz) file (SeqIndexDB::load_from_fastx, ext.rs:152).
+// --frg-file: <pgr_db_prefix>.mdb/.midx/.sdx/.frg are loaded (ext.rs:131 load_from_frg_index); target sub-sequences come from
+// the fragment store.  Otherwise only <pgr_db_prefix>.mdb/.midx are read (the AGC store is out of scope): needs --only-summary.  All queries go to the GPU in ONE batched call (the reference runs one
 // rayon task per query, pgr-query.rs:135); the range merging (pgr-query.rs:167-285, query_post.hpp) is host bookkeeping as
 // in the reference.  Targets are written in ascending sid order (the reference's order is FxHashMap iteration order).
 #include <cstdio>
@@ -85,8 +85,11 @@ int main(int argc, char **argv) {
         fprintf(stderr, "the option `--fastx_file` is specified, read the input file as a fastx file.\n");
         db.keep_sequences(!only_summary);
         rc = db.load_from_fastx(pos[0], w, k, r, min_span);
+    } else if (frg_file) {
+        fprintf(stderr, "the option `--frg_file` is specified, read the input file as a FRG backed index database files.\n");
+        rc = only_summary ? db.load_from_index_files(pos[0]) : db.load_from_frg_index(pos[0]);
     } else {
-        if (!only_summary) { fprintf(stderr, "error: without --fastx-file only the index (.mdb/.midx) is read%s; add --only-summary\n", frg_file ? " (the .frg store is out of scope)" : ""); return 2; }
+        if (!only_summary) { fprintf(stderr, "error: the AGC back end is out of scope: use --frg-file or --fastx-file, or add --only-summary\n"); return 2; }
         rc = db.load_from_index_files(pos[0]);
     }
     if (rc != PGR_OK) { fprintf(stderr, "%s\n", db.error().c_str()); return 1; }

@@ -145,9 +145,162 @@ int SeqIndexDB::load_from_index_files(const std::string &prefix) {
     return PGR_OK;
 }
 
-bool SeqIndexDB::get_sub_seq_by_id(uint32_t sid, size_t bgn, size_t end, std::vector<uint8_t> &out) const {
-    if (sid >= seq_data_.size() || bgn > end || end > seq_data_[sid].size()) return false;
-    out.assign(seq_data_[sid].begin() + (ptrdiff_t)bgn, seq_data_[sid].begin() + (ptrdiff_t)end);
+bool SeqIndexDB::get_sub_seq_by_id(uint32_t sid, size_t bgn, size_t end, std::vector<uint8_t> &out) {
+    if (sid < seq_data_.size()) {
+        if (bgn > end || end > seq_data_[sid].size()) return false;
+        out.assign(seq_data_[sid].begin() + (ptrdiff_t)bgn, seq_data_[sid].begin() + (ptrdiff_t)end);
+        return true;
+    }
+    if (!frag_store_.loaded()) return false;
+    std::vector<uint8_t> whole;                       // frag_file_io.rs:182-229 fetches chunk-wise; the result is seq[bgn..end)
+    if (!frag_store_.get_seq_by_id(sid, whole, err_) || bgn > end || end > whole.size()) return false;
+    out.assign(whole.begin() + (ptrdiff_t)bgn, whole.begin() + (ptrdiff_t)end);
+    return true;
+}
+
+int SeqIndexDB::load_from_frg_index(const std::string &prefix) {
+    const int rc = load_from_index_files(prefix);
+    if (rc != PGR_OK) return rc;
+    if (!frag_store_.load(prefix, spec_.k, err_)) return PGR_E_IO;
+    return PGR_OK;
+}
+
+// ---- FragStore -----------------------------------------------------------------------------------------------------------
+namespace {
+struct BinReader {
+    const uint8_t *p, *e;
+    bool ok = true;
+    uint8_t u8() { if (p >= e) { ok = false; return 0; } return *p++; }
+    uint64_t varint() {
+        const uint8_t t = u8();
+        if (t < 251) return t;
+        const int n = t == 251 ? 2 : t == 252 ? 4 : t == 253 ? 8 : 16;
+        if (e - p < n) { ok = false; return 0; }
+        uint64_t v = 0;
+        for (int i = 0; i < n && i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
+        p += n;
+        return v;
+    }
+    bool bytes(std::vector<uint8_t> &o) { const uint64_t n = varint(); if (!ok || (uint64_t)(e - p) < n) { ok = false; return false; } o.assign(p, p + n); p += n; return true; }
+    bool str(std::string &o) { const uint64_t n = varint(); if (!ok || (uint64_t)(e - p) < n) { ok = false; return false; } o.assign((const char *)p, n); p += n; return true; }
+};
+bool slurp_plain(const std::string &path, std::vector<uint8_t> &buf) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint8_t tmp[1 << 16];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    fclose(f);
+    return true;
+}
+bool inflate_raw(const uint8_t *in, size_t n, std::vector<uint8_t> &out) {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<Bytef *>(in); zs.avail_in = (uInt)n;
+    out.clear();
+    uint8_t tmp[1 << 16];
+    int rc;
+    do {
+        zs.next_out = tmp; zs.avail_out = sizeof tmp;
+        rc = inflate(&zs, Z_NO_FLUSH);
+        if (rc != Z_OK && rc != Z_STREAM_END) { inflateEnd(&zs); return false; }
+        out.insert(out.end(), tmp, tmp + (sizeof tmp - zs.avail_out));
+    } while (rc != Z_STREAM_END);
+    inflateEnd(&zs);
+    return true;
+}
+uint8_t rc_base(uint8_t b) {   // fasta_io.rs:26-44
+    switch (b) {
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+        default: return b;
+    }
+}
+}  // namespace
+
+bool FragStore::load(const std::string &prefix, uint32_t k, std::string &err) {
+    k_ = k;
+    std::vector<uint8_t> sd;
+    if (!slurp_plain(prefix + ".sdx", sd) || sd.size() < 7 || memcmp(sd.data(), "SDX:0.5", 7) != 0) { err = "sdx file open / version error"; return false; }
+    frg_.clear();
+    if (!slurp_plain(prefix + ".frg", frg_) || frg_.size() < 7 || memcmp(frg_.data(), "FRG:0.5", 7) != 0) { err = "frg file open / version error"; return false; }
+    BinReader r{sd.data() + 7, sd.data() + sd.size()};
+    chunk_size_ = r.varint();
+    const uint64_t na = r.varint();
+    addr_.clear();
+    for (uint64_t i = 0; i < na && r.ok; i++) { Addr a; a.off = r.varint(); a.len = r.varint(); a.bases = r.varint(); addr_.push_back(a); }
+    const uint64_t nsq = r.varint();
+    seqs_.clear();
+    for (uint64_t i = 0; i < nsq && r.ok; i++) {
+        SeqEntry s;
+        s.has_source = r.u8() != 0;
+        if (s.has_source) r.str(s.source);
+        r.str(s.name);
+        s.id = (uint32_t)r.varint(); s.frag_first = (uint32_t)r.varint(); s.frag_count = (uint32_t)r.varint(); s.len = r.varint();
+        seqs_.push_back(std::move(s));
+    }
+    if (!r.ok || chunk_size_ == 0) { err = "read sdx file error"; return false; }
+    cache_.clear();
+    return true;
+}
+
+const FragStore::Fragment *FragStore::fragment(uint32_t id, std::string &err) {
+    const uint64_t c = id / chunk_size_;
+    if (c >= addr_.size()) { err = "fragment id out of range"; return nullptr; }
+    for (auto &e : cache_) if (e.first == c) { const size_t i = id % chunk_size_; return i < e.second.size() ? &e.second[i] : nullptr; }
+    const Addr &a = addr_[c];
+    if (7 + a.off + a.len > frg_.size()) { err = "frg chunk out of range"; return nullptr; }
+    std::vector<uint8_t> raw;
+    if (!inflate_raw(frg_.data() + 7 + a.off, a.len, raw)) { err = "frg chunk inflate error"; return nullptr; }
+    BinReader r{raw.data(), raw.data() + raw.size()};
+    std::vector<Fragment> fr((size_t)r.varint());
+    for (auto &f : fr) {
+        f.kind = (uint8_t)r.varint();
+        if (f.kind == 0) {
+            f.ref = (uint32_t)r.varint(); f.reversed = r.u8() != 0; f.len = (uint32_t)r.varint();
+            f.segs.resize((size_t)r.varint());
+            for (auto &s : f.segs) {
+                s.type = (uint32_t)r.varint(); s.a = s.b = 0;
+                if (s.type == 1) { s.a = (uint32_t)r.varint(); s.b = (uint32_t)r.varint(); } else if (s.type == 2) s.a = r.u8();
+            }
+        } else {
+            r.bytes(f.bases);
+        }
+        if (!r.ok) { err = "frg chunk decode error"; return nullptr; }
+    }
+    if (cache_.size() >= 8) cache_.erase(cache_.begin());
+    cache_.emplace_back(c, std::move(fr));
+    const size_t i = id % chunk_size_;
+    return i < cache_.back().second.size() ? &cache_.back().second[i] : nullptr;
+}
+
+// seq_db.rs:685-735 reconstruct_seq_from_frags
+bool FragStore::get_seq_by_id(uint32_t sid, std::vector<uint8_t> &out, std::string &err) {
+    if (sid >= seqs_.size()) { err = "sequence id out of range"; return false; }
+    out.clear();
+    const SeqEntry &s = seqs_[sid];
+    for (uint32_t id = s.frag_first; id < s.frag_first + s.frag_count; id++) {
+        const Fragment *fp = fragment(id, err);
+        if (!fp) return false;
+        const Fragment f = *fp;                                   // copy: fetching the base may evict the chunk
+        if (f.kind == 1 || f.kind == 3) out.insert(out.end(), f.bases.begin(), f.bases.end());
+        else if (f.kind == 2) { if (f.bases.size() < k_) { err = "short internal fragment"; return false; } out.insert(out.end(), f.bases.begin() + k_, f.bases.end()); }
+        else {
+            const Fragment *bp = fragment(f.ref, err);
+            if (!bp || bp->kind != 2) { err = "base fragment is not raw"; return false; }
+            const std::vector<uint8_t> &base = bp->bases;
+            std::vector<uint8_t> seq;
+            for (const Seg &g : f.segs) {                         // seq_db.rs:158-174
+                if (g.type == 0) seq.insert(seq.end(), base.begin(), base.end());
+                else if (g.type == 1) { if (g.a > g.b || g.b > base.size()) { err = "bad match segment"; return false; } seq.insert(seq.end(), base.begin() + g.a, base.begin() + g.b); }
+                else seq.push_back((uint8_t)g.a);
+            }
+            if (f.reversed) { std::reverse(seq.begin(), seq.end()); for (auto &b : seq) b = rc_base(b); }
+            if (seq.size() < k_) { err = "short aligned fragment"; return false; }
+            out.insert(out.end(), seq.begin() + k_, seq.end());
+        }
+    }
     return true;
 }
 

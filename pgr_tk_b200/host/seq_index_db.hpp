@@ -23,6 +23,28 @@ bool read_fastx(const std::string &path, std::vector<SeqRec> &out, std::string &
 
 struct CompactSeq { uint32_t id; uint64_t len; std::string name, source; };
 
+// <prefix>.sdx + <prefix>.frg as a sequence store (frag_file_io.rs:14-229 CompactSeqFragFileStorage; seq_db.rs:685-735):
+// bincode 2 standard-config tables, one raw-deflate stream per chunk of fragments, fragments decoded chunk-wise on demand
+class FragStore {
+public:
+    struct Seg { uint32_t type, a, b; };
+    struct Fragment { uint8_t kind = 1; bool reversed = false; uint32_t ref = 0, len = 0; std::vector<Seg> segs; std::vector<uint8_t> bases; };
+    struct SeqEntry { std::string source, name; uint32_t id = 0, frag_first = 0, frag_count = 0; uint64_t len = 0; bool has_source = false; };
+    bool load(const std::string &prefix, uint32_t k, std::string &err);
+    bool loaded() const { return !frg_.empty() || !addr_.empty(); }
+    const std::vector<SeqEntry> &seqs() const { return seqs_; }
+    bool get_seq_by_id(uint32_t sid, std::vector<uint8_t> &out, std::string &err);
+private:
+    const Fragment *fragment(uint32_t id, std::string &err);
+    struct Addr { uint64_t off, len, bases; };
+    uint64_t chunk_size_ = 256;
+    std::vector<Addr> addr_;
+    std::vector<SeqEntry> seqs_;
+    std::vector<uint8_t> frg_;
+    uint32_t k_ = 0;
+    std::vector<std::pair<uint64_t, std::vector<Fragment>>> cache_;   // (chunk id, fragments), a few recent chunks
+};
+
 class SeqIndexDB {
 public:
     SeqIndexDB() = default;
@@ -36,10 +58,12 @@ public:
     // index part of ext.rs:87-150 (load_from_agc_index / load_from_frg_index): <prefix>.mdb + <prefix>.midx; sequences are
     // not available afterwards (the .agc / .frg stores are out of scope)
     int load_from_index_files(const std::string &prefix);
+    // ext.rs:131-150 load_from_frg_index: the index files plus the .sdx/.frg sequence store
+    int load_from_frg_index(const std::string &prefix);
     // keep the sequences of load_from_fastx in host memory (needed by get_sub_seq_by_id); set before loading
     void keep_sequences(bool on) { keep_seqs_ = on; }
     // ext.rs:455-489 for the FASTX back end: seq[bgn..end); false when the sequence is not held
-    bool get_sub_seq_by_id(uint32_t sid, size_t bgn, size_t end, std::vector<uint8_t> &out) const;
+    bool get_sub_seq_by_id(uint32_t sid, size_t bgn, size_t end, std::vector<uint8_t> &out);
     // ext.rs:252-282 for a batch of queries (pgr-query.rs:135 runs one rayon task per query); result freed by the caller
     // with pgr_b200_query_result_free
     int query_fragment_to_hps(const std::vector<SeqRec> &queries, const pgr_query_params &params, pgr_query_result **out);
@@ -59,6 +83,7 @@ private:
     std::vector<CompactSeq> seqs_;
     std::vector<std::vector<uint8_t>> seq_data_;
     bool keep_seqs_ = false;
+    FragStore frag_store_;
     std::string err_;
 };
 

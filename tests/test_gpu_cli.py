@@ -192,3 +192,52 @@ def test_pbundle_decomp_cli_matches_oracle(tmp_path):
         assert open(prefix + ".bed").read() == bed
         assert open(prefix + ".ctg.summary.tsv").read() == summ
         assert bed.count("\n") > 20 and ":R" in bed and ":U" in bed
+
+
+def test_query_cli_frg_backend_and_reference_fragment_store(tmp_path):
+    """--frg-file: target sub-sequences come out of the .sdx/.frg store.  (1) a store written by pgr-b200-make-frgdb gives
+    the same files as the FASTX back end; (2) the REFERENCE's own fixture store (test_seqs_frag.*) is read back correctly."""
+    import shutil
+    for cli in (CLI, QCLI):
+        if not os.path.exists(cli):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "pgr_tk_b200", "host")])
+    rng = np.random.default_rng(202)
+    anc = ACGT[rng.integers(0, 4, size=90000)]
+    haps = []
+    for h in range(4):
+        s = anc.copy()
+        m = np.nonzero(rng.random(len(s)) < 3e-3)[0]
+        s[m] = ACGT[rng.integers(0, 4, size=len(m))]
+        haps.append(s.tobytes())
+    db_fa = str(tmp_path / "db.fa")
+    _write_fasta(db_fa, [("h%d" % i, s) for i, s in enumerate(haps)])
+    q_fa = str(tmp_path / "q.fa")
+    _write_fasta(q_fa, [("qa", haps[1][10000:70000]), ("qb", haps[3][40000:80000])])
+    fl = tmp_path / "files.txt"
+    fl.write_text(db_fa + "\n")
+    subprocess.check_call([CLI, str(fl), str(tmp_path / "store")], cwd=ROOT)
+    subprocess.check_call([QCLI, db_fa, q_fa, str(tmp_path / "fx"), "--fastx-file"], cwd=ROOT)
+    subprocess.check_call([QCLI, str(tmp_path / "store"), q_fa, str(tmp_path / "fr"), "--frg-file"], cwd=ROOT)
+    for idx in range(2):
+        for ext in ("hit", "fa"):
+            a, b = open("%s.%03d.%s" % (tmp_path / "fx", idx, ext)).read(), open("%s.%03d.%s" % (tmp_path / "fr", idx, ext)).read()
+            assert a == b and len(a) > 100
+    # (2) the reference's fixture
+    for ext in ("mdb", "midx", "sdx", "frg"):
+        shutil.copy(os.path.join(GOLDEN, "test_seqs_frag." + ext), str(tmp_path / ("ref." + ext)))
+    recs = orc.parse_fasta(os.path.join(GOLDEN, "test_seqs.fa"))
+    by_name = {n: s for n, s in recs}
+    q2 = str(tmp_path / "q2.fa")
+    _write_fasta(q2, [("q0", recs[0][1]), ("q1", qpo.reverse_complement(recs[5][1][200:3000]))])
+    subprocess.check_call([QCLI, str(tmp_path / "ref"), q2, str(tmp_path / "rf"), "--frg-file"], cwd=ROOT)
+    n_checked = 0
+    for idx in range(2):
+        rows = [l.rstrip("\n").split("\t") for l in open("%s.%03d.hit" % (tmp_path / "rf", idx)) if not l.startswith("#")]
+        fa = open("%s.%03d.fa" % (tmp_path / "rf", idx)).read().split("\n")
+        assert len(rows) >= 10 and len(fa) == 2 * len(rows) + 1
+        for r, (hdr, seq) in zip(rows, zip(fa[0::2], fa[1::2])):
+            ctg, b, e, ori = r[7], int(r[8]), int(r[9]), int(r[10])
+            sub = by_name[ctg][b:e]
+            assert hdr == ">" + r[11] and seq.encode() == (qpo.reverse_complement(sub) if ori else sub)
+            n_checked += 1
+    assert n_checked >= 20
