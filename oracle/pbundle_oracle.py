@@ -137,3 +137,38 @@ def decomposition_files(cmd_string, seq_info, smps_by_sid, pbid, vmap, k, cutoff
             summ.append("\t".join(map(str, [ctg, ln, len(rv), rs, pct(rs, ln), rmean, rmin, rmax, len(nv), ns, pct(ns, ln), nmean, nmin, nmax,
                                             len(rv) + len(nv), pct(rs + ns, ln)])))
     return "\n".join(bed) + "\n", "\n".join(summ) + "\n"
+
+
+# ---- MAP-graph text files (ext.rs:652-959); canonical line orders where the reference walks FxHashMaps: S lines by segment
+# id, L lines by first appearance in the adjacency list, C lines by sequence id, F lines by key ascending ----------------
+def gfa_text(adj_list, frag_map, k, vmap=None):
+    """adj_list = [(sid, v, w)], v = (h0, h1, ori); frag_map[(h0, h1)] = [(frg_id, sid, bgn, end, ori)] -> GFA text
+    (generate_mapg_gfa ext.rs:735-786; with vmap = {(h0, h1): (bundle, ori, pos)} generate_principal_mapg_gfa :885-956)"""
+    overlaps, frag_id = {}, {}
+    for sid, v, w in adj_list:
+        if v[0] <= w[0]:
+            overlaps.setdefault((v, w), []).append((sid, v[2], w[2]))
+            frag_id.setdefault((v[0], v[1]), len(frag_id))
+            frag_id.setdefault((w[0], w[1]), len(frag_id))
+    out = ["H\tVN:Z:1.0\tCM:Z:Sparse Genome Graph Generated By pgr-tk"]
+    for smp, i in sorted(frag_id.items(), key=lambda t: t[1]):
+        hits = frag_map[smp]
+        ave_len = (sum(h[3] - h[2] for h in hits) & 0xFFFFFFFF) // len(hits)
+        line = "S\t%d\t*\tLN:i:%d\tSN:Z:%016x_%016x" % (i, ave_len + k, smp[0], smp[1])
+        if vmap is not None and smp in vmap:
+            line += "\tBN:i:%d\tBP:i:%d" % (vmap[smp][0], vmap[smp][2])
+        out.append(line)
+    for (v, w), vs in overlaps.items():
+        out.append("L\t%d\t%s\t%d\t%s\t%dM\tSC:i:%d" % (frag_id[(v[0], v[1])], "+-"[v[2]], frag_id[(w[0], w[1])], "+-"[w[2]], k, len(vs)))
+    return "\n".join(out) + "\n"
+
+
+def mapg_idx_text(spec, seq_info, frag_map):
+    """ext.rs:791-847; spec = (w, k, r, min_span, sketch); seq_info = [(sid, len, ctg, source)]"""
+    out = ["K\t%d\t%d\t%d\t%d\t%s" % (spec[0], spec[1], spec[2], spec[3], "true" if spec[4] else "false")]
+    for sid, ln, ctg, src in sorted(seq_info):
+        out.append("C\t%d\t%s\t%s\t%d" % (sid, ctg, src if src else "NA", ln))
+    for key in sorted(frag_map):
+        for v in frag_map[key]:
+            out.append("F\t%016x_%016x\t%d\t%d\t%d\t%d\t%d" % (key[0], key[1], v[0], v[1], v[2], v[3], v[4]))
+    return "\n".join(out) + "\n"

@@ -3,8 +3,8 @@
 //       [--min-cov 0] [--min-branch-size 8] [--bundle-length-cutoff 2500] [--bundle-merge-distance 10000]
 // Shimmers, ShmmrFragMap, MAP-graph adjacency list and vertex weights come from the GPU; the bundle walk, the consensus
 // ordering, the per-contig decomposition and the writers are host bookkeeping as in the reference.  Written:
-// <prefix>.bed and <prefix>.ctg.summary.tsv.  Not written: the GFA/idx files and the bincode .pdb, and
-// the --precomputed-bundles / --include inputs that depend on them.
+// <prefix>.mapg.gfa, <prefix>.mapg.idx, <prefix>.pmapg.gfa, <prefix>.bed and <prefix>.ctg.summary.tsv.  Not written (DESIGN.md
+// §7): the bincode .pdb, and the --precomputed-bundles / --include inputs that depend on it.
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 
+#include "mapg_gfa.hpp"
 #include "pbundle.hpp"
 #include "seq_index_db.hpp"
 
@@ -84,6 +85,7 @@ int main(int argc, char **argv) {
     db.keep_sequences(true);
     if (db.load_from_fastx(pos[0], w, k, r, min_span) != PGR_OK) { fprintf(stderr, "can't read file %s (%s)\n", pos[0].c_str(), db.error().c_str()); return 1; }
     std::vector<std::vector<BundleVertex>> pb;
+    std::vector<pgr_adj_pair> filtered_adj;
     {
         pgr_adj_pair *adj = nullptr;
         size_t n_adj = 0;
@@ -96,9 +98,26 @@ int main(int argc, char **argv) {
             if (pgr_b200_principal_bundles(db.index(), adj, n_adj, min_branch_size, &verts, &off, &nb, &flt, &nf) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
             pb.resize(nb);
             for (size_t b = 0; b < nb; b++) for (uint64_t i = off[b]; i < off[b + 1]; i++) pb[b].push_back({verts[i].h0, verts[i].h1, verts[i].ori});
+            filtered_adj.assign(flt, flt + nf);
             pgr_b200_free(verts); pgr_b200_free(off); pgr_b200_free(flt);
         }
         pgr_b200_free(adj);
+    }
+    // ---- MAP-graph files (pgr-pbundle-decomp.rs:304-331): the whole graph (min_count 0), its index, the principal graph ----
+    {
+        IndexCsr csr;
+        if (export_csr(db.index(), csr) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
+        pgr_adj_pair *adj0 = nullptr;
+        size_t n0 = 0;
+        if (pgr_b200_adj_list(db.index(), 0, nullptr, 0, 0, &adj0, &n0) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
+        pgr_shmmr_spec sp{w, k, r, min_span, 0};
+        VertexMap plain;                                                      // get_vertex_map_from_principal_bundles (ext.rs:512-531)
+        for (size_t b = 0; b < pb.size(); b++) for (size_t p = 0; p < pb[b].size(); p++) plain[{pb[b][p].h0, pb[b][p].h1}] = {b, pb[b][p].ori, p};
+        const bool ok = write_gfa(with_extension(pos[1], "mapg.gfa"), adj0, n0, csr, k, nullptr) &&
+                        write_mapg_idx(with_extension(pos[1], "mapg.idx"), sp, db.seqs(), csr) &&
+                        write_gfa(with_extension(pos[1], "pmapg.gfa"), filtered_adj.data(), filtered_adj.size(), csr, k, &plain);
+        pgr_b200_free(adj0);
+        if (!ok) { fprintf(stderr, "cannot write the MAP-graph files\n"); return 1; }
     }
     std::vector<std::vector<Smp>> smps;
     if (all_smps(db, smps) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }

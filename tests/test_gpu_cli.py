@@ -192,6 +192,14 @@ def test_pbundle_decomp_cli_matches_oracle(tmp_path):
         assert open(prefix + ".bed").read() == bed
         assert open(prefix + ".ctg.summary.tsv").read() == summ
         assert bed.count("\n") > 20 and ":R" in bed and ":U" in bed
+        # MAP-graph files: the whole graph, its index, the principal graph with bundle tags
+        fmap = o.as_map()
+        assert open(prefix + ".mapg.gfa").read() == pbo.gfa_text(adj_t, fmap, spec_t[1])
+        assert open(prefix + ".mapg.idx").read() == pbo.mapg_idx_text(spec_t + (0,), [(sid, ln, ctg, fa) for sid, ln, ctg in seq_info], fmap)
+        _, flt = bo.get_principal_bundles_from_adj_list(cnt, adj_t, branch)
+        plain = {(v[0], v[1]): (b, v[2], p) for b, path in enumerate(pb) for p, v in enumerate(path)}
+        pm = open(prefix + ".pmapg.gfa").read()
+        assert pm == pbo.gfa_text(flt, fmap, spec_t[1], plain) and "\tBN:i:" in pm
 
 
 def test_query_cli_frg_backend_and_reference_fragment_store(tmp_path):
