@@ -213,6 +213,7 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
     PGR_CUDA(cudaStreamSynchronize(st));
     for (uint64_t i = 0; i < ns; i++)
         if (hs[i].sid >= n_sid || off[hs[i].sid] == ~0ull || hs[i].end > sl[hs[i].sid] || hs[i].bgn < k) { release_all(); set_error("a fragment refers to a sequence that was not passed (sid %u)", hs[i].sid); return PGR_E_ARG; }
+    trace_mark("compress_fragments: sigs D2H + sequences H2D");
     // ---- device work ----
     std::vector<uint8_t> h_kind(ns), h_rc(ns);
     std::vector<uint32_t> h_ref(ns), h_ns(ns);
@@ -241,6 +242,7 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
         frag_compress_kernel<0><<<grid, 128, 0, st>>>(w, n_threads);
         idx->launches += 2;
         PGR_CUDA(cudaGetLastError());
+        trace_mark("compress_fragments: pass 0 (decide + count)");
         uint64_t tot_segs = 0;
         PGR_TRY(scan_u32(idx, d_ns.as<uint32_t>(), ns, d_segoff.as<uint64_t>(), &tot_segs));
         PGR_TRY(d_segs.ensure(std::max<uint64_t>(tot_segs, 1) * sizeof(pgr_aln_seg)));
@@ -248,6 +250,7 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
         frag_compress_kernel<1><<<grid, 128, 0, st>>>(w, n_threads);
         idx->launches += 1;
         PGR_CUDA(cudaGetLastError());
+        trace_mark("compress_fragments: pass 1 (segments)");
         h_segs.resize(tot_segs);
         PGR_CUDA(cudaMemcpyAsync(h_kind.data(), d_kind.p, ns, cudaMemcpyDeviceToHost, st));
         PGR_CUDA(cudaMemcpyAsync(h_rc.data(), d_rc.p, ns, cudaMemcpyDeviceToHost, st));
@@ -260,6 +263,7 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
         if (h_flag[0]) { release_all(); set_error("fragment longer than the alignment scratch was sized for"); return PGR_E_LIMIT; }
     }
     release_all();
+    trace_mark("compress_fragments: results D2H");
     // ---- fragment records in frg_id order (seq_db.rs:203-231, :326-347) ----
     // internal fragments by frg_id; the CSR rows give each one's base as a row-relative position
     std::vector<uint64_t> row_start(ns);
@@ -317,6 +321,7 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
     if (f != nf) { set_error("fragment count mismatch: assembled %zu, index counted %zu", f, nf); return PGR_E_ARG; }
     *n_frags = nf;
     *n_segs = h_segs.size();
+    trace_mark("compress_fragments: host assembly");
     return PGR_OK;
 }
 

@@ -1,0 +1,48 @@
+"""GPU: the pgrtk-compatible Python surface (pgr_tk_b200/pgrtk_compat.py over the C ABI) against the oracle, in the
+reference's own return shapes (pgr-tk/src/lib.rs)."""
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from pgr_tk_b200 import pgrtk_compat as pgrtk
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_seq_index_db_surface_matches_oracle():
+    fa = os.path.join(GOLDEN, "test_seqs.fa")
+    db = pgrtk.SeqIndexDB()
+    db.load_from_fastx(fa)
+    o = orc.Index(orc.mkspec(), 0)
+    o.load_fasta(fa)
+    recs = orc.parse_fasta(fa)
+    assert db.get_shmmr_spec() == (80, 56, 4, 64, False)
+    assert db.get_shmmr_map() == o.as_map()
+    assert len(db.seq_info) == 66 and db.seq_info[3] == (recs[3][0], fa, len(recs[3][1]))
+    assert bytes(db.get_sub_seq(fa, recs[5][0], 100, 200)) == recs[5][1][100:200]
+    pl = db.get_shmmr_pair_list()
+    assert len(pl) == 820 and pl == sorted(pl, key=lambda t: (t[0], t[1]))
+    q = recs[7][1][500:3000]
+    hits = db.query_fragment(q)
+    pairs, off, sig = o.raw_query(q)
+    exp = [((int(p["h0"]), int(p["h1"])), (int(p["bgn"]), int(p["end"]), int(p["ori"])),
+            [(int(h["frg_id"]), int(h["sid"]), int(h["bgn"]), int(h["end"]), int(h["ori"])) for h in sig[int(off[i]):int(off[i + 1])]])
+           for i, p in enumerate(pairs) if off[i + 1] > off[i]]
+    assert hits == exp and len(hits) > 3
+    res = db.query_fragment_to_hps(q, 0.025, 128, 128, 128, 8)
+    osid, otco, osc, ocho, ohits = o.query_fragment_to_hps(q, 0.025, max_count=128, max_count_query=128, max_count_target=128, max_aln_span=8)
+    assert [r[0] for r in res] == [int(s) for s in osid]
+    assert [[np.float32(sc) for sc, _ in r[1]] for r in res] == [[np.float32(osc[c]) for c in range(int(otco[t]), int(otco[t + 1]))] for t in range(len(osid))]
+    assert sum(len(a) for r in res for _, a in r[1]) == len(ohits)
+    adj = db.get_smp_adj_list(0)
+    oadj = o.adj_list(0)
+    assert len(adj) == len(oadj) and adj[0] == (int(oadj[0]["sid"]), (int(oadj[0]["a0"]), int(oadj[0]["a1"]), int(oadj[0]["ori0"])), (int(oadj[0]["b0"]), int(oadj[0]["b1"]), int(oadj[0]["ori1"])))
+    pb = db.get_principal_bundles(0, 2)
+    assert pb and all(len(b) > 0 for b in pb)
+    rows = db.sort_adj_list_by_weighted_dfs(adj, adj[0][1])
+    assert rows[0][0] == adj[0][1] and rows[0][1] is None
+    sp = pgrtk.get_shmmr_pairs_from_seq(recs[0][1], 80, 56, 4, 64)
+    assert len(sp) == len(orc.sequence_to_shmmrs(0, recs[0][1], orc.mkspec())) - 1
