@@ -206,6 +206,7 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
     for (size_t i = 0; i < n; i++) { off[sids[i]] = total; total += lens[i]; sp[sids[i]] = seqs[i]; sl[sids[i]] = lens[i]; }
     DevBuf d_seq, d_off, d_kind, d_rc, d_ref, d_ns, d_segoff, d_segs, d_scr, d_flag;
     auto release_all = [&]() { for (DevBuf *b : {&d_seq, &d_off, &d_kind, &d_rc, &d_ref, &d_ns, &d_segoff, &d_segs, &d_scr, &d_flag}) b->release(); };
+    struct Guard { decltype(release_all) &f; ~Guard() { f(); } } guard{release_all};   // every exit path frees the device buffers (release is idempotent)
     PGR_TRY(d_seq.ensure(std::max<uint64_t>(total, 1)));
     PGR_TRY(d_off.ensure(off.size() * sizeof(uint64_t)));
     for (size_t i = 0; i < n; i++) if (lens[i]) PGR_CUDA(cudaMemcpyAsync((uint8_t *)d_seq.p + off[sids[i]], seqs[i], lens[i], cudaMemcpyHostToDevice, st));
@@ -282,6 +283,7 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
     *segs = (pgr_aln_seg *)result_alloc(std::max<size_t>(h_segs.size(), 1) * sizeof(pgr_aln_seg));
     if (!*frags || !*segs) { set_error("out of host memory"); return PGR_E_ARG; }
     if (!h_segs.empty()) memcpy(*segs, h_segs.data(), h_segs.size() * sizeof(pgr_aln_seg));
+    auto drop = [&](int rc_) { result_free(*frags); result_free(*segs); *frags = nullptr; *segs = nullptr; return rc_; };   // error exits release the outputs
     size_t f = 0;
     auto put = [&](uint8_t kind, uint32_t sid, uint32_t bgn, uint32_t end) -> pgr_fragment & {
         pgr_fragment &r = (*frags)[f++];
@@ -290,7 +292,7 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
         return r;
     };
     for (uint32_t s : order) {
-        if (f >= nf) { set_error("more fragments than the index counted"); return PGR_E_ARG; }
+        if (f >= nf) { set_error("more fragments than the index counted"); return drop(PGR_E_ARG); }
         const uint32_t L = (uint32_t)sl[s];
         // internal fragments of s start at id f + 1 when the sequence has pairs
         if (f + 1 < nf && sig_of[f + 1] >= 0 && hs[(size_t)sig_of[f + 1]].sid == s) {
@@ -311,14 +313,14 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
             // no pair: 0 shimmers -> Prefix(whole), Suffix(empty); 1 shimmer -> split after it.  Rare: recompute the shimmers.
             pgr_mm128 *mm = nullptr;
             size_t nm = 0;
-            PGR_TRY(pgr_b200_sequence_to_shmmrs(s, sp[s], sl[s], &idx->spec, 0, &mm, &nm));
+            { const int rc_ = pgr_b200_sequence_to_shmmrs(s, sp[s], sl[s], &idx->spec, 0, &mm, &nm); if (rc_ != PGR_OK) return drop(rc_); }
             const uint32_t cut = nm ? (((uint32_t)(mm[0].y & 0xFFFFFFFFu) >> 1) + 1) : L;
             pgr_b200_free(mm);
             put(1, s, 0, cut);
             put(3, s, cut, L);
         }
     }
-    if (f != nf) { set_error("fragment count mismatch: assembled %zu, index counted %zu", f, nf); return PGR_E_ARG; }
+    if (f != nf) { set_error("fragment count mismatch: assembled %zu, index counted %zu", f, nf); return drop(PGR_E_ARG); }
     *n_frags = nf;
     *n_segs = h_segs.size();
     trace_mark("compress_fragments: host assembly");
