@@ -69,6 +69,18 @@ def test_make_frgdb_cli_append_and_flags(tmp_path):
     assert len(open(prefix + ".midx").readlines()) == 68
     # the .mdb can be loaded back by the library
     assert pg.ShmmrIndex.read_mdb(prefix + ".mdb").as_map() == o.as_map()
+    # the fragment store of the two files: fragment ids continue across files; content equals the oracle's, and every
+    # sequence is reconstructed from it
+    import frag_format as ff
+    from test_frag_format import oracle_db
+    recs = orc.parse_fasta(fa1) + orc.parse_fasta(fa2)
+    exp = oracle_db(recs, (48, 56, 4, 12))
+    cs, addr, seqs = ff.read_sdx(prefix + ".sdx")
+    frags = ff.decode_chunks(ff.read_frg_chunks(prefix + ".frg", addr))
+    assert frags == exp.frags
+    assert [(x["name"], x["id"], x["seq_frag_range"], x["len"]) for x in seqs] == [(x["name"], x["id"], x["seq_frag_range"], x["len"]) for x in exp.seqs]
+    assert [os.path.basename(x["source"]) for x in seqs] == ["test_seqs.fa"] * 66 + ["test_rev.fa"] * 2
+    assert all(ff.get_seq(frags, 56, x) == recs[i][1] for i, x in enumerate(seqs))
 
 
 # ---- pgr-b200-query (pgr-query.rs) ---------------------------------------------------------------------------------------
