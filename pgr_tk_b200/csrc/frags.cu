@@ -5,11 +5,13 @@
 // The reference walks the sequences in order; an internal fragment (the bases between two adjacent shimmers, with the
 // leading k-mer) longer than 128 bases is aligned against the earlier fragments of the same shimmer pair that are stored
 // raw (`Fragment::Internal`), in insertion order, and becomes `AlnSegments` against the first that matches.  All fragments
-// of one pair are one row of the finalized index (CSR, insertion order = (sequence, ordinal)), and rows are independent:
-// ONE THREAD PER ROW replays the reference's decisions for its row — which entries stay Internal, which base each
-// other entry aligns to — with the reference's alignment, band and traceback reproduced step by step, so the segments
-// are identical (tests compare with oracle/frag_oracle.py, which is pinned to the reference's own .frg fixture).
-// Two passes: (0) decide kind / base / orientation and count the segments, (1) write the segments at their offsets.
+// of one pair are one row of the finalized index (CSR, insertion order = (sequence, ordinal)), and rows are independent.
+// The reference's decisions for a row — which entries stay Internal, which base each other entry aligns to — are
+// reproduced with its alignment, band and traceback step by step, so the segments are identical (tests compare with
+// oracle/frag_oracle.py, which is pinned to the reference's own .frg fixture).  Three kernels: (0a) every entry against
+// the first entry of its row, one thread per entry — the common case, fully parallel and exact because the first entry is
+// always raw and always the first candidate; (0b) the entries that failed there, sequentially per row; (1) the
+// segments of the aligned entries written at their offsets, one thread per entry.
 #include <algorithm>
 #include <vector>
 
@@ -25,7 +27,7 @@ struct FragWork {
     uint32_t *scratch; uint64_t scratch_stride;    // per thread, in u32 words
     uint8_t *kind;                                 // [n_sigs] 0 = AlnSegments, 2 = Internal
     uint8_t *rc;                                   // [n_sigs]
-    uint32_t *ref_sig;                             // [n_sigs] CSR position of the base fragment
+    uint32_t *ref_sig;                             // [n_sigs] CSR index of the base fragment's signature
     uint32_t *n_segs;                              // [n_sigs]
     const uint64_t *seg_off;                       // [n_sigs+1] (pass 1)
     pgr_aln_seg *segs;                             // (pass 1)
@@ -124,52 +126,90 @@ __device__ bool align_fragment(const FragWork &w, uint32_t *scr, const FragView 
     return true;
 }
 
-template <int PASS>
-__global__ void frag_compress_kernel(const FragWork w, uint32_t n_threads) {
+__device__ __forceinline__ FragView frag_view(const FragWork &w, const pgr_frag_sig &sg, bool rc) {
+    FragView f;
+    f.len = sg.end - sg.bgn + w.k; f.rc = rc;
+    f.p = w.seq + w.seq_off[sg.sid] + (sg.bgn - w.k);
+    return f;
+}
+
+constexpr uint8_t FR_ALN = 0, FR_INTERNAL = 2, FR_PENDING = 3;
+
+// Pass 0a — one thread per signature.  The first entry of a row is always raw, and it is the first candidate of every
+// later entry of a LATER sequence: aligning against it needs nothing from the other entries, so all entries try it in
+// parallel.  An entry that matches is final (the reference stops at the first match).  An entry of the same sequence as
+// the first one has no candidate at all (candidates come from earlier sequences only) and stays raw.  Only an entry whose
+// alignment against the first one fails depends on what became of the entries before it: it is left PENDING for pass 0b.
+__global__ void frag_first_base_kernel(const FragWork w, uint32_t n_threads, uint64_t n_sigs) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;
+    uint32_t *scr = w.scratch + (size_t)t * w.scratch_stride;
+    for (uint64_t j = t; j < n_sigs; j += n_threads) {
+        uint64_t lo = 0, hi = w.n_keys;   // row of j: largest r with offsets[r] <= j
+        while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (w.offsets[mid] <= j) lo = mid; else hi = mid; }
+        const uint64_t r0 = w.offsets[lo];
+        const pgr_frag_sig sj = w.sigs[j];
+        uint8_t kind = FR_INTERNAL, rc = 0;
+        uint32_t ref = 0, cnt = 0;
+        if (j != r0 && sj.end - sj.bgn > 128) {
+            const pgr_frag_sig s0 = w.sigs[r0];
+            if (s0.sid < sj.sid) {
+                const bool rv = sj.ori != s0.ori;
+                if (align_fragment(w, scr, frag_view(w, s0, false), frag_view(w, sj, rv), [&](uint32_t, uint32_t, uint32_t) { cnt++; })) {
+                    kind = FR_ALN; rc = rv ? 1 : 0; ref = (uint32_t)r0;
+                } else {
+                    kind = FR_PENDING; cnt = 0;
+                }
+            }
+        }
+        w.kind[j] = kind; w.rc[j] = rc; w.ref_sig[j] = ref; w.n_segs[j] = cnt;
+    }
+}
+
+// Pass 0b — one thread per row: the pending entries, in insertion order, try the remaining raw entries before them that
+// belong to earlier sequences (the first entry has been tried); an entry that matches nothing stays raw and is a
+// candidate for the entries after it (seq_db.rs:258-318).
+__global__ void frag_pending_kernel(const FragWork w, uint32_t n_threads) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_threads) return;
     uint32_t *scr = w.scratch + (size_t)t * w.scratch_stride;
     for (uint64_t row = t; row < w.n_keys; row += n_threads) {
         const uint64_t r0 = w.offsets[row], r1 = w.offsets[row + 1];
-        for (uint64_t j = r0; j < r1; j++) {
+        for (uint64_t j = r0 + 1; j < r1; j++) {
+            if (w.kind[j] != FR_PENDING) continue;
             const pgr_frag_sig sj = w.sigs[j];
-            if (PASS == 0) {
-                w.kind[j] = 2; w.rc[j] = 0; w.ref_sig[j] = 0; w.n_segs[j] = 0;
-                if (sj.end - sj.bgn <= 128) continue;
-                FragView fj;
-                fj.len = sj.end - sj.bgn + w.k;
-                fj.p = w.seq + w.seq_off[sj.sid] + (sj.bgn - w.k);
-                for (uint64_t i = r0; i < j; i++) {
-                    const pgr_frag_sig si = w.sigs[i];
-                    if (si.sid >= sj.sid) break;          // the map a sequence sees holds earlier sequences only
-                    if (w.kind[i] != 2) continue;         // only raw fragments serve as a base
-                    FragView fi;
-                    fi.len = si.end - si.bgn + w.k; fi.rc = false;
-                    fi.p = w.seq + w.seq_off[si.sid] + (si.bgn - w.k);
-                    fj.rc = sj.ori != si.ori;
-                    uint32_t cnt = 0;
-                    if (align_fragment(w, scr, fi, fj, [&](uint32_t, uint32_t, uint32_t) { cnt++; })) {
-                        w.kind[j] = 0; w.rc[j] = fj.rc ? 1 : 0; w.ref_sig[j] = (uint32_t)(i - r0); w.n_segs[j] = cnt;
-                        break;
-                    }
+            uint8_t kind = FR_INTERNAL;
+            for (uint64_t i = r0 + 1; i < j; i++) {
+                const pgr_frag_sig si = w.sigs[i];
+                if (si.sid >= sj.sid) break;              // the map a sequence sees holds earlier sequences only
+                if (w.kind[i] != FR_INTERNAL) continue;   // only raw fragments serve as a base
+                const bool rv = sj.ori != si.ori;
+                uint32_t cnt = 0;
+                if (align_fragment(w, scr, frag_view(w, si, false), frag_view(w, sj, rv), [&](uint32_t, uint32_t, uint32_t) { cnt++; })) {
+                    kind = FR_ALN; w.rc[j] = rv ? 1 : 0; w.ref_sig[j] = (uint32_t)i; w.n_segs[j] = cnt;
+                    break;
                 }
-            } else {
-                if (w.kind[j] != 0) continue;
-                const pgr_frag_sig si = w.sigs[r0 + w.ref_sig[j]];
-                FragView fi, fj;
-                fi.len = si.end - si.bgn + w.k; fi.rc = false;
-                fi.p = w.seq + w.seq_off[si.sid] + (si.bgn - w.k);
-                fj.len = sj.end - sj.bgn + w.k; fj.rc = w.rc[j] != 0;
-                fj.p = w.seq + w.seq_off[sj.sid] + (sj.bgn - w.k);
-                pgr_aln_seg *out = w.segs + w.seg_off[j];
-                uint32_t pos = w.n_segs[j];
-                align_fragment(w, scr, fi, fj, [&](uint32_t type, uint32_t a, uint32_t b) {
-                    pos--;
-                    pgr_aln_seg s; s.type = type; s.a = a; s.b = b;
-                    out[pos] = s;
-                });
             }
+            w.kind[j] = kind;
         }
+    }
+}
+
+// Pass 1 — one thread per aligned signature: the alignment once more, segments written back to front at their offsets
+__global__ void frag_segments_kernel(const FragWork w, uint32_t n_threads, uint64_t n_sigs) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;
+    uint32_t *scr = w.scratch + (size_t)t * w.scratch_stride;
+    for (uint64_t j = t; j < n_sigs; j += n_threads) {
+        if (w.kind[j] != FR_ALN) continue;
+        const pgr_frag_sig sj = w.sigs[j], si = w.sigs[w.ref_sig[j]];
+        pgr_aln_seg *out = w.segs + w.seg_off[j];
+        uint32_t pos = w.n_segs[j];
+        align_fragment(w, scr, frag_view(w, si, false), frag_view(w, sj, w.rc[j] != 0), [&](uint32_t type, uint32_t a, uint32_t b) {
+            pos--;
+            pgr_aln_seg sg; sg.type = type; sg.a = a; sg.b = b;
+            out[pos] = sg;
+        });
     }
 }
 
@@ -233,22 +273,23 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
         w.seq = d_seq.as<uint8_t>(); w.seq_off = d_off.as<uint64_t>(); w.n_sid = n_sid; w.k = k;
         w.d_cap = 32 + (uint32_t)(0.1 * (double)(h_flag[1] + k)) + 1;
         w.scratch_stride = 2ull * (2 * w.d_cap + 3) + (uint64_t)w.d_cap * (FR_KPER + 1);
-        uint32_t n_threads = (uint32_t)std::min<uint64_t>(nk, 32768);
+        uint32_t n_threads = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ns, 1), 65536);
         while (n_threads > 256 && (uint64_t)n_threads * w.scratch_stride * 4 > (2ull << 30)) n_threads /= 2;   // <= 2 GiB of scratch
         PGR_TRY(d_scr.ensure((uint64_t)n_threads * w.scratch_stride * sizeof(uint32_t)));
         w.scratch = d_scr.as<uint32_t>();
         w.kind = d_kind.as<uint8_t>(); w.rc = d_rc.as<uint8_t>(); w.ref_sig = d_ref.as<uint32_t>(); w.n_segs = d_ns.as<uint32_t>();
         w.seg_off = nullptr; w.segs = nullptr; w.overflow = d_flag.as<uint32_t>();
         const unsigned grid = ceil_div<uint32_t>(n_threads, 128);
-        frag_compress_kernel<0><<<grid, 128, 0, st>>>(w, n_threads);
-        idx->launches += 2;
+        frag_first_base_kernel<<<grid, 128, 0, st>>>(w, n_threads, ns);
+        frag_pending_kernel<<<grid, 128, 0, st>>>(w, n_threads);
+        idx->launches += 3;
         PGR_CUDA(cudaGetLastError());
         trace_mark("compress_fragments: pass 0 (decide + count)");
         uint64_t tot_segs = 0;
         PGR_TRY(scan_u32(idx, d_ns.as<uint32_t>(), ns, d_segoff.as<uint64_t>(), &tot_segs));
         PGR_TRY(d_segs.ensure(std::max<uint64_t>(tot_segs, 1) * sizeof(pgr_aln_seg)));
         w.seg_off = d_segoff.as<uint64_t>(); w.segs = d_segs.as<pgr_aln_seg>();
-        frag_compress_kernel<1><<<grid, 128, 0, st>>>(w, n_threads);
+        frag_segments_kernel<<<grid, 128, 0, st>>>(w, n_threads, ns);
         idx->launches += 1;
         PGR_CUDA(cudaGetLastError());
         trace_mark("compress_fragments: pass 1 (segments)");
@@ -266,13 +307,6 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
     release_all();
     trace_mark("compress_fragments: results D2H");
     // ---- fragment records in frg_id order (seq_db.rs:203-231, :326-347) ----
-    // internal fragments by frg_id; the CSR rows give each one's base as a row-relative position
-    std::vector<uint64_t> row_start(ns);
-    {
-        std::vector<uint64_t> h_off(nk + 1);
-        if (nk) PGR_CUDA(cudaMemcpy(h_off.data(), idx->offsets.p, (nk + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        for (uint64_t r = 0; r < nk; r++) for (uint64_t j = h_off[r]; j < h_off[r + 1]; j++) row_start[j] = h_off[r];
-    }
     const size_t nf = idx->n_frags;
     std::vector<int64_t> sig_of(nf, -1);
     for (uint64_t i = 0; i < ns; i++) { if (hs[i].frg_id >= nf) { set_error("fragment id out of range"); return PGR_E_ARG; } sig_of[hs[i].frg_id] = (int64_t)i; }
@@ -303,7 +337,7 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
                 pgr_fragment &r = put(h_kind[j], s, hs[j].bgn - k, hs[j].end);
                 if (h_kind[j] == 0) {
                     r.reversed = h_rc[j];
-                    r.ref_frag = hs[row_start[j] + h_ref[j]].frg_id;
+                    r.ref_frag = hs[h_ref[j]].frg_id;
                     r.seg_off = h_segoff[j]; r.n_segs = h_ns[j];
                 }
                 last_end = hs[j].end;
