@@ -1021,31 +1021,35 @@ __global__ void __launch_bounds__(LV_NT) level_flags_kernel(const LevelParams p)
     }
 }
 
-// single-CTA exclusive scan of block sums (n_blocks is small: n_in / 2048)
+// single-CTA exclusive scan of block sums (n_blocks = n_in / 2048): every thread sums one contiguous chunk, the 1024
+// chunk sums are scanned once, every thread writes its chunk's prefixes (two barriers in all)
 __global__ void __launch_bounds__(1024) block_scan_kernel(const uint32_t *block_sum, uint64_t *block_prefix, uint32_t n_blocks) {
     __shared__ uint64_t wtot[32];
-    __shared__ uint64_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n_blocks; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint64_t v = (i < n_blocks) ? block_sum[i] : 0;
-        uint64_t incl = v;
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if ((threadIdx.x & 31) >= d) incl += t;
-        }
-        if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        uint64_t wb = 0;
-        for (uint32_t j = 0; j < (threadIdx.x >> 5); j++) wb += wtot[j];
-        const uint64_t c0 = carry;
-        if (i < n_blocks) block_prefix[i] = c0 + wb + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = c0 + wb + incl;
-        __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t per = (n_blocks + 1023) / 1024;
+    const uint32_t b = min(n_blocks, threadIdx.x * per), e = min(n_blocks, b + per);
+    uint64_t sum = 0;
+    for (uint32_t i = b; i < e; i++) sum += block_sum[i];
+    uint64_t incl = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
     }
-    if (threadIdx.x == 0) block_prefix[n_blocks] = carry;
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint64_t v = wtot[lane];
+        uint64_t wi = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        wtot[lane] = wi - v;
+    }
+    __syncthreads();
+    uint64_t run = wtot[warp] + incl - sum;
+    for (uint32_t i = b; i < e; i++) { block_prefix[i] = run; run += block_sum[i]; }
+    if (threadIdx.x == 1023) block_prefix[n_blocks] = run;   // the last thread's running sum is the total (empty chunks add 0)
 }
 
 __global__ void __launch_bounds__(LV_NT) level_scatter_kernel(const LevelParams p) {
