@@ -32,6 +32,9 @@ def test_pod_layouts():
     assert pg.MM128.itemsize == 16 and pg.SIG.itemsize == 20 and pg.QPAIR.itemsize == 32
     assert pg.HITPAIR.itemsize == 20 and pg.ADJ.itemsize == 40
     assert ctypes.sizeof(pg.ShmmrSpec) == 20
+    # PODs of the MAP-graph and fragment entry points (include/pgr_b200.h)
+    assert pg.GNODE.itemsize == 24 and pg.DFSNODE.itemsize == 72 and pg.ALNSEG.itemsize == 12 and pg.FRAGMENT.itemsize == 40
+    assert pg.FRAGMENT.fields["seg_off"][1] == 32 and pg.DFSNODE.fields["weight"][1] == 52
 
 
 def test_no_cpu_fallback_without_device():
