@@ -213,6 +213,29 @@ __global__ void frag_segments_kernel(const FragWork w, uint32_t n_threads, uint6
     }
 }
 
+// per-signature results -> fragment records at their fragment id (the CSR order is by key, the file order by id: the
+// permutation is a random scatter, done here rather than with cache-missing loops on the host).  Prefix / Suffix ids
+// keep kind 0xFF and are filled in by the host, which walks the records sequentially.
+__global__ void frag_record_kernel(const FragWork w, uint64_t n_sigs, pgr_fragment *rec, uint32_t n_frags, uint32_t *bad) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sigs) return;
+    const pgr_frag_sig sg = w.sigs[j];
+    if (sg.frg_id >= n_frags) { *bad = 1; return; }
+    pgr_fragment r;
+    r.kind = w.kind[j]; r.reversed = w.rc[j]; r.pad_[0] = r.pad_[1] = 0;
+    r.sid = sg.sid; r.bgn = sg.bgn - w.k; r.end = sg.end; r.len = sg.end - sg.bgn + w.k;
+    r.ref_frag = 0; r.n_segs = 0; r.pad2_ = 0; r.seg_off = 0;
+    if (r.kind == FR_ALN) { r.ref_frag = w.sigs[w.ref_sig[j]].frg_id; r.n_segs = w.n_segs[j]; r.seg_off = w.seg_off[j]; }
+    rec[sg.frg_id] = r;
+}
+
+__global__ void frag_validate_kernel(const pgr_frag_sig *sigs, uint64_t n, const uint64_t *seq_len, uint32_t n_sid, uint32_t k, uint32_t *bad) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const pgr_frag_sig sg = sigs[i];
+    if (sg.sid >= n_sid || seq_len[sg.sid] == 0 || sg.end > seq_len[sg.sid] || sg.bgn < k || sg.bgn >= sg.end) *bad = 1;
+}
+
 __global__ void max_span_kernel(const pgr_frag_sig *sigs, uint64_t n, uint32_t *mx) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicMax(mx, sigs[i].end - sigs[i].bgn);
@@ -233,9 +256,6 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
     cudaStream_t st = idx->ctx->stream;
     const uint64_t ns = idx->n_tuples, nk = idx->n_keys;
     const uint32_t k = idx->spec.k;
-    // ---- host copy of the signatures (fragment records are assembled on the host) ----
-    std::vector<pgr_frag_sig> hs(ns);
-    if (ns) PGR_CUDA(cudaMemcpyAsync(hs.data(), idx->sigs.p, ns * sizeof(pgr_frag_sig), cudaMemcpyDeviceToHost, st));
     // ---- sequence store on the device: sid -> offset ----
     uint32_t n_sid = 0;
     for (size_t i = 0; i < n; i++) n_sid = std::max<uint32_t>(n_sid, sids[i] + 1);
@@ -252,17 +272,34 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
     for (size_t i = 0; i < n; i++) if (lens[i]) PGR_CUDA(cudaMemcpyAsync((uint8_t *)d_seq.p + off[sids[i]], seqs[i], lens[i], cudaMemcpyHostToDevice, st));
     PGR_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     PGR_CUDA(cudaStreamSynchronize(st));
-    for (uint64_t i = 0; i < ns; i++)
-        if (hs[i].sid >= n_sid || off[hs[i].sid] == ~0ull || hs[i].end > sl[hs[i].sid] || hs[i].bgn < k) { release_all(); set_error("a fragment refers to a sequence that was not passed (sid %u)", hs[i].sid); return PGR_E_ARG; }
+    {   // every signature must refer to a sequence that was passed, inside its bounds
+        std::vector<uint64_t> lens64(std::max<uint32_t>(n_sid, 1), 0);
+        for (uint32_t sI = 0; sI < n_sid; sI++) lens64[sI] = off[sI] == ~0ull ? 0 : sl[sI];
+        DevBuf d_len;
+        PGR_TRY(d_len.ensure(lens64.size() * sizeof(uint64_t)));
+        PGR_TRY(d_flag.ensure(64));
+        PGR_CUDA(cudaMemcpyAsync(d_len.p, lens64.data(), lens64.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        PGR_CUDA(cudaMemsetAsync(d_flag.p, 0, 64, st));
+        if (ns) frag_validate_kernel<<<(unsigned)ceil_div<uint64_t>(ns, 256), 256, 0, st>>>(idx->sigs.as<pgr_frag_sig>(), ns, d_len.as<uint64_t>(), n_sid, k, d_flag.as<uint32_t>() + 2);
+        uint32_t h_bad[3] = {0, 0, 0};
+        PGR_CUDA(cudaMemcpyAsync(h_bad, d_flag.p, sizeof h_bad, cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaStreamSynchronize(st));
+        d_len.release();
+        if (h_bad[2]) { set_error("a fragment refers to a sequence that was not passed, or lies outside it"); return PGR_E_ARG; }
+    }
     trace_mark("compress_fragments: sigs D2H + sequences H2D");
     // ---- device work ----
-    std::vector<uint8_t> h_kind(ns), h_rc(ns);
-    std::vector<uint32_t> h_ref(ns), h_ns(ns);
-    std::vector<uint64_t> h_segoff(ns + 1, 0);
-    std::vector<pgr_aln_seg> h_segs;
+    const size_t nf = idx->n_frags;
+    DevBuf d_rec;
+    auto drop_rec = [&]() { d_rec.release(); };
+    struct Guard2 { decltype(drop_rec) &f; ~Guard2() { f(); } } guard2{drop_rec};
+    PGR_TRY(d_rec.ensure(std::max<size_t>(nf, 1) * sizeof(pgr_fragment)));
+    PGR_CUDA(cudaMemsetAsync(d_rec.p, 0xFF, std::max<size_t>(nf, 1) * sizeof(pgr_fragment), st));   // kind 0xFF = not an internal fragment
+    uint64_t tot_segs = 0;
+    *frags = nullptr; *segs = nullptr;
     if (ns) {
         PGR_TRY(d_kind.ensure(ns)); PGR_TRY(d_rc.ensure(ns)); PGR_TRY(d_ref.ensure(ns * sizeof(uint32_t))); PGR_TRY(d_ns.ensure(ns * sizeof(uint32_t)));
-        PGR_TRY(d_segoff.ensure((ns + 1) * sizeof(uint64_t))); PGR_TRY(d_flag.ensure(64));
+        PGR_TRY(d_segoff.ensure((ns + 1) * sizeof(uint64_t)));
         PGR_CUDA(cudaMemsetAsync(d_flag.p, 0, 64, st));
         max_span_kernel<<<(unsigned)ceil_div<uint64_t>(ns, 256), 256, 0, st>>>(idx->sigs.as<pgr_frag_sig>(), ns, d_flag.as<uint32_t>() + 1);
         uint32_t h_flag[2];
@@ -285,64 +322,50 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
         idx->launches += 3;
         PGR_CUDA(cudaGetLastError());
         trace_mark("compress_fragments: pass 0 (decide + count)");
-        uint64_t tot_segs = 0;
         PGR_TRY(scan_u32(idx, d_ns.as<uint32_t>(), ns, d_segoff.as<uint64_t>(), &tot_segs));
         PGR_TRY(d_segs.ensure(std::max<uint64_t>(tot_segs, 1) * sizeof(pgr_aln_seg)));
         w.seg_off = d_segoff.as<uint64_t>(); w.segs = d_segs.as<pgr_aln_seg>();
         frag_segments_kernel<<<grid, 128, 0, st>>>(w, n_threads, ns);
-        idx->launches += 1;
+        frag_record_kernel<<<(unsigned)ceil_div<uint64_t>(ns, 256), 256, 0, st>>>(w, ns, d_rec.as<pgr_fragment>(), (uint32_t)nf, d_flag.as<uint32_t>() + 2);
+        idx->launches += 2;
         PGR_CUDA(cudaGetLastError());
-        trace_mark("compress_fragments: pass 1 (segments)");
-        h_segs.resize(tot_segs);
-        PGR_CUDA(cudaMemcpyAsync(h_kind.data(), d_kind.p, ns, cudaMemcpyDeviceToHost, st));
-        PGR_CUDA(cudaMemcpyAsync(h_rc.data(), d_rc.p, ns, cudaMemcpyDeviceToHost, st));
-        PGR_CUDA(cudaMemcpyAsync(h_ref.data(), d_ref.p, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        PGR_CUDA(cudaMemcpyAsync(h_ns.data(), d_ns.p, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        PGR_CUDA(cudaMemcpyAsync(h_segoff.data(), d_segoff.p, (ns + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        if (tot_segs) PGR_CUDA(cudaMemcpyAsync(h_segs.data(), d_segs.p, tot_segs * sizeof(pgr_aln_seg), cudaMemcpyDeviceToHost, st));
-        PGR_CUDA(cudaMemcpyAsync(h_flag, d_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st));
-        PGR_CUDA(cudaStreamSynchronize(st));
-        if (h_flag[0]) { release_all(); set_error("fragment longer than the alignment scratch was sized for"); return PGR_E_LIMIT; }
+        trace_mark("compress_fragments: pass 1 (segments) + records");
     }
-    release_all();
-    trace_mark("compress_fragments: results D2H");
-    // ---- fragment records in frg_id order (seq_db.rs:203-231, :326-347) ----
-    const size_t nf = idx->n_frags;
-    std::vector<int64_t> sig_of(nf, -1);
-    for (uint64_t i = 0; i < ns; i++) { if (hs[i].frg_id >= nf) { set_error("fragment id out of range"); return PGR_E_ARG; } sig_of[hs[i].frg_id] = (int64_t)i; }
-    // sequences in sid order; a sequence's internal fragments are consecutive ids between its prefix and its suffix
-    std::vector<uint32_t> order;
-    for (uint32_t s = 0; s < n_sid; s++) if (off[s] != ~0ull) order.push_back(s);
+    // ---- results to the host: records in fragment-id order, segments ----
     *frags = (pgr_fragment *)result_alloc(std::max<size_t>(nf, 1) * sizeof(pgr_fragment));
-    *segs = (pgr_aln_seg *)result_alloc(std::max<size_t>(h_segs.size(), 1) * sizeof(pgr_aln_seg));
-    if (!*frags || !*segs) { set_error("out of host memory"); return PGR_E_ARG; }
-    if (!h_segs.empty()) memcpy(*segs, h_segs.data(), h_segs.size() * sizeof(pgr_aln_seg));
+    *segs = (pgr_aln_seg *)result_alloc(std::max<size_t>(tot_segs, 1) * sizeof(pgr_aln_seg));
     auto drop = [&](int rc_) { result_free(*frags); result_free(*segs); *frags = nullptr; *segs = nullptr; return rc_; };   // error exits release the outputs
+    if (!*frags || !*segs) { set_error("out of host memory"); return drop(PGR_E_ARG); }
+    {
+        uint32_t h_flag[3] = {0, 0, 0};
+        cudaError_t ce = cudaMemcpyAsync(*frags, d_rec.p, std::max<size_t>(nf, 1) * sizeof(pgr_fragment), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && tot_segs) ce = cudaMemcpyAsync(*segs, d_segs.p, tot_segs * sizeof(pgr_aln_seg), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_flag, d_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) { set_error("copying the fragment records failed: %s", cudaGetErrorString(ce)); return drop(PGR_E_CUDA); }
+        if (h_flag[0]) { set_error("fragment longer than the alignment scratch was sized for"); return drop(PGR_E_LIMIT); }
+        if (h_flag[2]) { set_error("fragment id out of range"); return drop(PGR_E_ARG); }
+    }
+    trace_mark("compress_fragments: results D2H");
+    // ---- Prefix / Suffix records (seq_db.rs:203-231, :326-347): a sequential walk over the records in id order ----
+    pgr_fragment *R = *frags;
     size_t f = 0;
-    auto put = [&](uint8_t kind, uint32_t sid, uint32_t bgn, uint32_t end) -> pgr_fragment & {
-        pgr_fragment &r = (*frags)[f++];
+    auto put = [&](uint8_t kind, uint32_t sid, uint32_t bgn, uint32_t end) {
+        pgr_fragment &r = R[f++];
         memset(&r, 0, sizeof r);
         r.kind = kind; r.sid = sid; r.bgn = bgn; r.end = end; r.len = end - bgn;
-        return r;
     };
-    for (uint32_t s : order) {
+    for (uint32_t s = 0; s < n_sid; s++) {
+        if (off[s] == ~0ull) continue;
         if (f >= nf) { set_error("more fragments than the index counted"); return drop(PGR_E_ARG); }
         const uint32_t L = (uint32_t)sl[s];
-        // internal fragments of s start at id f + 1 when the sequence has pairs
-        if (f + 1 < nf && sig_of[f + 1] >= 0 && hs[(size_t)sig_of[f + 1]].sid == s) {
-            put(1, s, 0, hs[(size_t)sig_of[f + 1]].bgn);                                  // Prefix(seq[..pos0 + 1])
+        if (R[f].kind != 0xFF) { set_error("fragment numbering does not match the sequences passed (sid %u)", s); return drop(PGR_E_ARG); }
+        if (f + 1 < nf && R[f + 1].kind != 0xFF && R[f + 1].sid == s) {
+            put(1, s, 0, R[f + 1].bgn + k);                                              // Prefix(seq[..pos0 + 1])
             uint32_t last_end = 0;
-            while (f < nf && sig_of[f] >= 0 && hs[(size_t)sig_of[f]].sid == s) {
-                const uint64_t j = (uint64_t)sig_of[f];
-                pgr_fragment &r = put(h_kind[j], s, hs[j].bgn - k, hs[j].end);
-                if (h_kind[j] == 0) {
-                    r.reversed = h_rc[j];
-                    r.ref_frag = hs[h_ref[j]].frg_id;
-                    r.seg_off = h_segoff[j]; r.n_segs = h_ns[j];
-                }
-                last_end = hs[j].end;
-            }
-            put(3, s, last_end, L);                                                       // Suffix(seq[pos_last + 1..])
+            while (f < nf && R[f].kind != 0xFF && R[f].sid == s) { last_end = R[f].end; f++; }   // the internal fragments are in place
+            if (f >= nf || R[f].kind != 0xFF) { set_error("fragment numbering does not match the sequences passed (sid %u)", s); return drop(PGR_E_ARG); }
+            put(3, s, last_end, L);                                                      // Suffix(seq[pos_last + 1..])
         } else {
             // no pair: 0 shimmers -> Prefix(whole), Suffix(empty); 1 shimmer -> split after it.  Rare: recompute the shimmers.
             pgr_mm128 *mm = nullptr;
@@ -350,14 +373,15 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
             { const int rc_ = pgr_b200_sequence_to_shmmrs(s, sp[s], sl[s], &idx->spec, 0, &mm, &nm); if (rc_ != PGR_OK) return drop(rc_); }
             const uint32_t cut = nm ? (((uint32_t)(mm[0].y & 0xFFFFFFFFu) >> 1) + 1) : L;
             pgr_b200_free(mm);
+            if (f + 1 >= nf || R[f + 1].kind != 0xFF) { set_error("fragment numbering does not match the sequences passed (sid %u)", s); return drop(PGR_E_ARG); }
             put(1, s, 0, cut);
             put(3, s, cut, L);
         }
     }
     if (f != nf) { set_error("fragment count mismatch: assembled %zu, index counted %zu", f, nf); return drop(PGR_E_ARG); }
     *n_frags = nf;
-    *n_segs = h_segs.size();
-    trace_mark("compress_fragments: host assembly");
+    *n_segs = tot_segs;
+    trace_mark("compress_fragments: prefix / suffix records");
     return PGR_OK;
 }
 
