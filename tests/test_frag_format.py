@@ -75,3 +75,34 @@ def test_match_reads_known_cases():
     segs = fo.deltas_to_aln_segs(m["deltas"], m["end0"], m["end1"], a, b)
     assert ff.reconstruct_from_segs(a, segs) == b
     assert fo.match_reads(a, bytes(reversed(a)), True, 0.1, 0, 0, 32) is None   # too divergent for d_max / the band
+
+
+def test_oracle_round_trip_on_mutated_haplotypes():
+    """size-independent property: whatever the alignments decide, every sequence is reconstructed from the store"""
+    import numpy as np
+    rng = np.random.default_rng(9)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[[65, 67, 71, 84]] = [84, 71, 67, 65]
+    anc = acgt[rng.integers(0, 4, size=40000)]
+    recs = []
+    for h in range(8):
+        s = anc.copy()
+        m = np.nonzero(rng.random(len(s)) < 0.003 * (1 + h % 3))[0]
+        s[m] = acgt[rng.integers(0, 4, size=len(m))]
+        for _ in range(h):                                                    # a few indels
+            a = int(rng.integers(1000, len(s) - 1000))
+            s = np.concatenate([s[:a], s[a + int(rng.integers(1, 30)):]]) if rng.random() < 0.5 else np.concatenate([s[:a], acgt[rng.integers(0, 4, size=int(rng.integers(1, 30)))], s[a:]])
+        if h % 2:
+            a = int(rng.integers(5000, 15000))
+            s = np.concatenate([s[:a], comp[s[a:a + 6000]][::-1], s[a + 6000:]])
+        recs.append(("h%d" % h, s.tobytes()))
+    recs.append(("tiny", b"ACGTTGCA" * 10))
+    for spec_t in ((80, 56, 4, 64), (48, 56, 4, 12), (24, 24, 2, 8)):
+        db = oracle_db(recs, spec_t, source="mem")
+        assert all(ff.get_seq(db.frags, spec_t[1], s) == recs[i][1] for i, s in enumerate(db.seqs))
+        kinds = [f[0] for f in db.frags]
+        assert kinds.count(ff.FRAG_ALN) > 20
+        # chunk encoding round trip
+        pay = ff.enc_chunk(db.frags[:256])
+        assert ff.decode_chunks([pay]) == db.frags[:256]
