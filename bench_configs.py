@@ -102,6 +102,26 @@ def config1(pg, orc, scale):
     assert same
 
 
+def frags_equal(fa, sa, fb, sb):
+    """two (FRAGMENT[], ALNSEG[]) results describe the same fragments (segment arrays may be laid out in different orders)"""
+    if len(fa) != len(fb):
+        return False
+    for f in ("kind", "reversed", "sid", "bgn", "end", "len", "ref_frag", "n_segs"):
+        if not np.array_equal(fa[f], fb[f]):
+            return False
+
+    def in_id_order(fr, sg):
+        cnt = fr["n_segs"].astype(np.int64)
+        tot = int(cnt.sum())
+        if tot == 0:
+            return sg[:0]
+        first = np.cumsum(cnt) - cnt                                   # position of each fragment's first segment in id order
+        idx = np.repeat(fr["seg_off"].astype(np.int64) - first, cnt) + np.arange(tot)
+        return sg[idx]
+    ga, gb = in_id_order(fa, sa), in_id_order(fb, sb)
+    return len(ga) == len(gb) and all(np.array_equal(ga[f], gb[f]) for f in ("type", "a", "b"))
+
+
 def config3(pg, orc, scale, dist_info):
     """full ShmmrFragMap build on 94 haplotypes x 50 Mb derived from one ancestor"""
     import torch
@@ -165,7 +185,22 @@ def config3(pg, orc, scale, dist_info):
             fr_s = time.perf_counter() - t0
             kinds = np.bincount(fr["kind"], minlength=4)
             raw = int(fr["len"][fr["kind"] != 0].sum())
-            frag_info = {"ms": fr_s * 1e3, "n_fragments": int(len(fr)), "aln_segments_fragments": int(kinds[0]), "internal_raw": int(kinds[2]),
+            # CPU beside it + parity at size: the first three haplotypes through the C++ oracle (all cores for a sequence's pairs,
+            # inserts sequential, as the reference's par_iter does) and through the GPU on their own
+            ns3 = min(3, n_hap)
+            t0 = time.perf_counter()
+            ofr, osg = orc.compress_fragments(list(range(ns3)), [v for v in views[:ns3]], orc.mkspec(80, 56, 4, 64), nthreads=host_cores())
+            cpu_fr_s = time.perf_counter() - t0
+            g3 = pg.ShmmrIndex(spec, 0)
+            g3.add_batch(list(range(ns3)), views[:ns3])
+            gfr, gsg = g3.compress_fragments(list(range(ns3)), views[:ns3])
+            g3.close()
+            frag_parity = frags_equal(gfr, gsg, ofr, osg)
+            b3 = sum(len(v) for v in views[:ns3])
+            frag_info = {"ms": fr_s * 1e3, "gbases_per_s": bases_local / fr_s / 1e9, "parity_%d_haplotypes_vs_oracle" % ns3: bool(frag_parity),
+                         "cpu_baseline": {"value": b3 / cpu_fr_s / 1e9, "unit": "Gbases/s", "cores": host_cores(), "kind": "port",
+                                          "sample": "%d of %d haplotypes: shimmers + seq_to_compressed (oracle/frag_oracle.cpp)" % (ns3, n_hap)},
+                         "n_fragments": int(len(fr)), "aln_segments_fragments": int(kinds[0]), "internal_raw": int(kinds[2]),
                          "alignment_segments": int(len(sg)), "bases_kept_raw": raw, "compression": bases_local / max(raw, 1),
                          "note": "host sequences in, per-fragment records + segments out (H2D of the bases and D2H inside)"}
         emit({"config": 3, "workload": "ShmmrFragMap build, %d haplotypes x %d bases (%.2f Gbases), 80/56/4/64" % (n_hap, L, bases_local / 1e9),
@@ -177,6 +212,7 @@ def config3(pg, orc, scale, dist_info):
                                "sample": "2 of 94 haplotypes, one sequence per thread + single-threaded inserts (seq_db.rs:461,326-340)"},
               "synth_gen_s": gen_s})
         assert parity and all(props.values()), props
+        assert frag_info is None or frag_info["parity_%d_haplotypes_vs_oracle" % min(3, n_hap)], "GPU fragments differ from the oracle"
         return g, haps
     import torch.distributed as dist
     from pgr_tk_b200 import distributed as D

@@ -221,6 +221,26 @@ class Index:
         return _take(out, n.value, ADJ)
 
 
+FRAGMENT = np.dtype([("kind", "u1"), ("reversed", "u1"), ("pad", "u1", 2), ("sid", "<u4"), ("bgn", "<u4"), ("end", "<u4"), ("len", "<u4"),
+                     ("ref_frag", "<u4"), ("n_segs", "<u4"), ("pad2", "<u4"), ("seg_off", "<u8")])
+ALNSEG = np.dtype([("type", "<u4"), ("a", "<u4"), ("b", "<u4")])
+
+
+def compress_fragments(sids, seqs, spec, nthreads=1):
+    """C++ restatement of seq_to_compressed over the sequences in order (oracle/frag_oracle.cpp) -> (FRAGMENT[], ALNSEG[])"""
+    arrs, ptrs, lens = _seq_arrays(seqs)
+    s = np.ascontiguousarray(sids, dtype=np.uint32)
+    fr, sg = C.c_void_p(), C.c_void_p()
+    nf, ns = C.c_size_t(), C.c_size_t()
+    L = lib()
+    L.orc_compress_fragments.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    rc = L.orc_compress_fragments(C.byref(spec), len(arrs), s.ctypes.data, ptrs, lens, nthreads, C.byref(fr), C.byref(nf), C.byref(sg), C.byref(ns))
+    if rc:
+        raise ValueError("oracle rc=%d" % rc)
+    return _take(fr, nf.value, FRAGMENT), _take(sg, ns.value, ALNSEG)
+
+
 def sparse_aln(hits, max_span, penalty, max_gap=None, oriented=False):
     """hits: HITPAIR array (sorted in place like the reference). Returns (scores, chain_off, chain_hits)."""
     h = np.ascontiguousarray(hits, dtype=HITPAIR)

@@ -106,3 +106,32 @@ def test_oracle_round_trip_on_mutated_haplotypes():
         # chunk encoding round trip
         pay = ff.enc_chunk(db.frags[:256])
         assert ff.decode_chunks([pay]) == db.frags[:256]
+
+
+def _records_to_tuples(fr, sg, seqs):
+    out = []
+    for f in fr:
+        if f["kind"] == ff.FRAG_ALN:
+            segs = []
+            for x in sg[int(f["seg_off"]):int(f["seg_off"]) + int(f["n_segs"])]:
+                t = int(x["type"])
+                segs.append((t,) if t == ff.SEG_FULL else ((t, int(x["a"]), int(x["b"])) if t == ff.SEG_MATCH else (t, int(x["a"]))))
+            out.append((ff.FRAG_ALN, int(f["ref_frag"]), bool(f["reversed"]), int(f["len"]), segs))
+        else:
+            out.append((int(f["kind"]), bytes(seqs[int(f["sid"])][int(f["bgn"]):int(f["end"])])))
+    return out
+
+
+def test_cpp_fragment_oracle_equals_the_fixture_and_the_python_oracle():
+    """oracle/frag_oracle.cpp (the restatement that runs at benchmark sizes / the CPU baseline) against the reference's fixture"""
+    _, _, _, _, frags = load_fixture()
+    recs = orc.parse_fasta(os.path.join(GOLDEN, "test_seqs.fa"))
+    seqs = [s for _, s in recs]
+    for nthreads in (1, 4):
+        fr, sg = orc.compress_fragments(list(range(len(seqs))), seqs, orc.mkspec(80, 56, 4, 64), nthreads=nthreads)
+        assert _records_to_tuples(fr, sg, seqs) == frags
+    # another spec, short / shimmer-free sequences
+    seqs2 = seqs[:12] + [b"ACGT" * 30, b"", seqs[3][:900]]
+    fr, sg = orc.compress_fragments(list(range(len(seqs2))), seqs2, orc.mkspec(48, 56, 4, 12), nthreads=2)
+    exp = oracle_db([("s%d" % i, s) for i, s in enumerate(seqs2)], (48, 56, 4, 12)).frags
+    assert _records_to_tuples(fr, sg, seqs2) == exp
