@@ -26,3 +26,5 @@ print("adj", len(idx.adj_list(0)), len(idx.adj_list(2, [1])))
 print("partition", idx.partition([1 << 40, 1 << 44]))
 adj = idx.adj_list(0)
 print("bundles", len(idx.get_principal_bundles_from_adj_list(adj, 2)[0]), len(idx.sort_adj_list_by_weighted_dfs(adj, (int(adj[0]["a0"]), int(adj[0]["a1"]), int(adj[0]["ori0"])))))
+fr, sg = idx.compress_fragments(list(range(5)), haps)
+print("fragments", len(fr), int((fr["kind"] == 0).sum()), len(sg))
