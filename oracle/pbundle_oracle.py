@@ -172,3 +172,57 @@ def mapg_idx_text(spec, seq_info, frag_map):
         for v in frag_map[key]:
             out.append("F\t%016x_%016x\t%d\t%d\t%d\t%d\t%d" % (key[0], key[1], v[0], v[1], v[2], v[3], v[4]))
     return "\n".join(out) + "\n"
+
+
+# ---- the .pdb file (pgr-pbundle-decomp.rs:158-226, :367-396): "PDB:0.5" + bincode 2 standard config of
+# (w, k, r, min_span, min_branch_size, min_cov, [(bundle_id, mean_order, [(h0, h1, ori)])], {(h0, h1): (bundle, ori, pos)}) ----
+def _vi(v):
+    if v < 251:
+        return bytes([v])
+    if v < 1 << 16:
+        return b"\xfb" + v.to_bytes(2, "little")
+    if v < 1 << 32:
+        return b"\xfc" + v.to_bytes(4, "little")
+    return b"\xfd" + v.to_bytes(8, "little")
+
+
+def encode_pdb(w, k, r, min_span, min_branch_size, min_cov, pbid, vmap):
+    o = [b"PDB:0.5", _vi(w), _vi(k), _vi(r), _vi(min_span), _vi(min_branch_size), _vi(min_cov), _vi(len(pbid))]
+    for bid, order, verts in pbid:
+        o += [_vi(bid), _vi(order), _vi(len(verts))]
+        for v in verts:
+            o += [_vi(v[0]), _vi(v[1]), bytes([v[2]])]
+    o.append(_vi(len(vmap)))
+    for key in sorted(vmap):                      # the reference writes FxHashMap order; canonical: ascending key
+        b = vmap[key]
+        o += [_vi(key[0]), _vi(key[1]), _vi(b[0]), bytes([b[1]]), _vi(b[2])]
+    return b"".join(o)
+
+
+def decode_pdb(buf):
+    assert buf[:7] == b"PDB:0.5"
+    pos = [7]
+
+    def u8():
+        pos[0] += 1
+        return buf[pos[0] - 1]
+
+    def vi():
+        t = u8()
+        if t < 251:
+            return t
+        n = {251: 2, 252: 4, 253: 8, 254: 16}[t]
+        v = int.from_bytes(buf[pos[0]:pos[0] + n], "little")
+        pos[0] += n
+        return v
+    head = tuple(vi() for _ in range(6))
+    pbid = []
+    for _ in range(vi()):
+        bid, order = vi(), vi()
+        pbid.append((bid, order, [(vi(), vi(), u8()) for _ in range(vi())]))
+    vmap = {}
+    for _ in range(vi()):
+        key = (vi(), vi())
+        vmap[key] = (vi(), u8(), vi())
+    assert pos[0] == len(buf)
+    return head, pbid, vmap

@@ -3,8 +3,9 @@
 //       [--min-cov 0] [--min-branch-size 8] [--bundle-length-cutoff 2500] [--bundle-merge-distance 10000]
 // Shimmers, ShmmrFragMap, MAP-graph adjacency list and vertex weights come from the GPU; the bundle walk, the consensus
 // ordering, the per-contig decomposition and the writers are host bookkeeping as in the reference.  Written:
-// <prefix>.mapg.gfa, <prefix>.mapg.idx, <prefix>.pmapg.gfa, <prefix>.bed and <prefix>.ctg.summary.tsv.  Not written (DESIGN.md
-// §7): the bincode .pdb, and the --precomputed-bundles / --include inputs that depend on it.
+// <prefix>.mapg.gfa, <prefix>.mapg.idx, <prefix>.pmapg.gfa, <prefix>.pdb, <prefix>.bed and <prefix>.ctg.summary.tsv; with
+// -p <file.pdb> (--precomputed-bundles) the bundles are read instead of computed and only the .bed / summary are written
+// (pgr-pbundle-decomp.rs:158-226).  Not supported: --include.
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -13,6 +14,7 @@
 #include <string>
 
 #include "mapg_gfa.hpp"
+#include "pdb_io.hpp"
 #include "pbundle.hpp"
 #include "seq_index_db.hpp"
 
@@ -58,7 +60,7 @@ static int all_smps(SeqIndexDB &db, std::vector<std::vector<Smp>> &out) {
 int main(int argc, char **argv) {
     uint32_t w = 48, k = 56, r = 4, min_span = 12;
     size_t min_cov = 0, min_branch_size = 8, bundle_length_cutoff = 2500, bundle_merge_distance = 10000;
-    std::string decomp_path;
+    std::string decomp_path, precomputed;
     std::vector<std::string> pos;
     std::string cmd_string;
     for (int i = 0; i < argc; i++) { if (i) cmd_string += " "; cmd_string += argv[i]; }
@@ -74,63 +76,77 @@ int main(int argc, char **argv) {
         else if (a == "--bundle-length-cutoff") bundle_length_cutoff = (size_t)atol(val());
         else if (a == "--bundle-merge-distance") bundle_merge_distance = (size_t)atol(val());
         else if (a == "-d" || a == "--decomp-fastx-path") decomp_path = val();
-        else if (a == "-p" || a == "--precomputed-bundles" || a == "-i" || a == "--include") { fprintf(stderr, "error: %s is not supported by this build (bincode .pdb / sequence store, DESIGN.md)\n", a.c_str()); return 2; }
+        else if (a == "-p" || a == "--precomputed-bundles") precomputed = val();
+        else if (a == "-i" || a == "--include") { fprintf(stderr, "error: %s is not supported by this build\n", a.c_str()); return 2; }
         else if (a == "-h" || a == "--help") { printf("usage: pgr-b200-pbundle-decomp <fastx_path> <output_prefix> [options of pgr-pbundle-decomp]\n"); return 0; }
         else pos.push_back(a);
     }
     if (pos.size() != 2) { fprintf(stderr, "usage: pgr-b200-pbundle-decomp <fastx_path> <output_prefix> [options of pgr-pbundle-decomp]\n"); return 2; }
 
-    // ---- principal bundles of <fastx_path> (pgr-pbundle-decomp.rs:228-246, ext.rs:491-510,552-650) ----
+    // ---- principal bundles: computed from <fastx_path> (pgr-pbundle-decomp.rs:228-246, ext.rs:491-510,552-650) or read from a
+    // .pdb written earlier (:158-226; its parameters override the command line) ----
     SeqIndexDB db;
     db.keep_sequences(true);
-    if (db.load_from_fastx(pos[0], w, k, r, min_span) != PGR_OK) { fprintf(stderr, "can't read file %s (%s)\n", pos[0].c_str(), db.error().c_str()); return 1; }
-    std::vector<std::vector<BundleVertex>> pb;
-    std::vector<pgr_adj_pair> filtered_adj;
-    {
-        pgr_adj_pair *adj = nullptr;
-        size_t n_adj = 0;
-        if (pgr_b200_adj_list(db.index(), min_cov, nullptr, 0, 0, &adj, &n_adj) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
-        if (n_adj) {
-            pgr_graph_node *verts = nullptr;
-            uint64_t *off = nullptr;
-            pgr_adj_pair *flt = nullptr;
-            size_t nb = 0, nf = 0;
-            if (pgr_b200_principal_bundles(db.index(), adj, n_adj, min_branch_size, &verts, &off, &nb, &flt, &nf) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
-            pb.resize(nb);
-            for (size_t b = 0; b < nb; b++) for (uint64_t i = off[b]; i < off[b + 1]; i++) pb[b].push_back({verts[i].h0, verts[i].h1, verts[i].ori});
-            filtered_adj.assign(flt, flt + nf);
-            pgr_b200_free(verts); pgr_b200_free(off); pgr_b200_free(flt);
-        }
-        pgr_b200_free(adj);
-    }
-    // ---- MAP-graph files (pgr-pbundle-decomp.rs:304-331): the whole graph (min_count 0), its index, the principal graph ----
-    {
-        IndexCsr csr;
-        if (export_csr(db.index(), csr) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
-        pgr_adj_pair *adj0 = nullptr;
-        size_t n0 = 0;
-        if (pgr_b200_adj_list(db.index(), 0, nullptr, 0, 0, &adj0, &n0) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
-        pgr_shmmr_spec sp{w, k, r, min_span, 0};
-        VertexMap plain;                                                      // get_vertex_map_from_principal_bundles (ext.rs:512-531)
-        for (size_t b = 0; b < pb.size(); b++) for (size_t p = 0; p < pb[b].size(); p++) plain[{pb[b][p].h0, pb[b][p].h1}] = {b, pb[b][p].ori, p};
-        const bool ok = write_gfa(with_extension(pos[1], "mapg.gfa"), adj0, n0, csr, k, nullptr) &&
-                        write_mapg_idx(with_extension(pos[1], "mapg.idx"), sp, db.seqs(), csr) &&
-                        write_gfa(with_extension(pos[1], "pmapg.gfa"), filtered_adj.data(), filtered_adj.size(), csr, k, &plain);
-        pgr_b200_free(adj0);
-        if (!ok) { fprintf(stderr, "cannot write the MAP-graph files\n"); return 1; }
-    }
     std::vector<std::vector<Smp>> smps;
-    if (all_smps(db, smps) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
     std::vector<BundleWithId> pbid;
     VertexMap vmap;
-    principal_bundles_with_id(pb, smps, pbid, vmap);
+    if (precomputed.empty()) {
+        if (db.load_from_fastx(pos[0], w, k, r, min_span) != PGR_OK) { fprintf(stderr, "can't read file %s (%s)\n", pos[0].c_str(), db.error().c_str()); return 1; }
+        std::vector<std::vector<BundleVertex>> pb;
+        std::vector<pgr_adj_pair> filtered_adj;
+        {
+            pgr_adj_pair *adj = nullptr;
+            size_t n_adj = 0;
+            if (pgr_b200_adj_list(db.index(), min_cov, nullptr, 0, 0, &adj, &n_adj) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
+            if (n_adj) {
+                pgr_graph_node *verts = nullptr;
+                uint64_t *off = nullptr;
+                pgr_adj_pair *flt = nullptr;
+                size_t nb = 0, nf = 0;
+                if (pgr_b200_principal_bundles(db.index(), adj, n_adj, min_branch_size, &verts, &off, &nb, &flt, &nf) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
+                pb.resize(nb);
+                for (size_t b = 0; b < nb; b++) for (uint64_t i = off[b]; i < off[b + 1]; i++) pb[b].push_back({verts[i].h0, verts[i].h1, verts[i].ori});
+                filtered_adj.assign(flt, flt + nf);
+                pgr_b200_free(verts); pgr_b200_free(off); pgr_b200_free(flt);
+            }
+            pgr_b200_free(adj);
+        }
+        // ---- MAP-graph files (pgr-pbundle-decomp.rs:304-331): the whole graph (min_count 0), its index, the principal graph ----
+        {
+            IndexCsr csr;
+            if (export_csr(db.index(), csr) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
+            pgr_adj_pair *adj0 = nullptr;
+            size_t n0 = 0;
+            if (pgr_b200_adj_list(db.index(), 0, nullptr, 0, 0, &adj0, &n0) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
+            pgr_shmmr_spec sp{w, k, r, min_span, 0};
+            VertexMap plain;                                                      // get_vertex_map_from_principal_bundles (ext.rs:512-531)
+            for (size_t b = 0; b < pb.size(); b++) for (size_t p = 0; p < pb[b].size(); p++) plain[{pb[b][p].h0, pb[b][p].h1}] = {b, pb[b][p].ori, p};
+            const bool ok = write_gfa(with_extension(pos[1], "mapg.gfa"), adj0, n0, csr, k, nullptr) &&
+                            write_mapg_idx(with_extension(pos[1], "mapg.idx"), sp, db.seqs(), csr) &&
+                            write_gfa(with_extension(pos[1], "pmapg.gfa"), filtered_adj.data(), filtered_adj.size(), csr, k, &plain);
+            pgr_b200_free(adj0);
+            if (!ok) { fprintf(stderr, "cannot write the MAP-graph files\n"); return 1; }
+        }
+        if (all_smps(db, smps) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
+        principal_bundles_with_id(pb, smps, pbid, vmap);
+        PdbData pd;                                                           // pgr-pbundle-decomp.rs:367-396
+        pd.w = w; pd.k = k; pd.r = r; pd.min_span = min_span; pd.min_branch_size = min_branch_size; pd.min_cov = min_cov;
+        pd.bundles = pbid; pd.vmap = vmap;
+        if (!write_pdb(with_extension(pos[1], "pdb"), pd)) { fprintf(stderr, "pdb file creating error\n"); return 1; }
+    } else {
+        PdbData pd;
+        if (!read_pdb(precomputed, pd)) { fprintf(stderr, "pdb input file open / reading error\n"); return 1; }
+        w = pd.w; k = pd.k; r = pd.r; min_span = pd.min_span; min_branch_size = (size_t)pd.min_branch_size; min_cov = (size_t)pd.min_cov;
+        pbid = std::move(pd.bundles); vmap = std::move(pd.vmap);
+    }
 
     // ---- the database that is decomposed (pgr-pbundle-decomp.rs:257-276) ----
     SeqIndexDB ddb_other;
     SeqIndexDB *ddb = &db;
-    if (!decomp_path.empty()) {
+    if (!decomp_path.empty() || !precomputed.empty()) {
+        const std::string dpath = decomp_path.empty() ? pos[0] : decomp_path;
         ddb_other.keep_sequences(true);
-        if (ddb_other.load_from_fastx(decomp_path, w, k, r, min_span) != PGR_OK) { fprintf(stderr, "can't read file %s\n", decomp_path.c_str()); return 1; }
+        if (ddb_other.load_from_fastx(dpath, w, k, r, min_span) != PGR_OK) { fprintf(stderr, "can't read file %s\n", dpath.c_str()); return 1; }
         ddb = &ddb_other;
         if (all_smps(*ddb, smps) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
     }

@@ -212,6 +212,15 @@ def test_pbundle_decomp_cli_matches_oracle(tmp_path):
         plain = {(v[0], v[1]): (b, v[2], p) for b, path in enumerate(pb) for p, v in enumerate(path)}
         pm = open(prefix + ".pmapg.gfa").read()
         assert pm == pbo.gfa_text(flt, fmap, spec_t[1], plain) and "\tBN:i:" in pm
+        # the .pdb: same content as the oracle's bundles; and -p reads it back to the same decomposition
+        head, d_pbid, d_vmap = pbo.decode_pdb(open(prefix + ".pdb", "rb").read())
+        assert head == spec_t + (branch, 0) and d_pbid == [(b, o_, list(v)) for b, o_, v in pbid] and d_vmap == vmap
+        assert open(prefix + ".pdb", "rb").read() == pbo.encode_pdb(*spec_t, branch, 0, pbid, vmap)
+        prefix2 = prefix + "_from_pdb"
+        subprocess.check_call([PCLI, fa, prefix2, "-p", prefix + ".pdb", "-w", "80", "--bundle-length-cutoff", str(cut), "--bundle-merge-distance", str(merge)], cwd=ROOT)
+        assert open(prefix2 + ".bed").read().split("\n")[1:] == bed.split("\n")[1:]
+        assert open(prefix2 + ".ctg.summary.tsv").read() == summ
+        assert not os.path.exists(prefix2 + ".mapg.gfa") and not os.path.exists(prefix2 + ".pdb")
 
 
 def test_query_cli_frg_backend_and_reference_fragment_store(tmp_path):
