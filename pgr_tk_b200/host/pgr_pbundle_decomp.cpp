@@ -5,7 +5,7 @@
 // ordering, the per-contig decomposition and the writers are host bookkeeping as in the reference.  Written:
 // <prefix>.mapg.gfa, <prefix>.mapg.idx, <prefix>.pmapg.gfa, <prefix>.pdb, <prefix>.bed and <prefix>.ctg.summary.tsv; with
 // -p <file.pdb> (--precomputed-bundles) the bundles are read instead of computed and only the .bed / summary are written
-// (pgr-pbundle-decomp.rs:158-226).  Not supported: --include.
+// (pgr-pbundle-decomp.rs:158-226); with -i <file> (--include) only the listed contigs are decomposed (:278-301).
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -60,7 +60,7 @@ static int all_smps(SeqIndexDB &db, std::vector<std::vector<Smp>> &out) {
 int main(int argc, char **argv) {
     uint32_t w = 48, k = 56, r = 4, min_span = 12;
     size_t min_cov = 0, min_branch_size = 8, bundle_length_cutoff = 2500, bundle_merge_distance = 10000;
-    std::string decomp_path, precomputed;
+    std::string decomp_path, precomputed, include_path;
     std::vector<std::string> pos;
     std::string cmd_string;
     for (int i = 0; i < argc; i++) { if (i) cmd_string += " "; cmd_string += argv[i]; }
@@ -77,7 +77,7 @@ int main(int argc, char **argv) {
         else if (a == "--bundle-merge-distance") bundle_merge_distance = (size_t)atol(val());
         else if (a == "-d" || a == "--decomp-fastx-path") decomp_path = val();
         else if (a == "-p" || a == "--precomputed-bundles") precomputed = val();
-        else if (a == "-i" || a == "--include") { fprintf(stderr, "error: %s is not supported by this build\n", a.c_str()); return 2; }
+        else if (a == "-i" || a == "--include") include_path = val();
         else if (a == "-h" || a == "--help") { printf("usage: pgr-b200-pbundle-decomp <fastx_path> <output_prefix> [options of pgr-pbundle-decomp]\n"); return 0; }
         else pos.push_back(a);
     }
@@ -148,6 +148,36 @@ int main(int argc, char **argv) {
         ddb_other.keep_sequences(true);
         if (ddb_other.load_from_fastx(dpath, w, k, r, min_span) != PGR_OK) { fprintf(stderr, "can't read file %s\n", dpath.c_str()); return 1; }
         ddb = &ddb_other;
+        if (all_smps(*ddb, smps) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
+    }
+    SeqIndexDB ddb_included;
+    if (!include_path.empty()) {                                              // pgr-pbundle-decomp.rs:278-301
+        FILE *inc = fopen(include_path.c_str(), "rb");
+        if (!inc) { fprintf(stderr, "can't open the include file\n"); return 1; }
+        std::vector<std::string> names;
+        char *line = nullptr;
+        size_t cap = 0;
+        ssize_t n;
+        while ((n = getline(&line, &cap, inc)) > 0) {
+            std::string l(line, (size_t)n);
+            while (!l.empty() && (l.back() == '\n' || l.back() == '\r')) l.pop_back();
+            if (std::find(names.begin(), names.end(), l) == names.end()) names.push_back(l);   // a set in the reference; file order here
+        }
+        free(line);
+        fclose(inc);
+        std::vector<SeqRec> list;
+        for (const auto &nm : names) {
+            const CompactSeq *hit = nullptr;
+            for (const auto &cs : ddb->seqs()) if (cs.name == nm) { hit = &cs; break; }
+            SeqRec rec;
+            rec.id = nm;
+            if (!hit || !ddb->get_sub_seq_by_id(hit->id, 0, hit->len, rec.seq)) { fprintf(stderr, "fail to fetch sequence %s\n", nm.c_str()); return 1; }
+            list.push_back(std::move(rec));
+        }
+        const std::string src = decomp_path.empty() ? pos[0] : decomp_path;
+        ddb_included.keep_sequences(true);
+        if (ddb_included.load_from_seq_list(list, src, w, k, r, min_span) != PGR_OK) { fprintf(stderr, "%s\n", ddb_included.error().c_str()); return 1; }
+        ddb = &ddb_included;
         if (all_smps(*ddb, smps) != PGR_OK) { fprintf(stderr, "%s\n", pgr_b200_last_error()); return 1; }
     }
 

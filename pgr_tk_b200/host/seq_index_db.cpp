@@ -96,6 +96,21 @@ int SeqIndexDB::append_from_fastx(const std::string &path) {
 int SeqIndexDB::load_seqs_from_fastx(const std::string &path) {
     std::vector<SeqRec> recs;
     if (!read_fastx(path, recs, err_)) return PGR_E_IO;
+    return add_records(recs, path);
+}
+
+int SeqIndexDB::load_from_seq_list(const std::vector<SeqRec> &seq_list, const std::string &source, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span) {
+    spec_.w = w; spec_.k = k; spec_.r = r; spec_.min_span = min_span; spec_.sketch = 0;
+    if (idx_) { pgr_b200_index_free(idx_); idx_ = nullptr; }
+    seqs_.clear();
+    seq_data_.clear();
+    idx_ = pgr_b200_index_new(&spec_, 0, -1);
+    if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
+    std::vector<SeqRec> recs = seq_list;
+    return add_records(recs, source);
+}
+
+int SeqIndexDB::add_records(std::vector<SeqRec> &recs, const std::string &source) {
     uint32_t sid = (uint32_t)seqs_.size();
     std::vector<uint32_t> sids;
     std::vector<const uint8_t *> ptrs;
@@ -105,7 +120,7 @@ int SeqIndexDB::load_seqs_from_fastx(const std::string &path) {
         ptrs.push_back(r.seq.data());
         lens.push_back(r.seq.size());
         CompactSeq cs;
-        cs.id = sid; cs.len = r.seq.size(); cs.name = r.id; cs.source = path;
+        cs.id = sid; cs.len = r.seq.size(); cs.name = r.id; cs.source = source;
         seqs_.push_back(std::move(cs));
         sid++;
     }

@@ -55,6 +55,8 @@ public:
     int load_from_fastx(const std::string &path, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span);
     // ext.rs:180-199
     int append_from_fastx(const std::string &path);
+    // ext.rs:212-250 load_from_seq_list: sequences given in memory, sids in list order
+    int load_from_seq_list(const std::vector<SeqRec> &seq_list, const std::string &source, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span);
     // index part of ext.rs:87-150 (load_from_agc_index / load_from_frg_index): <prefix>.mdb + <prefix>.midx; sequences are
     // not available afterwards (the .agc / .frg stores are out of scope)
     int load_from_index_files(const std::string &prefix);
@@ -78,6 +80,7 @@ public:
 
 private:
     int load_seqs_from_fastx(const std::string &path);
+    int add_records(std::vector<SeqRec> &recs, const std::string &source);
     pgr_b200_index *idx_ = nullptr;
     pgr_shmmr_spec spec_{};
     std::vector<CompactSeq> seqs_;

@@ -221,6 +221,16 @@ def test_pbundle_decomp_cli_matches_oracle(tmp_path):
         assert open(prefix2 + ".bed").read().split("\n")[1:] == bed.split("\n")[1:]
         assert open(prefix2 + ".ctg.summary.tsv").read() == summ
         assert not os.path.exists(prefix2 + ".mapg.gfa") and not os.path.exists(prefix2 + ".pdb")
+        # --include: only the listed contigs are decomposed (against the bundles of the whole file)
+        inc = tmp_path / ("inc%d.txt" % cut)
+        chosen = ["hap_03", "hap_09", "hap_01"]
+        inc.write_text("\n".join(chosen) + "\n")
+        prefix3 = prefix + "_inc"
+        subprocess.check_call([PCLI, fa, prefix3, "-i", str(inc)] + extra, cwd=ROOT)
+        keep = lambda text: [l for l in text.split("\n")[1:] if l and l.split("\t")[0] in chosen]
+        assert keep(open(prefix3 + ".bed").read()) == keep(bed) and len(keep(bed)) > 3
+        assert [l for l in open(prefix3 + ".bed").read().split("\n")[1:] if l] == keep(bed)
+        assert keep(open(prefix3 + ".ctg.summary.tsv").read()) == keep(summ) and len(keep(summ)) == 3
 
 
 def test_query_cli_frg_backend_and_reference_fragment_store(tmp_path):
