@@ -26,8 +26,8 @@ class Spec(C.Structure):
 
 
 def build(force=False):
-    src = os.path.join(ORACLE_DIR, "pgr_oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("pgr_oracle.cpp", "frag_oracle.cpp", "pgr_oracle.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return _LIB_PATH
 
