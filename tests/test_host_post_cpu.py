@@ -165,3 +165,74 @@ def test_bundle_ids_and_grouping_cpp_equals_oracle(tmp_path):
             for p in pbo.group_smps(smps[s], vmap, cutoff, merge):
                 exp.append("P %d " % s + " ".join("%d,%d,%d,%d" % (e[0][0], e[1], e[2], e[3]) for e in p))
         assert got == "".join(l + "\n" for l in exp), trial
+
+
+GPROG = r'''
+#include <cstdio>
+#include "mapg_gfa.hpp"
+using namespace pgrb200;
+// input: k; n_keys, per key: h0 h1 n, per sig: frg sid bgn end ori; n_adj, per pair: sid a0 a1 o0 b0 b1 o1; n_vmap, per: h0 h1 bundle ori pos
+int main(int argc, char **argv) {
+    unsigned k; size_t nk;
+    if (scanf("%u %zu", &k, &nk) != 2) return 2;
+    IndexCsr csr; csr.offsets.push_back(0);
+    for (size_t i = 0; i < nk; i++) {
+        uint64_t h0, h1; size_t n;
+        if (scanf("%lu %lu %zu", &h0, &h1, &n) != 3) return 2;
+        csr.keys.push_back(h0); csr.keys.push_back(h1);
+        for (size_t j = 0; j < n; j++) { pgr_frag_sig s; memset(&s, 0, sizeof s); unsigned o; if (scanf("%u %u %u %u %u", &s.frg_id, &s.sid, &s.bgn, &s.end, &o) != 5) return 2; s.ori = (uint8_t)o; csr.sigs.push_back(s); }
+        csr.offsets.push_back(csr.sigs.size());
+    }
+    size_t na;
+    if (scanf("%zu", &na) != 1) return 2;
+    std::vector<pgr_adj_pair> adj(na);
+    for (auto &a : adj) { memset(&a, 0, sizeof a); unsigned o0, o1; if (scanf("%u %lu %lu %u %lu %lu %u", &a.sid, &a.a0, &a.a1, &o0, &a.b0, &a.b1, &o1) != 7) return 2; a.ori0 = (uint8_t)o0; a.ori1 = (uint8_t)o1; }
+    size_t nv;
+    if (scanf("%zu", &nv) != 1) return 2;
+    VertexMap vm;
+    for (size_t i = 0; i < nv; i++) { uint64_t h0, h1; size_t b, p; unsigned o; if (scanf("%lu %lu %zu %u %zu", &h0, &h1, &b, &o, &p) != 5) return 2; vm[{h0, h1}] = {b, (uint8_t)o, p}; }
+    std::vector<CompactSeq> seqs = {{0, 20, "a", "f.fa"}, {1, 30, "b", ""}};
+    pgr_shmmr_spec sp{80, k, 4, 64, 0};
+    return write_gfa(argv[1], adj.data(), adj.size(), csr, k, nv ? &vm : nullptr) && write_mapg_idx(argv[2], sp, seqs, csr) ? 0 : 3;
+}
+'''
+
+
+def test_gfa_writers_cpp_equal_oracle(tmp_path):
+    import pgr_tk_b200 as pg
+    if not os.path.exists(pg.library_path()):
+        pg.build_library()
+    src = tmp_path / "gfa.cpp"
+    src.write_text("#include <cstring>\n" + GPROG)
+    exe = str(tmp_path / "gfa")
+    libdir = os.path.dirname(pg.library_path())
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", HOST, "-o", exe, str(src), "-L" + libdir, "-lpgr_b200", "-Wl,-rpath," + libdir])
+    rng = np.random.default_rng(12)
+    for trial in range(10):
+        keys = sorted({(int(rng.integers(1, 1 << 50)), int(rng.integers(1, 1 << 50))) for _ in range(12)})
+        fmap, frg = {}, 0
+        for kk in keys:
+            sigs = []
+            for _ in range(int(rng.integers(1, 5))):
+                b = int(rng.integers(57, 5000))
+                sigs.append((frg, int(rng.integers(0, 2)), b, b + int(rng.integers(10, 900)), int(rng.integers(0, 2))))
+                frg += 1
+            fmap[kk] = sigs
+        adj = []
+        for _ in range(int(rng.integers(3, 30))):
+            v, w = keys[int(rng.integers(0, len(keys)))], keys[int(rng.integers(0, len(keys)))]
+            adj.append((int(rng.integers(0, 2)), (v[0], v[1], int(rng.integers(0, 2))), (w[0], w[1], int(rng.integers(0, 2)))))
+        vmap = {kk: (int(rng.integers(0, 4)), int(rng.integers(0, 2)), int(rng.integers(0, 9))) for kk in keys[::3]} if trial % 2 else {}
+        inp = ["56 %d" % len(keys)]
+        for kk in keys:
+            inp.append("%d %d %d " % (kk[0], kk[1], len(fmap[kk])) + " ".join("%d %d %d %d %d" % s for s in fmap[kk]))
+        inp.append(str(len(adj)))
+        for sid, v, w in adj:
+            inp.append("%d %d %d %d %d %d %d" % (sid, v[0], v[1], v[2], w[0], w[1], w[2]))
+        inp.append(str(len(vmap)))
+        for kk, b in vmap.items():
+            inp.append("%d %d %d %d %d" % (kk[0], kk[1], b[0], b[1], b[2]))
+        g, x = str(tmp_path / "o.gfa"), str(tmp_path / "o.idx")
+        subprocess.run([exe, g, x], input="\n".join(inp) + "\n", text=True, check=True)
+        assert open(g).read() == pbo.gfa_text(adj, fmap, 56, vmap if vmap else None), trial
+        assert open(x).read() == pbo.mapg_idx_text((80, 56, 4, 64, 0), [(0, 20, "a", "f.fa"), (1, 30, "b", None)], fmap)
