@@ -78,3 +78,38 @@ def test_sketch_local():
         ref = orc.sequence_to_shmmrs(3, seq, orc.mkspec(80, k, r, ms, True))
         xs, ys = lr.sketch_local(3, seq, k, r, ms)
         assert list(ref["x"]) == list(xs) and list(ref["y"]) == list(ys)
+
+
+def test_prefix_candidates_plus_tie_rule_equal_exact_selection():
+    """The tile kernel selects on a PREFIX of the key (24 bits) and repairs the result with one rule (phase 5): a
+    candidate (selected on the prefixes) that has no other candidate with the same prefix within distance < w is
+    selected for sure; one that has is tested exactly.  This is that argument as a property test on the numpy model,
+    with prefixes short enough (3-6 bits) that ties are everywhere:
+      * every exactly selected position is a prefix candidate,
+      * every prefix candidate without a same-prefix candidate within w-1 positions is exactly selected,
+    so testing only the tied candidates exactly gives the exact selection."""
+    rng = np.random.default_rng(77)
+    for trial in range(60):
+        n = int(rng.integers(50, 600))
+        w = int(rng.integers(2, 130))
+        bits = int(rng.integers(3, 7))
+        x = rng.integers(0, 1 << 20, size=n, dtype=np.int64)
+        if trial % 3 == 0:                               # runs of equal keys (tandem repeats)
+            x[rng.integers(0, n, size=n // 3)] = x[rng.integers(0, n)]
+        if n < w:
+            continue
+        pre = x >> (20 - bits)
+        exact = lr.window_select(x, w)
+        cand = lr.window_select(pre, w)
+        assert not (exact & ~cand).any()                 # candidates are a superset
+        idx = np.nonzero(cand)[0]
+        tied = np.zeros(n, dtype=bool)
+        for a, i in enumerate(idx):                      # neighbouring candidates within distance < w with the same prefix
+            for j in idx[max(0, a - w):a + w + 1]:
+                if j != i and abs(int(j) - int(i)) < w and pre[j] == pre[i]:
+                    tied[i] = True
+                    break
+        untied = cand & ~tied
+        assert not (untied & ~exact).any()               # an untied candidate is exactly selected
+        repaired = untied | (tied & exact)               # tied candidates get the exact test
+        assert np.array_equal(repaired, exact)
