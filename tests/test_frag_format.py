@@ -135,3 +135,55 @@ def test_cpp_fragment_oracle_equals_the_fixture_and_the_python_oracle():
     fr, sg = orc.compress_fragments(list(range(len(seqs2))), seqs2, orc.mkspec(48, 56, 4, 12), nthreads=2)
     exp = oracle_db([("s%d" % i, s) for i, s in enumerate(seqs2)], (48, 56, 4, 12)).frags
     assert _records_to_tuples(fr, sg, seqs2) == exp
+
+
+def test_row_parallel_scheme_equals_the_sequential_decisions():
+    """frags.cu decides a shimmer-pair row in two steps - every entry against the row's first entry in parallel, then the
+    entries that failed there sequentially - instead of the reference's one sequential walk (seq_db.rs:258-318).  The two
+    are the same function of (row order, sequence ids, fragment lengths, which pairs align): property test on random rows
+    with an arbitrary `aligns(i, j)` relation."""
+    import numpy as np
+    rng = np.random.default_rng(31)
+    for trial in range(300):
+        m = int(rng.integers(1, 14))
+        sid = np.sort(rng.integers(0, 6, size=m))
+        long_ = rng.random(m) < 0.8                       # frg_len > 128
+        ok = rng.random((m, m)) < rng.choice([0.2, 0.6, 0.95])
+
+        def sequential():
+            kind, ref = ["I"] * m, [None] * m
+            for j in range(m):
+                if not long_[j]:
+                    continue
+                for i in range(j):
+                    if sid[i] >= sid[j]:                  # frag_map holds earlier sequences only
+                        break
+                    if kind[i] != "I":
+                        continue
+                    if ok[i, j]:
+                        kind[j], ref[j] = "A", i
+                        break
+            return kind, ref
+
+        def two_step():
+            kind, ref = ["I"] * m, [None] * m
+            for j in range(1, m):                         # pass 0a: independent of each other
+                if long_[j] and sid[0] < sid[j]:
+                    if ok[0, j]:
+                        kind[j], ref[j] = "A", 0
+                    else:
+                        kind[j] = "P"
+            for j in range(1, m):                         # pass 0b: the pending ones, in order
+                if kind[j] != "P":
+                    continue
+                kind[j] = "I"
+                for i in range(1, j):
+                    if sid[i] >= sid[j]:
+                        break
+                    if kind[i] != "I":
+                        continue
+                    if ok[i, j]:
+                        kind[j], ref[j] = "A", i
+                        break
+            return kind, ref
+        assert sequential() == two_step(), trial
