@@ -355,27 +355,19 @@ static bool deflate_raw(const std::vector<uint8_t> &in, std::vector<uint8_t> &ou
     return rc == Z_STREAM_END;
 }
 
-int SeqIndexDB::write_to_frag_files(const std::string &prefix, size_t chunk_size) {
-    if (!idx_) { err_ = "no index"; return PGR_E_ARG; }
-    if (seq_data_.size() != seqs_.size()) { err_ = "write_to_frag_files needs the sequences (keep_sequences(true) before loading)"; return PGR_E_ARG; }
-    std::vector<uint32_t> sids;
-    std::vector<const uint8_t *> ptrs;
-    std::vector<size_t> lens;
-    for (size_t i = 0; i < seqs_.size(); i++) { sids.push_back(seqs_[i].id); ptrs.push_back(seq_data_[i].data()); lens.push_back(seq_data_[i].size()); }
-    pgr_fragment *frags = nullptr;
-    pgr_aln_seg *segs = nullptr;
-    size_t nf = 0, nsg = 0;
-    int rc = pgr_b200_index_compress_fragments(idx_, seqs_.size(), sids.data(), ptrs.data(), lens.data(), &frags, &nf, &segs, &nsg);
-    if (rc != PGR_OK) { err_ = pgr_b200_last_error(); return rc; }
+// seq_db.rs:814-873 on the fragment records of pgr_b200_index_compress_fragments (tests feed the oracle's records, which
+// have the same layout, to run this writer without a device)
+int write_frag_store(const std::string &prefix, size_t chunk_size, uint32_t k, const pgr_fragment *frags, size_t nf, const pgr_aln_seg *segs,
+                     const std::vector<CompactSeq> &seqs, const std::vector<std::vector<uint8_t>> &seq_data, std::string &err) {
+    if (chunk_size == 0 || seq_data.size() != seqs.size()) { err = "write_frag_store: bad arguments"; return PGR_E_ARG; }
     FILE *frg = fopen((prefix + ".frg").c_str(), "wb"), *sdx = fopen((prefix + ".sdx").c_str(), "wb");
-    if (!frg || !sdx) { err_ = "frag file creating fail"; if (frg) fclose(frg); if (sdx) fclose(sdx); pgr_b200_free(frags); pgr_b200_free(segs); return PGR_E_IO; }
+    if (!frg || !sdx) { err = "frag file creating fail"; if (frg) fclose(frg); if (sdx) fclose(sdx); return PGR_E_IO; }
     fwrite("FRG:0.5", 1, 7, frg);
     fwrite("SDX:0.5", 1, 7, sdx);
-    const uint32_t k = spec_.k;
     std::vector<uint8_t> sd;
     put_varint(sd, chunk_size);
     put_varint(sd, (nf + chunk_size - 1) / chunk_size);
-    std::vector<std::pair<uint32_t, uint32_t>> range(seqs_.size(), {0, 0});   // per sequence (first fragment, count)
+    std::vector<std::pair<uint32_t, uint32_t>> range(seqs.size(), {0, 0});   // per sequence (first fragment, count)
     uint64_t offset = 0;
     for (size_t c0 = 0; c0 < nf; c0 += chunk_size) {
         const size_t c1 = std::min(nf, c0 + chunk_size);
@@ -384,6 +376,7 @@ int SeqIndexDB::write_to_frag_files(const std::string &prefix, size_t chunk_size
         uint32_t total_len = 0;
         for (size_t i = c0; i < c1; i++) {
             const pgr_fragment &f = frags[i];
+            if (f.sid >= seqs.size() || f.end > seq_data[f.sid].size() || f.bgn > f.end) { err = "fragment record out of range"; fclose(frg); fclose(sdx); return PGR_E_ARG; }
             auto &rg = range[f.sid];
             if (rg.second == 0) rg.first = (uint32_t)i;
             rg.second++;
@@ -397,29 +390,45 @@ int SeqIndexDB::write_to_frag_files(const std::string &prefix, size_t chunk_size
                 }
                 total_len += f.len - k;
             } else {
-                put_bytes(w, seq_data_[f.sid].data() + f.bgn, f.end - f.bgn);
+                put_bytes(w, seq_data[f.sid].data() + f.bgn, f.end - f.bgn);
                 total_len += f.kind == 2 ? f.len - k : f.len;
             }
         }
-        if (!deflate_raw(w, z)) { err_ = "deflate failed"; fclose(frg); fclose(sdx); pgr_b200_free(frags); pgr_b200_free(segs); return PGR_E_IO; }
+        if (!deflate_raw(w, z)) { err = "deflate failed"; fclose(frg); fclose(sdx); return PGR_E_IO; }
         fwrite(z.data(), 1, z.size(), frg);
         put_varint(sd, offset); put_varint(sd, z.size()); put_varint(sd, total_len);
         offset += z.size();
     }
-    put_varint(sd, seqs_.size());
-    for (size_t i = 0; i < seqs_.size(); i++) {              // CompactSeq {source: Option<String>, name, id, seq_frag_range, len}
-        sd.push_back(1); put_string(sd, seqs_[i].source);
-        put_string(sd, seqs_[i].name);
-        put_varint(sd, seqs_[i].id);
+    put_varint(sd, seqs.size());
+    for (size_t i = 0; i < seqs.size(); i++) {               // CompactSeq {source: Option<String>, name, id, seq_frag_range, len}
+        sd.push_back(1); put_string(sd, seqs[i].source);
+        put_string(sd, seqs[i].name);
+        put_varint(sd, seqs[i].id);
         put_varint(sd, range[i].first); put_varint(sd, range[i].second);
-        put_varint(sd, seqs_[i].len);
+        put_varint(sd, seqs[i].len);
     }
     fwrite(sd.data(), 1, sd.size(), sdx);
     fclose(frg);
     fclose(sdx);
+    return PGR_OK;
+}
+
+int SeqIndexDB::write_to_frag_files(const std::string &prefix, size_t chunk_size) {
+    if (!idx_) { err_ = "no index"; return PGR_E_ARG; }
+    if (seq_data_.size() != seqs_.size()) { err_ = "write_to_frag_files needs the sequences (keep_sequences(true) before loading)"; return PGR_E_ARG; }
+    std::vector<uint32_t> sids;
+    std::vector<const uint8_t *> ptrs;
+    std::vector<size_t> lens;
+    for (size_t i = 0; i < seqs_.size(); i++) { sids.push_back(seqs_[i].id); ptrs.push_back(seq_data_[i].data()); lens.push_back(seq_data_[i].size()); }
+    pgr_fragment *frags = nullptr;
+    pgr_aln_seg *segs = nullptr;
+    size_t nf = 0, nsg = 0;
+    int rc = pgr_b200_index_compress_fragments(idx_, seqs_.size(), sids.data(), ptrs.data(), lens.data(), &frags, &nf, &segs, &nsg);
+    if (rc != PGR_OK) { err_ = pgr_b200_last_error(); return rc; }
+    rc = write_frag_store(prefix, chunk_size, spec_.k, frags, nf, segs, seqs_, seq_data_, err_);
     pgr_b200_free(frags);
     pgr_b200_free(segs);
-    return PGR_OK;
+    return rc;
 }
 
 int SeqIndexDB::write_shmmr_map_index(const std::string &prefix) {

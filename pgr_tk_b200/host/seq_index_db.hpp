@@ -45,6 +45,10 @@ private:
     std::vector<std::pair<uint64_t, std::vector<Fragment>>> cache_;   // (chunk id, fragments), a few recent chunks
 };
 
+// seq_db.rs:814-873 write_to_frag_files on fragment records laid out as pgr_b200_index_compress_fragments returns them
+int write_frag_store(const std::string &prefix, size_t chunk_size, uint32_t k, const pgr_fragment *frags, size_t n_frags, const pgr_aln_seg *segs,
+                     const std::vector<CompactSeq> &seqs, const std::vector<std::vector<uint8_t>> &seq_data, std::string &err);
+
 class SeqIndexDB {
 public:
     SeqIndexDB() = default;
