@@ -146,6 +146,9 @@ int pgr_b200_index_add_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids
 int pgr_b200_index_stage_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
                                uint64_t *n_frags_in_batch);
 int pgr_b200_index_commit_batch(pgr_b200_index *idx, uint32_t frag_base);
+/* stage_batch for sequences that already live in device memory (layout rules of pgr_b200_ctx_set_device_seqs) */
+int pgr_b200_index_stage_device(pgr_b200_index *idx, const uint8_t *dev_base, size_t n, const uint32_t *sids, const uint64_t *offs,
+                                const uint64_t *lens, uint64_t *n_frags_in_batch);
 /* stable sort by (h0,h1) and CSR build; implied by every read access */
 int pgr_b200_index_finalize(pgr_b200_index *idx);
 int pgr_b200_index_counts(pgr_b200_index *idx, size_t *n_keys, size_t *n_sigs, uint32_t *n_frags);
@@ -162,6 +165,60 @@ int pgr_b200_index_partition(pgr_b200_index *idx, size_t n_parts, const uint64_t
 /* write_shmmr_map_file (seq_db.rs:1291-1326; keys written ascending) / read_mdb_file (seq_db.rs:1328-1407) */
 int pgr_b200_index_write_mdb(pgr_b200_index *idx, const char *path);
 pgr_b200_index *pgr_b200_index_read_mdb(const char *path, int device);
+
+/* ---- multi-GPU ShmmrFragMap build -------------------------------------------------------------------- */
+/* Sequences shard over the GPUs in blocks; shimmers and tuples are computed where the sequences are; ONE all-to-all of
+ * the 40-byte tuples (grouped ncclSend/ncclRecv over NVLink, key ranges cut at sampled splitters of h0) leaves every GPU
+ * with one key range, which it sorts (stable) into its CSR slice.  Slices in rank order = the canonical key-ascending map
+ * of load_seqs_from_seq_vec / load_index_from_seq_vec (seq_db.rs:507-525, :573-615): per-key vectors in insertion order,
+ * FASTX fragment ids from one global running counter.  Two process models:
+ *   (1) one process per GPU (torchrun): pgr_b200_comm_unique_id on rank 0, broadcast the bytes, pgr_b200_comm_init_rank
+ *       everywhere, then the collective pgr_b200_index_build_sharded with each rank's contiguous block of the sequence list;
+ *   (2) one process, n_gpus devices (what §8b's `pgr_b200_index_new(spec, mode, n_gpus)` names): pgr_b200_mindex_*.    */
+#define PGR_B200_COMM_ID_BYTES 128
+typedef struct pgr_b200_comm pgr_b200_comm;      /* one rank of an NCCL communicator */
+typedef struct pgr_b200_mindex pgr_b200_mindex;  /* a ShmmrFragMap sharded by key range over the GPUs of one process */
+typedef struct {
+    uint32_t rank, n_ranks;
+    uint64_t n_tuples_local;   /* tuples produced from this rank's sequences                    */
+    uint64_t n_tuples_sent;    /* of those, tuples that left this GPU in the all-to-all          */
+    uint64_t n_tuples_owned;   /* tuples of this rank's key range after the exchange             */
+    uint64_t bytes_sent, bytes_recv;   /* all-to-all payload that crossed NVLink (40 B per tuple) */
+    uint64_t total_frags;      /* global fragment count (frags.len() of the reference)           */
+    float stage_ms, partition_ms, exchange_ms, sort_ms;   /* CUDA events on this rank's stream    */
+} pgr_shard_stats;
+int pgr_b200_comm_unique_id(uint8_t id[PGR_B200_COMM_ID_BYTES]);
+pgr_b200_comm *pgr_b200_comm_init_rank(const uint8_t id[PGR_B200_COMM_ID_BYTES], int rank, int n_ranks, int device);
+void pgr_b200_comm_free(pgr_b200_comm *comm);
+/* collective over `comm`: this rank's block (HOST buffers; ranks hold consecutive blocks of the global sequence list in
+ * rank order) -> idx holds this rank's key range, finalized.  stats may be NULL. */
+int pgr_b200_index_build_sharded(pgr_b200_index *idx, pgr_b200_comm *comm, size_t n, const uint32_t *sids, const uint8_t *const *seqs,
+                                 const size_t *lens, pgr_shard_stats *stats);
+/* the same with the block already resident in this rank's HBM (layout rules of pgr_b200_ctx_set_device_seqs) */
+int pgr_b200_index_build_sharded_device(pgr_b200_index *idx, pgr_b200_comm *comm, const uint8_t *dev_base, size_t n, const uint32_t *sids,
+                                        const uint64_t *offs, const uint64_t *lens, pgr_shard_stats *stats);
+/* the exchange step alone (collective): idx holds committed tuples of this rank's block */
+int pgr_b200_index_merge(pgr_b200_index *idx, pgr_b200_comm *comm, pgr_shard_stats *stats);
+
+/* one process, n_gpus devices (0 .. n_gpus-1), one host thread and one NCCL rank per device (ncclCommInitAll) */
+pgr_b200_mindex *pgr_b200_mindex_new(const pgr_shmmr_spec *spec, int frg_id_mode, int n_gpus);
+/* explicit device list; shards that share a device (testing the sharded build on one GPU) exchange through
+ * device-to-device copies instead of NCCL, which refuses duplicate devices */
+pgr_b200_mindex *pgr_b200_mindex_new_devices(const pgr_shmmr_spec *spec, int frg_id_mode, int n_shards, const int *devices);
+void pgr_b200_mindex_free(pgr_b200_mindex *m);
+int pgr_b200_mindex_n_shards(const pgr_b200_mindex *m);
+/* replaces load_seqs_from_seq_vec / load_index_from_seq_vec for the index part: the batch is cut into n_gpus consecutive
+ * blocks of about equal bases; may be called once per input file like the reference does */
+int pgr_b200_mindex_add_batch(pgr_b200_mindex *m, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens);
+/* the all-to-all merge + per-owner sort; implied by every read access */
+int pgr_b200_mindex_finalize(pgr_b200_mindex *m);
+int pgr_b200_mindex_counts(pgr_b200_mindex *m, size_t *n_keys, size_t *n_sigs, uint32_t *n_frags);
+int pgr_b200_mindex_stats(pgr_b200_mindex *m, int shard, pgr_shard_stats *out);
+/* shard `s` as an ordinary index (borrowed; owned by m): query / adjacency / export of one key range */
+pgr_b200_index *pgr_b200_mindex_shard(pgr_b200_mindex *m, int shard);
+/* canonical CSR / .mdb of the whole map = the slices in shard order (same layout as the single-GPU calls) */
+int pgr_b200_mindex_export_csr(pgr_b200_mindex *m, uint64_t *keys, uint64_t *offsets, pgr_frag_sig *sigs);
+int pgr_b200_mindex_write_mdb(pgr_b200_mindex *m, const char *path);
 
 /* ---- query, chaining, adjacency ------------------------------------------------------------------------------ */
 /* replaces seq_db::raw_query_fragment(&frag_map, &query, &spec) -> Vec<FragmentHit> (seq_db.rs:1200-1228): per query

@@ -45,6 +45,16 @@ class QueryParams(C.Structure):
                 ("max_aln_span", C.c_int64), ("max_gap", C.c_int64), ("oriented", C.c_int32)]
 
 
+class ShardStats(C.Structure):
+    """pgr_shard_stats: what one rank did in the multi-GPU build"""
+    _fields_ = [("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("n_tuples_local", C.c_uint64), ("n_tuples_sent", C.c_uint64),
+                ("n_tuples_owned", C.c_uint64), ("bytes_sent", C.c_uint64), ("bytes_recv", C.c_uint64), ("total_frags", C.c_uint64),
+                ("stage_ms", C.c_float), ("partition_ms", C.c_float), ("exchange_ms", C.c_float), ("sort_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class QueryResult(C.Structure):
     _fields_ = [("n_queries", C.c_size_t), ("n_targets", C.c_size_t), ("n_chains", C.c_size_t), ("n_hits", C.c_size_t),
                 ("q_target_off", C.POINTER(C.c_uint64)), ("target_sid", C.POINTER(C.c_uint32)),
@@ -68,11 +78,28 @@ def build_library(force=False):
 _lib = None
 
 
+def _preload_nccl():
+    """libpgr_b200.so links libnccl.so.2 by soname.  When PyTorch's bundled NCCL is installed, map that copy first so that
+    the process holds ONE NCCL whatever the import order (torch after pgr_tk_b200 would otherwise get the system copy)."""
+    try:
+        import importlib.util
+        sp = importlib.util.find_spec("nvidia.nccl")
+        for d in (sp.submodule_search_locations if sp else []):
+            path = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return path
+    except Exception:
+        pass
+    return None
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(_LIB):
             raise PgrError(-3, "libpgr_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        _preload_nccl()
         L = C.CDLL(_LIB)
         vp, sz, u32, u64 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64
         P = C.POINTER
@@ -103,7 +130,29 @@ def lib():
         L.pgr_b200_index_add_batch.argtypes = [vp, sz, vp, vp, vp]
         L.pgr_b200_index_stage_batch.argtypes = [vp, sz, vp, vp, vp, P(u64)]
         L.pgr_b200_index_commit_batch.argtypes = [vp, u32]
+        L.pgr_b200_index_stage_device.argtypes = [vp, vp, sz, vp, vp, vp, P(u64)]
         L.pgr_b200_index_finalize.argtypes = [vp]
+        L.pgr_b200_comm_unique_id.argtypes = [vp]
+        L.pgr_b200_comm_init_rank.restype = vp
+        L.pgr_b200_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.pgr_b200_comm_free.argtypes = [vp]
+        L.pgr_b200_index_build_sharded.argtypes = [vp, vp, sz, vp, vp, vp, P(ShardStats)]
+        L.pgr_b200_index_build_sharded_device.argtypes = [vp, vp, vp, sz, vp, vp, vp, P(ShardStats)]
+        L.pgr_b200_index_merge.argtypes = [vp, vp, P(ShardStats)]
+        L.pgr_b200_mindex_new.restype = vp
+        L.pgr_b200_mindex_new.argtypes = [P(ShmmrSpec), C.c_int, C.c_int]
+        L.pgr_b200_mindex_new_devices.restype = vp
+        L.pgr_b200_mindex_new_devices.argtypes = [P(ShmmrSpec), C.c_int, C.c_int, vp]
+        L.pgr_b200_mindex_free.argtypes = [vp]
+        L.pgr_b200_mindex_n_shards.argtypes = [vp]
+        L.pgr_b200_mindex_add_batch.argtypes = [vp, sz, vp, vp, vp]
+        L.pgr_b200_mindex_finalize.argtypes = [vp]
+        L.pgr_b200_mindex_counts.argtypes = [vp, P(sz), P(sz), P(u32)]
+        L.pgr_b200_mindex_stats.argtypes = [vp, C.c_int, P(ShardStats)]
+        L.pgr_b200_mindex_shard.restype = vp
+        L.pgr_b200_mindex_shard.argtypes = [vp, C.c_int]
+        L.pgr_b200_mindex_export_csr.argtypes = [vp, vp, vp, vp]
+        L.pgr_b200_mindex_write_mdb.argtypes = [vp, C.c_char_p]
         L.pgr_b200_index_counts.argtypes = [vp, P(sz), P(sz), P(u32)]
         L.pgr_b200_index_export_csr.argtypes = [vp, vp, vp, vp]
         L.pgr_b200_index_tuples_device.argtypes = [vp, P(vp), P(sz)]
@@ -321,6 +370,42 @@ class ShmmrIndex:
     def finalize(self):
         _check(lib().pgr_b200_index_finalize(self.h))
 
+    def build_sharded(self, comm, sids, seqs):
+        """collective over `comm` (multi-GPU build, one process per GPU): this rank's block of HOST sequences in, this
+        rank's key range (finalized) out.  Returns the rank's pgr_shard_stats as a dict."""
+        arrs, ptrs, lens = _seq_arrays(seqs)
+        s = np.ascontiguousarray(sids, dtype=np.uint32)
+        st = ShardStats()
+        _check(lib().pgr_b200_index_build_sharded(self.h, comm.h, len(arrs), s.ctypes.data, ptrs, lens, C.byref(st)))
+        return st.as_dict()
+
+    def build_sharded_ptrs(self, comm, sids, ptrs, lens):
+        """build_sharded from raw host pointers (slices of a pinned HostBuffer)"""
+        n = len(ptrs)
+        p = (C.c_void_p * max(1, n))(*ptrs)
+        l = (C.c_size_t * max(1, n))(*lens)
+        s = np.ascontiguousarray(sids, dtype=np.uint32)
+        st = ShardStats()
+        _check(lib().pgr_b200_index_build_sharded(self.h, comm.h, n, s.ctypes.data, p, l, C.byref(st)))
+        return st.as_dict()
+
+    def build_sharded_device(self, comm, dev_base, sids, offs, lens):
+        """build_sharded with the block already resident in this rank's HBM"""
+        s = np.ascontiguousarray(sids, dtype=np.uint32)
+        o = np.ascontiguousarray(offs, dtype=np.uint64)
+        l = np.ascontiguousarray(lens, dtype=np.uint64)
+        st = ShardStats()
+        _check(lib().pgr_b200_index_build_sharded_device(self.h, comm.h, C.c_void_p(dev_base), len(s), s.ctypes.data, o.ctypes.data, l.ctypes.data, C.byref(st)))
+        return st.as_dict()
+
+    def stage_device(self, dev_base, sids, offs, lens):
+        s = np.ascontiguousarray(sids, dtype=np.uint32)
+        o = np.ascontiguousarray(offs, dtype=np.uint64)
+        l = np.ascontiguousarray(lens, dtype=np.uint64)
+        nf = C.c_uint64()
+        _check(lib().pgr_b200_index_stage_device(self.h, C.c_void_p(dev_base), len(s), s.ctypes.data, o.ctypes.data, l.ctypes.data, C.byref(nf)))
+        return nf.value
+
     def counts(self):
         nk, ns, nf = C.c_size_t(), C.c_size_t(), C.c_uint32()
         _check(lib().pgr_b200_index_counts(self.h, C.byref(nk), C.byref(ns), C.byref(nf)))
@@ -441,6 +526,111 @@ class ShmmrIndex:
         if adj.size == 0:
             return []
         return self.get_principal_bundles_from_adj_list(adj, path_len_cutoff)[0]
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """NCCL unique id (bytes) made by one rank; broadcast it to the others by any means and pass it to Comm()"""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check(lib().pgr_b200_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Comm:
+    """one rank of the library's NCCL communicator (multi-GPU index build, one process per GPU)"""
+
+    def __init__(self, unique_id, rank, n_ranks, device=-1):
+        assert len(unique_id) == COMM_ID_BYTES
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self.h = lib().pgr_b200_comm_init_rank(buf, rank, n_ranks, device)
+        if not self.h:
+            _check(-3 if device_count() == 0 else -4)
+        self.rank, self.n_ranks = rank, n_ranks
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pgr_b200_comm_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class ShardedIndex:
+    """ShmmrFragMap sharded by key range over the GPUs of this process (pgr_b200_mindex): one host thread and one NCCL
+    rank per GPU, ONE all-to-all of the tuples at finalize.  devices=[0, 0] puts two shards on one GPU (test set-up)."""
+
+    def __init__(self, spec, frg_id_mode=FRG_ID_FASTX, n_gpus=None, devices=None):
+        if devices is not None:
+            d = (C.c_int * len(devices))(*devices)
+            self.h = lib().pgr_b200_mindex_new_devices(C.byref(spec), frg_id_mode, len(devices), d)
+        else:
+            self.h = lib().pgr_b200_mindex_new(C.byref(spec), frg_id_mode, n_gpus)
+        if not self.h:
+            _check(-3 if device_count() == 0 else -1)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pgr_b200_mindex_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def n_shards(self):
+        return lib().pgr_b200_mindex_n_shards(self.h)
+
+    def add_batch(self, sids, seqs):
+        arrs, ptrs, lens = _seq_arrays(seqs)
+        s = np.ascontiguousarray(sids, dtype=np.uint32)
+        _check(lib().pgr_b200_mindex_add_batch(self.h, len(arrs), s.ctypes.data, ptrs, lens))
+
+    def finalize(self):
+        _check(lib().pgr_b200_mindex_finalize(self.h))
+
+    def counts(self):
+        nk, ns, nf = C.c_size_t(), C.c_size_t(), C.c_uint32()
+        _check(lib().pgr_b200_mindex_counts(self.h, C.byref(nk), C.byref(ns), C.byref(nf)))
+        return nk.value, ns.value, nf.value
+
+    def stats(self):
+        self.finalize()
+        out = []
+        for g in range(self.n_shards()):
+            st = ShardStats()
+            _check(lib().pgr_b200_mindex_stats(self.h, g, C.byref(st)))
+            out.append(st.as_dict())
+        return out
+
+    def shard(self, g):
+        """shard g as a ShmmrIndex view (owned by this object: do not close it)"""
+        h = lib().pgr_b200_mindex_shard(self.h, g)
+        if not h:
+            _check(-1)
+        return _BorrowedIndex(h)
+
+    def export(self):
+        nk, ns, _ = self.counts()
+        keys = np.zeros((max(nk, 1), 2), dtype=np.uint64)
+        offs = np.zeros(nk + 1, dtype=np.uint64)
+        sigs = np.zeros(max(ns, 1), dtype=SIG)
+        _check(lib().pgr_b200_mindex_export_csr(self.h, keys.ctypes.data, offs.ctypes.data, sigs.ctypes.data))
+        return keys[:nk], offs, sigs[:ns]
+
+    def write_mdb(self, path):
+        _check(lib().pgr_b200_mindex_write_mdb(self.h, path.encode()))
+
+
+class _BorrowedIndex(ShmmrIndex):
+    """a ShmmrIndex whose handle belongs to a ShardedIndex"""
+
+    def __init__(self, h):
+        self.h = h
+
+    def close(self):
+        self.h = None
+
+    __del__ = close
 
 
 def sparse_aln(hits, max_span, penalty, max_gap=None, oriented=False):

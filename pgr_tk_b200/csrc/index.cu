@@ -49,6 +49,8 @@ static int emit_tuples(pgr_b200_index *idx, const uint32_t *sids, size_t cn, siz
     pair_off[cn] = np;
     if (!query_mode) idx->n_frags = frags;
     *n_pairs_out = np;
+    const uint32_t ord0 = query_mode ? 0u : idx->ord_base + idx->ord_in_batch;   // insertion ordinal of the chunk's first sequence
+    if (!query_mode) idx->ord_in_batch += (uint32_t)cn;
     FragTuple *dst = dst_override;
     if (!dst) {
         PGR_TRY(index_reserve_tuples(idx, idx->n_tuples + np));
@@ -65,6 +67,7 @@ static int emit_tuples(pgr_b200_index *idx, const uint32_t *sids, size_t cn, siz
     p.mm = ctx->d_result; p.mm_off = ctx->d_result_off; p.n_seq = (uint32_t)cn; p.sid = idx->d_sid.as<uint32_t>();
     p.pair_off = idx->d_pair_off.as<uint64_t>(); p.frg_base = idx->d_frg_base.as<uint32_t>(); p.out = dst; p.n_mm = n_mm;
     p.query_mode = query_mode ? 1u : 0u;
+    p.ord_base = ord0;
     pair_tuples_kernel<<<(uint32_t)ceil_div<uint64_t>(n_mm, 256), 256, 0, st>>>(p);
     PGR_CUDA(cudaGetLastError());
     PGR_CUDA(cudaStreamSynchronize(st));  // host vectors above go out of scope
@@ -174,6 +177,32 @@ __global__ void gather_tuples_kernel(const FragTuple *in, const uint32_t *idx, u
     if (i < n) out[i] = in[idx[i]];
 }
 
+// the .mdb byte stream of a canonical CSR (seq_db.rs:1291-1326): "mdb", spec as 5 x u32, n_keys, then per key
+// (h0, h1, len, len x 17-byte FragmentSignature)
+int write_mdb_file(const pgr_shmmr_spec &spec, uint64_t nk, const uint64_t *keys, const uint64_t *offs, const pgr_frag_sig *sigs, const char *path) {
+    const uint64_t ns = nk ? offs[nk] : 0;
+    std::vector<uint8_t> buf(31 + nk * 24 + ns * 17);
+    uint8_t *w = buf.data();
+    auto p32 = [&](uint32_t v) { memcpy(w, &v, 4); w += 4; };
+    auto p64 = [&](uint64_t v) { memcpy(w, &v, 8); w += 8; };
+    *w++ = 'm'; *w++ = 'd'; *w++ = 'b';
+    p32(spec.w); p32(spec.k); p32(spec.r); p32(spec.min_span); p32(spec.sketch ? 1u : 0u);
+    p64(nk);
+    for (uint64_t i = 0; i < nk; i++) {
+        p64(keys[2 * i]); p64(keys[2 * i + 1]); p64(offs[i + 1] - offs[i]);
+        for (uint64_t j = offs[i]; j < offs[i + 1]; j++) {
+            const pgr_frag_sig &s = sigs[j];
+            p32(s.frg_id); p32(s.sid); p32(s.bgn); p32(s.end); *w++ = s.ori;
+        }
+    }
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_error("cannot create %s", path); return PGR_E_IO; }
+    const size_t wr = fwrite(buf.data(), 1, buf.size(), f);
+    const int cl = fclose(f);
+    if (wr != buf.size() || cl != 0) { set_error("short write to %s", path); return PGR_E_IO; }
+    return PGR_OK;
+}
+
 }  // namespace pgr
 
 extern "C" {
@@ -196,7 +225,7 @@ void pgr_b200_index_free(pgr_b200_index *idx) {
                       &idx->head, &idx->block_sum, &idx->block_prefix, &idx->d_sid, &idx->d_pair_off, &idx->d_frg_base, &idx->qtuples,
                       &idx->q_hit_begin, &idx->q_hit_count, &idx->scratch0, &idx->scratch1, &idx->scratch2, &idx->scratch3,
                       &idx->sid_count, &idx->hitsA, &idx->hitsB, &idx->seg_keys, &idx->seg_off, &idx->chain_f, &idx->chain_u, &idx->chain_b,
-                      &idx->chain_seg, &idx->asm_prefix, &idx->asm_has, &idx->asm_out};
+                      &idx->chain_seg, &idx->asm_prefix, &idx->asm_has, &idx->asm_out, &idx->sendbuf};
     for (auto b : bufs) b->release();
     pgr_b200_ctx_free(idx->ctx);
     delete idx;
@@ -210,11 +239,45 @@ int pgr_b200_index_get_spec(const pgr_b200_index *idx, pgr_shmmr_spec *spec) {
 
 int pgr_b200_index_add_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens) {
     if (!idx || (n && (!sids || !seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
+    if (idx->staged) { set_error("a staged batch is pending: call pgr_b200_index_commit_batch first"); return PGR_E_ARG; }
     idx->finalized = false;
+    idx->ord_in_batch = 0;
+    const uint64_t t0 = idx->n_tuples;
+    const uint32_t f0 = idx->n_frags;
     trace_mark("index_add_batch: begin");
     const int rc = index_batch_tuples(idx, n, sids, seqs, lens, false, nullptr, nullptr, nullptr);
     trace_mark("index_add_batch: shimmers + tuples");
+    if (rc != PGR_OK) { idx->n_tuples = t0; idx->n_frags = f0; }   // a failed batch leaves the index as it was
     return rc;
+}
+
+// stage_batch for sequences that already live in device memory (layout rules of pgr_b200_ctx_set_device_seqs)
+int pgr_b200_index_stage_device(pgr_b200_index *idx, const uint8_t *dev_base, size_t n, const uint32_t *sids, const uint64_t *offs,
+                                const uint64_t *lens, uint64_t *n_frags_in_batch) {
+    if (!idx || (n && (!sids || !dev_base || !offs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
+    if (idx->staged) { set_error("a staged batch is pending: call pgr_b200_index_commit_batch first"); return PGR_E_ARG; }
+    pgr_b200_ctx *ctx = idx->ctx;
+    idx->finalized = false;
+    idx->staged_prev_frags = idx->n_frags;
+    idx->staged_t0 = idx->n_tuples;
+    idx->n_frags = 0;
+    idx->ord_in_batch = 0;
+    auto fail = [&](int rc) { idx->n_frags = idx->staged_prev_frags; idx->n_tuples = idx->staged_t0; return rc; };
+    int rc = pgr_b200_ctx_set_device_seqs(ctx, dev_base, n, nullptr, offs, lens);
+    if (rc != PGR_OK) return fail(rc);
+    ctx->timer.reset();
+    memset(ctx->counters, 0, sizeof ctx->counters);
+    ctx->r0 = 0; ctx->rn = n;
+    size_t ns = 0;
+    if (n) {
+        if ((rc = shmmrs_range(ctx, idx->spec, 0, &ns)) != PGR_OK) return fail(rc);
+        uint64_t np = 0;
+        if ((rc = emit_tuples(idx, sids, n, ns, false, nullptr, &np)) != PGR_OK) return fail(rc);
+    }
+    idx->staged_frags = idx->n_frags;
+    if (n_frags_in_batch) *n_frags_in_batch = (idx->mode == 0) ? idx->staged_frags : 0;
+    idx->staged = true;
+    return PGR_OK;
 }
 
 // stage: the chunked, copy/compute-overlapped path of add_batch with fragment ids counted from 0; commit shifts the ids
@@ -228,8 +291,9 @@ int pgr_b200_index_stage_batch(pgr_b200_index *idx, size_t n, const uint32_t *si
     idx->staged_prev_frags = idx->n_frags;
     idx->staged_t0 = idx->n_tuples;
     idx->n_frags = 0;
+    idx->ord_in_batch = 0;
     const int rc = index_batch_tuples(idx, n, sids, seqs, lens, false, nullptr, nullptr, nullptr);
-    if (rc != PGR_OK) { idx->n_frags = idx->staged_prev_frags; return rc; }
+    if (rc != PGR_OK) { idx->n_frags = idx->staged_prev_frags; idx->n_tuples = idx->staged_t0; return rc; }
     idx->staged_frags = idx->n_frags;
     if (n_frags_in_batch) *n_frags_in_batch = (idx->mode == 0) ? idx->staged_frags : 0;
     idx->staged = true;
@@ -272,8 +336,16 @@ int pgr_b200_index_finalize(pgr_b200_index *idx) {
     PGR_TRY(idx->idxA.ensure(n * sizeof(uint32_t)));
     trace_mark("index_finalize: alloc");
     const uint32_t g = (uint32_t)ceil_div<uint64_t>(n, 256);
-    tuple_keys_kernel<<<g, 256, 0, st>>>(idx->tuples.as<FragTuple>(), n, idx->keysA.as<SortKey>());
     iota_kernel<<<g, 256, 0, st>>>(idx->idxA.as<uint32_t>(), n);
+    if (idx->ord_sort) {
+        // tuples of interleaved blocks (multi-GPU merge of several batches): minor key = the sequences' insertion ordinal
+        tuple_ord_keys_kernel<<<g, 256, 0, st>>>(idx->tuples.as<FragTuple>(), n, idx->keysA.as<SortKey>());
+        PGR_TRY(index_sort(idx, n, 0, 3));
+        tuple_keys_perm_kernel<<<g, 256, 0, st>>>(idx->tuples.as<FragTuple>(), idx->idxA.as<uint32_t>(), n, idx->keysA.as<SortKey>());
+        idx->launches += 1;
+    } else {
+        tuple_keys_kernel<<<g, 256, 0, st>>>(idx->tuples.as<FragTuple>(), n, idx->keysA.as<SortKey>());
+    }
     idx->launches += 2;
     PGR_TRY(index_sort(idx, n, 0, 13));
     PGR_TRY(idx->sigs.ensure(n * sizeof(pgr_frag_sig)));
@@ -384,26 +456,7 @@ int pgr_b200_index_write_mdb(pgr_b200_index *idx, const char *path) {
     if (nk == 0) offs[0] = 0;
     uint64_t dk = 0; pgr_frag_sig ds;
     PGR_TRY(pgr_b200_index_export_csr(idx, nk ? keys.data() : &dk, offs.data(), ns ? sigs.data() : &ds));
-    std::vector<uint8_t> buf;
-    buf.reserve(31 + nk * 24 + ns * 17);
-    auto p32 = [&](uint32_t v) { for (int i = 0; i < 4; i++) buf.push_back((uint8_t)(v >> (8 * i))); };
-    auto p64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) buf.push_back((uint8_t)(v >> (8 * i))); };
-    buf.push_back('m'); buf.push_back('d'); buf.push_back('b');
-    p32(idx->spec.w); p32(idx->spec.k); p32(idx->spec.r); p32(idx->spec.min_span); p32(idx->spec.sketch ? 1u : 0u);
-    p64(nk);
-    for (uint64_t i = 0; i < nk; i++) {
-        p64(keys[2 * i]); p64(keys[2 * i + 1]); p64(offs[i + 1] - offs[i]);
-        for (uint64_t j = offs[i]; j < offs[i + 1]; j++) {
-            const pgr_frag_sig &s = sigs[j];
-            p32(s.frg_id); p32(s.sid); p32(s.bgn); p32(s.end); buf.push_back(s.ori);
-        }
-    }
-    FILE *f = fopen(path, "wb");
-    if (!f) { set_error("cannot create %s", path); return PGR_E_IO; }
-    const size_t wr = fwrite(buf.data(), 1, buf.size(), f);
-    fclose(f);
-    if (wr != buf.size()) { set_error("short write to %s", path); return PGR_E_IO; }
-    return PGR_OK;
+    return write_mdb_file(idx->spec, nk, keys.data(), offs.data(), sigs.data(), path);
 }
 
 // seq_db.rs:1328-1407: any key order is accepted; per-key vectors keep their file order
@@ -423,14 +476,17 @@ pgr_b200_index *pgr_b200_index_read_mdb(const char *path, int device) {
     pgr_shmmr_spec spec;
     spec.w = r32(); spec.k = r32(); spec.r = r32(); spec.min_span = r32(); spec.sketch = r32() & 1u;
     const uint64_t nk = r64();
+    if (nk > (buf.size() - c) / 24) { set_error("%s is truncated", path); return nullptr; }
     std::vector<FragTuple> tuples;
+    uint64_t max_frg = 0;
     for (uint64_t i = 0; i < nk; i++) {
         if (c + 24 > buf.size()) { set_error("%s is truncated", path); return nullptr; }
         const uint64_t h0 = r64(), h1 = r64(), vl = r64();
-        if (c + 17 * vl > buf.size()) { set_error("%s is truncated", path); return nullptr; }
+        if (vl > (buf.size() - c) / 17) { set_error("%s is truncated", path); return nullptr; }   // no overflow: compare counts
         for (uint64_t j = 0; j < vl; j++) {
             FragTuple t;
-            t.h0 = h0; t.h1 = h1; t.frg_id = r32(); t.sid = r32(); t.bgn = r32(); t.end = r32(); t.ori = buf[c]; c += 1; t.pad_ = 0;
+            t.h0 = h0; t.h1 = h1; t.frg_id = r32(); t.sid = r32(); t.bgn = r32(); t.end = r32(); t.ori = buf[c]; c += 1; t.ord = 0;
+            max_frg = std::max<uint64_t>(max_frg, (uint64_t)t.frg_id + 1);
             tuples.push_back(t);
         }
     }
@@ -442,6 +498,8 @@ pgr_b200_index *pgr_b200_index_read_mdb(const char *path, int device) {
         set_error("H2D failed"); pgr_b200_index_free(idx); return nullptr;
     }
     idx->n_tuples = tuples.size();
+    idx->n_frags = (uint32_t)std::min<uint64_t>(max_frg, 0xFFFFFFFFull);   // fragment ids in use (no prefix/suffix records in an .mdb)
+    idx->from_mdb = true;
     if (pgr_b200_index_finalize(idx) != PGR_OK) { pgr_b200_index_free(idx); return nullptr; }
     return idx;
 }

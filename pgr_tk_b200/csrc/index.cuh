@@ -21,6 +21,12 @@ struct pgr_b200_index {
     bool staged = false;
     uint64_t staged_t0 = 0;           // first tuple of the staged batch
     uint32_t staged_frags = 0, staged_prev_frags = 0;
+    // multi-GPU build (shard.cu): tuples carry the insertion ordinal of their sequence (FragTuple::ord = ord_base + position in
+    // the batch); the owner's sort uses it as the minor key when blocks of several batches interleave (ord_sort)
+    uint32_t ord_base = 0, ord_in_batch = 0;
+    bool from_mdb = false;            // read from an .mdb: no sequences behind it, appending is refused by the host mirror
+    bool ord_sort = false;
+    pgr::DevBuf sendbuf;              // tuples partitioned by destination shard
     // scratch
     pgr::DevBuf keysA, keysB, idxA, idxB, hist, head, block_sum, block_prefix, d_sid, d_pair_off, d_frg_base;
     pgr::DevBuf qtuples, q_hit_begin, q_hit_count, scratch0, scratch1, scratch2, scratch3;
@@ -36,4 +42,5 @@ int index_batch_tuples(pgr_b200_index *idx, size_t n, const uint32_t *sids, cons
 int index_sort(pgr_b200_index *idx, uint64_t n, int first_pass, int last_pass);
 __global__ void iota_kernel(uint32_t *p, uint64_t n);
 __global__ void set_u64_kernel(uint64_t *p, uint64_t v);
+int write_mdb_file(const pgr_shmmr_spec &spec, uint64_t nk, const uint64_t *keys, const uint64_t *offs, const pgr_frag_sig *sigs, const char *path);
 }  // namespace pgr

@@ -10,7 +10,7 @@ struct FragTuple {
     uint64_t h0, h1;                    // canonical key, h0 <= h1 (seq_db.rs:238-242, :391-395)
     uint32_t frg_id, sid, bgn, end;     // FragmentSignature (seq_db.rs:75)
     uint32_t ori;                       // 0/1
-    uint32_t pad_;
+    uint32_t ord;                       // insertion ordinal of the sequence (multi-GPU merge, shard.cu); 0 elsewhere
 };
 static_assert(sizeof(FragTuple) == 40, "FragTuple layout");
 
@@ -24,6 +24,7 @@ struct PairParams {
     FragTuple *out;              // [pair_off[n_seq]]
     uint64_t n_mm;
     uint32_t query_mode;         // 1: strict '<' canonicalisation (seq_db.rs:1213-1217), 0: '<=' (index build)
+    uint32_t ord_base;           // FragTuple::ord = ord_base + s
 };
 
 // adjacent shimmers -> tuple (pair_shmmrs seq_db.rs:102-111; seq_to_compressed :233-245,:326-338; seq_to_index :386-400)
@@ -45,7 +46,7 @@ __global__ void pair_tuples_kernel(const PairParams p) {
     t.end = ((uint32_t)(m1.y & 0xFFFFFFFFu) >> 1) + 1;
     t.sid = p.sid[s];
     t.frg_id = p.frg_base[s] + (uint32_t)j;
-    t.pad_ = 0;
+    t.ord = p.ord_base + s;
     p.out[p.pair_off[s] + j] = t;
 }
 
@@ -53,6 +54,21 @@ __global__ void tuple_keys_kernel(const FragTuple *t, uint64_t n, SortKey *keys)
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     SortKey k; k.k0 = t[i].h0; k.k1 = t[i].h1;
+    keys[i] = k;
+}
+// minor-key round of the multi-GPU merge: sort by the sequences' insertion ordinal first ...
+__global__ void tuple_ord_keys_kernel(const FragTuple *t, uint64_t n, SortKey *keys) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SortKey k; k.k0 = 0; k.k1 = t[i].ord;
+    keys[i] = k;
+}
+// ... then take the hash keys in that order
+__global__ void tuple_keys_perm_kernel(const FragTuple *t, const uint32_t *idx, uint64_t n, SortKey *keys) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FragTuple &x = t[idx[i]];
+    SortKey k; k.k0 = x.h0; k.k1 = x.h1;
     keys[i] = k;
 }
 

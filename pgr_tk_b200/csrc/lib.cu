@@ -4,3 +4,4 @@
 #include "query.cu"
 #include "bundles.cu"
 #include "frags.cu"
+#include "shard.cu"

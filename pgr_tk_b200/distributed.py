@@ -1,12 +1,13 @@
-"""Multi-GPU ShmmrFragMap build: one process per GPU, sequences sharded in contiguous blocks, ONE exchange step.
+"""Multi-GPU ShmmrFragMap build, one process per GPU (torchrun): the plumbing around the library's collective
+`pgr_b200_index_build_sharded` (pgr_tk_b200/csrc/shard.cu).
 
-    stage (shimmers, per rank) -> all-gather fragment totals (global FASTX frg_id bases, seq_db.rs:203-231)
-    -> commit (tuples) -> sampled key splitters -> stable partition -> all-to-all of 40-byte tuples over NCCL/NVLink
-    -> per-owner stable sort + CSR (rank r owns the r-th key range, so slices concatenate in canonical key order)
+    rank 0: pgr_b200_comm_unique_id  --broadcast (torch.distributed, any backend)-->  every rank: pgr_b200_comm_init_rank
+    every rank: pgr_b200_index_build_sharded(its consecutive block of the sequence list)
+        = shimmers + tuples -> all-gather of fragment totals -> device-side splitters -> stable partition
+          -> ONE all-to-all (grouped ncclSend/ncclRecv over NVLink) -> stable sort + CSR of the rank's key range
 
-torch.distributed is the plumbing (process group, all_gather, all_to_all_single); partition, sort and CSR are the
-library's CUDA kernels.  The host-side pieces (`frag_bases`, `choose_splitters`, `exchange_records`) work on CPU
-tensors with the gloo backend too, which is how tests/test_distributed_gloo.py covers them without a GPU.
+torch.distributed only carries the 128-byte NCCL id; the exchange itself runs inside libpgr_b200 on the library's
+own communicator.  `shard_blocks` is the block rule the single-process form (pgr_b200_mindex_add_batch) uses too.
 """
 import numpy as np
 import torch
@@ -14,102 +15,55 @@ import torch.distributed as dist
 
 from . import api
 
-TUPLE_BYTES = api.TUPLE.itemsize  # 40
-SAMPLES_PER_RANK = 4096
+
+def shard_blocks(lens, world):
+    """cut a sequence list into `world` consecutive blocks of about equal bases: cut g falls after the first sequence
+    that brings the running total to g/world of all bases.  Returns world+1 boundaries."""
+    n = len(lens)
+    total = int(sum(int(x) for x in lens))
+    cut = [0] + [n] * world
+    acc, g = 0, 1
+    for i, ln in enumerate(lens):
+        if g >= world:
+            break
+        acc += int(ln)
+        while g < world and acc * world >= total * g:
+            cut[g] = i + 1
+            g += 1
+    return cut
 
 
-def frag_bases(n_frags_local, group=None, device="cpu"):
-    """exclusive prefix over ranks of the fragment ids each shard consumes -> (base of this rank, total)"""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    t = torch.tensor([int(n_frags_local)], dtype=torch.int64, device=device)
-    out = [torch.zeros_like(t) for _ in range(world)]
-    dist.all_gather(out, t, group=group)
-    vals = [int(x.item()) for x in out]
-    return sum(vals[:rank]), sum(vals)
+def broadcast_id(id_bytes, group=None, device="cpu"):
+    """rank 0 passes the id bytes, the others None; everybody gets rank 0's bytes"""
+    t = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8)
+    if dist.get_rank(group) == 0:
+        t = torch.frombuffer(bytearray(id_bytes), dtype=torch.uint8).clone()
+    t = t.to(device)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return bytes(t.cpu().numpy().tobytes())
 
 
-def choose_splitters(local_h0_sample, group=None, device="cpu"):
-    """world-1 ascending splitters of the h0 key space from an all-gathered sample (minimizer hashes are skewed low,
-    so quantiles of a sample, not top bits)"""
-    world = dist.get_world_size(group)
-    s = np.zeros(SAMPLES_PER_RANK + 1, dtype=np.int64)
-    k = min(len(local_h0_sample), SAMPLES_PER_RANK)
-    s[0] = k
-    s[1:1 + k] = np.asarray(local_h0_sample[:k], dtype=np.uint64).view(np.int64)
-    t = torch.from_numpy(s).to(device)
-    out = [torch.zeros_like(t) for _ in range(world)]
-    dist.all_gather(out, t, group=group)
-    allv = []
-    for o in out:
-        o = o.cpu().numpy()
-        allv.append(o[1:1 + int(o[0])].view(np.uint64))
-    allv = np.sort(np.concatenate(allv)) if allv else np.zeros(0, dtype=np.uint64)
-    if len(allv) == 0:
-        return np.zeros(world - 1, dtype=np.uint64)
-    q = [(len(allv) * (i + 1)) // world for i in range(world - 1)]
-    return allv[np.minimum(q, len(allv) - 1)].astype(np.uint64)
-
-
-def exchange_records(send, send_counts, group=None):
-    """all-to-all of fixed-size records. send: uint8 tensor [n_send * rec] already ordered by destination rank;
-    send_counts: records per destination.  Returns (recv uint8 tensor, recv_counts)."""
-    world = dist.get_world_size(group)
-    dev = send.device
-    sc = torch.tensor([int(c) for c in send_counts], dtype=torch.int64, device=dev)
-    rc = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_to_all_single(rc, sc, group=group)
-    recv_counts = [int(x) for x in rc.cpu().tolist()]
-    recv = torch.empty(sum(recv_counts) * TUPLE_BYTES, dtype=torch.uint8, device=dev)
-    dist.all_to_all_single(recv, send, output_split_sizes=[c * TUPLE_BYTES for c in recv_counts],
-                           input_split_sizes=[int(c) * TUPLE_BYTES for c in send_counts], group=group)
-    return recv, recv_counts
-
-
-class _DevMem:
-    """expose a raw device pointer to torch through __cuda_array_interface__"""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
-def build_index_distributed(spec, local_sids, local_seqs, frg_id_mode=api.FRG_ID_FASTX, device=None, group=None):
-    """Every rank passes its contiguous block of the global sequence list; returns this rank's ShmmrIndex slice
-    (keys of the rank's key range) and a dict of timings / counts.  Must be called by all ranks of `group`."""
+def init_comm(device=None, group=None):
+    """the library's own NCCL communicator over the ranks of `group` (collective)"""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev_index = torch.cuda.current_device() if device is None else device
-    dev = torch.device("cuda", dev_index)
+    tdev = torch.device("cuda", dev_index) if dist.get_backend(group) == "nccl" else "cpu"
+    uid = api.comm_unique_id() if rank == 0 else None
+    uid = broadcast_id(uid, group, tdev)
+    return api.Comm(uid, rank, world, dev_index)
+
+
+def build_index_distributed(spec, local_sids, local_seqs, frg_id_mode=api.FRG_ID_FASTX, device=None, group=None, comm=None):
+    """Every rank passes its consecutive block of the global sequence list (rank order = list order); returns this
+    rank's ShmmrIndex slice (the rank's key range, finalized) and the rank's pgr_shard_stats.  Collective."""
+    dev_index = torch.cuda.current_device() if device is None else device
+    own = comm is None
+    if own:
+        comm = init_comm(dev_index, group)
     idx = api.ShmmrIndex(spec, frg_id_mode, dev_index)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    ev[0].record()
-    n_frags = idx.stage_batch(local_sids, local_seqs)
-    base, total_frags = frag_bases(n_frags, group, dev)
-    idx.commit_batch(base)
-    ev[1].record()
-    ptr, n = idx.tuples_device()
-    if world > 1:
-        # sample h0 of every stride-th tuple (first 8 bytes of each 40-byte record)
-        if n:
-            raw = torch.as_tensor(_DevMem(ptr, n * TUPLE_BYTES), device=dev)
-            stride = max(1, n // SAMPLES_PER_RANK)
-            sample = raw.view(n, TUPLE_BYTES)[::stride, :8].contiguous().view(torch.int64).flatten().cpu().numpy().view(np.uint64)
-        else:
-            sample = np.zeros(0, dtype=np.uint64)
-        splitters = choose_splitters(sample, group, dev)
-        counts = idx.partition(splitters)
-        ptr, n = idx.tuples_device()
-        send = torch.as_tensor(_DevMem(ptr, n * TUPLE_BYTES), device=dev) if n else torch.empty(0, dtype=torch.uint8, device=dev)
-        ev[2].record()
-        recv, recv_counts = exchange_records(send, counts, group)
-        torch.cuda.synchronize()
-        idx.set_tuples_device(recv.data_ptr(), sum(recv_counts))
-        del recv
-    else:
-        ev[2].record()
-    idx.finalize()
-    ev[3].record()
-    torch.cuda.synchronize()
+    info = idx.build_sharded(comm, local_sids, local_seqs)
     nk, ns, _ = idx.counts()
-    info = {"stage_commit_ms": ev[0].elapsed_time(ev[1]), "partition_ms": ev[1].elapsed_time(ev[2]),
-            "exchange_sort_ms": ev[2].elapsed_time(ev[3]), "n_keys": nk, "n_sigs": ns, "total_frags": total_frags}
+    info.update({"n_keys": nk, "n_sigs": ns})
+    if own:
+        comm.close()
     return idx, info

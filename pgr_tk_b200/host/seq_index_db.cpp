@@ -84,11 +84,12 @@ int SeqIndexDB::load_from_fastx(const std::string &path, uint32_t w, uint32_t k,
     seq_data_.clear();
     idx_ = pgr_b200_index_new(&spec_, 0 /* FASTX fragment numbering */, -1);
     if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
+    fastx_backend_ = true;
     return load_seqs_from_fastx(path);
 }
 
 int SeqIndexDB::append_from_fastx(const std::string &path) {
-    if (!idx_) { err_ = "Only DB created with load_from_fastx() can add data from another fastx file"; return PGR_E_ARG; }
+    if (!idx_ || !fastx_backend_) { err_ = "Only DB created with load_from_fastx() can add data from another fastx file"; return PGR_E_ARG; }
     return load_seqs_from_fastx(path);
 }
 
@@ -106,6 +107,7 @@ int SeqIndexDB::load_from_seq_list(const std::vector<SeqRec> &seq_list, const st
     seq_data_.clear();
     idx_ = pgr_b200_index_new(&spec_, 0, -1);
     if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
+    fastx_backend_ = true;
     std::vector<SeqRec> recs = seq_list;
     return add_records(recs, source);
 }
@@ -136,6 +138,7 @@ int SeqIndexDB::load_from_index_files(const std::string &prefix) {
     if (idx_) { pgr_b200_index_free(idx_); idx_ = nullptr; }
     seqs_.clear();
     seq_data_.clear();
+    fastx_backend_ = false;
     idx_ = pgr_b200_index_read_mdb((prefix + ".mdb").c_str(), -1);
     if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_IO; }
     pgr_b200_index_get_spec(idx_, &spec_);

@@ -90,6 +90,7 @@ private:
     std::vector<CompactSeq> seqs_;
     std::vector<std::vector<uint8_t>> seq_data_;
     bool keep_seqs_ = false;
+    bool fastx_backend_ = false;   // created by load_from_fastx / load_from_seq_list: the only back end append_from_fastx accepts (ext.rs:180-199)
     FragStore frag_store_;
     std::string err_;
 };

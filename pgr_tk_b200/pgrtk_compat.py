@@ -71,8 +71,8 @@ class SeqIndexDB:
         out = []
         for i, p in enumerate(pairs):
             sigs = [(int(h["frg_id"]), int(h["sid"]), int(h["bgn"]), int(h["end"]), int(h["ori"])) for h in hits[int(off[i]):int(off[i + 1])]]
-            if sigs:   # raw_query_fragment keeps the pairs that are in the map (seq_db.rs:1219-1226)
-                out.append(((int(p["h0"]), int(p["h1"])), (int(p["bgn"]), int(p["end"]), int(p["ori"])), sigs))
+            # raw_query_fragment returns EVERY query pair, with an empty vector when the key is absent (seq_db.rs:1219-1226)
+            out.append(((int(p["h0"]), int(p["h1"])), (int(p["bgn"]), int(p["end"]), int(p["ori"])), sigs))
         return out
 
     def query_fragment_to_hps(self, seq, penalty, max_count=None, max_count_query=None, max_count_target=None, max_aln_span=None,

@@ -1,7 +1,8 @@
-"""world_size-2 gloo test (CPU) of the host-side logic of the multi-GPU index build (pgr_tk_b200/distributed.py):
-fragment-id bases, sampled splitters, the all-to-all plan, and that contiguous shards + stable partition + stable
-sort reproduce the single-process map.  Tuples come from the oracle here (no GPU); the CUDA partition/sort kernels are
-covered by the -m gpu tests."""
+"""world_size-2 gloo tests (CPU) of the multi-GPU index build: the scheme the library implements in CUDA + NCCL
+(pgr_tk_b200/csrc/shard.cu) restated in numpy (tests/dist_model.py: fragment-id bases, splitters as quantiles of an
+all-gathered sample, the all-to-all plan) — consecutive blocks + stable partition + stable sort must reproduce the
+single-process map — and the host-side plumbing of pgr_tk_b200/distributed.py (block rule, NCCL-id broadcast).
+Tuples come from the oracle here (no GPU); the CUDA kernels and NCCL are covered by the -m gpu tests."""
 import os
 import socket
 import sys
@@ -41,14 +42,19 @@ def _make_seqs():
 
 def _worker(rank, world, port, q):
     import orc
-    from pgr_tk_b200 import api, distributed as D
+    from pgr_tk_b200 import api, distributed as PD
+    import dist_model as D
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         seqs = _make_seqs()
         n = len(seqs)
-        lo, hi = (n * rank) // world, (n * (rank + 1)) // world        # contiguous sid blocks
+        cut = PD.shard_blocks([len(s) for s in seqs], world)          # consecutive blocks of about equal bases
+        lo, hi = cut[rank], cut[rank + 1]
+        # the NCCL id travels over the process group as 128 opaque bytes
+        uid = PD.broadcast_id(bytes(range(128)) if rank == 0 else None)
+        assert uid == bytes(range(128))
         spec = orc.mkspec(80, 56, 4, 64)
         # shard: shimmers -> fragment count -> global base
         _, offs = orc.shmmrs_batch(list(range(lo, hi)), seqs[lo:hi], spec)
@@ -66,7 +72,8 @@ def _worker(rank, world, port, q):
             t[f] = sigs[f]
         t["ori"] = sigs["ori"]
         t["frg_id"] = sigs["frg_id"] + base
-        splitters = D.choose_splitters(t["h0"][:: max(1, len(t) // D.SAMPLES_PER_RANK)])
+        # the partition works on tuples in insertion order; here they come in key order, which the stable sort undoes
+        splitters = D.choose_splitters(D.sample_h0(t["h0"]))
         assert len(splitters) == world - 1 and np.all(np.diff(splitters.astype(np.float64)) >= 0)
         dest = np.searchsorted(splitters, t["h0"], side="right")
         order = np.argsort(dest, kind="stable")

@@ -30,8 +30,16 @@ def test_seq_index_db_surface_matches_oracle():
     pairs, off, sig = o.raw_query(q)
     exp = [((int(p["h0"]), int(p["h1"])), (int(p["bgn"]), int(p["end"]), int(p["ori"])),
             [(int(h["frg_id"]), int(h["sid"]), int(h["bgn"]), int(h["end"]), int(h["ori"])) for h in sig[int(off[i]):int(off[i + 1])]])
-           for i, p in enumerate(pairs) if off[i + 1] > off[i]]
+           for i, p in enumerate(pairs)]
     assert hits == exp and len(hits) > 3
+    # a mutated query: pairs without a hit stay in the result with an empty signature list (seq_db.rs:1219-1226)
+    qm = bytearray(q)
+    for i in range(0, len(qm), 97):
+        qm[i] = ord("A") if qm[i] != ord("A") else ord("C")
+    hm = db.query_fragment(bytes(qm))
+    pm, om, _ = o.raw_query(bytes(qm))
+    assert len(hm) == len(pm) and [len(h[2]) for h in hm] == [int(om[i + 1] - om[i]) for i in range(len(pm))]
+    assert any(len(h[2]) == 0 for h in hm)
     res = db.query_fragment_to_hps(q, 0.025, 128, 128, 128, 8)
     osid, otco, osc, ocho, ohits = o.query_fragment_to_hps(q, 0.025, max_count=128, max_count_query=128, max_count_target=128, max_aln_span=8)
     assert [r[0] for r in res] == [int(s) for s in osid]
