@@ -11,6 +11,12 @@ A step = one pass of the hot path over that batch.
   roofline : dominant kernel (l0_minimizers), algorithmic bytes (1 B/base + 16 B/shimmer) / its CUDA-event time
   cpu_baseline : the C++ oracle (restatement of the reference's rayon path) on the box's host cores, bounded sample
 
+  e2e_pageable : the same call with plain pageable host memory (what a Rust `&Vec<u8>` hands over)
+  assembly_like : the same batch decorated like a real assembly (N gaps, soft-masked lower case, microsatellites, inverted
+          repeats; bench_synth.decorate_assembly_like) — the paths uniform ACGT never takes — with its own oracle check
+  index_build : BASELINE.json configs[2], the full ShmmrFragMap build on 94 x 50 Mb haplotypes, STRONG scaling over the N
+          GPUs with the NCCL all-to-all inside libpgr_b200, host-to-CSR and HBM-resident, parity flags (bench_index.py)
+
 `--impl reference` times the oracle alone (all host threads), same metric/config, on a bounded sample per step.
 """
 import argparse
@@ -47,6 +53,10 @@ def parse_args():
     ap.add_argument("--contig-len", type=int, default=CONTIG_LEN)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-index", action="store_true", help="skip the config-3 index build (index_build object)")
+    ap.add_argument("--no-assembly", action="store_true", help="skip the assembly-like variant of the batch")
+    ap.add_argument("--index-haps", type=int, default=94)
+    ap.add_argument("--index-hap-len", type=int, default=50_000_000)
     return ap.parse_args()
 
 
@@ -294,8 +304,28 @@ def main():
         except Exception:
             pass
 
+    # ---- CPU baseline beside it (rank 0, N=1 only); doubles as a full-size parity spot check of the resident result ------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import orc
+        cores = host_cores()
+        n_sample = min(n_contigs, max(2 * cores, 16))
+        sample = store[SLACK: SLACK + n_sample * clen].cpu().numpy()
+        seqs = [sample[i * clen:(i + 1) * clen] for i in range(n_sample)]
+        ospec = orc.mkspec(*SPEC)
+        orc.shmmrs_batch(list(range(min(cores, n_sample))), seqs[:cores], ospec, False, nthreads=cores)  # warm
+        t0 = time.perf_counter()
+        cpu_out, cpu_off = orc.shmmrs_batch(list(range(n_sample)), seqs, ospec, False, nthreads=cores)
+        dt = time.perf_counter() - t0
+        got, goff = ctx.shmmrs_download()
+        k = int(goff[n_sample])
+        assert k == int(cpu_off[-1]) and np.array_equal(got[:k], cpu_out), "GPU result differs from the oracle on the CPU sample"
+        cpu = {"value": n_sample * clen / dt / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
+               "sample": "first %d of %d contigs x %d bases, one sequence per thread (seq_db.rs:461); parity of these contigs checked" % (n_sample, n_contigs, clen)}
+        del sample, seqs, got
+
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------------------
-    e2e = None
+    e2e = e2e_pageable = assembly = None
     if not args.no_e2e:
         L = pg.lib()
         hb = pg.host_alloc(bases)
@@ -329,27 +359,83 @@ def main():
         e2e = {"value": world * bases / (e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": bases, "d2h_bytes_per_step": d2h,
                "api": "pgr_b200_shmmrs_batch (host pointers in pinned memory -> host MM128 array)"}
+        # ---- the same call on pageable memory: what a drop-in `sequence_to_shmmrs(&Vec<u8>)` caller hands over -----------
+        pg_arr = np.empty(bases, dtype=np.uint8)
+        np.copyto(pg_arr, hb.array)
+        pptrs = (C.c_void_p * n_contigs)(*[pg_arr.ctypes.data + i * clen for i in range(n_contigs)])
+        ptimes = []
+        for it in range(1 + min(3, args.steps)):
+            barrier()
+            t0 = time.perf_counter()
+            rc = L.pgr_b200_shmmrs_batch(n_contigs, rids.ctypes.data, pptrs, clens, C.byref(spec), 0, C.byref(out), offs_out.ctypes.data)
+            t1 = time.perf_counter()
+            if rc != 0:
+                raise SystemExit("pgr_b200_shmmrs_batch (pageable) failed: %s" % L.pgr_b200_last_error().decode())
+            assert int(offs_out[-1]) == n_shmmrs
+            L.pgr_b200_free(out)
+            if it >= 1:
+                ptimes.append(t1 - t0)
+        p_ms = statistics.mean(ptimes) * 1e3
+        tp = torch.tensor([p_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        p_ms = float(tp.item())
+        e2e_pageable = {"value": world * bases / (p_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": p_ms, "reps": len(ptimes),
+                        "api": "pgr_b200_shmmrs_batch (host pointers in PAGEABLE memory -> host MM128 array)"}
+        del pg_arr, pptrs
+
+        # ---- assembly-like decoration of the same batch (rank 0, N = 1): gaps, soft masking, microsatellites, inverted repeats
+        if not args.no_assembly and world == 1:
+            import concurrent.futures as cf
+            import bench_synth as S
+            with cf.ThreadPoolExecutor(max_workers=min(16, host_cores())) as ex:
+                list(ex.map(lambda i: S.decorate_assembly_like(hb.array[i * clen:(i + 1) * clen], 5000 + i), range(n_contigs)))
+            store[SLACK: SLACK + bases].copy_(hb_t)
+            torch.cuda.synchronize()
+            ctx.set_device_seqs(store.data_ptr(), offs, lens)
+            for _ in range(2):
+                n_asm = ctx.shmmrs(spec)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = min(5, args.steps)
+            a0.record(stream)
+            for _ in range(reps):
+                n_asm = ctx.shmmrs(spec)
+            a1.record(stream)
+            torch.cuda.synchronize()
+            a_ms = a0.elapsed_time(a1) / reps
+            cnt = ctx.counters()
+            asm_stages = dict(ctx.timings())
+            assembly = {"value": bases / (a_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": a_ms, "reps": reps, "shmmrs": n_asm,
+                        "slowdown_vs_uniform_acgt": a_ms / dev_ms_max,
+                        "n_fraction": float((hb.array[:50_000_000] == ord("N")).mean()), "lower_case_fraction": float(((hb.array[:50_000_000] & 0x20) != 0).mean()),
+                        "whole_sequence_replays": int(cnt[2]), "local_patches": int(cnt[4]), "kernel_launches_per_step": int(cnt[0]),
+                        "stages_ms": asm_stages,
+                        "input": "config-2 batch + bench_synth.decorate_assembly_like: N runs 10 kb-5 Mb, soft-masked runs, (AT)n/(CG)n/(ACGT)n and inverted repeats every ~50 kb"}
+            if not args.no_cpu:
+                import orc
+                n_chk = min(n_contigs, max(host_cores(), 8))
+                seqs_chk = [hb.array[i * clen:(i + 1) * clen] for i in range(n_chk)]
+                cpu_out, cpu_off = orc.shmmrs_batch(list(range(n_chk)), seqs_chk, orc.mkspec(*SPEC), False, nthreads=host_cores())
+                got, goff = ctx.shmmrs_download()
+                k = int(goff[n_chk])
+                assembly["parity_first_%d_contigs_vs_oracle" % n_chk] = bool(k == int(cpu_off[-1]) and np.array_equal(got[:k], cpu_out))
+                assert assembly["parity_first_%d_contigs_vs_oracle" % n_chk], "assembly-like batch: GPU result differs from the oracle"
         hb.free()
 
-    # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        import orc
-        cores = host_cores()
-        n_sample = min(n_contigs, max(2 * cores, 16))
-        sample = store[SLACK: SLACK + n_sample * clen].cpu().numpy()
-        seqs = [sample[i * clen:(i + 1) * clen] for i in range(n_sample)]
-        ospec = orc.mkspec(*SPEC)
-        orc.shmmrs_batch(list(range(min(cores, n_sample))), seqs[:cores], ospec, False, nthreads=cores)  # warm
-        t0 = time.perf_counter()
-        cpu_out, cpu_off = orc.shmmrs_batch(list(range(n_sample)), seqs, ospec, False, nthreads=cores)
-        dt = time.perf_counter() - t0
-        # and it doubles as a full-size parity spot check of the resident result
-        got, goff = ctx.shmmrs_download()
-        k = int(goff[n_sample])
-        assert k == int(cpu_off[-1]) and np.array_equal(got[:k], cpu_out), "GPU result differs from the oracle on the CPU sample"
-        cpu = {"value": n_sample * clen / dt / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
-               "sample": "first %d of %d contigs x %d bases, one sequence per thread (seq_db.rs:461); parity of these contigs checked" % (n_sample, n_contigs, clen)}
+    ctx.close()
+    del store
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[2]: the multi-GPU ShmmrFragMap build, strong scaling, NCCL all-to-all inside the library -----------
+    index_build = None
+    if not args.no_index:
+        import bench_index
+        from pgr_tk_b200 import distributed as PD
+        comm = PD.init_comm(local_rank) if world > 1 else pg.Comm(pg.comm_unique_id(), 0, 1, local_rank)
+        index_build = bench_index.run(pg, torch, dist, rank, world, local_rank, comm, reps=3, n_hap=args.index_haps, hap_len=args.index_hap_len,
+                                      oracle_parity=not args.no_cpu, cores=host_cores())
+        comm.close()
 
     if rank == 0:
         line = {
@@ -365,10 +451,15 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if e2e_pageable is not None:
+            line["e2e_pageable"] = e2e_pageable
+        if assembly is not None:
+            line["assembly_like"] = assembly
+        if index_build is not None:
+            line["index_build"] = index_build
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

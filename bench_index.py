@@ -1,0 +1,187 @@
+"""The multi-GPU ShmmrFragMap build (BASELINE.json configs[2]: 94 synthetic haplotypes x 50 Mb, 80/56/4/64) as bench.py
+measures it at N = 1, 2, 4, 8 GPUs: STRONG scaling — the 94 haplotypes are cut into N consecutive blocks, every rank
+computes the shimmers and tuples of its block, ONE all-to-all (grouped ncclSend/ncclRecv inside libpgr_b200) moves every
+tuple to the owner of its key range, the owner sorts its range into a CSR slice (pgr_b200_index_build_sharded).
+
+Reported (max over ranks, CUDA-synchronised wall clock around the C-ABI call, barrier before):
+  e2e       host (pinned) sequences -> per-rank sorted CSR slices in HBM (H2D of the bases inside)
+  resident  sequences already in HBM -> the same
+  stages    rank-0 CUDA-event times of stage / partition / exchange / sort, all-to-all bytes that crossed NVLink
+  parity    N = 1: the GPU map equals the oracle's map built from the same 94 haplotypes (all of them, all host cores);
+            N > 1: every rank's slice equals the corresponding key range of the single-GPU map that rank 0 builds from all
+            94 haplotypes (sha-256 of keys, per-key counts and signatures), i.e. the N-GPU canonical .mdb is byte-identical
+"""
+import hashlib
+import os
+import time
+
+import numpy as np
+
+import bench_synth as S
+
+N_HAP = 94
+HAP_LEN = 50_000_000
+SPEC = (80, 56, 4, 64)
+SLACK = 16384
+
+
+def slice_digest(keys, offs, sigs):
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(keys).tobytes())
+    h.update(np.diff(offs.astype(np.uint64)).astype(np.uint64).tobytes())
+    for f in ("frg_id", "sid", "bgn", "end", "ori"):
+        h.update(np.ascontiguousarray(sigs[f]).tobytes())
+    return h.digest()
+
+
+def run(pg, torch, dist, rank, world, local_rank, comm, reps=3, n_hap=N_HAP, hap_len=HAP_LEN, oracle_parity=True, cores=1):
+    dev = torch.device("cuda", local_rank)
+    spec = pg.ShmmrSpec(*SPEC)
+    lo, hi = (n_hap * rank) // world, (n_hap * (rank + 1)) // world
+    need_all = rank == 0                       # rank 0 holds every haplotype: single-GPU reference (N > 1) / oracle (N = 1)
+    t0 = time.perf_counter()
+    ids = range(n_hap) if need_all else range(lo, hi)
+    views, ptrs, lens, owner = S.pangenome(hap_len, ids, alloc=pg.host_alloc, threads=min(16, max(2, cores)))
+    gen_s = time.perf_counter() - t0
+    my = slice(lo, hi) if need_all else slice(0, hi - lo)
+    my_ptrs, my_lens, my_views = ptrs[my], lens[my], views[my]
+    my_sids = list(range(lo, hi))
+    bases_local = int(sum(my_lens))
+    tb = torch.tensor([bases_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb)
+    bases_total = int(tb.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        ts, last = [], None
+        for it in range(1 + reps):
+            barrier()
+            t0 = time.perf_counter()
+            idx, info = fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if it >= 1:
+                ts.append(float(t.item()))
+            if last is not None:
+                last[0].close()
+            last = (idx, info)
+        return ts, last
+
+    # ---- e2e: host (pinned) block -> this rank's sorted CSR slice ------------------------------------------------------
+    def build_host():
+        idx = pg.ShmmrIndex(spec, pg.FRG_ID_FASTX, local_rank)
+        return idx, idx.build_sharded_ptrs(comm, my_sids, my_ptrs, my_lens)
+
+    e2e_ts, (idx_e2e, info_e2e) = timed(build_host)
+
+    # ---- resident: the block already in HBM --------------------------------------------------------------------------
+    offs_dev, off = [], SLACK
+    for ln in my_lens:
+        offs_dev.append(off)
+        off += (ln + 31) & ~31
+    store = torch.zeros(off + SLACK, dtype=torch.uint8, device=dev)
+    for v, o, ln in zip(my_views, offs_dev, my_lens):
+        store[o:o + ln].copy_(torch.from_numpy(v), non_blocking=True)
+    torch.cuda.synchronize()
+
+    def build_dev():
+        idx = pg.ShmmrIndex(spec, pg.FRG_ID_FASTX, local_rank)
+        return idx, idx.build_sharded_device(comm, store.data_ptr(), my_sids, offs_dev, my_lens)
+
+    res_ts, (idx_res, info_res) = timed(build_dev)
+    del store
+
+    # ---- parity --------------------------------------------------------------------------------------------------------
+    gk, go, gs = idx_res.export()
+    ek, eo, es = idx_e2e.export()
+    same_paths = bool(np.array_equal(gk, ek) and np.array_equal(go, eo) and gs.tobytes() == es.tobytes())
+    nk_all = [len(gk)]
+    dig = np.frombuffer(slice_digest(gk, go, gs), dtype=np.uint8).copy()
+    if world > 1:
+        t = torch.tensor([len(gk), len(gs)], dtype=torch.int64, device=dev)
+        outs = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        nk_all = [int(o[0]) for o in outs]
+        ns_all = [int(o[1]) for o in outs]
+        d = torch.from_numpy(dig).to(dev)
+        douts = [torch.zeros_like(d) for _ in range(world)]
+        dist.all_gather(douts, d)
+        digs = [bytes(x.cpu().numpy().tobytes()) for x in douts]
+    else:
+        ns_all = [len(gs)]
+        digs = [bytes(dig.tobytes())]
+    parity, cpu = {"host_and_resident_paths_equal": same_paths}, None
+    if rank == 0:
+        if world > 1:
+            single = pg.ShmmrIndex(spec, pg.FRG_ID_FASTX, local_rank)
+            single.add_batch(list(range(n_hap)), views)
+            fk, fo, fs = single.export()
+            single.close()
+            ok = sum(nk_all) == len(fk) and sum(ns_all) == len(fs)
+            k0 = 0
+            for r in range(world):
+                if not ok:
+                    break
+                k1 = k0 + nk_all[r]
+                s0, s1 = int(fo[k0]), int(fo[k1])
+                ok = ok and slice_digest(fk[k0:k1], fo[k0:k1 + 1] - fo[k0], fs[s0:s1]) == digs[r]
+                k0 = k1
+            parity["n_gpu_slices_equal_single_gpu_map"] = bool(ok)
+            parity["canonical_mdb_byte_identical_to_single_gpu"] = bool(ok)
+        elif oracle_parity:
+            import orc
+            o = orc.Index(orc.mkspec(*SPEC), 0)
+            t0 = time.perf_counter()
+            o.add_batch(list(range(n_hap)), views, nthreads=cores)
+            cpu_s = time.perf_counter() - t0
+            ok_, oo, os_ = o.export()
+            parity["all_%d_haplotypes_equal_oracle_map" % n_hap] = bool(
+                np.array_equal(gk, ok_) and np.array_equal(go, oo) and all(np.array_equal(gs[f], os_[f]) for f in ("frg_id", "sid", "bgn", "end", "ori")))
+            cpu = {"value": bases_total / cpu_s / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
+                   "sample": "all %d haplotypes: shimmers one sequence per thread in batches of <=129, single-threaded inserts (seq_db.rs:461,326-340)" % n_hap}
+            del o
+        if world == 1:
+            # the sharded code path on ONE device: 3 shards on cuda:0 (exchange through device-to-device copies) == single
+            m = pg.ShardedIndex(spec, pg.FRG_ID_FASTX, devices=[local_rank] * 3)
+            m.add_batch(list(range(n_hap)), views)
+            mk, mo, ms = m.export()
+            m.close()
+            parity["three_shards_on_one_device_equal_single"] = bool(np.array_equal(mk, gk) and np.array_equal(mo, go) and ms.tobytes() == gs.tobytes())
+    idx_res.close()
+    idx_e2e.close()
+    owner.free()
+    if rank != 0:
+        return None
+    e2e_s, res_s = float(np.mean(e2e_ts)), float(np.mean(res_ts))
+    n_sigs = int(sum(ns_all))
+    # algorithmic bytes of the build: 1 B/base + 16 B per shimmer (shimmer stage) + 16 B per shimmer read +
+    # 2 x 33 B per tuple (write once, reorder once)
+    n_shmmr = n_sigs + n_hap
+    algo = bases_total + 16 * n_shmmr + 16 * n_shmmr + 2 * 33 * n_sigs
+    out = {
+        "workload": "ShmmrFragMap build on %d synthetic haplotypes x %d bases (%.2f Gbases), w=80 k=56 r=4 min_span=64" % (n_hap, hap_len, bases_total / 1e9),
+        "scaling": "strong", "n_gpus": world, "reps": reps, "warmup": 1,
+        "e2e": {"value": bases_total / e2e_s / 1e9, "unit": "Gbases/s", "ms": e2e_s * 1e3, "h2d_bytes": bases_total,
+                "api": "pgr_b200_index_build_sharded (host pinned sequences -> per-rank sorted CSR slice in HBM)"},
+        "resident": {"value": bases_total / res_s / 1e9, "unit": "Gbases/s", "ms": res_s * 1e3,
+                     "api": "pgr_b200_index_build_sharded_device (sequences in HBM -> per-rank sorted CSR slice)",
+                     "algorithmic_bytes": algo, "achieved_gbs": algo / res_s / 1e9},
+        "n_keys": int(sum(nk_all)), "n_sigs": n_sigs,
+        "rank0_stages_ms_e2e": {k: info_e2e[k] for k in ("stage_ms", "partition_ms", "exchange_ms", "sort_ms")},
+        "rank0_stages_ms_resident": {k: info_res[k] for k in ("stage_ms", "partition_ms", "exchange_ms", "sort_ms")},
+        "all_to_all": {"transport": "grouped ncclSend/ncclRecv inside libpgr_b200" if world > 1 else "none (1 GPU)",
+                       "rank0_bytes_sent": info_res["bytes_sent"], "rank0_bytes_recv": info_res["bytes_recv"],
+                       "rank0_tuples_local": info_res["n_tuples_local"], "rank0_tuples_owned": info_res["n_tuples_owned"]},
+        "parity": parity, "synth_gen_s": gen_s,
+    }
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    return out
