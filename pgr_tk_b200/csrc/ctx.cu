@@ -8,7 +8,7 @@
 #include <ctime>
 #include <mutex>
 
-#include "shmmr_kernels.cuh"
+#include "patch_kernels.cuh"
 
 namespace pgr {
 
@@ -177,7 +177,7 @@ void pgr_b200_ctx_free(pgr_b200_ctx *ctx) {
     pgr::DevBuf *bufs[] = {&ctx->seq_store, &ctx->d_off, &ctx->d_len, &ctx->d_rid, &ctx->tile_prefix, &ctx->cta_tile, &ctx->arena,
                            &ctx->chunk_count, &ctx->seq_count, &ctx->seq_flag, &ctx->replay_list, &ctx->replay_count,
                            &ctx->chunk_prefix, &ctx->seq_fast, &ctx->seq_dst, &ctx->bufA, &ctx->bufB, &ctx->flags,
-                           &ctx->block_sum, &ctx->block_prefix, &ctx->block_chunk, &ctx->off_a, &ctx->off_b, &ctx->fix_mm, &ctx->fix_off, &ctx->skips, &ctx->n_skips};
+                           &ctx->block_sum, &ctx->block_prefix, &ctx->block_chunk, &ctx->off_a, &ctx->off_b, &ctx->fix_mm, &ctx->fix_off, &ctx->mark_bits, &ctx->allinv_bits, &ctx->n_skips};
     for (auto b : bufs) b->release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -450,131 +450,173 @@ int occupancy_l0(int *occ) {
     return PGR_OK;
 }
 
-// Replace the level-0 entries around pushed palindromic positions (fmmer == rmmer) by an exact replay of the reference
-// machine (patch_replay_kernel), then splice: flat list moves bufA -> bufB -> (swap) bufA, offsets updated in seq_dst.
-int apply_palindrome_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_skips, const std::vector<uint32_t> &flagged,
-                             const std::vector<uint64_t> &off0, uint64_t *n_l0) {
+// Replace the level-0 entries around the marked blocks (palindromes, bytes outside ACGTacgt) by an exact replay of the
+// reference machine (patch_kernels.cuh), then splice: flat list moves bufA -> bufB -> (swap) bufA, offsets updated in seq_dst.
+int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_marks, const std::vector<uint32_t> &flagged,
+                  const std::vector<uint64_t> &off0, uint64_t word_lo, uint64_t word_hi, uint64_t *n_l0) {
     cudaStream_t st = ctx->stream;
     const size_t n = ctx->rn;
-    std::vector<uint2> sk(n_skips);
-    PGR_CUDA(cudaMemcpyAsync(sk.data(), ctx->skips.p, n_skips * sizeof(uint2), cudaMemcpyDeviceToHost, st));
-    PGR_CUDA(cudaStreamSynchronize(st));
-    std::vector<uint64_t> key;
-    key.reserve(n_skips);
-    for (auto &e : sk) if (!flagged[e.x]) key.push_back(((uint64_t)e.x << 32) | e.y);   // flagged sequences are replayed whole
-    std::sort(key.begin(), key.end());
-    key.erase(std::unique(key.begin(), key.end()), key.end());       // halo positions are seen by two tiles
-    if (key.empty()) return PGR_OK;
-    std::vector<uint32_t> aff_seq, skip_off(1, 0), skip_pos;
-    for (size_t i = 0; i < key.size(); i++) {
-        const uint32_t s = (uint32_t)(key[i] >> 32);
-        if (aff_seq.empty() || aff_seq.back() != s) { if (!aff_seq.empty()) skip_off.push_back((uint32_t)skip_pos.size()); aff_seq.push_back(s); }
-        skip_pos.push_back((uint32_t)key[i]);
-    }
-    skip_off.push_back((uint32_t)skip_pos.size());
-    const uint32_t n_aff = (uint32_t)aff_seq.size(), n_slots = (uint32_t)skip_pos.size();
-    DevBuf d_aff, d_soff, d_spos, d_np, d_q, d_eoff, d_entries, d_meta, d_epatch;
-    auto cleanup = [&]() { d_aff.release(); d_soff.release(); d_spos.release(); d_np.release(); d_q.release(); d_eoff.release();
-                           d_entries.release(); d_meta.release(); d_epatch.release(); };
+    const uint32_t gap = (6 * spec.w + spec.k + 64 + 31) / 32 + 1;
+    DevBuf d_sorted, d_clusters, d_q, d_nadd, d_nfill, d_eoff, d_foff, d_fills, d_entries, d_meta;
+    auto cleanup = [&]() { d_sorted.release(); d_clusters.release(); d_q.release(); d_nadd.release(); d_nfill.release(); d_eoff.release();
+                           d_foff.release(); d_fills.release(); d_entries.release(); d_meta.release(); };
     int rc = PGR_OK;
 #define PATCH_TRY(x) do { rc = (x); if (rc != PGR_OK) { cleanup(); return rc; } } while (0)
 #define PATCH_CUDA(x) do { if ((x) != cudaSuccess) { set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); cleanup(); return PGR_E_CUDA; } } while (0)
-    PATCH_TRY(d_aff.ensure(n_aff * 4)); PATCH_TRY(d_soff.ensure((n_aff + 1) * 4)); PATCH_TRY(d_spos.ensure(n_slots * 4));
-    PATCH_TRY(d_np.ensure(n_aff * 4)); PATCH_TRY(d_q.ensure((size_t)n_slots * 4 * 3)); PATCH_TRY(d_eoff.ensure((size_t)n_slots * 8));
-    PATCH_CUDA(cudaMemcpyAsync(d_aff.p, aff_seq.data(), n_aff * 4, cudaMemcpyHostToDevice, st));
-    PATCH_CUDA(cudaMemcpyAsync(d_soff.p, skip_off.data(), (n_aff + 1) * 4, cudaMemcpyHostToDevice, st));
-    PATCH_CUDA(cudaMemcpyAsync(d_spos.p, skip_pos.data(), n_slots * 4, cudaMemcpyHostToDevice, st));
-    PatchParams pp;
-    pp.seq = ctx->d_seq; pp.off = ctx->d_off.as<uint64_t>() + ctx->r0; pp.len = ctx->d_len.as<uint32_t>() + ctx->r0;
-    pp.aff_seq = d_aff.as<uint32_t>(); pp.skip_off = d_soff.as<uint32_t>(); pp.skip_pos = d_spos.as<uint32_t>(); pp.n_aff = n_aff;
-    pp.w = spec.w; pp.k = spec.k; pp.n_patches = d_np.as<uint32_t>();
-    pp.q0 = d_q.as<uint32_t>(); pp.q1 = pp.q0 + n_slots; pp.n_add = pp.q0 + 2 * n_slots;
-    pp.entry_off = d_eoff.as<uint64_t>(); pp.entries = nullptr;
-    const int slot_t = ctx->timer.begin("l0_palindrome_patches", st);
-    patch_replay_kernel<0><<<ceil_div<uint32_t>(n_aff, 32), 32, 0, st>>>(pp);
+    const int slot_t = ctx->timer.begin("l0_patches", st);
+    // 1. clusters of marked blocks.  The finder looks sequences up by store offset: sorted copy of the chunk's tables
+    std::vector<uint32_t> ord(n);
+    for (size_t i = 0; i < n; i++) ord[i] = (uint32_t)i;
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ctx->h_off[ctx->r0 + a] < ctx->h_off[ctx->r0 + b]; });
+    std::vector<uint64_t> s_off(n);
+    std::vector<uint32_t> s_len(n);
+    for (size_t i = 0; i < n; i++) { s_off[i] = ctx->h_off[ctx->r0 + ord[i]]; s_len[i] = ctx->h_len[ctx->r0 + ord[i]]; }
+    PATCH_TRY(d_sorted.ensure(n * 16 + 64));
+    uint64_t *ds_off = d_sorted.as<uint64_t>();
+    uint32_t *ds_len = (uint32_t *)(ds_off + n), *ds_sid = ds_len + n;
+    PATCH_CUDA(cudaMemcpyAsync(ds_off, s_off.data(), n * 8, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(ds_len, s_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(ds_sid, ord.data(), n * 4, cudaMemcpyHostToDevice, st));
+    PATCH_TRY(d_clusters.ensure((size_t)n_marks * sizeof(Cluster) + 64));   // every cluster holds at least one marking event
+    uint32_t *d_ncl = (uint32_t *)((uint8_t *)d_clusters.p + (size_t)n_marks * sizeof(Cluster));
+    PATCH_CUDA(cudaMemsetAsync(d_ncl, 0, 4, st));
+    ClusterFindParams cf;
+    cf.bits = ctx->mark_bits.as<uint32_t>(); cf.word_lo = word_lo; cf.word_hi = word_hi;
+    cf.s_off = ds_off; cf.s_len = ds_len; cf.s_sid = ds_sid; cf.n_seq = (uint32_t)n; cf.gap = gap;
+    cf.out = d_clusters.as<Cluster>(); cf.cap = n_marks; cf.n_out = d_ncl;
+    cluster_find_kernel<<<(uint32_t)ceil_div<uint64_t>(word_hi - word_lo, 256), 256, 0, st>>>(cf);
     PATCH_CUDA(cudaGetLastError());
-    std::vector<uint32_t> h_np(n_aff), h_q(3 * (size_t)n_slots);
-    PATCH_CUDA(cudaMemcpyAsync(h_np.data(), d_np.p, n_aff * 4, cudaMemcpyDeviceToHost, st));
-    PATCH_CUDA(cudaMemcpyAsync(h_q.data(), d_q.p, (size_t)n_slots * 12, cudaMemcpyDeviceToHost, st));
+    uint32_t n_cl = 0;
+    PATCH_CUDA(cudaMemcpyAsync(&n_cl, d_ncl, 4, cudaMemcpyDeviceToHost, st));
     PATCH_CUDA(cudaStreamSynchronize(st));
-    // compact patch table (sorted by sequence, then position) + per-slot entry offsets for the write pass
-    std::vector<uint32_t> pseq, pq0, pq1, padd;
-    std::vector<uint64_t> pentry_off, slot_eoff(n_slots, 0);
+    if (n_cl > n_marks) { set_error("cluster list overflow"); cleanup(); return PGR_E_CUDA; }
+    std::vector<Cluster> cl(n_cl);
+    PATCH_CUDA(cudaMemcpyAsync(cl.data(), d_clusters.p, (size_t)n_cl * sizeof(Cluster), cudaMemcpyDeviceToHost, st));
+    PATCH_CUDA(cudaStreamSynchronize(st));
+    // whole-sequence replays (flagged) need no patch; the rest sorted by (sequence, position)
+    cl.erase(std::remove_if(cl.begin(), cl.end(), [&](const Cluster &c) { return flagged[c.sid] != 0; }), cl.end());
+    std::sort(cl.begin(), cl.end(), [](const Cluster &a, const Cluster &b) { return a.sid != b.sid ? a.sid < b.sid : a.pos < b.pos; });
+    size_t P = cl.size();
+    if (P == 0) { ctx->timer.end(slot_t, st); cleanup(); return PGR_OK; }
+    PATCH_CUDA(cudaMemcpyAsync(d_clusters.p, cl.data(), P * sizeof(Cluster), cudaMemcpyHostToDevice, st));
+    // 2. count pass
+    PATCH_TRY(d_q.ensure(P * 12)); PATCH_TRY(d_nadd.ensure(P * 8)); PATCH_TRY(d_nfill.ensure(P * 4));
+    PATCH_TRY(d_eoff.ensure(P * 8)); PATCH_TRY(d_foff.ensure(P * 4));
+    ReplayClusterParams rp;
+    rp.seq = ctx->d_seq; rp.off = ctx->d_off.as<uint64_t>() + ctx->r0; rp.len = ctx->d_len.as<uint32_t>() + ctx->r0;
+    rp.mark_bits = ctx->mark_bits.as<uint32_t>(); rp.allinv_bits = ctx->allinv_bits.as<uint32_t>();
+    rp.clusters = d_clusters.as<Cluster>(); rp.n_clusters = (uint32_t)P; rp.w = spec.w; rp.k = spec.k; rp.gap = gap;
+    rp.q0 = d_q.as<uint32_t>(); rp.q1 = rp.q0 + P; rp.t_stop = rp.q0 + 2 * P; rp.n_add = d_nadd.as<uint64_t>(); rp.n_fill = d_nfill.as<uint32_t>();
+    rp.entry_off = d_eoff.as<uint64_t>(); rp.fill_off = d_foff.as<uint32_t>(); rp.entries = nullptr; rp.fills = nullptr;
+    cluster_replay_kernel<0><<<ceil_div<uint32_t>((uint32_t)P, 32), 32, 0, st>>>(rp);
+    PATCH_CUDA(cudaGetLastError());
+    std::vector<uint32_t> h_q(3 * P), h_nfill(P);
+    std::vector<uint64_t> h_nadd(P);
+    PATCH_CUDA(cudaMemcpyAsync(h_q.data(), d_q.p, P * 12, cudaMemcpyDeviceToHost, st));
+    PATCH_CUDA(cudaMemcpyAsync(h_nadd.data(), d_nadd.p, P * 8, cudaMemcpyDeviceToHost, st));
+    PATCH_CUDA(cudaMemcpyAsync(h_nfill.data(), d_nfill.p, P * 4, cudaMemcpyDeviceToHost, st));
+    PATCH_CUDA(cudaStreamSynchronize(st));
+    if (getenv("PGR_B200_DEBUG_PATCHES"))
+        for (size_t j = 0; j < P; j++) fprintf(stderr, "[patch] sid %u pos %u q0 %u q1 %u t_stop %u n_add %llu n_fill %u\n", cl[j].sid, cl[j].pos, h_q[j], h_q[P + j], h_q[2 * P + j], (unsigned long long)h_nadd[j], h_nfill[j]);
+    {   // a replay that ran past the start of later clusters (stuck machine, or to the end of the sequence) subsumes them:
+        // their own replays assumed a machine in its normal regime and are dropped
+        size_t o = 0;
+        uint32_t cur_sid = 0xFFFFFFFFu, reach = 0;   // stop position of the last kept patch of cur_sid
+        std::vector<uint32_t> kq0, kq1;
+        for (size_t j = 0; j < P; j++) {
+            if (cl[j].sid == cur_sid && (reach == 0xFFFFFFFFu || cl[j].pos <= reach)) continue;
+            cur_sid = cl[j].sid; reach = h_q[2 * P + j];
+            cl[o] = cl[j]; kq0.push_back(h_q[j]); kq1.push_back(h_q[P + j]); h_nadd[o] = h_nadd[j]; h_nfill[o] = h_nfill[j];
+            o++;
+        }
+        if (o != P) {
+            ctx->counters[7] += P - o;
+            P = o;
+            cl.resize(P); h_nadd.resize(P); h_nfill.resize(P);
+            PATCH_CUDA(cudaMemcpyAsync(d_clusters.p, cl.data(), P * sizeof(Cluster), cudaMemcpyHostToDevice, st));
+            rp.n_clusters = (uint32_t)P; rp.q1 = rp.q0 + P; rp.t_stop = rp.q0 + 2 * P;
+        }
+        h_q.assign(kq0.begin(), kq0.end());
+        h_q.insert(h_q.end(), kq1.begin(), kq1.end());
+    }
+    std::vector<uint64_t> pentry_off(P);
+    std::vector<uint32_t> pfill_off(P);
+    uint64_t n_entries = 0, n_fills = 0;
+    for (size_t j = 0; j < P; j++) { pentry_off[j] = n_entries; n_entries += h_nadd[j]; pfill_off[j] = (uint32_t)n_fills; n_fills += h_nfill[j]; }
+    // 3. write pass + fill segments
+    PATCH_TRY(d_entries.ensure(std::max<uint64_t>(1, n_entries) * sizeof(pgr_mm128)));
+    PATCH_TRY(d_fills.ensure(std::max<uint64_t>(1, n_fills) * sizeof(FillSeg)));
+    PATCH_CUDA(cudaMemcpyAsync(d_eoff.p, pentry_off.data(), P * 8, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(d_foff.p, pfill_off.data(), P * 4, cudaMemcpyHostToDevice, st));
+    rp.entries = d_entries.as<pgr_mm128>(); rp.fills = d_fills.as<FillSeg>();
+    cluster_replay_kernel<1><<<ceil_div<uint32_t>((uint32_t)P, 32), 32, 0, st>>>(rp);
+    if (n_fills) fill_segments_kernel<<<(uint32_t)n_fills, 256, 0, st>>>(d_fills.as<FillSeg>(), d_entries.as<pgr_mm128>());
+    PATCH_CUDA(cudaGetLastError());
+    // 4. splice.  Patch metadata on the device: [pseq | pq0 | pq1 | plb | pub] u32, then pn_add, pentry_off, pdelta, pdst (8 B each),
+    //    off1[n+1] u64, seq_first_patch[n] i32, seq_n_patch[n] u32
+    std::vector<uint32_t> pseq(P);
     std::vector<int32_t> seq_first(n, -1);
     std::vector<uint32_t> seq_np(n, 0);
-    uint64_t n_entries = 0;
-    for (uint32_t a = 0; a < n_aff; a++) {
-        seq_first[aff_seq[a]] = (int32_t)pseq.size();
-        seq_np[aff_seq[a]] = h_np[a];
-        for (uint32_t j = 0; j < h_np[a]; j++) {
-            const uint32_t slot = skip_off[a] + j;
-            pseq.push_back(aff_seq[a]); pq0.push_back(h_q[slot]); pq1.push_back(h_q[n_slots + slot]); padd.push_back(h_q[2 * (size_t)n_slots + slot]);
-            pentry_off.push_back(n_entries);
-            slot_eoff[slot] = n_entries;
-            n_entries += h_q[2 * (size_t)n_slots + slot];
-        }
-    }
-    const uint32_t n_patches = (uint32_t)pseq.size();
-    PATCH_TRY(d_entries.ensure(std::max<uint64_t>(1, n_entries) * sizeof(pgr_mm128)));
-    PATCH_CUDA(cudaMemcpyAsync(d_eoff.p, slot_eoff.data(), (size_t)n_slots * 8, cudaMemcpyHostToDevice, st));
-    pp.entries = d_entries.as<pgr_mm128>();
-    patch_replay_kernel<1><<<ceil_div<uint32_t>(n_aff, 32), 32, 0, st>>>(pp);
-    PATCH_CUDA(cudaGetLastError());
-    // patch metadata on the device: [pseq | pq0 | pq1 | padd | plb | pub] u32, then pentry_off, pdelta, pdst u64/i64
-    const size_t P = n_patches;
-    PATCH_TRY(d_meta.ensure(P * 4 * 6 + P * 8 * 3 + n * 4 * 2 + (n + 1) * 8 + 64));
+    for (size_t j = 0; j < P; j++) { pseq[j] = cl[j].sid; if (seq_first[cl[j].sid] < 0) seq_first[cl[j].sid] = (int32_t)j; seq_np[cl[j].sid]++; }
+    PATCH_TRY(d_meta.ensure(P * 4 * 6 + P * 8 * 4 + (n + 1) * 8 + n * 8 + 64));
     uint32_t *m_u32 = d_meta.as<uint32_t>();
-    uint64_t *m_u64 = (uint64_t *)(m_u32 + 6 * P + (P & 1) * 0 + ((6 * P) & 1));
-    // keep 8-byte alignment of the u64 block
-    m_u64 = (uint64_t *)(((uintptr_t)(m_u32 + 6 * P) + 7) & ~(uintptr_t)7);
-    int32_t *m_first = (int32_t *)(m_u64 + 3 * P + (n + 1));
+    uint64_t *m_u64 = (uint64_t *)(((uintptr_t)(m_u32 + 5 * P) + 7) & ~(uintptr_t)7);
+    int32_t *m_first = (int32_t *)(m_u64 + 4 * P + (n + 1));
     uint32_t *m_np = (uint32_t *)(m_first + n);
     PATCH_CUDA(cudaMemcpyAsync(m_u32, pseq.data(), P * 4, cudaMemcpyHostToDevice, st));
-    PATCH_CUDA(cudaMemcpyAsync(m_u32 + P, pq0.data(), P * 4, cudaMemcpyHostToDevice, st));
-    PATCH_CUDA(cudaMemcpyAsync(m_u32 + 2 * P, pq1.data(), P * 4, cudaMemcpyHostToDevice, st));
-    PATCH_CUDA(cudaMemcpyAsync(m_u32 + 3 * P, padd.data(), P * 4, cudaMemcpyHostToDevice, st));
-    PATCH_CUDA(cudaMemcpyAsync(m_u64, pentry_off.data(), P * 8, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(m_u32 + P, h_q.data(), P * 8, cudaMemcpyHostToDevice, st));           // pq0 | pq1
+    PATCH_CUDA(cudaMemcpyAsync(m_u64, h_nadd.data(), P * 8, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(m_u64 + P, pentry_off.data(), P * 8, cudaMemcpyHostToDevice, st));
     PATCH_CUDA(cudaMemcpyAsync(m_first, seq_first.data(), n * 4, cudaMemcpyHostToDevice, st));
     PATCH_CUDA(cudaMemcpyAsync(m_np, seq_np.data(), n * 4, cudaMemcpyHostToDevice, st));
     SpliceParams sp;
     sp.flat0 = ctx->bufA.as<pgr_mm128>(); sp.off0 = ctx->seq_dst.as<uint64_t>(); sp.n_seq = (uint32_t)n;
     sp.seq_first_patch = m_first; sp.seq_n_patch = m_np;
-    sp.pseq = m_u32; sp.pq0 = m_u32 + P; sp.pq1 = m_u32 + 2 * P; sp.pn_add = m_u32 + 3 * P; sp.plb = m_u32 + 4 * P; sp.pub = m_u32 + 5 * P;
-    sp.pentry_off = m_u64; sp.pdelta = (const int64_t *)(m_u64 + P); sp.pdst = m_u64 + 2 * P; sp.off1 = m_u64 + 3 * P;
-    sp.entries = d_entries.as<pgr_mm128>(); sp.n_patches = n_patches; sp.n0 = off0[n];
-    splice_bounds_kernel<<<ceil_div<uint32_t>(n_patches, 64), 64, 0, st>>>(sp);
+    sp.pseq = m_u32; sp.pq0 = m_u32 + P; sp.pq1 = m_u32 + 2 * P; sp.plb = m_u32 + 3 * P; sp.pub = m_u32 + 4 * P;
+    sp.pn_add = m_u64; sp.pentry_off = m_u64 + P; sp.pdelta = (const int64_t *)(m_u64 + 2 * P); sp.pdst = m_u64 + 3 * P; sp.off1 = m_u64 + 4 * P;
+    sp.entries = d_entries.as<pgr_mm128>(); sp.n_patches = (uint32_t)P; sp.n0 = off0[n];
+    splice_bounds_kernel<<<ceil_div<uint32_t>((uint32_t)P, 64), 64, 0, st>>>(sp);
     PATCH_CUDA(cudaGetLastError());
     std::vector<uint32_t> plb(P), pub(P);
     PATCH_CUDA(cudaMemcpyAsync(plb.data(), sp.plb, P * 4, cudaMemcpyDeviceToHost, st));
     PATCH_CUDA(cudaMemcpyAsync(pub.data(), sp.pub, P * 4, cudaMemcpyDeviceToHost, st));
     PATCH_CUDA(cudaStreamSynchronize(st));
-    std::vector<int64_t> pdelta(P), seq_delta(n, 0);
+    // consecutive patches of a sequence must not overlap (the cluster gap guarantees it)
     for (size_t j = 0; j < P; j++) {
-        pdelta[j] = seq_delta[pseq[j]];
-        seq_delta[pseq[j]] += (int64_t)padd[j] - (int64_t)(pub[j] - plb[j]);
+        if (pub[j] < plb[j] || (j > 0 && pseq[j] == pseq[j - 1] && plb[j] < pub[j - 1])) {
+            set_error("overlapping level-0 patches (sequence %u len %u w %u k %u gap %u): patch %zu pos %u q0 %u q1 %u lb %u ub %u n_add %llu | prev pos %u q0 %u q1 %u lb %u ub %u",
+                      pseq[j], ctx->h_len[ctx->r0 + pseq[j]], spec.w, spec.k, gap, j, cl[j].pos, h_q[j], h_q[P + j], plb[j], pub[j], (unsigned long long)h_nadd[j],
+                      j ? cl[j - 1].pos : 0u, j ? h_q[j - 1] : 0u, j ? h_q[P + j - 1] : 0u, j ? plb[j - 1] : 0u, j ? pub[j - 1] : 0u);
+            cleanup(); return PGR_E_CUDA;
+        }
+    }
+    std::vector<int64_t> pdelta(P), seq_delta(n, 0);
+    std::vector<int64_t> before(P);
+    for (size_t j = 0; j < P; j++) {
+        before[j] = seq_delta[pseq[j]];
+        seq_delta[pseq[j]] += (int64_t)h_nadd[j] - (int64_t)(pub[j] - plb[j]);
+        pdelta[j] = seq_delta[pseq[j]];          // shift of the entries that follow patch j
     }
     std::vector<uint64_t> off1(n + 1), pdst(P);
     uint64_t acc = 0;
     for (size_t i = 0; i < n; i++) { off1[i] = acc; acc += (uint64_t)((int64_t)(off0[i + 1] - off0[i]) + seq_delta[i]); }
     off1[n] = acc;
-    for (size_t j = 0; j < P; j++) pdst[j] = off1[pseq[j]] + plb[j] + (uint64_t)pdelta[j];
-    std::vector<uint32_t> entry_patch(n_entries);
-    for (size_t j = 0; j < P; j++) for (uint32_t e = 0; e < padd[j]; e++) entry_patch[pentry_off[j] + e] = (uint32_t)j;
-    PATCH_TRY(d_epatch.ensure(std::max<uint64_t>(1, n_entries) * 4));
+    for (size_t j = 0; j < P; j++) pdst[j] = off1[pseq[j]] + plb[j] + (uint64_t)before[j];
     PATCH_CUDA(cudaMemcpyAsync((void *)sp.pdelta, pdelta.data(), P * 8, cudaMemcpyHostToDevice, st));
     PATCH_CUDA(cudaMemcpyAsync((void *)sp.pdst, pdst.data(), P * 8, cudaMemcpyHostToDevice, st));
     PATCH_CUDA(cudaMemcpyAsync((void *)sp.off1, off1.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (n_entries) PATCH_CUDA(cudaMemcpyAsync(d_epatch.p, entry_patch.data(), n_entries * 4, cudaMemcpyHostToDevice, st));
     PATCH_TRY(ctx->bufB.ensure(std::max<uint64_t>(1, acc) * sizeof(pgr_mm128)));
     sp.flat1 = ctx->bufB.as<pgr_mm128>();
     if (sp.n0) splice_copy_kernel<<<(uint32_t)ceil_div<uint64_t>(sp.n0, 256), 256, 0, st>>>(sp);
-    if (n_entries) splice_patch_kernel<<<(uint32_t)ceil_div<uint64_t>(n_entries, 256), 256, 0, st>>>(sp, n_entries, d_epatch.as<uint32_t>());
+    splice_patch_kernel<<<(uint32_t)P, 256, 0, st>>>(sp);
     PATCH_CUDA(cudaGetLastError());
     PATCH_CUDA(cudaMemcpyAsync(ctx->seq_dst.p, off1.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     ctx->timer.end(slot_t, st);
     PATCH_CUDA(cudaStreamSynchronize(st));
-    ctx->counters[0] += 5;
-    ctx->counters[4] = n_patches;
+    ctx->counters[0] += 6 + (n_fills ? 1 : 0);
+    ctx->counters[4] = P;
+    ctx->counters[5] = n_fills;
+    ctx->counters[6] = n_entries;
     std::swap(ctx->bufA, ctx->bufB);
     PATCH_TRY(ctx->bufB.ensure(std::max<uint64_t>(1, acc) * sizeof(pgr_mm128)));
     *n_l0 = acc;
@@ -627,8 +669,19 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     PGR_TRY(ctx->chunk_count.ensure(G * sizeof(uint64_t)));
     PGR_TRY(ctx->seq_count.ensure(n * sizeof(uint32_t)));
     PGR_TRY(ctx->seq_flag.ensure(n * sizeof(uint32_t)));
-    PGR_TRY(ctx->skips.ensure((size_t)SKIP_CAP * sizeof(uint2)));
     PGR_TRY(ctx->n_skips.ensure(64));
+    // disturbance bitmaps over the 32-base blocks of the store region this chunk occupies (one bit per block, twice)
+    uint64_t blk_lo = ~0ull, blk_hi = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t o = ctx->h_off[ctx->r0 + i], l = ctx->h_len[ctx->r0 + i];
+        blk_lo = std::min(blk_lo, o >> 5); blk_hi = std::max(blk_hi, (o + l + 31) >> 5);
+    }
+    const uint64_t word_lo = blk_lo >> 5, word_hi = (blk_hi + 31) >> 5;
+    if ((size_t)word_hi * 4 + 64 > ctx->mark_bits.cap) {
+        PGR_TRY(ctx->mark_bits.ensure((size_t)word_hi * 4 + 64));
+        PGR_TRY(ctx->allinv_bits.ensure((size_t)word_hi * 4 + 64));
+        ctx->bits_dirty_lo = 0; ctx->bits_dirty_hi = ctx->mark_bits.cap / 4;   // fresh allocation: clear everything once
+    }
     trace_mark("run_l0: partition + buffers");
     PGR_CUDA(cudaMemcpyAsync(ctx->tile_prefix.p, tile_prefix.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     PGR_CUDA(cudaMemcpyAsync(ctx->cta_tile.p, cta_tile.data(), (G + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -646,6 +699,11 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         PGR_CUDA(cudaMemsetAsync(ctx->seq_count.p, 0, n * sizeof(uint32_t), st));
         PGR_CUDA(cudaMemsetAsync(ctx->seq_flag.p, 0, n * sizeof(uint32_t), st));
         PGR_CUDA(cudaMemsetAsync(ctx->n_skips.p, 0, sizeof(uint32_t), st));
+        if (ctx->bits_dirty_hi > ctx->bits_dirty_lo) {   // the bitmaps are cleared only where an earlier launch marked blocks
+            PGR_CUDA(cudaMemsetAsync(ctx->mark_bits.as<uint32_t>() + ctx->bits_dirty_lo, 0, (ctx->bits_dirty_hi - ctx->bits_dirty_lo) * 4, st));
+            PGR_CUDA(cudaMemsetAsync(ctx->allinv_bits.as<uint32_t>() + ctx->bits_dirty_lo, 0, (ctx->bits_dirty_hi - ctx->bits_dirty_lo) * 4, st));
+            ctx->bits_dirty_lo = ctx->bits_dirty_hi = 0;
+        }
         L0Params p;
         p.seq = ctx->d_seq; p.off = (ctx->d_off.as<uint64_t>() + ctx->r0); p.len = (ctx->d_len.as<uint32_t>() + ctx->r0);
         p.tile_prefix = ctx->tile_prefix.as<uint32_t>(); p.cta_tile = ctx->cta_tile.as<uint32_t>();
@@ -653,7 +711,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         p.arena = ctx->arena.as<pgr_mm128>(); p.chunk_cap = chunk_cap;
         p.chunk_count = ctx->chunk_count.as<uint64_t>(); p.seq_count = ctx->seq_count.as<uint32_t>();
         p.seq_flag = ctx->seq_flag.as<uint32_t>();
-        p.skips = ctx->skips.as<uint2>(); p.n_skips = ctx->n_skips.as<uint32_t>(); p.skip_cap = SKIP_CAP;
+        p.mark_bits = ctx->mark_bits.as<uint32_t>(); p.allinv_bits = ctx->allinv_bits.as<uint32_t>(); p.n_marks = ctx->n_skips.as<uint32_t>();
         p.m1 = ~0ull;
         trace_mark("run_l0: arena + memsets");
         const int slot = ctx->timer.begin("l0_minimizers", st);
@@ -668,6 +726,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         PGR_CUDA(cudaMemcpyAsync(h_flag, ctx->seq_flag.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         PGR_CUDA(cudaMemcpyAsync(h_nskips, ctx->n_skips.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         PGR_CUDA(cudaStreamSynchronize(st));
+        if (*h_nskips) { ctx->bits_dirty_lo = word_lo; ctx->bits_dirty_hi = word_hi; }
         uint64_t mx = 0;
         for (uint32_t c = 0; c < G; c++) mx = std::max(mx, h_chunk[c]);
         if (mx <= chunk_cap) break;
@@ -731,7 +790,7 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     PGR_TRY(ctx->bufB.ensure(std::max<uint64_t>(total, 1) * sizeof(pgr_mm128)));
     // No sequence to replay and no palindrome / invalid-byte record: the level-0 list is never patched, so the next
     // level reads it straight from the arena chunks (ChunkView) and the gather pass is skipped.
-    const uint32_t n_skips_seen = std::min<uint32_t>(*h_nskips, SKIP_CAP);
+    const uint32_t n_skips_seen = *h_nskips;
     static const bool always_gather = getenv("PGR_B200_ALWAYS_GATHER") != nullptr;   // A/B aid
     ctx->l0_chunked = total && replay.empty() && n_skips_seen == 0 && !always_gather;
     ctx->l0_chunk_cap = chunk_cap; ctx->l0_chunks = G;
@@ -760,11 +819,11 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     // the host vectors above are pageable: make sure the async copies are done before they go out of scope
     PGR_CUDA(cudaStreamSynchronize(st));
     trace_mark("run_l0: replay + gather");
-    const uint32_t n_skips = std::min<uint32_t>(*h_nskips, SKIP_CAP);
-    if (n_skips && total) {
+    const uint32_t n_marks = *h_nskips;
+    if (n_marks) {
         std::vector<uint32_t> flags(h_flag, h_flag + n);
-        PGR_TRY(apply_palindrome_patches(ctx, spec, n_skips, flags, seq_dst, n_l0));
-        trace_mark("run_l0: palindrome patches");
+        PGR_TRY(apply_patches(ctx, spec, n_marks, flags, seq_dst, word_lo, word_hi, n_l0));
+        trace_mark("run_l0: patches");
     }
     return PGR_OK;
 }

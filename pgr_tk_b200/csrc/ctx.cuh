@@ -44,7 +44,6 @@ struct StageTimer {
     void destroy();
 };
 
-constexpr uint32_t SKIP_CAP = 1u << 20;  // palindromic positions recorded per launch before whole-sequence replay takes over
 constexpr size_t SEQ_SLACK = 16384;  // readable bytes kept before the first and after the last sequence
 
 }  // namespace pgr
@@ -67,7 +66,8 @@ struct pgr_b200_ctx {
     void *h_ctl = nullptr; size_t h_ctl_cap = 0;
     // shimmer pipeline buffers
     pgr::DevBuf tile_prefix, cta_tile, arena, chunk_count, seq_count, seq_flag, replay_list, replay_count;
-    pgr::DevBuf chunk_prefix, seq_fast, seq_dst, bufA, bufB, flags, block_sum, block_prefix, block_chunk, off_a, off_b, skips, n_skips;
+    pgr::DevBuf chunk_prefix, seq_fast, seq_dst, bufA, bufB, flags, block_sum, block_prefix, block_chunk, off_a, off_b, mark_bits, allinv_bits, n_skips;
+    uint64_t bits_dirty_lo = 0, bits_dirty_hi = 0;   // bitmap words an earlier launch may have set (cleared lazily)
     uint64_t chunk_cap = 0;
     // result of the last shmmrs call
     const pgr_mm128 *d_result = nullptr;

@@ -7,8 +7,10 @@
 //             (rescans only) by one thread of the sequence's last tile;
 //   level 1,2: the same window-minimum rule over list indices with window r (reduce_shmmr, applied twice);
 //   min_span filter on the level-2 list.
-// Sequences containing a byte outside ACGTacgt or a pushed reverse-complement palindrome (fmmer == rmmer,
-// shmmrutils.rs:477) are flagged and recomputed by replay_l0_kernel, an exact sequential restatement.
+// The rule does not hold around a byte outside ACGTacgt (the reference keeps a stale k-mer, shmmrutils.rs:459-476) or a
+// pushed reverse-complement palindrome (fmmer == rmmer, shmmrutils.rs:477).  The tile kernel marks the 32-base blocks
+// that contain either in a bitmap; patch_kernels.cuh turns the marked blocks into clusters and replays the reference
+// machine around every cluster (one thread per cluster, long invalid runs crossed in closed form).
 #pragma once
 #include "common.cuh"
 
@@ -44,10 +46,11 @@ struct L0Params {
     uint64_t chunk_cap;          // entries per chunk
     uint64_t *chunk_count;       // [grid] entries demanded by each CTA (may exceed chunk_cap => host retries)
     uint32_t *seq_count;         // [n_seq] level-0 entries per sequence (atomicAdd per tile)
-    uint32_t *seq_flag;          // [n_seq] != 0 => sequence must be replayed sequentially
-    uint2 *skips;                // (sequence, position) of pushed positions with fmmer == rmmer (shmmrutils.rs:477)
-    uint32_t *n_skips;           // running count; beyond skip_cap the sequence is flagged instead
-    uint32_t skip_cap;
+    uint32_t *seq_flag;          // [n_seq] != 0 => sequence must be replayed sequentially (candidate list overflow; never seen)
+    // disturbance bitmaps over the 32-base blocks of the sequence store (block = (seq_off + pos) / 32):
+    uint32_t *mark_bits;         //   block holds a byte outside ACGTacgt or a pushed position with fmmer == rmmer
+    uint32_t *allinv_bits;       //   all 32 bytes of the block are outside ACGTacgt (interior of a long invalid run)
+    uint32_t *n_marks;           // number of marking events (0 => the level-0 list needs no patch)
     uint64_t m1;                 // ~0 (the -1 of the hash's first step) as a parameter: an IMAD.WIDE addend straight from the constant bank
                                  // instead of two MOVs per position
 };
@@ -228,25 +231,39 @@ __device__ __forceinline__ uint32_t make_tile_desc(const L0Params &p, uint32_t t
     return sid;
 }
 
-// cold path of the key loop: a pushed palindrome (not pushed by the reference); the neighbourhood is re-derived by
-// patch_replay_kernel
-__device__ __noinline__ void record_skip(uint32_t *n_skips, uint2 *skips, uint32_t cap, uint32_t seq_id, int pos, uint32_t *bad) {
-    const uint32_t slot = atomicAdd(n_skips, 1u);
-    if (slot < cap) skips[slot] = make_uint2(seq_id, (uint32_t)pos); else *bad = 1;
+// cold path: mark the 32-base block at sequence position blk_pos as disturbed (idempotent; halo blocks are marked by
+// two tiles); the neighbourhood is re-derived by cluster_replay_kernel
+__device__ __noinline__ void mark_block(uint32_t *bits, uint32_t *n_marks, uint64_t seq_off, int32_t blk_pos) {
+    const uint64_t g = (seq_off + (uint64_t)(int64_t)blk_pos) >> 5;
+    atomicOr(&bits[g >> 5], 1u << (g & 31));
+    atomicAdd(n_marks, 1u);
+}
+
+// key positions of block t whose k-byte window holds an invalid byte (i0 = invalid mask of the block, i1 / i2 = of the
+// one / two blocks before it): their keys are not the reference's (stale k-mer) and are taken from the replay
+__device__ __noinline__ uint32_t dirty_mask(uint32_t i0, uint32_t i1, uint32_t i2, uint32_t k) {
+    const unsigned __int128 v = ((unsigned __int128)i0 << 64) | ((unsigned __int128)i1 << 32) | i2;
+    const unsigned __int128 km = (((unsigned __int128)1) << k) - 1;
+    uint32_t d = 0;
+    for (uint32_t i = 0; i < 32; i++) if ((v >> (65 + i - k)) & km) d |= 1u << i;   // bytes [64+i-k+1, 64+i]
+    return d;
 }
 
 // cold path of the fast key loop: some position of this thread's block has equal top words of plane 0 on both strands, so the
-// strand picked from them may be wrong: redo the prefix of those positions exactly and record the palindromes
-__device__ __noinline__ void strand_tie_scan(uint32_t *n_skips, uint2 *skips, uint32_t cap, L0Smem &s, L0Smem::TileDesc &D, int kb, int32_t blk_pos, int32_t L, uint32_t k) {
+// strand picked from them may be wrong: redo the prefix of those positions exactly and mark the block if one is a palindrome
+__device__ __noinline__ void strand_tie_scan(const L0Params &p, L0Smem &s, L0Smem::TileDesc &D, int kb, int32_t blk_pos, int32_t L, uint32_t k, uint32_t dirty) {
+    bool pal = false;
     for (int i = 0; i < 32; i++) {
+        if ((dirty >> i) & 1u) continue;
         const int q = 32 * kb + i, pos = blk_pos + i;
         const KmerRegs r = kmer_at(s, q, k);
         if ((uint32_t)(r.f0 >> (k - 32)) != (uint32_t)(r.r0 >> (k - 32))) continue;
         const bool rev = r.r0 < r.f0;
         const uint64_t h = rev ? (u64hash(r.r0) ^ u64hash(r.r1 ^ HASH_XOR)) : (u64hash(r.f0) ^ u64hash(r.f1 ^ HASH_XOR));
         s.H[pidx(q)] = (uint32_t)(h >> 32) & 0x00FFFFFFu;   // the fast loop's 24-bit prefix
-        if (r.f0 == r.r0 && r.f1 == r.r1 && pos >= (int)k && pos < L) record_skip(n_skips, skips, cap, D.seq_id, pos, &D.bad);
+        pal = pal || (r.f0 == r.r0 && r.f1 == r.r1 && pos >= (int)k && pos < L);
     }
+    if (pal) mark_block(p.mark_bits, p.n_marks, D.seq_off, blk_pos);
 }
 
 // Level-0 minimizers of one tile.  W, K > 0 are compile-time specialisations; 0 = read from params.
@@ -293,7 +310,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         const int32_t blk_pos = keys_start + 32 * (tid - L0_CTX);  // sequence position of this thread's first base
 
         // ---- phase 1: 32 bases -> plane words -------------------------------------------------------------
-        uint32_t f0 = 0, f1 = 0;
+        uint32_t f0 = 0, f1 = 0, inv = 0;
         const bool blk_live = (blk_pos + 32 > 0) && (blk_pos < L);  // block intersects the sequence
         if (blk_live) {
             const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -307,18 +324,21 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             }
             bad_bits &= 0xDFDFDFDFu;                 // lower case is valid
             if (bad_bits || blk_pos < 0 || blk_pos + 32 > L) {
-                // slow exact check restricted to the bytes that belong to the sequence; the first byte outside ACGTacgt
-                // seeds an exact local replay (patch_replay_kernel), like a palindrome does
-                int first_bad = -1;
+                // slow exact check restricted to the bytes that belong to the sequence: a block with a byte outside ACGTacgt
+                // is marked (its neighbourhood is replayed exactly), like a palindrome's
 #pragma unroll 1
                 for (int j = 0; j < 32; j++) {
                     const int pos = blk_pos + j;
-                    if (first_bad < 0 && pos >= 0 && pos < L && !byte_is_acgt((wd[j >> 2] >> (8 * (j & 3))) & 0xFF)) first_bad = pos;
+                    if (pos >= 0 && pos < L && !byte_is_acgt((wd[j >> 2] >> (8 * (j & 3))) & 0xFF)) inv |= 1u << j;
                 }
-                if (first_bad >= 0) record_skip(p.n_skips, p.skips, p.skip_cap, D.seq_id, first_bad, &D.bad);
+                if (inv) {
+                    mark_block(p.mark_bits, p.n_marks, D.seq_off, blk_pos);
+                    if (inv == 0xFFFFFFFFu) { const uint64_t g = (D.seq_off + (uint64_t)(int64_t)blk_pos) >> 5; atomicOr(&p.allinv_bits[g >> 5], 1u << (g & 31)); }
+                }
             }
         }
         s.F0[tid] = f0; s.F1[tid] = f1;
+        s.bext[tid + 2] = inv;   // invalid-byte mask of block tid, read by the two following blocks below; bext is rewritten in phase 3
         if (tid < 8) { s.F0[L0_NT + tid] = 0; s.F1[L0_NT + tid] = 0; }
         __syncthreads();   // planes visible; also publishes thread 0's descriptor of the next tile
         if (has_next) {    // the loads fly while the key loop runs
@@ -332,7 +352,12 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
 
         // ---- phase 2: keys for blocks CTX.. ------------------------------------------------------------------
         const int kb = tid - L0_CTX;  // key block index (negative for the two context threads)
+        uint32_t dirty = 0;           // key positions of this block whose k-byte window holds an invalid byte
         if (tid >= L0_CTX && blk_live) {
+            {
+                const uint32_t i1 = s.bext[tid + 1], i2 = s.bext[tid];
+                if (inv | i1 | i2) dirty = dirty_mask(inv, i1, i2, k);
+            }
             const uint32_t a2 = s.F0[tid - 2], a1 = s.F0[tid - 1], a0 = f0;
             const uint32_t b2 = s.F1[tid - 2], b1 = s.F1[tid - 1], b0 = f1;
             // r-planes: Q = G >> (32*(tid-2) + 65 - k), so that rmmer(i) = (Q >> i) & kmask
@@ -383,7 +408,10 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                     // orders consistently with x, and prefix ties between candidates are resolved exactly in phase 5
                     s.H[base + i] = (uhi ^ vhi) & 0x00FFFFFFu;
                 }
-                if (!no_tie) strand_tie_scan(p.n_skips, p.skips, p.skip_cap, s, D, kb, blk_pos, L, k);
+                if (!no_tie) strand_tie_scan(p, s, D, kb, blk_pos, L, k, dirty);
+                if (dirty) {   // never candidates; the maximal prefix keeps them from shadowing clean keys
+                    for (int i = 0; i < 32; i++) if ((dirty >> i) & 1u) s.H[base + i] = 0x00FFFFFFu;
+                }
             } else {
     #pragma unroll U
                 for (int i = 0; i < 32; i++) {
@@ -394,7 +422,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                     const uint32_t r1lo = fsr(q10, q11, i) & mlo, r1hi = fsr(q11, q12, i) & mhi;
                     if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
                         const int pos = blk_pos + i;
-                        if (f0hi == r0hi && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L) record_skip(p.n_skips, p.skips, p.skip_cap, D.seq_id, pos, &D.bad);
+                        if (f0hi == r0hi && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L && !((dirty >> i) & 1u)) mark_block(p.mark_bits, p.n_marks, D.seq_off, blk_pos);
                     }
                     // strand: reverse iff rmmer.0 < fmmer.0 (shmmrutils.rs:486, plane 0 only); one 64-bit compare, four selects
                     uint32_t ulo, uhi, vlo, vhi;
@@ -407,7 +435,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                     u64hash_dev32(ulo, uhi);
                     u64hash_dev32(vlo, vhi);
                     // MM128.x high word = hash bits 24..55
-                    s.H[base + i] = __funnelshift_r(ulo ^ vlo, uhi ^ vhi, 24);
+                    s.H[base + i] = ((dirty >> i) & 1u) ? 0xFFFFFFFFu : __funnelshift_r(ulo ^ vlo, uhi ^ vhi, 24);
                 }
             }
         }
@@ -488,11 +516,11 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                         if (M == s.H[base + o]) cand |= 1u << o;
                     }
                 }
-                cand &= vmask;
+                cand &= vmask & ~dirty;
             } else {
                 // small windows: direct evaluation (w <= 32); w is uniform, so no barrier mismatch with the branch above
                 for (int o = 0; o < 32; o++) {
-                    if (!((vmask >> o) & 1u)) continue;
+                    if (!(((vmask & ~dirty) >> o) & 1u)) continue;
                     const int q = 32 * kb + o;
                     const uint32_t hq = s.H[pidx(q)];
                     // l / r = run of neighbours with H >= hq inside the valid position range (and inside the tile's keys:
@@ -711,219 +739,6 @@ __global__ void replay_l0_kernel(const ReplayParams p) {
         mdist++;
     }
     if (!MODE) p.count[sid] = (uint32_t)n_out;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Palindrome patches.  A pushed position with fmmer == rmmer is skipped by the reference (not pushed, mdist not
-// advanced), which breaks the local rule in its neighbourhood and can leave the machine in an anomalous state
-// (duplicate emissions, stuck mdist) until its next emission.  One thread per affected sequence replays the exact
-// machine around every cluster of such positions:
-//   start S = p* - 2w (a fresh machine is in sync with the true one after w pushes without a skip; S is pulled back so
-//   that those w pushes lie before L-w+k, or set to k = the true start when the cluster is near the sequence start);
-//   emissions at times < T0 = S + w are discarded, q0 = position of the last of them;
-//   the replay ends at the first emission at a time t with  p_last + 2w <= t < L-w+k - w  and no further skip within w
-//   (from there the machine is in its normal regime and the windows of later positions contain no skip): q1 = the
-//   position emitted last; otherwise it runs to the end of the sequence (q1 = UINT32_MAX).
-// The patch replaces the tile kernel's level-0 entries with q0 < pos <= q1.
-struct PatchParams {
-    const uint8_t *seq; const uint64_t *off; const uint32_t *len;
-    const uint32_t *aff_seq;      // [n_aff] sequence ordinals with skips
-    const uint32_t *skip_off;     // [n_aff+1] offsets into skip_pos
-    const uint32_t *skip_pos;     // sorted positions per affected sequence
-    uint32_t n_aff;
-    uint32_t w, k;
-    // per-patch outputs, slot = skip_off[a] + j (at most one patch per skip)
-    uint32_t *n_patches;          // [n_aff]
-    uint32_t *q0, *q1, *n_add;    // q0 = UINT32_MAX encodes "from the start" (-1)
-    const uint64_t *entry_off;    // [n_slots] (mode 1) where the patch's entries go
-    pgr_mm128 *entries;
-};
-
-template <int MODE>
-__global__ void patch_replay_kernel(const PatchParams p) {
-    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= p.n_aff) return;
-    const uint32_t sid = p.aff_seq[a];
-    const uint8_t *sq = p.seq + p.off[sid];
-    const int64_t L = p.len[sid];
-    const int64_t w = p.w, k = p.k;
-    const uint64_t mask = ~0ull >> (64 - k);
-    const uint32_t shift = (uint32_t)k - 1;
-    const int64_t E = L - w + k;                      // rule (2) active for pos < E
-    const uint32_t *sk = p.skip_pos + p.skip_off[a];
-    const uint32_t ns = p.skip_off[a + 1] - p.skip_off[a];
-    const uint32_t slot0 = p.skip_off[a];
-    uint32_t n_patch = 0, si = 0;
-    uint64_t rx[128]; uint32_t ry[128];
-    while (si < ns) {
-        const int64_t pstar = sk[si];
-        int64_t S = pstar - 2 * w;
-        if (S + w > E - 1) S = E - 1 - w;
-        bool from_start = false;
-        if (S < k + w + 1) { S = k; from_start = true; }
-        const int64_t T0 = from_start ? k : S + w;
-        // registers at S: the last k VALID bases before S (shmmrutils.rs:461-476 updates them on valid bases only);
-        // from the true start they begin at zero.  `since_bad` counts the bytes since the last one outside ACGTacgt:
-        // the tile kernel's key at p is the true key iff the k bytes ending at p are all ACGTacgt.
-        uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;
-        int64_t r_begin = 0;
-        if (!from_start) {
-            int64_t b = S; int64_t got = 0;
-            while (b > 0 && got < k) { b--; if (base_code(sq[b]) < 4) got++; }
-            r_begin = b;
-        }
-        int64_t since_bad = 1 << 30;
-        for (int64_t q = r_begin; q < S; q++) {
-            const uint32_t ch = sq[q];
-            const uint32_t c = base_code(ch);
-            if (c < 4) {
-                f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
-                const uint64_t rc = 3 ^ c;
-                r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
-            }
-            since_bad = byte_is_acgt(ch) ? since_bad + 1 : 0;
-        }
-        for (int64_t i = 0; i < w; i++) { rx[i] = ~0ull; ry[i] = ~0u; }
-        uint32_t r_start = 0, r_end = 0, r_len = 0;
-        uint64_t min_x = ~0ull, mdist = 0;
-        int64_t p_last = pstar;
-        uint32_t q0 = 0xFFFFFFFFu, q1 = 0xFFFFFFFFu, n_add = 0;
-        uint32_t last_emit = 0xFFFFFFFFu;
-        bool done = false;
-        pgr_mm128 *dst = MODE ? p.entries + p.entry_off[slot0 + n_patch] : nullptr;
-        for (int64_t pos = S; pos < L && !done; pos++) {
-            const uint32_t ch = sq[pos];
-            const uint32_t c = base_code(ch);
-            if (c < 4) {
-                f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
-                const uint64_t rc = 3 ^ c;
-                r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
-            }
-            since_bad = byte_is_acgt(ch) ? since_bad + 1 : 0;
-            if (since_bad < k) p_last = pos;              // the tile kernel's key here is not the reference's
-            if (f0 == r0 && f1 == r1) { if (pos >= k) p_last = pos; continue; }
-            if (pos < k) continue;
-            const bool rev = r0 < f0;
-            const uint64_t h = rev ? (u64hash(r0) ^ u64hash(r1 ^ HASH_XOR)) : (u64hash(f0) ^ u64hash(f1 ^ HASH_XOR));
-            const uint64_t mx = (h << 8) | (uint64_t)k;
-            const uint32_t my = ((uint32_t)pos << 1) | (rev ? 1u : 0u);
-            rx[r_end] = mx; ry[r_end] = my;
-            r_end = (r_end + 1) % (uint32_t)w;
-            if (r_len < (uint32_t)w) r_len++; else r_start = (r_start + 1) % (uint32_t)w;
-            bool emitted = false;
-            if (mdist == (uint64_t)(w - 1)) {
-                uint64_t mn = ~0ull;
-                for (uint32_t i = 0; i < r_len; i++) if (rx[i] < mn) mn = rx[i];
-                uint32_t last_y = 0;
-                for (uint32_t i = 0; i < (uint32_t)w; i++) {
-                    const uint32_t sl = (r_start + i) % (uint32_t)w;
-                    if (rx[sl] == mn) {
-                        if (pos >= T0) {
-                            if (MODE) { pgr_mm128 mm; mm.x = rx[sl]; mm.y = ((uint64_t)sid << 32) | ry[sl]; dst[n_add] = mm; }
-                            n_add++;
-                        } else {
-                            q0 = ry[sl] >> 1;
-                        }
-                        last_y = ry[sl];
-                        last_emit = ry[sl] >> 1;
-                        emitted = true;
-                    }
-                }
-                min_x = mn;
-                mdist = (uint64_t)pos - (uint64_t)(last_y >> 1);
-            } else if (mx <= min_x && pos >= w + k && pos < E && pos < L) {
-                if (pos >= T0) {
-                    if (MODE) { pgr_mm128 mm; mm.x = mx; mm.y = ((uint64_t)sid << 32) | my; dst[n_add] = mm; }
-                    n_add++;
-                } else {
-                    q0 = (uint32_t)pos;
-                }
-                last_emit = (uint32_t)pos;
-                emitted = true;
-                min_x = mx;
-                mdist = 0;
-            } else {
-                mdist++;
-            }
-            if (emitted && pos >= T0) {
-                // every skip up to pos has been seen by the machine; find the next one in the list
-                while (si < ns && (int64_t)sk[si] <= pos) si++;
-                bool next_far = (si >= ns) || ((int64_t)sk[si] > pos + w);
-                if (next_far && pos >= p_last + 2 * w && pos < E - w) {
-                    // invalid bytes are recorded once per 32-base block: make sure none hides just ahead
-                    const int64_t ahead = min(L, pos + w + 33);
-                    for (int64_t q = pos + 1; q < ahead && next_far; q++) next_far = byte_is_acgt(sq[q]);
-                    if (next_far) { q1 = last_emit; done = true; }
-                }
-            }
-        }
-        if (!done) si = ns;  // ran to the end of the sequence: everything after q0 is replaced
-        if (from_start) q0 = 0xFFFFFFFFu;
-        p.q0[slot0 + n_patch] = q0; p.q1[slot0 + n_patch] = q1; p.n_add[slot0 + n_patch] = n_add;
-        n_patch++;
-    }
-    p.n_patches[a] = n_patch;
-}
-
-// splice the patches into the flat level-0 list.  Patches are sorted by (sequence, q0); per patch: lb = number of the
-// sequence's entries with pos <= q0 (0 for "from the start"), ub = number with pos <= q1.
-struct SpliceParams {
-    const pgr_mm128 *flat0; const uint64_t *off0;      // before
-    pgr_mm128 *flat1; const uint64_t *off1;            // after
-    uint32_t n_seq;
-    const int32_t *seq_first_patch;                    // [n_seq] first patch index of the sequence or -1
-    const uint32_t *seq_n_patch;                       // [n_seq]
-    const uint32_t *pq0, *pq1;                         // per patch
-    uint32_t *plb, *pub;                               // per patch (bounds kernel output)
-    const int64_t *pdelta;                             // per patch: cumulative (added - removed) of the sequence's EARLIER patches
-    const uint64_t *pdst;                              // per patch: where its entries start in flat1
-    const uint32_t *pseq; const uint32_t *pn_add; const uint64_t *pentry_off;
-    const pgr_mm128 *entries;
-    uint32_t n_patches;
-    uint64_t n0;
-};
-
-__device__ __forceinline__ uint32_t mm_pos32(const pgr_mm128 &m) { return (uint32_t)(m.y & 0xFFFFFFFFu) >> 1; }
-
-__global__ void splice_bounds_kernel(const SpliceParams p) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p.n_patches) return;
-    const uint32_t s = p.pseq[j];
-    const uint64_t b = p.off0[s], e = p.off0[s + 1];
-    auto count_le = [&](uint32_t q) -> uint32_t {   // entries of s with pos <= q
-        uint64_t lo = b, hi = e;
-        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (mm_pos32(p.flat0[mid]) <= q) lo = mid + 1; else hi = mid; }
-        return (uint32_t)(lo - b);
-    };
-    p.plb[j] = (p.pq0[j] == 0xFFFFFFFFu) ? 0u : count_le(p.pq0[j]);
-    p.pub[j] = (p.pq1[j] == 0xFFFFFFFFu) ? (uint32_t)(e - b) : count_le(p.pq1[j]);
-}
-
-__global__ void splice_copy_kernel(const SpliceParams p) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n0) return;
-    const pgr_mm128 mm = p.flat0[i];
-    const uint32_t s = (uint32_t)(mm.y >> 32);
-    const uint64_t rel = i - p.off0[s];
-    const int32_t fp = p.seq_first_patch[s];
-    if (fp < 0) { p.flat1[p.off1[s] + rel] = mm; return; }
-    // patches of s are sorted; find the last one whose lb <= rel
-    const uint32_t np = p.seq_n_patch[s];
-    int64_t delta = 0;
-    for (uint32_t j = 0; j < np; j++) {
-        const uint32_t lb = p.plb[fp + j], ub = p.pub[fp + j];
-        if (rel < lb) break;
-        if (rel < ub) return;                          // inside (q0, q1]: replaced by the patch
-        delta = p.pdelta[fp + j] + (int64_t)p.pn_add[fp + j] - (int64_t)(ub - lb);
-    }
-    p.flat1[p.off1[s] + (uint64_t)((int64_t)rel + delta)] = mm;
-}
-
-__global__ void splice_patch_kernel(const SpliceParams p, uint64_t n_entries_total, const uint32_t *entry_patch) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_entries_total) return;
-    const uint32_t j = entry_patch[i];
-    p.flat1[p.pdst[j] + (i - p.pentry_off[j])] = p.entries[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------

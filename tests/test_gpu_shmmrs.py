@@ -205,3 +205,54 @@ def test_lowercase_is_fast_path():
     assert ctx.counters()[2] == 0
     assert np.array_equal(got, orc.sequence_to_shmmrs(0, s, orc.mkspec()))
     ctx.close()
+
+
+def test_long_invalid_runs_are_crossed_in_closed_form():
+    """Mb-scale gaps: the replay thread jumps over the all-invalid blocks (fill segments) instead of walking them, and a run
+    entered with fmmer == rmmer (leading N: all-zero registers) pushes nothing; every alignment of the run ends to the
+    32-base blocks, runs closer than k / w / the cluster gap to each other, runs at both sequence ends"""
+    rng = np.random.default_rng(211)
+    r = lambda L, a=b"ACGT": rand_seq(rng, L, a)
+    seqs = [
+        r(40000) + b"N" * 300_000 + r(40000),                           # one gap
+        b"N" * 100_000 + r(30000) + b"N" * 70_001,                      # telomere-style gaps at both ends
+        r(5003) + b"N" * 9_999 + r(17) + b"N" * 20_000 + r(70) + b"N" * 12_345 + r(300) + b"N" * 5_000 + r(8000),   # gaps closer than k, w, cluster gap
+        r(20000, b"acgt") + b"n" * 50_000 + r(20000, b"ACGTacgt"),      # soft-masked flanks, lower-case gap
+        b"AT" * 40 + b"N" * 40_000 + b"AT" * 40 + r(6000),              # gap entered with palindromic registers ((AT)n, k even)
+        r(10000) + b"N" * 32 + r(10000) + b"N" * 64 + r(10000) + b"N" * 31 + r(10000) + b"N" * 33 + r(9999) + b"N" * 96,
+        b"".join(r(int(rng.integers(50, 3000))) + b"N" * int(rng.integers(1, 4000)) for _ in range(60)),          # scaffold-like
+        r(100_000),                                                     # clean
+    ]
+    for i in range(32):     # every alignment of run start and length modulo 32
+        seqs.append(r(3000 + i) + b"N" * (2000 + 7 * i) + r(3000))
+    for w, k, r_, ms in [(80, 56, 4, 64), (48, 56, 4, 12), (24, 24, 12, 24), (128, 31, 3, 7), (5, 7, 1, 0), (1, 9, 2, 0)]:
+        assert_batch_equal(seqs, pg.ShmmrSpec(w, k, r_, ms))
+    assert_batch_equal(seqs[:8], pg.ShmmrSpec(80, 56, 4, 64), padding=True)
+    ctx = pg.Ctx(0)
+    ctx.upload(seqs)
+    ctx.shmmrs(pg.ShmmrSpec())
+    c = ctx.counters()
+    assert c[2] == 0          # no whole-sequence replay
+    assert c[5] >= 8          # fill segments: the long runs were jumped over
+    assert c[6] >= 500_000    # level-0 entries supplied by patches (the reference emits every position of a saturated run)
+    ctx.close()
+
+
+def test_assembly_like_decoration():
+    """bench_synth.decorate_assembly_like (N gaps, soft masking, microsatellites, inverted repeats) on a few Mb"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench_synth as S
+    rng = np.random.default_rng(5)
+    seqs = []
+    for i, L in enumerate((3_000_000, 1_000_003, 400_000)):
+        a = S.rand_seq(rng, L).copy()
+        S.decorate_assembly_like(a, 100 + i)
+        seqs.append(a.tobytes())
+    for spec in (pg.ShmmrSpec(80, 56, 4, 64), pg.ShmmrSpec(48, 56, 4, 12)):
+        assert_batch_equal(seqs, spec)
+    ctx = pg.Ctx(0)
+    ctx.upload(seqs)
+    ctx.shmmrs(pg.ShmmrSpec())
+    assert ctx.counters()[2] == 0
+    ctx.close()
