@@ -132,7 +132,7 @@ def decorate_assembly_like(seq, seed, n_frac=0.02, lower_frac=0.3, repeat_every=
     # gaps
     covered = 0
     while covered < n_frac * L:
-        ln = int(min(L // 4, 10 ** rng.uniform(4.0, 6.7)))
+        ln = int(min(max(10_000, 1.5 * n_frac * L), 10 ** rng.uniform(4.0, 6.7)))
         a = int(rng.integers(0, max(1, L - ln)))
         seq[a:a + ln] = ord("N")
         covered += ln

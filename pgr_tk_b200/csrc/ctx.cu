@@ -457,9 +457,9 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     cudaStream_t st = ctx->stream;
     const size_t n = ctx->rn;
     const uint32_t gap = (6 * spec.w + spec.k + 64 + 31) / 32 + 1;
-    DevBuf d_sorted, d_clusters, d_q, d_nadd, d_nfill, d_eoff, d_foff, d_fills, d_entries, d_meta;
+    DevBuf d_sorted, d_clusters, d_q, d_nadd, d_nfill, d_eoff, d_entries, d_meta, d_slab, d_list;
     auto cleanup = [&]() { d_sorted.release(); d_clusters.release(); d_q.release(); d_nadd.release(); d_nfill.release(); d_eoff.release();
-                           d_foff.release(); d_fills.release(); d_entries.release(); d_meta.release(); };
+                           d_entries.release(); d_meta.release(); d_slab.release(); d_list.release(); };
     int rc = PGR_OK;
 #define PATCH_TRY(x) do { rc = (x); if (rc != PGR_OK) { cleanup(); return rc; } } while (0)
 #define PATCH_CUDA(x) do { if ((x) != cudaSuccess) { set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); cleanup(); return PGR_E_CUDA; } } while (0)
@@ -477,81 +477,134 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     PATCH_CUDA(cudaMemcpyAsync(ds_off, s_off.data(), n * 8, cudaMemcpyHostToDevice, st));
     PATCH_CUDA(cudaMemcpyAsync(ds_len, s_len.data(), n * 4, cudaMemcpyHostToDevice, st));
     PATCH_CUDA(cudaMemcpyAsync(ds_sid, ord.data(), n * 4, cudaMemcpyHostToDevice, st));
-    PATCH_TRY(d_clusters.ensure((size_t)n_marks * sizeof(Cluster) + 64));   // every cluster holds at least one marking event
-    uint32_t *d_ncl = (uint32_t *)((uint8_t *)d_clusters.p + (size_t)n_marks * sizeof(Cluster));
-    PATCH_CUDA(cudaMemsetAsync(d_ncl, 0, 4, st));
+    bool in_order = true;                              // store order == sequence order: the finder's output needs no sort
+    for (size_t i = 0; i < n; i++) in_order = in_order && ord[i] == i;
+    const uint32_t cf_grid = (uint32_t)ceil_div<uint64_t>(word_hi - word_lo, CF_NT);
+    PATCH_TRY(ctx->block_sum.ensure((size_t)cf_grid * sizeof(uint32_t)));
+    PATCH_TRY(ctx->block_prefix.ensure(((size_t)cf_grid + 1) * sizeof(uint64_t)));
     ClusterFindParams cf;
     cf.bits = ctx->mark_bits.as<uint32_t>(); cf.word_lo = word_lo; cf.word_hi = word_hi;
     cf.s_off = ds_off; cf.s_len = ds_len; cf.s_sid = ds_sid; cf.n_seq = (uint32_t)n; cf.gap = gap;
-    cf.out = d_clusters.as<Cluster>(); cf.cap = n_marks; cf.n_out = d_ncl;
-    cluster_find_kernel<<<(uint32_t)ceil_div<uint64_t>(word_hi - word_lo, 256), 256, 0, st>>>(cf);
+    cf.out = nullptr; cf.cap = 0; cf.n_out = nullptr;
+    cluster_find_kernel<0><<<cf_grid, CF_NT, 0, st>>>(cf, ctx->block_sum.as<uint32_t>(), nullptr);
+    block_scan_kernel<<<1, 1024, 0, st>>>(ctx->block_sum.as<uint32_t>(), ctx->block_prefix.as<uint64_t>(), cf_grid);
     PATCH_CUDA(cudaGetLastError());
-    uint32_t n_cl = 0;
-    PATCH_CUDA(cudaMemcpyAsync(&n_cl, d_ncl, 4, cudaMemcpyDeviceToHost, st));
+    uint64_t n_cl64 = 0;
+    PATCH_CUDA(cudaMemcpyAsync(&n_cl64, ctx->block_prefix.as<uint64_t>() + cf_grid, 8, cudaMemcpyDeviceToHost, st));
     PATCH_CUDA(cudaStreamSynchronize(st));
-    if (n_cl > n_marks) { set_error("cluster list overflow"); cleanup(); return PGR_E_CUDA; }
+    if (n_cl64 > 0xFFFFFFF0ull) { set_error("too many clusters"); cleanup(); return PGR_E_LIMIT; }
+    const uint32_t n_cl = (uint32_t)n_cl64;
+    PATCH_TRY(d_clusters.ensure((size_t)std::max<uint32_t>(1, n_cl) * sizeof(Cluster)));
+    cf.out = d_clusters.as<Cluster>(); cf.cap = n_cl;
+    cluster_find_kernel<1><<<cf_grid, CF_NT, 0, st>>>(cf, nullptr, ctx->block_prefix.as<uint64_t>());
+    PATCH_CUDA(cudaGetLastError());
+    trace_mark("patches: clusters found");
     std::vector<Cluster> cl(n_cl);
     PATCH_CUDA(cudaMemcpyAsync(cl.data(), d_clusters.p, (size_t)n_cl * sizeof(Cluster), cudaMemcpyDeviceToHost, st));
     PATCH_CUDA(cudaStreamSynchronize(st));
-    // whole-sequence replays (flagged) need no patch; the rest sorted by (sequence, position)
-    cl.erase(std::remove_if(cl.begin(), cl.end(), [&](const Cluster &c) { return flagged[c.sid] != 0; }), cl.end());
-    std::sort(cl.begin(), cl.end(), [](const Cluster &a, const Cluster &b) { return a.sid != b.sid ? a.sid < b.sid : a.pos < b.pos; });
+    if (!in_order) std::sort(cl.begin(), cl.end(), [](const Cluster &a, const Cluster &b) { return a.sid != b.sid ? a.sid < b.sid : a.pos < b.pos; });
+    // whole-sequence replays (flagged) need no patch; the rest in (sequence, position) order
+    bool any_flagged = false;
+    for (size_t i = 0; i < n; i++) any_flagged = any_flagged || flagged[i] != 0;
+    if (any_flagged) cl.erase(std::remove_if(cl.begin(), cl.end(), [&](const Cluster &c) { return flagged[c.sid] != 0; }), cl.end());
     size_t P = cl.size();
     if (P == 0) { ctx->timer.end(slot_t, st); cleanup(); return PGR_OK; }
-    PATCH_CUDA(cudaMemcpyAsync(d_clusters.p, cl.data(), P * sizeof(Cluster), cudaMemcpyHostToDevice, st));
-    // 2. count pass
-    PATCH_TRY(d_q.ensure(P * 12)); PATCH_TRY(d_nadd.ensure(P * 8)); PATCH_TRY(d_nfill.ensure(P * 4));
-    PATCH_TRY(d_eoff.ensure(P * 8)); PATCH_TRY(d_foff.ensure(P * 4));
+    if (any_flagged || !in_order) PATCH_CUDA(cudaMemcpyAsync(d_clusters.p, cl.data(), P * sizeof(Cluster), cudaMemcpyHostToDevice, st));
+    // 2. replay.  Pass A: one thread per cluster, entries into per-cluster slabs.  The few clusters that run out of steps or
+    //    of slab (stuck machines waiting for a small key, Mb-scale gaps with many entries) are redone by one warp each:
+    //    count pass, then write pass at exact offsets.
+    PATCH_TRY(d_q.ensure(P * 12)); PATCH_TRY(d_nadd.ensure(P * 8)); PATCH_TRY(d_nfill.ensure(P * 4)); PATCH_TRY(d_eoff.ensure(P * 8));
+    if ((rc = d_slab.ensure(P * (size_t)RC_SLAB * sizeof(pgr_mm128))) != PGR_OK) { cleanup(); return rc; }
     ReplayClusterParams rp;
     rp.seq = ctx->d_seq; rp.off = ctx->d_off.as<uint64_t>() + ctx->r0; rp.len = ctx->d_len.as<uint32_t>() + ctx->r0;
     rp.mark_bits = ctx->mark_bits.as<uint32_t>(); rp.allinv_bits = ctx->allinv_bits.as<uint32_t>();
-    rp.clusters = d_clusters.as<Cluster>(); rp.n_clusters = (uint32_t)P; rp.w = spec.w; rp.k = spec.k; rp.gap = gap;
+    rp.clusters = d_clusters.as<Cluster>(); rp.list = nullptr; rp.n_list = (uint32_t)P; rp.w = spec.w; rp.k = spec.k; rp.gap = gap;
     rp.q0 = d_q.as<uint32_t>(); rp.q1 = rp.q0 + P; rp.t_stop = rp.q0 + 2 * P; rp.n_add = d_nadd.as<uint64_t>(); rp.n_fill = d_nfill.as<uint32_t>();
-    rp.entry_off = d_eoff.as<uint64_t>(); rp.fill_off = d_foff.as<uint32_t>(); rp.entries = nullptr; rp.fills = nullptr;
-    cluster_replay_kernel<0><<<ceil_div<uint32_t>((uint32_t)P, 32), 32, 0, st>>>(rp);
-    PATCH_CUDA(cudaGetLastError());
+    rp.entry_off = d_eoff.as<uint64_t>(); rp.entries = nullptr; rp.slab = d_slab.as<pgr_mm128>();
+    DevBuf d_cyc;
+    const bool dbg_cycles = getenv("PGR_B200_DEBUG_PATCHES") != nullptr;
+    if (dbg_cycles && (rc = d_cyc.ensure(P * 8)) != PGR_OK) { cleanup(); return rc; }
+    rp.cycles = dbg_cycles ? d_cyc.as<unsigned long long>() : nullptr;
+    cluster_replay_kernel<0, 0><<<ceil_div<uint32_t>((uint32_t)P, RC_NT), RC_NT, 0, st>>>(rp);
+    if (cudaGetLastError() != cudaSuccess) { set_error("cluster_replay_kernel launch failed"); cleanup(); d_cyc.release(); return PGR_E_CUDA; }
     std::vector<uint32_t> h_q(3 * P), h_nfill(P);
     std::vector<uint64_t> h_nadd(P);
-    PATCH_CUDA(cudaMemcpyAsync(h_q.data(), d_q.p, P * 12, cudaMemcpyDeviceToHost, st));
-    PATCH_CUDA(cudaMemcpyAsync(h_nadd.data(), d_nadd.p, P * 8, cudaMemcpyDeviceToHost, st));
-    PATCH_CUDA(cudaMemcpyAsync(h_nfill.data(), d_nfill.p, P * 4, cudaMemcpyDeviceToHost, st));
-    PATCH_CUDA(cudaStreamSynchronize(st));
-    if (getenv("PGR_B200_DEBUG_PATCHES"))
-        for (size_t j = 0; j < P; j++) fprintf(stderr, "[patch] sid %u pos %u q0 %u q1 %u t_stop %u n_add %llu n_fill %u\n", cl[j].sid, cl[j].pos, h_q[j], h_q[P + j], h_q[2 * P + j], (unsigned long long)h_nadd[j], h_nfill[j]);
-    {   // a replay that ran past the start of later clusters (stuck machine, or to the end of the sequence) subsumes them:
-        // their own replays assumed a machine in its normal regime and are dropped
-        size_t o = 0;
+    auto fetch = [&]() -> bool {
+        return cudaMemcpyAsync(h_q.data(), d_q.p, P * 12, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+               cudaMemcpyAsync(h_nadd.data(), d_nadd.p, P * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+               cudaMemcpyAsync(h_nfill.data(), d_nfill.p, P * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+               cudaStreamSynchronize(st) == cudaSuccess;
+    };
+    if (!fetch()) { set_error("D2H of the patch table failed"); cleanup(); d_cyc.release(); return PGR_E_CUDA; }
+    trace_mark("patches: pass A (thread per cluster)");
+    std::vector<uint32_t> heavy;
+    for (size_t j = 0; j < P; j++) if (h_q[2 * P + j] == RC_HEAVY) heavy.push_back((uint32_t)j);
+    std::vector<uint8_t> is_heavy(P, 0);
+    for (uint32_t j : heavy) is_heavy[j] = 1;
+    if (!heavy.empty()) {
+        if ((rc = d_list.ensure(heavy.size() * 4)) != PGR_OK) { cleanup(); d_cyc.release(); return rc; }
+        cudaMemcpyAsync(d_list.p, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice, st);
+        rp.list = d_list.as<uint32_t>(); rp.n_list = (uint32_t)heavy.size();
+        cluster_replay_kernel<0, 1><<<ceil_div<uint32_t>(rp.n_list, RC_NT / 32), RC_NT, 0, st>>>(rp);
+        if (cudaGetLastError() != cudaSuccess || !fetch()) { set_error("heavy cluster replay failed"); cleanup(); d_cyc.release(); return PGR_E_CUDA; }
+        trace_mark("patches: heavy clusters, count pass");
+    }
+    ctx->counters[3] = heavy.size();
+    if (dbg_cycles) {
+        std::vector<unsigned long long> cyc(P);
+        cudaMemcpy(cyc.data(), d_cyc.p, P * 8, cudaMemcpyDeviceToHost);
+        std::vector<size_t> ix(P);
+        for (size_t j = 0; j < P; j++) ix[j] = j;
+        std::sort(ix.begin(), ix.end(), [&](size_t a, size_t b) { return cyc[a] > cyc[b]; });
+        for (size_t t = 0; t < std::min<size_t>(12, P); t++) {
+            const size_t j = ix[t];
+            fprintf(stderr, "[slow patch] %.3f ms sid %u len %u pos %u q0 %u q1 %u t_stop %u n_add %llu n_fill %u heavy %d\n", cyc[j] / 1.9e6, cl[j].sid,
+                    ctx->h_len[ctx->r0 + cl[j].sid], cl[j].pos, h_q[j], h_q[P + j], h_q[2 * P + j], (unsigned long long)h_nadd[j], h_nfill[j], (int)is_heavy[j]);
+        }
+        if (atoi(getenv("PGR_B200_DEBUG_PATCHES")) > 1)
+            for (size_t j = 0; j < P; j++) fprintf(stderr, "[patch] sid %u pos %u q0 %u q1 %u t_stop %u n_add %llu n_fill %u\n", cl[j].sid, cl[j].pos, h_q[j], h_q[P + j], h_q[2 * P + j], (unsigned long long)h_nadd[j], h_nfill[j]);
+    }
+    d_cyc.release();
+    // a replay that ran past the start of later clusters (stuck machine, or to the end of the sequence) subsumes them: their own
+    // replays assumed a machine in its normal regime and are dropped
+    std::vector<uint32_t> keep;       // indices into the cluster table of pass A
+    {
         uint32_t cur_sid = 0xFFFFFFFFu, reach = 0;   // stop position of the last kept patch of cur_sid
-        std::vector<uint32_t> kq0, kq1;
         for (size_t j = 0; j < P; j++) {
             if (cl[j].sid == cur_sid && (reach == 0xFFFFFFFFu || cl[j].pos <= reach)) continue;
             cur_sid = cl[j].sid; reach = h_q[2 * P + j];
-            cl[o] = cl[j]; kq0.push_back(h_q[j]); kq1.push_back(h_q[P + j]); h_nadd[o] = h_nadd[j]; h_nfill[o] = h_nfill[j];
-            o++;
+            keep.push_back((uint32_t)j);
         }
-        if (o != P) {
-            ctx->counters[7] += P - o;
-            P = o;
-            cl.resize(P); h_nadd.resize(P); h_nfill.resize(P);
-            PATCH_CUDA(cudaMemcpyAsync(d_clusters.p, cl.data(), P * sizeof(Cluster), cudaMemcpyHostToDevice, st));
-            rp.n_clusters = (uint32_t)P; rp.q1 = rp.q0 + P; rp.t_stop = rp.q0 + 2 * P;
+        ctx->counters[7] += P - keep.size();
+    }
+    const size_t P0 = P;              // size of the pass-A table (slab index space)
+    // entries of the kept heavy clusters: exact offsets, write pass
+    uint64_t n_entries = 0, n_fills = 0, n_heavy_entries = 0;
+    std::vector<uint64_t> eoff(P0, 0);
+    std::vector<uint32_t> heavy_keep;
+    for (uint32_t j : keep) { n_entries += h_nadd[j]; n_fills += h_nfill[j]; if (is_heavy[j]) { eoff[j] = n_heavy_entries; n_heavy_entries += h_nadd[j]; heavy_keep.push_back(j); } }
+    if ((rc = d_entries.ensure(std::max<uint64_t>(1, n_heavy_entries) * sizeof(pgr_mm128))) != PGR_OK) { cleanup(); return rc; }
+    if (!heavy_keep.empty()) {
+        cudaMemcpyAsync(d_eoff.p, eoff.data(), P0 * 8, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_list.p, heavy_keep.data(), heavy_keep.size() * 4, cudaMemcpyHostToDevice, st);
+        rp.list = d_list.as<uint32_t>(); rp.n_list = (uint32_t)heavy_keep.size(); rp.entries = d_entries.as<pgr_mm128>(); rp.cycles = nullptr;
+        cluster_replay_kernel<1, 1><<<ceil_div<uint32_t>(rp.n_list, RC_NT / 32), RC_NT, 0, st>>>(rp);
+        if (cudaGetLastError() != cudaSuccess) { set_error("heavy cluster write pass failed"); cleanup(); return PGR_E_CUDA; }
+    }
+    // compact the per-patch tables to the kept patches
+    std::vector<const pgr_mm128 *> psrc;
+    {
+        std::vector<Cluster> kcl; std::vector<uint32_t> kq0, kq1, knf; std::vector<uint64_t> kna;
+        for (uint32_t j : keep) {
+            kcl.push_back(cl[j]); kq0.push_back(h_q[j]); kq1.push_back(h_q[P0 + j]); kna.push_back(h_nadd[j]); knf.push_back(h_nfill[j]);
+            psrc.push_back(is_heavy[j] ? d_entries.as<pgr_mm128>() + eoff[j] : d_slab.as<pgr_mm128>() + (size_t)j * RC_SLAB);
         }
+        cl.swap(kcl); h_nadd.swap(kna); h_nfill.swap(knf);
         h_q.assign(kq0.begin(), kq0.end());
         h_q.insert(h_q.end(), kq1.begin(), kq1.end());
+        P = keep.size();
     }
-    std::vector<uint64_t> pentry_off(P);
-    std::vector<uint32_t> pfill_off(P);
-    uint64_t n_entries = 0, n_fills = 0;
-    for (size_t j = 0; j < P; j++) { pentry_off[j] = n_entries; n_entries += h_nadd[j]; pfill_off[j] = (uint32_t)n_fills; n_fills += h_nfill[j]; }
-    // 3. write pass + fill segments
-    PATCH_TRY(d_entries.ensure(std::max<uint64_t>(1, n_entries) * sizeof(pgr_mm128)));
-    PATCH_TRY(d_fills.ensure(std::max<uint64_t>(1, n_fills) * sizeof(FillSeg)));
-    PATCH_CUDA(cudaMemcpyAsync(d_eoff.p, pentry_off.data(), P * 8, cudaMemcpyHostToDevice, st));
-    PATCH_CUDA(cudaMemcpyAsync(d_foff.p, pfill_off.data(), P * 4, cudaMemcpyHostToDevice, st));
-    rp.entries = d_entries.as<pgr_mm128>(); rp.fills = d_fills.as<FillSeg>();
-    cluster_replay_kernel<1><<<ceil_div<uint32_t>((uint32_t)P, 32), 32, 0, st>>>(rp);
-    if (n_fills) fill_segments_kernel<<<(uint32_t)n_fills, 256, 0, st>>>(d_fills.as<FillSeg>(), d_entries.as<pgr_mm128>());
-    PATCH_CUDA(cudaGetLastError());
+    trace_mark("patches: heavy write pass + tables");
     // 4. splice.  Patch metadata on the device: [pseq | pq0 | pq1 | plb | pub] u32, then pn_add, pentry_off, pdelta, pdst (8 B each),
     //    off1[n+1] u64, seq_first_patch[n] i32, seq_n_patch[n] u32
     std::vector<uint32_t> pseq(P);
@@ -566,21 +619,22 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     PATCH_CUDA(cudaMemcpyAsync(m_u32, pseq.data(), P * 4, cudaMemcpyHostToDevice, st));
     PATCH_CUDA(cudaMemcpyAsync(m_u32 + P, h_q.data(), P * 8, cudaMemcpyHostToDevice, st));           // pq0 | pq1
     PATCH_CUDA(cudaMemcpyAsync(m_u64, h_nadd.data(), P * 8, cudaMemcpyHostToDevice, st));
-    PATCH_CUDA(cudaMemcpyAsync(m_u64 + P, pentry_off.data(), P * 8, cudaMemcpyHostToDevice, st));
+    PATCH_CUDA(cudaMemcpyAsync(m_u64 + P, psrc.data(), P * 8, cudaMemcpyHostToDevice, st));
     PATCH_CUDA(cudaMemcpyAsync(m_first, seq_first.data(), n * 4, cudaMemcpyHostToDevice, st));
     PATCH_CUDA(cudaMemcpyAsync(m_np, seq_np.data(), n * 4, cudaMemcpyHostToDevice, st));
     SpliceParams sp;
     sp.flat0 = ctx->bufA.as<pgr_mm128>(); sp.off0 = ctx->seq_dst.as<uint64_t>(); sp.n_seq = (uint32_t)n;
     sp.seq_first_patch = m_first; sp.seq_n_patch = m_np;
     sp.pseq = m_u32; sp.pq0 = m_u32 + P; sp.pq1 = m_u32 + 2 * P; sp.plb = m_u32 + 3 * P; sp.pub = m_u32 + 4 * P;
-    sp.pn_add = m_u64; sp.pentry_off = m_u64 + P; sp.pdelta = (const int64_t *)(m_u64 + 2 * P); sp.pdst = m_u64 + 3 * P; sp.off1 = m_u64 + 4 * P;
-    sp.entries = d_entries.as<pgr_mm128>(); sp.n_patches = (uint32_t)P; sp.n0 = off0[n];
+    sp.pn_add = m_u64; sp.psrc = (const pgr_mm128 *const *)(m_u64 + P); sp.pdelta = (const int64_t *)(m_u64 + 2 * P); sp.pdst = m_u64 + 3 * P; sp.off1 = m_u64 + 4 * P;
+    sp.n_patches = (uint32_t)P; sp.n0 = off0[n];
     splice_bounds_kernel<<<ceil_div<uint32_t>((uint32_t)P, 64), 64, 0, st>>>(sp);
     PATCH_CUDA(cudaGetLastError());
     std::vector<uint32_t> plb(P), pub(P);
     PATCH_CUDA(cudaMemcpyAsync(plb.data(), sp.plb, P * 4, cudaMemcpyDeviceToHost, st));
     PATCH_CUDA(cudaMemcpyAsync(pub.data(), sp.pub, P * 4, cudaMemcpyDeviceToHost, st));
     PATCH_CUDA(cudaStreamSynchronize(st));
+    trace_mark("patches: write pass + bounds");
     // consecutive patches of a sequence must not overlap (the cluster gap guarantees it)
     for (size_t j = 0; j < P; j++) {
         if (pub[j] < plb[j] || (j > 0 && pseq[j] == pseq[j - 1] && plb[j] < pub[j - 1])) {
@@ -613,7 +667,8 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     PATCH_CUDA(cudaMemcpyAsync(ctx->seq_dst.p, off1.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     ctx->timer.end(slot_t, st);
     PATCH_CUDA(cudaStreamSynchronize(st));
-    ctx->counters[0] += 6 + (n_fills ? 1 : 0);
+    trace_mark("patches: splice");
+    ctx->counters[0] += 6;
     ctx->counters[4] = P;
     ctx->counters[5] = n_fills;
     ctx->counters[6] = n_entries;

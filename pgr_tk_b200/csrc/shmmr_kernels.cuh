@@ -250,20 +250,23 @@ __device__ __noinline__ uint32_t dirty_mask(uint32_t i0, uint32_t i1, uint32_t i
 }
 
 // cold path of the fast key loop: some position of this thread's block has equal top words of plane 0 on both strands, so the
-// strand picked from them may be wrong: redo the prefix of those positions exactly and mark the block if one is a palindrome
-__device__ __noinline__ void strand_tie_scan(const L0Params &p, L0Smem &s, L0Smem::TileDesc &D, int kb, int32_t blk_pos, int32_t L, uint32_t k, uint32_t dirty) {
-    bool pal = false;
+// strand picked from them may be wrong: redo the prefix of those positions exactly.  Returns true (and marks the block) if
+// one of them is a pushed palindrome: the whole block is then re-derived by the replay and none of its keys matters.
+__device__ __noinline__ bool strand_tie_scan(const L0Params &p, L0Smem &s, L0Smem::TileDesc &D, int kb, int32_t blk_pos, int32_t L, uint32_t k, uint32_t dirty) {
     for (int i = 0; i < 32; i++) {
         if ((dirty >> i) & 1u) continue;
         const int q = 32 * kb + i, pos = blk_pos + i;
         const KmerRegs r = kmer_at(s, q, k);
         if ((uint32_t)(r.f0 >> (k - 32)) != (uint32_t)(r.r0 >> (k - 32))) continue;
+        if (r.f0 == r.r0 && r.f1 == r.r1 && pos >= (int)k && pos < L) {
+            mark_block(p.mark_bits, p.n_marks, D.seq_off, blk_pos);
+            return true;
+        }
         const bool rev = r.r0 < r.f0;
         const uint64_t h = rev ? (u64hash(r.r0) ^ u64hash(r.r1 ^ HASH_XOR)) : (u64hash(r.f0) ^ u64hash(r.f1 ^ HASH_XOR));
         s.H[pidx(q)] = (uint32_t)(h >> 32) & 0x00FFFFFFu;   // the fast loop's 24-bit prefix
-        pal = pal || (r.f0 == r.r0 && r.f1 == r.r1 && pos >= (int)k && pos < L);
     }
-    if (pal) mark_block(p.mark_bits, p.n_marks, D.seq_off, blk_pos);
+    return false;
 }
 
 // Level-0 minimizers of one tile.  W, K > 0 are compile-time specialisations; 0 = read from params.
@@ -326,14 +329,16 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             if (bad_bits || blk_pos < 0 || blk_pos + 32 > L) {
                 // slow exact check restricted to the bytes that belong to the sequence: a block with a byte outside ACGTacgt
                 // is marked (its neighbourhood is replayed exactly), like a palindrome's
+                uint32_t minv = 0;   // bytes the reference's LUT maps to 4 (raw codes 0..3 are bases for it, shmmrutils.rs:426)
 #pragma unroll 1
                 for (int j = 0; j < 32; j++) {
                     const int pos = blk_pos + j;
-                    if (pos >= 0 && pos < L && !byte_is_acgt((wd[j >> 2] >> (8 * (j & 3))) & 0xFF)) inv |= 1u << j;
+                    const uint32_t ch = (wd[j >> 2] >> (8 * (j & 3))) & 0xFF;
+                    if (pos >= 0 && pos < L && !byte_is_acgt(ch)) { inv |= 1u << j; if (ch > 3) minv |= 1u << j; }
                 }
                 if (inv) {
                     mark_block(p.mark_bits, p.n_marks, D.seq_off, blk_pos);
-                    if (inv == 0xFFFFFFFFu) { const uint64_t g = (D.seq_off + (uint64_t)(int64_t)blk_pos) >> 5; atomicOr(&p.allinv_bits[g >> 5], 1u << (g & 31)); }
+                    if (minv == 0xFFFFFFFFu) { const uint64_t g = (D.seq_off + (uint64_t)(int64_t)blk_pos) >> 5; atomicOr(&p.allinv_bits[g >> 5], 1u << (g & 31)); }
                 }
             }
         }
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         if (tid >= L0_CTX && blk_live) {
             {
                 const uint32_t i1 = s.bext[tid + 1], i2 = s.bext[tid];
-                if (inv | i1 | i2) dirty = dirty_mask(inv, i1, i2, k);
+                if (inv | i1 | i2) dirty = (inv == 0xFFFFFFFFu) ? 0xFFFFFFFFu : dirty_mask(inv, i1, i2, k);
             }
             const uint32_t a2 = s.F0[tid - 2], a1 = s.F0[tid - 1], a0 = f0;
             const uint32_t b2 = s.F1[tid - 2], b1 = s.F1[tid - 1], b0 = f1;
@@ -368,7 +373,10 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             const uint32_t q00 = fsr(ra0, ra1, cb), q01 = fsr(ra1, ra2, cb), q02 = fsr(ra2, ra3, cb);
             const uint32_t q10 = fsr(rb0, rb1, cb), q11 = fsr(rb1, rb2, cb), q12 = fsr(rb2, rb3, cb);
             const int base = pidx(32 * kb);
-            if constexpr (K > 32) {
+            if (dirty == 0xFFFFFFFFu) {
+                // interior of an invalid run: no key of this block is the reference's; none is a candidate
+                for (int i = 0; i < 32; i++) s.H[base + i] = (K > 32) ? 0x00FFFFFFu : 0xFFFFFFFFu;
+            } else if constexpr (K > 32) {
                 // Fast key loop (K > 32; 61 instructions per position against 72 for the generic loop below).  Each
                 // strand carries X = the TOP 32 bits of its K-bit plane-0 register (bits [K-32, K)), a plain funnel
                 // extraction from the plane string pre-shifted by K-32 once per thread.  The strand (shmmrutils.rs:486) is
@@ -408,11 +416,14 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                     // orders consistently with x, and prefix ties between candidates are resolved exactly in phase 5
                     s.H[base + i] = (uhi ^ vhi) & 0x00FFFFFFu;
                 }
-                if (!no_tie) strand_tie_scan(p, s, D, kb, blk_pos, L, k, dirty);
+                // a block with a pushed palindrome lies inside a replay patch as a whole (patch_kernels.cuh): none of its
+                // positions needs to be a candidate, which spares the exact tie tests of phase 5 in low-complexity sequence
+                if (!no_tie && strand_tie_scan(p, s, D, kb, blk_pos, L, k, dirty)) dirty = 0xFFFFFFFFu;
                 if (dirty) {   // never candidates; the maximal prefix keeps them from shadowing clean keys
                     for (int i = 0; i < 32; i++) if ((dirty >> i) & 1u) s.H[base + i] = 0x00FFFFFFu;
                 }
             } else {
+                bool pal_blk = false;   // the block holds a pushed palindrome: replayed as a whole, no candidates (see above)
     #pragma unroll U
                 for (int i = 0; i < 32; i++) {
                     const uint32_t sh = 31 - i;
@@ -422,7 +433,10 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                     const uint32_t r1lo = fsr(q10, q11, i) & mlo, r1hi = fsr(q11, q12, i) & mhi;
                     if (f0lo == r0lo) {                             // rare: possible palindrome (shmmrutils.rs:477)
                         const int pos = blk_pos + i;
-                        if (f0hi == r0hi && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L && !((dirty >> i) & 1u)) mark_block(p.mark_bits, p.n_marks, D.seq_off, blk_pos);
+                        if (f0hi == r0hi && f1lo == r1lo && f1hi == r1hi && pos >= (int)k && pos < L && !((dirty >> i) & 1u) && !pal_blk) {
+                            mark_block(p.mark_bits, p.n_marks, D.seq_off, blk_pos);
+                            pal_blk = true;
+                        }
                     }
                     // strand: reverse iff rmmer.0 < fmmer.0 (shmmrutils.rs:486, plane 0 only); one 64-bit compare, four selects
                     uint32_t ulo, uhi, vlo, vhi;
@@ -436,6 +450,10 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                     u64hash_dev32(vlo, vhi);
                     // MM128.x high word = hash bits 24..55
                     s.H[base + i] = ((dirty >> i) & 1u) ? 0xFFFFFFFFu : __funnelshift_r(ulo ^ vlo, uhi ^ vhi, 24);
+                }
+                if (pal_blk) {
+                    dirty = 0xFFFFFFFFu;
+                    for (int i = 0; i < 32; i++) s.H[base + i] = 0xFFFFFFFFu;
                 }
             }
         }

@@ -233,8 +233,9 @@ def test_long_invalid_runs_are_crossed_in_closed_form():
     ctx.shmmrs(pg.ShmmrSpec())
     c = ctx.counters()
     assert c[2] == 0          # no whole-sequence replay
-    assert c[5] >= 8          # fill segments: the long runs were jumped over
-    assert c[6] >= 500_000    # level-0 entries supplied by patches (the reference emits every position of a saturated run)
+    assert c[5] >= 8          # the long runs were jumped over ...
+    assert c[6] < 100_000     # ... and only their two ends materialised (the reference's level-0 list holds every position of a
+                              # saturated run, ~0.6 M entries here; the middle cannot survive the min_span filter)
     ctx.close()
 
 
