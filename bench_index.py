@@ -60,6 +60,8 @@ def run(pg, torch, dist, rank, world, local_rank, comm, reps=3, n_hap=N_HAP, hap
     def timed(fn):
         ts, last = [], None
         for it in range(1 + reps):
+            if last is not None:
+                last[0].close()          # a fresh index every step; the previous one returns its memory to the device pool first
             barrier()
             t0 = time.perf_counter()
             idx, info = fn()
@@ -70,8 +72,6 @@ def run(pg, torch, dist, rank, world, local_rank, comm, reps=3, n_hap=N_HAP, hap
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if it >= 1:
                 ts.append(float(t.item()))
-            if last is not None:
-                last[0].close()
             last = (idx, info)
         return ts, last
 

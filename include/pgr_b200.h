@@ -95,6 +95,10 @@ void pgr_b200_free(void *p);
 /* pinned host staging for callers that want the H2D copy at PCIe rate (bench.py e2e leg) */
 void *pgr_b200_host_alloc(size_t bytes);
 void pgr_b200_host_free(void *p);
+/* page-lock memory the caller already owns (a file buffer a reader thread parsed in place), so that the batch calls copy
+ * from it at PCIe rate without a staging copy; 0 on success.  Unregister before freeing it. */
+int pgr_b200_host_register(void *p, size_t bytes);
+int pgr_b200_host_unregister(void *p);
 
 /* ---- sequence_to_shmmrs ---------------------------------------------------------------------------------- */
 /* replaces shmmrutils::sequence_to_shmmrs(rid, &seq, &spec, padding) -> Vec<MM128>   (shmmrutils.rs:657-669);
@@ -219,6 +223,10 @@ pgr_b200_index *pgr_b200_mindex_shard(pgr_b200_mindex *m, int shard);
 /* canonical CSR / .mdb of the whole map = the slices in shard order (same layout as the single-GPU calls) */
 int pgr_b200_mindex_export_csr(pgr_b200_mindex *m, uint64_t *keys, uint64_t *offsets, pgr_frag_sig *sigs);
 int pgr_b200_mindex_write_mdb(pgr_b200_mindex *m, const char *path);
+/* the whole map as ONE ordinary finalized index on `device` (slices copied GPU to GPU, offsets rebased): what queries,
+ * frag_map_to_adj_list and fragment compression run against after a multi-GPU build.  New handle, freed by the caller
+ * with pgr_b200_index_free. */
+pgr_b200_index *pgr_b200_mindex_gather(pgr_b200_mindex *m, int device);
 
 /* ---- query, chaining, adjacency ------------------------------------------------------------------------------ */
 /* replaces seq_db::raw_query_fragment(&frag_map, &query, &spec) -> Vec<FragmentHit> (seq_db.rs:1200-1228): per query

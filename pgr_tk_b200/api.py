@@ -153,6 +153,10 @@ def lib():
         L.pgr_b200_mindex_shard.argtypes = [vp, C.c_int]
         L.pgr_b200_mindex_export_csr.argtypes = [vp, vp, vp, vp]
         L.pgr_b200_mindex_write_mdb.argtypes = [vp, C.c_char_p]
+        L.pgr_b200_mindex_gather.restype = vp
+        L.pgr_b200_mindex_gather.argtypes = [vp, C.c_int]
+        L.pgr_b200_host_register.argtypes = [vp, sz]
+        L.pgr_b200_host_unregister.argtypes = [vp]
         L.pgr_b200_index_counts.argtypes = [vp, P(sz), P(sz), P(u32)]
         L.pgr_b200_index_export_csr.argtypes = [vp, vp, vp, vp]
         L.pgr_b200_index_tuples_device.argtypes = [vp, P(vp), P(sz)]
@@ -619,6 +623,13 @@ class ShardedIndex:
 
     def write_mdb(self, path):
         _check(lib().pgr_b200_mindex_write_mdb(self.h, path.encode()))
+
+    def gather(self, device=0):
+        """the whole map as one ordinary ShmmrIndex on `device` (for queries, adjacency, fragment compression)"""
+        h = lib().pgr_b200_mindex_gather(self.h, device)
+        if not h:
+            _check(-4)
+        return ShmmrIndex(handle=h)
 
 
 class _BorrowedIndex(ShmmrIndex):

@@ -145,6 +145,17 @@ void *pgr_b200_host_alloc(size_t bytes) {
     return p;
 }
 void pgr_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+int pgr_b200_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) { set_error("NULL argument"); return PGR_E_ARG; }
+    if (pgr_b200_device_count() <= 0) { set_error("no CUDA device available"); return PGR_E_NO_DEVICE; }
+    PGR_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return PGR_OK;
+}
+int pgr_b200_host_unregister(void *p) {
+    if (!p) return PGR_OK;
+    PGR_CUDA(cudaHostUnregister(p));
+    return PGR_OK;
+}
 
 pgr_b200_ctx *pgr_b200_ctx_new(int device) {
     int n = pgr_b200_device_count();

@@ -240,6 +240,7 @@ int pgr_b200_index_get_spec(const pgr_b200_index *idx, pgr_shmmr_spec *spec) {
 int pgr_b200_index_add_batch(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens) {
     if (!idx || (n && (!sids || !seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
     if (idx->staged) { set_error("a staged batch is pending: call pgr_b200_index_commit_batch first"); return PGR_E_ARG; }
+    if (idx->gathered) { set_error("an index gathered from a multi-GPU build is read-only"); return PGR_E_ARG; }
     idx->finalized = false;
     idx->ord_in_batch = 0;
     const uint64_t t0 = idx->n_tuples;
@@ -384,6 +385,7 @@ int pgr_b200_index_counts(pgr_b200_index *idx, size_t *n_keys, size_t *n_sigs, u
 int pgr_b200_index_export_csr(pgr_b200_index *idx, uint64_t *keys, uint64_t *offsets, pgr_frag_sig *sigs) {
     if (!idx || !keys || !offsets || !sigs) { set_error("NULL argument"); return PGR_E_ARG; }
     PGR_TRY(pgr_b200_index_finalize(idx));
+    PGR_CUDA(cudaSetDevice(idx->ctx->device));
     cudaStream_t st = idx->ctx->stream;
     if (idx->n_keys) PGR_CUDA(cudaMemcpyAsync(keys, idx->ukeys.p, idx->n_keys * sizeof(SortKey), cudaMemcpyDeviceToHost, st));
     PGR_CUDA(cudaMemcpyAsync(offsets, idx->offsets.p, (idx->n_keys + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));

@@ -24,6 +24,7 @@ struct pgr_b200_index {
     // multi-GPU build (shard.cu): tuples carry the insertion ordinal of their sequence (FragTuple::ord = ord_base + position in
     // the batch); the owner's sort uses it as the minor key when blocks of several batches interleave (ord_sort)
     uint32_t ord_base = 0, ord_in_batch = 0;
+    bool gathered = false;            // CSR copied from the shards of a multi-GPU build: no tuples behind it, read-only
     bool from_mdb = false;            // read from an .mdb: no sequences behind it, appending is refused by the host mirror
     bool ord_sort = false;
     pgr::DevBuf sendbuf;              // tuples partitioned by destination shard

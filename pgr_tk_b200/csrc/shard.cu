@@ -243,6 +243,11 @@ __global__ void __launch_bounds__(PT_NT) part_scatter_kernel(const FragTuple *t,
     }
 }
 
+__global__ void add_u64_kernel(uint64_t *p, uint64_t n, uint64_t v) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += v;
+}
+
 }  // namespace pgr
 
 // ---- handles ------------------------------------------------------------------------------------------------------
@@ -646,6 +651,36 @@ int pgr_b200_mindex_export_csr(pgr_b200_mindex *m, uint64_t *keys, uint64_t *off
         k0 += nk; s0 += ns;
     }
     return PGR_OK;
+}
+
+pgr_b200_index *pgr_b200_mindex_gather(pgr_b200_mindex *m, int device) {
+    if (!m) { set_error("NULL argument"); return nullptr; }
+    size_t nk = 0, ns = 0;
+    if (pgr_b200_mindex_counts(m, &nk, &ns, nullptr) != PGR_OK) return nullptr;
+    if (ns >= 0xFFFFFFF0ull) { set_error("more than 2^32 signatures on one device"); return nullptr; }
+    pgr_b200_index *g = pgr_b200_index_new(&m->spec, m->mode, device);
+    if (!g) return nullptr;
+    auto fail = [&]() -> pgr_b200_index * { pgr_b200_index_free(g); return nullptr; };
+    pgr_b200_ctx *ctx = g->ctx;
+    cudaStream_t st = ctx->stream;
+    if (g->ukeys.ensure(std::max<size_t>(1, nk) * sizeof(SortKey)) != PGR_OK || g->offsets.ensure((nk + 2) * sizeof(uint64_t)) != PGR_OK ||
+        g->sigs.ensure(std::max<size_t>(1, ns) * sizeof(pgr_frag_sig)) != PGR_OK) return fail();
+    size_t k0 = 0, s0 = 0;
+    for (int r = 0; r < m->n; r++) {
+        pgr_b200_index *sh = m->shard[r];
+        const size_t k = sh->n_keys, s = sh->n_tuples;
+        cudaError_t e = cudaSuccess;
+        if (k) e = cudaMemcpyPeerAsync(g->ukeys.as<SortKey>() + k0, ctx->device, sh->ukeys.p, sh->ctx->device, k * sizeof(SortKey), st);
+        if (e == cudaSuccess && k) e = cudaMemcpyPeerAsync(g->offsets.as<uint64_t>() + k0, ctx->device, sh->offsets.p, sh->ctx->device, k * sizeof(uint64_t), st);
+        if (e == cudaSuccess && s) e = cudaMemcpyPeerAsync(g->sigs.as<pgr_frag_sig>() + s0, ctx->device, sh->sigs.p, sh->ctx->device, s * sizeof(pgr_frag_sig), st);
+        if (e != cudaSuccess) { set_error("peer copy of shard %d failed: %s", r, cudaGetErrorString(e)); return fail(); }
+        if (k && s0) add_u64_kernel<<<(uint32_t)ceil_div<uint64_t>(k, 256), 256, 0, st>>>(g->offsets.as<uint64_t>() + k0, k, s0);
+        k0 += k; s0 += s;
+    }
+    set_u64_kernel<<<1, 1, 0, st>>>(g->offsets.as<uint64_t>() + nk, ns);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { set_error("gather failed"); return fail(); }
+    g->n_keys = nk; g->n_tuples = ns; g->n_frags = (uint32_t)m->n_frags; g->finalized = true; g->gathered = true;
+    return g;
 }
 
 int pgr_b200_mindex_write_mdb(pgr_b200_mindex *m, const char *path) {

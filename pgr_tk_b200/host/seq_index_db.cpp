@@ -3,85 +3,46 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace pgrb200 {
 
-// read a whole file, transparently inflating gzip (seq_db.rs:420-454 sniffs the magic bytes 0x1f 0x8b)
-static bool slurp(const std::string &path, std::vector<uint8_t> &buf, std::string &err) {
-    gzFile f = gzopen(path.c_str(), "rb");   // zlib reads plain files as-is
-    if (!f) { err = "cannot open " + path; return false; }
-    uint8_t tmp[1 << 16];
-    int got;
-    while ((got = gzread(f, tmp, sizeof tmp)) > 0) buf.insert(buf.end(), tmp, tmp + got);
-    const bool ok = got == 0;
-    gzclose(f);
-    if (!ok) err = "read error on " + path;
-    return ok;
-}
-
-// fasta_io.rs:46-172.  The reader's constructor consumes the first byte of the file ('>' or '@').
+// fasta_io.rs:46-172 (the parsing itself: fastx_ingest.cpp)
 bool read_fastx(const std::string &path, std::vector<SeqRec> &out, std::string &err) {
-    std::vector<uint8_t> b;
-    if (!slurp(path, b, err)) return false;
-    if (b.empty()) { err = "empty file: " + path; return false; }       // fasta_io.rs:58-63
-    const bool fastq = b[0] == '@';
-    size_t p = 1;
-    const size_t N = b.size();
-    auto take_id = [&](size_t line_end) {
-        std::string id;
-        for (size_t i = p; i < line_end; i++) {
-            const uint8_t c = b[i];
-            if (c == ' ') break;                                         // read_until(b' ')
-            if (c != '\n' && c != '\r') id.push_back((char)c);
-        }
-        return id;
-    };
-    auto line_end_from = [&](size_t q) { while (q < N && b[q] != '\n') q++; return q < N ? q + 1 : N; };
-    if (!fastq) {
-        for (;;) {
-            if (p >= N) break;                                           // read_until returned 0 -> None (fasta_io.rs:90-93)
-            const size_t le = line_end_from(p);
-            SeqRec rec;
-            rec.id = take_id(le);
-            p = le;
-            while (p < N && b[p] != '>') { const uint8_t c = b[p]; if (c != '\n' && c != '\r') rec.seq.push_back(c); p++; }
-            if (p < N) p++;                                              // the '>' of the next record is consumed
-            out.push_back(std::move(rec));
-        }
-    } else {
-        for (;;) {                                                       // fasta_io.rs:120-165
-            const size_t le = line_end_from(p);
-            SeqRec rec;
-            rec.id = take_id(le);
-            p = le;
-            const size_t se = line_end_from(p);
-            for (size_t i = p; i < se; i++) if (b[i] != '\n' && b[i] != '\r') rec.seq.push_back(b[i]);
-            p = se;
-            while (p < N && b[p] != '+') p++;                            // read_until(b'+')
-            if (p < N) p++;
-            p = line_end_from(p);                                        // rest of the '+' line
-            p = line_end_from(p);                                        // quality line
-            size_t q = p;
-            while (q < N && b[q] != '@') q++;                            // read_until(b'@')
-            const size_t consumed = (q < N ? q + 1 : N) - p;
-            p = q < N ? q + 1 : N;
-            out.push_back(std::move(rec));
-            if (consumed == 0) break;                                    // res == Some(0) -> None
-        }
+    ParsedFile pf;
+    parse_fastx_file(path, false, pf);
+    if (!pf.ok) { err = pf.err; return false; }
+    for (size_t i = 0; i < pf.seqs.size(); i++) {
+        SeqRec r;
+        r.id = pf.ids[i];
+        r.seq.assign(pf.seqs[i].p, pf.seqs[i].p + pf.seqs[i].len);
+        out.push_back(std::move(r));
     }
     return true;
 }
 
-SeqIndexDB::~SeqIndexDB() { if (idx_) pgr_b200_index_free(idx_); }
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+SeqIndexDB::~SeqIndexDB() { reset(); }
+
+void SeqIndexDB::reset() {
+    if (idx_) { pgr_b200_index_free(idx_); idx_ = nullptr; }
+    if (midx_) { pgr_b200_mindex_free(midx_); midx_ = nullptr; }
+    seqs_.clear();
+    seq_data_.clear();
+    file_bufs_.clear();
+    owned_seqs_.clear();
+    fastx_backend_ = false;
+}
 
 int SeqIndexDB::load_from_fastx(const std::string &path, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span) {
     spec_.w = w; spec_.k = k; spec_.r = r; spec_.min_span = min_span; spec_.sketch = 0;
-    if (idx_) { pgr_b200_index_free(idx_); idx_ = nullptr; }
-    seqs_.clear();
-    seq_data_.clear();
+    reset();
     idx_ = pgr_b200_index_new(&spec_, 0 /* FASTX fragment numbering */, -1);
     if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
     fastx_backend_ = true;
@@ -95,16 +56,93 @@ int SeqIndexDB::append_from_fastx(const std::string &path) {
 
 // seq_db.rs:471-525: sid continues from seqs.len(); records are handed to the GPU in the reference's batches of <=129
 int SeqIndexDB::load_seqs_from_fastx(const std::string &path) {
-    std::vector<SeqRec> recs;
-    if (!read_fastx(path, recs, err_)) return PGR_E_IO;
-    return add_records(recs, path);
+    std::vector<std::unique_ptr<ParsedFile>> one;
+    one.emplace_back(new ParsedFile());
+    parse_fastx_file(path, true, *one[0]);
+    if (!one[0]->ok) { err_ = one[0]->err; return PGR_E_IO; }
+    return add_parsed(one);
+}
+
+// the sequences of the parsed files (in file order) become the next sequence ids; ONE GPU call for all of them: the batch
+// boundary (129 records in the reference) only sets its parallel granularity, fragment ids are a running counter across batches
+int SeqIndexDB::add_parsed(std::vector<std::unique_ptr<ParsedFile>> &files) {
+    uint32_t sid = (uint32_t)seqs_.size();
+    std::vector<uint32_t> sids;
+    std::vector<const uint8_t *> ptrs;
+    std::vector<size_t> lens;
+    for (auto &f : files) {
+        for (size_t i = 0; i < f->seqs.size(); i++) {
+            sids.push_back(sid);
+            ptrs.push_back(f->seqs[i].p);
+            lens.push_back(f->seqs[i].len);
+            CompactSeq cs;
+            cs.id = sid; cs.len = f->seqs[i].len; cs.name = f->ids[i]; cs.source = f->path;
+            seqs_.push_back(std::move(cs));
+            if (keep_seqs_) seq_data_.push_back(f->seqs[i]);
+            sid++;
+        }
+        timing_.bases += f->bases; timing_.reader_read_s += f->read_s; timing_.reader_parse_s += f->parse_s; timing_.reader_pin_s += f->pin_s;
+    }
+    const double t0 = now_s();
+    const int rc = midx_ ? pgr_b200_mindex_add_batch(midx_, sids.size(), sids.data(), ptrs.data(), lens.data())
+                         : pgr_b200_index_add_batch(idx_, sids.size(), sids.data(), ptrs.data(), lens.data());
+    timing_.gpu_index_s += now_s() - t0;
+    if (rc != PGR_OK) err_ = pgr_b200_last_error();
+    for (auto &f : files) { if (keep_seqs_) file_bufs_.push_back(std::move(f->buf)); }
+    return rc;
+}
+
+int SeqIndexDB::load_from_fastx_list(const std::vector<std::string> &paths, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span, int n_readers, int n_gpus,
+                                     const std::vector<int> &devices) {
+    spec_.w = w; spec_.k = k; spec_.r = r; spec_.min_span = min_span; spec_.sketch = 0;
+    reset();
+    timing_ = Timing();
+    if (paths.empty()) { err_ = "empty file list"; return PGR_E_ARG; }
+    if (!devices.empty()) n_gpus = (int)devices.size();
+    if (n_gpus > 1) {
+        midx_ = devices.empty() ? pgr_b200_mindex_new(&spec_, 0, n_gpus) : pgr_b200_mindex_new_devices(&spec_, 0, n_gpus, devices.data());
+        if (!midx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
+    } else {
+        idx_ = pgr_b200_index_new(&spec_, 0, -1);
+        if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
+    }
+    fastx_backend_ = true;
+    FastxPipeline pipe(paths, n_readers, true);
+    // a batch = the files that are parsed by now (at least one); with several GPUs at least a few files per call so that every
+    // GPU has a block of the batch to work on
+    const size_t max_batch = (size_t)std::max(8, 4 * std::max(1, n_gpus));
+    size_t i = 0;
+    while (i < paths.size()) {
+        std::vector<std::unique_ptr<ParsedFile>> batch;
+        const double t0 = now_s();
+        do {
+            batch.push_back(pipe.take(i));
+            i++;
+            if (!batch.back()->ok) { err_ = batch.back()->err; return PGR_E_IO; }
+        } while (i < paths.size() && batch.size() < max_batch && (pipe.ready(i) || (n_gpus > 1 && batch.size() < (size_t)n_gpus)));
+        timing_.wait_parse_s += now_s() - t0;
+        const int rc = add_parsed(batch);
+        if (rc != PGR_OK) return rc;
+    }
+    if (midx_) {
+        const double t0 = now_s();
+        if (pgr_b200_mindex_finalize(midx_) != PGR_OK) { err_ = pgr_b200_last_error(); return PGR_E_CUDA; }
+        idx_ = pgr_b200_mindex_gather(midx_, 0);
+        if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_CUDA; }
+        pgr_b200_mindex_free(midx_);
+        midx_ = nullptr;
+        timing_.merge_s += now_s() - t0;
+    } else {
+        const double t0 = now_s();
+        if (pgr_b200_index_finalize(idx_) != PGR_OK) { err_ = pgr_b200_last_error(); return PGR_E_CUDA; }
+        timing_.merge_s += now_s() - t0;
+    }
+    return PGR_OK;
 }
 
 int SeqIndexDB::load_from_seq_list(const std::vector<SeqRec> &seq_list, const std::string &source, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span) {
     spec_.w = w; spec_.k = k; spec_.r = r; spec_.min_span = min_span; spec_.sketch = 0;
-    if (idx_) { pgr_b200_index_free(idx_); idx_ = nullptr; }
-    seqs_.clear();
-    seq_data_.clear();
+    reset();
     idx_ = pgr_b200_index_new(&spec_, 0, -1);
     if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
     fastx_backend_ = true;
@@ -130,15 +168,16 @@ int SeqIndexDB::add_records(std::vector<SeqRec> &recs, const std::string &source
     // no effect on results (fragment ids are a running counter across batches)
     const int rc = pgr_b200_index_add_batch(idx_, recs.size(), sids.data(), ptrs.data(), lens.data());
     if (rc != PGR_OK) err_ = pgr_b200_last_error();
-    if (keep_seqs_) for (auto &r : recs) seq_data_.push_back(std::move(r.seq));
+    if (keep_seqs_) for (auto &r : recs) {
+        owned_seqs_.push_back(std::move(r.seq));
+        SeqSpan sp; sp.p = owned_seqs_.back().data(); sp.len = owned_seqs_.back().size();
+        seq_data_.push_back(sp);
+    }
     return rc;
 }
 
 int SeqIndexDB::load_from_index_files(const std::string &prefix) {
-    if (idx_) { pgr_b200_index_free(idx_); idx_ = nullptr; }
-    seqs_.clear();
-    seq_data_.clear();
-    fastx_backend_ = false;
+    reset();
     idx_ = pgr_b200_index_read_mdb((prefix + ".mdb").c_str(), -1);
     if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_IO; }
     pgr_b200_index_get_spec(idx_, &spec_);
@@ -165,8 +204,8 @@ int SeqIndexDB::load_from_index_files(const std::string &prefix) {
 
 bool SeqIndexDB::get_sub_seq_by_id(uint32_t sid, size_t bgn, size_t end, std::vector<uint8_t> &out) {
     if (sid < seq_data_.size()) {
-        if (bgn > end || end > seq_data_[sid].size()) return false;
-        out.assign(seq_data_[sid].begin() + (ptrdiff_t)bgn, seq_data_[sid].begin() + (ptrdiff_t)end);
+        if (bgn > end || end > seq_data_[sid].len) return false;
+        out.assign(seq_data_[sid].p + bgn, seq_data_[sid].p + end);
         return true;
     }
     if (!frag_store_.loaded()) return false;
@@ -360,47 +399,72 @@ static bool deflate_raw(const std::vector<uint8_t> &in, std::vector<uint8_t> &ou
 
 // seq_db.rs:814-873 on the fragment records of pgr_b200_index_compress_fragments (tests feed the oracle's records, which
 // have the same layout, to run this writer without a device)
+// chunks of `chunk_size` fragments are encoded (bincode 2, standard configuration) and deflated independently — by a pool of
+// host threads, like the reference's par_iter over the chunks (seq_db.rs:829-853) — and written in chunk order
 int write_frag_store(const std::string &prefix, size_t chunk_size, uint32_t k, const pgr_fragment *frags, size_t nf, const pgr_aln_seg *segs,
-                     const std::vector<CompactSeq> &seqs, const std::vector<std::vector<uint8_t>> &seq_data, std::string &err) {
+                     const std::vector<CompactSeq> &seqs, const std::vector<SeqSpan> &seq_data, std::string &err, int n_threads) {
     if (chunk_size == 0 || seq_data.size() != seqs.size()) { err = "write_frag_store: bad arguments"; return PGR_E_ARG; }
+    std::vector<std::pair<uint32_t, uint32_t>> range(seqs.size(), {0, 0});   // per sequence (first fragment, count)
+    for (size_t i = 0; i < nf; i++) {
+        const pgr_fragment &f = frags[i];
+        if (f.sid >= seqs.size() || f.end > seq_data[f.sid].len || f.bgn > f.end) { err = "fragment record out of range"; return PGR_E_ARG; }
+        auto &rg = range[f.sid];
+        if (rg.second == 0) rg.first = (uint32_t)i;
+        rg.second++;
+    }
+    const size_t n_chunks = (nf + chunk_size - 1) / chunk_size;
+    std::vector<std::vector<uint8_t>> z(n_chunks);
+    std::vector<uint32_t> total_len(n_chunks, 0);
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+    auto work = [&]() {
+        std::vector<uint8_t> w;
+        for (;;) {
+            const size_t c = next.fetch_add(1);
+            if (c >= n_chunks || failed.load()) return;
+            const size_t c0 = c * chunk_size, c1 = std::min(nf, c0 + chunk_size);
+            w.clear();
+            put_varint(w, c1 - c0);
+            uint32_t tl = 0;
+            for (size_t i = c0; i < c1; i++) {
+                const pgr_fragment &f = frags[i];
+                put_varint(w, f.kind);
+                if (f.kind == 0) {                               // AlnSegments((ref, reversed, len, Vec<AlnSegment>))
+                    put_varint(w, f.ref_frag); w.push_back(f.reversed ? 1 : 0); put_varint(w, f.len); put_varint(w, f.n_segs);
+                    for (uint32_t s = 0; s < f.n_segs; s++) {
+                        const pgr_aln_seg &g = segs[f.seg_off + s];
+                        put_varint(w, g.type);
+                        if (g.type == 1) { put_varint(w, g.a); put_varint(w, g.b); } else if (g.type == 2) w.push_back((uint8_t)g.a);
+                    }
+                    tl += f.len - k;
+                } else {
+                    put_bytes(w, seq_data[f.sid].p + f.bgn, f.end - f.bgn);
+                    tl += f.kind == 2 ? f.len - k : f.len;
+                }
+            }
+            total_len[c] = tl;
+            if (!deflate_raw(w, z[c])) failed.store(true);
+        }
+    };
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, n_chunks));
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (failed.load()) { err = "deflate failed"; return PGR_E_IO; }
     FILE *frg = fopen((prefix + ".frg").c_str(), "wb"), *sdx = fopen((prefix + ".sdx").c_str(), "wb");
     if (!frg || !sdx) { err = "frag file creating fail"; if (frg) fclose(frg); if (sdx) fclose(sdx); return PGR_E_IO; }
     fwrite("FRG:0.5", 1, 7, frg);
     fwrite("SDX:0.5", 1, 7, sdx);
     std::vector<uint8_t> sd;
     put_varint(sd, chunk_size);
-    put_varint(sd, (nf + chunk_size - 1) / chunk_size);
-    std::vector<std::pair<uint32_t, uint32_t>> range(seqs.size(), {0, 0});   // per sequence (first fragment, count)
+    put_varint(sd, n_chunks);
     uint64_t offset = 0;
-    for (size_t c0 = 0; c0 < nf; c0 += chunk_size) {
-        const size_t c1 = std::min(nf, c0 + chunk_size);
-        std::vector<uint8_t> w, z;
-        put_varint(w, c1 - c0);
-        uint32_t total_len = 0;
-        for (size_t i = c0; i < c1; i++) {
-            const pgr_fragment &f = frags[i];
-            if (f.sid >= seqs.size() || f.end > seq_data[f.sid].size() || f.bgn > f.end) { err = "fragment record out of range"; fclose(frg); fclose(sdx); return PGR_E_ARG; }
-            auto &rg = range[f.sid];
-            if (rg.second == 0) rg.first = (uint32_t)i;
-            rg.second++;
-            put_varint(w, f.kind);
-            if (f.kind == 0) {                               // AlnSegments((ref, reversed, len, Vec<AlnSegment>))
-                put_varint(w, f.ref_frag); w.push_back(f.reversed ? 1 : 0); put_varint(w, f.len); put_varint(w, f.n_segs);
-                for (uint32_t s = 0; s < f.n_segs; s++) {
-                    const pgr_aln_seg &g = segs[f.seg_off + s];
-                    put_varint(w, g.type);
-                    if (g.type == 1) { put_varint(w, g.a); put_varint(w, g.b); } else if (g.type == 2) w.push_back((uint8_t)g.a);
-                }
-                total_len += f.len - k;
-            } else {
-                put_bytes(w, seq_data[f.sid].data() + f.bgn, f.end - f.bgn);
-                total_len += f.kind == 2 ? f.len - k : f.len;
-            }
-        }
-        if (!deflate_raw(w, z)) { err = "deflate failed"; fclose(frg); fclose(sdx); return PGR_E_IO; }
-        fwrite(z.data(), 1, z.size(), frg);
-        put_varint(sd, offset); put_varint(sd, z.size()); put_varint(sd, total_len);
-        offset += z.size();
+    for (size_t c = 0; c < n_chunks; c++) {
+        fwrite(z[c].data(), 1, z[c].size(), frg);
+        put_varint(sd, offset); put_varint(sd, z[c].size()); put_varint(sd, total_len[c]);
+        offset += z[c].size();
     }
     put_varint(sd, seqs.size());
     for (size_t i = 0; i < seqs.size(); i++) {               // CompactSeq {source: Option<String>, name, id, seq_frag_range, len}
@@ -411,8 +475,8 @@ int write_frag_store(const std::string &prefix, size_t chunk_size, uint32_t k, c
         put_varint(sd, seqs[i].len);
     }
     fwrite(sd.data(), 1, sd.size(), sdx);
-    fclose(frg);
-    fclose(sdx);
+    const bool bad = ferror(frg) || ferror(sdx);
+    if (fclose(frg) != 0 || fclose(sdx) != 0 || bad) { err = "frag file writing error"; return PGR_E_IO; }
     return PGR_OK;
 }
 
@@ -422,13 +486,17 @@ int SeqIndexDB::write_to_frag_files(const std::string &prefix, size_t chunk_size
     std::vector<uint32_t> sids;
     std::vector<const uint8_t *> ptrs;
     std::vector<size_t> lens;
-    for (size_t i = 0; i < seqs_.size(); i++) { sids.push_back(seqs_[i].id); ptrs.push_back(seq_data_[i].data()); lens.push_back(seq_data_[i].size()); }
+    for (size_t i = 0; i < seqs_.size(); i++) { sids.push_back(seqs_[i].id); ptrs.push_back(seq_data_[i].p); lens.push_back(seq_data_[i].len); }
     pgr_fragment *frags = nullptr;
     pgr_aln_seg *segs = nullptr;
     size_t nf = 0, nsg = 0;
+    double t0 = now_s();
     int rc = pgr_b200_index_compress_fragments(idx_, seqs_.size(), sids.data(), ptrs.data(), lens.data(), &frags, &nf, &segs, &nsg);
+    timing_.frag_gpu_s += now_s() - t0;
     if (rc != PGR_OK) { err_ = pgr_b200_last_error(); return rc; }
+    t0 = now_s();
     rc = write_frag_store(prefix, chunk_size, spec_.k, frags, nf, segs, seqs_, seq_data_, err_);
+    timing_.frag_encode_s += now_s() - t0;
     pgr_b200_free(frags);
     pgr_b200_free(segs);
     return rc;
@@ -436,7 +504,9 @@ int SeqIndexDB::write_to_frag_files(const std::string &prefix, size_t chunk_size
 
 int SeqIndexDB::write_shmmr_map_index(const std::string &prefix) {
     if (!idx_) { err_ = "no index"; return PGR_E_ARG; }
+    const double t0 = now_s();
     int rc = pgr_b200_index_write_mdb(idx_, (prefix + ".mdb").c_str());
+    timing_.mdb_write_s += now_s() - t0;
     if (rc != PGR_OK) { err_ = pgr_b200_last_error(); return rc; }
     FILE *f = fopen((prefix + ".midx").c_str(), "wb");
     if (!f) { err_ = "file create error"; return PGR_E_IO; }

@@ -13,12 +13,13 @@
 #include <vector>
 
 #include "../../include/pgr_b200.h"
+#include "fastx_ingest.hpp"
 
 namespace pgrb200 {
 
 struct SeqRec { std::string id; std::vector<uint8_t> seq; };
 
-// whole-file FASTA/FASTQ parser with the reference's exact field rules
+// whole-file FASTA/FASTQ parser with the reference's exact field rules (fastx_ingest.cpp does the parsing)
 bool read_fastx(const std::string &path, std::vector<SeqRec> &out, std::string &err);
 
 struct CompactSeq { uint32_t id; uint64_t len; std::string name, source; };
@@ -47,7 +48,7 @@ private:
 
 // seq_db.rs:814-873 write_to_frag_files on fragment records laid out as pgr_b200_index_compress_fragments returns them
 int write_frag_store(const std::string &prefix, size_t chunk_size, uint32_t k, const pgr_fragment *frags, size_t n_frags, const pgr_aln_seg *segs,
-                     const std::vector<CompactSeq> &seqs, const std::vector<std::vector<uint8_t>> &seq_data, std::string &err);
+                     const std::vector<CompactSeq> &seqs, const std::vector<SeqSpan> &seq_data, std::string &err, int n_threads = 0);
 
 class SeqIndexDB {
 public:
@@ -59,6 +60,14 @@ public:
     int load_from_fastx(const std::string &path, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span);
     // ext.rs:180-199
     int append_from_fastx(const std::string &path);
+    // pgr-make-frgdb.rs:48-63 as a pipeline: the files of the list are read, parsed and page-locked by `n_readers` threads while
+    // the GPU(s) index the files that are ready (same result as load_from_fastx + append_from_fastx file by file).  n_gpus > 1
+    // builds the map sharded over the GPUs (pgr_b200_mindex_*, one NCCL all-to-all) and gathers it onto device 0 at the end.
+    int load_from_fastx_list(const std::vector<std::string> &paths, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span, int n_readers, int n_gpus,
+                             const std::vector<int> &devices = {});   // devices: one per shard (may repeat: sharded build on one GPU, a test set-up)
+    // wall seconds per phase of the calls above and of the writers (for the CLI's --timing report)
+    struct Timing { double wait_parse_s = 0, gpu_index_s = 0, merge_s = 0, frag_gpu_s = 0, frag_encode_s = 0, mdb_write_s = 0, reader_read_s = 0, reader_parse_s = 0, reader_pin_s = 0; uint64_t bases = 0; };
+    const Timing &timing() const { return timing_; }
     // ext.rs:212-250 load_from_seq_list: sequences given in memory, sids in list order
     int load_from_seq_list(const std::vector<SeqRec> &seq_list, const std::string &source, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span);
     // index part of ext.rs:87-150 (load_from_agc_index / load_from_frg_index): <prefix>.mdb + <prefix>.midx; sequences are
@@ -85,10 +94,16 @@ public:
 private:
     int load_seqs_from_fastx(const std::string &path);
     int add_records(std::vector<SeqRec> &recs, const std::string &source);
+    int add_parsed(std::vector<std::unique_ptr<ParsedFile>> &files);
+    void reset();
     pgr_b200_index *idx_ = nullptr;
+    pgr_b200_mindex *midx_ = nullptr;   // multi-GPU build in progress
     pgr_shmmr_spec spec_{};
     std::vector<CompactSeq> seqs_;
-    std::vector<std::vector<uint8_t>> seq_data_;
+    std::vector<SeqSpan> seq_data_;                       // views of the sequences (FASTX back end) ...
+    std::vector<std::unique_ptr<FileBuf>> file_bufs_;     // ... into the page-locked file buffers they were parsed in
+    std::vector<std::vector<uint8_t>> owned_seqs_;        // ... or into these (load_from_seq_list)
+    Timing timing_;
     bool keep_seqs_ = false;
     bool fastx_backend_ = false;   // created by load_from_fastx / load_from_seq_list: the only back end append_from_fastx accepts (ext.rs:180-199)
     FragStore frag_store_;

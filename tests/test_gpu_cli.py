@@ -280,3 +280,64 @@ def test_query_cli_frg_backend_and_reference_fragment_store(tmp_path):
             assert hdr == ">" + r[11] and seq.encode() == (qpo.reverse_complement(sub) if ori else sub)
             n_checked += 1
     assert n_checked >= 20
+
+
+def test_make_frgdb_cli_sharded_pipeline_same_files(tmp_path):
+    """--devices 0,0,0 (the multi-GPU build with three shards on one device), several readers, plain and .gz inputs, a FASTQ:
+    every output file equals the single-GPU run's byte for byte (.frg: same inflated payloads), --index-only writes the same
+    .mdb/.midx and no store, --timing prints one JSON line"""
+    import gzip
+    import json
+    import numpy as np
+    if not os.path.exists(CLI):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "pgr_tk_b200", "host")])
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    anc = acgt[rng.integers(0, 4, size=150_000)]
+    paths = []
+    for i in range(7):
+        s = anc.copy()
+        m = rng.random(len(s)) < 0.004
+        s[m] = acgt[rng.integers(0, 4, size=int(m.sum()))]
+        recs = b""
+        for j in range(int(rng.integers(1, 4))):
+            a = int(rng.integers(0, 40_000))
+            part = s[a:a + int(rng.integers(30_000, 100_000))].tobytes()
+            recs += b">h%d_c%d sample\n" % (i, j) + b"\n".join(part[q:q + 70] for q in range(0, len(part), 70)) + b"\n"
+        p = str(tmp_path / ("h%d.fa" % i)) + (".gz" if i % 2 else "")
+        if p.endswith(".gz"):
+            with gzip.open(p, "wb") as f:
+                f.write(recs)
+        else:
+            open(p, "wb").write(recs)
+        paths.append(p)
+    fq = str(tmp_path / "reads.fq")
+    open(fq, "wb").write(b"".join(b"@r%d\n%s\n+\n%s\n" % (i, anc[i * 9000:i * 9000 + 8000].tobytes(), b"I" * 8000) for i in range(4)))
+    paths.insert(3, fq)
+    fl = tmp_path / "files.txt"
+    fl.write_text("\n".join(paths) + "\n")
+    one, sh, io = str(tmp_path / "one"), str(tmp_path / "sharded"), str(tmp_path / "indexonly")
+    subprocess.check_call([CLI, str(fl), one, "--readers", "1"], cwd=ROOT)
+    r = subprocess.run([CLI, str(fl), sh, "--devices", "0,0,0", "--readers", "4", "--timing"], cwd=ROOT, capture_output=True, text=True, check=True)
+    t = json.loads(r.stderr.strip().splitlines()[-1])
+    assert t["files"] == 8 and t["gpus"] == 3 and t["bases"] > 0 and t["wall_s"] > 0
+    subprocess.check_call([CLI, str(fl), io, "--index-only"], cwd=ROOT)
+    for ext in (".mdb", ".midx", ".sdx"):
+        assert open(one + ext, "rb").read() == open(sh + ext, "rb").read(), ext
+    assert open(one + ".frg", "rb").read() == open(sh + ".frg", "rb").read()
+    assert open(io + ".mdb", "rb").read() == open(one + ".mdb", "rb").read() and open(io + ".midx", "rb").read() == open(one + ".midx", "rb").read()
+    assert not os.path.exists(io + ".frg") and not os.path.exists(io + ".sdx")
+    # against the oracle: same records (the reference's FASTQ reader does not yield the last record of the file), same map
+    sys_path = os.path.join(ROOT, "oracle")
+    import sys
+    sys.path.insert(0, sys_path)
+    import fastx_oracle as fo
+    recs = []
+    for p in paths:
+        buf = gzip.open(p, "rb").read() if p.endswith(".gz") else open(p, "rb").read()
+        recs += fo.parse_fastx(buf)
+    assert len(recs) == len(open(one + ".midx").read().splitlines())
+    o = orc.Index(orc.mkspec(), 0)
+    o.add_batch(list(range(len(recs))), [s for _, s in recs])
+    o.write_mdb(str(tmp_path / "o.mdb"))
+    assert open(one + ".mdb", "rb").read() == open(tmp_path / "o.mdb", "rb").read()

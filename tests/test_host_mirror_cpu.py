@@ -43,7 +43,7 @@ def test_fasta_reader_and_frag_store_on_the_reference_fixture(tmp_path):
     src.write_text(PROG)
     exe = str(tmp_path / "t")
     libdir = os.path.dirname(pg.library_path())
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", HOST, "-o", exe, str(src), os.path.join(HOST, "seq_index_db.cpp"),
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", HOST, "-o", exe, str(src), os.path.join(HOST, "seq_index_db.cpp"), os.path.join(HOST, "fastx_ingest.cpp"), "-pthread",
                            "-L" + libdir, "-lpgr_b200", "-lz", "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe, os.path.join(GOLDEN, "test_seqs.fa"), os.path.join(GOLDEN, "test_seqs_frag")]).decode().split()
     assert out == ["66", "66"]
@@ -62,11 +62,11 @@ int main(int argc, char **argv) {
     std::string err;
     if (!read_fastx(argv[1], recs, err)) return 2;
     std::vector<uint32_t> sids; std::vector<const uint8_t *> ptrs; std::vector<size_t> lens;
-    std::vector<CompactSeq> seqs; std::vector<std::vector<uint8_t>> data;
+    std::vector<CompactSeq> seqs; std::vector<SeqSpan> data;
     for (size_t i = 0; i < recs.size(); i++) {
         sids.push_back((uint32_t)i); ptrs.push_back(recs[i].seq.data()); lens.push_back(recs[i].seq.size());
         CompactSeq cs; cs.id = (uint32_t)i; cs.len = recs[i].seq.size(); cs.name = recs[i].id; cs.source = "test_seqs.fa";
-        seqs.push_back(cs); data.push_back(recs[i].seq);
+        seqs.push_back(cs); SeqSpan sp; sp.p = recs[i].seq.data(); sp.len = recs[i].seq.size(); data.push_back(sp);
     }
     pgr_shmmr_spec sp{80, 56, 4, 64, 0};
     pgr_fragment *fr = nullptr; pgr_aln_seg *sg = nullptr; size_t nf = 0, ns = 0;
@@ -93,7 +93,7 @@ def test_frag_store_writer_reproduces_the_reference_store(tmp_path):
     src.write_text(WPROG)
     exe = str(tmp_path / "w")
     libdir, odir = os.path.dirname(pg.library_path()), os.path.join(ROOT, "oracle")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", HOST, "-o", exe, str(src), os.path.join(HOST, "seq_index_db.cpp"),
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", HOST, "-o", exe, str(src), os.path.join(HOST, "seq_index_db.cpp"), os.path.join(HOST, "fastx_ingest.cpp"), "-pthread",
                            "-L" + libdir, "-lpgr_b200", "-L" + odir, "-lpgr_oracle", "-lz", "-Wl,-rpath," + libdir, "-Wl,-rpath," + odir])
     prefix = str(tmp_path / "st")
     out = subprocess.check_output([exe, os.path.join(GOLDEN, "test_seqs.fa"), prefix]).decode().split()
