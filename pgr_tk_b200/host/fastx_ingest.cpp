@@ -16,20 +16,70 @@ namespace pgrb200 {
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 FileBuf::~FileBuf() {
-    if (pinned) pgr_b200_host_unregister(p);
-    free(p);
+    if (!p) return;
+    if (pool) pool->give_back(p, cap, pinned);
+    else if (pinned) pgr_b200_host_free(p);
+    else free(p);
 }
 
+PinnedPool::~PinnedPool() {
+    for (auto &it : free_) { if (in_slab(it.p)) continue; if (it.pinned) pgr_b200_host_free(it.p); else free(it.p); }
+    if (slab_) pgr_b200_host_free(slab_);
+}
+
+void PinnedPool::reserve(size_t n, size_t bytes) {
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    if (!n || !bytes || slab_) return;
+    slab_ = (uint8_t *)pgr_b200_host_alloc(n * bytes);
+    if (!slab_) return;                               // no device / no memory: acquire() falls back to single allocations
+    slab_bytes_ = n * bytes;
+    std::lock_guard<std::mutex> lk(mu_);
+    for (size_t i = 0; i < n; i++) free_.push_back({slab_ + i * bytes, bytes, true});
+}
+
+void PinnedPool::give_back(uint8_t *p, size_t cap, bool pinned) {
+    std::lock_guard<std::mutex> lk(mu_);
+    free_.push_back({p, cap, pinned});
+}
+
+void PinnedPool::acquire(FileBuf &b, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        int best = -1;
+        for (size_t i = 0; i < free_.size(); i++)
+            if (free_[i].cap >= bytes && (best < 0 || free_[i].cap < free_[best].cap)) best = (int)i;
+        if (best < 0 && !free_.empty()) {            // none is large enough: retire the smallest, allocate a larger one below
+            size_t sm = 0;
+            for (size_t i = 1; i < free_.size(); i++) if (free_[i].cap < free_[sm].cap) sm = i;
+            if (!in_slab(free_[sm].p)) {
+                if (free_[sm].pinned) pgr_b200_host_free(free_[sm].p); else free(free_[sm].p);
+                free_.erase(free_.begin() + (ptrdiff_t)sm);
+            }
+        }
+        if (best >= 0) {
+            b.p = free_[best].p; b.cap = free_[best].cap; b.pinned = free_[best].pinned; b.pool = this; b.size = 0;
+            free_.erase(free_.begin() + best);
+            return;
+        }
+    }
+    const size_t cap = ((bytes + bytes / 8 + (1u << 20)) + 4095) & ~(size_t)4095;
+    void *np = pgr_b200_host_alloc(cap);
+    b.pinned = np != nullptr;
+    if (!np && posix_memalign(&np, 4096, cap) != 0) np = nullptr;   // no device (CPU tests): plain memory
+    b.p = (uint8_t *)np; b.cap = np ? cap : 0; b.pool = this; b.size = 0;
+}
+
+// make room for `need` bytes, keeping the first b.size bytes
 static bool grow(FileBuf &b, size_t need) {
     if (need <= b.cap) return true;
-    size_t ncap = std::max(need, b.cap * 2);
-    ncap = (ncap + 4095) & ~(size_t)4095;
-    void *np = nullptr;
-    if (posix_memalign(&np, 4096, ncap) != 0) return false;
-    if (b.size) memcpy(np, b.p, b.size);
-    free(b.p);
-    b.p = (uint8_t *)np; b.cap = ncap;
-    return true;
+    const size_t ncap = ((std::max(need, b.cap * 2)) + 4095) & ~(size_t)4095;
+    FileBuf nb;
+    if (b.pool) b.pool->acquire(nb, ncap);
+    else { void *np = nullptr; if (posix_memalign(&np, 4096, ncap) == 0) { nb.p = (uint8_t *)np; nb.cap = ncap; } }
+    if (!nb.p) return false;
+    if (b.size) memcpy(nb.p, b.p, b.size);
+    std::swap(b.p, nb.p); std::swap(b.cap, nb.cap); std::swap(b.pinned, nb.pinned); std::swap(b.pool, nb.pool);
+    return true;                                                     // nb's destructor disposes of the old block
 }
 
 // whole file into a page-aligned buffer; gzip members are inflated (zlib reads plain files as-is, but read(2) is faster)
@@ -146,10 +196,11 @@ static void parse_fastq(FileBuf &b, ParsedFile &out) {
     }
 }
 
-void parse_fastx_file(const std::string &path, bool pin, ParsedFile &out) {
+void parse_fastx_file(const std::string &path, IngestMode mode, PinnedPool *pool, ParsedFile &out) {
     out.path = path;
     out.ok = false;
     out.buf.reset(new FileBuf());
+    if (mode == INGEST_PINNED && pool) out.buf->pool = pool;            // grow() then draws page-locked blocks from the pool
     double t0 = now_s();
     if (!read_whole(path, *out.buf, out.err)) return;
     double t1 = now_s();
@@ -158,20 +209,43 @@ void parse_fastx_file(const std::string &path, bool pin, ParsedFile &out) {
     if (out.buf->p[0] == '@') parse_fastq(*out.buf, out); else parse_fasta(*out.buf, out);
     double t2 = now_s();
     out.parse_s = t2 - t1;
-    if (pin && out.bases) {
-        // page-lock what holds sequence bytes now (the compacted front of the buffer)
-        const uint8_t *last = out.seqs.empty() ? out.buf->p : out.seqs.back().p + out.seqs.back().len;
-        const size_t bytes = ((size_t)(last - out.buf->p) + 4095) & ~(size_t)4095;
-        if (pgr_b200_host_register(out.buf->p, std::min(bytes, out.buf->cap)) == PGR_OK) out.buf->pinned = true;   // failure only costs speed
+    if (mode == INGEST_KEEP && pool && out.bases) {
+        // the caller keeps the pageable bytes; the GPU call reads a compact page-locked copy that goes back to the pool
+        out.gpu_buf.reset(new FileBuf());
+        pool->acquire(*out.gpu_buf, out.bases + 64);
+        if (out.gpu_buf->p) {
+            size_t off = 0;
+            for (auto &sp : out.seqs) {
+                memcpy(out.gpu_buf->p + off, sp.p, sp.len);
+                SeqSpan g; g.p = out.gpu_buf->p + off; g.len = sp.len;
+                out.gpu_seqs.push_back(g);
+                off += sp.len;
+            }
+        } else {
+            out.gpu_buf.reset();
+        }
     }
     out.pin_s = now_s() - t2;
     out.ok = true;
 }
 
-FastxPipeline::FastxPipeline(std::vector<std::string> paths, int n_readers, bool pin, size_t window)
-    : paths_(std::move(paths)), pin_(pin), window_(window ? window : (size_t)std::max(2, n_readers) * 2) {
+FastxPipeline::FastxPipeline(std::vector<std::string> paths, int n_readers, IngestMode mode, size_t window)
+    : paths_(std::move(paths)), mode_(mode), window_(window ? window : (size_t)std::max(2, n_readers) + 4) {
     slot_.resize(paths_.size());
     done_.assign(paths_.size(), 0);
+    if (mode_ != INGEST_PLAIN) {
+        // page-locked slots for the files in flight, sized for the largest file (gzip: its inflated size is a guess, a
+        // slot that turns out too small is replaced on the fly)
+        size_t mx = 0;
+        for (auto &p : paths_) {
+            struct stat st;
+            if (stat(p.c_str(), &st) == 0) {
+                const bool gz = p.size() > 3 && p.compare(p.size() - 3, 3, ".gz") == 0;
+                mx = std::max(mx, (size_t)st.st_size * (gz ? 4 : 1));
+            }
+        }
+        pool_.reserve(std::min(paths_.size(), window_), mx + (1u << 16));   // files parsed-and-waiting plus files being parsed <= window
+    }
     n_readers = std::max(1, std::min<int>(n_readers, (int)std::max<size_t>(1, paths_.size())));
     for (int i = 0; i < n_readers; i++) threads_.emplace_back([this] { worker(); });
 }
@@ -192,7 +266,7 @@ void FastxPipeline::worker() {
             i = next_claim_++;
         }
         std::unique_ptr<ParsedFile> pf(new ParsedFile());
-        parse_fastx_file(paths_[i], pin_, *pf);
+        parse_fastx_file(paths_[i], mode_, &pool_, *pf);
         {
             std::lock_guard<std::mutex> lk(mu_);
             slot_[i] = std::move(pf);

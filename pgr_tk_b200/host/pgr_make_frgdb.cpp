@@ -59,6 +59,7 @@ int main(int argc, char **argv) {
         else if (prefix.empty()) prefix = a;
         else { fprintf(stderr, "error: unexpected argument %s\n", a.c_str()); return 2; }
     }
+    if (!devices.empty()) n_gpus = (int)devices.size();
     if (filelist.empty() || prefix.empty()) { fprintf(stderr, "usage: pgr-b200-make-frgdb <filelist> <prefix> [-w 80] [-k 56] [-r 4] [--min-span 64]\n"); return 2; }
     std::ifstream in(filelist);
     if (!in) { fprintf(stderr, "can't open the input file that contains the paths to the fastx files\n"); return 1; }

@@ -15,7 +15,7 @@ namespace pgrb200 {
 // fasta_io.rs:46-172 (the parsing itself: fastx_ingest.cpp)
 bool read_fastx(const std::string &path, std::vector<SeqRec> &out, std::string &err) {
     ParsedFile pf;
-    parse_fastx_file(path, false, pf);
+    parse_fastx_file(path, INGEST_PLAIN, nullptr, pf);
     if (!pf.ok) { err = pf.err; return false; }
     for (size_t i = 0; i < pf.seqs.size(); i++) {
         SeqRec r;
@@ -58,7 +58,7 @@ int SeqIndexDB::append_from_fastx(const std::string &path) {
 int SeqIndexDB::load_seqs_from_fastx(const std::string &path) {
     std::vector<std::unique_ptr<ParsedFile>> one;
     one.emplace_back(new ParsedFile());
-    parse_fastx_file(path, true, *one[0]);
+    parse_fastx_file(path, INGEST_PLAIN, nullptr, *one[0]);
     if (!one[0]->ok) { err_ = one[0]->err; return PGR_E_IO; }
     return add_parsed(one);
 }
@@ -73,7 +73,7 @@ int SeqIndexDB::add_parsed(std::vector<std::unique_ptr<ParsedFile>> &files) {
     for (auto &f : files) {
         for (size_t i = 0; i < f->seqs.size(); i++) {
             sids.push_back(sid);
-            ptrs.push_back(f->seqs[i].p);
+            ptrs.push_back(f->gpu_seqs.empty() ? f->seqs[i].p : f->gpu_seqs[i].p);   // the page-locked copy when there is one
             lens.push_back(f->seqs[i].len);
             CompactSeq cs;
             cs.id = sid; cs.len = f->seqs[i].len; cs.name = f->ids[i]; cs.source = f->path;
@@ -88,7 +88,7 @@ int SeqIndexDB::add_parsed(std::vector<std::unique_ptr<ParsedFile>> &files) {
                          : pgr_b200_index_add_batch(idx_, sids.size(), sids.data(), ptrs.data(), lens.data());
     timing_.gpu_index_s += now_s() - t0;
     if (rc != PGR_OK) err_ = pgr_b200_last_error();
-    for (auto &f : files) { if (keep_seqs_) file_bufs_.push_back(std::move(f->buf)); }
+    for (auto &f : files) { f->gpu_buf.reset(); if (keep_seqs_) file_bufs_.push_back(std::move(f->buf)); }
     return rc;
 }
 
@@ -107,10 +107,10 @@ int SeqIndexDB::load_from_fastx_list(const std::vector<std::string> &paths, uint
         if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
     }
     fastx_backend_ = true;
-    FastxPipeline pipe(paths, n_readers, true);
+    FastxPipeline pipe(paths, n_readers, keep_seqs_ ? INGEST_KEEP : INGEST_PINNED);
     // a batch = the files that are parsed by now (at least one); with several GPUs at least a few files per call so that every
     // GPU has a block of the batch to work on
-    const size_t max_batch = (size_t)std::max(8, 4 * std::max(1, n_gpus));
+    const size_t max_batch = (size_t)std::max(4, 2 * std::max(1, n_gpus));   // page-locked slots are scarce: window = readers + 4
     size_t i = 0;
     while (i < paths.size()) {
         std::vector<std::unique_ptr<ParsedFile>> batch;

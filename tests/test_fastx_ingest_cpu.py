@@ -27,7 +27,7 @@ using namespace pgrb200;
 int main(int argc, char **argv) {
     std::vector<std::string> paths;
     for (int i = 2; i < argc; i++) paths.push_back(argv[i]);
-    FastxPipeline pipe(paths, atoi(argv[1]), false);
+    FastxPipeline pipe(paths, atoi(argv[1]), argc > 2 && argv[1][0] == '4' ? INGEST_KEEP : INGEST_PINNED);
     for (size_t i = 0; i < paths.size(); i++) {
         auto pf = pipe.take(i);
         if (!pf->ok) { printf("E %s\n", pf->err.c_str()); continue; }
