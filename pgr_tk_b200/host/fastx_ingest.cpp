@@ -244,7 +244,7 @@ FastxPipeline::FastxPipeline(std::vector<std::string> paths, int n_readers, Inge
                 mx = std::max(mx, (size_t)st.st_size * (gz ? 4 : 1));
             }
         }
-        pool_.reserve(std::min(paths_.size(), window_), mx + (1u << 16));   // files parsed-and-waiting plus files being parsed <= window
+        pool_.reserve(std::min(paths_.size(), window_ + 4), mx + (1u << 16));   // files in flight (<= window) + the consumer's current batch (<= 4 per GPU pair)
     }
     n_readers = std::max(1, std::min<int>(n_readers, (int)std::max<size_t>(1, paths_.size())));
     for (int i = 0; i < n_readers; i++) threads_.emplace_back([this] { worker(); });
