@@ -249,6 +249,13 @@ int pgr_b200_sparse_aln(pgr_hit_pair *hits, size_t n, uint32_t max_span, float p
 int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *keeps, size_t n_keeps, int has_keeps, pgr_adj_pair **out,
                       size_t *n_out);
 
+/* replaces seq_db::generate_smp_adj_list_for_seq(&seq, sid, &frag_map, &spec, min_count) -> AdjList (seq_db.rs:946-1000) for a
+ * batch of sequences — SeqIndexDB::generate_mapg_gfa runs it over every sequence of the database when method != "from_fragmap"
+ * (ext.rs:696-722), with min_count 0 for the sequences in `keeps`: pass that per sequence in min_counts[].  The result is the
+ * per-sequence lists concatenated in the order given (the reference concatenates in hash-map order of seq_info: unpinned). */
+int pgr_b200_smp_adj_list_for_seqs(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
+                                   const uint64_t *min_counts, pgr_adj_pair **out, size_t *n_out);
+
 /* ---- fragment compression (the .frg/.sdx content of pgr-make-frgdb) --------------------------------------------- */
 /* replaces the alignment branch of CompactSeqDB::seq_to_compressed (seq_db.rs:189-358; shmmrutils::match_reads
  * shmmrutils.rs:57-223, deltas_to_aln_segs seq_db.rs:113-156) for every sequence of a FASTX-mode index: the caller passes the

@@ -170,6 +170,7 @@ def lib():
         L.pgr_b200_query_result_free.argtypes = [P(QueryResult)]
         L.pgr_b200_sparse_aln.argtypes = [vp, sz, u32, C.c_float, C.c_int64, C.c_int, P(sz), P(vp), P(vp), P(vp)]
         L.pgr_b200_adj_list.argtypes = [vp, sz, vp, sz, C.c_int, P(vp), P(sz)]
+        L.pgr_b200_smp_adj_list_for_seqs.argtypes = [vp, sz, vp, vp, vp, vp, P(vp), P(sz)]
         L.pgr_b200_index_compress_fragments.argtypes = [vp, sz, vp, vp, vp, P(vp), P(sz), P(vp), P(sz)]
         L.pgr_b200_sort_adj_list_by_weighted_dfs.argtypes = [vp, vp, sz, vp, P(vp), P(sz)]
         L.pgr_b200_principal_bundles.argtypes = [vp, vp, sz, sz, P(vp), P(vp), P(sz), P(vp), P(sz)]
@@ -492,6 +493,16 @@ class ShmmrIndex:
         k = np.ascontiguousarray(keeps if keeps is not None else [], dtype=np.uint32)
         out, n = C.c_void_p(), C.c_size_t()
         _check(lib().pgr_b200_adj_list(self.h, min_count, k.ctypes.data, k.size, int(keeps is not None), C.byref(out), C.byref(n)))
+        return _take(out, n.value, ADJ)
+
+    def smp_adj_list_for_seqs(self, sids, seqs, min_counts):
+        """generate_smp_adj_list_for_seq (seq_db.rs:946-1000) for every (sid, seq, min_count) -> ADJ[...] in the order given"""
+        keep, ptrs, lens = _seq_arrays(seqs)
+        sid_a = np.ascontiguousarray(sids, dtype=np.uint32)
+        mc = np.ascontiguousarray(min_counts, dtype=np.uint64)
+        out, n = C.c_void_p(), C.c_size_t()
+        _check(lib().pgr_b200_smp_adj_list_for_seqs(self.h, len(keep), sid_a.ctypes.data, ptrs, lens, mc.ctypes.data, C.byref(out), C.byref(n)))
+        del keep
         return _take(out, n.value, ADJ)
 
     def compress_fragments(self, sids, seqs):

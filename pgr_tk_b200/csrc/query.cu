@@ -181,15 +181,39 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
                                                  idx->q_hit_count.as<uint32_t>(), idx->sid_count.as<uint32_t>(), idx->sigs.as<pgr_frag_sig>(), f,
                                                  idx->scratch2.as<uint64_t>(), idx->hitsA.as<HitRec>(), idx->keysA.as<SortKey>());
             const uint32_t gh = (uint32_t)ceil_div<uint64_t>(n_hits, 256);
-            iota_kernel<<<gh, 256, 0, st>>>(idx->idxA.as<uint32_t>(), n_hits);
-            idx->launches += 2;
+            idx->launches += 1;
             trace_mark("query_batch: filters+expand");
-            // stable sort by (qid, sid): bytes 0..3 of k1 (sid) then bytes 0..3 of k0 (qid)
-            PGR_TRY(index_sort(idx, n_hits, 0, 3));
-            PGR_TRY(index_sort(idx, n_hits, 7, 10));
             PGR_TRY(idx->head.ensure(n_hits));
-            hit_gather_kernel<<<gh, 256, 0, st>>>(idx->hitsA.as<HitRec>(), idx->keysA.as<SortKey>(), idx->idxA.as<uint32_t>(), n_hits,
-                                                  idx->hitsB.as<HitRec>(), idx->head.as<uint8_t>());
+            // The hits come out query by query (pairs of a query are contiguous, expansion keeps their order): what is left is
+            // a stable sort by target sid inside every query.  One CTA per query does it in shared memory; a batch with a
+            // query of more than QS_CAP hits takes the global radix sort instead.
+            PGR_TRY(idx->scratch3.ensure((n_q + 1) * sizeof(uint64_t)));
+            uint64_t *hq_off = idx->scratch3.as<uint64_t>();
+            hit_query_offsets_kernel<<<(uint32_t)ceil_div<uint64_t>(n_q + 1, 256), 256, 0, st>>>(idx->scratch0.as<uint64_t>(), idx->scratch2.as<uint64_t>(), n_q, hq_off);
+            std::vector<uint64_t> h_hq(n_q + 1);
+            PGR_CUDA(cudaMemcpyAsync(h_hq.data(), hq_off, (n_q + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            PGR_CUDA(cudaStreamSynchronize(st));
+            uint64_t max_q_hits = 0;
+            for (size_t q = 0; q < n_q; q++) max_q_hits = std::max(max_q_hits, h_hq[q + 1] - h_hq[q]);
+            static const bool force_global_sort = getenv("PGR_B200_QUERY_GLOBAL_SORT") != nullptr;   // A/B aid
+            if (max_q_hits <= QS_CAP && !force_global_sort) {
+                uint32_t m = 1;
+                while (m < max_q_hits) m <<= 1;
+                static bool attr_set = false;
+                if (!attr_set) { PGR_CUDA(cudaFuncSetAttribute(query_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QS_CAP * 8)); attr_set = true; }
+                query_sort_kernel<<<(uint32_t)n_q, QS_NT, (size_t)m * 8, st>>>(idx->hitsA.as<HitRec>(), hq_off, idx->hitsB.as<HitRec>(), idx->head.as<uint8_t>());
+                hit_keys_kernel<<<gh, 256, 0, st>>>(idx->hitsB.as<HitRec>(), n_hits, idx->keysA.as<SortKey>());
+                idx->launches += 3;
+                PGR_CUDA(cudaGetLastError());
+            } else {
+                iota_kernel<<<gh, 256, 0, st>>>(idx->idxA.as<uint32_t>(), n_hits);
+                // stable sort by (qid, sid): bytes 0..3 of k1 (sid) then bytes 0..3 of k0 (qid)
+                PGR_TRY(index_sort(idx, n_hits, 0, 3));
+                PGR_TRY(index_sort(idx, n_hits, 7, 10));
+                hit_gather_kernel<<<gh, 256, 0, st>>>(idx->hitsA.as<HitRec>(), idx->keysA.as<SortKey>(), idx->idxA.as<uint32_t>(), n_hits,
+                                                      idx->hitsB.as<HitRec>(), idx->head.as<uint8_t>());
+                idx->launches += 2;
+            }
             // segments = runs of equal (qid, sid)
             const uint32_t nb = (uint32_t)ceil_div<uint64_t>(n_hits, CS_BLK);
             PGR_TRY(idx->block_sum.ensure(nb * sizeof(uint32_t)));
@@ -221,8 +245,17 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
             cp.best_pre = (int32_t *)u; cp.cls_first = u + n_hits; cp.cls_last = u + 2 * n_hits; cp.order = u + 3 * n_hits; cp.out_idx = u + 4 * n_hits;
             cp.visited = idx->chain_b.as<uint8_t>(); cp.out_start = cp.visited + n_hits;
             cp.seg_n_out = idx->chain_seg.as<uint32_t>(); cp.seg_n_chains = cp.seg_n_out + n_seg; cp.seg_err = cp.seg_n_out + 2 * n_seg;
-            chain_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 64), 64, 0, st>>>(cp);
-            idx->launches += 1;
+            // segments of up to CH_CAP hits (nearly all): one warp each, staged in shared memory; larger ones: one thread each
+            static const bool chain_unstaged = getenv("PGR_B200_CHAIN_UNSTAGED") != nullptr;   // A/B aid
+            if (chain_unstaged) {
+                chain_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 64), 64, 0, st>>>(cp, 0u);
+            } else {
+                static bool ch_attr = false;
+                if (!ch_attr) { PGR_CUDA(cudaFuncSetAttribute(chain_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CH_WARPS * sizeof(ChainSmem)))); ch_attr = true; }
+                chain_staged_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, CH_WARPS), CH_WARPS * 32, CH_WARPS * sizeof(ChainSmem), st>>>(cp);
+                chain_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 64), 64, 0, st>>>(cp, (uint32_t)CH_CAP);
+            }
+            idx->launches += 2;
             PGR_CUDA(cudaGetLastError());
             trace_mark("query_batch: chain kernel");
             // nested result arrays on the device, then one D2H per array into (pinned) result buffers
@@ -336,7 +369,7 @@ int pgr_b200_sparse_aln(pgr_hit_pair *hits, size_t n, uint32_t max_span, float p
     cp.best_pre = (int32_t *)u; cp.cls_first = u + n; cp.cls_last = u + 2 * n; cp.order = u + 3 * n; cp.out_idx = u + 4 * n;
     cp.visited = d_b.as<uint8_t>(); cp.out_start = cp.visited + n;
     cp.seg_n_out = d_meta; cp.seg_n_chains = d_meta + 1; cp.seg_err = d_meta + 2;
-    chain_kernel<<<1, 64, 0, st>>>(cp);
+    chain_kernel<<<1, 64, 0, st>>>(cp, 0u);
     std::vector<uint32_t> out_idx(n);
     std::vector<uint8_t> out_start(n);
     std::vector<float> out_score(n);
@@ -414,6 +447,46 @@ int pgr_b200_adj_list(pgr_b200_index *idx, size_t min_count, const uint32_t *kee
     PGR_CUDA(cudaStreamSynchronize(st));
     *n_out = total;
     trace_mark("adj_list: join + D2H");
+    return PGR_OK;
+}
+
+// replaces seq_db::generate_smp_adj_list_for_seq(&seq, sid, &frag_map, &spec, min_count) -> AdjList for a batch of sequences
+int pgr_b200_smp_adj_list_for_seqs(pgr_b200_index *idx, size_t n, const uint32_t *sids, const uint8_t *const *seqs, const size_t *lens,
+                                   const uint64_t *min_counts, pgr_adj_pair **out, size_t *n_out) {
+    if (!idx || !out || !n_out || (n && (!sids || !seqs || !lens || !min_counts))) { set_error("NULL argument"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(idx->ctx->device));
+    cudaStream_t st = idx->ctx->stream;
+    *out = (pgr_adj_pair *)result_alloc(sizeof(pgr_adj_pair));
+    *n_out = 0;
+    uint64_t n_qp = 0;
+    std::vector<uint64_t> qp_off;
+    PGR_TRY(query_pairs_and_lookup(idx, n, seqs, lens, &n_qp, &qp_off));   // pairs with the strict '<' rule (seq_db.rs:962-966), key counts
+    if (n_qp < 2) return PGR_OK;
+    PGR_TRY(idx->scratch0.ensure((n + 1) * sizeof(uint64_t) + n * sizeof(uint64_t) + n * sizeof(uint32_t)));
+    uint64_t *d_qoff = idx->scratch0.as<uint64_t>(), *d_mc = d_qoff + (n + 1);
+    uint32_t *d_sids = (uint32_t *)(d_mc + n);
+    PGR_CUDA(cudaMemcpyAsync(d_qoff, qp_off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGR_CUDA(cudaMemcpyAsync(d_mc, min_counts, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGR_CUDA(cudaMemcpyAsync(d_sids, sids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    PGR_TRY(idx->scratch1.ensure(n_qp * sizeof(uint32_t)));
+    PGR_TRY(idx->scratch2.ensure((n_qp + 1) * sizeof(uint64_t)));
+    const uint32_t g = (uint32_t)ceil_div<uint64_t>(n_qp, 256);
+    smp_adj_flag_kernel<<<g, 256, 0, st>>>(idx->qtuples.as<FragTuple>(), n_qp, d_qoff, idx->q_hit_count.as<uint32_t>(), d_mc, idx->scratch1.as<uint32_t>());
+    uint64_t total = 0;
+    PGR_TRY(scan_u32(idx, idx->scratch1.as<uint32_t>(), n_qp, idx->scratch2.as<uint64_t>(), &total));
+    idx->launches += 1;
+    if (total == 0) return PGR_OK;
+    PGR_TRY(idx->scratch3.ensure(2 * total * sizeof(pgr_adj_pair)));
+    smp_adj_emit_kernel<<<g, 256, 0, st>>>(idx->qtuples.as<FragTuple>(), n_qp, idx->scratch1.as<uint32_t>(), idx->scratch2.as<uint64_t>(), d_sids,
+                                           idx->scratch3.as<pgr_adj_pair>());
+    idx->launches += 1;
+    PGR_CUDA(cudaGetLastError());
+    result_free(*out);
+    *out = (pgr_adj_pair *)result_alloc(2 * total * sizeof(pgr_adj_pair));
+    if (!*out) { set_error("out of host memory"); return PGR_E_ARG; }
+    PGR_CUDA(cudaMemcpyAsync(*out, idx->scratch3.p, 2 * total * sizeof(pgr_adj_pair), cudaMemcpyDeviceToHost, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    *n_out = 2 * total;
     return PGR_OK;
 }
 

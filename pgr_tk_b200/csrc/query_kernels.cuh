@@ -131,6 +131,80 @@ __global__ void hit_gather_kernel(const HitRec *in, const SortKey *keys, const u
     head[i] = (i == 0 || keys[i].k0 != keys[i - 1].k0 || keys[i].k1 != keys[i - 1].k1) ? 1 : 0;
 }
 
+// ---- generate_smp_adj_list_for_seq (seq_db.rs:946-1000), all sequences of a batch at once ---------------------------------
+// pair i of a sequence and its successor w give two entries iff both keys are in the map with at least min_count signatures
+// and v.end == w.bgn
+__global__ void smp_adj_flag_kernel(const FragTuple *qt, uint64_t n_qp, const uint64_t *qp_off, const uint32_t *hit_cnt, const uint64_t *min_count,
+                                    uint32_t *flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_qp) return;
+    const uint32_t q = qt[i].sid;   // ordinal of the sequence in the batch
+    uint32_t f = 0;
+    if (i + 1 < qp_off[q + 1]) {
+        const uint64_t mc = min_count[q];
+        const uint32_t cv = hit_cnt[i], cw = hit_cnt[i + 1];
+        f = (cv > 0 && cw > 0 && cv >= mc && cw >= mc && qt[i].end == qt[i + 1].bgn) ? 1u : 0u;
+    }
+    flag[i] = f;
+}
+__global__ void smp_adj_emit_kernel(const FragTuple *qt, uint64_t n_qp, const uint32_t *flag, const uint64_t *rank, const uint32_t *sids, pgr_adj_pair *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_qp || !flag[i]) return;
+    const FragTuple v = qt[i], w = qt[i + 1];
+    pgr_adj_pair a, b;
+    a.sid = b.sid = sids[v.sid];
+    a.pad_[0] = a.pad_[1] = b.pad_[0] = b.pad_[1] = 0;
+    a.a0 = v.h0; a.a1 = v.h1; a.ori0 = (uint8_t)v.ori; a.b0 = w.h0; a.b1 = w.h1; a.ori1 = (uint8_t)w.ori;
+    b.a0 = w.h0; b.a1 = w.h1; b.ori0 = (uint8_t)(1u - w.ori); b.b0 = v.h0; b.b1 = v.h1; b.ori1 = (uint8_t)(1u - v.ori);
+    out[2 * rank[i]] = a;
+    out[2 * rank[i] + 1] = b;
+}
+
+// ---- hits of one query -> stable order by target sid (aln.rs:213-228 builds one list per target in query-pair order) --------
+// The hits of a batch are generated query by query; only the order by sid INSIDE a query is missing.  One CTA per query:
+// (sid, position in the query's hit list) keys are sorted in shared memory (bitonic on 64-bit keys: position as the minor key
+// makes it stable) and the 32-byte records are moved once.  A global LSD radix sort of the same data takes 8 passes.
+constexpr int QS_NT = 256, QS_CAP = 8192;
+__global__ void hit_query_offsets_kernel(const uint64_t *qp_off, const uint64_t *hit_off, uint64_t n_q, uint64_t *hq_off) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q <= n_q) hq_off[q] = hit_off[qp_off[q]];
+}
+__global__ void __launch_bounds__(QS_NT) query_sort_kernel(const HitRec *in, const uint64_t *hq_off, HitRec *out, uint8_t *head) {
+    extern __shared__ __align__(16) unsigned char qs_raw[];
+    uint64_t *key = reinterpret_cast<uint64_t *>(qs_raw);
+    const uint64_t b = hq_off[blockIdx.x], e = hq_off[blockIdx.x + 1];
+    const uint32_t n = (uint32_t)(e - b);
+    if (n == 0) return;
+    uint32_t m = 1;
+    while (m < n) m <<= 1;
+    for (uint32_t i = threadIdx.x; i < m; i += QS_NT) key[i] = i < n ? (((uint64_t)in[b + i].sid << 32) | i) : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < m; i += QS_NT) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const uint64_t x = key[i], y = key[l];
+                    if ((x > y) == ((i & k) == 0)) { key[i] = y; key[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t r = threadIdx.x; r < n; r += QS_NT) {
+        const uint64_t kx = key[r];
+        out[b + r] = in[b + (uint32_t)kx];
+        head[b + r] = (r == 0 || (uint32_t)(key[r - 1] >> 32) != (uint32_t)(kx >> 32)) ? 1 : 0;
+    }
+}
+// segment keys (qid, sid) of the sorted hits for the run-length step
+__global__ void hit_keys_kernel(const HitRec *h, uint64_t n, SortKey *keys) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SortKey k; k.k0 = h[i].qid; k.k1 = h[i].sid;
+    keys[i] = k;
+}
+
 // ---- sparse_aln (aln.rs:12-142), one thread per (query, target) segment ---------------------------------------------
 struct ChainParams {
     const HitRec *hits;          // sorted by (qid, sid), each segment already non-decreasing in qb (stable)
@@ -164,25 +238,23 @@ __device__ __forceinline__ bool head_before(const float *vs, uint32_t a, uint32_
     return vs[a] > vs[b] || (vs[a] == vs[b] && a < b);
 }
 
-__global__ void chain_kernel(const ChainParams p) {
-    const uint64_t sgi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (sgi >= p.n_seg) return;
-    const uint64_t b = p.seg_off[sgi], e = p.seg_off[sgi + 1];
-    const uint32_t n = (uint32_t)(e - b);
-    p.seg_n_out[sgi] = 0; p.seg_n_chains[sgi] = 0; p.seg_err[sgi] = 0;
-    if (n < 2) return;  // aln.rs:237 filter(|(_sid, hps)| hps.len() > 1)
-    const HitRec *h = p.hits + b;
-    float *vs = p.v_s + b;
-    int32_t *bp = p.best_pre + b;
-    uint32_t *cf = p.cls_first + b, *cl = p.cls_last + b, *ord = p.order + b;
-    uint8_t *vis = p.visited + b;
+// sparse_aln on one segment: h[0..n) sorted by qb (stable); every array has n entries and may live in shared or global memory.
+// PAR > 1: the duplicate classes are computed by PAR cooperating lanes (lane = 0..PAR-1, all lanes of the warp must call);
+// everything sequential (DP, head order, traceback) runs on lane 0 only.
+template <int PAR>
+__device__ __forceinline__ void chain_segment(const ChainParams &p, const HitRec *h, uint32_t n, float *vs, int32_t *bp, uint32_t *cf, uint32_t *cl,
+                                              uint32_t *ord, uint8_t *vis, uint32_t *oi, uint8_t *ost, float *osc, int lane, uint32_t &n_out_r,
+                                              uint32_t &n_ch_r, uint32_t &err_r) {
     // duplicate classes: identical HitPairs share one map entry; equal values have equal qb, so they sit in one qb run
-    for (uint32_t i = 0; i < n; i++) {
+    for (uint32_t i = (uint32_t)lane; i < n; i += PAR) {
         uint32_t f = i, l = i;
         for (uint32_t j = i; j > 0 && h[j - 1].qb == h[i].qb; j--) if (same_hp(h[j - 1], h[i])) f = j - 1;
         for (uint32_t j = i + 1; j < n && h[j].qb == h[i].qb; j++) if (same_hp(h[j], h[i])) l = j;
         cf[i] = f; cl[i] = l;
     }
+    if (PAR > 1) __syncwarp();
+    n_out_r = 0; n_ch_r = 0; err_r = 0;
+    if (lane != 0) return;
     // DP (aln.rs:25-103).  v_s.get(pre) sees the LATEST inserted duplicate with index < i
     vs[0] = __fsub_rn((float)h[0].qe, (float)h[0].qb);
     bp[0] = -1;
@@ -258,14 +330,11 @@ __global__ void chain_kernel(const ChainParams p) {
     }
     // traceback (aln.rs:105-141)
     uint32_t n_out = 0, n_ch = 0;
-    uint32_t *oi = p.out_idx + b;
-    uint8_t *ost = p.out_start + b;
-    float *osc = p.out_score + b;
-    for (uint32_t t = 0; t < m; t++) {
+        for (uint32_t t = 0; t < m; t++) {
         const uint32_t head = ord[t];
         if (vis[head]) continue;
         const float best_s = vs[cl[head]];
-        if (!(best_s > 0.0f)) { p.seg_err[sgi] = 1; break; }   // the reference loops forever here
+        if (!(best_s > 0.0f)) { err_r = 1; break; }   // the reference loops forever here
         const uint32_t start = n_out;
         int32_t v = (int32_t)head;
         while (v >= 0) {
@@ -282,8 +351,56 @@ __global__ void chain_kernel(const ChainParams p) {
         osc[start] = __fsub_rn(best_s, vs[cl[oi[start]]]);
         n_ch++;
     }
-    p.seg_n_out[sgi] = n_out;
-    p.seg_n_chains[sgi] = n_ch;
+    n_out_r = n_out;
+    n_ch_r = n_ch;
+}
+
+// one thread per (query, target) segment, all arrays in global memory: the segments too large for the staged kernel below
+__global__ void chain_kernel(const ChainParams p, uint32_t min_n) {
+    const uint64_t sgi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sgi >= p.n_seg) return;
+    const uint64_t b = p.seg_off[sgi], e = p.seg_off[sgi + 1];
+    const uint32_t n = (uint32_t)(e - b);
+    if (n <= min_n && min_n) return;                  // done by chain_staged_kernel
+    p.seg_n_out[sgi] = 0; p.seg_n_chains[sgi] = 0; p.seg_err[sgi] = 0;
+    if (n < 2) return;  // aln.rs:237 filter(|(_sid, hps)| hps.len() > 1)
+    uint32_t n_out, n_ch, err;
+    chain_segment<1>(p, p.hits + b, n, p.v_s + b, p.best_pre + b, p.cls_first + b, p.cls_last + b, p.order + b, p.visited + b, p.out_idx + b,
+                     p.out_start + b, p.out_score + b, 0, n_out, n_ch, err);
+    p.seg_n_out[sgi] = n_out; p.seg_n_chains[sgi] = n_ch; p.seg_err[sgi] = err;
+}
+
+// one WARP per segment of at most CH_CAP hits: the hit records are staged into shared memory with coalesced loads (the
+// thread-per-segment kernel reads them record by record from global memory, ~5x the bytes), the DP arrays live there too,
+// and the chains leave with coalesced stores.  Same arithmetic, same order of operations as chain_segment everywhere.
+constexpr int CH_CAP = 256, CH_WARPS = 4;
+struct ChainSmem {
+    HitRec h[CH_CAP];
+    float vs[CH_CAP]; int32_t bp[CH_CAP]; uint32_t cf[CH_CAP], cl[CH_CAP], ord[CH_CAP], oi[CH_CAP]; float osc[CH_CAP];
+    uint8_t vis[CH_CAP], ost[CH_CAP];
+};
+__global__ void __launch_bounds__(CH_WARPS * 32) chain_staged_kernel(const ChainParams p) {
+    extern __shared__ __align__(16) unsigned char ch_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ChainSmem &s = reinterpret_cast<ChainSmem *>(ch_raw)[warp];
+    const uint64_t sgi = (uint64_t)blockIdx.x * CH_WARPS + warp;
+    if (sgi >= p.n_seg) return;
+    const uint64_t b = p.seg_off[sgi], e = p.seg_off[sgi + 1];
+    const uint32_t n = (uint32_t)(e - b);
+    if (n > CH_CAP) return;                           // chain_kernel's
+    if (n < 2) { if (lane == 0) { p.seg_n_out[sgi] = 0; p.seg_n_chains[sgi] = 0; p.seg_err[sgi] = 0; } return; }
+    {   // 32-byte records as two 16-byte halves: consecutive lanes read consecutive 16 bytes
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.hits + b);
+        uint4 *dst = reinterpret_cast<uint4 *>(s.h);
+        for (uint32_t i = (uint32_t)lane; i < 2 * n; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    uint32_t n_out = 0, n_ch = 0, err = 0;
+    chain_segment<32>(p, s.h, n, s.vs, s.bp, s.cf, s.cl, s.ord, s.vis, s.oi, s.ost, s.osc, lane, n_out, n_ch, err);
+    n_out = __shfl_sync(0xFFFFFFFFu, n_out, 0);
+    __syncwarp();
+    for (uint32_t i = (uint32_t)lane; i < n_out; i += 32) { p.out_idx[b + i] = s.oi[i]; p.out_start[b + i] = s.ost[i]; p.out_score[b + i] = s.osc[i]; }
+    if (lane == 0) { p.seg_n_out[sgi] = n_out; p.seg_n_chains[sgi] = n_ch; p.seg_err[sgi] = err; }
 }
 
 // nested result arrays built on the device: one thread per segment copies its chains to their final places

@@ -129,6 +129,37 @@ class SeqIndexDB:
         return [(int(a["sid"]), (int(a["a0"]), int(a["a1"]), int(a["ori0"])), (int(a["b0"]), int(a["b1"]), int(a["ori1"])))
                 for a in self._idx.adj_list(min_count, keeps)]
 
+    def get_smp_adj_list_by_seq(self, min_count, keeps=None):
+        """the adjacency list generate_mapg_gfa builds when method != "from_fragmap" (ext.rs:696-722): every sequence's own
+        shimmer pairs through generate_smp_adj_list_for_seq (seq_db.rs:946-1000), min_count 0 for the sequences in `keeps`;
+        sequences in ascending sid order (the reference walks seq_info's hash map: order unpinned)"""
+        sids = sorted(self.seq_info)
+        ks = set(keeps) if keeps is not None else set()
+        mcs = [0 if sid in ks else min_count for sid in sids]
+        adj = self._idx.smp_adj_list_for_seqs(sids, [self._seqs[sid][2] for sid in sids], mcs)
+        return [(int(a["sid"]), (int(a["a0"]), int(a["a1"]), int(a["ori0"])), (int(a["b0"]), int(a["b1"]), int(a["ori1"]))) for a in adj]
+
+    def generate_mapg_gfa(self, min_count, filepath, method="from_fragmap", keeps=None):
+        """lib.rs:1066-1080 -> ext.rs:652-786.  S lines by segment id, L lines by first appearance in the adjacency list (the
+        reference iterates FxHashMaps: order unpinned)"""
+        adj = self.get_smp_adj_list(min_count, keeps) if method == "from_fragmap" else self.get_smp_adj_list_by_seq(min_count, keeps)
+        fmap = self.get_shmmr_map()
+        k = self.get_shmmr_spec()[1]
+        overlaps, frag_id = {}, {}
+        for sid, v, w in adj:
+            if v[0] <= w[0]:                                   # ext.rs:724
+                overlaps.setdefault((v, w), []).append((sid, v[2], w[2]))
+                frag_id.setdefault((v[0], v[1]), len(frag_id))
+                frag_id.setdefault((w[0], w[1]), len(frag_id))
+        with open(filepath, "w") as f:
+            f.write("H\tVN:Z:1.0\tCM:Z:Sparse Genome Graph Generated By pgr-tk\n")
+            for smp, i in sorted(frag_id.items(), key=lambda t: t[1]):
+                hits = fmap[smp]
+                ave_len = (sum(h[3] - h[2] for h in hits) & 0xFFFFFFFF) // len(hits)
+                f.write("S\t%d\t*\tLN:i:%d\tSN:Z:%016x_%016x\n" % (i, ave_len + k, smp[0], smp[1]))
+            for (v, w), vs in overlaps.items():
+                f.write("L\t%d\t%s\t%d\t%s\t%dM\tSC:i:%d\n" % (frag_id[(v[0], v[1])], "+-"[v[2]], frag_id[(w[0], w[1])], "+-"[w[2]], k, len(vs)))
+
     def _adj_array(self, adj_list):
         a = np.zeros(len(adj_list), dtype=api.ADJ)
         for i, (sid, v, w) in enumerate(adj_list):
