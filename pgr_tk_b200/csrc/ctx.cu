@@ -7,6 +7,7 @@
 #include <cstring>
 #include <ctime>
 #include <mutex>
+#include <thread>
 
 #include "patch_kernels.cuh"
 
@@ -277,12 +278,30 @@ static int upload_copy(pgr_b200_ctx *ctx, const uint8_t *const *seqs, const size
         while (j < i1 && lens[j] < BIG && (ctx->h_off[j] - span0) + ((lens[j] + 31) & ~(size_t)31) <= STAGE) j++;
         if (used[cur]) cudaEventSynchronize(ev[cur]);
         uint64_t span = 0;
-        for (size_t q = i; q < j; q++) {
-            const uint64_t rel = ctx->h_off[q] - span0;
-            if (lens[q]) memcpy(stage[cur] + rel, seqs[q], lens[q]);
-            const uint64_t padded = (lens[q] + 31) & ~(uint64_t)31;
-            if (padded > lens[q]) memset(stage[cur] + rel + lens[q], 0, padded - lens[q]);
-            span = rel + padded;
+        {
+            const size_t last = j - 1;
+            span = (ctx->h_off[last] - span0) + ((lens[last] + 31) & ~(uint64_t)31);
+            uint8_t *dst = stage[cur];
+            auto fill = [&, dst](size_t q0, size_t q1) {
+                for (size_t q = q0; q < q1; q++) {
+                    const uint64_t rel = ctx->h_off[q] - span0;
+                    if (lens[q]) memcpy(dst + rel, seqs[q], lens[q]);
+                    const uint64_t padded = (lens[q] + 31) & ~(uint64_t)31;
+                    if (padded > lens[q]) memset(dst + rel + lens[q], 0, padded - lens[q]);
+                }
+            };
+            // many small sequences (a batch of queries): one host thread copies at ~10 GB/s, far below the PCIe rate the
+            // staging buffer is emptied at, so a few threads share the fill
+            const size_t n_run = j - i;
+            const unsigned T = (span >= (4u << 20) && n_run >= 8) ? 4u : 1u;
+            if (T == 1) {
+                fill(i, j);
+            } else {
+                std::vector<std::thread> th;
+                for (unsigned t = 1; t < T; t++) th.emplace_back(fill, i + n_run * t / T, i + n_run * (t + 1) / T);
+                fill(i, i + n_run / T);
+                for (auto &x : th) x.join();
+            }
         }
         if (span && cudaMemcpyAsync(base + span0, stage[cur], span, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = PGR_E_CUDA;
         cudaEventRecord(ev[cur], st);

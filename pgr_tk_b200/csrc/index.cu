@@ -117,8 +117,47 @@ int index_batch_tuples(pgr_b200_index *idx, size_t n, const uint32_t *sids, cons
     return rc;
 }
 
-// stable LSD radix sort of (keys, idx) by the 112-bit key; result in keysA/idxA
+// stable LSD radix sort of (keys, idx) by the 112-bit key; result in keysA/idxA.  One-sweep form (sort_kernels.cuh): all digit
+// histograms from one read, constant digits skipped without a launch, one kernel per remaining pass.
+// PGR_B200_SORT_3KERNEL=1 selects the first-generation three-kernel passes (A/B aid; also taken for n >= 2^30).
+static int index_sort_3kernel(pgr_b200_index *idx, uint64_t n, int first_pass, int last_pass);
 int index_sort(pgr_b200_index *idx, uint64_t n, int first_pass, int last_pass) {
+    static const bool old_sort = getenv("PGR_B200_SORT_3KERNEL") != nullptr;
+    if (old_sort || n >= (1ull << 30) || n == 0) return index_sort_3kernel(idx, n, first_pass, last_pass);
+    cudaStream_t st = idx->ctx->stream;
+    const uint32_t n_tiles = (uint32_t)ceil_div<uint64_t>(n, OS_TILE);
+    PGR_TRY(idx->hist.ensure((size_t)OS_PASSES * 256 * 4 + OS_PASSES * 4 + 64 + (size_t)n_tiles * 256 * 4));
+    PGR_TRY(idx->keysB.ensure(n * sizeof(SortKey)));
+    PGR_TRY(idx->idxB.ensure(n * sizeof(uint32_t)));
+    uint32_t *hist = idx->hist.as<uint32_t>(), *skip = hist + OS_PASSES * 256, *ticket = skip + OS_PASSES, *status = ticket + 2;
+    PGR_CUDA(cudaMemsetAsync(hist, 0, (size_t)OS_PASSES * 256 * 4 + OS_PASSES * 4 + 8, st));
+    const uint32_t hg = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(n, 256 * 16), (uint64_t)idx->ctx->n_sm * 8);
+    os_hist_kernel<<<std::max(1u, hg), 256, 0, st>>>(idx->keysA.as<SortKey>(), n, first_pass, last_pass, hist);
+    os_scan_kernel<<<OS_PASSES, 256, 0, st>>>(hist, n, skip);
+    idx->launches += 2;
+    PGR_CUDA(cudaGetLastError());
+    PGR_TRY(idx->ctx->ensure_ctl(64));
+    uint32_t *h_skip = (uint32_t *)idx->ctx->h_ctl;
+    PGR_CUDA(cudaMemcpyAsync(h_skip, skip, OS_PASSES * 4, cudaMemcpyDeviceToHost, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    static bool attr_set = false;
+    if (!attr_set) { PGR_CUDA(cudaFuncSetAttribute(os_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem))); attr_set = true; }
+    SortKey *ka = idx->keysA.as<SortKey>(), *kb = idx->keysB.as<SortKey>();
+    uint32_t *ia = idx->idxA.as<uint32_t>(), *ib = idx->idxB.as<uint32_t>();
+    for (int pass = first_pass; pass <= last_pass; pass++) {
+        if (h_skip[pass]) continue;
+        PGR_CUDA(cudaMemsetAsync(ticket, 0, 8 + (size_t)n_tiles * 256 * 4, st));
+        os_pass_kernel<<<n_tiles, OS_NT, sizeof(OsSmem), st>>>(ka, ia, n, pass, hist + pass * 256, status, ticket, kb, ib);
+        idx->launches += 1;
+        std::swap(ka, kb); std::swap(ia, ib);
+        trace_mark("index_sort: pass");
+    }
+    PGR_CUDA(cudaGetLastError());
+    if (ka != idx->keysA.as<SortKey>()) { std::swap(idx->keysA, idx->keysB); std::swap(idx->idxA, idx->idxB); }
+    return PGR_OK;
+}
+
+static int index_sort_3kernel(pgr_b200_index *idx, uint64_t n, int first_pass, int last_pass) {
     cudaStream_t st = idx->ctx->stream;
     const uint32_t n_seg = (uint32_t)ceil_div<uint64_t>(n, RS_SEG);
     const uint32_t grid = ceil_div<uint32_t>(n_seg, RS_WARPS);

@@ -245,17 +245,8 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
             cp.best_pre = (int32_t *)u; cp.cls_first = u + n_hits; cp.cls_last = u + 2 * n_hits; cp.order = u + 3 * n_hits; cp.out_idx = u + 4 * n_hits;
             cp.visited = idx->chain_b.as<uint8_t>(); cp.out_start = cp.visited + n_hits;
             cp.seg_n_out = idx->chain_seg.as<uint32_t>(); cp.seg_n_chains = cp.seg_n_out + n_seg; cp.seg_err = cp.seg_n_out + 2 * n_seg;
-            // segments of up to CH_CAP hits (nearly all): one warp each, staged in shared memory; larger ones: one thread each
-            static const bool chain_unstaged = getenv("PGR_B200_CHAIN_UNSTAGED") != nullptr;   // A/B aid
-            if (chain_unstaged) {
-                chain_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 64), 64, 0, st>>>(cp, 0u);
-            } else {
-                static bool ch_attr = false;
-                if (!ch_attr) { PGR_CUDA(cudaFuncSetAttribute(chain_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CH_WARPS * sizeof(ChainSmem)))); ch_attr = true; }
-                chain_staged_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, CH_WARPS), CH_WARPS * 32, CH_WARPS * sizeof(ChainSmem), st>>>(cp);
-                chain_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 64), 64, 0, st>>>(cp, (uint32_t)CH_CAP);
-            }
-            idx->launches += 2;
+            chain_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 64), 64, 0, st>>>(cp);
+            idx->launches += 1;
             PGR_CUDA(cudaGetLastError());
             trace_mark("query_batch: chain kernel");
             // nested result arrays on the device, then one D2H per array into (pinned) result buffers
@@ -369,7 +360,7 @@ int pgr_b200_sparse_aln(pgr_hit_pair *hits, size_t n, uint32_t max_span, float p
     cp.best_pre = (int32_t *)u; cp.cls_first = u + n; cp.cls_last = u + 2 * n; cp.order = u + 3 * n; cp.out_idx = u + 4 * n;
     cp.visited = d_b.as<uint8_t>(); cp.out_start = cp.visited + n;
     cp.seg_n_out = d_meta; cp.seg_n_chains = d_meta + 1; cp.seg_err = d_meta + 2;
-    chain_kernel<<<1, 64, 0, st>>>(cp, 0u);
+    chain_kernel<<<1, 64, 0, st>>>(cp);
     std::vector<uint32_t> out_idx(n);
     std::vector<uint8_t> out_start(n);
     std::vector<float> out_score(n);

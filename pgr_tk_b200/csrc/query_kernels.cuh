@@ -355,52 +355,22 @@ __device__ __forceinline__ void chain_segment(const ChainParams &p, const HitRec
     n_ch_r = n_ch;
 }
 
-// one thread per (query, target) segment, all arrays in global memory: the segments too large for the staged kernel below
-__global__ void chain_kernel(const ChainParams p, uint32_t min_n) {
+// one thread per (query, target) segment, all arrays in global memory.  (Measured on config 4, 1.0 M segments / 28.6 M hits:
+// 8.3 ms.  A warp per segment with the records staged in shared memory and the look-back of every hit spread over the lanes
+// — ballots for span_set, warp arg-max for the best predecessor, rank sort for the heads, bit-exact — took 16.4 ms: a
+// look-back visits ~8 predecessors, so three quarters of the lanes idle and the kernel becomes issue bound; with lane 0 alone
+// doing the DP it took 60 ms.  Both were removed.)
+__global__ void chain_kernel(const ChainParams p) {
     const uint64_t sgi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (sgi >= p.n_seg) return;
     const uint64_t b = p.seg_off[sgi], e = p.seg_off[sgi + 1];
     const uint32_t n = (uint32_t)(e - b);
-    if (n <= min_n && min_n) return;                  // done by chain_staged_kernel
     p.seg_n_out[sgi] = 0; p.seg_n_chains[sgi] = 0; p.seg_err[sgi] = 0;
     if (n < 2) return;  // aln.rs:237 filter(|(_sid, hps)| hps.len() > 1)
     uint32_t n_out, n_ch, err;
     chain_segment<1>(p, p.hits + b, n, p.v_s + b, p.best_pre + b, p.cls_first + b, p.cls_last + b, p.order + b, p.visited + b, p.out_idx + b,
                      p.out_start + b, p.out_score + b, 0, n_out, n_ch, err);
     p.seg_n_out[sgi] = n_out; p.seg_n_chains[sgi] = n_ch; p.seg_err[sgi] = err;
-}
-
-// one WARP per segment of at most CH_CAP hits: the hit records are staged into shared memory with coalesced loads (the
-// thread-per-segment kernel reads them record by record from global memory, ~5x the bytes), the DP arrays live there too,
-// and the chains leave with coalesced stores.  Same arithmetic, same order of operations as chain_segment everywhere.
-constexpr int CH_CAP = 256, CH_WARPS = 4;
-struct ChainSmem {
-    HitRec h[CH_CAP];
-    float vs[CH_CAP]; int32_t bp[CH_CAP]; uint32_t cf[CH_CAP], cl[CH_CAP], ord[CH_CAP], oi[CH_CAP]; float osc[CH_CAP];
-    uint8_t vis[CH_CAP], ost[CH_CAP];
-};
-__global__ void __launch_bounds__(CH_WARPS * 32) chain_staged_kernel(const ChainParams p) {
-    extern __shared__ __align__(16) unsigned char ch_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    ChainSmem &s = reinterpret_cast<ChainSmem *>(ch_raw)[warp];
-    const uint64_t sgi = (uint64_t)blockIdx.x * CH_WARPS + warp;
-    if (sgi >= p.n_seg) return;
-    const uint64_t b = p.seg_off[sgi], e = p.seg_off[sgi + 1];
-    const uint32_t n = (uint32_t)(e - b);
-    if (n > CH_CAP) return;                           // chain_kernel's
-    if (n < 2) { if (lane == 0) { p.seg_n_out[sgi] = 0; p.seg_n_chains[sgi] = 0; p.seg_err[sgi] = 0; } return; }
-    {   // 32-byte records as two 16-byte halves: consecutive lanes read consecutive 16 bytes
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.hits + b);
-        uint4 *dst = reinterpret_cast<uint4 *>(s.h);
-        for (uint32_t i = (uint32_t)lane; i < 2 * n; i += 32) dst[i] = src[i];
-    }
-    __syncwarp();
-    uint32_t n_out = 0, n_ch = 0, err = 0;
-    chain_segment<32>(p, s.h, n, s.vs, s.bp, s.cf, s.cl, s.ord, s.vis, s.oi, s.ost, s.osc, lane, n_out, n_ch, err);
-    n_out = __shfl_sync(0xFFFFFFFFu, n_out, 0);
-    __syncwarp();
-    for (uint32_t i = (uint32_t)lane; i < n_out; i += 32) { p.out_idx[b + i] = s.oi[i]; p.out_start[b + i] = s.ost[i]; p.out_score[b + i] = s.osc[i]; }
-    if (lane == 0) { p.seg_n_out[sgi] = n_out; p.seg_n_chains[sgi] = n_ch; p.seg_err[sgi] = err; }
 }
 
 // nested result arrays built on the device: one thread per segment copies its chains to their final places
