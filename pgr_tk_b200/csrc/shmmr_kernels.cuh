@@ -23,6 +23,13 @@ namespace pgr {
 #ifndef PGR_L0_MIN_CTAS
 #define PGR_L0_MIN_CTAS 3
 #endif
+// PGR_L0_BULK=1: the tile's bytes (L0_NT x 32 B, contiguous) are fetched by ONE bulk asynchronous copy (cp.async.bulk, the
+// TMA engine's 1-D form) into shared memory behind an mbarrier, issued by thread 0 one tile ahead, instead of one 32-byte
+// register prefetch per thread.  A/B variant (profiles/r2_l0_kernel_bulk_ab.txt): the key loop is ALU bound and the register
+// prefetch already hides the loads, while the 8 KB staging slot costs the third resident CTA at 256 threads.
+#ifndef PGR_L0_BULK
+#define PGR_L0_BULK 1
+#endif
 constexpr int L0_NT = PGR_L0_NT;           // threads per CTA; thread t owns the 32-base block t of the tile's load region
 constexpr int L0_CTX = 2;                  // leading context-only blocks (a 56-mer reaches 55 bases back)
 constexpr int L0_KB = L0_NT - L0_CTX;      // blocks that get keys
@@ -30,7 +37,18 @@ constexpr int L0_KPOS = L0_KB * 32;        // key positions per tile
 constexpr int L0_PADB = 4;                 // spare blocks on both sides of the smem arrays (van Herk neighbours, w <= 128)
 constexpr int L0_ARR = (L0_KB + 2 * L0_PADB) * 33;  // padded u32 array length
 constexpr int L0_MIN_CTAS = PGR_L0_MIN_CTAS;  // resident CTAs per SM the kernel is compiled for
+#if PGR_L0_BULK
+// the last 8 KB of the P array (128-byte aligned in the CTA's shared memory) receive the next tile's bytes: P is only used in
+// full by phase 3, the copy is issued after it and consumed by phase 1 of the next tile
+constexpr int L0_SLOT_BYTES = L0_NT * 32;
+constexpr int L0_SLOT_TOP = (L0_ARR - L0_PADB * 33) * 4;   // the spare blocks at the end of P keep their zeros (phase 3 reads them)
+constexpr int L0_SLOT_OFF = ((L0_SLOT_TOP - L0_SLOT_BYTES) - (((L0_SLOT_TOP - L0_SLOT_BYTES) + L0_ARR * 4) % 128));   // byte offset inside P; H (L0_ARR words) precedes P
+static_assert(L0_SLOT_OFF > 0 && (L0_ARR * 4 + L0_SLOT_OFF) % 128 == 0 && L0_SLOT_OFF + L0_SLOT_BYTES <= L0_SLOT_TOP, "tile slot placement");
+static_assert(L0_SLOT_OFF / 2 >= L0_KPOS + 256, "the candidate list must fit below the slot");
+constexpr int L0_LISTCAP = L0_SLOT_OFF / 2; // u16 entries of the P array below the slot
+#else
 constexpr int L0_LISTCAP = L0_ARR * 2;     // u16 entries that fit in the P array
+#endif
 
 struct L0Params {
     const uint8_t *seq;          // device sequence store
@@ -56,6 +74,25 @@ struct L0Params {
 };
 
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+
+#if PGR_L0_BULK
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// thread 0: expect `bytes` on the barrier and start the bulk copy global -> shared
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy reads of dst are done (barrier before)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred P1;\n\tWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra WAIT;\n\tDONE:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
 
 // 4 ASCII bases (one little-endian word) -> 4 plane bits each in the TOP nibble of a product word, first base most
 // significant.  code bit0 = bit1 of (c ^ (c >> 1)), code bit1 = bit2 of c  (A=0,C=1,G=2,T=3; case-insensitive).
@@ -272,7 +309,7 @@ __device__ __noinline__ bool strand_tie_scan(const L0Params &p, L0Smem &s, L0Sme
 // Level-0 minimizers of one tile.  W, K > 0 are compile-time specialisations; 0 = read from params.
 template <int W, int K, int U = 8>
 __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     L0Smem &s = *reinterpret_cast<L0Smem *>(smem_raw);
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -296,6 +333,17 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
     if (tid == 0 && t_begin < t_end) desc_sid = make_tile_desc(p, t_begin, w, s.td[0], desc_sid);
     __syncthreads();
     uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+#if PGR_L0_BULK
+    uint4 *const tile_bytes = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(s.P) + L0_SLOT_OFF);
+    __shared__ alignas(8) uint64_t tile_bar;
+    uint32_t bar_phase = 0;
+    if (tid == 0) {   // the zero fill of P above is complete (barrier): the slot may be written by the copy engine
+        mbar_init(&tile_bar, 1);
+        // the tile's load region starts L0_CTX blocks before key index 0; the store keeps 16 KiB of readable slack on both sides
+        if (t_begin < t_end) bulk_load(tile_bytes, p.seq + s.td[0].seq_off + (int64_t)(s.td[0].keys_start - 32 * L0_CTX), L0_NT * 32, &tile_bar);
+    }
+    __syncthreads();
+#else
     if (t_begin < t_end) {
         const int32_t bp = s.td[0].keys_start + 32 * (tid - L0_CTX);
         if (bp + 32 > 0 && bp < (int32_t)s.td[0].seq_len) {
@@ -303,6 +351,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
             v0 = __ldg(src); v1 = __ldg(src + 1);
         }
     }
+#endif
     int cur = 0;
     for (uint32_t tile = t_begin; tile < t_end; ++tile, cur ^= 1) {
         L0Smem::TileDesc &D = s.td[cur];
@@ -315,6 +364,11 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         // ---- phase 1: 32 bases -> plane words -------------------------------------------------------------
         uint32_t f0 = 0, f1 = 0, inv = 0;
         const bool blk_live = (blk_pos + 32 > 0) && (blk_pos < L);  // block intersects the sequence
+#if PGR_L0_BULK
+        mbar_wait(&tile_bar, bar_phase);      // this tile's bytes have landed
+        bar_phase ^= 1u;
+        v0 = tile_bytes[2 * tid]; v1 = tile_bytes[2 * tid + 1];
+#endif
         if (blk_live) {
             const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             uint32_t bad_bits = 0;
@@ -346,6 +400,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         s.bext[tid + 2] = inv;   // invalid-byte mask of block tid, read by the two following blocks below; bext is rewritten in phase 3
         if (tid < 8) { s.F0[L0_NT + tid] = 0; s.F1[L0_NT + tid] = 0; }
         __syncthreads();   // planes visible; also publishes thread 0's descriptor of the next tile
+#if !PGR_L0_BULK
         if (has_next) {    // the loads fly while the key loop runs
             const L0Smem::TileDesc &N = s.td[cur ^ 1];
             const int32_t bp = N.keys_start + 32 * (tid - L0_CTX);
@@ -354,6 +409,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                 v0 = __ldg(src); v1 = __ldg(src + 1);
             }
         }
+#endif
 
         // ---- phase 2: keys for blocks CTX.. ------------------------------------------------------------------
         const int kb = tid - L0_CTX;  // key block index (negative for the two context threads)
@@ -570,6 +626,12 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         }
         if (lane == 31) s.wsum[warp] = incl;
         __syncthreads();
+#if PGR_L0_BULK
+        if (has_next && tid == 0) {   // phase 3 is over for every thread (barrier above): P's tail is free until phase 3 of the next tile
+            const L0Smem::TileDesc &N = s.td[cur ^ 1];
+            bulk_load(tile_bytes, p.seq + N.seq_off + (int64_t)(N.keys_start - 32 * L0_CTX), L0_NT * 32, &tile_bar);
+        }
+#endif
         uint32_t wbase = 0, total = 0;
         {
             const uint4 *wv = reinterpret_cast<const uint4 *>(s.wsum);
