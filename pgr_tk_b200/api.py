@@ -157,6 +157,9 @@ def lib():
         L.pgr_b200_mindex_gather.argtypes = [vp, C.c_int]
         L.pgr_b200_host_register.argtypes = [vp, sz]
         L.pgr_b200_host_unregister.argtypes = [vp]
+        L.pgr_b200_pack_bases.restype = None
+        L.pgr_b200_pack_bases.argtypes = [vp, sz, vp, vp, vp]
+        L.pgr_b200_pack_isa.restype = C.c_char_p
         L.pgr_b200_index_counts.argtypes = [vp, P(sz), P(sz), P(u32)]
         L.pgr_b200_index_export_csr.argtypes = [vp, vp, vp, vp]
         L.pgr_b200_index_tuples_device.argtypes = [vp, P(vp), P(sz)]
@@ -234,6 +237,28 @@ def get_shmmrs_from_seqs(rids, seqs, spec, padding=False):
     out = C.c_void_p()
     _check(lib().pgr_b200_shmmrs_batch(n, r.ctypes.data, ptrs, lens, C.byref(spec), int(padding), C.byref(out), offs.ctypes.data))
     return _take(out, int(offs[n]), MM128), offs
+
+
+def pack_bases(seq):
+    """host half of the packed transport (pgr_b200_pack_bases): the three bit planes (p0, p1, v) of `seq`, one u32 per
+    32-byte block each; runs on the host, no device needed"""
+    a = np.frombuffer(_bytes(seq), dtype=np.uint8)
+    nb = (len(a) + 31) // 32
+    p0, p1, v = (np.zeros(max(nb, 1), dtype=np.uint32) for _ in range(3))
+    lib().pgr_b200_pack_bases(a.ctypes.data, len(a), p0.ctypes.data, p1.ctypes.data, v.ctypes.data)
+    return p0[:nb], p1[:nb], v[:nb]
+
+
+TRANSPORT_PACKED, TRANSPORT_DIRECT = 0, 1
+
+
+def set_transport(mode):
+    """process-wide host-to-device transport of large inputs (pgr_b200_set_transport); returns the previous mode"""
+    return lib().pgr_b200_set_transport(int(mode))
+
+
+def pack_isa():
+    return lib().pgr_b200_pack_isa().decode()
 
 
 class HostBuffer:

@@ -6,9 +6,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 
+#include "pack_upload.cuh"
 #include "patch_kernels.cuh"
 
 namespace pgr {
@@ -152,6 +154,10 @@ int pgr_b200_host_register(void *p, size_t bytes) {
     PGR_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
     return PGR_OK;
 }
+void pgr_b200_pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) { pgr::pack_bases(src, n_bytes, p0, p1, v); }
+const char *pgr_b200_pack_isa(void) { return pgr::pack_isa(); }
+int pgr_b200_pool_threads(void) { return (int)pgr::pool_threads(); }
+int pgr_b200_set_transport(int mode) { return pgr::transport_mode().exchange(mode == PGR_TRANSPORT_DIRECT ? 1 : 0); }
 int pgr_b200_host_unregister(void *p) {
     if (!p) return PGR_OK;
     PGR_CUDA(cudaHostUnregister(p));
@@ -193,6 +199,7 @@ void pgr_b200_ctx_free(pgr_b200_ctx *ctx) {
     for (auto b : bufs) b->release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->pack) pgr::pack_ring_release(ctx->pack);
     ctx->timer.destroy();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -324,7 +331,12 @@ int pgr_b200_ctx_upload(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const
     if (!ctx || (n && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
     PGR_CUDA(cudaSetDevice(ctx->device));
     PGR_TRY(upload_layout(ctx, n, rids, seqs, lens));
-    PGR_TRY(upload_copy(ctx, seqs, lens, 0, n, ctx->stream));
+    if (packed_upload_enabled() && ctx->total_bases >= PACK_MIN_BYTES) {
+        if (!ctx->pack && !(ctx->pack = pack_ring_acquire(ctx->device))) return PGR_E_CUDA;
+        PGR_TRY(upload_packed(ctx->pack, ctx->seq_store.as<uint8_t>(), ctx->h_off, ctx->h_len, seqs, 0, n, ctx->stream));
+    } else {
+        PGR_TRY(upload_copy(ctx, seqs, lens, 0, n, ctx->stream));
+    }
     PGR_CUDA(cudaStreamSynchronize(ctx->stream));
     return PGR_OK;
 }
@@ -1150,13 +1162,43 @@ int pgr::run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const ui
     std::vector<cudaEvent_t> ev(n_chunks);
     int rc = PGR_OK;
     for (size_t c = 0; c < n_chunks; c++) cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming);
-    for (size_t c = 0; c < n_chunks && rc == PGR_OK; c++) {
-        rc = upload_copy(ctx, seqs, lens, cut[c], cut[c + 1], ctx->copy_stream);
-        cudaEventRecord(ev[c], ctx->copy_stream);
+    // Packed transport (pack_upload.cuh): the host packs the bases into bit planes while earlier chunks are copied and
+    // computed, so the packing runs on its own host thread and hands the chunks over one by one.  Direct transport: the
+    // copies are queued up front (asynchronous when the caller's buffers are page-locked).
+    const bool packed = packed_upload_enabled() && ctx->total_bases >= PACK_MIN_BYTES;
+    if (packed && !ctx->pack && !(ctx->pack = pack_ring_acquire(ctx->device))) rc = PGR_E_CUDA;
+    std::thread uploader;
+    std::mutex up_mu;
+    std::condition_variable up_cv;
+    size_t up_ready = 0;          // chunks whose event has been recorded
+    int up_rc = PGR_OK;
+    std::string up_err;
+    if (rc == PGR_OK && packed) {
+        uploader = std::thread([&] {
+            int r = cudaSetDevice(ctx->device) == cudaSuccess ? PGR_OK : PGR_E_CUDA;
+            for (size_t c = 0; c < n_chunks; c++) {
+                if (r == PGR_OK) r = upload_packed(ctx->pack, ctx->seq_store.as<uint8_t>(), ctx->h_off, ctx->h_len, seqs, cut[c], cut[c + 1], ctx->copy_stream);
+                if (r == PGR_OK && cudaEventRecord(ev[c], ctx->copy_stream) != cudaSuccess) r = PGR_E_CUDA;
+                std::lock_guard<std::mutex> lk(up_mu);
+                if (r != PGR_OK && up_rc == PGR_OK) { up_rc = r; up_err = get_error(); }
+                up_ready = c + 1;
+                up_cv.notify_all();
+            }
+        });
+    } else {
+        for (size_t c = 0; c < n_chunks && rc == PGR_OK; c++) {
+            rc = upload_copy(ctx, seqs, lens, cut[c], cut[c + 1], ctx->copy_stream);
+            cudaEventRecord(ev[c], ctx->copy_stream);
+        }
     }
     uint64_t tot[8] = {0};
     trace_mark("run_chunked: H2D queued/staged");
     for (size_t c = 0; c < n_chunks && rc == PGR_OK; c++) {
+        if (uploader.joinable()) {
+            std::unique_lock<std::mutex> lk(up_mu);
+            up_cv.wait(lk, [&] { return up_ready > c; });
+            if (up_rc != PGR_OK) { rc = up_rc; set_error("%s", up_err.c_str()); break; }
+        }
         cudaStreamWaitEvent(ctx->stream, ev[c], 0);
         ctx->r0 = cut[c];
         ctx->rn = cut[c + 1] - cut[c];
@@ -1168,6 +1210,7 @@ int pgr::run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const ui
         rc = on_chunk(cut[c], ctx->rn, ns);
         trace_mark("run_chunked: on_chunk");
     }
+    if (uploader.joinable()) uploader.join();
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
     for (size_t c = 0; c < n_chunks; c++) cudaEventDestroy(ev[c]);

@@ -7,6 +7,8 @@
 
 namespace pgr {
 
+struct PackRing;
+
 // grow-only device buffer, backed by the device's stream-ordered memory pool (cudaMallocAsync): the pool keeps freed
 // blocks (release threshold = unlimited, set in pgr_b200_ctx_new), so contexts and indexes that come and go in one
 // process do not pay cudaMalloc/cudaFree again
@@ -64,6 +66,7 @@ struct pgr_b200_ctx {
     // pinned staging for small sequences and control read-backs
     void *h_stage = nullptr; size_t h_stage_cap = 0;
     void *h_ctl = nullptr; size_t h_ctl_cap = 0;
+    pgr::PackRing *pack = nullptr;      // packed host-to-device transport (pack_upload.cuh), acquired on first use
     // shimmer pipeline buffers
     pgr::DevBuf tile_prefix, cta_tile, arena, chunk_count, seq_count, seq_flag, replay_list, replay_count;
     pgr::DevBuf chunk_prefix, seq_fast, seq_dst, bufA, bufB, flags, block_sum, block_prefix, block_chunk, off_a, off_b, mark_bits, allinv_bits, n_skips;

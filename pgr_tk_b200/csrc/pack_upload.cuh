@@ -1,0 +1,165 @@
+// pack_upload.cuh — packed host-to-device transport of sequence bytes (included by ctx.cu).
+//
+// A batch of bases normally crosses PCIe as ASCII, one byte per base, and PCIe is what bounds every host-buffer entry
+// point (pgr_b200_shmmrs_batch: 5 GB at ~50 GB/s = 100 ms around 26 ms of kernels).  sequence_to_shmmrs only reads the
+// class of a byte (shmmrutils.rs:426-436: A/a/0, C/c/1, G/g/2, T/t/3, anything else), i.e. 2 bits + 1 validity bit per base.
+// The host packs those three bit planes with SIMD on all its cores (hostpack.cpp) straight out of the caller's buffers
+// — pageable or page-locked alike — into a small ring of page-locked slots; each slot crosses PCIe as 12 bytes per 32 bases
+// and unpack_kernel rewrites it as canonical ASCII ("ACGT", 'N', 0 for padding) at its place in the device sequence store,
+// so every kernel downstream is unchanged and sees a store that is equivalent for the reference's LUT.
+//   PGR_B200_H2D=direct or pgr_b200_set_transport(PGR_TRANSPORT_DIRECT) disables the packed transport (A/B:
+//   profiles/r2_e2e_packed_ab.txt)
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "hostpack.hpp"
+
+namespace pgr {
+
+constexpr uint32_t PACK_SLOT_BLOCKS = 1u << 20;   // 32-byte blocks per slot: 32 MiB of bases, 12 MiB packed
+constexpr uint32_t PACK_PIECE_BLOCKS = 1u << 14;  // blocks per host work item (512 KiB of bases)
+constexpr int PACK_SLOTS = 4;
+constexpr uint64_t PACK_MIN_BYTES = 4ull << 20;   // smaller uploads go the direct way
+
+// one thread per block: three plane words -> 32 bytes (two 16-byte stores)
+__global__ void __launch_bounds__(256) unpack_kernel(const uint32_t *__restrict__ planes, uint32_t nb, uint8_t *__restrict__ dst) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t p0 = planes[b], p1 = planes[nb + b], v = planes[2 * nb + b];
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t a = (p0 >> (4 * j)) & 15u, c = (p1 >> (4 * j)) & 15u;
+        // selector nibble of byte i = code of base 4j+i; pool bytes 0..3 = 'A','C','G','T'
+        uint32_t sel = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) sel |= ((((a >> i) & 1u) | (((c >> i) & 1u) << 1))) << (4 * i);
+        w[j] = __byte_perm(0x54474341u, 0u, sel);
+    }
+    if (v != 0xFFFFFFFFu) {   // rare: invalid bytes ('N') and padding (0)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int bit = 4 * j + i;
+                if (!((v >> bit) & 1u)) w[j] = (w[j] & ~(0xFFu << (8 * i))) | ((((p0 >> bit) & 1u) ? 0u : (uint32_t)'N') << (8 * i));
+            }
+        }
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)b * 32);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// page-locked + device slot ring of one device; kept in a process-wide free list because page-locking costs ~0.8 ms/MB
+struct PackRing {
+    int device = 0;
+    uint32_t *h = nullptr;      // PACK_SLOTS x 3 x PACK_SLOT_BLOCKS words, page-locked
+    uint32_t *d = nullptr;      // the same on the device
+    cudaEvent_t h2d_done[PACK_SLOTS] = {}, unpack_done[PACK_SLOTS] = {};
+    bool used[PACK_SLOTS] = {};
+    cudaStream_t unpack_stream = nullptr;
+    uint64_t seq = 0;
+    static constexpr size_t slot_words() { return 3ull * PACK_SLOT_BLOCKS; }
+};
+
+inline std::mutex &pack_ring_mu() { static std::mutex m; return m; }
+inline std::vector<PackRing *> &pack_ring_free() { static std::vector<PackRing *> v; return v; }
+
+inline PackRing *pack_ring_acquire(int device) {
+    {
+        std::lock_guard<std::mutex> lk(pack_ring_mu());
+        auto &fl = pack_ring_free();
+        for (size_t i = 0; i < fl.size(); i++)
+            if (fl[i]->device == device) { PackRing *r = fl[i]; fl.erase(fl.begin() + i); return r; }
+    }
+    PackRing *r = new PackRing();
+    r->device = device;
+    const size_t bytes = PACK_SLOTS * PackRing::slot_words() * 4;
+    bool ok = cudaMallocHost((void **)&r->h, bytes) == cudaSuccess && cudaMalloc((void **)&r->d, bytes) == cudaSuccess;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    ok = ok && cudaStreamCreateWithPriority(&r->unpack_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
+    for (int s = 0; ok && s < PACK_SLOTS; s++)
+        ok = cudaEventCreateWithFlags(&r->h2d_done[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&r->unpack_done[s], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        if (r->h) cudaFreeHost(r->h);
+        if (r->d) cudaFree(r->d);
+        delete r;
+        set_error("cannot allocate the packed-upload ring");
+        return nullptr;
+    }
+    return r;
+}
+
+inline void pack_ring_release(PackRing *r) {
+    if (!r) return;
+    cudaStreamSynchronize(r->unpack_stream);
+    for (int s = 0; s < PACK_SLOTS; s++) r->used[s] = false;
+    std::lock_guard<std::mutex> lk(pack_ring_mu());
+    pack_ring_free().push_back(r);
+}
+
+// 0 = packed (default), 1 = direct; initialised from PGR_B200_H2D, changed by pgr_b200_set_transport
+inline std::atomic<int> &transport_mode() {
+    static std::atomic<int> m{[] { const char *e = getenv("PGR_B200_H2D"); return (e && std::string(e) == "direct") ? 1 : 0; }()};
+    return m;
+}
+inline bool packed_upload_enabled() { return transport_mode().load(std::memory_order_relaxed) == 0; }
+
+// sequences [i0, i1) of the layout (h_off: 32-byte aligned consecutive store offsets, h_len) -> store, through the ring.
+// Host work happens on the calling thread + the pool; copies on st_copy, expansion on the ring's own stream; on return
+// everything is queued and st_copy waits for the last expansion (so an event recorded on st_copy covers the chunk).
+inline int upload_packed(PackRing *ring, uint8_t *store, const std::vector<uint64_t> &h_off, const std::vector<uint32_t> &h_len,
+                         const uint8_t *const *seqs, size_t i0, size_t i1, cudaStream_t st_copy) {
+    while (i0 < i1 && h_len[i0] == 0) i0++;
+    while (i1 > i0 && h_len[i1 - 1] == 0) i1--;
+    if (i0 >= i1) return PGR_OK;
+    const uint64_t B0 = h_off[i0] >> 5;
+    const uint64_t B1 = (h_off[i1 - 1] + (((uint64_t)h_len[i1 - 1] + 31) & ~31ull)) >> 5;
+    int last_slot = -1;
+    for (uint64_t sb = B0; sb < B1; sb += PACK_SLOT_BLOCKS) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(PACK_SLOT_BLOCKS, B1 - sb);
+        const int s = (int)(ring->seq++ % PACK_SLOTS);
+        if (ring->used[s]) PGR_CUDA(cudaEventSynchronize(ring->h2d_done[s]));   // the copy that read this slot is over
+        uint32_t *hp = ring->h + (size_t)s * PackRing::slot_words();
+        uint32_t *p0 = hp, *p1 = hp + nb, *pv = hp + 2 * (size_t)nb;
+        const size_t n_pieces = (nb + PACK_PIECE_BLOCKS - 1) / PACK_PIECE_BLOCKS;
+        parallel_for(n_pieces, [&](size_t pc) {
+            uint64_t b = sb + pc * PACK_PIECE_BLOCKS;
+            const uint64_t be = std::min<uint64_t>(sb + nb, b + PACK_PIECE_BLOCKS);
+            // sequence that holds block b: the last one of [i0, i1) whose offset is <= 32 b (empty sequences share the offset
+            // of their successor, upper_bound steps over them)
+            size_t i = (size_t)(std::upper_bound(h_off.begin() + i0, h_off.begin() + i1, b << 5) - h_off.begin()) - 1;
+            while (b < be) {
+                const uint64_t within = (b << 5) - h_off[i];
+                const uint64_t len = h_len[i];
+                if (within >= len) { i++; continue; }   // (only for empty sequences)
+                const uint64_t take = std::min<uint64_t>(len - within, (be - b) << 5);
+                pack_bases(seqs[i] + within, take, p0 + (b - sb), p1 + (b - sb), pv + (b - sb));
+                b += (take + 31) >> 5;
+                if (within + take >= len) i++;
+            }
+        });
+        uint32_t *dp = ring->d + (size_t)s * PackRing::slot_words();
+        if (ring->used[s]) PGR_CUDA(cudaStreamWaitEvent(st_copy, ring->unpack_done[s], 0));   // the device slot has been expanded
+        PGR_CUDA(cudaMemcpyAsync(dp, hp, (size_t)nb * 12, cudaMemcpyHostToDevice, st_copy));
+        PGR_CUDA(cudaEventRecord(ring->h2d_done[s], st_copy));
+        PGR_CUDA(cudaStreamWaitEvent(ring->unpack_stream, ring->h2d_done[s], 0));
+        unpack_kernel<<<(nb + 255) / 256, 256, 0, ring->unpack_stream>>>(dp, nb, store + (sb << 5));
+        PGR_CUDA(cudaGetLastError());
+        PGR_CUDA(cudaEventRecord(ring->unpack_done[s], ring->unpack_stream));
+        ring->used[s] = true;
+        last_slot = s;
+    }
+    if (last_slot >= 0) PGR_CUDA(cudaStreamWaitEvent(st_copy, ring->unpack_done[last_slot], 0));
+    return PGR_OK;
+}
+
+}  // namespace pgr
