@@ -21,7 +21,7 @@
 namespace pgr {
 
 constexpr uint32_t PACK_SLOT_BLOCKS = 1u << 20;   // 32-byte blocks per slot: 32 MiB of bases, 12 MiB packed
-constexpr uint32_t PACK_PIECE_BLOCKS = 1u << 14;  // blocks per host work item (512 KiB of bases)
+constexpr uint32_t PACK_PIECE_BLOCKS = 1u << 12;  // blocks per host work item (128 KiB of bases: 256 items per slot balance 16-32 threads)
 constexpr int PACK_SLOTS = 4;
 constexpr uint64_t PACK_MIN_BYTES = 4ull << 20;   // smaller uploads go the direct way
 
