@@ -197,6 +197,7 @@ void pgr_b200_ctx_free(pgr_b200_ctx *ctx) {
                            &ctx->chunk_prefix, &ctx->seq_fast, &ctx->seq_dst, &ctx->bufA, &ctx->bufB, &ctx->flags,
                            &ctx->block_sum, &ctx->block_prefix, &ctx->block_chunk, &ctx->off_a, &ctx->off_b, &ctx->fix_mm, &ctx->fix_off, &ctx->mark_bits, &ctx->allinv_bits, &ctx->n_skips};
     for (auto b : bufs) b->release();
+    for (auto &b : ctx->patch_buf) b.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->pack) pgr::pack_ring_release(ctx->pack);
@@ -499,9 +500,21 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     cudaStream_t st = ctx->stream;
     const size_t n = ctx->rn;
     const uint32_t gap = (6 * spec.w + spec.k + 64 + 31) / 32 + 1;
-    DevBuf d_sorted, d_clusters, d_q, d_nadd, d_nfill, d_eoff, d_entries, d_meta, d_slab, d_list;
-    auto cleanup = [&]() { d_sorted.release(); d_clusters.release(); d_q.release(); d_nadd.release(); d_nfill.release(); d_eoff.release();
-                           d_entries.release(); d_meta.release(); d_slab.release(); d_list.release(); };
+    // scratch of the patch pass lives in the context (grow-only): allocating and releasing ten buffers per call cost more
+    // than the kernels (every release synchronises the device)
+    DevBuf &d_sorted = ctx->patch_buf[0], &d_clusters = ctx->patch_buf[1], &d_q = ctx->patch_buf[2], &d_nadd = ctx->patch_buf[3],
+           &d_nfill = ctx->patch_buf[4], &d_eoff = ctx->patch_buf[5], &d_entries = ctx->patch_buf[6], &d_meta = ctx->patch_buf[7],
+           &d_slab = ctx->patch_buf[8], &d_list = ctx->patch_buf[9];
+    auto cleanup = [&]() {};
+    // device -> host copies of the per-cluster tables go through the page-locked control buffer (a pageable destination
+    // makes the driver stage the copy, ~1 ms for the 2-3 MB of a 95 k cluster batch)
+    auto d2h = [&](void *dst, const void *src, size_t bytes) -> bool {
+        if (bytes == 0) return true;
+        if (ctx->ensure_ctl(bytes) != PGR_OK) return false;
+        if (cudaMemcpyAsync(ctx->h_ctl, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return false;
+        memcpy(dst, ctx->h_ctl, bytes);
+        return true;
+    };
     int rc = PGR_OK;
 #define PATCH_TRY(x) do { rc = (x); if (rc != PGR_OK) { cleanup(); return rc; } } while (0)
 #define PATCH_CUDA(x) do { if ((x) != cudaSuccess) { set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); cleanup(); return PGR_E_CUDA; } } while (0)
@@ -542,8 +555,7 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     PATCH_CUDA(cudaGetLastError());
     trace_mark("patches: clusters found");
     std::vector<Cluster> cl(n_cl);
-    PATCH_CUDA(cudaMemcpyAsync(cl.data(), d_clusters.p, (size_t)n_cl * sizeof(Cluster), cudaMemcpyDeviceToHost, st));
-    PATCH_CUDA(cudaStreamSynchronize(st));
+    if (!d2h(cl.data(), d_clusters.p, (size_t)n_cl * sizeof(Cluster))) { set_error("D2H of the cluster table failed"); return PGR_E_CUDA; }
     if (!in_order) std::sort(cl.begin(), cl.end(), [](const Cluster &a, const Cluster &b) { return a.sid != b.sid ? a.sid < b.sid : a.pos < b.pos; });
     // whole-sequence replays (flagged) need no patch; the rest in (sequence, position) order
     bool any_flagged = false;
@@ -572,10 +584,7 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     std::vector<uint32_t> h_q(3 * P), h_nfill(P);
     std::vector<uint64_t> h_nadd(P);
     auto fetch = [&]() -> bool {
-        return cudaMemcpyAsync(h_q.data(), d_q.p, P * 12, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-               cudaMemcpyAsync(h_nadd.data(), d_nadd.p, P * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-               cudaMemcpyAsync(h_nfill.data(), d_nfill.p, P * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-               cudaStreamSynchronize(st) == cudaSuccess;
+        return d2h(h_q.data(), d_q.p, P * 12) && d2h(h_nadd.data(), d_nadd.p, P * 8) && d2h(h_nfill.data(), d_nfill.p, P * 4);
     };
     if (!fetch()) { set_error("D2H of the patch table failed"); cleanup(); d_cyc.release(); return PGR_E_CUDA; }
     trace_mark("patches: pass A (thread per cluster)");
@@ -673,9 +682,7 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     splice_bounds_kernel<<<ceil_div<uint32_t>((uint32_t)P, 64), 64, 0, st>>>(sp);
     PATCH_CUDA(cudaGetLastError());
     std::vector<uint32_t> plb(P), pub(P);
-    PATCH_CUDA(cudaMemcpyAsync(plb.data(), sp.plb, P * 4, cudaMemcpyDeviceToHost, st));
-    PATCH_CUDA(cudaMemcpyAsync(pub.data(), sp.pub, P * 4, cudaMemcpyDeviceToHost, st));
-    PATCH_CUDA(cudaStreamSynchronize(st));
+    if (!d2h(plb.data(), sp.plb, P * 4) || !d2h(pub.data(), sp.pub, P * 4)) { set_error("D2H of the patch bounds failed"); return PGR_E_CUDA; }
     trace_mark("patches: write pass + bounds");
     // consecutive patches of a sequence must not overlap (the cluster gap guarantees it)
     for (size_t j = 0; j < P; j++) {

@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClust
                 const uint64_t mx = (h << 8) | (uint64_t)k;
                 const uint32_t my = ((uint32_t)pos << 1) | (rev ? 1u : 0u);
                 rx[r_end] = mx; ry[r_end] = my;
-                r_end = (r_end + 1) % (uint32_t)w;
-                if (r_len < (uint32_t)w) r_len++; else r_start = (r_start + 1) % (uint32_t)w;
+                r_end = (r_end + 1 == (uint32_t)w) ? 0u : r_end + 1;
+                if (r_len < (uint32_t)w) r_len++; else r_start = (r_start + 1 == (uint32_t)w) ? 0u : r_start + 1;
                 eq_count = (mx == last_x) ? eq_count + 1 : 1;
                 last_x = mx;
                 bool emitted = false, emitted_here = false;
@@ -247,8 +247,7 @@ __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClust
                     uint64_t mn = ~0ull;
                     for (uint32_t i = 0; i < r_len; i++) if (rx[i] < mn) mn = rx[i];
                     uint32_t last_y = 0;
-                    for (uint32_t i = 0; i < (uint32_t)w; i++) {
-                        const uint32_t sl = (r_start + i) % (uint32_t)w;
+                    for (uint32_t i = 0, sl = r_start; i < (uint32_t)w; i++, sl = (sl + 1 == (uint32_t)w) ? 0u : sl + 1) {
                         if (rx[sl] == mn) {
                             if (pos >= T0) {
                                 if (COOP ? MODE != 0 : n_add < RC_SLAB) { pgr_mm128 mm; mm.x = rx[sl]; mm.y = ((uint64_t)sid << 32) | ry[sl]; dst[n_add] = mm; }
