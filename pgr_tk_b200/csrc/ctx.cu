@@ -504,7 +504,7 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     // than the kernels (every release synchronises the device)
     DevBuf &d_sorted = ctx->patch_buf[0], &d_clusters = ctx->patch_buf[1], &d_q = ctx->patch_buf[2], &d_nadd = ctx->patch_buf[3],
            &d_nfill = ctx->patch_buf[4], &d_eoff = ctx->patch_buf[5], &d_entries = ctx->patch_buf[6], &d_meta = ctx->patch_buf[7],
-           &d_slab = ctx->patch_buf[8], &d_list = ctx->patch_buf[9];
+           &d_slab = ctx->patch_buf[8], &d_list = ctx->patch_buf[9], &d_hslab = ctx->patch_buf[10];
     auto cleanup = [&]() {};
     // device -> host copies of the per-cluster tables go through the page-locked control buffer (a pageable destination
     // makes the driver stage the copy, ~1 ms for the 2-3 MB of a 95 k cluster batch)
@@ -574,12 +574,14 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     rp.mark_bits = ctx->mark_bits.as<uint32_t>(); rp.allinv_bits = ctx->allinv_bits.as<uint32_t>();
     rp.clusters = d_clusters.as<Cluster>(); rp.list = nullptr; rp.n_list = (uint32_t)P; rp.w = spec.w; rp.k = spec.k; rp.gap = gap;
     rp.q0 = d_q.as<uint32_t>(); rp.q1 = rp.q0 + P; rp.t_stop = rp.q0 + 2 * P; rp.n_add = d_nadd.as<uint64_t>(); rp.n_fill = d_nfill.as<uint32_t>();
-    rp.entry_off = d_eoff.as<uint64_t>(); rp.entries = nullptr; rp.slab = d_slab.as<pgr_mm128>();
+    rp.entry_off = d_eoff.as<uint64_t>(); rp.entries = nullptr; rp.slab = d_slab.as<pgr_mm128>(); rp.hslab = nullptr;
     DevBuf d_cyc;
     const bool dbg_cycles = getenv("PGR_B200_DEBUG_PATCHES") != nullptr;
     if (dbg_cycles && (rc = d_cyc.ensure(P * 8)) != PGR_OK) { cleanup(); return rc; }
     rp.cycles = dbg_cycles ? d_cyc.as<unsigned long long>() : nullptr;
-    cluster_replay_kernel<0, 0><<<ceil_div<uint32_t>((uint32_t)P, RC_NT), RC_NT, 0, st>>>(rp);
+    { const int sl = ctx->timer.begin("patch_kernel_thread_per_cluster", st);
+      cluster_replay_kernel<0, 0><<<ceil_div<uint32_t>((uint32_t)P, RC_NT), RC_NT, 0, st>>>(rp);
+      ctx->timer.end(sl, st); }
     if (cudaGetLastError() != cudaSuccess) { set_error("cluster_replay_kernel launch failed"); cleanup(); d_cyc.release(); return PGR_E_CUDA; }
     std::vector<uint32_t> h_q(3 * P), h_nfill(P);
     std::vector<uint64_t> h_nadd(P);
@@ -596,7 +598,11 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
         if ((rc = d_list.ensure(heavy.size() * 4)) != PGR_OK) { cleanup(); d_cyc.release(); return rc; }
         cudaMemcpyAsync(d_list.p, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice, st);
         rp.list = d_list.as<uint32_t>(); rp.n_list = (uint32_t)heavy.size();
-        cluster_replay_kernel<0, 1><<<ceil_div<uint32_t>(rp.n_list, RC_NT / 32), RC_NT, 0, st>>>(rp);
+        if ((rc = d_hslab.ensure(heavy.size() * (size_t)RC_HSLAB * sizeof(pgr_mm128))) != PGR_OK) return rc;
+        rp.hslab = d_hslab.as<pgr_mm128>();
+        { const int sl = ctx->timer.begin("patch_kernel_warp_per_heavy_cluster", st);
+          cluster_replay_kernel<0, 1><<<ceil_div<uint32_t>(rp.n_list, RC_NT / 32), RC_NT, 0, st>>>(rp);
+          ctx->timer.end(sl, st); }
         if (cudaGetLastError() != cudaSuccess || !fetch()) { set_error("heavy cluster replay failed"); cleanup(); d_cyc.release(); return PGR_E_CUDA; }
         trace_mark("patches: heavy clusters, count pass");
     }
@@ -633,7 +639,13 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     uint64_t n_entries = 0, n_fills = 0, n_heavy_entries = 0;
     std::vector<uint64_t> eoff(P0, 0);
     std::vector<uint32_t> heavy_keep;
-    for (uint32_t j : keep) { n_entries += h_nadd[j]; n_fills += h_nfill[j]; if (is_heavy[j]) { eoff[j] = n_heavy_entries; n_heavy_entries += h_nadd[j]; heavy_keep.push_back(j); } }
+    // heavy clusters whose entries fit the slab of the count pass are final; only the others are replayed once more
+    std::vector<uint32_t> heavy_slot(P0, 0);   // position of a heavy cluster in the count pass's list = its slab
+    for (size_t t = 0; t < heavy.size(); t++) heavy_slot[heavy[t]] = (uint32_t)t;
+    for (uint32_t j : keep) {
+        n_entries += h_nadd[j]; n_fills += h_nfill[j];
+        if (is_heavy[j] && h_nadd[j] > (uint64_t)RC_HSLAB) { eoff[j] = n_heavy_entries; n_heavy_entries += h_nadd[j]; heavy_keep.push_back(j); }
+    }
     if ((rc = d_entries.ensure(std::max<uint64_t>(1, n_heavy_entries) * sizeof(pgr_mm128))) != PGR_OK) { cleanup(); return rc; }
     if (!heavy_keep.empty()) {
         cudaMemcpyAsync(d_eoff.p, eoff.data(), P0 * 8, cudaMemcpyHostToDevice, st);
@@ -648,7 +660,8 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
         std::vector<Cluster> kcl; std::vector<uint32_t> kq0, kq1, knf; std::vector<uint64_t> kna;
         for (uint32_t j : keep) {
             kcl.push_back(cl[j]); kq0.push_back(h_q[j]); kq1.push_back(h_q[P0 + j]); kna.push_back(h_nadd[j]); knf.push_back(h_nfill[j]);
-            psrc.push_back(is_heavy[j] ? d_entries.as<pgr_mm128>() + eoff[j] : d_slab.as<pgr_mm128>() + (size_t)j * RC_SLAB);
+            psrc.push_back(!is_heavy[j] ? d_slab.as<pgr_mm128>() + (size_t)j * RC_SLAB
+                           : h_nadd[j] > (uint64_t)RC_HSLAB ? d_entries.as<pgr_mm128>() + eoff[j] : d_hslab.as<pgr_mm128>() + (size_t)heavy_slot[j] * RC_HSLAB);
         }
         cl.swap(kcl); h_nadd.swap(kna); h_nfill.swap(knf);
         h_q.assign(kq0.begin(), kq0.end());
@@ -710,8 +723,10 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     PATCH_CUDA(cudaMemcpyAsync((void *)sp.off1, off1.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     PATCH_TRY(ctx->bufB.ensure(std::max<uint64_t>(1, acc) * sizeof(pgr_mm128)));
     sp.flat1 = ctx->bufB.as<pgr_mm128>();
-    if (sp.n0) splice_copy_kernel<<<(uint32_t)ceil_div<uint64_t>(sp.n0, 256), 256, 0, st>>>(sp);
-    splice_patch_kernel<<<(uint32_t)P, 256, 0, st>>>(sp);
+    { const int sl = ctx->timer.begin("patch_kernel_splice", st);
+      if (sp.n0) splice_copy_kernel<<<(uint32_t)ceil_div<uint64_t>(sp.n0, 256), 256, 0, st>>>(sp);
+      splice_patch_kernel<<<(uint32_t)P, 256, 0, st>>>(sp);
+      ctx->timer.end(sl, st); }
     PATCH_CUDA(cudaGetLastError());
     PATCH_CUDA(cudaMemcpyAsync(ctx->seq_dst.p, off1.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     ctx->timer.end(slot_t, st);

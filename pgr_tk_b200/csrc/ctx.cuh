@@ -70,7 +70,7 @@ struct pgr_b200_ctx {
     // shimmer pipeline buffers
     pgr::DevBuf tile_prefix, cta_tile, arena, chunk_count, seq_count, seq_flag, replay_list, replay_count;
     pgr::DevBuf chunk_prefix, seq_fast, seq_dst, bufA, bufB, flags, block_sum, block_prefix, block_chunk, off_a, off_b, mark_bits, allinv_bits, n_skips;
-    pgr::DevBuf patch_buf[10];          // scratch of apply_patches (cluster tables, slabs, splice metadata)
+    pgr::DevBuf patch_buf[11];          // scratch of apply_patches (cluster tables, slabs, splice metadata)
     uint64_t bits_dirty_lo = 0, bits_dirty_hi = 0;   // bitmap words an earlier launch may have set (cleared lazily)
     uint64_t chunk_cap = 0;
     // result of the last shmmrs call

@@ -120,6 +120,8 @@ struct ReplayClusterParams {
     const uint64_t *entry_off;    // [n_clusters] where the patch's entries go (COOP = 1, MODE 1)
     pgr_mm128 *entries;
     pgr_mm128 *slab;              // [n_clusters * RC_SLAB] (COOP = 0)
+    pgr_mm128 *hslab;             // [n_list * RC_HSLAB] (COOP = 1, MODE 0): the count pass of a heavy cluster keeps its first RC_HSLAB
+                                  // entries, so that only the clusters with more need the write pass; NULL = count only
 };
 
 // k-mer registers after the bytes [.., upto): the last k machine-valid bases before `upto` (shmmrutils.rs:461-476 updates
@@ -157,6 +159,7 @@ __device__ __forceinline__ MachineRegs load_regs(const uint8_t *sq, int64_t upto
 constexpr int RC_NT = 128;
 constexpr int RC_SLAB = 96;
 constexpr int RC_BUDGET = 2048;
+constexpr int RC_HSLAB = 1024;
 constexpr uint32_t RC_HEAVY = 0xFFFFFFFEu;
 template <int MODE, int COOP>
 __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClusterParams p) {
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClust
     uint64_t n_add = 0;
     bool done = false;
     int64_t pos = S, no_scan_before = 0;
-    pgr_mm128 *dst = COOP ? (MODE ? p.entries + p.entry_off[ci] : nullptr) : p.slab + (size_t)ci * RC_SLAB;
+    pgr_mm128 *dst = COOP ? (MODE ? p.entries + p.entry_off[ci] : (p.hslab ? p.hslab + (size_t)li * RC_HSLAB : nullptr)) : p.slab + (size_t)ci * RC_SLAB;
+    const uint64_t wcap = COOP ? (MODE ? ~0ull : (p.hslab ? (uint64_t)RC_HSLAB : 0ull)) : (uint64_t)RC_SLAB;   // entries below it are written
     int64_t steps = 0;
     bool heavy = false;
     if (lane == 0) {
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClust
                     for (uint32_t i = 0, sl = r_start; i < (uint32_t)w; i++, sl = (sl + 1 == (uint32_t)w) ? 0u : sl + 1) {
                         if (rx[sl] == mn) {
                             if (pos >= T0) {
-                                if (COOP ? MODE != 0 : n_add < RC_SLAB) { pgr_mm128 mm; mm.x = rx[sl]; mm.y = ((uint64_t)sid << 32) | ry[sl]; dst[n_add] = mm; }
+                                if (n_add < wcap) { pgr_mm128 mm; mm.x = rx[sl]; mm.y = ((uint64_t)sid << 32) | ry[sl]; dst[n_add] = mm; }
                                 n_add++;
                             } else {
                                 q0 = ry[sl] >> 1;
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClust
                     emitted_here = (last_y >> 1) == (uint32_t)pos;
                 } else if (mx <= min_x && pos >= w + k && pos < E && pos < L) {
                     if (pos >= T0) {
-                        if (COOP ? MODE != 0 : n_add < RC_SLAB) { pgr_mm128 mm; mm.x = mx; mm.y = ((uint64_t)sid << 32) | my; dst[n_add] = mm; }
+                        if (n_add < wcap) { pgr_mm128 mm; mm.x = mx; mm.y = ((uint64_t)sid << 32) | my; dst[n_add] = mm; }
                         n_add++;
                     } else {
                         q0 = (uint32_t)pos;
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClust
                         const int64_t cnt = P - pos;
                         for (int64_t i = 1; i <= cnt; i++) {
                             if (i > FILL_KEEP && i <= cnt - FILL_KEEP) { i = cnt - FILL_KEEP; continue; }
-                            if (COOP ? MODE != 0 : n_add < RC_SLAB) { pgr_mm128 mm; mm.x = mx; mm.y = ((uint64_t)sid << 32) | ((uint64_t)(uint32_t)(pos + i) << 1) | (rev ? 1u : 0u); dst[n_add] = mm; }
+                            if (n_add < wcap) { pgr_mm128 mm; mm.x = mx; mm.y = ((uint64_t)sid << 32) | ((uint64_t)(uint32_t)(pos + i) << 1) | (rev ? 1u : 0u); dst[n_add] = mm; }
                             n_add++;
                         }
                         n_fill++;
