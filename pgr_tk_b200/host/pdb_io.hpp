@@ -44,6 +44,8 @@ struct Reader {
         p += n;
         return v;
     }
+    // element count, bounded by the remaining bytes before anything is allocated from it
+    uint64_t count() { const uint64_t n = varint(); if (!ok || n > (uint64_t)(e - p)) { ok = false; return 0; } return n; }
 };
 }  // namespace pdb_detail
 
@@ -72,15 +74,15 @@ inline bool decode_pdb(const std::vector<uint8_t> &buf, PdbData &d) {
     pdb_detail::Reader r{buf.data() + 7, buf.data() + buf.size()};
     d.w = (uint32_t)r.varint(); d.k = (uint32_t)r.varint(); d.r = (uint32_t)r.varint(); d.min_span = (uint32_t)r.varint();
     d.min_branch_size = r.varint(); d.min_cov = r.varint();
-    d.bundles.assign((size_t)r.varint(), {});
+    d.bundles.assign((size_t)r.count(), {});
     for (auto &b : d.bundles) {
         if (!r.ok) return false;
         b.bundle_id = (size_t)r.varint(); b.mean_order = (size_t)r.varint();
-        b.vertices.assign((size_t)r.varint(), {});
+        b.vertices.assign((size_t)r.count(), {});
         for (auto &v : b.vertices) { v.h0 = r.varint(); v.h1 = r.varint(); v.ori = r.u8(); }
     }
     d.vmap.clear();
-    const uint64_t n = r.varint();
+    const uint64_t n = r.count();
     for (uint64_t i = 0; i < n && r.ok; i++) {
         const uint64_t h0 = r.varint(), h1 = r.varint();
         BundleRef br;

@@ -238,6 +238,9 @@ struct BinReader {
         p += n;
         return v;
     }
+    // an element count: every element takes at least one byte, so a count above the remaining bytes is a corrupt file (checked
+    // BEFORE anything is allocated from it)
+    uint64_t count() { const uint64_t n = varint(); if (!ok || n > (uint64_t)(e - p)) { ok = false; return 0; } return n; }
     bool bytes(std::vector<uint8_t> &o) { const uint64_t n = varint(); if (!ok || (uint64_t)(e - p) < n) { ok = false; return false; } o.assign(p, p + n); p += n; return true; }
     bool str(std::string &o) { const uint64_t n = varint(); if (!ok || (uint64_t)(e - p) < n) { ok = false; return false; } o.assign((const char *)p, n); p += n; return true; }
 };
@@ -284,10 +287,10 @@ bool FragStore::load(const std::string &prefix, uint32_t k, std::string &err) {
     if (!slurp_plain(prefix + ".frg", frg_) || frg_.size() < 7 || memcmp(frg_.data(), "FRG:0.5", 7) != 0) { err = "frg file open / version error"; return false; }
     BinReader r{sd.data() + 7, sd.data() + sd.size()};
     chunk_size_ = r.varint();
-    const uint64_t na = r.varint();
+    const uint64_t na = r.count();
     addr_.clear();
     for (uint64_t i = 0; i < na && r.ok; i++) { Addr a; a.off = r.varint(); a.len = r.varint(); a.bases = r.varint(); addr_.push_back(a); }
-    const uint64_t nsq = r.varint();
+    const uint64_t nsq = r.count();
     seqs_.clear();
     for (uint64_t i = 0; i < nsq && r.ok; i++) {
         SeqEntry s;
@@ -311,12 +314,12 @@ const FragStore::Fragment *FragStore::fragment(uint32_t id, std::string &err) {
     std::vector<uint8_t> raw;
     if (!inflate_raw(frg_.data() + 7 + a.off, a.len, raw)) { err = "frg chunk inflate error"; return nullptr; }
     BinReader r{raw.data(), raw.data() + raw.size()};
-    std::vector<Fragment> fr((size_t)r.varint());
+    std::vector<Fragment> fr((size_t)r.count());
     for (auto &f : fr) {
         f.kind = (uint8_t)r.varint();
         if (f.kind == 0) {
             f.ref = (uint32_t)r.varint(); f.reversed = r.u8() != 0; f.len = (uint32_t)r.varint();
-            f.segs.resize((size_t)r.varint());
+            f.segs.resize((size_t)r.count());
             for (auto &s : f.segs) {
                 s.type = (uint32_t)r.varint(); s.a = s.b = 0;
                 if (s.type == 1) { s.a = (uint32_t)r.varint(); s.b = (uint32_t)r.varint(); } else if (s.type == 2) s.a = r.u8();

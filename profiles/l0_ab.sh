@@ -1,6 +1,9 @@
 #!/bin/bash
-# A/B of the level-0 kernel variants (run on the B200 box): device-resident config-2 step, 10 timed steps each
-for v in default bulk256p plain224; do
+# A/B of the level-0 kernel variants (run on the B200 box): device-resident config-2 step, 10 timed steps each, twice in
+# alternation.  Variants are alternative builds of the library under profiles/ab/ (git-ignored; see the nvcc line in
+# profiles/r2_l0_kernel_bulk_ab.txt), selected through PGR_B200_LIB.
+for round in 1 2; do
+for v in default plain; do
   if [ $v = default ]; then unset PGR_B200_LIB; else export PGR_B200_LIB=$PWD/profiles/ab/libpgr_b200_$v.so; fi
   python - <<PY
 import json, subprocess, sys, os
@@ -11,4 +14,5 @@ try:
 except Exception as e:
     print("$v FAILED", r.stderr[-400:])
 PY
+done
 done
