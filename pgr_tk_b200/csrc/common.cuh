@@ -75,6 +75,29 @@ __device__ __forceinline__ void u64hash_dev32m(uint32_t &lo, uint32_t &hi, uint6
     xorshift_r<28>(lo, hi);
     mul64c<0x80000001u>(lo, hi);
 }
+// PGR_L0_HIMASK: which right shifts of the HIGH word in the key loop's hashes run on the FMA pipe as IMAD.HI with an
+// opaque power-of-two factor (a kernel parameter, so that the compiler cannot turn it back into a shift) instead of SHF on the
+// ALU pipe, which is the pipe that bounds the kernel: bit 0 = the >> 24, bit 1 = the >> 14, bit 2 = the >> 28 of u64hash,
+// bit 3 = the >> (64 - K) that makes the high words of the two plane registers.  A/B in profiles/r2_l0_kernel_himask_ab.txt.
+#ifndef PGR_L0_HIMASK
+#define PGR_L0_HIMASK 0
+#endif
+struct HiShift { uint32_t c24, c14, c28, chs; };   // 2^(32-24), 2^(32-14), 2^(32-28), 2^(32-(64-K))
+template <int S, bool HI>
+__device__ __forceinline__ void xorshift_r_x(uint32_t &lo, uint32_t &hi, uint32_t c) {   // key ^= key >> S, 0 < S < 32
+    const uint32_t t_lo = __funnelshift_r(lo, hi, S);
+    const uint32_t t_hi = HI ? __umulhi(hi, c) : (hi >> S);
+    lo ^= t_lo; hi ^= t_hi;
+}
+__device__ __forceinline__ void u64hash_dev32x(uint32_t &lo, uint32_t &hi, uint64_t m1, const HiShift &c) {
+    mul64c<0x1FFFFFu>(lo, hi, m1);
+    xorshift_r_x<24, (PGR_L0_HIMASK & 1) != 0>(lo, hi, c.c24);
+    mul64c<265u>(lo, hi);
+    xorshift_r_x<14, (PGR_L0_HIMASK & 2) != 0>(lo, hi, c.c14);
+    mul64c<21u>(lo, hi);
+    xorshift_r_x<28, (PGR_L0_HIMASK & 4) != 0>(lo, hi, c.c28);
+    mul64c<0x80000001u>(lo, hi);
+}
 __device__ __forceinline__ uint64_t u64hash_dev(uint64_t key) {
     uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
     u64hash_dev32(lo, hi);

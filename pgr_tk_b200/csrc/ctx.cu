@@ -832,6 +832,8 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
         p.seq_flag = ctx->seq_flag.as<uint32_t>();
         p.mark_bits = ctx->mark_bits.as<uint32_t>(); p.allinv_bits = ctx->allinv_bits.as<uint32_t>(); p.n_marks = ctx->n_skips.as<uint32_t>();
         p.m1 = ~0ull;
+        p.hs.c24 = 1u << (32 - 24); p.hs.c14 = 1u << (32 - 14); p.hs.c28 = 1u << (32 - 28);
+        p.hs.chs = (k > 32) ? 1u << (32 - (64 - k)) : 0u;   // used by the K > 32 kernels only (64 - K < 32)
         trace_mark("run_l0: arena + memsets");
         const int slot = ctx->timer.begin("l0_minimizers", st);
         if (variant == 1) PGR_TRY((launch_l0<80, 56>(p, (int)G, st)));

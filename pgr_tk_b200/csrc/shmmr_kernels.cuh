@@ -46,9 +46,16 @@ constexpr int L0_SLOT_OFF = ((L0_SLOT_TOP - L0_SLOT_BYTES) - (((L0_SLOT_TOP - L0
 static_assert(L0_SLOT_OFF > 0 && (L0_ARR * 4 + L0_SLOT_OFF) % 128 == 0 && L0_SLOT_OFF + L0_SLOT_BYTES <= L0_SLOT_TOP, "tile slot placement");
 static_assert(L0_SLOT_OFF / 2 >= L0_KPOS + 256, "the candidate list must fit below the slot");
 constexpr int L0_LISTCAP = L0_SLOT_OFF / 2; // u16 entries of the P array below the slot
+constexpr int L0_CH_TOP = L0_SLOT_OFF / 4;  // first P word that belongs to the slot
 #else
 constexpr int L0_LISTCAP = L0_ARR * 2;     // u16 entries that fit in the P array
+constexpr int L0_CH_TOP = L0_ARR;
 #endif
+// key prefixes of the candidates, in list order, in the P words behind the largest possible candidate list: phase 5 compares
+// neighbouring candidates through it with independent loads instead of list -> H chains
+constexpr int L0_CH_OFF = (L0_KPOS + 256) / 2;      // first word
+constexpr int L0_CH_CAP = L0_CH_TOP - L0_CH_OFF;    // entries; a tile with more candidates takes the chained form
+static_assert(L0_CH_CAP >= 1024, "room for the candidates' key prefixes");
 
 struct L0Params {
     const uint8_t *seq;          // device sequence store
@@ -71,6 +78,7 @@ struct L0Params {
     uint32_t *n_marks;           // number of marking events (0 => the level-0 list needs no patch)
     uint64_t m1;                 // ~0 (the -1 of the hash's first step) as a parameter: an IMAD.WIDE addend straight from the constant bank
                                  // instead of two MOVs per position
+    HiShift hs;                  // opaque power-of-two factors of the IMAD.HI shifts (PGR_L0_HIMASK)
 };
 
 __device__ __forceinline__ uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
@@ -125,6 +133,12 @@ __device__ __forceinline__ bool byte_is_acgt(uint32_t c) {
 __device__ __forceinline__ uint32_t min3u(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
 __device__ __forceinline__ uint32_t max3u(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
 
+struct DescCache {
+    uint32_t sid;                    // UINT32_MAX = nothing cached
+    uint32_t tp_lo, tp_hi;           // tile_prefix[sid], tile_prefix[sid + 1]
+    uint32_t len;
+    uint64_t off;
+};
 struct L0Smem {
     uint32_t H[L0_ARR];      // key prefix: the top bits of MM128.x (hash bits 32..55 in the K > 32 kernels, 24..55 in the
                              // generic one); padded index q + q/32 + PADB*33
@@ -148,6 +162,7 @@ struct L0Smem {
         uint32_t pad_;
         uint64_t seq_off;
     } td[2];
+    DescCache dc;            // thread 0 only (shared memory instead of six registers of every thread)
 };
 
 __device__ __forceinline__ int pidx(int q) { return q + (q >> 5) + L0_PADB * 33; }  // q may be negative (>= -PADB*32)
@@ -233,26 +248,31 @@ __device__ __noinline__ bool selected_exact(const L0Smem &s, int q, int pos, int
     return l + r + 1 >= w;
 }
 
-// tile -> descriptor (executed by one thread).  sid_hint = sequence of the previous tile of this CTA (tiles are handed
-// out in order, so the next tile belongs to the same sequence or to one shortly after it: no binary search, whose ten
-// dependent loads would keep the whole CTA waiting at the next barrier); UINT32_MAX = none (first tile of the CTA).
-__device__ __forceinline__ uint32_t make_tile_desc(const L0Params &p, uint32_t tile, uint32_t w, L0Smem::TileDesc &d, uint32_t sid_hint) {
-    uint32_t sid;
-    if (sid_hint != 0xFFFFFFFFu) {
-        sid = sid_hint;
-        while (p.tile_prefix[sid + 1] <= tile) sid++;   // sequences without tiles (L <= k) are skipped
-    } else {
-        // (sequence, tile index): largest sid with tile_prefix[sid] <= tile
-        uint32_t lo = 0, hi = p.n_seq;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (p.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+// tile -> descriptor (executed by one thread).  The sequence of the newest descriptor is kept in shared memory
+// (DescCache): tiles are handed out in order, so the next tile nearly always belongs to the same sequence and needs no
+// global load at all — the three dependent loads of a fresh look-up (~1.5 us) sat in front of a barrier of every tile.
+// A new sequence is found by walking forward from the cached one; the first tile of a CTA takes a binary search.
+__device__ __forceinline__ void make_tile_desc(const L0Params &p, uint32_t tile, uint32_t w, L0Smem::TileDesc &d, DescCache &c) {
+    if (c.sid == 0xFFFFFFFFu || tile >= c.tp_hi) {
+        uint32_t sid;
+        if (c.sid != 0xFFFFFFFFu) {
+            sid = c.sid + 1;
+            while (p.tile_prefix[sid + 1] <= tile) sid++;   // sequences without tiles (L <= k) are skipped
+        } else {
+            // (sequence, tile index): largest sid with tile_prefix[sid] <= tile
+            uint32_t lo = 0, hi = p.n_seq;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (p.tile_prefix[mid] <= tile) lo = mid; else hi = mid;
+            }
+            sid = lo;
         }
-        sid = lo;
+        c.sid = sid; c.tp_lo = p.tile_prefix[sid]; c.tp_hi = p.tile_prefix[sid + 1]; c.len = p.len[sid]; c.off = p.off[sid];
     }
-    const uint32_t j = tile - p.tile_prefix[sid];
-    const uint32_t L = p.len[sid];
-    const uint32_t nt = p.tile_prefix[sid + 1] - p.tile_prefix[sid];
+    const uint32_t sid = c.sid;
+    const uint32_t j = tile - c.tp_lo;
+    const uint32_t L = c.len;
+    const uint32_t nt = c.tp_hi - c.tp_lo;
     int32_t ks = (int32_t)(j * p.tile_stride) - (int32_t)p.halo;
     const bool last = (j + 1 == nt);
     if (last) {  // the tail replay needs keys and selections back to E - 2w: pull the tile back if it is short
@@ -263,9 +283,8 @@ __device__ __forceinline__ uint32_t make_tile_desc(const L0Params &p, uint32_t t
     d.seq_id = sid; d.seq_len = L; d.keys_start = ks; d.is_last = last ? 1u : 0u;
     d.out_lo = (int32_t)(j * p.tile_stride);
     d.out_hi = (int32_t)min((uint64_t)L, (uint64_t)(j + 1) * p.tile_stride);
-    d.seq_off = p.off[sid];
+    d.seq_off = c.off;
     d.bad = 0; d.n_tail = 0; d.any_reject = 0; d.n_pre = 0; d.n_post = 0;
-    return sid;
 }
 
 // cold path: mark the 32-base block at sequence position blk_pos as disturbed (idempotent; halo blocks are marked by
@@ -329,8 +348,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
     for (int i = tid; i < L0_ARR; i += L0_NT) { s.H[i] = 0; s.P[i] = 0; }
 
     // first tile: descriptor + this thread's 32 bases
-    uint32_t desc_sid = 0xFFFFFFFFu;   // thread 0: sequence of the newest descriptor
-    if (tid == 0 && t_begin < t_end) desc_sid = make_tile_desc(p, t_begin, w, s.td[0], desc_sid);
+    if (tid == 0) { s.dc.sid = 0xFFFFFFFFu; if (t_begin < t_end) make_tile_desc(p, t_begin, w, s.td[0], s.dc); }
     __syncthreads();
     uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
 #if PGR_L0_BULK
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
     for (uint32_t tile = t_begin; tile < t_end; ++tile, cur ^= 1) {
         L0Smem::TileDesc &D = s.td[cur];
         const bool has_next = tile + 1 < t_end;
-        if (tid == 0 && has_next) desc_sid = make_tile_desc(p, tile + 1, w, s.td[cur ^ 1], desc_sid);   // overlaps with phases 1-2 of this tile
+        if (tid == 0 && has_next) make_tile_desc(p, tile + 1, w, s.td[cur ^ 1], s.dc);   // overlaps with phases 1-2 of this tile
         const int32_t L = (int32_t)D.seq_len;
         const int32_t keys_start = D.keys_start;
         const int32_t blk_pos = keys_start + 32 * (tid - L0_CTX);  // sequence position of this thread's first base
@@ -446,6 +464,7 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                 const uint32_t q0p0 = fsr(q00, q01, PS), q0p1 = fsr(q01, q02, PS);
                 const uint32_t q1p0 = fsr(q10, q11, PS), q1p1 = fsr(q11, q12, PS);
                 const uint64_t m1 = p.m1;
+                const HiShift hsc = p.hs;
                 bool no_tie = true;   // stays true unless some position of the block has X_f == X_r
 #pragma unroll U
                 for (int i = 0; i < 32; i++) {
@@ -464,10 +483,12 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
                         : "=&r"(ulo), "=&r"(vlo), "=&r"(vx)
                         : "r"(r0x), "r"(f0x), "r"(q00), "r"(q01), "r"(q10), "r"(q11), "r"(q1p0), "r"(q1p1),
                           "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(b0p), "r"(b1p), "r"((uint32_t)i), "r"(sl));
-                    uint32_t uhi = ux >> HS, vhi = vx >> HS;
+                    uint32_t uhi, vhi;
+                    if ((PGR_L0_HIMASK & 8) != 0) { uhi = __umulhi(ux, hsc.chs); vhi = __umulhi(vx, hsc.chs); }
+                    else { uhi = ux >> HS; vhi = vx >> HS; }
                     vlo ^= (uint32_t)HASH_XOR;
-                    u64hash_dev32m(ulo, uhi, m1);
-                    u64hash_dev32m(vlo, vhi, m1);
+                    u64hash_dev32x(ulo, uhi, m1, hsc);
+                    u64hash_dev32x(vlo, vhi, m1, hsc);
                     // key prefix of this kernel: the top 24 bits of MM128.x = hash bits 32..55 (one LOP3); any prefix of x
                     // orders consistently with x, and prefix ties between candidates are resolved exactly in phase 5
                     s.H[base + i] = (uhi ^ vhi) & 0x00FFFFFFu;
@@ -645,12 +666,17 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         }
         const uint32_t lo_idx = D.n_pre;                       // list index of the first candidate in the output range
         const uint32_t n_in = total - D.n_pre - D.n_post;      // candidates in the output range
+        uint32_t *const chv = s.P + L0_CH_OFF;
+        const bool ch_ok = total <= (uint32_t)L0_CH_CAP;
         {
             uint32_t dst = wbase + incl - cnt, rem = cand;
+            const int hb = pidx(32 * kb);
             while (rem) {
                 const int o = __ffs(rem) - 1;
                 rem &= rem - 1;
-                list[dst++] = (uint16_t)(32 * kb + o);
+                list[dst] = (uint16_t)(32 * kb + o);
+                if (ch_ok) chv[dst] = s.H[hb + o];
+                dst++;
             }
         }
         __syncthreads();
@@ -660,10 +686,37 @@ __global__ void __launch_bounds__(L0_NT, L0_MIN_CTAS) l0_kernel(const L0Params p
         // (the other may sit in the halo) is tested exactly; a rejected one is marked (bit 15) and dropped below.
         for (uint32_t j = lo_idx + tid; j < lo_idx + n_in; j += L0_NT) {
             const int q = list[j] & 0x7FFF;
-            const uint32_t hq = s.H[pidx(q)];
             bool tie = false;
-            for (int jj = (int)j - 1; jj >= 0 && q - (int)(list[jj] & 0x7FFF) < (int)w && !tie; jj--) tie = (s.H[pidx(list[jj] & 0x7FFF)] == hq);
-            for (uint32_t jj = j + 1; jj < total && (int)(list[jj] & 0x7FFF) - q < (int)w && !tie; jj++) tie = (s.H[pidx(list[jj] & 0x7FFF)] == hq);
+            if (ch_ok) {
+                // four neighbours per side and round, all loads independent (positions from the list, prefixes from chv); a
+                // round whose farthest neighbour is still within w of q is followed by another one (rare)
+                const uint32_t hq = chv[j];
+                for (int jj = (int)j - 1; jj >= 0 && !tie;) {
+                    const int i0 = jj, i1 = max(jj - 1, 0), i2 = max(jj - 2, 0), i3 = max(jj - 3, 0);
+                    const int q0 = list[i0] & 0x7FFF, q1 = list[i1] & 0x7FFF, q2 = list[i2] & 0x7FFF, q3 = list[i3] & 0x7FFF;
+                    const uint32_t h0 = chv[i0], h1 = chv[i1], h2 = chv[i2], h3 = chv[i3];
+                    const bool n0 = q - q0 < (int)w, n1 = n0 && jj >= 1 && q - q1 < (int)w, n2 = n1 && jj >= 2 && q - q2 < (int)w,
+                               n3 = n2 && jj >= 3 && q - q3 < (int)w;
+                    tie = (n0 && h0 == hq) || (n1 && h1 == hq) || (n2 && h2 == hq) || (n3 && h3 == hq);
+                    if (!n3) break;
+                    jj -= 4;
+                }
+                for (uint32_t jj = j + 1; jj < total && !tie;) {
+                    const uint32_t last = total - 1;
+                    const uint32_t i0 = jj, i1 = min(jj + 1, last), i2 = min(jj + 2, last), i3 = min(jj + 3, last);
+                    const int q0 = list[i0] & 0x7FFF, q1 = list[i1] & 0x7FFF, q2 = list[i2] & 0x7FFF, q3 = list[i3] & 0x7FFF;
+                    const uint32_t h0 = chv[i0], h1 = chv[i1], h2 = chv[i2], h3 = chv[i3];
+                    const bool n0 = q0 - q < (int)w, n1 = n0 && jj + 1 <= last && q1 - q < (int)w, n2 = n1 && jj + 2 <= last && q2 - q < (int)w,
+                               n3 = n2 && jj + 3 <= last && q3 - q < (int)w;
+                    tie = (n0 && h0 == hq) || (n1 && h1 == hq) || (n2 && h2 == hq) || (n3 && h3 == hq);
+                    if (!n3) break;
+                    jj += 4;
+                }
+            } else {
+                const uint32_t hq = s.H[pidx(q)];
+                for (int jj = (int)j - 1; jj >= 0 && q - (int)(list[jj] & 0x7FFF) < (int)w && !tie; jj--) tie = (s.H[pidx(list[jj] & 0x7FFF)] == hq);
+                for (uint32_t jj = j + 1; jj < total && (int)(list[jj] & 0x7FFF) - q < (int)w && !tie; jj++) tie = (s.H[pidx(list[jj] & 0x7FFF)] == hq);
+            }
             if (tie && !selected_exact(s, q, q + keys_start, (int)w, a_lo, a_hi, k)) { list[j] = (uint16_t)(q | 0x8000); D.any_reject = 1u; }
         }
         __syncthreads();

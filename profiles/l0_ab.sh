@@ -3,7 +3,7 @@
 # alternation.  Variants are alternative builds of the library under profiles/ab/ (git-ignored; see the nvcc line in
 # profiles/r2_l0_kernel_bulk_ab.txt), selected through PGR_B200_LIB.
 for round in 1 2; do
-for v in default plain; do
+for v in ${VARIANTS:-default plain}; do
   if [ $v = default ]; then unset PGR_B200_LIB; else export PGR_B200_LIB=$PWD/profiles/ab/libpgr_b200_$v.so; fi
   python - <<PY
 import json, subprocess, sys, os
