@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-index", action="store_true", help="skip the config-3 index build (index_build object)")
     ap.add_argument("--no-assembly", action="store_true", help="skip the assembly-like variant of the batch")
+    ap.add_argument("--no-sketch", action="store_true", help="skip the sketch-mode leg")
     ap.add_argument("--index-haps", type=int, default=94)
     ap.add_argument("--index-hap-len", type=int, default=50_000_000)
     return ap.parse_args()
@@ -324,6 +325,39 @@ def main():
                "sample": "first %d of %d contigs x %d bases, one sequence per thread (seq_db.rs:461); parity of these contigs checked" % (n_sample, n_contigs, clen)}
         del sample, seqs, got
 
+    # ---- sketch mode of the same call (ShmmrSpec.sketch, shmmrutils.rs:558-630) on the same resident batch, rank 0 / N = 1 ----
+    sketch = None
+    if world == 1 and not args.no_sketch:
+        sspec = pg.ShmmrSpec(*SPEC, True)
+        for _ in range(2):
+            n_sk = ctx.shmmrs(sspec)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = min(5, args.steps)
+        k0.record(stream)
+        for _ in range(reps):
+            n_sk = ctx.shmmrs(sspec)
+        k1.record(stream)
+        torch.cuda.synchronize()
+        s_ms = k0.elapsed_time(k1) / reps
+        sk_stages = dict(ctx.timings())
+        # the dominant kernel reads 1 B per base and writes 8 B of masks per 32 bases
+        sketch = {"value": bases / (s_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": s_ms, "reps": reps, "shmmrs": int(n_sk),
+                  "stages_ms": sk_stages, "spec": "k=56 r=4 min_span=64 sketch=true (threshold 2^(60-r): 1 position in 256 before the span filter)",
+                  "mask_kernel_algorithmic_gbs": (bases * (1.0 + 8.0 / 32.0)) / (sk_stages.get("sketch_masks", s_ms) * 1e-3) / 1e9}
+        if not args.no_cpu:
+            import orc
+            n_chk = min(n_contigs, 8)
+            sample = store[SLACK: SLACK + n_chk * clen].cpu().numpy()
+            cpu_out, cpu_off = orc.shmmrs_batch(list(range(n_chk)), [sample[i * clen:(i + 1) * clen] for i in range(n_chk)],
+                                                orc.mkspec(*SPEC, True), False, nthreads=host_cores())
+            got, goff = ctx.shmmrs_download()
+            kk = int(goff[n_chk])
+            sketch["parity_first_%d_contigs_vs_oracle" % n_chk] = bool(kk == int(cpu_off[-1]) and np.array_equal(got[:kk], cpu_out))
+            assert sketch["parity_first_%d_contigs_vs_oracle" % n_chk], "sketch mode: GPU result differs from the oracle"
+            del sample
+        ctx.shmmrs(spec)   # leave the minimizer result resident, as the legs below expect
+
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------------------
     e2e = e2e_direct = e2e_pageable = assembly = None
     if not args.no_e2e:
@@ -469,6 +503,8 @@ def main():
             line["e2e_pageable"] = e2e_pageable
         if assembly is not None:
             line["assembly_like"] = assembly
+        if sketch is not None:
+            line["sketch_mode"] = sketch
         if index_build is not None:
             line["index_build"] = index_build
         if cpu is not None:

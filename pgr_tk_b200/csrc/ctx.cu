@@ -12,6 +12,7 @@
 
 #include "pack_upload.cuh"
 #include "patch_kernels.cuh"
+#include "sketch_kernels.cuh"
 
 namespace pgr {
 
@@ -949,53 +950,110 @@ int run_l0(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     return PGR_OK;
 }
 
-// sketch mode (shmmrutils.rs:558-630): flat list of kept k-mers in ctx->bufA, offsets in ctx->seq_dst
+// sketch mode (shmmrutils.rs:558-630): flat list of kept k-mers in ctx->bufA, offsets in ctx->seq_dst (sketch_kernels.cuh)
 int run_sketch(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     cudaStream_t st = ctx->stream;
     const size_t n = ctx->rn;
-    std::vector<uint64_t> seg_prefix(n + 1);
-    uint64_t n_segs = 0;
-    for (size_t i = 0; i < n; i++) { seg_prefix[i] = n_segs; n_segs += ceil_div<uint64_t>(ctx->h_len[ctx->r0 + i], SK_SEG); }
-    seg_prefix[n] = n_segs;
+    std::vector<uint32_t> tile_prefix(n + 1);
+    uint64_t n_tiles64 = 0, blk_lo = ~0ull, blk_hi = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t o = ctx->h_off[ctx->r0 + i], l = ctx->h_len[ctx->r0 + i];
+        tile_prefix[i] = (uint32_t)n_tiles64;
+        n_tiles64 += ceil_div<uint64_t>(l, SKT_KPOS);
+        if (l) { blk_lo = std::min(blk_lo, o >> 5); blk_hi = std::max(blk_hi, (o + l + 31) >> 5); }
+    }
+    if (n_tiles64 >= 0x7FFFFFFFull) { set_error("too many tiles in one chunk"); return PGR_E_LIMIT; }
+    const uint32_t n_tiles = (uint32_t)n_tiles64;
+    tile_prefix[n] = n_tiles;
     PGR_TRY(ctx->seq_dst.ensure((n + 1) * sizeof(uint64_t)));
-    if (n_segs == 0) {
+    if (n_tiles == 0) {
         PGR_CUDA(cudaMemsetAsync(ctx->seq_dst.p, 0, (n + 1) * sizeof(uint64_t), st));
         *n_l0 = 0;
         return PGR_OK;
     }
-    // reuse: tile_prefix <- seg_prefix (u64), seq_count <- seg_count, chunk_prefix <- seg_off
-    PGR_TRY(ctx->tile_prefix.ensure((n + 1) * sizeof(uint64_t)));
-    PGR_TRY(ctx->seq_count.ensure(n_segs * sizeof(uint32_t)));
-    PGR_TRY(ctx->chunk_prefix.ensure((n_segs + 1) * sizeof(uint64_t)));
-    PGR_CUDA(cudaMemcpyAsync(ctx->tile_prefix.p, seg_prefix.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    SketchParams sp;
+    const uint64_t n_blk = blk_hi - blk_lo;
+    const uint64_t word_lo = blk_lo >> 5, word_hi = (blk_hi + 31) >> 5;
+    // buffers (reused from the minimizer pipeline): tile_prefix, seq_count <- tile counts, chunk_prefix <- tile offsets,
+    // flags <- keep masks, block_chunk <- strand masks, mark_bits <- marked (not clean) blocks, allinv_bits
+    PGR_TRY(ctx->tile_prefix.ensure((n + 1) * sizeof(uint32_t)));
+    PGR_TRY(ctx->seq_count.ensure((size_t)n_tiles * sizeof(uint32_t)));
+    PGR_TRY(ctx->chunk_prefix.ensure(((size_t)n_tiles + 1) * sizeof(uint64_t)));
+    PGR_TRY(ctx->flags.ensure(n_blk * sizeof(uint32_t)));
+    PGR_TRY(ctx->block_chunk.ensure(n_blk * sizeof(uint32_t)));
+    PGR_TRY(ctx->n_skips.ensure(64));
+    if ((size_t)word_hi * 4 + 64 > ctx->mark_bits.cap) {
+        PGR_TRY(ctx->mark_bits.ensure((size_t)word_hi * 4 + 64));
+        PGR_TRY(ctx->allinv_bits.ensure((size_t)word_hi * 4 + 64));
+        ctx->bits_dirty_lo = 0; ctx->bits_dirty_hi = ctx->mark_bits.cap / 4;
+    }
+    if (ctx->bits_dirty_hi > ctx->bits_dirty_lo) {   // cleared only where an earlier launch marked blocks
+        PGR_CUDA(cudaMemsetAsync(ctx->mark_bits.as<uint32_t>() + ctx->bits_dirty_lo, 0, (ctx->bits_dirty_hi - ctx->bits_dirty_lo) * 4, st));
+        PGR_CUDA(cudaMemsetAsync(ctx->allinv_bits.as<uint32_t>() + ctx->bits_dirty_lo, 0, (ctx->bits_dirty_hi - ctx->bits_dirty_lo) * 4, st));
+        ctx->bits_dirty_lo = ctx->bits_dirty_hi = 0;
+    }
+    PGR_CUDA(cudaMemsetAsync(ctx->n_skips.p, 0, sizeof(uint32_t), st));
+    PGR_CUDA(cudaMemcpyAsync(ctx->tile_prefix.p, tile_prefix.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SketchTParams sp;
     sp.seq = ctx->d_seq; sp.off = (ctx->d_off.as<uint64_t>() + ctx->r0); sp.len = (ctx->d_len.as<uint32_t>() + ctx->r0);
-    sp.blk_prefix = ctx->tile_prefix.as<uint64_t>(); sp.n_seq = (uint32_t)n; sp.k = spec.k; sp.r = spec.r;
-    sp.seg_count = ctx->seq_count.as<uint32_t>(); sp.seg_off = nullptr; sp.out = nullptr;
-    const uint32_t grid = (uint32_t)ceil_div<uint64_t>(n_segs, 128);
-    int slot = ctx->timer.begin("sketch_count", st);
-    sketch_kernel<0><<<grid, 128, 0, st>>>(sp, n_segs);
+    sp.tile_prefix = ctx->tile_prefix.as<uint32_t>(); sp.n_seq = (uint32_t)n; sp.n_tiles = n_tiles; sp.k = spec.k; sp.r = spec.r;
+    sp.blk_base = blk_lo; sp.keep = ctx->flags.as<uint32_t>(); sp.strand = ctx->block_chunk.as<uint32_t>();
+    sp.dirty_bits = ctx->mark_bits.as<uint32_t>(); sp.allinv_bits = ctx->allinv_bits.as<uint32_t>(); sp.n_dirty = ctx->n_skips.as<uint32_t>();
+    sp.tile_count = ctx->seq_count.as<uint32_t>(); sp.tile_off = nullptr; sp.out = nullptr;
+    int slot = ctx->timer.begin("sketch_masks", st);
+    sketch_mask_kernel<<<n_tiles, L0_NT, 0, st>>>(sp);
     ctx->timer.end(slot, st);
     PGR_CUDA(cudaGetLastError());
-    PGR_TRY(ctx->ensure_ctl(n_segs * sizeof(uint32_t) + 64));
-    uint32_t *h_seg = (uint32_t *)ctx->h_ctl;
-    PGR_CUDA(cudaMemcpyAsync(h_seg, ctx->seq_count.p, n_segs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PGR_TRY(ctx->ensure_ctl((size_t)n_tiles * sizeof(uint32_t) + 64));
+    uint32_t *h_nd = (uint32_t *)ctx->h_ctl;
+    PGR_CUDA(cudaMemcpyAsync(h_nd, ctx->n_skips.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PGR_CUDA(cudaStreamSynchronize(st));
-    std::vector<uint64_t> seg_off(n_segs + 1), seq_dst(n + 1);
+    const uint32_t n_dirty = *h_nd;
+    ctx->counters[4] = n_dirty;
+    if (n_dirty) {
+        // the marked blocks are looked up by store offset: sorted copy of the chunk's sequence table
+        ctx->bits_dirty_lo = word_lo; ctx->bits_dirty_hi = word_hi;
+        std::vector<uint32_t> ord(n);
+        for (size_t i = 0; i < n; i++) ord[i] = (uint32_t)i;
+        std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return ctx->h_off[ctx->r0 + a] < ctx->h_off[ctx->r0 + b]; });
+        std::vector<uint64_t> s_off(n);
+        std::vector<uint32_t> s_len(n);
+        for (size_t i = 0; i < n; i++) { s_off[i] = ctx->h_off[ctx->r0 + ord[i]]; s_len[i] = ctx->h_len[ctx->r0 + ord[i]]; }
+        DevBuf &d_sorted = ctx->patch_buf[0];
+        PGR_TRY(d_sorted.ensure(n * 16 + 64));
+        SketchSeqTable tb;
+        uint64_t *ds_off = d_sorted.as<uint64_t>();
+        uint32_t *ds_len = (uint32_t *)(ds_off + n), *ds_sid = ds_len + n;
+        PGR_CUDA(cudaMemcpyAsync(ds_off, s_off.data(), n * 8, cudaMemcpyHostToDevice, st));
+        PGR_CUDA(cudaMemcpyAsync(ds_len, s_len.data(), n * 4, cudaMemcpyHostToDevice, st));
+        PGR_CUDA(cudaMemcpyAsync(ds_sid, ord.data(), n * 4, cudaMemcpyHostToDevice, st));
+        tb.s_off = ds_off; tb.s_len = ds_len; tb.s_sid = ds_sid; tb.n = (uint32_t)n;
+        slot = ctx->timer.begin("sketch_marked_blocks", st);
+        sketch_dirty_kernel<<<(uint32_t)ceil_div<uint64_t>(word_hi - word_lo, 128), 128, 0, st>>>(sp, tb, word_lo, word_hi);
+        ctx->timer.end(slot, st);
+        PGR_CUDA(cudaGetLastError());
+        PGR_CUDA(cudaStreamSynchronize(st));   // the sorted host tables go out of scope
+        ctx->counters[0] += 1;
+    }
+    sketch_count_kernel<<<(uint32_t)ceil_div<uint64_t>((uint64_t)n_tiles * 32, 256), 256, 0, st>>>(sp);
+    PGR_CUDA(cudaGetLastError());
+    uint32_t *h_cnt = (uint32_t *)ctx->h_ctl;
+    PGR_CUDA(cudaMemcpyAsync(h_cnt, ctx->seq_count.p, (size_t)n_tiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PGR_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint64_t> tile_off((size_t)n_tiles + 1), seq_dst(n + 1);
     uint64_t a = 0;
-    for (uint64_t s = 0; s < n_segs; s++) { seg_off[s] = a; a += h_seg[s]; }
-    seg_off[n_segs] = a;
-    for (size_t i = 0; i <= n; i++) seq_dst[i] = seg_off[seg_prefix[i]];
+    for (uint32_t t = 0; t < n_tiles; t++) { tile_off[t] = a; a += h_cnt[t]; }
+    tile_off[n_tiles] = a;
+    for (size_t i = 0; i <= n; i++) seq_dst[i] = tile_off[tile_prefix[i]];
     *n_l0 = a;
-    PGR_CUDA(cudaMemcpyAsync(ctx->chunk_prefix.p, seg_off.data(), (n_segs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    PGR_CUDA(cudaMemcpyAsync(ctx->chunk_prefix.p, tile_off.data(), ((size_t)n_tiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     PGR_CUDA(cudaMemcpyAsync(ctx->seq_dst.p, seq_dst.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     PGR_TRY(ctx->bufA.ensure(std::max<uint64_t>(a, 1) * sizeof(pgr_mm128)));
     PGR_TRY(ctx->bufB.ensure(std::max<uint64_t>(a, 1) * sizeof(pgr_mm128)));
-    sp.seg_off = ctx->chunk_prefix.as<uint64_t>(); sp.out = ctx->bufA.as<pgr_mm128>();
+    sp.tile_off = ctx->chunk_prefix.as<uint64_t>(); sp.out = ctx->bufA.as<pgr_mm128>();
     slot = ctx->timer.begin("sketch_write", st);
-    sketch_kernel<1><<<grid, 128, 0, st>>>(sp, n_segs);
+    sketch_write_kernel<<<n_tiles, L0_NT, 0, st>>>(sp);
     ctx->timer.end(slot, st);
-    ctx->counters[0] += 2;
+    ctx->counters[0] += 3;
     PGR_CUDA(cudaGetLastError());
     PGR_CUDA(cudaStreamSynchronize(st));
     return PGR_OK;

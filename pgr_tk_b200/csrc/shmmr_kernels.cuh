@@ -172,7 +172,8 @@ __device__ __forceinline__ uint32_t rplane(const uint32_t *F, int j) { return j 
 
 // k-mer registers of key index q rebuilt from the plane words (same arithmetic as the key loop)
 struct KmerRegs { uint64_t f0, f1, r0, r1; };
-__device__ __forceinline__ KmerRegs kmer_at(const L0Smem &s, int q, uint32_t k) {
+template <class SM>   // any shared-memory struct with the plane arrays F0 / F1 (L0Smem, SketchSmem)
+__device__ __forceinline__ KmerRegs kmer_at(const SM &s, int q, uint32_t k) {
     const int t = (q >> 5) + L0_CTX, i = q & 31;
     const uint64_t kmask = ~0ull >> (64 - k);
     const uint32_t sh = 31 - i;
@@ -190,7 +191,8 @@ __device__ __forceinline__ KmerRegs kmer_at(const L0Smem &s, int q, uint32_t k) 
     return r;
 }
 // full 64-bit hash and strand of key index q (shmmrutils.rs:485-496)
-__device__ __forceinline__ uint64_t hash_at(const L0Smem &s, int q, uint32_t k, uint32_t &strand) {
+template <class SM>
+__device__ __forceinline__ uint64_t hash_at(const SM &s, int q, uint32_t k, uint32_t &strand) {
     const KmerRegs r = kmer_at(s, q, k);
     const bool rev = r.r0 < r.f0;
     strand = rev ? 1u : 0u;
@@ -1376,75 +1378,6 @@ __global__ void __launch_bounds__(LF_NT) level_fused_kernel(const LevelFusedPara
         const int64_t b = (int64_t)p.seq_off_in[sid];
         if (b < i1 || (last_tile && b == i1)) p.seq_off_out[sid] = base + s.excl[b - i0]; else break;
     }
-}
-
-// sketch mode (shmmrutils.rs:558-630): every position whose full 64-bit hash is below the threshold is kept.
-// One thread per 32-base block, rolling over its positions (k-mer windows from the plane words as in l0_kernel is
-// the fast design; sketch mode is not on the benchmarked path, so this kernel favours simplicity: two passes,
-// count then write, exact for every input including invalid bytes and palindromes).
-struct SketchParams {
-    const uint8_t *seq; const uint64_t *off; const uint32_t *len;
-    const uint64_t *blk_prefix;   // [n_seq+1] cumulative number of 1024-base segments
-    uint32_t n_seq; uint32_t k, r;
-    uint32_t *seg_count;          // [n_segs]
-    const uint64_t *seg_off;      // [n_segs+1] (pass 2)
-    pgr_mm128 *out;
-};
-
-constexpr int SK_SEG = 1024;
-
-template <int MODE>
-__global__ void sketch_kernel(const SketchParams p, uint64_t n_segs) {
-    const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (seg >= n_segs) return;
-    uint32_t lo = 0, hi = p.n_seq;
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (p.blk_prefix[mid] <= seg) lo = mid; else hi = mid; }
-    const uint32_t sid = lo;
-    const uint64_t L = p.len[sid];
-    const uint8_t *sq = p.seq + p.off[sid];
-    const uint64_t s0 = (seg - p.blk_prefix[sid]) * SK_SEG, s1 = min(L, s0 + SK_SEG);
-    const uint32_t k = p.k;
-    const uint64_t mask = ~0ull >> (64 - k);
-    const uint32_t shift = k - 1;
-    const uint64_t thr = (~0ull >> 4) >> p.r;
-    // registers at s0: replay the last k valid bases before s0
-    uint64_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;
-    {
-        uint64_t b = s0; uint32_t got = 0;
-        while (b > 0 && got < k) { b--; if (base_code(sq[b]) < 4) got++; }
-        for (uint64_t q = b; q < s0; q++) {
-            const uint32_t c = base_code(sq[q]);
-            if (c < 4) {
-                f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
-                const uint64_t rc = 3 ^ c;
-                r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
-            }
-        }
-    }
-    uint64_t n = 0;
-    pgr_mm128 *dst = MODE ? p.out + p.seg_off[seg] : nullptr;
-    for (uint64_t pos = s0; pos < s1; pos++) {
-        const uint32_t c = base_code(sq[pos]);
-        if (c < 4) {
-            f0 = ((f0 << 1) | (c & 1)) & mask; f1 = ((f1 << 1) | (c >> 1)) & mask;
-            const uint64_t rc = 3 ^ c;
-            r0 = ((r0 >> 1) | ((rc & 1) << shift)) & mask; r1 = ((r1 >> 1) | ((rc >> 1) << shift)) & mask;
-        }
-        if (f0 == r0 && f1 == r1) continue;
-        if (pos < k) continue;
-        const bool rev = r0 < f0;
-        const uint64_t h = rev ? (u64hash(r0) ^ u64hash(r1 ^ HASH_XOR)) : (u64hash(f0) ^ u64hash(f1 ^ HASH_XOR));
-        if (h < thr) {
-            if (MODE) {
-                pgr_mm128 mm;
-                mm.x = (h << 8) | k;
-                mm.y = ((uint64_t)sid << 32) | ((uint64_t)(uint32_t)pos << 1) | (rev ? 1u : 0u);
-                dst[n] = mm;
-            }
-            n++;
-        }
-    }
-    if (!MODE) p.seg_count[seg] = (uint32_t)n;
 }
 
 }  // namespace pgr

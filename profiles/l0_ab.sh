@@ -7,7 +7,7 @@ for v in ${VARIANTS:-default plain}; do
   if [ $v = default ]; then unset PGR_B200_LIB; else export PGR_B200_LIB=$PWD/profiles/ab/libpgr_b200_$v.so; fi
   python - <<PY
 import json, subprocess, sys, os
-r = subprocess.run([sys.executable, "bench.py", "--no-index", "--no-assembly", "--no-e2e", "--steps", "10", "--warmup", "3"], capture_output=True, text=True)
+r = subprocess.run([sys.executable, "bench.py", "--no-index", "--no-assembly", "--no-e2e", "--no-sketch", "--steps", "10", "--warmup", "3"], capture_output=True, text=True)
 try:
     d = json.loads(r.stdout.strip().splitlines()[-1])
     print("$v", "step_ms %.3f" % d["ms_per_step"], "l0_ms %.3f" % d["stages_ms"]["l0_minimizers"], "levels_ms %.3f" % d["stages_ms"]["reduce_and_span"], "Gbases/s %.1f" % d["value"], "parity(cpu sample)", "cpu_baseline" in d)

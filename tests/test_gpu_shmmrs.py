@@ -257,3 +257,57 @@ def test_assembly_like_decoration():
     ctx.shmmrs(pg.ShmmrSpec())
     assert ctx.counters()[2] == 0
     ctx.close()
+
+
+def test_sketch_mode_tiled_paths():
+    """sketch mode through the tiled kernels (sketch_kernels.cuh): sequences of many tiles, every tile-edge length, soft masking,
+    N runs of every alignment (kb to Mb: the all-invalid bitmap walk), raw codes 0..3, junk bytes, leading / trailing runs,
+    a sequence made of invalid bytes only, reverse-complement palindromes, every r"""
+    rng = np.random.default_rng(23)
+
+    def with_runs(L, runs):
+        a = np.frombuffer(rand_seq(rng, L), dtype=np.uint8).copy()
+        for s, n, ch in runs:
+            a[s:s + n] = ch
+        return a.tobytes()
+
+    half = rand_seq(rng, 400)
+    comp = bytes({65: 84, 67: 71, 71: 67, 84: 65}[c] for c in reversed(half))
+    seqs = [
+        rand_seq(rng, 300_000),
+        rand_seq(rng, 8127), rand_seq(rng, 8128), rand_seq(rng, 8129), rand_seq(rng, 16256), rand_seq(rng, 16257), rand_seq(rng, 57), rand_seq(rng, 56), b"",
+        rand_seq(rng, 100_000, b"ACGTacgt"),
+        with_runs(200_000, [(0, 5000, ord("N")), (50_001, 31, ord("N")), (60_000, 32, ord("n")), (70_016, 64, ord("N")), (90_000, 1, ord("N")),
+                            (120_003, 40_000, ord("N")), (199_000, 1000, ord("N"))]),
+        with_runs(2_500_000, [(100_000, 2_000_000, ord("N")), (2_200_000, 3, ord("-"))]),
+        with_runs(50_000, [(1000, 1, 0), (2000, 1, 1), (3000, 2, 2), (4000, 1, 3), (5000, 3, 4), (6000, 1, 255), (7000, 10, ord("*"))]),
+        b"N" * 70_000,
+        half + comp + rand_seq(rng, 20_000) + comp + half,
+        b"AT" * 5000 + rand_seq(rng, 9000) + b"ACGT" * 3000,
+    ]
+    for k, r, ms in [(56, 4, 64), (56, 1, 0), (31, 12, 5), (16, 2, 0), (24, 7, 24), (5, 3, 0)]:
+        assert_batch_equal(seqs, pg.ShmmrSpec(80, k, r, ms, True))
+
+
+def test_sketch_mode_device_store_any_order():
+    """the marked-block pass looks sequences up by store offset: a device store whose sequences are not in offset order"""
+    import torch
+    rng = np.random.default_rng(29)
+    seqs = [np.frombuffer(rand_seq(rng, L, b"ACGTN"), dtype=np.uint8) for L in (40_000, 9_000, 70_001)]
+    slack = 16384
+    offs, off = [], slack
+    for s in reversed(seqs):          # laid out in reverse order
+        offs.append(off)
+        off += (len(s) + 31) & ~31
+    offs = offs[::-1]
+    store = torch.zeros(off + slack, dtype=torch.uint8, device="cuda")
+    for s, o in zip(seqs, offs):
+        store[o:o + len(s)] = torch.from_numpy(s.copy()).cuda()
+    ctx = pg.Ctx(0)
+    ctx.set_device_seqs(store.data_ptr(), offs, [len(s) for s in seqs])
+    spec = pg.ShmmrSpec(80, 56, 3, 10, True)
+    ctx.shmmrs(spec)
+    got, goff = ctx.shmmrs_download()
+    exp, eoff = orc.shmmrs_batch([0, 1, 2], [s.tobytes() for s in seqs], ospec(spec), False, nthreads=3)
+    assert list(goff) == list(eoff) and np.array_equal(got, exp)
+    ctx.close()
