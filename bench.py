@@ -393,11 +393,13 @@ def main():
 
         # default transport: bases packed to 3 bits on the host cores, expanded on the device (pack_upload.cuh)
         e_ms, d2h = time_e2e(args.steps, 2)
+        took_packed = pg.lib().pgr_b200_last_transport() == pg.TRANSPORT_PACKED
         packed_bytes = ((bases + 31) // 32) * 12
         e2e = {"value": world * bases / (e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": packed_bytes, "d2h_bytes_per_step": d2h, "host_input_bytes_per_step": bases,
-               "transport": "packed: %d host threads (%s) turn the caller's bytes into 3 bit planes per 32-base block, 12 B per 32 bases cross PCIe, "
-                            "unpack_kernel restores canonical ASCII in the device store" % (pg.lib().pgr_b200_pool_threads(), pg.pack_isa()),
+               "h2d_bytes_per_step": packed_bytes if took_packed else bases, "d2h_bytes_per_step": d2h, "host_input_bytes_per_step": bases,
+               "transport": ("packed: %d host threads (%s) turn the caller's bytes into 3 bit planes per 32-base block, 12 B per 32 bases cross PCIe, "
+                             "unpack_kernel restores canonical ASCII in the device store" % (pg.lib().pgr_b200_pool_threads(), pg.pack_isa())) if took_packed
+                            else "direct copy of the page-locked bytes (the library's choice with %d host threads for this rank)" % pg.lib().pgr_b200_pool_threads(),
                "api": "pgr_b200_shmmrs_batch (host pointers in pinned memory -> host MM128 array)"}
         # A/B: the caller's bytes copied as they are (round-1 path; asynchronous because the buffer is page-locked)
         pg.set_transport(pg.TRANSPORT_DIRECT)

@@ -107,6 +107,10 @@ int pgr_b200_host_unregister(void *p);
 #define PGR_TRANSPORT_PACKED 0 /* default: large host inputs cross PCIe as bit planes (3 bits per base) */
 #define PGR_TRANSPORT_DIRECT 1 /* the caller's bytes are copied as they are (asynchronous only from page-locked memory) */
 int pgr_b200_set_transport(int mode); /* process-wide; returns the previous mode.  PGR_B200_H2D=direct sets the initial one */
+/* In PGR_TRANSPORT_PACKED mode a batch is still copied directly when it is small (< 4 MB) or when the host has few threads for
+ * this process (< 10, e.g. 8 ranks on a 32-CPU node) and the source is page-locked: the direct copy is then the faster one.
+ * Transport the newest batch call of this process took: PGR_TRANSPORT_PACKED / PGR_TRANSPORT_DIRECT, -1 before the first. */
+int pgr_b200_last_transport(void);
 void pgr_b200_pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v);
 const char *pgr_b200_pack_isa(void);
 int pgr_b200_pool_threads(void); /* host threads the library's host-side loops use (PGR_B200_HOST_THREADS overrides) */

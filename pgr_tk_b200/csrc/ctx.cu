@@ -158,6 +158,7 @@ int pgr_b200_host_register(void *p, size_t bytes) {
 void pgr_b200_pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) { pgr::pack_bases(src, n_bytes, p0, p1, v); }
 const char *pgr_b200_pack_isa(void) { return pgr::pack_isa(); }
 int pgr_b200_pool_threads(void) { return (int)pgr::pool_threads(); }
+int pgr_b200_last_transport(void) { return pgr::last_transport().load(); }
 int pgr_b200_set_transport(int mode) { return pgr::transport_mode().exchange(mode == PGR_TRANSPORT_DIRECT ? 1 : 0); }
 int pgr_b200_host_unregister(void *p) {
     if (!p) return PGR_OK;
@@ -333,7 +334,7 @@ int pgr_b200_ctx_upload(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const
     if (!ctx || (n && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
     PGR_CUDA(cudaSetDevice(ctx->device));
     PGR_TRY(upload_layout(ctx, n, rids, seqs, lens));
-    if (packed_upload_enabled() && ctx->total_bases >= PACK_MIN_BYTES) {
+    if (choose_packed(seqs, lens, n, ctx->total_bases)) {
         if (!ctx->pack && !(ctx->pack = pack_ring_acquire(ctx->device))) return PGR_E_CUDA;
         PGR_TRY(upload_packed(ctx->pack, ctx->seq_store.as<uint8_t>(), ctx->h_off, ctx->h_len, seqs, 0, n, ctx->stream));
     } else {
@@ -1247,7 +1248,8 @@ int pgr::run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const ui
     // Packed transport (pack_upload.cuh): the host packs the bases into bit planes while earlier chunks are copied and
     // computed, so the packing runs on its own host thread and hands the chunks over one by one.  Direct transport: the
     // copies are queued up front (asynchronous when the caller's buffers are page-locked).
-    const bool packed = packed_upload_enabled() && ctx->total_bases >= PACK_MIN_BYTES;
+    const bool packed = choose_packed(seqs, lens, n, ctx->total_bases);
+    last_transport().store(packed ? 0 : 1);
     if (packed && !ctx->pack && !(ctx->pack = pack_ring_acquire(ctx->device))) rc = PGR_E_CUDA;
     std::thread uploader;
     std::mutex up_mu;
@@ -1255,11 +1257,12 @@ int pgr::run_chunked(pgr_b200_ctx *ctx, size_t n, const uint32_t *rids, const ui
     size_t up_ready = 0;          // chunks whose event has been recorded
     int up_rc = PGR_OK;
     std::string up_err;
+    const bool src_locked = packed && source_page_locked(seqs, lens, n);
     if (rc == PGR_OK && packed) {
         uploader = std::thread([&] {
             int r = cudaSetDevice(ctx->device) == cudaSuccess ? PGR_OK : PGR_E_CUDA;
             for (size_t c = 0; c < n_chunks; c++) {
-                if (r == PGR_OK) r = upload_packed(ctx->pack, ctx->seq_store.as<uint8_t>(), ctx->h_off, ctx->h_len, seqs, cut[c], cut[c + 1], ctx->copy_stream);
+                if (r == PGR_OK) r = upload_packed(ctx->pack, ctx->seq_store.as<uint8_t>(), ctx->h_off, ctx->h_len, seqs, cut[c], cut[c + 1], ctx->copy_stream, src_locked);
                 if (r == PGR_OK && cudaEventRecord(ev[c], ctx->copy_stream) != cudaSuccess) r = PGR_E_CUDA;
                 std::lock_guard<std::mutex> lk(up_mu);
                 if (r != PGR_OK && up_rc == PGR_OK) { up_rc = r; up_err = get_error(); }

@@ -129,6 +129,9 @@ struct Pool {
             cpu_set_t set;
             if (sched_getaffinity(0, sizeof set, &set) == 0) t = (unsigned)CPU_COUNT(&set);
             if (!t) t = std::thread::hardware_concurrency();
+            // one process per GPU (torchrun): the processes of a node share its CPUs, so each takes its share; an oversubscribed
+            // pool turns the per-slot joins of the packer into waits for descheduled threads
+            if (const char *lw = getenv("LOCAL_WORLD_SIZE")) { const unsigned w = (unsigned)atoi(lw); if (w > 1) t = std::max(1u, t / w); }
             t = std::min(t, 32u);
         }
         n_threads = std::max(1u, t);

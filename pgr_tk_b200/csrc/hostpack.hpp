@@ -19,6 +19,6 @@ const char *pack_isa();   // "avx512bw", "avx2" or "scalar": what pack_bases run
 
 // persistent worker pool shared by the library's host-side loops; fn(i) for i in [0, n), the caller takes part
 void parallel_for(size_t n, const std::function<void(size_t)> &fn);
-unsigned pool_threads();  // workers + caller (PGR_B200_HOST_THREADS, default = the CPUs this process may run on, at most 32)
+unsigned pool_threads();  // workers + caller: PGR_B200_HOST_THREADS, else the CPUs this process may run on divided by LOCAL_WORLD_SIZE, at most 32
 
 }  // namespace pgr

@@ -12,6 +12,8 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <deque>
 #include <mutex>
 #include <vector>
 
@@ -64,8 +66,20 @@ struct PackRing {
     bool used[PACK_SLOTS] = {};
     cudaStream_t unpack_stream = nullptr;
     uint64_t seq = 0;
+    // Hybrid feeding (page-locked sources): whenever the copies already queued will be over before the host has packed its next
+    // slot, that slot is copied as it is instead — PCIe carries plain bytes in the gaps the packer leaves, the packer skips
+    // the slot.  The backlog is estimated from the queued copies that have not completed yet.
+    static constexpr int N_TRACK = 64;
+    cudaEvent_t track_ev[N_TRACK] = {};
+    struct Queued { int ev; float est_ms; };
+    std::deque<Queued> queued;
+    int track_next = 0;
+    float pack_ms = 0.45f;          // running estimate of the host time to pack one full slot
+    uint64_t n_direct_slots = 0, n_packed_slots = 0;
     static constexpr size_t slot_words() { return 3ull * PACK_SLOT_BLOCKS; }
 };
+constexpr float PCIE_GB_PER_MS = 0.050f;   // ~50 GB/s: only used to size the backlog estimate
+constexpr size_t HYBRID_MAX_SEGMENTS = 64;  // a slot made of more pieces than this (many short sequences) is always packed
 
 inline std::mutex &pack_ring_mu() { static std::mutex m; return m; }
 inline std::vector<PackRing *> &pack_ring_free() { static std::vector<PackRing *> v; return v; }
@@ -87,6 +101,7 @@ inline PackRing *pack_ring_acquire(int device) {
     for (int s = 0; ok && s < PACK_SLOTS; s++)
         ok = cudaEventCreateWithFlags(&r->h2d_done[s], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&r->unpack_done[s], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < PackRing::N_TRACK; i++) ok = cudaEventCreateWithFlags(&r->track_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         if (r->h) cudaFreeHost(r->h);
@@ -102,6 +117,7 @@ inline void pack_ring_release(PackRing *r) {
     if (!r) return;
     cudaStreamSynchronize(r->unpack_stream);
     for (int s = 0; s < PACK_SLOTS; s++) r->used[s] = false;
+    r->queued.clear();
     std::lock_guard<std::mutex> lk(pack_ring_mu());
     pack_ring_free().push_back(r);
 }
@@ -113,19 +129,94 @@ inline std::atomic<int> &transport_mode() {
 }
 inline bool packed_upload_enabled() { return transport_mode().load(std::memory_order_relaxed) == 0; }
 
+// is the batch's memory page-locked (judged by its first sequence of a megabyte or more)?
+inline bool source_page_locked(const uint8_t *const *seqs, const size_t *lens, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        if (lens[i] < (1u << 20)) continue;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, seqs[i]) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    }
+    return false;
+}
+
+// Which transport a batch takes when the mode is the default.  Packing pays when the host packs faster than PCIe copies
+// (~5.6 GB/s per pool thread against ~50 GB/s for a page-locked source) or when the source is pageable, which the direct copy
+// moves at ~10 GB/s through the driver's staging.  A page-locked source is fed in hybrid form (see PackRing): slots are copied
+// as they are whenever the packer cannot keep the copy engine busy.  With very few host threads per process (8 ranks on a
+// 32-CPU node: 4 each) the node's aggregate host-to-device rate is the limit and packing only competes for memory bandwidth:
+// measured at N = 8, direct 168.5, hybrid 152.6, packed only 93.3 Gbases/s — so below PACK_MIN_THREADS a page-locked source is
+// copied directly.  (N = 1, 16 threads: hybrid 99.2, packed only 87.2, direct 49.4 Gbases/s.)
+constexpr unsigned PACK_MIN_THREADS = 6;
+inline std::atomic<int> &last_transport() { static std::atomic<int> t{-1}; return t; }   // what the newest batch call took (0 packed, 1 direct)
+inline bool choose_packed(const uint8_t *const *seqs, const size_t *lens, size_t n, uint64_t total_bases) {
+    if (!packed_upload_enabled() || total_bases < PACK_MIN_BYTES) return false;
+    if (pool_threads() >= PACK_MIN_THREADS) return true;
+    return !source_page_locked(seqs, lens, n);
+}
+
 // sequences [i0, i1) of the layout (h_off: 32-byte aligned consecutive store offsets, h_len) -> store, through the ring.
 // Host work happens on the calling thread + the pool; copies on st_copy, expansion on the ring's own stream; on return
 // everything is queued and st_copy waits for the last expansion (so an event recorded on st_copy covers the chunk).
 inline int upload_packed(PackRing *ring, uint8_t *store, const std::vector<uint64_t> &h_off, const std::vector<uint32_t> &h_len,
-                         const uint8_t *const *seqs, size_t i0, size_t i1, cudaStream_t st_copy) {
+                         const uint8_t *const *seqs, size_t i0, size_t i1, cudaStream_t st_copy, bool src_page_locked = false) {
     while (i0 < i1 && h_len[i0] == 0) i0++;
     while (i1 > i0 && h_len[i1 - 1] == 0) i1--;
     if (i0 >= i1) return PGR_OK;
     const uint64_t B0 = h_off[i0] >> 5;
     const uint64_t B1 = (h_off[i1 - 1] + (((uint64_t)h_len[i1 - 1] + 31) & ~31ull)) >> 5;
     int last_slot = -1;
+    // copies queued on st_copy that are not over yet, as milliseconds of PCIe time
+    auto backlog_ms = [&]() -> float {
+        while (!ring->queued.empty() && cudaEventQuery(ring->track_ev[ring->queued.front().ev]) == cudaSuccess) ring->queued.pop_front();
+        float t = 0;
+        for (const auto &q : ring->queued) t += q.est_ms;
+        return t;
+    };
+    auto track = [&](float est_ms) -> int {
+        if ((int)ring->queued.size() >= PackRing::N_TRACK - 1) {   // keep the event ring ahead of the queue
+            PGR_CUDA(cudaEventSynchronize(ring->track_ev[ring->queued.front().ev]));
+            ring->queued.pop_front();
+        }
+        const int e = ring->track_next;
+        ring->track_next = (e + 1) % PackRing::N_TRACK;
+        PGR_CUDA(cudaEventRecord(ring->track_ev[e], st_copy));
+        ring->queued.push_back({e, est_ms});
+        return PGR_OK;
+    };
+    static const bool hybrid_off = getenv("PGR_B200_NO_HYBRID") != nullptr;   // A/B aid
     for (uint64_t sb = B0; sb < B1; sb += PACK_SLOT_BLOCKS) {
         const uint32_t nb = (uint32_t)std::min<uint64_t>(PACK_SLOT_BLOCKS, B1 - sb);
+        if (src_page_locked && !hybrid_off && backlog_ms() < ring->pack_ms * ((float)nb / PACK_SLOT_BLOCKS)) {
+            // the copy engine would run dry while this slot is packed: send the slot's bytes as they are
+            size_t i = (size_t)(std::upper_bound(h_off.begin() + i0, h_off.begin() + i1, sb << 5) - h_off.begin()) - 1;
+            // (count the pieces first: a slot of many short sequences is cheaper to pack than to copy piecewise)
+            size_t n_seg = 0;
+            { uint64_t b = sb; size_t ii = i; const uint64_t be = sb + nb;
+              while (b < be && n_seg <= HYBRID_MAX_SEGMENTS) {
+                  const uint64_t within = (b << 5) - h_off[ii], len = h_len[ii];
+                  if (within >= len) { ii++; continue; }
+                  const uint64_t take = std::min<uint64_t>(len - within, (be - b) << 5);
+                  n_seg++; b += (take + 31) >> 5; if (within + take >= len) ii++;
+              } }
+            if (n_seg <= HYBRID_MAX_SEGMENTS) {
+                uint64_t b = sb, bytes = 0;
+                const uint64_t be = sb + nb;
+                while (b < be) {
+                    const uint64_t within = (b << 5) - h_off[i], len = h_len[i];
+                    if (within >= len) { i++; continue; }
+                    const uint64_t take = std::min<uint64_t>(len - within, (be - b) << 5);
+                    PGR_CUDA(cudaMemcpyAsync(store + h_off[i] + within, seqs[i] + within, take, cudaMemcpyHostToDevice, st_copy));
+                    bytes += take;
+                    b += (take + 31) >> 5;
+                    if (within + take >= len) i++;
+                }
+                PGR_TRY(track((float)bytes * 1e-9f / PCIE_GB_PER_MS));
+                ring->n_direct_slots++;
+                continue;
+            }
+        }
+        const auto t_pack0 = std::chrono::steady_clock::now();
         const int s = (int)(ring->seq++ % PACK_SLOTS);
         if (ring->used[s]) PGR_CUDA(cudaEventSynchronize(ring->h2d_done[s]));   // the copy that read this slot is over
         uint32_t *hp = ring->h + (size_t)s * PackRing::slot_words();
@@ -147,10 +238,16 @@ inline int upload_packed(PackRing *ring, uint8_t *store, const std::vector<uint6
                 if (within + take >= len) i++;
             }
         });
+        if (nb == PACK_SLOT_BLOCKS) {
+            const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_pack0).count();
+            ring->pack_ms = 0.75f * ring->pack_ms + 0.25f * std::min(ms, 8.0f);
+        }
+        ring->n_packed_slots++;
         uint32_t *dp = ring->d + (size_t)s * PackRing::slot_words();
         if (ring->used[s]) PGR_CUDA(cudaStreamWaitEvent(st_copy, ring->unpack_done[s], 0));   // the device slot has been expanded
         PGR_CUDA(cudaMemcpyAsync(dp, hp, (size_t)nb * 12, cudaMemcpyHostToDevice, st_copy));
         PGR_CUDA(cudaEventRecord(ring->h2d_done[s], st_copy));
+        PGR_TRY(track((float)nb * 12e-9f / PCIE_GB_PER_MS));
         PGR_CUDA(cudaStreamWaitEvent(ring->unpack_stream, ring->h2d_done[s], 0));
         unpack_kernel<<<(nb + 255) / 256, 256, 0, ring->unpack_stream>>>(dp, nb, store + (sb << 5));
         PGR_CUDA(cudaGetLastError());
