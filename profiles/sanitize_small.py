@@ -28,3 +28,16 @@ adj = idx.adj_list(0)
 print("bundles", len(idx.get_principal_bundles_from_adj_list(adj, 2)[0]), len(idx.sort_adj_list_by_weighted_dfs(adj, (int(adj[0]["a0"]), int(adj[0]["a1"]), int(adj[0]["ori0"])))))
 fr, sg = idx.compress_fragments(list(range(5)), haps)
 print("fragments", len(fr), int((fr["kind"] == 0).sum()), len(sg))
+# round 2: packed transport (>= 4 MB batch: pack ring, unpack_kernel, hybrid slots), sketch mode through its marked-block pass,
+# level-0 patches (cluster finder, thread and warp replay, splice), sharded build on one device, per-sequence adjacency
+big = [r(2_300_000) + b"N" * 70 + r(900_000), r(1_500_001).lower(), r(700_000)]
+for spec in (pg.ShmmrSpec(80, 56, 4, 64), pg.ShmmrSpec(80, 56, 4, 64, True)):
+    mm, off = pg.get_shmmrs_from_seqs([0, 1, 2], big, spec)
+    print("packed transport shimmers", len(mm))
+gap = r(60000) + b"N" * 40000 + r(30000) + b"AT" * 60 + r(20000) + b"n" * 333 + r(5000)
+for spec in (pg.ShmmrSpec(80, 56, 4, 64), pg.ShmmrSpec(80, 56, 4, 64, True), pg.ShmmrSpec(80, 24, 2, 0, True)):
+    print("gaps", len(pg.sequence_to_shmmrs(0, gap, spec)))
+m = pg.ShardedIndex(pg.ShmmrSpec(48, 56, 4, 12), pg.FRG_ID_FASTX, devices=[0, 0, 0])
+m.add_batch(list(range(5)), haps)
+print("sharded", [len(x) for x in m.export()])
+m.close()
