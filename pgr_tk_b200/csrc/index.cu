@@ -3,6 +3,10 @@
 // plus .mdb I/O (seq_db.rs:1291-1407).  Query, chaining and adjacency live in query.cu.
 #include "index.cuh"
 
+#include <memory>
+
+#include "hostpack.hpp"
+
 #include <algorithm>
 #include <cstring>
 
@@ -220,25 +224,35 @@ __global__ void gather_tuples_kernel(const FragTuple *in, const uint32_t *idx, u
 // (h0, h1, len, len x 17-byte FragmentSignature)
 int write_mdb_file(const pgr_shmmr_spec &spec, uint64_t nk, const uint64_t *keys, const uint64_t *offs, const pgr_frag_sig *sigs, const char *path) {
     const uint64_t ns = nk ? offs[nk] : 0;
-    std::vector<uint8_t> buf(31 + nk * 24 + ns * 17);
-    uint8_t *w = buf.data();
-    auto p32 = [&](uint32_t v) { memcpy(w, &v, 4); w += 4; };
-    auto p64 = [&](uint64_t v) { memcpy(w, &v, 8); w += 8; };
-    *w++ = 'm'; *w++ = 'd'; *w++ = 'b';
-    p32(spec.w); p32(spec.k); p32(spec.r); p32(spec.min_span); p32(spec.sketch ? 1u : 0u);
-    p64(nk);
-    for (uint64_t i = 0; i < nk; i++) {
-        p64(keys[2 * i]); p64(keys[2 * i + 1]); p64(offs[i + 1] - offs[i]);
-        for (uint64_t j = offs[i]; j < offs[i + 1]; j++) {
-            const pgr_frag_sig &s = sigs[j];
-            p32(s.frg_id); p32(s.sid); p32(s.bgn); p32(s.end); *w++ = s.ori;
-        }
+    const size_t total = 31 + nk * 24 + ns * 17;
+    std::unique_ptr<uint8_t[]> buf(new uint8_t[total]);   // no zero fill: every byte is written below
+    {
+        uint8_t *w = buf.get();
+        auto p32 = [&](uint32_t v) { memcpy(w, &v, 4); w += 4; };
+        *w++ = 'm'; *w++ = 'd'; *w++ = 'b';
+        p32(spec.w); p32(spec.k); p32(spec.r); p32(spec.min_span); p32(spec.sketch ? 1u : 0u);
+        memcpy(w, &nk, 8);
     }
+    // key i starts at 31 + 24 i + 17 offs[i]: the records are formatted by the host pool, a range of keys per item
+    const uint64_t per = 1u << 14;
+    parallel_for((size_t)ceil_div<uint64_t>(nk, per), [&](size_t it) {
+        const uint64_t k0 = it * per, k1 = std::min<uint64_t>(nk, k0 + per);
+        uint8_t *w = buf.get() + 31 + k0 * 24 + offs[k0] * 17;
+        for (uint64_t i = k0; i < k1; i++) {
+            const uint64_t cnt = offs[i + 1] - offs[i];
+            memcpy(w, &keys[2 * i], 16); memcpy(w + 16, &cnt, 8); w += 24;
+            for (uint64_t j = offs[i]; j < offs[i + 1]; j++) {
+                const pgr_frag_sig &sg = sigs[j];
+                memcpy(w, &sg.frg_id, 4); memcpy(w + 4, &sg.sid, 4); memcpy(w + 8, &sg.bgn, 4); memcpy(w + 12, &sg.end, 4); w[16] = sg.ori;
+                w += 17;
+            }
+        }
+    });
     FILE *f = fopen(path, "wb");
     if (!f) { set_error("cannot create %s", path); return PGR_E_IO; }
-    const size_t wr = fwrite(buf.data(), 1, buf.size(), f);
+    const size_t wr = fwrite(buf.get(), 1, total, f);
     const int cl = fclose(f);
-    if (wr != buf.size() || cl != 0) { set_error("short write to %s", path); return PGR_E_IO; }
+    if (wr != total || cl != 0) { set_error("short write to %s", path); return PGR_E_IO; }
     return PGR_OK;
 }
 
@@ -493,11 +507,15 @@ int pgr_b200_index_write_mdb(pgr_b200_index *idx, const char *path) {
     PGR_TRY(pgr_b200_index_finalize(idx));
     const uint64_t nk = idx->n_keys, ns = idx->n_tuples;
     std::vector<uint64_t> keys(2 * nk), offs(nk + 1);
-    std::vector<pgr_frag_sig> sigs(ns);
     if (nk == 0) offs[0] = 0;
     uint64_t dk = 0; pgr_frag_sig ds;
-    PGR_TRY(pgr_b200_index_export_csr(idx, nk ? keys.data() : &dk, offs.data(), ns ? sigs.data() : &ds));
-    return write_mdb_file(idx->spec, nk, keys.data(), offs.data(), sigs.data(), path);
+    // the signatures (20 B each, the bulk of the map) come back into a page-locked pool buffer: PCIe rate, no zero fill
+    pgr_frag_sig *sigs = ns ? (pgr_frag_sig *)result_alloc(ns * sizeof(pgr_frag_sig)) : &ds;
+    if (!sigs) { set_error("out of host memory"); return PGR_E_ARG; }
+    int rc = pgr_b200_index_export_csr(idx, nk ? keys.data() : &dk, offs.data(), sigs);
+    if (rc == PGR_OK) rc = write_mdb_file(idx->spec, nk, keys.data(), offs.data(), sigs, path);
+    if (ns) result_free(sigs);
+    return rc;
 }
 
 // seq_db.rs:1328-1407: any key order is accepted; per-key vectors keep their file order
@@ -506,9 +524,18 @@ pgr_b200_index *pgr_b200_index_read_mdb(const char *path, int device) {
     FILE *f = fopen(path, "rb");
     if (!f) { set_error("cannot open %s", path); return nullptr; }
     std::vector<uint8_t> buf;
-    uint8_t tmp[1 << 16];
-    size_t got;
-    while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    {   // one read of the whole file when its size is known (a regular file), chunks otherwise
+        long sz = -1;
+        if (fseek(f, 0, SEEK_END) == 0) { sz = ftell(f); rewind(f); }
+        if (sz > 0) {
+            buf.resize((size_t)sz);
+            const size_t got = fread(buf.data(), 1, buf.size(), f);
+            buf.resize(got);
+        }
+        uint8_t tmp[1 << 16];
+        size_t got;
+        while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    }
     fclose(f);
     if (buf.size() < 31 || memcmp(buf.data(), "mdb", 3) != 0) { set_error("%s is not an .mdb file", path); return nullptr; }
     size_t c = 3;

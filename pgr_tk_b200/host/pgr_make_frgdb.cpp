@@ -85,10 +85,10 @@ int main(int argc, char **argv) {
     if (timing) {
         const auto &t = sdb.timing();
         fprintf(stderr, "{\"files\": %zu, \"bases\": %llu, \"gpus\": %d, \"readers\": %d, \"wall_s\": %.4f, \"index_wall_s\": %.4f, \"frag_store_wall_s\": %.4f, "
-                        "\"mdb_midx_wall_s\": %.4f, \"consumer\": {\"wait_for_parser_s\": %.4f, \"gpu_index_calls_s\": %.4f, \"finalize_merge_s\": %.4f, "
+                        "\"mdb_midx_wall_s\": %.4f, \"consumer\": {\"device_init_s\": %.4f, \"wait_for_parser_s\": %.4f, \"gpu_index_calls_s\": %.4f, \"finalize_merge_s\": %.4f, "
                         "\"frag_compress_gpu_s\": %.4f, \"frag_encode_deflate_write_s\": %.4f, \"mdb_write_s\": %.4f}, "
                         "\"reader_threads_total\": {\"read_s\": %.4f, \"parse_s\": %.4f, \"page_lock_s\": %.4f}}\n",
-                paths.size(), (unsigned long long)t.bases, n_gpus, n_readers, t_all, t_index, t_frags - t_index, t_all - t_frags, t.wait_parse_s, t.gpu_index_s, t.merge_s,
+                paths.size(), (unsigned long long)t.bases, n_gpus, n_readers, t_all, t_index, t_frags - t_index, t_all - t_frags, t.device_init_s, t.wait_parse_s, t.gpu_index_s, t.merge_s,
                 t.frag_gpu_s, t.frag_encode_s, t.mdb_write_s, t.reader_read_s, t.reader_parse_s, t.reader_pin_s);
     }
     return 0;

@@ -99,6 +99,15 @@ int SeqIndexDB::load_from_fastx_list(const std::vector<std::string> &paths, uint
     timing_ = Timing();
     if (paths.empty()) { err_ = "empty file list"; return PGR_E_ARG; }
     if (!devices.empty()) n_gpus = (int)devices.size();
+    fastx_backend_ = true;
+    // The library's packed transport reads the caller's bytes with its own host threads and moves pageable memory as fast as
+    // page-locked memory, so the files are parsed in plain memory: reserving page-locked slots cost ~1 s per GB here, more
+    // than the whole index build of config 3.  PGR_B200_INGEST_PINNED=1 restores the page-locked slots (A/B:
+    // profiles/r2_cli_make_frgdb.txt).
+    static const bool pinned_slots = getenv("PGR_B200_INGEST_PINNED") != nullptr;
+    FastxPipeline pipe(paths, n_readers, !pinned_slots ? INGEST_PLAIN : keep_seqs_ ? INGEST_KEEP : INGEST_PINNED);
+    // the readers are already at work on the first files while the CUDA context comes up (0.3 - 2 s depending on the box)
+    const double t_init0 = now_s();
     if (n_gpus > 1) {
         midx_ = devices.empty() ? pgr_b200_mindex_new(&spec_, 0, n_gpus) : pgr_b200_mindex_new_devices(&spec_, 0, n_gpus, devices.data());
         if (!midx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
@@ -106,8 +115,7 @@ int SeqIndexDB::load_from_fastx_list(const std::vector<std::string> &paths, uint
         idx_ = pgr_b200_index_new(&spec_, 0, -1);
         if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_NO_DEVICE; }
     }
-    fastx_backend_ = true;
-    FastxPipeline pipe(paths, n_readers, keep_seqs_ ? INGEST_KEEP : INGEST_PINNED);
+    timing_.device_init_s = now_s() - t_init0;
     // a batch = the files that are parsed by now (at least one); with several GPUs at least a few files per call so that every
     // GPU has a block of the batch to work on
     const size_t max_batch = (size_t)std::max(4, 2 * std::max(1, n_gpus));   // page-locked slots are scarce: window = readers + 4

@@ -66,7 +66,7 @@ public:
     int load_from_fastx_list(const std::vector<std::string> &paths, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span, int n_readers, int n_gpus,
                              const std::vector<int> &devices = {});   // devices: one per shard (may repeat: sharded build on one GPU, a test set-up)
     // wall seconds per phase of the calls above and of the writers (for the CLI's --timing report)
-    struct Timing { double wait_parse_s = 0, gpu_index_s = 0, merge_s = 0, frag_gpu_s = 0, frag_encode_s = 0, mdb_write_s = 0, reader_read_s = 0, reader_parse_s = 0, reader_pin_s = 0; uint64_t bases = 0; };
+    struct Timing { double device_init_s = 0, wait_parse_s = 0, gpu_index_s = 0, merge_s = 0, frag_gpu_s = 0, frag_encode_s = 0, mdb_write_s = 0, reader_read_s = 0, reader_parse_s = 0, reader_pin_s = 0; uint64_t bases = 0; };
     const Timing &timing() const { return timing_; }
     // ext.rs:212-250 load_from_seq_list: sequences given in memory, sids in list order
     int load_from_seq_list(const std::vector<SeqRec> &seq_list, const std::string &source, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span);
