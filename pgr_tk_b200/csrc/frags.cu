@@ -269,7 +269,16 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
     struct Guard { decltype(release_all) &f; ~Guard() { f(); } } guard{release_all};   // every exit path frees the device buffers (release is idempotent)
     PGR_TRY(d_seq.ensure(std::max<uint64_t>(total, 1)));
     PGR_TRY(d_off.ensure(off.size() * sizeof(uint64_t)));
-    for (size_t i = 0; i < n; i++) if (lens[i]) PGR_CUDA(cudaMemcpyAsync((uint8_t *)d_seq.p + off[sids[i]], seqs[i], lens[i], cudaMemcpyHostToDevice, st));
+    {
+        // pageable sources go through the page-locked ring with the host pool doing the copies (PCIe rate instead of ~10 GB/s)
+        pgr_b200_ctx *ctx = idx->ctx;
+        const bool staged = total >= PACK_MIN_BYTES && !source_page_locked(seqs, lens, n) && (ctx->pack || (ctx->pack = pack_ring_acquire(ctx->device)));
+        for (size_t i = 0; i < n; i++) {
+            if (!lens[i]) continue;
+            if (staged && lens[i] >= (1u << 20)) PGR_TRY(upload_raw_staged(ctx->pack, (uint8_t *)d_seq.p + off[sids[i]], seqs[i], lens[i], st));
+            else PGR_CUDA(cudaMemcpyAsync((uint8_t *)d_seq.p + off[sids[i]], seqs[i], lens[i], cudaMemcpyHostToDevice, st));
+        }
+    }
     PGR_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     PGR_CUDA(cudaStreamSynchronize(st));
     {   // every signature must refer to a sequence that was passed, inside its bounds
@@ -332,14 +341,25 @@ int pgr_b200_index_compress_fragments(pgr_b200_index *idx, size_t n, const uint3
         trace_mark("compress_fragments: pass 1 (segments) + records");
     }
     // ---- results to the host: records in fragment-id order, segments ----
-    *frags = (pgr_fragment *)result_alloc(std::max<size_t>(nf, 1) * sizeof(pgr_fragment));
-    *segs = (pgr_aln_seg *)result_alloc(std::max<size_t>(tot_segs, 1) * sizeof(pgr_aln_seg));
+    // large record sets come back through the page-locked ring into plain memory (download_staged); small ones into pool buffers
+    const size_t rec_bytes = std::max<size_t>(nf, 1) * sizeof(pgr_fragment), seg_bytes = std::max<size_t>(tot_segs, 1) * sizeof(pgr_aln_seg);
+    pgr_b200_ctx *rctx = idx->ctx;
+    const bool staged_out = rec_bytes + seg_bytes >= (64u << 20) && (rctx->pack || (rctx->pack = pack_ring_acquire(rctx->device)));
+    *frags = (pgr_fragment *)(staged_out ? malloc(rec_bytes) : result_alloc(rec_bytes));
+    *segs = (pgr_aln_seg *)(staged_out ? malloc(seg_bytes) : result_alloc(seg_bytes));
     auto drop = [&](int rc_) { result_free(*frags); result_free(*segs); *frags = nullptr; *segs = nullptr; return rc_; };   // error exits release the outputs
     if (!*frags || !*segs) { set_error("out of host memory"); return drop(PGR_E_ARG); }
     {
         uint32_t h_flag[3] = {0, 0, 0};
-        cudaError_t ce = cudaMemcpyAsync(*frags, d_rec.p, std::max<size_t>(nf, 1) * sizeof(pgr_fragment), cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess && tot_segs) ce = cudaMemcpyAsync(*segs, d_segs.p, tot_segs * sizeof(pgr_aln_seg), cudaMemcpyDeviceToHost, st);
+        cudaError_t ce = cudaSuccess;
+        if (staged_out) {
+            int rc2 = download_staged(rctx->pack, (uint8_t *)*frags, (const uint8_t *)d_rec.p, rec_bytes, st);
+            if (rc2 == PGR_OK && tot_segs) rc2 = download_staged(rctx->pack, (uint8_t *)*segs, (const uint8_t *)d_segs.p, tot_segs * sizeof(pgr_aln_seg), st);
+            if (rc2 != PGR_OK) return drop(rc2);
+        } else {
+            ce = cudaMemcpyAsync(*frags, d_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess && tot_segs) ce = cudaMemcpyAsync(*segs, d_segs.p, tot_segs * sizeof(pgr_aln_seg), cudaMemcpyDeviceToHost, st);
+        }
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_flag, d_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) { set_error("copying the fragment records failed: %s", cudaGetErrorString(ce)); return drop(PGR_E_CUDA); }

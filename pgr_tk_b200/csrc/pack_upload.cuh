@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstring>
 #include <deque>
 #include <mutex>
 #include <vector>
@@ -256,6 +257,54 @@ inline int upload_packed(PackRing *ring, uint8_t *store, const std::vector<uint6
         last_slot = s;
     }
     if (last_slot >= 0) PGR_CUDA(cudaStreamWaitEvent(st_copy, ring->unpack_done[last_slot], 0));
+    return PGR_OK;
+}
+
+// Raw bytes of a pageable source (fragment compression compares the caller's bytes as they are, so it cannot take the packed
+// transport): the host pool copies them into the ring's page-locked slots, which then cross PCIe at its rate — a direct
+// cudaMemcpyAsync from pageable memory moves ~10 GB/s through the driver's own staging.
+inline int upload_raw_staged(PackRing *ring, uint8_t *dst_dev, const uint8_t *src, size_t bytes, cudaStream_t st) {
+    const size_t slot_bytes = PackRing::slot_words() * 4, piece = 256u << 10;
+    for (size_t o = 0; o < bytes; o += slot_bytes) {
+        const size_t nbytes = std::min(slot_bytes, bytes - o);
+        const int s = (int)(ring->seq++ % PACK_SLOTS);
+        if (ring->used[s]) PGR_CUDA(cudaEventSynchronize(ring->h2d_done[s]));
+        uint8_t *hp = reinterpret_cast<uint8_t *>(ring->h + (size_t)s * PackRing::slot_words());
+        parallel_for((nbytes + piece - 1) / piece, [&](size_t i) { memcpy(hp + i * piece, src + o + i * piece, std::min(piece, nbytes - i * piece)); });
+        PGR_CUDA(cudaMemcpyAsync(dst_dev + o, hp, nbytes, cudaMemcpyHostToDevice, st));
+        PGR_CUDA(cudaEventRecord(ring->h2d_done[s], st));
+        PGR_CUDA(cudaEventRecord(ring->unpack_done[s], st));   // the device slot of this index is not in use: keeps a later packed upload's wait trivial
+        ring->used[s] = true;
+    }
+    return PGR_OK;
+}
+
+// The reverse for large one-off results: device -> ring slots at PCIe rate -> the host pool copies them into plain memory.
+// Page-locking a fresh result buffer costs ~0.5-0.8 ms/MB, five times what the copy itself takes, and a copy into pageable memory
+// runs at ~10 GB/s through the driver's staging; this keeps PCIe busy with neither.  Synchronous: the data is in dst on return.
+inline int download_staged(PackRing *ring, uint8_t *dst, const uint8_t *src_dev, size_t bytes, cudaStream_t st) {
+    const size_t slot_bytes = PackRing::slot_words() * 4, piece = 256u << 10;
+    const size_t n = (bytes + slot_bytes - 1) / slot_bytes;
+    PGR_CUDA(cudaStreamSynchronize(st));   // the ring's slots may still feed an upload queued on another stream: drain ours, then own the ring
+    for (int s = 0; s < PACK_SLOTS; s++) if (ring->used[s]) { PGR_CUDA(cudaEventSynchronize(ring->h2d_done[s])); PGR_CUDA(cudaEventSynchronize(ring->unpack_done[s])); }
+    auto issue = [&](size_t i) -> int {
+        const int s = (int)(i % PACK_SLOTS);
+        uint8_t *hp = reinterpret_cast<uint8_t *>(ring->h + (size_t)s * PackRing::slot_words());
+        PGR_CUDA(cudaMemcpyAsync(hp, src_dev + i * slot_bytes, std::min(slot_bytes, bytes - i * slot_bytes), cudaMemcpyDeviceToHost, st));
+        PGR_CUDA(cudaEventRecord(ring->h2d_done[s], st));
+        return PGR_OK;
+    };
+    for (size_t i = 0; i < std::min<size_t>(n, PACK_SLOTS); i++) PGR_TRY(issue(i));
+    for (size_t i = 0; i < n; i++) {
+        const int s = (int)(i % PACK_SLOTS);
+        PGR_CUDA(cudaEventSynchronize(ring->h2d_done[s]));
+        const uint8_t *hp = reinterpret_cast<const uint8_t *>(ring->h + (size_t)s * PackRing::slot_words());
+        const size_t nbytes = std::min(slot_bytes, bytes - i * slot_bytes);
+        uint8_t *d = dst + i * slot_bytes;
+        parallel_for((nbytes + piece - 1) / piece, [&](size_t q) { memcpy(d + q * piece, hp + q * piece, std::min(piece, nbytes - q * piece)); });
+        if (i + PACK_SLOTS < n) PGR_TRY(issue(i + PACK_SLOTS));
+    }
+    for (int s = 0; s < PACK_SLOTS; s++) ring->used[s] = false;   // every slot is idle again
     return PGR_OK;
 }
 

@@ -97,3 +97,39 @@ def test_synthetic_haplotypes_equal_the_oracle():
         kinds = [f[0] for f in exp]
         assert kinds.count(ff.FRAG_ALN) > 100 and kinds.count(ff.FRAG_INTERNAL) > 50
         assert any(f[0] == ff.FRAG_ALN and f[2] for f in exp)                              # reverse-complemented alignments occur
+
+
+def test_large_pageable_batch_through_the_staged_upload():
+    """>= 4 MB of pageable sequences: the raw bytes reach the device through the page-locked ring (upload_raw_staged) and the
+    index through the packed transport; records and segments equal the C++ fragment oracle (soft-masked stretches included:
+    match_reads compares raw bytes, the index only base classes)"""
+    rng = np.random.default_rng(505)
+    anc = ACGT[rng.integers(0, 4, size=2_200_000)]
+    seqs = []
+    for h in range(3):
+        s = anc.copy()
+        pos = rng.integers(0, len(s), size=len(s) // 400)
+        s[pos] = ACGT[rng.integers(0, 4, size=len(pos))]
+        if h == 1:
+            s[700_000:760_000] |= 0x20
+        if h == 2:
+            s = np.concatenate([s[:900_000], s[950_000:]])
+        seqs.append(s.tobytes())
+    assert sum(map(len, seqs)) >= 4 << 20
+    spec_t = (80, 56, 4, 64)
+    g = pg.ShmmrIndex(pg.ShmmrSpec(*spec_t), 0)
+    g.add_batch([0, 1, 2], seqs)
+    fr, sg = g.compress_fragments([0, 1, 2], seqs)
+    g.close()
+    efr, esg = orc.compress_fragments([0, 1, 2], seqs, orc.mkspec(*spec_t), nthreads=3)
+    assert len(fr) == len(efr) and len(sg) == len(esg)
+    for f in ("kind", "sid", "bgn", "end", "len", "reversed", "ref_frag", "n_segs"):
+        assert np.array_equal(fr[f], efr[f]), f
+
+    def segs_in_id_order(frags, segs):   # the segment arrays are laid out differently (index order / id order): compare per fragment
+        idx = np.concatenate([np.arange(int(o), int(o) + int(c)) for o, c in zip(frags["seg_off"], frags["n_segs"]) if c] or [np.zeros(0, dtype=np.int64)])
+        return segs[idx.astype(np.int64)]
+    a, b = segs_in_id_order(fr, sg), segs_in_id_order(efr, esg)
+    assert len(a) == len(b) == len(sg)
+    for f in ("type", "a", "b"):
+        assert np.array_equal(a[f], b[f]), f
