@@ -278,8 +278,9 @@ void pgr_b200_index_free(pgr_b200_index *idx) {
                       &idx->head, &idx->block_sum, &idx->block_prefix, &idx->d_sid, &idx->d_pair_off, &idx->d_frg_base, &idx->qtuples,
                       &idx->q_hit_begin, &idx->q_hit_count, &idx->scratch0, &idx->scratch1, &idx->scratch2, &idx->scratch3,
                       &idx->sid_count, &idx->hitsA, &idx->hitsB, &idx->seg_keys, &idx->seg_off, &idx->chain_f, &idx->chain_u, &idx->chain_b,
-                      &idx->chain_seg, &idx->asm_prefix, &idx->asm_has, &idx->asm_out, &idx->sendbuf};
+                      &idx->chain_seg, &idx->asm_prefix, &idx->asm_has, &idx->asm_out, &idx->asm_out2, &idx->sendbuf};
     for (auto b : bufs) b->release();
+    if (idx->d2h_stream) cudaStreamDestroy(idx->d2h_stream);
     pgr_b200_ctx_free(idx->ctx);
     delete idx;
 }

@@ -31,7 +31,8 @@ struct pgr_b200_index {
     // scratch
     pgr::DevBuf keysA, keysB, idxA, idxB, hist, head, block_sum, block_prefix, d_sid, d_pair_off, d_frg_base;
     pgr::DevBuf qtuples, q_hit_begin, q_hit_count, scratch0, scratch1, scratch2, scratch3;
-    pgr::DevBuf sid_count, hitsA, hitsB, seg_keys, seg_off, chain_f, chain_u, chain_b, chain_seg, asm_prefix, asm_has, asm_out;
+    pgr::DevBuf sid_count, hitsA, hitsB, seg_keys, seg_off, chain_f, chain_u, chain_b, chain_seg, asm_prefix, asm_has, asm_out, asm_out2;
+    cudaStream_t d2h_stream = nullptr;   // result download of one query group while the next is computed
     bool sid_count_valid = false;
     uint64_t launches = 0;
 };

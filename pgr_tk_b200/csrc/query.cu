@@ -130,16 +130,23 @@ void pgr_b200_query_result_free(pgr_query_result *r) {
     free(r);
 }
 
-// replaces SeqIndexDB::query_fragment_to_hps (ext.rs:252-282) for a batch of queries
-int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *seqs, const size_t *lens, const pgr_query_params *prm,
-                         pgr_query_result **out) {
-    if (!idx || !prm || !out || (n_q && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
-    PGR_CUDA(cudaSetDevice(idx->ctx->device));
+}  // extern "C"
+
+// device half of query_fragment_to_hps for queries [0, n_q) of `seqs`: shimmers, pairs, look-up, filters, expansion, per-query
+// sort, chaining and the nested result arrays, left in `asm_out` (QueryGroupOut points into it).  The offsets it writes are
+// already global: chain_base / hit_base = chains / hits of the groups before this one.
+struct QueryGroupOut {
+    uint64_t n_targets = 0, n_chains = 0, n_hits = 0;
+    const uint32_t *target_sid = nullptr, *target_qid = nullptr;
+    const uint64_t *target_chain_off = nullptr, *chain_hit_off = nullptr;
+    const float *chain_score = nullptr;
+    const pgr_hit_pair *hits = nullptr;
+};
+static int query_group(pgr_b200_index *idx, size_t n_q, const uint8_t *const *seqs, const size_t *lens, const pgr_query_params *prm, DevBuf &asm_out,
+                       uint64_t chain_base, uint64_t hit_base, QueryGroupOut *out) {
     pgr_b200_ctx *ctx = idx->ctx;
     cudaStream_t st = ctx->stream;
-    trace_mark("query_batch: begin");
-    PGR_TRY(ensure_sid_count(idx));
-    trace_mark("query_batch: sid_count");
+    *out = QueryGroupOut();
     uint64_t n_qp = 0;
     std::vector<uint64_t> qp_off;
     PGR_TRY(query_pairs_and_lookup(idx, n_q, seqs, lens, &n_qp, &qp_off));
@@ -150,12 +157,6 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
     f.max_count_query = prm->max_count_query < 0 ? 128u : (uint32_t)prm->max_count_query;
     f.max_count_target = prm->max_count_target < 0 ? 128u : (uint32_t)prm->max_count_target;
     const uint32_t max_span = prm->max_aln_span < 0 ? 8u : (uint32_t)prm->max_aln_span;
-
-    std::vector<uint64_t> q_target_off(n_q + 1, 0);
-    uint32_t *r_target_sid = nullptr; uint64_t *r_target_chain_off = nullptr; float *r_chain_score = nullptr;
-    uint64_t *r_chain_hit_off = nullptr; pgr_hit_pair *r_hits = nullptr;
-    size_t n_targets = 0, n_chains = 0, n_hits_out = 0;
-    bool have_result = false;
 
     uint64_t n_hits = 0;
     if (n_qp) {
@@ -266,8 +267,8 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
                 for (uint64_t s = 0; s < n_seg; s++)
                     if (err[s]) { set_error("sparse_aln: all scores <= 0 (the reference would not terminate)"); return PGR_E_ASSERT; }
             }
-            PGR_TRY(idx->asm_out.ensure(tot_targets * 16 + (tot_targets + 1) * 8 + tot_chains * 4 + (tot_chains + 1) * 8 + tot_hits * sizeof(pgr_hit_pair) + 256));
-            uint8_t *ob = idx->asm_out.as<uint8_t>();
+            PGR_TRY(asm_out.ensure(tot_targets * 16 + (tot_targets + 1) * 8 + tot_chains * 4 + (tot_chains + 1) * 8 + tot_hits * sizeof(pgr_hit_pair) + 256));
+            uint8_t *ob = asm_out.as<uint8_t>();
             AssembleParams ap;
             ap.hits = idx->hitsB.as<HitRec>(); ap.seg_off = idx->seg_off.as<uint64_t>(); ap.seg_keys = idx->seg_keys.as<SortKey>(); ap.n_seg = n_seg;
             ap.out_idx = cp.out_idx; ap.out_start = cp.out_start; ap.out_score = cp.out_score; ap.seg_n_out = cp.seg_n_out;
@@ -278,50 +279,152 @@ int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *
             ap.target_sid = (uint32_t *)ob; ob += tot_targets * 4;
             ap.target_qid = (uint32_t *)ob; ob += tot_targets * 4;
             ap.chain_score = (float *)ob;
+            ap.chain_base = chain_base; ap.hit_base = hit_base;
             assemble_kernel<<<(uint32_t)ceil_div<uint64_t>(n_seg, 128), 128, 0, st>>>(ap);
-            set_u64_kernel<<<1, 1, 0, st>>>(ap.target_chain_off + tot_targets, tot_chains);
-            set_u64_kernel<<<1, 1, 0, st>>>(ap.chain_hit_off + tot_chains, tot_hits);
+            set_u64_kernel<<<1, 1, 0, st>>>(ap.target_chain_off + tot_targets, chain_base + tot_chains);
+            set_u64_kernel<<<1, 1, 0, st>>>(ap.chain_hit_off + tot_chains, hit_base + tot_hits);
             idx->launches += 4;
             PGR_CUDA(cudaGetLastError());
             trace_mark("query_batch: device assembly");
-            r_target_sid = (uint32_t *)result_alloc(std::max<uint64_t>(1, tot_targets) * 4);
-            r_target_chain_off = (uint64_t *)result_alloc((tot_targets + 1) * 8);
-            r_chain_score = (float *)result_alloc(std::max<uint64_t>(1, tot_chains) * 4);
-            r_chain_hit_off = (uint64_t *)result_alloc((tot_chains + 1) * 8);
-            r_hits = (pgr_hit_pair *)result_alloc(std::max<uint64_t>(1, tot_hits) * sizeof(pgr_hit_pair));
-            std::vector<uint32_t> tq(tot_targets);
-            if (tot_targets) {
-                PGR_CUDA(cudaMemcpyAsync(r_target_sid, ap.target_sid, tot_targets * 4, cudaMemcpyDeviceToHost, st));
-                PGR_CUDA(cudaMemcpyAsync(tq.data(), ap.target_qid, tot_targets * 4, cudaMemcpyDeviceToHost, st));
-            }
-            PGR_CUDA(cudaMemcpyAsync(r_target_chain_off, ap.target_chain_off, (tot_targets + 1) * 8, cudaMemcpyDeviceToHost, st));
-            if (tot_chains) PGR_CUDA(cudaMemcpyAsync(r_chain_score, ap.chain_score, tot_chains * 4, cudaMemcpyDeviceToHost, st));
-            PGR_CUDA(cudaMemcpyAsync(r_chain_hit_off, ap.chain_hit_off, (tot_chains + 1) * 8, cudaMemcpyDeviceToHost, st));
-            if (tot_hits) PGR_CUDA(cudaMemcpyAsync(r_hits, ap.hits_out, tot_hits * sizeof(pgr_hit_pair), cudaMemcpyDeviceToHost, st));
-            PGR_CUDA(cudaStreamSynchronize(st));
-            n_targets = tot_targets; n_chains = tot_chains; n_hits_out = tot_hits;
-            // targets are sorted by query: q_target_off[q] = number of targets of queries < q
-            size_t ti = 0;
-            for (size_t q = 0; q < n_q; q++) {
-                q_target_off[q] = ti;
-                while (ti < tot_targets && tq[ti] == q) ti++;
-            }
-            q_target_off[n_q] = ti;
-            have_result = true;
+            out->n_targets = tot_targets; out->n_chains = tot_chains; out->n_hits = tot_hits;
+            out->target_sid = ap.target_sid; out->target_qid = ap.target_qid; out->target_chain_off = ap.target_chain_off;
+            out->chain_score = ap.chain_score; out->chain_hit_off = ap.chain_hit_off; out->hits = ap.hits_out;
         }
     }
-    trace_mark("query_batch: host assembly");
-    if (!have_result) {
-        r_target_sid = (uint32_t *)result_alloc(4); r_target_chain_off = (uint64_t *)result_alloc(8); r_chain_score = (float *)result_alloc(4);
-        r_chain_hit_off = (uint64_t *)result_alloc(8); r_hits = (pgr_hit_pair *)result_alloc(sizeof(pgr_hit_pair));
-        r_target_chain_off[0] = 0; r_chain_hit_off[0] = 0;
+    return PGR_OK;
+}
+
+// grow-only host array for the batch result (page-locked pool buffers): append(n) returns where the next n items go
+namespace {
+template <class T>
+struct HostArr {
+    T *p = nullptr; size_t n = 0, cap = 0;
+    // false when out of memory.  `sync` is called before the contents move to a larger buffer (copies may be in flight).
+    template <class F> bool reserve(size_t need, F sync, size_t hint = 0) {
+        if (need <= cap) return true;
+        const size_t ncap = std::max(std::max(need, hint), cap + cap / 2);   // the hint only sizes an allocation that has to happen anyway
+        T *np = (T *)result_alloc(std::max<size_t>(1, ncap) * sizeof(T));
+        if (!np) return false;
+        if (p) { sync(); memcpy(np, p, n * sizeof(T)); result_free(p); }
+        p = np; cap = ncap;
+        return true;
     }
+};
+}  // namespace
+
+extern "C" {
+
+// replaces SeqIndexDB::query_fragment_to_hps (ext.rs:252-282) for a batch of queries.  A large batch is cut into groups of
+// queries: the device-to-host copy of a group's result (the hit pairs are the bulk: 20 B each) runs on its own stream while
+// the next group is computed, into one set of host arrays whose offsets are global from the start.
+int pgr_b200_query_batch(pgr_b200_index *idx, size_t n_q, const uint8_t *const *seqs, const size_t *lens, const pgr_query_params *prm,
+                         pgr_query_result **out) {
+    if (!idx || !prm || !out || (n_q && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
+    PGR_CUDA(cudaSetDevice(idx->ctx->device));
+    pgr_b200_ctx *ctx = idx->ctx;
+    cudaStream_t st = ctx->stream;
+    trace_mark("query_batch: begin");
+    PGR_TRY(ensure_sid_count(idx));
+    trace_mark("query_batch: sid_count");
+    uint64_t total_len = 0;
+    for (size_t q = 0; q < n_q; q++) total_len += lens[q];
+    static const int forced_groups = getenv("PGR_B200_QUERY_GROUPS") ? atoi(getenv("PGR_B200_QUERY_GROUPS")) : 0;   // A/B aid
+    // Default: one group.  Measured on config 4 (10 000 x 20 kb queries, 573 MB of result; profiles/r2_sort_query_ab.txt): the copy
+    // of a group's result does hide behind the next group's kernels, but four groups of 2 500 queries cost more in per-group work
+    // (upload not overlapped inside a group, shorter chain launches) than the 8.6 ms they hide: 34.4 ms with one group, ~36 ms with four.
+    size_t n_groups = forced_groups > 0 ? (size_t)forced_groups : 1;
+    n_groups = std::max<size_t>(1, std::min(n_groups, std::max<size_t>(1, n_q)));
+    std::vector<size_t> cut(n_groups + 1, n_q);
+    cut[0] = 0;
+    {
+        uint64_t acc = 0;
+        size_t g = 1;
+        for (size_t q = 0; q < n_q && g < n_groups; q++) {
+            acc += lens[q];
+            while (g < n_groups && acc * n_groups >= total_len * g) cut[g++] = q + 1;
+        }
+    }
+    if (!idx->d2h_stream) PGR_CUDA(cudaStreamCreateWithFlags(&idx->d2h_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = idx->d2h_stream;
+    cudaEvent_t ev_ready[2], ev_copied[2];
+    for (int i = 0; i < 2; i++) { cudaEventCreateWithFlags(&ev_ready[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming); }
+    bool copied_pending[2] = {false, false};
+    HostArr<uint32_t> h_tsid, h_tqid;
+    HostArr<uint64_t> h_tco, h_cho;
+    HostArr<float> h_score;
+    HostArr<pgr_hit_pair> h_hits;
+    std::vector<std::pair<size_t, size_t>> group_targets;   // (first target, count) per group, for q_target_off
+    auto sync_copies = [&]() { cudaStreamSynchronize(cs); };
+    int rc = PGR_OK;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(cs);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_ready[i]); cudaEventDestroy(ev_copied[i]); }
+    };
+    auto fail = [&](int r) { cleanup(); result_free(h_tsid.p); result_free(h_tqid.p); result_free(h_tco.p); result_free(h_cho.p); result_free(h_score.p); result_free(h_hits.p); return r; };
+    for (size_t g = 0; g < n_groups; g++) {
+        const int slot = (int)(g & 1);
+        DevBuf &asm_out = slot ? idx->asm_out2 : idx->asm_out;
+        if (copied_pending[slot]) { cudaEventSynchronize(ev_copied[slot]); copied_pending[slot] = false; }   // the copy out of this buffer is over
+        QueryGroupOut go;
+        const size_t q0 = cut[g], nq = cut[g + 1] - cut[g];
+        if (nq == 0) { group_targets.push_back({h_tsid.n, 0}); continue; }
+        rc = query_group(idx, nq, seqs + q0, lens + q0, prm, asm_out, h_score.n, h_hits.n, &go);
+        if (rc != PGR_OK) return fail(rc);
+        group_targets.push_back({h_tsid.n, (size_t)go.n_targets});
+        if (go.n_targets == 0 && go.n_chains == 0 && go.n_hits == 0) continue;
+        // capacity: after the first group with results, extrapolate to the whole batch (+30 %)
+        const double scale = (double)total_len / (double)std::max<uint64_t>(1, [&] { uint64_t a = 0; for (size_t q = 0; q < cut[g + 1]; q++) a += lens[q]; return a; }()) * 1.3;
+        const bool ok = h_tsid.reserve(h_tsid.n + go.n_targets, sync_copies, (size_t)((h_tsid.n + go.n_targets) * scale)) &&
+                        h_tqid.reserve(h_tqid.n + go.n_targets, sync_copies, (size_t)((h_tqid.n + go.n_targets) * scale)) &&
+                        h_tco.reserve(h_tco.n + go.n_targets + 1, sync_copies, (size_t)((h_tco.n + go.n_targets) * scale) + 1) &&
+                        h_score.reserve(h_score.n + go.n_chains, sync_copies, (size_t)((h_score.n + go.n_chains) * scale)) &&
+                        h_cho.reserve(h_cho.n + go.n_chains + 1, sync_copies, (size_t)((h_cho.n + go.n_chains) * scale) + 1) &&
+                        h_hits.reserve(h_hits.n + go.n_hits, sync_copies, (size_t)((h_hits.n + go.n_hits) * scale));
+        if (!ok) { set_error("out of host memory"); return fail(PGR_E_ARG); }
+        cudaEventRecord(ev_ready[slot], st);
+        cudaStreamWaitEvent(cs, ev_ready[slot], 0);
+        cudaError_t ce = cudaSuccess;
+        if (go.n_targets) {
+            ce = cudaMemcpyAsync(h_tsid.p + h_tsid.n, go.target_sid, go.n_targets * 4, cudaMemcpyDeviceToHost, cs);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_tqid.p + h_tqid.n, go.target_qid, go.n_targets * 4, cudaMemcpyDeviceToHost, cs);
+        }
+        // the offset arrays carry one closing entry per group; the next group overwrites it with its own first entry (equal value)
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_tco.p + h_tco.n, go.target_chain_off, (go.n_targets + 1) * 8, cudaMemcpyDeviceToHost, cs);
+        if (ce == cudaSuccess && go.n_chains) ce = cudaMemcpyAsync(h_score.p + h_score.n, go.chain_score, go.n_chains * 4, cudaMemcpyDeviceToHost, cs);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_cho.p + h_cho.n, go.chain_hit_off, (go.n_chains + 1) * 8, cudaMemcpyDeviceToHost, cs);
+        if (ce == cudaSuccess && go.n_hits) ce = cudaMemcpyAsync(h_hits.p + h_hits.n, go.hits, go.n_hits * sizeof(pgr_hit_pair), cudaMemcpyDeviceToHost, cs);
+        if (ce != cudaSuccess) { set_error("D2H of the query result failed: %s", cudaGetErrorString(ce)); return fail(PGR_E_CUDA); }
+        cudaEventRecord(ev_copied[slot], cs);
+        copied_pending[slot] = true;
+        h_tsid.n += go.n_targets; h_tqid.n += go.n_targets; h_tco.n += go.n_targets;
+        h_score.n += go.n_chains; h_cho.n += go.n_chains; h_hits.n += go.n_hits;
+    }
+    cleanup();
+    trace_mark("query_batch: host assembly");
+    const size_t n_targets = h_tsid.n, n_chains = h_score.n, n_hits_out = h_hits.n;
+    // closing entries (also for an empty result)
+    if (!h_tco.reserve(n_targets + 1, sync_copies) || !h_cho.reserve(n_chains + 1, sync_copies) || !h_tsid.reserve(1, sync_copies) ||
+        !h_score.reserve(1, sync_copies) || !h_hits.reserve(1, sync_copies)) { set_error("out of host memory"); return fail(PGR_E_ARG); }
+    h_tco.p[n_targets] = n_chains; h_cho.p[n_chains] = n_hits_out;
+    // targets are sorted by query inside a group, groups are in query order: q_target_off[q] = number of targets of queries < q
+    std::vector<uint64_t> q_target_off(n_q + 1, 0);
+    for (size_t g = 0; g < n_groups; g++) {
+        const size_t q0 = cut[g], nq = cut[g + 1] - cut[g];
+        size_t ti = group_targets[g].first;
+        const size_t te = ti + group_targets[g].second;
+        for (size_t q = 0; q < nq; q++) {
+            q_target_off[q0 + q] = ti;
+            while (ti < te && h_tqid.p[ti] == q) ti++;
+        }
+    }
+    q_target_off[n_q] = n_targets;
+    result_free(h_tqid.p);
     pgr_query_result *r = (pgr_query_result *)calloc(1, sizeof(pgr_query_result));
     r->n_queries = n_q; r->n_targets = n_targets; r->n_chains = n_chains; r->n_hits = n_hits_out;
     r->q_target_off = (uint64_t *)result_alloc((n_q + 1) * 8);
     memcpy(r->q_target_off, q_target_off.data(), (n_q + 1) * 8);
-    r->target_sid = r_target_sid; r->target_chain_off = r_target_chain_off; r->chain_score = r_chain_score;
-    r->chain_hit_off = r_chain_hit_off; r->hits = r_hits;
+    r->target_sid = h_tsid.p; r->target_chain_off = h_tco.p; r->chain_score = h_score.p;
+    r->chain_hit_off = h_cho.p; r->hits = h_hits.p;
     *out = r;
     return PGR_OK;
 }

@@ -381,6 +381,7 @@ struct AssembleParams {
     const uint64_t *hit_prefix, *chain_prefix, *target_prefix;     // exclusive scans over segments
     uint32_t *target_sid, *target_qid; uint64_t *target_chain_off;
     float *chain_score; uint64_t *chain_hit_off; pgr_hit_pair *hits_out;
+    uint64_t chain_base, hit_base;   // chains / hits of the query groups before this one: the offsets written are global
 };
 __global__ void seg_has_kernel(const uint32_t *seg_n_out, uint64_t n_seg, uint32_t *has) {
     const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -394,10 +395,10 @@ __global__ void assemble_kernel(const AssembleParams p) {
     const uint64_t t = p.target_prefix[s], b = p.seg_off[s], hb = p.hit_prefix[s];
     p.target_sid[t] = (uint32_t)p.seg_keys[s].k1;
     p.target_qid[t] = (uint32_t)p.seg_keys[s].k0;
-    p.target_chain_off[t] = p.chain_prefix[s];
+    p.target_chain_off[t] = p.chain_base + p.chain_prefix[s];
     uint64_t c = p.chain_prefix[s];
     for (uint32_t a = 0; a < n_out; a++) {
-        if (p.out_start[b + a]) { p.chain_score[c] = p.out_score[b + a]; p.chain_hit_off[c] = hb + a; c++; }
+        if (p.out_start[b + a]) { p.chain_score[c] = p.out_score[b + a]; p.chain_hit_off[c] = p.hit_base + hb + a; c++; }
         const HitRec h = p.hits[b + p.out_idx[b + a]];
         pgr_hit_pair hp;
         hp.qb = h.qb; hp.qe = h.qe; hp.tb = h.tb; hp.te = h.te; hp.qo = h.qo; hp.to = h.to; hp.pad_[0] = hp.pad_[1] = 0;
