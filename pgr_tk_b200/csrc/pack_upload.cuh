@@ -144,11 +144,11 @@ inline bool source_page_locked(const uint8_t *const *seqs, const size_t *lens, s
 // Which transport a batch takes when the mode is the default.  Packing pays when the host packs faster than PCIe copies
 // (~5.6 GB/s per pool thread against ~50 GB/s for a page-locked source) or when the source is pageable, which the direct copy
 // moves at ~10 GB/s through the driver's staging.  A page-locked source is fed in hybrid form (see PackRing): slots are copied
-// as they are whenever the packer cannot keep the copy engine busy.  With very few host threads per process (8 ranks on a
-// 32-CPU node: 4 each) the node's aggregate host-to-device rate is the limit and packing only competes for memory bandwidth:
-// measured at N = 8, direct 168.5, hybrid 152.6, packed only 93.3 Gbases/s — so below PACK_MIN_THREADS a page-locked source is
-// copied directly.  (N = 1, 16 threads: hybrid 99.2, packed only 87.2, direct 49.4 Gbases/s.)
-constexpr unsigned PACK_MIN_THREADS = 6;
+// as they are whenever the packer cannot keep the copy engine busy.  With few host threads per process (one process per GPU on a
+// node with 24-32 CPUs) the node's aggregate host-to-device rate is the limit and packing only competes for memory bandwidth.
+// Whole-job Gbases/s of the e2e leg, hybrid against direct, by ranks x pool threads: 1 x 16: 95-99 / 48-49; 2 x 12: 112 / 96;
+// 4 x 8: 148 / 175; 8 x 4: 153 / 169 (packed only: 93) — so below PACK_MIN_THREADS a page-locked source is copied directly.
+constexpr unsigned PACK_MIN_THREADS = 10;
 inline std::atomic<int> &last_transport() { static std::atomic<int> t{-1}; return t; }   // what the newest batch call took (0 packed, 1 direct)
 inline bool choose_packed(const uint8_t *const *seqs, const size_t *lens, size_t n, uint64_t total_bases) {
     if (!packed_upload_enabled() || total_bases < PACK_MIN_BYTES) return false;
