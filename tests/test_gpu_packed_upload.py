@@ -64,3 +64,52 @@ def test_packed_index_equals_oracle():
     ek, eo, es = o.export()
     assert np.array_equal(gk, ek) and np.array_equal(go, eo)
     assert all(np.array_equal(gs[f], es[f]) for f in ("frg_id", "sid", "bgn", "end", "ori"))
+
+
+def test_hybrid_feeding_of_a_page_locked_batch_equals_the_direct_copy():
+    """a page-locked batch of several ring slots (hybrid feeding: some slots packed, some copied as they are) gives the same
+    shimmers as the direct transport, and the oracle's on its first sequences"""
+    import ctypes as C
+    rng = np.random.default_rng(81)
+    lens = [33_000_001, 5_000_017, 41_000_000, 64, 12_345_678, 9_000_000]
+    total = sum(lens)
+    hb = pg.host_alloc(total + 64 * len(lens))
+    ptrs, off = [], 0
+    for i, L in enumerate(lens):
+        v = hb.array[off:off + L]
+        v[:] = np.frombuffer(messy(rng, L, i % 3), dtype=np.uint8)
+        ptrs.append(hb.ptr + off)
+        off += (L + 63) & ~63
+    spec = pg.ShmmrSpec(80, 56, 4, 64)
+    Lb = pg.lib()
+
+    def run():
+        n = len(lens)
+        cp = (C.c_void_p * n)(*ptrs)
+        cl = (C.c_size_t * n)(*lens)
+        rids = np.arange(n, dtype=np.uint32)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        out = C.c_void_p()
+        rc = Lb.pgr_b200_shmmrs_batch(n, rids.ctypes.data, cp, cl, C.byref(spec), 0, C.byref(out), offs.ctypes.data)
+        assert rc == 0, Lb.pgr_b200_last_error()
+        k = int(offs[-1])
+        mm = np.frombuffer((C.c_char * (k * 16)).from_address(out.value), dtype=pg.MM128, count=k).copy()
+        Lb.pgr_b200_free(out)
+        return mm, offs
+
+    for _ in range(2):   # the second call finds the ring warm and its pack-time estimate settled
+        a, ao = run()
+    assert Lb.pgr_b200_last_transport() == pg.TRANSPORT_PACKED or Lb.pgr_b200_pool_threads() < 10
+    prev = pg.set_transport(pg.TRANSPORT_DIRECT)
+    try:
+        b, bo = run()
+        assert Lb.pgr_b200_last_transport() == pg.TRANSPORT_DIRECT
+    finally:
+        pg.set_transport(prev)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    o1 = (lens[0] + 63) & ~63
+    seq1 = bytes(hb.array[o1:o1 + lens[1]])
+    exp = orc.sequence_to_shmmrs(1, seq1, orc.mkspec(80, 56, 4, 64))
+    k0, k1 = int(ao[1]), int(ao[2])
+    assert k1 - k0 == len(exp) and np.array_equal(a[k0:k1], exp)
+    hb.free()
