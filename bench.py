@@ -286,7 +286,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "l0_kernel<80,56> (l0_minimizers)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": l0,
                 "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "integer-issue bound, not HBM bound (SURVEY §8d): ~93 int32 instructions per base, ALU pipe 71 % busy; see int_issue, DESIGN.md and profiles/"}
+                "note": "integer-issue bound, not HBM bound (SURVEY §8d): ~94 int32 instructions per base, ALU pipe 73 % busy; see int_issue, DESIGN.md and profiles/"}
     traffic_file = os.path.join(ROOT, "profiles", "l0_traffic.json")
     if os.path.exists(traffic_file):
         try:

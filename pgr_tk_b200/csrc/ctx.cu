@@ -1001,7 +1001,8 @@ int run_sketch(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint64_t *n_l0) {
     sp.dirty_bits = ctx->mark_bits.as<uint32_t>(); sp.allinv_bits = ctx->allinv_bits.as<uint32_t>(); sp.n_dirty = ctx->n_skips.as<uint32_t>();
     sp.tile_count = ctx->seq_count.as<uint32_t>(); sp.tile_off = nullptr; sp.out = nullptr;
     int slot = ctx->timer.begin("sketch_masks", st);
-    sketch_mask_kernel<<<n_tiles, L0_NT, 0, st>>>(sp);
+    if (spec.k == 56) sketch_mask_kernel<56><<<n_tiles, L0_NT, 0, st>>>(sp);
+    else sketch_mask_kernel<0><<<n_tiles, L0_NT, 0, st>>>(sp);
     ctx->timer.end(slot, st);
     PGR_CUDA(cudaGetLastError());
     PGR_TRY(ctx->ensure_ctl((size_t)n_tiles * sizeof(uint32_t) + 64));

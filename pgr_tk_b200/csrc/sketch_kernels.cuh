@@ -148,6 +148,10 @@ __device__ __forceinline__ void sketch_planes(SketchSmem &s, const uint8_t *sq, 
     if (tid < 8) { s.F0[L0_NT + tid] = 0; s.F1[L0_NT + tid] = 0; }
 }
 
+// K > 32: the key loop of l0_kernel's fast form (strand from the top 32 bits X of the plane-0 registers, plane 1 and the low
+// words for the chosen strand only); a block in which some position has X_f == X_r — every palindrome is one — is redone by
+// the generic loop, which tests strand and palindrome exactly.  K = 0: generic loop only.
+template <int K>
 __global__ void __launch_bounds__(L0_NT) sketch_mask_kernel(const SketchTParams p) {
     __shared__ SketchSmem s;
     const int tid = threadIdx.x;
@@ -183,6 +187,42 @@ __global__ void __launch_bounds__(L0_NT) sketch_mask_kernel(const SketchTParams 
         const uint32_t q00 = fsr(ra0, ra1, cb), q01 = fsr(ra1, ra2, cb), q02 = fsr(ra2, ra3, cb);
         const uint32_t q10 = fsr(rb0, rb1, cb), q11 = fsr(rb1, rb2, cb), q12 = fsr(rb2, rb3, cb);
         const uint64_t thr = sketch_threshold(p.r);
+        bool fast_done = false;
+        if constexpr (K > 32) {
+            constexpr uint32_t PS = K - 32, HS = 64 - K;
+            const uint32_t a0p = fsr(a0, a1, PS), a1p = fsr(a1, a2, PS);
+            const uint32_t b0p = fsr(b0, b1, PS), b1p = fsr(b1, b2, PS);
+            const uint32_t q0p0 = fsr(q00, q01, PS), q0p1 = fsr(q01, q02, PS);
+            const uint32_t q1p0 = fsr(q10, q11, PS), q1p1 = fsr(q11, q12, PS);
+            const uint32_t thr_hi = (uint32_t)(thr >> 32), thr_lo = (uint32_t)thr;
+            bool no_tie = true;
+            uint32_t kp = 0, sd = 0;
+#pragma unroll 4
+            for (int i = 0; i < 32; i++) {
+                const uint32_t sl = (uint32_t)i + 1u;
+                const uint32_t f0x = __funnelshift_lc(a0p, a1p, sl), r0x = fsr(q0p0, q0p1, i);
+                no_tie &= (f0x != r0x);
+                const bool rev = r0x < f0x;
+                const uint32_t ux = min(f0x, r0x);
+                uint32_t ulo = rev ? fsr(q00, q01, i) : __funnelshift_lc(a0, a1, sl);
+                uint32_t vlo = (rev ? fsr(q10, q11, i) : __funnelshift_lc(b0, b1, sl)) ^ (uint32_t)HASH_XOR;
+                const uint32_t vx = rev ? fsr(q1p0, q1p1, i) : __funnelshift_lc(b0p, b1p, sl);
+                uint32_t uhi = ux >> HS, vhi = vx >> HS;
+                u64hash_dev32(ulo, uhi);
+                u64hash_dev32(vlo, vhi);
+                const uint32_t hh = uhi ^ vhi, hl = ulo ^ vlo;
+                if (hh < thr_hi || (hh == thr_hi && hl < thr_lo)) { kp |= 1u << i; if (rev) sd |= 1u << i; }
+            }
+            if (no_tie) {
+                // positions outside [k, L) are masked here (the loop above is branch-free)
+                uint32_t ok = 0xFFFFFFFFu;
+                if (blk_pos < (int64_t)k) ok &= (blk_pos + 32 <= (int64_t)k) ? 0u : (0xFFFFFFFFu << (uint32_t)((int64_t)k - blk_pos));
+                if (blk_pos + 32 > L) ok &= 0xFFFFFFFFu >> (uint32_t)(blk_pos + 32 - L);
+                keep = kp & ok; strand = sd & ok;
+                fast_done = true;
+            }
+        }
+        if (!fast_done)
 #pragma unroll 4
         for (int i = 0; i < 32; i++) {
             const uint32_t sh = 31 - i;
