@@ -546,27 +546,59 @@ pgr_b200_index *pgr_b200_index_read_mdb(const char *path, int device) {
     spec.w = r32(); spec.k = r32(); spec.r = r32(); spec.min_span = r32(); spec.sketch = r32() & 1u;
     const uint64_t nk = r64();
     if (nk > (buf.size() - c) / 24) { set_error("%s is truncated", path); return nullptr; }
-    std::vector<FragTuple> tuples;
-    uint64_t max_frg = 0;
+    // pass 1 (sequential, headers only): where every key's records start and how many signatures precede it
+    std::vector<uint64_t> key_at(nk), sig_before(nk + 1);
+    uint64_t n_sig = 0;
     for (uint64_t i = 0; i < nk; i++) {
         if (c + 24 > buf.size()) { set_error("%s is truncated", path); return nullptr; }
-        const uint64_t h0 = r64(), h1 = r64(), vl = r64();
+        key_at[i] = c;
+        uint64_t vl; memcpy(&vl, &buf[c + 16], 8);
+        c += 24;
         if (vl > (buf.size() - c) / 17) { set_error("%s is truncated", path); return nullptr; }   // no overflow: compare counts
-        for (uint64_t j = 0; j < vl; j++) {
-            FragTuple t;
-            t.h0 = h0; t.h1 = h1; t.frg_id = r32(); t.sid = r32(); t.bgn = r32(); t.end = r32(); t.ori = buf[c]; c += 1; t.ord = 0;
-            max_frg = std::max<uint64_t>(max_frg, (uint64_t)t.frg_id + 1);
-            tuples.push_back(t);
-        }
+        sig_before[i] = n_sig;
+        n_sig += vl; c += 17 * vl;
     }
+    sig_before[nk] = n_sig;
+    if (n_sig >= 0xFFFFFFF0ull) { set_error("%s holds more than 2^32 signatures", path); return nullptr; }
+    // pass 2 (host pool): the records of a range of keys -> tuples at their final places
+    std::unique_ptr<FragTuple[]> tuples(new FragTuple[std::max<uint64_t>(1, n_sig)]);
+    const uint64_t per = 1u << 13;
+    std::vector<uint64_t> max_of((size_t)ceil_div<uint64_t>(std::max<uint64_t>(nk, 1), per), 0);
+    parallel_for(max_of.size(), [&](size_t it) {
+        const uint64_t k0 = it * per, k1 = std::min<uint64_t>(nk, k0 + per);
+        uint64_t mx = 0;
+        for (uint64_t i = k0; i < k1; i++) {
+            const uint8_t *q = &buf[key_at[i]];
+            uint64_t h0, h1;
+            memcpy(&h0, q, 8); memcpy(&h1, q + 8, 8);
+            q += 24;
+            FragTuple *t = tuples.get() + sig_before[i];
+            for (uint64_t j = sig_before[i]; j < sig_before[i + 1]; j++, t++, q += 17) {
+                t->h0 = h0; t->h1 = h1;
+                memcpy(&t->frg_id, q, 4); memcpy(&t->sid, q + 4, 4); memcpy(&t->bgn, q + 8, 4); memcpy(&t->end, q + 12, 4);
+                t->ori = q[16]; t->ord = 0;
+                mx = std::max<uint64_t>(mx, (uint64_t)t->frg_id + 1);
+            }
+        }
+        max_of[it] = mx;
+    });
+    uint64_t max_frg = 0;
+    for (uint64_t m : max_of) max_frg = std::max(max_frg, m);
     pgr_b200_index *idx = pgr_b200_index_new(&spec, 0, device);
     if (!idx) return nullptr;
-    if (index_reserve_tuples(idx, tuples.size()) != PGR_OK) { pgr_b200_index_free(idx); return nullptr; }
-    if (!tuples.empty() &&
-        cudaMemcpy(idx->tuples.p, tuples.data(), tuples.size() * sizeof(FragTuple), cudaMemcpyHostToDevice) != cudaSuccess) {
-        set_error("H2D failed"); pgr_b200_index_free(idx); return nullptr;
+    if (index_reserve_tuples(idx, n_sig) != PGR_OK) { pgr_b200_index_free(idx); return nullptr; }
+    if (n_sig) {
+        // through the page-locked ring (the tuple array is plain memory): PCIe rate instead of the driver's staging
+        pgr_b200_ctx *ctx = idx->ctx;
+        const size_t bytes = n_sig * sizeof(FragTuple);
+        int rc = PGR_OK;
+        if (bytes >= PACK_MIN_BYTES && (ctx->pack || (ctx->pack = pack_ring_acquire(ctx->device)))) {
+            rc = upload_raw_staged(ctx->pack, (uint8_t *)idx->tuples.p, (const uint8_t *)tuples.get(), bytes, ctx->stream);
+            if (rc == PGR_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = PGR_E_CUDA;
+        } else if (cudaMemcpy(idx->tuples.p, tuples.get(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = PGR_E_CUDA;
+        if (rc != PGR_OK) { set_error("H2D of the .mdb records failed"); pgr_b200_index_free(idx); return nullptr; }
     }
-    idx->n_tuples = tuples.size();
+    idx->n_tuples = n_sig;
     idx->n_frags = (uint32_t)std::min<uint64_t>(max_frg, 0xFFFFFFFFull);   // fragment ids in use (no prefix/suffix records in an .mdb)
     idx->from_mdb = true;
     if (pgr_b200_index_finalize(idx) != PGR_OK) { pgr_b200_index_free(idx); return nullptr; }
