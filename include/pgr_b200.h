@@ -99,19 +99,23 @@ void pgr_b200_host_free(void *p);
  * from it at PCIe rate without a staging copy; 0 on success.  Unregister before freeing it. */
 int pgr_b200_host_register(void *p, size_t bytes);
 int pgr_b200_host_unregister(void *p);
-/* Host half of the packed transport the batch calls use for large inputs (3 bits per base over PCIe instead of 8; the
- * device expands them again): bases -> three bit planes per 32-byte block, bit j = byte j; v = 1: a base with code p1:p0
- * in the reference's LUT order (shmmrutils.rs:426-436: A/a/0 -> 0, C/c/1 -> 1, G/g/2 -> 2, T/t/3 -> 3); v = 0, p0 = 0:
- * any other byte; v = 0, p0 = 1: padding of the last block.  Runs on the host (SIMD picked at run time, see
- * pgr_b200_pack_isa); exported so that it can be checked without a device.  Each plane holds (n_bytes + 31) / 32 words. */
-#define PGR_TRANSPORT_PACKED 0 /* default: large host inputs cross PCIe as bit planes (3 bits per base) */
+#define PGR_TRANSPORT_PACKED 0 /* default: large host inputs cross PCIe as bit planes (2-3 bits per base) */
 #define PGR_TRANSPORT_DIRECT 1 /* the caller's bytes are copied as they are (asynchronous only from page-locked memory) */
 int pgr_b200_set_transport(int mode); /* process-wide; returns the previous mode.  PGR_B200_H2D=direct sets the initial one */
 /* In PGR_TRANSPORT_PACKED mode a batch is still copied directly when it is small (< 4 MB) or when the host has few threads for
- * this process (< 10, e.g. 8 ranks on a 32-CPU node) and the source is page-locked: the direct copy is then the faster one.
- * Transport the newest batch call of this process took: PGR_TRANSPORT_PACKED / PGR_TRANSPORT_DIRECT, -1 before the first. */
+ * this process (< 10, e.g. 4 or 8 ranks on a 32-CPU node) and the source is page-locked: the direct copy is then the faster
+ * one.  Transport the newest batch call of this process took: PGR_TRANSPORT_PACKED / PGR_TRANSPORT_DIRECT, -1 before the first. */
 int pgr_b200_last_transport(void);
-void pgr_b200_pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v);
+/* bytes the packed / hybrid transport has put on PCIe in this process so far (bit planes of packed slots + plain bytes of the
+ * slots copied as they are); the difference around a call is what that call really moved host to device */
+uint64_t pgr_b200_transport_bytes(void);
+/* Host half of the packed transport the batch calls use for large inputs (2-3 bits per base over PCIe instead of 8; the
+ * device expands them again): bases -> three bit planes per 32-byte block, bit j = byte j; v = 1: a base with code p1:p0
+ * in the reference's LUT order (shmmrutils.rs:426-436: A/a/0 -> 0, C/c/1 -> 1, G/g/2 -> 2, T/t/3 -> 3; the padding of the last
+ * block counts as code 0); v = 0: any other byte.  Returns the AND of the validity words (all ones: every byte a base — the
+ * transport then leaves the validity plane at home).  Runs on the host (SIMD picked at run time, see pgr_b200_pack_isa);
+ * exported so that it can be checked without a device.  Each plane holds (n_bytes + 31) / 32 words. */
+uint32_t pgr_b200_pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v);
 const char *pgr_b200_pack_isa(void);
 int pgr_b200_pool_threads(void); /* host threads the library's host-side loops use (PGR_B200_HOST_THREADS overrides) */
 

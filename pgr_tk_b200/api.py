@@ -157,9 +157,10 @@ def lib():
         L.pgr_b200_mindex_gather.argtypes = [vp, C.c_int]
         L.pgr_b200_host_register.argtypes = [vp, sz]
         L.pgr_b200_host_unregister.argtypes = [vp]
-        L.pgr_b200_pack_bases.restype = None
+        L.pgr_b200_pack_bases.restype = C.c_uint32
         L.pgr_b200_pack_bases.argtypes = [vp, sz, vp, vp, vp]
         L.pgr_b200_pack_isa.restype = C.c_char_p
+        L.pgr_b200_transport_bytes.restype = C.c_uint64
         L.pgr_b200_index_counts.argtypes = [vp, P(sz), P(sz), P(u32)]
         L.pgr_b200_index_export_csr.argtypes = [vp, vp, vp, vp]
         L.pgr_b200_index_tuples_device.argtypes = [vp, P(vp), P(sz)]
@@ -245,7 +246,8 @@ def pack_bases(seq):
     a = np.frombuffer(_bytes(seq), dtype=np.uint8)
     nb = (len(a) + 31) // 32
     p0, p1, v = (np.zeros(max(nb, 1), dtype=np.uint32) for _ in range(3))
-    lib().pgr_b200_pack_bases(a.ctypes.data, len(a), p0.ctypes.data, p1.ctypes.data, v.ctypes.data)
+    all_valid = lib().pgr_b200_pack_bases(a.ctypes.data, len(a), p0.ctypes.data, p1.ctypes.data, v.ctypes.data)
+    pack_bases.last_all_valid = int(all_valid) & 0xFFFFFFFF   # AND of the validity words (all ones: bases only)
     return p0[:nb], p1[:nb], v[:nb]
 
 

@@ -155,10 +155,11 @@ int pgr_b200_host_register(void *p, size_t bytes) {
     PGR_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
     return PGR_OK;
 }
-void pgr_b200_pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) { pgr::pack_bases(src, n_bytes, p0, p1, v); }
+uint32_t pgr_b200_pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) { return pgr::pack_bases(src, n_bytes, p0, p1, v); }
 const char *pgr_b200_pack_isa(void) { return pgr::pack_isa(); }
 int pgr_b200_pool_threads(void) { return (int)pgr::pool_threads(); }
 int pgr_b200_last_transport(void) { return pgr::last_transport().load(); }
+uint64_t pgr_b200_transport_bytes(void) { return pgr::transport_bytes().load(); }
 int pgr_b200_set_transport(int mode) { return pgr::transport_mode().exchange(mode == PGR_TRANSPORT_DIRECT ? 1 : 0); }
 int pgr_b200_host_unregister(void *p) {
     if (!p) return PGR_OK;

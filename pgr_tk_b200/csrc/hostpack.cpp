@@ -32,22 +32,26 @@ inline void pack_block_scalar(const uint8_t *s, size_t n, uint32_t &p0, uint32_t
         }
         if (code < 4) { a |= (code & 1u) << j; b |= (code >> 1) << j; c |= 1u << j; }
     }
-    if (n < 32) a |= 0xFFFFFFFFu << n;   // padding marker: v = 0, p0 = 1
+    if (n < 32) c |= 0xFFFFFFFFu << n;   // padding behind the end of a sequence counts as valid (code 0): its bytes are never read as sequence
     p0 = a; p1 = b; v = c;
 }
 
-void pack_scalar(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) {
+// every packer returns the AND of the validity words it wrote (all ones = every byte a base)
+uint32_t pack_scalar(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) {
     size_t b = 0;
-    for (size_t i = 0; i < n_bytes; i += 32, b++) pack_block_scalar(src + i, std::min<size_t>(32, n_bytes - i), p0[b], p1[b], v[b]);
+    uint32_t all = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n_bytes; i += 32, b++) { pack_block_scalar(src + i, std::min<size_t>(32, n_bytes - i), p0[b], p1[b], v[b]); all &= v[b]; }
+    return all;
 }
 
 // code bit 0 = bit 1 of (c ^ (c >> 1)), code bit 1 = bit 2 of c for the eight letters; a letter is recognised by looking the
 // expected upper-case byte up by its low nibble (non-letters map to 0x20, which (c & 0xDF) never equals)
-__attribute__((target("avx2"))) void pack_avx2(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) {
+__attribute__((target("avx2"))) uint32_t pack_avx2(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) {
     const __m256i lut = _mm256_setr_epi8(0x20, 0x41, 0x20, 0x43, 0x54, 0x20, 0x20, 0x47, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20,
                                          0x20, 0x41, 0x20, 0x43, 0x54, 0x20, 0x20, 0x47, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20);
     const __m256i m_case = _mm256_set1_epi8((char)0xDF), m_nib = _mm256_set1_epi8(0x0F), m_fc = _mm256_set1_epi8((char)0xFC), zero = _mm256_setzero_si256();
     const size_t nb = n_bytes / 32;
+    uint32_t all = 0xFFFFFFFFu;
     for (size_t b = 0; b < nb; b++) {
         const __m256i c = _mm256_loadu_si256((const __m256i *)(src + 32 * b));
         const __m256i t = _mm256_xor_si256(c, _mm256_srli_epi16(c, 1));
@@ -62,15 +66,18 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *src, size_t n_byte
             ok |= raw;
         }
         p0[b] = a & ok; p1[b] = d & ok; v[b] = ok;
+        all &= ok;
     }
-    if (n_bytes % 32) pack_block_scalar(src + 32 * nb, n_bytes % 32, p0[nb], p1[nb], v[nb]);
+    if (n_bytes % 32) { pack_block_scalar(src + 32 * nb, n_bytes % 32, p0[nb], p1[nb], v[nb]); all &= v[nb]; }
+    return all;
 }
 
-__attribute__((target("avx512f,avx512bw"))) void pack_avx512(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) {
+__attribute__((target("avx512f,avx512bw"))) uint32_t pack_avx512(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) {
     const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0x20, 0x41, 0x20, 0x43, 0x54, 0x20, 0x20, 0x47, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20, 0x20));
     const __m512i m_case = _mm512_set1_epi8((char)0xDF), m_nib = _mm512_set1_epi8(0x0F), m_fc = _mm512_set1_epi8((char)0xFC);
     const __m512i b1 = _mm512_set1_epi8(1), b2 = _mm512_set1_epi8(2), b4 = _mm512_set1_epi8(4);
     const size_t n64 = n_bytes / 64;
+    uint64_t all = ~0ull;
     for (size_t q = 0; q < n64; q++) {
         _mm_prefetch((const char *)(src + 64 * q + 2048), _MM_HINT_NTA);
         const __m512i c = _mm512_loadu_si512((const void *)(src + 64 * q));
@@ -89,12 +96,15 @@ __attribute__((target("avx512f,avx512bw"))) void pack_avx512(const uint8_t *src,
         p0[2 * q] = (uint32_t)a; p0[2 * q + 1] = (uint32_t)(a >> 32);
         p1[2 * q] = (uint32_t)d; p1[2 * q + 1] = (uint32_t)(d >> 32);
         v[2 * q] = (uint32_t)ok; v[2 * q + 1] = (uint32_t)(ok >> 32);
+        all &= ok;
     }
+    uint32_t all32 = (uint32_t)all & (uint32_t)(all >> 32);
     const size_t done = 64 * n64;
-    if (done < n_bytes) pack_avx2(src + done, n_bytes - done, p0 + 2 * n64, p1 + 2 * n64, v + 2 * n64);
+    if (done < n_bytes) all32 &= pack_avx2(src + done, n_bytes - done, p0 + 2 * n64, p1 + 2 * n64, v + 2 * n64);
+    return all32;
 }
 
-using PackFn = void (*)(const uint8_t *, size_t, uint32_t *, uint32_t *, uint32_t *);
+using PackFn = uint32_t (*)(const uint8_t *, size_t, uint32_t *, uint32_t *, uint32_t *);
 struct Isa { PackFn fn; const char *name; };
 Isa pick_isa() {
     const char *force = getenv("PGR_B200_PACK_ISA");   // test aid: "scalar" / "avx2"
@@ -186,7 +196,7 @@ Pool &pool() { static Pool p; return p; }
 
 }  // namespace
 
-void pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) { isa().fn(src, n_bytes, p0, p1, v); }
+uint32_t pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v) { return isa().fn(src, n_bytes, p0, p1, v); }
 const char *pack_isa() { return isa().name; }
 void parallel_for(size_t n, const std::function<void(size_t)> &fn) { pool().run(n, fn); }
 unsigned pool_threads() { return pool().n_threads; }

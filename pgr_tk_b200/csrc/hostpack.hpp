@@ -10,11 +10,12 @@
 namespace pgr {
 
 // Planes of block b (32 consecutive bytes of the store), bit j = byte j of the block:
-//   v = 1           : a base, code = p1:p0 (A 0, C 1, G 2, T 3)
-//   v = 0, p0 = 0   : a byte the reference maps to no base (written back as 'N')
-//   v = 0, p0 = 1   : padding behind the end of a sequence (written back as 0, what the direct copy leaves there)
-// Packs n_bytes bytes starting at src (the beginning of a block); the last block is padded when n_bytes % 32 != 0.
-void pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v);
+//   v = 1 : a base, code = p1:p0 (A 0, C 1, G 2, T 3); the padding behind the end of a sequence in its last block counts as
+//           code 0 (those bytes are never read as sequence)
+//   v = 0 : a byte the reference maps to no base (written back as 'N'); p0 = p1 = 0
+// Packs n_bytes bytes starting at src (the beginning of a block); returns the AND of the validity words written (all ones:
+// every byte was a base, and the validity plane need not cross PCIe).
+uint32_t pack_bases(const uint8_t *src, size_t n_bytes, uint32_t *p0, uint32_t *p1, uint32_t *v);
 const char *pack_isa();   // "avx512bw", "avx2" or "scalar": what pack_bases runs on this machine
 
 // persistent worker pool shared by the library's host-side loops; fn(i) for i in [0, n), the caller takes part

@@ -4,8 +4,9 @@
 // point (pgr_b200_shmmrs_batch: 5 GB at ~50 GB/s = 100 ms around 26 ms of kernels).  sequence_to_shmmrs only reads the
 // class of a byte (shmmrutils.rs:426-436: A/a/0, C/c/1, G/g/2, T/t/3, anything else), i.e. 2 bits + 1 validity bit per base.
 // The host packs those three bit planes with SIMD on all its cores (hostpack.cpp) straight out of the caller's buffers
-// — pageable or page-locked alike — into a small ring of page-locked slots; each slot crosses PCIe as 12 bytes per 32 bases
-// and unpack_kernel rewrites it as canonical ASCII ("ACGT", 'N', 0 for padding) at its place in the device sequence store,
+// — pageable or page-locked alike — into a small ring of page-locked slots; a slot crosses PCIe as 8 bytes per 32 bases when
+// every byte of it is a base (the validity plane stays at home) and as 12 otherwise, and unpack_kernel rewrites it as
+// canonical ASCII ("ACGT", 'N') at its place in the device sequence store,
 // so every kernel downstream is unchanged and sees a store that is equivalent for the reference's LUT.
 //   PGR_B200_H2D=direct or pgr_b200_set_transport(PGR_TRANSPORT_DIRECT) disables the packed transport (A/B:
 //   profiles/r2_e2e_packed_ab.txt)
@@ -29,10 +30,11 @@ constexpr int PACK_SLOTS = 4;
 constexpr uint64_t PACK_MIN_BYTES = 4ull << 20;   // smaller uploads go the direct way
 
 // one thread per block: three plane words -> 32 bytes (two 16-byte stores)
-__global__ void __launch_bounds__(256) unpack_kernel(const uint32_t *__restrict__ planes, uint32_t nb, uint8_t *__restrict__ dst) {
+// has_v = 0: the slot holds bases only and its validity plane stayed on the host (2 bits per base crossed PCIe)
+__global__ void __launch_bounds__(256) unpack_kernel(const uint32_t *__restrict__ planes, uint32_t nb, uint8_t *__restrict__ dst, uint32_t has_v) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    const uint32_t p0 = planes[b], p1 = planes[nb + b], v = planes[2 * nb + b];
+    const uint32_t p0 = planes[b], p1 = planes[nb + b], v = has_v ? planes[2 * nb + b] : 0xFFFFFFFFu;
     uint32_t w[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -43,13 +45,13 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint32_t *__restrict_
         for (int i = 0; i < 4; i++) sel |= ((((a >> i) & 1u) | (((c >> i) & 1u) << 1))) << (4 * i);
         w[j] = __byte_perm(0x54474341u, 0u, sel);
     }
-    if (v != 0xFFFFFFFFu) {   // rare: invalid bytes ('N') and padding (0)
+    if (v != 0xFFFFFFFFu) {   // rare: bytes that are no bases -> 'N'
 #pragma unroll
         for (int j = 0; j < 8; j++) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int bit = 4 * j + i;
-                if (!((v >> bit) & 1u)) w[j] = (w[j] & ~(0xFFu << (8 * i))) | ((((p0 >> bit) & 1u) ? 0u : (uint32_t)'N') << (8 * i));
+                if (!((v >> bit) & 1u)) w[j] = (w[j] & ~(0xFFu << (8 * i))) | ((uint32_t)'N' << (8 * i));
             }
         }
     }
@@ -76,7 +78,7 @@ struct PackRing {
     std::deque<Queued> queued;
     int track_next = 0;
     float pack_ms = 0.45f;          // running estimate of the host time to pack one full slot
-    uint64_t n_direct_slots = 0, n_packed_slots = 0;
+    uint64_t n_direct_slots = 0, n_packed_slots = 0, bytes_sent = 0;   // since the ring was made (diagnostics)
     static constexpr size_t slot_words() { return 3ull * PACK_SLOT_BLOCKS; }
 };
 constexpr float PCIE_GB_PER_MS = 0.050f;   // ~50 GB/s: only used to size the backlog estimate
@@ -149,6 +151,7 @@ inline bool source_page_locked(const uint8_t *const *seqs, const size_t *lens, s
 // Whole-job Gbases/s of the e2e leg, hybrid against direct, by ranks x pool threads: 1 x 16: 95-99 / 48-49; 2 x 12: 112 / 96;
 // 4 x 8: 148 / 175; 8 x 4: 153 / 169 (packed only: 93) — so below PACK_MIN_THREADS a page-locked source is copied directly.
 constexpr unsigned PACK_MIN_THREADS = 10;
+inline std::atomic<uint64_t> &transport_bytes() { static std::atomic<uint64_t> b{0}; return b; }   // bytes the packed / hybrid transport put on PCIe (process-wide)
 inline std::atomic<int> &last_transport() { static std::atomic<int> t{-1}; return t; }   // what the newest batch call took (0 packed, 1 direct)
 inline bool choose_packed(const uint8_t *const *seqs, const size_t *lens, size_t n, uint64_t total_bases) {
     if (!packed_upload_enabled() || total_bases < PACK_MIN_BYTES) return false;
@@ -214,6 +217,8 @@ inline int upload_packed(PackRing *ring, uint8_t *store, const std::vector<uint6
                 }
                 PGR_TRY(track((float)bytes * 1e-9f / PCIE_GB_PER_MS));
                 ring->n_direct_slots++;
+                ring->bytes_sent += bytes;
+                transport_bytes().fetch_add(bytes, std::memory_order_relaxed);
                 continue;
             }
         }
@@ -223,7 +228,9 @@ inline int upload_packed(PackRing *ring, uint8_t *store, const std::vector<uint6
         uint32_t *hp = ring->h + (size_t)s * PackRing::slot_words();
         uint32_t *p0 = hp, *p1 = hp + nb, *pv = hp + 2 * (size_t)nb;
         const size_t n_pieces = (nb + PACK_PIECE_BLOCKS - 1) / PACK_PIECE_BLOCKS;
+        std::atomic<uint32_t> all_valid{0xFFFFFFFFu};
         parallel_for(n_pieces, [&](size_t pc) {
+            uint32_t allv = 0xFFFFFFFFu;
             uint64_t b = sb + pc * PACK_PIECE_BLOCKS;
             const uint64_t be = std::min<uint64_t>(sb + nb, b + PACK_PIECE_BLOCKS);
             // sequence that holds block b: the last one of [i0, i1) whose offset is <= 32 b (empty sequences share the offset
@@ -234,11 +241,15 @@ inline int upload_packed(PackRing *ring, uint8_t *store, const std::vector<uint6
                 const uint64_t len = h_len[i];
                 if (within >= len) { i++; continue; }   // (only for empty sequences)
                 const uint64_t take = std::min<uint64_t>(len - within, (be - b) << 5);
-                pack_bases(seqs[i] + within, take, p0 + (b - sb), p1 + (b - sb), pv + (b - sb));
+                allv &= pack_bases(seqs[i] + within, take, p0 + (b - sb), p1 + (b - sb), pv + (b - sb));
                 b += (take + 31) >> 5;
                 if (within + take >= len) i++;
             }
+            if (allv != 0xFFFFFFFFu) all_valid.fetch_and(allv, std::memory_order_relaxed);
         });
+        // a slot of bases only (the common case: gaps are few) leaves its validity plane at home: planes are laid out p0 | p1 | v
+        const bool has_v = all_valid.load() != 0xFFFFFFFFu;
+        const size_t slot_bytes = (size_t)nb * (has_v ? 12 : 8);
         if (nb == PACK_SLOT_BLOCKS) {
             const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_pack0).count();
             ring->pack_ms = 0.75f * ring->pack_ms + 0.25f * std::min(ms, 8.0f);
@@ -246,11 +257,13 @@ inline int upload_packed(PackRing *ring, uint8_t *store, const std::vector<uint6
         ring->n_packed_slots++;
         uint32_t *dp = ring->d + (size_t)s * PackRing::slot_words();
         if (ring->used[s]) PGR_CUDA(cudaStreamWaitEvent(st_copy, ring->unpack_done[s], 0));   // the device slot has been expanded
-        PGR_CUDA(cudaMemcpyAsync(dp, hp, (size_t)nb * 12, cudaMemcpyHostToDevice, st_copy));
+        PGR_CUDA(cudaMemcpyAsync(dp, hp, slot_bytes, cudaMemcpyHostToDevice, st_copy));
         PGR_CUDA(cudaEventRecord(ring->h2d_done[s], st_copy));
-        PGR_TRY(track((float)nb * 12e-9f / PCIE_GB_PER_MS));
+        PGR_TRY(track((float)slot_bytes * 1e-9f / PCIE_GB_PER_MS));
+        ring->bytes_sent += slot_bytes;
+        transport_bytes().fetch_add(slot_bytes, std::memory_order_relaxed);
         PGR_CUDA(cudaStreamWaitEvent(ring->unpack_stream, ring->h2d_done[s], 0));
-        unpack_kernel<<<(nb + 255) / 256, 256, 0, ring->unpack_stream>>>(dp, nb, store + (sb << 5));
+        unpack_kernel<<<(nb + 255) / 256, 256, 0, ring->unpack_stream>>>(dp, nb, store + (sb << 5), has_v ? 1u : 0u);
         PGR_CUDA(cudaGetLastError());
         PGR_CUDA(cudaEventRecord(ring->unpack_done[s], ring->unpack_stream));
         ring->used[s] = true;

@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def planes_expected(a):
-    """(p0, p1, v) per 32-byte block from the LUT: bytes 0..3 and ACGTacgt are bases, anything else is not; padding of the
-    last block is marked v = 0, p0 = 1"""
+    """(p0, p1, v) per 32-byte block from the LUT: bytes 0..3 and ACGTacgt are bases, anything else is not; the padding of the
+    last block counts as a base with code 0"""
     lut = np.full(256, 4, dtype=np.uint8)
     for ch, c in ((b"A", 0), (b"C", 1), (b"G", 2), (b"T", 3)):
         lut[ch[0]] = c
@@ -23,14 +23,14 @@ def planes_expected(a):
     lut[:4] = np.arange(4)
     code = lut[a]
     nb = (len(a) + 31) // 32
-    full = np.full(nb * 32, 5, dtype=np.uint8)   # 5 = padding
+    full = np.full(nb * 32, 0, dtype=np.uint8)   # padding = code 0
     full[:len(a)] = code
     full = full.reshape(nb, 32)
     sh = np.arange(32, dtype=np.uint64)
     def plane(mask):
         return (mask.astype(np.uint64) << sh).sum(axis=1).astype(np.uint32)
     ok = full < 4
-    return plane(((full & 1) == 1) & ok | (full == 5)), plane(((full >> 1) & 1 == 1) & ok), plane(ok)
+    return plane(((full & 1) == 1) & ok), plane(((full >> 1) & 1 == 1) & ok), plane(ok)
 
 
 def check_all(rng):
@@ -48,6 +48,9 @@ def check_all(rng):
             exp = planes_expected(a)
             for g, e, name in zip(got, exp, ("p0", "p1", "v")):
                 assert np.array_equal(g, e), (pg.pack_isa(), name, len(a), shift)
+            # the return value: AND of the validity words (what lets a slot leave its validity plane at home)
+            exp_all = int(np.bitwise_and.reduce(exp[2])) if len(exp[2]) else 0xFFFFFFFF
+            assert pg.pack_bases.last_all_valid == exp_all, (pg.pack_isa(), len(a), shift)
 
 
 def test_pack_bases_matches_the_lut():
