@@ -80,8 +80,10 @@ def run(pg, torch, dist, rank, world, local_rank, comm, reps=3, n_hap=N_HAP, hap
         idx = pg.ShmmrIndex(spec, pg.FRG_ID_FASTX, local_rank)
         return idx, idx.build_sharded_ptrs(comm, my_sids, my_ptrs, my_lens)
 
+    tb0 = pg.lib().pgr_b200_transport_bytes()
     e2e_ts, (idx_e2e, info_e2e) = timed(build_host)
     took_packed = pg.lib().pgr_b200_last_transport() == pg.TRANSPORT_PACKED
+    pcie_bytes_rank0 = (pg.lib().pgr_b200_transport_bytes() - tb0) // (1 + reps)   # this rank, per build (counted by the library)
 
     # ---- resident: the block already in HBM --------------------------------------------------------------------------
     offs_dev, off = [], SLACK
@@ -170,8 +172,8 @@ def run(pg, torch, dist, rank, world, local_rank, comm, reps=3, n_hap=N_HAP, hap
     out = {
         "workload": "ShmmrFragMap build on %d synthetic haplotypes x %d bases (%.2f Gbases), w=80 k=56 r=4 min_span=64" % (n_hap, hap_len, bases_total / 1e9),
         "scaling": "strong", "n_gpus": world, "reps": reps, "warmup": 1,
-        "e2e": {"value": bases_total / e2e_s / 1e9, "unit": "Gbases/s", "ms": e2e_s * 1e3, "ms_reps": [round(t * 1e3, 3) for t in e2e_ts], "h2d_bytes": ((bases_total + 31) // 32) * 12 if took_packed else bases_total, "host_input_bytes": bases_total,
-                "transport": "packed (3 bit planes per 32-base block; pack_upload.cuh)" if took_packed else "direct copy (few host threads per rank)",
+        "e2e": {"value": bases_total / e2e_s / 1e9, "unit": "Gbases/s", "ms": e2e_s * 1e3, "ms_reps": [round(t * 1e3, 3) for t in e2e_ts], "h2d_bytes_rank0": int(pcie_bytes_rank0) if took_packed else bases_local, "host_input_bytes": bases_total,
+                "transport": "packed / hybrid (2-3 bit planes per 32-base block, plain slots in the gaps; pack_upload.cuh)" if took_packed else "direct copy (few host threads per rank)",
                 "api": "pgr_b200_index_build_sharded (host pinned sequences -> per-rank sorted CSR slice in HBM)"},
         "resident": {"value": bases_total / res_s / 1e9, "unit": "Gbases/s", "ms": res_s * 1e3, "ms_reps": [round(t * 1e3, 3) for t in res_ts],
                      "api": "pgr_b200_index_build_sharded_device (sequences in HBM -> per-rank sorted CSR slice)",
