@@ -359,7 +359,9 @@ __device__ __forceinline__ void chain_segment(const ChainParams &p, const HitRec
 // 8.3 ms.  A warp per segment with the records staged in shared memory and the look-back of every hit spread over the lanes
 // — ballots for span_set, warp arg-max for the best predecessor, rank sort for the heads, bit-exact — took 16.4 ms: a
 // look-back visits ~8 predecessors, so three quarters of the lanes idle and the kernel becomes issue bound; with lane 0 alone
-// doing the DP it took 60 ms.  Both were removed.)
+// doing the DP it took 60 ms.  Both were removed.  Round 2 also tried one thread per segment with the records of a CTA's 32
+// segments staged in shared memory by one coalesced pass (48 KB per CTA): the DRAM traffic falls, but only 128 threads fit per
+// SM and the DP is a chain of dependent instructions that lives on latency hiding: ~17 ms.  Removed as well.)
 __global__ void chain_kernel(const ChainParams p) {
     const uint64_t sgi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (sgi >= p.n_seg) return;
