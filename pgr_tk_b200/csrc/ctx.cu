@@ -544,8 +544,10 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     cf.bits = ctx->mark_bits.as<uint32_t>(); cf.word_lo = word_lo; cf.word_hi = word_hi;
     cf.s_off = ds_off; cf.s_len = ds_len; cf.s_sid = ds_sid; cf.n_seq = (uint32_t)n; cf.gap = gap;
     cf.out = nullptr; cf.cap = 0; cf.n_out = nullptr;
+    const int slot_find = ctx->timer.begin("patch_kernel_find_count", st);
     cluster_find_kernel<0><<<cf_grid, CF_NT, 0, st>>>(cf, ctx->block_sum.as<uint32_t>(), nullptr);
     block_scan_kernel<<<1, 1024, 0, st>>>(ctx->block_sum.as<uint32_t>(), ctx->block_prefix.as<uint64_t>(), cf_grid);
+    ctx->timer.end(slot_find, st);
     PATCH_CUDA(cudaGetLastError());
     uint64_t n_cl64 = 0;
     PATCH_CUDA(cudaMemcpyAsync(&n_cl64, ctx->block_prefix.as<uint64_t>() + cf_grid, 8, cudaMemcpyDeviceToHost, st));
@@ -554,7 +556,9 @@ int apply_patches(pgr_b200_ctx *ctx, const pgr_shmmr_spec &spec, uint32_t n_mark
     const uint32_t n_cl = (uint32_t)n_cl64;
     PATCH_TRY(d_clusters.ensure((size_t)std::max<uint32_t>(1, n_cl) * sizeof(Cluster)));
     cf.out = d_clusters.as<Cluster>(); cf.cap = n_cl;
-    cluster_find_kernel<1><<<cf_grid, CF_NT, 0, st>>>(cf, nullptr, ctx->block_prefix.as<uint64_t>());
+    { const int sl = ctx->timer.begin("patch_kernel_find_write", st);
+      cluster_find_kernel<1><<<cf_grid, CF_NT, 0, st>>>(cf, nullptr, ctx->block_prefix.as<uint64_t>());
+      ctx->timer.end(sl, st); }
     PATCH_CUDA(cudaGetLastError());
     trace_mark("patches: clusters found");
     std::vector<Cluster> cl(n_cl);

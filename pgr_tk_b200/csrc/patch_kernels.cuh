@@ -41,38 +41,45 @@ __device__ __forceinline__ bool bit_at(const uint32_t *bits, uint64_t g) { retur
 // Two launches (WRITE = 0: starts per CTA -> block_scan_kernel -> WRITE = 1: clusters in bitmap order, which is sequence
 // order for a store laid out by pgr_b200_ctx_upload): no atomics, no sort.
 constexpr int CF_NT = 256;
+// sequence (index into the offset-sorted table) that holds block g, found by walking forward from a cached one: the marks of a
+// thread's word nearly always belong to one sequence, and sequences are far longer than a word's 1024 bases
+struct SeqCursor { uint32_t lo = 0xFFFFFFFFu; uint64_t first = 0, next_first = 0; };
+__device__ __forceinline__ void seq_of_block(const ClusterFindParams &p, uint64_t g, SeqCursor &c) {
+    if (c.lo == 0xFFFFFFFFu) {
+        uint32_t lo = 0, hi = p.n_seq;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((p.s_off[mid] >> 5) <= g) lo = mid; else hi = mid; }
+        c.lo = lo;
+    } else {
+        while (c.lo + 1 < p.n_seq && (p.s_off[c.lo + 1] >> 5) <= g) c.lo++;
+    }
+    c.first = p.s_off[c.lo] >> 5;
+    c.next_first = c.lo + 1 < p.n_seq ? (p.s_off[c.lo + 1] >> 5) : ~0ull;
+}
 template <int WRITE>
 __global__ void __launch_bounds__(CF_NT) cluster_find_kernel(const ClusterFindParams p, uint32_t *cta_count, const uint64_t *cta_prefix) {
     __shared__ uint32_t wsum[CF_NT / 32];
     const uint64_t wi = p.word_lo + (uint64_t)blockIdx.x * CF_NT + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t word = wi < p.word_hi ? p.bits[wi] : 0u;
-    uint32_t starts = 0;                              // bit b: block wi*32+b starts a cluster
-    uint32_t sids[4]; uint64_t firsts[4];             // (a word rarely holds more than one start; up to 4 cached, rest recomputed)
-    uint32_t n_cached = 0;
+    const bool live = wi < p.word_hi;
+    const uint32_t word0 = live ? p.bits[wi] : 0u;
+    const uint32_t prev = (live && word0 && wi > 0) ? p.bits[wi - 1] : 0u;   // the gap (< 32 blocks) reaches at most one word back
+    uint32_t word = word0, starts = 0;                // starts bit b: block wi*32+b starts a cluster
+    SeqCursor cur;
     while (word) {
         const uint32_t b = __ffs(word) - 1;
         word &= word - 1;
         const uint64_t g = wi * 32 + b;
-        // cheap test first: any mark in the gap blocks before g at all (sequence boundary ignored)?
-        bool any = false;
-        for (uint64_t q = (g > p.gap ? g - p.gap : 0); q < g && !any; q++) any = bit_at(p.bits, q);
-        uint32_t lo = 0;
-        uint64_t first = 0;
-        if (any || WRITE) {
-            // sequence of block g: last sorted sequence with off/32 <= g
-            uint32_t hi = p.n_seq;
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((p.s_off[mid] >> 5) <= g) lo = mid; else hi = mid; }
-            first = p.s_off[lo] >> 5;
-            if (any) {
-                const uint64_t from = (g - first > p.gap) ? g - p.gap : first;
-                any = false;
-                for (uint64_t q = from; q < g && !any; q++) any = bit_at(p.bits, q);
-            }
+        // the 32 blocks before g, block g-1 in bit 31: marks among the last `gap` of them (inside the block's own sequence) mean
+        // that g continues a cluster
+        const uint32_t before = __funnelshift_r(prev, word0, b);
+        uint32_t win = before >> (32 - p.gap);
+        if (win) {
+            if (cur.lo == 0xFFFFFFFFu || g >= cur.next_first) seq_of_block(p, g, cur);
+            const uint64_t room = g - cur.first;      // blocks of the sequence before g
+            if (room < p.gap) win = room ? (before >> (32 - (uint32_t)room)) : 0u;
         }
-        if (any) continue;
+        if (win) continue;
         starts |= 1u << b;
-        if (WRITE && n_cached < 4) { sids[n_cached] = p.s_sid[lo]; firsts[n_cached] = first; n_cached++; }
     }
     const uint32_t cnt = __popc(starts);
     uint32_t incl = cnt;
@@ -83,20 +90,12 @@ __global__ void __launch_bounds__(CF_NT) cluster_find_kernel(const ClusterFindPa
     for (int i = 0; i < CF_NT / 32; i++) { if (i < warp) wbase += wsum[i]; total += wsum[i]; }
     if (!WRITE) { if (threadIdx.x == 0) cta_count[blockIdx.x] = total; return; }
     uint64_t dst = cta_prefix[blockIdx.x] + wbase + incl - cnt;
-    uint32_t j = 0;
     while (starts) {
         const uint32_t b = __ffs(starts) - 1;
         starts &= starts - 1;
         const uint64_t g = wi * 32 + b;
-        uint32_t sid; uint64_t first;
-        if (j < 4) { sid = sids[j]; first = firsts[j]; }
-        else {
-            uint32_t lo = 0, hi = p.n_seq;
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((p.s_off[mid] >> 5) <= g) lo = mid; else hi = mid; }
-            sid = p.s_sid[lo]; first = p.s_off[lo] >> 5;
-        }
-        j++;
-        if (dst < p.cap) { Cluster c; c.sid = sid; c.pos = (uint32_t)((g - first) << 5); p.out[dst] = c; }
+        if (cur.lo == 0xFFFFFFFFu || g >= cur.next_first || g < cur.first) { if (g < cur.first) cur.lo = 0xFFFFFFFFu; seq_of_block(p, g, cur); }
+        if (dst < p.cap) { Cluster c; c.sid = p.s_sid[cur.lo]; c.pos = (uint32_t)((g - cur.first) << 5); p.out[dst] = c; }
         dst++;
     }
 }
