@@ -247,10 +247,17 @@ __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClust
                 last_x = mx;
                 bool emitted = false, emitted_here = false;
                 if (mdist == (uint64_t)(w - 1)) {
+                    // one pass for the minimum, how often it occurs and where; the ring-order pass below only runs over a single
+                    // slot when the minimum is unique (the common case outside repeats)
                     uint64_t mn = ~0ull;
-                    for (uint32_t i = 0; i < r_len; i++) if (rx[i] < mn) mn = rx[i];
+                    uint32_t n_min = 0, slot_min = 0;
+                    for (uint32_t i = 0; i < r_len; i++) {
+                        const uint64_t x = rx[i];
+                        if (x < mn) { mn = x; n_min = 1; slot_min = i; } else if (x == mn) n_min++;
+                    }
                     uint32_t last_y = 0;
-                    for (uint32_t i = 0, sl = r_start; i < (uint32_t)w; i++, sl = (sl + 1 == (uint32_t)w) ? 0u : sl + 1) {
+                    const bool one = n_min == 1 && r_len == (uint32_t)w;
+                    for (uint32_t i = one ? (uint32_t)w - 1 : 0u, sl = one ? slot_min : r_start; i < (uint32_t)w; i++, sl = (sl + 1 == (uint32_t)w) ? 0u : sl + 1) {
                         if (rx[sl] == mn) {
                             if (pos >= T0) {
                                 if (n_add < wcap) { pgr_mm128 mm; mm.x = rx[sl]; mm.y = ((uint64_t)sid << 32) | ry[sl]; dst[n_add] = mm; }
