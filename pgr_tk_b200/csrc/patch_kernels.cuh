@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClust
                 }
                 if (pos < k) continue;
                 const bool rev = r0 < f0;
-                const uint64_t h = rev ? (u64hash(r0) ^ u64hash(r1 ^ HASH_XOR)) : (u64hash(f0) ^ u64hash(f1 ^ HASH_XOR));
+                const uint64_t h = u64hash_dev(rev ? r0 : f0) ^ u64hash_dev((rev ? r1 : f1) ^ HASH_XOR);   // one pair of hashes on the selected strand, no divergent branch
                 const uint64_t mx = (h << 8) | (uint64_t)k;
                 const uint32_t my = ((uint32_t)pos << 1) | (rev ? 1u : 0u);
                 rx[r_end] = mx; ry[r_end] = my;
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(RC_NT) cluster_replay_kernel(const ReplayClust
                     h0 = ((h0 >> 1) | ((rc & 1) << shift)) & mask; h1 = ((h1 >> 1) | ((rc >> 1) << shift)) & mask;
                     if (g0 == h0 && g1 == h1) continue;        // palindrome: not pushed
                     const bool rv = h0 < g0;
-                    const uint64_t hh = rv ? (u64hash(h0) ^ u64hash(h1 ^ HASH_XOR)) : (u64hash(g0) ^ u64hash(g1 ^ HASH_XOR));
+                    const uint64_t hh = u64hash_dev(rv ? h0 : g0) ^ u64hash_dev((rv ? h1 : g1) ^ HASH_XOR);
                     if (((hh << 8) | (uint64_t)k) <= thr) mine = (uint32_t)q;
                 }
             }

@@ -133,8 +133,8 @@ __device__ __forceinline__ void planes4v(uint32_t wd, uint32_t &p0, uint32_t &p1
 }
 
 __device__ __forceinline__ bool byte_is_acgt(uint32_t c) {
-    c &= 0xDFu;
-    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+    const uint32_t code = (((c ^ (c >> 1)) >> 1) & 1u) | ((c >> 1) & 2u);
+    return (c & 0xDFu) == ((0x54474341u >> (8u * code)) & 0xFFu);
 }
 
 __device__ __forceinline__ uint32_t min3u(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
@@ -817,15 +817,14 @@ struct ReplayParams {
     pgr_mm128 *dst;
 };
 
-__device__ __forceinline__ uint32_t base_code(uint32_t c) {  // LUT of shmmrutils.rs:426-436
-    if (c < 4) return c;
-    switch (c) {
-        case 'A': case 'a': return 0;
-        case 'C': case 'c': return 1;
-        case 'G': case 'g': return 2;
-        case 'T': case 't': return 3;
-        default: return 4;
-    }
+// LUT of shmmrutils.rs:426-436 without a branch (the sequential kernels call it once per base from lanes that hold different
+// bases: a switch diverges five ways): the code bits of a letter are bit 1 of c ^ (c >> 1) and bit 2 of c (A 0, C 1, G 2, T 3,
+// either case); the byte is that letter iff it equals the expected upper-case letter once the case bit is dropped; raw 0..3 are
+// codes themselves; anything else maps to 4.
+__device__ __forceinline__ uint32_t base_code(uint32_t c) {
+    const uint32_t code = (((c ^ (c >> 1)) >> 1) & 1u) | ((c >> 1) & 2u);
+    const uint32_t expect = (0x54474341u >> (8u * code)) & 0xFFu;   // 'A', 'C', 'G', 'T'
+    return c < 4u ? c : ((c & 0xDFu) == expect ? code : 4u);
 }
 
 template <int MODE>

@@ -104,7 +104,7 @@ __device__ __forceinline__ void sketch_walk_block(const uint8_t *sq, int64_t L, 
         if (f0 == r0 && f1 == r1) continue;
         if (pos < (int64_t)k) continue;
         const bool rev = r0 < f0;
-        const uint64_t h = rev ? (u64hash(r0) ^ u64hash(r1 ^ HASH_XOR)) : (u64hash(f0) ^ u64hash(f1 ^ HASH_XOR));
+        const uint64_t h = u64hash_dev(rev ? r0 : f0) ^ u64hash_dev((rev ? r1 : f1) ^ HASH_XOR);   // one pair of hashes on the selected strand, no divergent branch
         if (h < thr) emit(i, h, rev);
     }
 }
