@@ -3,7 +3,7 @@ measures it at N = 1, 2, 4, 8 GPUs: STRONG scaling — the 94 haplotypes are cut
 computes the shimmers and tuples of its block, ONE all-to-all (grouped ncclSend/ncclRecv inside libpgr_b200) moves every
 tuple to the owner of its key range, the owner sorts its range into a CSR slice (pgr_b200_index_build_sharded).
 
-Reported (max over ranks, CUDA-synchronised wall clock around the C-ABI call, barrier before):
+Reported (max over ranks, CUDA-synchronised wall clock around the C-ABI call, barrier before; `ms` = median of the repetitions):
   e2e       host (pinned) sequences -> per-rank sorted CSR slices in HBM (H2D of the bases inside)
   resident  sequences already in HBM -> the same
   stages    rank-0 CUDA-event times of stage / partition / exchange / sort, all-to-all bytes that crossed NVLink
@@ -95,9 +95,15 @@ def run(pg, torch, dist, rank, world, local_rank, comm, reps=3, n_hap=N_HAP, hap
         store[o:o + ln].copy_(torch.from_numpy(v), non_blocking=True)
     torch.cuda.synchronize()
 
+    phase_log = []
+
     def build_dev():
+        t0 = time.perf_counter()
         idx = pg.ShmmrIndex(spec, pg.FRG_ID_FASTX, local_rank)
-        return idx, idx.build_sharded_device(comm, store.data_ptr(), my_sids, offs_dev, my_lens)
+        t1 = time.perf_counter()
+        info = idx.build_sharded_device(comm, store.data_ptr(), my_sids, offs_dev, my_lens)
+        phase_log.append((round((t1 - t0) * 1e3, 3), round((time.perf_counter() - t1) * 1e3, 3)))
+        return idx, info
 
     res_ts, (idx_res, info_res) = timed(build_dev)
     del store
@@ -163,7 +169,9 @@ def run(pg, torch, dist, rank, world, local_rank, comm, reps=3, n_hap=N_HAP, hap
     owner.free()
     if rank != 0:
         return None
-    e2e_s, res_s = float(np.mean(e2e_ts)), float(np.mean(res_ts))
+    # the median of the repetitions (all of them are listed as ms_reps): a single slow repetition — a page-locked allocation or a
+    # driver hiccup on a shared box, seen once at 994 ms against 47 — would otherwise be the whole figure
+    e2e_s, res_s = float(np.median(e2e_ts)), float(np.median(res_ts))
     n_sigs = int(sum(ns_all))
     # algorithmic bytes of the build: 1 B/base + 16 B per shimmer (shimmer stage) + 16 B per shimmer read +
     # 2 x 33 B per tuple (write once, reorder once)
@@ -181,6 +189,7 @@ def run(pg, torch, dist, rank, world, local_rank, comm, reps=3, n_hap=N_HAP, hap
         "n_keys": int(sum(nk_all)), "n_sigs": n_sigs,
         "rank0_stages_ms_e2e": {k: info_e2e[k] for k in ("stage_ms", "partition_ms", "exchange_ms", "sort_ms")},
         "rank0_stages_ms_resident": {k: info_res[k] for k in ("stage_ms", "partition_ms", "exchange_ms", "sort_ms")},
+        "rank0_host_ms_resident": {"index_new": [p[0] for p in phase_log[1:]], "build_call": [p[1] for p in phase_log[1:]]},
         "all_to_all": {"transport": "grouped ncclSend/ncclRecv inside libpgr_b200" if world > 1 else "none (1 GPU)",
                        "rank0_bytes_sent": info_res["bytes_sent"], "rank0_bytes_recv": info_res["bytes_recv"],
                        "rank0_tuples_local": info_res["n_tuples_local"], "rank0_tuples_owned": info_res["n_tuples_owned"]},

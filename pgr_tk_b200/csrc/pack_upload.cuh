@@ -155,7 +155,8 @@ inline std::atomic<uint64_t> &transport_bytes() { static std::atomic<uint64_t> b
 inline std::atomic<int> &last_transport() { static std::atomic<int> t{-1}; return t; }   // what the newest batch call took (0 packed, 1 direct)
 inline bool choose_packed(const uint8_t *const *seqs, const size_t *lens, size_t n, uint64_t total_bases) {
     if (!packed_upload_enabled() || total_bases < PACK_MIN_BYTES) return false;
-    if (pool_threads() >= PACK_MIN_THREADS) return true;
+    static const unsigned min_threads = getenv("PGR_B200_PACK_MIN_THREADS") ? (unsigned)atoi(getenv("PGR_B200_PACK_MIN_THREADS")) : PACK_MIN_THREADS;   // tuning aid
+    if (pool_threads() >= min_threads) return true;
     return !source_page_locked(seqs, lens, n);
 }
 
