@@ -253,6 +253,17 @@ pgr_b200_index *pgr_b200_mindex_gather(pgr_b200_mindex *m, int device);
  * hits[hit_off[i] .. hit_off[i+1]).  Library-allocated outputs (pgr_b200_free). */
 int pgr_b200_raw_query(pgr_b200_index *idx, const uint8_t *seq, size_t len, pgr_query_pair **pairs, size_t *n_pairs, uint64_t **hit_off,
                        pgr_frag_sig **hits);
+/* The .mdb-resident variant: read_mdb_file_to_frag_locations (seq_db.rs:1409-1471) keeps only key -> (file offset, count) in
+ * memory and leaves the signatures in the memory-mapped file; raw_query_fragment_from_mmap_midx (seq_db.rs:1230-1269, caller
+ * ext.rs:285-342) computes the query's shimmers (on the device here), looks every pair up in that table and reads its signatures
+ * out of the map (get_fragment_signatures_from_mmap_file).  Same outputs as pgr_b200_raw_query; nothing of the index is loaded
+ * into HBM, so an .mdb larger than the device (or a one-off look-up) costs the header pass only. */
+typedef struct pgr_b200_mdb_map pgr_b200_mdb_map;
+pgr_b200_mdb_map *pgr_b200_mdb_map_open(const char *mdb_path);
+void pgr_b200_mdb_map_close(pgr_b200_mdb_map *m);
+int pgr_b200_mdb_map_info(const pgr_b200_mdb_map *m, pgr_shmmr_spec *spec, size_t *n_keys, size_t *n_sigs);
+int pgr_b200_raw_query_mmap(pgr_b200_mdb_map *m, const uint8_t *seq, size_t len, pgr_query_pair **pairs, size_t *n_pairs, uint64_t **hit_off,
+                            pgr_frag_sig **hits);
 /* replaces SeqIndexDB::query_fragment_to_hps (ext.rs:252-282 -> aln.rs:147-242) for a batch of queries (the reference
  * runs one rayon task per query, pgr-query.rs:135).  Canonical forms where the reference leaks hash-map order: targets
  * ascending by sid; equal-score chain heads by position in the q_bgn-sorted hit list. */

@@ -6,6 +6,6 @@ There is no CPU fallback: importing works anywhere (so that the CPU test-suite c
 call raises PgrError when libpgr_b200.so is missing or no B200 is visible.
 """
 from .api import (  # noqa: F401
-    FRG_ID_AGC, FRG_ID_FASTX, TUPLE, Comm, ShardedIndex, ShardStats, comm_unique_id, QueryParams, ShmmrIndex, sparse_aln, ADJ, ALNSEG, FRAGMENT, GNODE, DFSNODE, HITPAIR, MM128, QPAIR, SIG, Ctx, PgrError, ShmmrSpec, build_library, device_count, get_shmmrs_from_seqs,
+    FRG_ID_AGC, FRG_ID_FASTX, TUPLE, Comm, MdbMap, ShardedIndex, ShardStats, comm_unique_id, QueryParams, ShmmrIndex, sparse_aln, ADJ, ALNSEG, FRAGMENT, GNODE, DFSNODE, HITPAIR, MM128, QPAIR, SIG, Ctx, PgrError, ShmmrSpec, build_library, device_count, get_shmmrs_from_seqs,
     host_alloc, lib, library_path, pack_bases, pack_isa, set_transport, TRANSPORT_PACKED, TRANSPORT_DIRECT, sequence_to_shmmrs, set_default_device,
 )

@@ -573,6 +573,41 @@ class ShmmrIndex:
 COMM_ID_BYTES = 128
 
 
+class MdbMap:
+    """the .mdb-resident look-up of the reference (read_mdb_file_to_frag_locations + raw_query_fragment_from_mmap_midx,
+    seq_db.rs:1409-1471, :1230-1269): the key table in memory, the signatures left in the memory-mapped file"""
+
+    def __init__(self, path):
+        L = lib()
+        L.pgr_b200_mdb_map_open.restype = C.c_void_p
+        L.pgr_b200_mdb_map_open.argtypes = [C.c_char_p]
+        L.pgr_b200_mdb_map_close.argtypes = [C.c_void_p]
+        L.pgr_b200_mdb_map_info.argtypes = [C.c_void_p, C.POINTER(ShmmrSpec), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.pgr_b200_raw_query_mmap.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_void_p)]
+        self.h = L.pgr_b200_mdb_map_open(str(path).encode())
+        if not self.h:
+            raise PgrError(-5, L.pgr_b200_last_error().decode())
+
+    def info(self):
+        spec, nk, ns = ShmmrSpec(), C.c_size_t(), C.c_size_t()
+        _check(lib().pgr_b200_mdb_map_info(self.h, C.byref(spec), C.byref(nk), C.byref(ns)))
+        return spec, nk.value, ns.value
+
+    def raw_query(self, seq):
+        """-> (pairs QPAIR[n], hit_off[n+1], hits SIG[...]), as ShmmrIndex.raw_query"""
+        a = _bytes(seq)
+        pairs, n, off, hits = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_void_p()
+        _check(lib().pgr_b200_raw_query_mmap(self.h, a.ctypes.data, a.size, C.byref(pairs), C.byref(n), C.byref(off), C.byref(hits)))
+        offs = _take(off, n.value + 1, np.uint64)
+        return _take(pairs, n.value, QPAIR), offs, _take(hits, int(offs[-1]), SIG)
+
+    def close(self):
+        if self.h:
+            lib().pgr_b200_mdb_map_close(self.h)
+            self.h = None
+
+
 def comm_unique_id():
     """NCCL unique id (bytes) made by one rank; broadcast it to the others by any means and pass it to Comm()"""
     buf = (C.c_uint8 * COMM_ID_BYTES)()

@@ -4,6 +4,13 @@
 #include <cstring>
 
 #include "index.cuh"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <memory>
 #include "query_kernels.cuh"
 
 using namespace pgr;
@@ -118,6 +125,122 @@ int pgr_b200_raw_query(pgr_b200_index *idx, const uint8_t *seq, size_t len, pgr_
     PGR_CUDA(cudaStreamSynchronize(st));
     *pairs = host_dup(qp);
     *n_pairs = n_qp;
+    *hit_off = host_dup(off);
+    *hits = host_dup(hs);
+    return PGR_OK;
+}
+
+// ---- .mdb-resident look-ups (seq_db.rs:1230-1269, :1409-1471) ---------------------------------------------------------
+}  // extern "C"
+
+struct pgr_b200_mdb_map {
+    pgr_shmmr_spec spec;
+    int fd = -1;
+    const uint8_t *base = nullptr;    // the memory-mapped file
+    size_t bytes = 0;
+    // keys sorted ascending with the file position and length of their signature vectors (ShmmrIndexFileLocation)
+    std::vector<uint64_t> h0, h1, at;
+    std::vector<uint32_t> cnt;
+    size_t n_sigs = 0;
+};
+
+extern "C" {
+
+pgr_b200_mdb_map *pgr_b200_mdb_map_open(const char *path) {
+    if (!path) { set_error("path is NULL"); return nullptr; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { set_error("cannot open %s", path); return nullptr; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size < 31) { close(fd); set_error("%s is not an .mdb file", path); return nullptr; }
+    void *mp = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (mp == MAP_FAILED) { close(fd); set_error("mmap of %s failed", path); return nullptr; }
+    std::unique_ptr<pgr_b200_mdb_map> m(new pgr_b200_mdb_map());
+    m->fd = fd; m->base = (const uint8_t *)mp; m->bytes = (size_t)sb.st_size;
+    auto fail = [&](const char *why) -> pgr_b200_mdb_map * { set_error("%s: %s", path, why); munmap(mp, m->bytes); close(fd); return nullptr; };
+    const uint8_t *b = m->base;
+    if (memcmp(b, "mdb", 3) != 0) return fail("not an .mdb file");
+    size_t c = 3;
+    auto r32 = [&]() { uint32_t v; memcpy(&v, b + c, 4); c += 4; return v; };
+    m->spec.w = r32(); m->spec.k = r32(); m->spec.r = r32(); m->spec.min_span = r32(); m->spec.sketch = r32() & 1u;
+    uint64_t nk; memcpy(&nk, b + c, 8); c += 8;
+    if (nk > (m->bytes - c) / 24) return fail("truncated");
+    // header pass: the 24-byte key records only; the signatures are never touched here
+    std::vector<uint64_t> k0(nk), k1(nk), at(nk);
+    std::vector<uint32_t> cn(nk);
+    for (uint64_t i = 0; i < nk; i++) {
+        if (c + 24 > m->bytes) return fail("truncated");
+        uint64_t vl;
+        memcpy(&k0[i], b + c, 8); memcpy(&k1[i], b + c + 8, 8); memcpy(&vl, b + c + 16, 8);
+        c += 24;
+        if (vl > (m->bytes - c) / 17 || vl > 0xFFFFFFFFull) return fail("truncated");
+        at[i] = c; cn[i] = (uint32_t)vl;
+        c += 17 * vl;
+        m->n_sigs += vl;
+    }
+    // the file may list its keys in any order (the reference writes hash-map order): sort the table by key
+    std::vector<uint32_t> ord(nk);
+    for (uint64_t i = 0; i < nk; i++) ord[i] = (uint32_t)i;
+    bool sorted = true;
+    for (uint64_t i = 1; i < nk && sorted; i++) sorted = k0[i - 1] < k0[i] || (k0[i - 1] == k0[i] && k1[i - 1] < k1[i]);
+    if (!sorted) std::sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return k0[x] != k0[y] ? k0[x] < k0[y] : k1[x] < k1[y]; });
+    m->h0.resize(nk); m->h1.resize(nk); m->at.resize(nk); m->cnt.resize(nk);
+    for (uint64_t i = 0; i < nk; i++) { const uint32_t j = ord[i]; m->h0[i] = k0[j]; m->h1[i] = k1[j]; m->at[i] = at[j]; m->cnt[i] = cn[j]; }
+    return m.release();
+}
+
+void pgr_b200_mdb_map_close(pgr_b200_mdb_map *m) {
+    if (!m) return;
+    if (m->base) munmap((void *)m->base, m->bytes);
+    if (m->fd >= 0) close(m->fd);
+    delete m;
+}
+
+int pgr_b200_mdb_map_info(const pgr_b200_mdb_map *m, pgr_shmmr_spec *spec, size_t *n_keys, size_t *n_sigs) {
+    if (!m) { set_error("NULL argument"); return PGR_E_ARG; }
+    if (spec) *spec = m->spec;
+    if (n_keys) *n_keys = m->h0.size();
+    if (n_sigs) *n_sigs = m->n_sigs;
+    return PGR_OK;
+}
+
+// raw_query_fragment_from_mmap_midx: shimmers on the device, pairs with the strict '<' rule (seq_db.rs:1243-1253), table look-up,
+// signatures decoded from the 17-byte records of the map (:1473-1504)
+int pgr_b200_raw_query_mmap(pgr_b200_mdb_map *m, const uint8_t *seq, size_t len, pgr_query_pair **pairs, size_t *n_pairs, uint64_t **hit_off,
+                            pgr_frag_sig **hits) {
+    if (!m || !pairs || !n_pairs || !hit_off || !hits) { set_error("NULL argument"); return PGR_E_ARG; }
+    pgr_mm128 *mm = nullptr;
+    size_t n_mm = 0;
+    PGR_TRY(pgr_b200_sequence_to_shmmrs(0, seq, len, &m->spec, 0, &mm, &n_mm));
+    const size_t np = n_mm > 1 ? n_mm - 1 : 0;
+    std::vector<pgr_query_pair> qp(np);
+    std::vector<uint64_t> off(np + 1, 0);
+    std::vector<size_t> slot(np, (size_t)-1);
+    const size_t nk = m->h0.size();
+    for (size_t i = 0; i < np; i++) {
+        const uint64_t s0 = mm[i].x >> 8, s1 = mm[i + 1].x >> 8;
+        const bool fwd = s0 < s1;
+        pgr_query_pair &q = qp[i];
+        memset(&q, 0, sizeof q);
+        q.h0 = fwd ? s0 : s1; q.h1 = fwd ? s1 : s0; q.ori = fwd ? 0 : 1;
+        q.bgn = ((uint32_t)(mm[i].y & 0xFFFFFFFFu) >> 1) + 1;
+        q.end = ((uint32_t)(mm[i + 1].y & 0xFFFFFFFFu) >> 1) + 1;
+        size_t lo = 0, hi = nk;
+        while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (m->h0[mid] < q.h0 || (m->h0[mid] == q.h0 && m->h1[mid] < q.h1)) lo = mid + 1; else hi = mid; }
+        if (lo < nk && m->h0[lo] == q.h0 && m->h1[lo] == q.h1) { slot[i] = lo; off[i + 1] = off[i] + m->cnt[lo]; } else off[i + 1] = off[i];
+    }
+    pgr_b200_free(mm);
+    std::vector<pgr_frag_sig> hs(off[np]);
+    for (size_t i = 0; i < np; i++) {
+        if (slot[i] == (size_t)-1) continue;
+        const uint8_t *r = m->base + m->at[slot[i]];
+        pgr_frag_sig *o = hs.data() + off[i];
+        for (uint32_t j = 0; j < m->cnt[slot[i]]; j++, r += 17, o++) {
+            memset(o, 0, sizeof *o);
+            memcpy(&o->frg_id, r, 4); memcpy(&o->sid, r + 4, 4); memcpy(&o->bgn, r + 8, 4); memcpy(&o->end, r + 12, 4); o->ori = r[16];
+        }
+    }
+    *pairs = host_dup(qp);
+    *n_pairs = np;
     *hit_off = host_dup(off);
     *hits = host_dup(hs);
     return PGR_OK;

@@ -200,3 +200,46 @@ def test_query_long_and_tiny_queries_mixed():
     queries = [haps[2][:150000], b"A", haps[1][1000:1400], revcomp(haps[4][50000:190000]), b"N" * 3000, haps[0][100:3000]]
     n = assert_query_equal(g, o, queries, 0.025, max_count=128, max_count_query=128, max_count_target=128, max_aln_span=8)
     assert n >= 3
+
+
+def test_mdb_resident_raw_query_equals_the_loaded_index(tmp_path):
+    """raw_query_fragment_from_mmap_midx (seq_db.rs:1230-1269): the key table in memory, signatures read out of the memory-mapped
+    .mdb — same pairs, offsets and signatures as the index loaded into HBM and as the oracle; also on the reference's own fixture
+    .mdb, whose keys are in hash-map order"""
+    rng = np.random.default_rng(23)
+    haps = pangenome(rng, 5, 90000)
+    g, o = build_pair(haps)
+    path = str(tmp_path / "t.mdb")
+    g.write_mdb(path)
+    m = pg.MdbMap(path)
+    spec, nk, ns = m.info()
+    assert (spec.w, spec.k, spec.r, spec.min_span) == (80, 56, 4, 64) and (nk, ns) == g.counts()[:2]
+    for qi in range(3):
+        a = int(rng.integers(0, 50000))
+        q = mutate(rng, haps[qi][a:a + 25000], 0.002)
+        if qi == 1:
+            q = revcomp(q)
+        mp, moff, mh = m.raw_query(q)
+        gp, goff, gh = g.raw_query(q)
+        op, ooff, oh = o.raw_query(q)
+        for other_p, other_off, other_h in ((gp, goff, gh), (op, ooff, oh)):
+            assert fields_equal(mp, other_p, ["h0", "h1", "bgn", "end", "ori"])
+            assert np.array_equal(moff, other_off)
+            assert fields_equal(mh, other_h, ["frg_id", "sid", "bgn", "end", "ori"])
+        assert len(mh) > 0
+    m.close()
+    # the reference's fixture: keys in the file's (hash-map) order, per-key vectors in file order
+    import os
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    fm = pg.MdbMap(os.path.join(golden, "test_seqs_frag.mdb"))
+    fi = pg.ShmmrIndex.read_mdb(os.path.join(golden, "test_seqs_frag.mdb"))
+    recs = orc.parse_fasta(os.path.join(golden, "test_seqs.fa"))
+    for _, s in recs[:5]:
+        mp, moff, mh = fm.raw_query(s)
+        ip, ioff, ih = fi.raw_query(s)
+        assert fields_equal(mp, ip, ["h0", "h1", "bgn", "end", "ori"]) and np.array_equal(moff, ioff)
+        assert fields_equal(mh, ih, ["frg_id", "sid", "bgn", "end", "ori"])
+    fm.close()
+    fi.close()
+    with pytest.raises(pg.PgrError):
+        pg.MdbMap(str(tmp_path / "missing.mdb"))
