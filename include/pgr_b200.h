@@ -264,6 +264,12 @@ void pgr_b200_mdb_map_close(pgr_b200_mdb_map *m);
 int pgr_b200_mdb_map_info(const pgr_b200_mdb_map *m, pgr_shmmr_spec *spec, size_t *n_keys, size_t *n_sigs);
 int pgr_b200_raw_query_mmap(pgr_b200_mdb_map *m, const uint8_t *seq, size_t len, pgr_query_pair **pairs, size_t *n_pairs, uint64_t **hit_off,
                             pgr_frag_sig **hits);
+/* query_fragment_to_hps_from_mmap_file (ext.rs:285-342 -> seq_db.rs:1230-1269 + aln.rs) for a batch of queries: the signature
+ * vectors of the keys the queries hit are read out of the map into a temporary device index on `device`, which then answers
+ * the batch exactly as pgr_b200_query_batch does on the whole index (the filters and the chaining only ever see those keys).
+ * Device memory and transfer are proportional to the hits, not to the .mdb. */
+int pgr_b200_query_batch_mmap(pgr_b200_mdb_map *m, int device, size_t n_queries, const uint8_t *const *seqs, const size_t *lens,
+                              const pgr_query_params *params, pgr_query_result **out);
 /* replaces SeqIndexDB::query_fragment_to_hps (ext.rs:252-282 -> aln.rs:147-242) for a batch of queries (the reference
  * runs one rayon task per query, pgr-query.rs:135).  Canonical forms where the reference leaks hash-map order: targets
  * ascending by sid; equal-score chain heads by position in the q_bgn-sorted hit list. */

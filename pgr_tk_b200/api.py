@@ -495,20 +495,7 @@ class ShmmrIndex:
         prm = QueryParams(penalty, opt(max_count), opt(max_count_query), opt(max_count_target), opt(max_aln_span), opt(max_gap), int(oriented))
         res = C.POINTER(QueryResult)()
         _check(lib().pgr_b200_query_batch(self.h, len(arrs), ptrs, lens, C.byref(prm), C.byref(res)))
-        r = res.contents
-
-        def arr(ptr, n, dt):
-            dt = np.dtype(dt)
-            if n == 0:
-                return np.zeros(0, dtype=dt)
-            addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
-            return np.frombuffer((C.c_char * (n * dt.itemsize)).from_address(addr), dtype=dt, count=n).copy()
-
-        out = (arr(r.q_target_off, r.n_queries + 1, np.uint64), arr(r.target_sid, r.n_targets, np.uint32),
-               arr(r.target_chain_off, r.n_targets + 1, np.uint64), arr(r.chain_score, r.n_chains, np.float32),
-               arr(r.chain_hit_off, r.n_chains + 1, np.uint64), arr(r.hits, r.n_hits, HITPAIR))
-        lib().pgr_b200_query_result_free(res)
-        return out
+        return _take_query_result(res)
 
     def query_fragment_to_hps(self, seq, penalty, **kw):
         """single-query form: (target_sid, target_chain_off, chain_score, chain_hit_off, hits)"""
@@ -573,6 +560,24 @@ class ShmmrIndex:
 COMM_ID_BYTES = 128
 
 
+def _take_query_result(res):
+    """pgr_query_result* -> (q_target_off, target_sid, target_chain_off, chain_score, chain_hit_off, hits HITPAIR[...]); frees it"""
+    r = res.contents
+
+    def arr(ptr, n, dt):
+        dt = np.dtype(dt)
+        if n == 0:
+            return np.zeros(0, dtype=dt)
+        addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
+        return np.frombuffer((C.c_char * (n * dt.itemsize)).from_address(addr), dtype=dt, count=n).copy()
+
+    out = (arr(r.q_target_off, r.n_queries + 1, np.uint64), arr(r.target_sid, r.n_targets, np.uint32),
+           arr(r.target_chain_off, r.n_targets + 1, np.uint64), arr(r.chain_score, r.n_chains, np.float32),
+           arr(r.chain_hit_off, r.n_chains + 1, np.uint64), arr(r.hits, r.n_hits, HITPAIR))
+    lib().pgr_b200_query_result_free(res)
+    return out
+
+
 class MdbMap:
     """the .mdb-resident look-up of the reference (read_mdb_file_to_frag_locations + raw_query_fragment_from_mmap_midx,
     seq_db.rs:1409-1471, :1230-1269): the key table in memory, the signatures left in the memory-mapped file"""
@@ -601,6 +606,18 @@ class MdbMap:
         _check(lib().pgr_b200_raw_query_mmap(self.h, a.ctypes.data, a.size, C.byref(pairs), C.byref(n), C.byref(off), C.byref(hits)))
         offs = _take(off, n.value + 1, np.uint64)
         return _take(pairs, n.value, QPAIR), offs, _take(hits, int(offs[-1]), SIG)
+
+    def query_batch(self, seqs, penalty, max_count=None, max_count_query=None, max_count_target=None, max_aln_span=None,
+                    max_gap=None, oriented=False, device=-1):
+        """query_fragment_to_hps_from_mmap_file (ext.rs:285-342) for every sequence of `seqs`; result as ShmmrIndex.query_batch"""
+        arrs, ptrs, lens = _seq_arrays(seqs)
+        opt = lambda v: -1 if v is None else int(v)
+        prm = QueryParams(penalty, opt(max_count), opt(max_count_query), opt(max_count_target), opt(max_aln_span), opt(max_gap), int(oriented))
+        res = C.POINTER(QueryResult)()
+        L = lib()
+        L.pgr_b200_query_batch_mmap.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(QueryParams), C.POINTER(C.POINTER(QueryResult))]
+        _check(L.pgr_b200_query_batch_mmap(self.h, device, len(arrs), ptrs, lens, C.byref(prm), C.byref(res)))
+        return _take_query_result(res)
 
     def close(self):
         if self.h:

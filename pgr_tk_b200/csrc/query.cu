@@ -246,6 +246,60 @@ int pgr_b200_raw_query_mmap(pgr_b200_mdb_map *m, const uint8_t *seq, size_t len,
     return PGR_OK;
 }
 
+// query_fragment_to_hps_from_mmap_file for a batch: sub-index of the hit keys, then the ordinary batch
+int pgr_b200_query_batch_mmap(pgr_b200_mdb_map *m, int device, size_t n_q, const uint8_t *const *seqs, const size_t *lens,
+                              const pgr_query_params *prm, pgr_query_result **out) {
+    if (!m || !prm || !out || (n_q && (!seqs || !lens))) { set_error("NULL argument"); return PGR_E_ARG; }
+    // 1. shimmers of every query (device), the distinct keys of their pairs (strict '<' rule as in the query path)
+    std::vector<uint32_t> rids(n_q);
+    for (size_t q = 0; q < n_q; q++) rids[q] = (uint32_t)q;
+    std::vector<size_t> offs(n_q + 1, 0);
+    pgr_mm128 *mm = nullptr;
+    PGR_TRY(pgr_b200_shmmrs_batch(n_q, rids.data(), seqs, lens, &m->spec, 0, &mm, offs.data()));   // on the calling thread's default device
+    std::vector<std::pair<uint64_t, uint64_t>> keys;
+    for (size_t q = 0; q < n_q; q++)
+        for (size_t i = offs[q]; i + 1 < offs[q + 1]; i++) {
+            const uint64_t s0 = mm[i].x >> 8, s1 = mm[i + 1].x >> 8;
+            keys.emplace_back(std::min(s0, s1), std::max(s0, s1));
+        }
+    pgr_b200_free(mm);
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    // 2. their signature vectors out of the map -> tuples (file order inside a key, as read_mdb keeps it)
+    const size_t nk = m->h0.size();
+    std::vector<FragTuple> tuples;
+    uint64_t max_frg = 0;
+    for (const auto &k : keys) {
+        size_t lo = 0, hi = nk;
+        while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (m->h0[mid] < k.first || (m->h0[mid] == k.first && m->h1[mid] < k.second)) lo = mid + 1; else hi = mid; }
+        if (lo >= nk || m->h0[lo] != k.first || m->h1[lo] != k.second) continue;
+        const uint8_t *r = m->base + m->at[lo];
+        for (uint32_t j = 0; j < m->cnt[lo]; j++, r += 17) {
+            FragTuple t;
+            t.h0 = k.first; t.h1 = k.second;
+            memcpy(&t.frg_id, r, 4); memcpy(&t.sid, r + 4, 4); memcpy(&t.bgn, r + 8, 4); memcpy(&t.end, r + 12, 4);
+            t.ori = r[16]; t.ord = 0;
+            max_frg = std::max<uint64_t>(max_frg, (uint64_t)t.frg_id + 1);
+            tuples.push_back(t);
+        }
+    }
+    // 3. temporary index of those keys, the ordinary batch on it
+    pgr_b200_index *idx = pgr_b200_index_new(&m->spec, 0, device);
+    if (!idx) return PGR_E_NO_DEVICE;
+    int rc = index_reserve_tuples(idx, std::max<size_t>(1, tuples.size()));
+    if (rc == PGR_OK && !tuples.empty() &&
+        cudaMemcpy(idx->tuples.p, tuples.data(), tuples.size() * sizeof(FragTuple), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D of the hit keys failed"); rc = PGR_E_CUDA; }
+    if (rc == PGR_OK) {
+        idx->n_tuples = tuples.size();
+        idx->n_frags = (uint32_t)std::min<uint64_t>(max_frg, 0xFFFFFFFFull);
+        idx->from_mdb = true;
+        rc = pgr_b200_index_finalize(idx);
+    }
+    if (rc == PGR_OK) rc = pgr_b200_query_batch(idx, n_q, seqs, lens, prm, out);
+    pgr_b200_index_free(idx);
+    return rc;
+}
+
 void pgr_b200_query_result_free(pgr_query_result *r) {
     if (!r) return;
     result_free(r->q_target_off); result_free(r->target_sid); result_free(r->target_chain_off); result_free(r->chain_score);

@@ -227,6 +227,13 @@ def test_mdb_resident_raw_query_equals_the_loaded_index(tmp_path):
             assert np.array_equal(moff, other_off)
             assert fields_equal(mh, other_h, ["frg_id", "sid", "bgn", "end", "ori"])
         assert len(mh) > 0
+    # the chaining entry point over the map (query_fragment_to_hps_from_mmap_file, ext.rs:285-342) == the batch on the loaded index
+    queries = [mutate(rng, haps[i % 5][5000 * i:5000 * i + 20000], 0.002) for i in range(6)] + [b"ACGT" * 50, b""]
+    for kw in (dict(max_count=128, max_count_query=128, max_count_target=128, max_aln_span=8), dict(max_aln_span=3, max_gap=5000, oriented=True), {}):
+        a = m.query_batch(queries, 0.025, **kw)
+        b = g.query_batch(queries, 0.025, **kw)
+        assert len(a) == len(b) and all(x.tobytes() == y.tobytes() for x, y in zip(a, b)), kw
+    assert len(a[1]) > 0
     m.close()
     # the reference's fixture: keys in the file's (hash-map) order, per-key vectors in file order
     import os
