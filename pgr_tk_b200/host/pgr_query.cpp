@@ -51,7 +51,7 @@ int main(int argc, char **argv) {
     uint32_t w = 80, k = 56, r = 4, min_span = 64;
     double gap_penalty = 0.025;
     long merge_range_tol = 100000, max_count = 128, max_query_count = 128, max_target_count = 128, max_aln_chain_span = 8;
-    bool fastx_file = false, frg_file = false, only_summary = false, bed_summary = false;
+    bool fastx_file = false, frg_file = false, only_summary = false, bed_summary = false, mdb_resident = false;
     std::vector<std::string> pos;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -70,6 +70,7 @@ int main(int argc, char **argv) {
         else if (a == "--fastx-file") fastx_file = true;
         else if (a == "--frg-file") frg_file = true;
         else if (a == "--only-summary") only_summary = true;
+        else if (a == "--mdb-resident") mdb_resident = true;   // addition: leave the .mdb on disk (memory-mapped), as the reference's agc / frg back ends do
         else if (a == "--bed-summary") bed_summary = true;
         else if (a == "-h" || a == "--help") { printf("usage: pgr-b200-query <pgr_db_prefix|fastx> <query_fastx> <output_prefix> [--fastx-file] [options of pgr-query]\n"); return 0; }
         else pos.push_back(a);
@@ -87,10 +88,10 @@ int main(int argc, char **argv) {
         rc = db.load_from_fastx(pos[0], w, k, r, min_span);
     } else if (frg_file) {
         fprintf(stderr, "the option `--frg_file` is specified, read the input file as a FRG backed index database files.\n");
-        rc = only_summary ? db.load_from_index_files(pos[0]) : db.load_from_frg_index(pos[0]);
+        rc = only_summary ? db.load_from_index_files(pos[0], mdb_resident) : db.load_from_frg_index(pos[0]);
     } else {
         if (!only_summary) { fprintf(stderr, "error: the AGC back end is out of scope: use --frg-file or --fastx-file, or add --only-summary\n"); return 2; }
-        rc = db.load_from_index_files(pos[0]);
+        rc = db.load_from_index_files(pos[0], mdb_resident);
     }
     if (rc != PGR_OK) { fprintf(stderr, "%s\n", db.error().c_str()); return 1; }
 

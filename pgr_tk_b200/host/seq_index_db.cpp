@@ -33,6 +33,7 @@ SeqIndexDB::~SeqIndexDB() { reset(); }
 void SeqIndexDB::reset() {
     if (idx_) { pgr_b200_index_free(idx_); idx_ = nullptr; }
     if (midx_) { pgr_b200_mindex_free(midx_); midx_ = nullptr; }
+    if (map_) { pgr_b200_mdb_map_close(map_); map_ = nullptr; }
     seqs_.clear();
     seq_data_.clear();
     file_bufs_.clear();
@@ -184,11 +185,17 @@ int SeqIndexDB::add_records(std::vector<SeqRec> &recs, const std::string &source
     return rc;
 }
 
-int SeqIndexDB::load_from_index_files(const std::string &prefix) {
+int SeqIndexDB::load_from_index_files(const std::string &prefix, bool mdb_resident) {
     reset();
-    idx_ = pgr_b200_index_read_mdb((prefix + ".mdb").c_str(), -1);
-    if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_IO; }
-    pgr_b200_index_get_spec(idx_, &spec_);
+    if (mdb_resident) {
+        map_ = pgr_b200_mdb_map_open((prefix + ".mdb").c_str());
+        if (!map_) { err_ = pgr_b200_last_error(); return PGR_E_IO; }
+        pgr_b200_mdb_map_info(map_, &spec_, nullptr, nullptr);
+    } else {
+        idx_ = pgr_b200_index_read_mdb((prefix + ".mdb").c_str(), -1);
+        if (!idx_) { err_ = pgr_b200_last_error(); return PGR_E_IO; }
+        pgr_b200_index_get_spec(idx_, &spec_);
+    }
     FILE *f = fopen((prefix + ".midx").c_str(), "rb");
     if (!f) { err_ = "cannot open " + prefix + ".midx"; return PGR_E_IO; }
     char *line = nullptr;
@@ -373,11 +380,12 @@ bool FragStore::get_seq_by_id(uint32_t sid, std::vector<uint8_t> &out, std::stri
 }
 
 int SeqIndexDB::query_fragment_to_hps(const std::vector<SeqRec> &queries, const pgr_query_params &params, pgr_query_result **out) {
-    if (!idx_) { err_ = "no index"; return PGR_E_ARG; }
+    if (!idx_ && !map_) { err_ = "no index"; return PGR_E_ARG; }
     std::vector<const uint8_t *> ptrs;
     std::vector<size_t> lens;
     for (auto &q : queries) { ptrs.push_back(q.seq.data()); lens.push_back(q.seq.size()); }
-    const int rc = pgr_b200_query_batch(idx_, queries.size(), ptrs.data(), lens.data(), &params, out);
+    const int rc = map_ ? pgr_b200_query_batch_mmap(map_, -1, queries.size(), ptrs.data(), lens.data(), &params, out)
+                        : pgr_b200_query_batch(idx_, queries.size(), ptrs.data(), lens.data(), &params, out);
     if (rc != PGR_OK) err_ = pgr_b200_last_error();
     return rc;
 }

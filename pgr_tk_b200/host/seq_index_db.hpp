@@ -72,7 +72,9 @@ public:
     int load_from_seq_list(const std::vector<SeqRec> &seq_list, const std::string &source, uint32_t w, uint32_t k, uint32_t r, uint32_t min_span);
     // index part of ext.rs:87-150 (load_from_agc_index / load_from_frg_index): <prefix>.mdb + <prefix>.midx; sequences are
     // not available afterwards (the .agc / .frg stores are out of scope)
-    int load_from_index_files(const std::string &prefix);
+    // mdb_resident = true: read_mdb_file_to_frag_locations (seq_db.rs:1409-1471, what ext.rs:87-150 does): only the key table of the
+    // .mdb is read, the file stays memory-mapped and queries go through pgr_b200_query_batch_mmap (ext.rs:285-342)
+    int load_from_index_files(const std::string &prefix, bool mdb_resident = false);
     // ext.rs:131-150 load_from_frg_index: the index files plus the .sdx/.frg sequence store
     int load_from_frg_index(const std::string &prefix);
     // keep the sequences of load_from_fastx in host memory (needed by get_sub_seq_by_id); set before loading
@@ -98,6 +100,7 @@ private:
     void reset();
     pgr_b200_index *idx_ = nullptr;
     pgr_b200_mindex *midx_ = nullptr;   // multi-GPU build in progress
+    pgr_b200_mdb_map *map_ = nullptr;   // the .mdb-resident back end (index left on disk)
     pgr_shmmr_spec spec_{};
     std::vector<CompactSeq> seqs_;
     std::vector<SeqSpan> seq_data_;                       // views of the sequences (FASTX back end) ...

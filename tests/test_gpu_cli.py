@@ -165,6 +165,11 @@ def test_query_cli_matches_oracle_postprocessing(tmp_path):
     for idx in range(len(queries)):
         assert open("%s.%03d.hit" % (prefix, idx)).read() == open("%s.%03d.hit" % (str(tmp_path / "out_100000"), idx)).read()
         assert not os.path.exists("%s.%03d.fa" % (prefix, idx))
+    # the same with the .mdb left on disk (read_mdb_file_to_frag_locations + query_fragment_to_hps_from_mmap_file, ext.rs:87-150,285-342)
+    prefix_m = str(tmp_path / "out_mmap")
+    subprocess.check_call([QCLI, str(tmp_path / "idx"), q_fa, prefix_m, "--only-summary", "--mdb-resident"], cwd=ROOT)
+    for idx in range(len(queries)):
+        assert open("%s.%03d.hit" % (prefix_m, idx)).read() == open("%s.%03d.hit" % (prefix, idx)).read()
 
 
 # ---- pgr-b200-pbundle-decomp (pgr-pbundle-decomp.rs) ----------------------------------------------------------------------
