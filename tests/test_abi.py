@@ -53,3 +53,16 @@ def test_spec_asserts_become_error_codes():
         with pytest.raises(pg.PgrError) as e:
             pg.sequence_to_shmmrs(0, b"ACGT" * 100, bad)
         assert e.value.code == -2
+
+
+def test_mdb_map_header_pass_needs_no_device():
+    """pgr_b200_mdb_map_open (read_mdb_file_to_frag_locations, seq_db.rs:1409-1471) is host code: the reference's fixture .mdb
+    gives its spec, 55 keys and 820 signatures; a file that is no .mdb is refused"""
+    golden = os.path.join(ROOT, "tests", "golden")
+    m = pg.MdbMap(os.path.join(golden, "test_seqs_frag.mdb"))
+    spec, nk, ns = m.info()
+    assert (spec.w, spec.k, spec.r, spec.min_span, spec.sketch) == (80, 56, 4, 64, 0)
+    assert (nk, ns) == (55, 820)
+    m.close()
+    with pytest.raises(pg.PgrError):
+        pg.MdbMap(os.path.join(golden, "test_seqs.fa"))
