@@ -393,11 +393,11 @@ def main():
 
         # default transport: bases packed to 3 bits on the host cores, expanded on the device (pack_upload.cuh)
         tb0 = pg.lib().pgr_b200_transport_bytes()
-        e_ms, d2h = time_e2e(args.steps, 2)
+        e_ms, d2h = time_e2e(args.steps, 3)
         took_packed = pg.lib().pgr_b200_last_transport() == pg.TRANSPORT_PACKED
         # what really crossed PCIe per step: bit planes of the packed slots (8 B per 32 bases when a slot holds bases only, 12
         # otherwise) + the plain bytes of the slots the hybrid feeding copied as they are; counted by the library
-        packed_bytes = (pg.lib().pgr_b200_transport_bytes() - tb0) // (args.steps + 2)
+        packed_bytes = (pg.lib().pgr_b200_transport_bytes() - tb0) // (args.steps + 3)
         e2e = {"value": world * bases / (e_ms * 1e-3) / 1e9, "unit": "Gbases/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": packed_bytes if took_packed else bases, "d2h_bytes_per_step": d2h, "host_input_bytes_per_step": bases,
                "transport": ("packed: %d host threads (%s) turn the caller's bytes into 3 bit planes per 32-base block, 12 B per 32 bases cross PCIe, "
