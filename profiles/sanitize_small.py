@@ -41,3 +41,9 @@ m = pg.ShardedIndex(pg.ShmmrSpec(48, 56, 4, 12), pg.FRG_ID_FASTX, devices=[0, 0,
 m.add_batch(list(range(5)), haps)
 print("sharded", [len(x) for x in m.export()])
 m.close()
+# .mdb-resident look-up and query (temporary device index of the hit keys), grouped query batch
+idx.write_mdb("/tmp/sanitize_small.mdb")
+mm_ = pg.MdbMap("/tmp/sanitize_small.mdb")
+print("mdb map", mm_.info()[1:], len(mm_.raw_query(haps[2][1000:21000])[2]), [len(x) for x in mm_.query_batch([haps[1][2000:22000], b"ACGT"], 0.025)])
+mm_.close()
+os.environ["PGR_B200_QUERY_GROUPS"] = "2"
