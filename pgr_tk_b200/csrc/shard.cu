@@ -47,6 +47,8 @@ struct Transport {
     // send + send_off[p] .. send_off[p+1] goes to rank p; recv + recv_off[p] .. recv_off[p+1] comes from rank p (bytes)
     virtual int all_to_all(const uint8_t *send, const uint64_t *send_off, uint8_t *recv, const uint64_t *recv_off, cudaStream_t st) = 0;
     virtual const char *name() const = 0;
+    // a shard of this process failed outside the transport: peers blocked in (or arriving at) a rendez-vous must not wait for it
+    virtual void abort() {}
 };
 
 struct NcclTransport : Transport {
@@ -83,13 +85,21 @@ struct LocalBus {
     std::vector<const uint8_t *> send;
     std::vector<const uint64_t *> send_off;
     std::vector<int> device;
-    void barrier() {
+    bool failed = false;              // set by abort(): a shard gave up, every barrier (current and later) returns false
+    bool barrier() {
         std::unique_lock<std::mutex> lk(mu);
+        if (failed) return false;
         const uint64_t g = generation;
         if (++waiting == n) { waiting = 0; generation++; cv.notify_all(); }
-        else cv.wait(lk, [&] { return generation != g; });
+        else cv.wait(lk, [&] { return generation != g || failed; });
+        return !failed;
+    }
+    void abort() {
+        { std::lock_guard<std::mutex> lk(mu); failed = true; }
+        cv.notify_all();
     }
 };
+#define PGR_BUS_BARRIER(bus) do { if (!(bus)->barrier()) { ::pgr::set_error("another shard of this process failed"); return PGR_E_CUDA; } } while (0)
 
 struct LocalTransport : Transport {
     std::shared_ptr<LocalBus> bus;
@@ -97,29 +107,30 @@ struct LocalTransport : Transport {
     int all_gather_inplace(void *recv, size_t bytes, cudaStream_t st) override {
         PGR_CUDA(cudaStreamSynchronize(st));           // own contribution is complete
         bus->send[rank] = (const uint8_t *)recv;
-        bus->barrier();
+        PGR_BUS_BARRIER(bus);
         for (int p = 0; p < n_ranks; p++) {
             if (p == rank) continue;
             PGR_CUDA(cudaMemcpyPeerAsync((uint8_t *)recv + (size_t)p * bytes, device, bus->send[p] + (size_t)p * bytes, bus->device[p], bytes, st));
         }
         PGR_CUDA(cudaStreamSynchronize(st));
-        bus->barrier();                                // nobody reuses its buffer before every peer has read it
+        PGR_BUS_BARRIER(bus);                          // nobody reuses its buffer before every peer has read it
         return PGR_OK;
     }
     int all_to_all(const uint8_t *send, const uint64_t *send_off, uint8_t *recv, const uint64_t *recv_off, cudaStream_t st) override {
         PGR_CUDA(cudaStreamSynchronize(st));
         bus->send[rank] = send;
         bus->send_off[rank] = send_off;
-        bus->barrier();
+        PGR_BUS_BARRIER(bus);
         for (int p = 0; p < n_ranks; p++) {
             const uint64_t rb = recv_off[p + 1] - recv_off[p];
             if (rb) PGR_CUDA(cudaMemcpyPeerAsync(recv + recv_off[p], device, bus->send[p] + bus->send_off[p][rank], bus->device[p], rb, st));
         }
         PGR_CUDA(cudaStreamSynchronize(st));
-        bus->barrier();
+        PGR_BUS_BARRIER(bus);
         return PGR_OK;
     }
     const char *name() const override { return "local-d2d"; }
+    void abort() override { bus->abort(); }
 };
 
 // ---- kernels of the merge -----------------------------------------------------------------------------------------
@@ -482,11 +493,19 @@ int for_each_shard(pgr_b200_mindex *m, F f) {
     for (int g = 0; g < m->n; g++)
         th.emplace_back([&, g] {
             rc[g] = f(g);
-            if (rc[g] != PGR_OK) err[g] = get_error();
+            if (rc[g] != PGR_OK) {
+                err[g] = get_error();
+                if (g < (int)m->comm.size() && m->comm[g]) m->comm[g]->tp->abort();   // peers waiting at a rendez-vous give up too
+            }
         });
     for (auto &t : th) t.join();
-    for (int g = 0; g < m->n; g++)
-        if (rc[g] != PGR_OK) { set_error("shard %d: %s", g, err[g].c_str()); return rc[g]; }
+    int first = -1;
+    for (int g = 0; g < m->n; g++) {   // report the shard that failed on its own, not one that gave up at a rendez-vous because of it
+        if (rc[g] == PGR_OK) continue;
+        if (first < 0) first = g;
+        if (err[g].rfind("another shard", 0) != 0) { first = g; break; }
+    }
+    if (first >= 0) { set_error("shard %d: %s", first, err[first].c_str()); return rc[first]; }
     return PGR_OK;
 }
 
